@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the BMA-predictive hot path (BASELINE.json config 4) on B200.
+
+One "step" = one pass of the predictive path over one batch of synthetic calibrated logits
+z[S=64, B=65536, C=1000] (float32, 16.8 GB, larger than L2):
+    fb200_bma_reduce_cls   -> mean, aleatoric/epistemic variance, entropy + split, log_prob, mode
+    fb200_aps_scores       -> adaptive-prediction-set scores for every class of the mean  [B,C]
+    fb200_conformal_sets   -> rank-count sets against 50 000 pre-sorted validation scores
+    fb200_ece_bins         -> ECE / MCE / accuracy / Brier of the mean
+`value` times that with z resident in HBM; `e2e` times the same work through the public
+`predictive_from_logits_batches` call with pinned HOST batches (H2D of every batch and D2H of every
+result inside the timed region).  `--impl reference` times the CPU oracle (numpy restatement of the
+reference's jnp path - JAX itself cannot be installed here) on a bounded sample with all host cores.
+
+Contract: python bench.py --gpus N --steps K --warmup W  (N > 1 under torchrun, one rank per GPU).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "posterior_predictive_SBC_elems_per_s"
+UNIT = "elems/s"
+S_FULL, B_FULL, C_FULL = 64, 65536, 1000
+N_VAL = 50_000
+ERROR = 0.05
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = (
+        "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    z, t, val_sorted, thr = args
+    from oracle import predictive as P
+    from oracle import scoring as Sc
+    import numpy as np
+
+    mean = P.cls_mean(z)
+    P.cls_aleatoric_variance(z)
+    P.cls_epistemic_variance(z)
+    P.cls_entropy(z)
+    P.cls_aleatoric_entropy(z)
+    P.cls_epistemic_entropy(z)
+    P.cls_log_prob(z, t)
+    P.cls_mode(z)
+    scores = Sc.aps_cumsums(mean)
+    counts = (len(val_sorted) - np.searchsorted(val_sorted, scores, side="right")).astype(np.float32)
+    (counts < thr).sum(1)
+    Sc.compute_counts_confs_accs(mean.argmax(-1), mean, t)
+    return z.size
+
+
+def cpu_reference_throughput(rows_per_core, steps, warmup, cores=None):
+    """Times the oracle (fair variant: no O(C^2) entropy loop) on [S, rows_per_core*cores, C] per step,
+    the batch split over `cores` forked workers.  Returns (elems/s, ms_per_step, cores, sample text)."""
+    import multiprocessing as mp
+
+    import numpy as np
+
+    from oracle import predictive as P
+    from oracle import scoring as Sc
+
+    cores = cores or os.cpu_count() or 1
+    r = np.random.default_rng(0)
+    shards = []
+    val = np.sort(Sc.aps_score(P.softmax((4 * r.standard_normal((2048, C_FULL))).astype(np.float32)), r.integers(0, C_FULL, 2048)))
+    thr = Sc.conformal_threshold(len(val), ERROR)
+    for _ in range(cores):
+        z = (4 * r.standard_normal((S_FULL, rows_per_core, C_FULL))).astype(np.float32)
+        t = r.integers(0, C_FULL, rows_per_core).astype(np.int32)
+        shards.append((z, t, val, thr))
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            done = pool.map(_cpu_worker, shards)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    elems = S_FULL * rows_per_core * cores * C_FULL
+    total = sum(times)
+    sample = f"oracle (numpy) on z[{S_FULL},{rows_per_core * cores},{C_FULL}] f32 per step, {cores} forked workers"
+    return elems * len(times) / total, 1e3 * total / len(times), cores, sample
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, ms, cores, sample = cpu_reference_throughput(args.cpu_rows_per_core, args.steps, args.warmup)
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": v,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "c4 predictive z[S=64,B,C=1000] -> BMA reductions + APS conformal sets + ECE (bounded CPU sample)",
+                   "S": S_FULL, "C": C_FULL},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference's jnp path (oracle/), not JAX: jax/flax/optax are not installable here",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+WANT = ("mean", "aleatoric_variance", "epistemic_variance", "entropy", "aleatoric_entropy", "epistemic_entropy",
+        "log_prob", "mode")
+
+
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.predictive import pipeline
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: fortuna_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, B, Cn = args.S, args.B, args.C
+    if B % world:
+        raise SystemExit("B must be divisible by the number of GPUs")
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    # synthetic calibrated logits 4*N(0,1): softmax neither flat nor one-hot; generated in slabs
+    z = torch.empty((S, B, Cn), dtype=torch.float32, device=dev)
+    for s in range(S):
+        z[s].normal_(0.0, 4.0, generator=gen)
+    gen.manual_seed(99)  # targets / validation scores identical on every rank
+    targets = torch.randint(0, Cn, (B,), device=dev, generator=gen, dtype=torch.int32)
+    val_logits = torch.empty((N_VAL, Cn), dtype=torch.float32, device=dev).normal_(0.0, 4.0, generator=gen)
+    val_targets = torch.randint(0, Cn, (N_VAL,), device=dev, generator=gen, dtype=torch.int32)
+    val_mean = ops.bma_reduce_cls(val_logits.unsqueeze(0).contiguous(), ("mean",))["mean"]
+    val_sorted = ops.sort_f32_(ops.aps_scores(val_mean, val_targets))
+    del val_logits, val_mean
+    calib = pipeline.ConformalCalibration(val_sorted, N_VAL, ERROR)
+
+    runner = pipeline.PredictivePipeline(S, B, Cn, dev, WANT, world=world, rank=rank)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (args.steps + 1))]
+
+    def one_step(i=None):
+        if i is not None:
+            ev[2 * i].record()
+        runner.reduce(z, targets)
+        if i is not None:
+            ev[2 * i + 1].record()
+        runner.score(targets, calib)
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        one_step(i)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_start.elapsed_time(t_end)
+    reduce_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
+    if world > 1:
+        tt = torch.tensor([total_ms, reduce_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, reduce_ms = float(tt[0]), float(tt[1])
+    ms_per_step = total_ms / args.steps
+    elems_per_step = float(S) * B * Cn * world  # every rank evaluates its own S samples (weak scaling in S)
+    value = elems_per_step / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel: algorithmic bytes per launch / measured launch time
+    n_bc_out = 3 if world == 1 else 3  # mean + two variance arrays (fused) or three partial-sum arrays
+    alg_bytes = 4.0 * S * B * Cn + 4.0 * n_bc_out * B * Cn + 4.0 * B * 6
+    peak, peak_src = _peaks()
+    achieved = alg_bytes / (reduce_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("bma_reduce_cls_kernel")
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": f"c4 predictive z[S={S},B={B},C={Cn}] f32 -> BMA reductions + APS conformal sets + ECE",
+            "S_per_gpu": S, "B": B, "C": Cn, "n_val": N_VAL, "error": ERROR,
+            "parallelism": "single GPU" if world == 1 else f"S-sharded x{world}: reduce-scatter of partial sums over B + all-gather of (max,sumexp)",
+            "l2": "inputs (16.8 GB) larger than L2; no flush needed",
+        },
+        "roofline": {
+            "bound": "hbm", "kernel": "bma_reduce_cls_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": reduce_ms,
+            "algorithmic_bytes_per_launch": alg_bytes,
+        },
+        "gpu_launches": runner.launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_e2e:
+        line["e2e"] = pipeline.bench_e2e(S, B, Cn, dev, WANT, calib, args, UNIT)
+    elif world > 1:
+        line["e2e"] = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            from fortuna_b200.bench_extras import sampler_extras
+
+            line["extras"] = sampler_extras(dev, peak)
+        except Exception as exc:  # extras never invalidate the headline
+            line["extras"] = {"error": repr(exc)}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, ms, cores, sample = cpu_reference_throughput(args.cpu_rows_per_core, 1, 0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--S", type=int, default=S_FULL)
+    ap.add_argument("--B", type=int, default=B_FULL)
+    ap.add_argument("--C", type=int, default=C_FULL)
+    ap.add_argument("--cpu-rows-per-core", type=int, default=64)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-batch", type=int, default=4096)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

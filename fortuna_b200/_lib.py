@@ -1,0 +1,155 @@
+"""ctypes binding of libfortuna_b200.so (the C ABI in include/fortuna_b200.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  Importing this module never builds
+or loads anything; the first call to :func:`lib` loads the shared object and raises
+``FortunaB200LibraryError`` if it is missing (run ``python -m fortuna_b200.build`` or
+``__graft_entry__.build()``).
+"""
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfortuna_b200.so")
+
+F32, BF16 = 0, 1
+W_SDC, W_SCD = 0, 1
+TILE_PAIRS = 1024
+
+
+class FortunaB200LibraryError(RuntimeError):
+    pass
+
+
+class FortunaB200Error(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        super().__init__(f"{where} failed with code {code}: {error_string(code)}")
+
+
+class Leaf(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("len", C.c_int64)]
+
+
+class Tile(C.Structure):
+    _fields_ = [("leaf", C.c_int32), ("pair_start", C.c_uint32)]
+
+
+class SgmcmcHParams(C.Structure):
+    _fields_ = [
+        ("step_size", C.c_float),
+        ("momentum_decay", C.c_double),
+        ("zero_momentum", C.c_int32),
+        ("rmsprop", C.c_int32),
+        ("rms_alpha", C.c_double),
+        ("rms_eps", C.c_double),
+    ]
+
+
+_P = C.c_void_p
+
+
+class ClsOutputs(C.Structure):
+    _fields_ = [
+        (n, _P)
+        for n in (
+            "mean",
+            "aleatoric_variance",
+            "epistemic_variance",
+            "variance",
+            "std",
+            "mode",
+            "entropy",
+            "aleatoric_entropy",
+            "epistemic_entropy",
+            "log_prob",
+            "ensemble_log_prob",
+        )
+    ]
+
+
+class ClsPartials(C.Structure):
+    _fields_ = [(n, _P) for n in ("sum_p", "sum_p2", "sum_pq", "sum_plogp", "ll_max", "ll_sumexp")]
+
+
+class RegOutputs(C.Structure):
+    _fields_ = [
+        (n, _P)
+        for n in (
+            "mean",
+            "aleatoric_variance",
+            "epistemic_variance",
+            "variance",
+            "std",
+            "log_prob",
+            "ensemble_log_prob",
+        )
+    ]
+
+
+_i, _i64, _u32, _f, _sz = C.c_int, C.c_int64, C.c_uint32, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/fortuna_b200.h one to one
+SIGNATURES = {
+    "fb200_abi_version": (_i, []),
+    "fb200_error_string": (C.c_char_p, [_i]),
+    "fb200_threefry_split": (_i, [_P, _i, _P, _P]),
+    "fb200_threefry_fold_in": (_i, [_P, _u32, _P, _P]),
+    "fb200_random_bits": (_i, [_P, _i64, _P, _P]),
+    "fb200_random_normal": (_i, [_P, _i64, _P, _P]),
+    "fb200_sample_indices": (_i, [_P, _i, _i, _P, _P]),
+    "fb200_sgmcmc_num_tiles_host": (_i64, [C.POINTER(Leaf), _i]),
+    "fb200_sgmcmc_build_tiles_host": (_i, [C.POINTER(Leaf), _i, C.POINTER(Tile), _i64]),
+    "fb200_sgmcmc_step_f32": (
+        _i,
+        [_P, _P, _P, _P, _P, _i64, _P, _i, _P, _i64, _P, _P, _P, C.POINTER(SgmcmcHParams), _P],
+    ),
+    "fb200_sgd_explore_step_f32": (_i, [_P, _P, _P, _P, _i64, C.POINTER(SgmcmcHParams), _P]),
+    "fb200_bank_put_f32": (_i, [_P, _i64, _i, _P, _P]),
+    "fb200_last_layer_logits": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
+    "fb200_transpose_w_bf16": (_i, [_P, _i, _P, _i, _i, _i, _P]),
+    "fb200_bma_reduce_cls": (
+        _i,
+        [_P, _i, _P, _P, _i, _i, _i, C.POINTER(ClsOutputs), C.POINTER(ClsPartials), _P],
+    ),
+    "fb200_bma_finalize_cls": (_i, [C.POINTER(ClsPartials), _i, _i, _i, C.POINTER(ClsOutputs), _P]),
+    "fb200_merge_lse_pairs": (_i, [_P, _P, _i, _i, _P, _P, _P]),
+    "fb200_bma_reduce_reg": (_i, [_P, _P, _P, _i, _i, _i, C.POINTER(RegOutputs), _P]),
+    "fb200_aps_scores": (_i, [_P, _P, _i, _i, _P, _P, _P]),
+    "fb200_simple_scores": (_i, [_P, _P, _i, _i, _P, _P]),
+    "fb200_credible_sets": (_i, [_P, _i, _i, _f, _P, _P, _P]),
+    "fb200_sort_workspace_bytes": (_sz, [_i64]),
+    "fb200_sort_f32": (_i, [_P, _i64, _P, _sz, _P]),
+    "fb200_conformal_sets": (_i, [_P, _i, _P, _i, _i, _f, _P, _P, _P]),
+    "fb200_ece_bins": (_i, [_P, _i, _i, _P, _P, _P, _i, _P, _P, _P, _P, _P, _P]),
+    "fb200_quantile_sorted": (_i, [_P, _i64, _P, _i, _P, _P]),
+}
+
+_LIB = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the CUDA library has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FortunaB200LibraryError(
+                f"{LIB_PATH} is missing. fortuna_b200 has no CPU fallback: build the CUDA library with "
+                "`python -m fortuna_b200.build` (needs nvcc) before using it."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+def error_string(code):
+    return lib().fb200_error_string(int(code)).decode()
+
+
+def check(code, where):
+    if code != 0:
+        raise FortunaB200Error(code, where)

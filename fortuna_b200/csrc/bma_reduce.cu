@@ -1,0 +1,634 @@
+// K3 + K4: single-pass Bayesian-model-averaging reductions over calibrated logits z[S,B,C].
+//
+// Replaces (reference file:line)
+//   fortuna/prob_model/predictive/base.py:624-647   _batched_mean            sum_s softmax / S
+//   fortuna/prob_model/predictive/base.py:735-758   _batched_aleatoric_variance   sum_s p(1-p) / S
+//   fortuna/prob_model/predictive/base.py:806-836   _batched_epistemic_variance   max(0, E p^2 - (E p)^2)
+//   fortuna/prob_model/predictive/base.py:179-203, 104-128   log_prob / ensemble_log_prob
+//   fortuna/prob_model/predictive/classification.py:71-86, 257-432   mode, (aleatoric|epistemic) entropy
+//   fortuna/prob_output_layer/classification.py:25-28, 54-69, 88-104  per-sample maps
+//   fortuna/output_calibrator/classification.py:14-17                  z = logits * exp(-log_temp)
+//
+// Data movement: logits are read from HBM exactly once.  A CTA owns a tile of TB consecutive inputs b and
+// walks the S samples; for each s the TB rows z[s, b0:b0+TB, :] are one contiguous block, fetched by a
+// producer warp with cp.async.bulk (TMA engine) into an mbarrier-signalled shared-memory ring.  Eight
+// consumer warps each own whole rows (G lanes per row), so the per-row max / sum-exp are warp-shuffle
+// reductions and the per-(b,c) sums over s live in registers until the tile's single store.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "async_copy.cuh"
+#include "common.cuh"
+
+namespace fb200 {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kReduceThreads = (kConsumerWarps + 1) * 32;
+constexpr int kMaxStages = 8;
+
+struct ClsArgs {
+  const void* logits;
+  const float* log_temp;
+  const int32_t* targets;
+  int S, B, C;
+  fb200_cls_outputs_t out;
+  fb200_cls_partials_t part;
+  int partial_mode;
+  int n_tiles;
+  int n_stages;
+  int ss;                      // samples per pipeline stage
+  uint32_t tile_stride_bytes;  // bytes between consecutive samples inside a stage (multiple of 16)
+  uint32_t stage_bytes;        // multiple of 128
+  int bulk_ok;                 // base pointer and sample stride are 16-byte aligned
+  float log_S;                 // float32 log(S)
+};
+
+template <typename T, int VEC>
+struct RowLoad;
+template <>
+struct RowLoad<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&z)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w;
+  }
+};
+template <>
+struct RowLoad<float, 1> {
+  static __device__ __forceinline__ void load(const float* p, float (&z)[1]) { z[0] = *p; }
+};
+template <>
+struct RowLoad<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&z)[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    z[0] = __uint_as_float(v.x << 16);
+    z[1] = __uint_as_float(v.x & 0xFFFF0000u);
+    z[2] = __uint_as_float(v.y << 16);
+    z[3] = __uint_as_float(v.y & 0xFFFF0000u);
+  }
+};
+template <>
+struct RowLoad<__nv_bfloat16, 1> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&z)[1]) { z[0] = __bfloat162float(*p); }
+};
+
+// Per-row finalisation shared by the fused kernel and the partial-sum finaliser.
+struct RowFinal {
+  float ent_terms;  // sum_c mean log mean over this lane's classes
+  float best_v;
+  int best_c;
+};
+
+template <typename T, int G, int NV, int VEC>
+__global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const ClsArgs a) {
+  constexpr int R = 32 / G;                 // rows per warp
+  constexpr int TB = kConsumerWarps * R;    // rows per tile
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  unsigned char* stages = smem_raw + 128;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = a.S, B = a.B, C = a.C;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.n_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kConsumerWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int n_chunks = (S + a.ss - 1) / a.ss;  // pipeline steps per tile
+
+  if (warp == kConsumerWarps) {
+    // ------------------------------------------------------------------ producer warp
+    const T* base = reinterpret_cast<const T*>(a.logits);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int b0 = tile * TB;
+      const int rows = min(TB, B - b0);
+      const uint32_t bytes = (uint32_t)rows * (uint32_t)C * (uint32_t)sizeof(T);
+      const bool bulk = a.bulk_ok && ((bytes & 15u) == 0);
+      for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+        const int stage = it % a.n_stages;
+        const uint32_t round = it / a.n_stages;
+        if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1u);
+        const int s0 = ch * a.ss;
+        const int ns = min(a.ss, S - s0);
+        unsigned char* dst = stages + (size_t)stage * a.stage_bytes;
+        if (bulk) {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full_bar[stage], bytes * (uint32_t)ns);
+            for (int q = 0; q < ns; ++q) {
+              const T* src = base + ((size_t)(s0 + q) * B + b0) * C;
+              bulk_g2s(dst + (size_t)q * a.tile_stride_bytes, src, bytes, &full_bar[stage]);
+            }
+          }
+        } else {
+          // ragged tail tile or unaligned tensor: the producer warp copies element-wise
+          const int n_el = rows * C;
+          for (int q = 0; q < ns; ++q) {
+            const T* src = base + ((size_t)(s0 + q) * B + b0) * C;
+            T* d = reinterpret_cast<T*>(dst + (size_t)q * a.tile_stride_bytes);
+            for (int i = lane; i < n_el; i += 32) d[i] = src[i];
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[stage]);
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer warps
+  const int gr = lane / G;
+  const int g = lane % G;
+  const int row = warp * R + gr;
+  const float scale = a.log_temp ? expf(-a.log_temp[0]) : 1.0f;
+  const bool has_temp = a.log_temp != nullptr;
+
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int b = tile * TB + row;
+    const bool valid_row = b < B;
+    float sp[NV][VEC], sp2[NV][VEC], spq[NV][VEC];
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) sp[j][k] = sp2[j][k] = spq[j][k] = 0.0f;
+    float spl = 0.0f, sum_l = 0.0f;
+    float lmax = -CUDART_INF_F, lsum = 0.0f;
+    int y = -1;
+    if (a.targets && valid_row) y = a.targets[b];
+    const bool y_ok = (y >= 0) && (y < C);
+
+    for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+      const int stage = it % a.n_stages;
+      const uint32_t round = it / a.n_stages;
+      mbar_wait(&full_bar[stage], round & 1u);
+      const int s0 = ch * a.ss;
+      const int ns = min(a.ss, S - s0);
+      const unsigned char* sbase = stages + (size_t)stage * a.stage_bytes;
+      for (int q = 0; q < ns; ++q) {
+        const T* rowp = reinterpret_cast<const T*>(sbase + (size_t)q * a.tile_stride_bytes) + (size_t)row * C;
+        float z[NV][VEC];
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c0 = (g + G * j) * VEC;
+          if (c0 < C) {
+            RowLoad<T, VEC>::load(rowp + c0, z[j]);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              if (has_temp) z[j][k] *= scale;
+              m = fmaxf(m, z[j][k]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) z[j][k] = -CUDART_INF_F;
+          }
+        }
+        m = group_max<G>(m);
+        // jsp.special.logsumexp replaces a non-finite max by 0
+        const float ms = (fabsf(m) <= 3.4028234e38f) ? m : 0.0f;
+        // pass B: e = exp(z - max) (kept in z's registers), row sum, and sum_c e * (z - max) for the
+        // entropy term: sum_c p log p = (sum_c e t) / sum - log(sum), t = z - max  (no second exp, no z reload)
+        float psum[VEC], pset[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) psum[k] = pset[k] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c0 = (g + G * j) * VEC;
+          if (c0 < C) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              const float t = z[j][k] - ms;
+              const float ev = __expf(t);
+              z[j][k] = ev;
+              psum[k] += ev;
+              pset[k] = fmaf(ev, t, pset[k]);  // 0 * -inf = NaN for a -inf logit, like the reference
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) z[j][k] = 0.0f;
+          }
+        }
+        float sum = psum[0], set = pset[0];
+#pragma unroll
+        for (int k = 1; k < VEC; ++k) {
+          sum += psum[k];
+          set += pset[k];
+        }
+        sum = group_sum<G>(sum);
+        const float inv = 1.0f / sum;
+        const float lsum_row = __logf(sum);
+        const float lse = ms + lsum_row;
+        spl = fmaf(inv, set, spl);  // lane-partial of sum_c p t; the -log(sum) part is row-uniform
+        sum_l += lsum_row;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float p = z[j][k] * inv;
+            sp[j][k] += p;
+            sp2[j][k] = fmaf(p, p, sp2[j][k]);
+            spq[j][k] = fmaf(p, 1.0f - p, spq[j][k]);
+          }
+        }
+        if (a.targets) {
+          float zt = 0.0f;
+          if (y_ok) {
+            float tmp[1];
+            RowLoad<T, 1>::load(rowp + y, tmp);
+            zt = has_temp ? tmp[0] * scale : tmp[0];
+          }
+          const float ll = zt - lse;
+          if (ll > lmax) {
+            lsum = lsum * __expf(lmax - ll) + 1.0f;
+            lmax = ll;
+          } else if (ll > -CUDART_INF_F) {
+            lsum += __expf(ll - lmax);
+          } else if (ll != ll) {
+            lsum = ll;  // NaN propagates like the reference's logsumexp
+          }
+          if (a.out.ensemble_log_prob && valid_row && g == 0)
+            a.out.ensemble_log_prob[(size_t)(s0 + q) * B + b] = ll;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+
+    // ------------------------------------------------------------------ tile epilogue
+    const float Sf = (float)S;
+    const float spl_row = group_sum<G>(spl) - sum_l;  // sum_s sum_c p log p for this row
+    if (a.partial_mode) {
+      if (valid_row) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c0 = (g + G * j) * VEC;
+          if (c0 < C) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              const size_t o = (size_t)b * C + c0 + k;
+              a.part.sum_p[o] = sp[j][k];
+              a.part.sum_p2[o] = sp2[j][k];
+              a.part.sum_pq[o] = spq[j][k];
+            }
+          }
+        }
+        if (g == 0) {
+          a.part.sum_plogp[b] = spl_row;
+          a.part.ll_max[b] = lmax;
+          a.part.ll_sumexp[b] = lsum;
+        }
+      }
+      continue;
+    }
+
+    float ent_terms = 0.0f;
+    float best_v = -CUDART_INF_F;
+    int best_c = 0x7FFFFFFF;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c0 = (g + G * j) * VEC;
+      if (c0 < C) {
+        float mean[VEC], av[VEC], ev[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          mean[k] = sp[j][k] / Sf;
+          av[k] = spq[j][k] / Sf;
+          ev[k] = fmaxf(0.0f, __fsub_rn(sp2[j][k] / Sf, __fmul_rn(mean[k], mean[k])));
+          if (mean[k] > 0.0f) ent_terms = fmaf(mean[k], logf(mean[k]), ent_terms);
+          if (mean[k] > best_v) {
+            best_v = mean[k];
+            best_c = c0 + k;
+          }
+        }
+        if (valid_row) {
+          const size_t o = (size_t)b * C + c0;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            if (a.out.mean) a.out.mean[o + k] = mean[k];
+            if (a.out.aleatoric_variance) a.out.aleatoric_variance[o + k] = av[k];
+            if (a.out.epistemic_variance) a.out.epistemic_variance[o + k] = ev[k];
+            if (a.out.variance) a.out.variance[o + k] = av[k] + ev[k];
+            if (a.out.std) a.out.std[o + k] = sqrtf(av[k] + ev[k]);
+          }
+        }
+      }
+    }
+    const float ent = -group_sum<G>(ent_terms);
+    const float alea = -spl_row / Sf;
+    // argmax with first-maximum tie-break across the G lanes of the row
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+      if (ov > best_v || (ov == best_v && oc < best_c)) {
+        best_v = ov;
+        best_c = oc;
+      }
+    }
+    if (valid_row && g == 0) {
+      if (a.out.entropy) a.out.entropy[b] = ent;
+      if (a.out.aleatoric_entropy) a.out.aleatoric_entropy[b] = alea;
+      if (a.out.epistemic_entropy) a.out.epistemic_entropy[b] = ent - alea;
+      if (a.out.mode) a.out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
+      if (a.out.log_prob) a.out.log_prob[b] = (lmax + logf(lsum)) - a.log_S;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Finalise from (all-reduced) partial sums: one warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bma_finalize_cls_kernel(const fb200_cls_partials_t part, int s_total, int B,
+                                                               int C, const fb200_cls_outputs_t out, float log_S) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const int b = warp;
+  const float Sf = (float)s_total;
+  float ent_terms = 0.0f;
+  float best_v = -CUDART_INF_F;
+  int best_c = 0x7FFFFFFF;
+  for (int c = lane; c < C; c += 32) {
+    const size_t o = (size_t)b * C + c;
+    const float mean = part.sum_p[o] / Sf;
+    const float av = part.sum_pq[o] / Sf;
+    const float ev = fmaxf(0.0f, __fsub_rn(part.sum_p2[o] / Sf, __fmul_rn(mean, mean)));
+    if (mean > 0.0f) ent_terms = fmaf(mean, logf(mean), ent_terms);
+    if (mean > best_v) {
+      best_v = mean;
+      best_c = c;
+    }
+    if (out.mean) out.mean[o] = mean;
+    if (out.aleatoric_variance) out.aleatoric_variance[o] = av;
+    if (out.epistemic_variance) out.epistemic_variance[o] = ev;
+    if (out.variance) out.variance[o] = av + ev;
+    if (out.std) out.std[o] = sqrtf(av + ev);
+  }
+  const float ent = -group_sum<32>(ent_terms);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ov > best_v || (ov == best_v && oc < best_c)) {
+      best_v = ov;
+      best_c = oc;
+    }
+  }
+  if (lane == 0) {
+    const float alea = -part.sum_plogp[b] / Sf;
+    if (out.entropy) out.entropy[b] = ent;
+    if (out.aleatoric_entropy) out.aleatoric_entropy[b] = alea;
+    if (out.epistemic_entropy) out.epistemic_entropy[b] = ent - alea;
+    if (out.mode) out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
+    if (out.log_prob) out.log_prob[b] = (part.ll_max[b] + logf(part.ll_sumexp[b])) - log_S;
+  }
+}
+
+__global__ void __launch_bounds__(256) merge_lse_pairs_kernel(const float* __restrict__ max_in,
+                                                              const float* __restrict__ sum_in, int R, int B,
+                                                              float* __restrict__ max_out,
+                                                              float* __restrict__ sum_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float M = -CUDART_INF_F;
+  for (int r = 0; r < R; ++r) M = fmaxf(M, max_in[(size_t)r * B + b]);
+  float s = 0.0f;
+  for (int r = 0; r < R; ++r) {
+    const float mr = max_in[(size_t)r * B + b];
+    const float sr = sum_in[(size_t)r * B + b];
+    if (mr > -CUDART_INF_F) s += sr * __expf(mr - M);
+    else if (sr != sr) s = sr;
+  }
+  max_out[b] = M;
+  sum_out[b] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Regression maps: z[S,B,2d] = [mu, log var]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bma_reduce_reg_moments_kernel(const float* __restrict__ z,
+                                                                     const float* __restrict__ log_temp, int S,
+                                                                     int B, int d, const fb200_reg_outputs_t out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j)
+  if (i >= (int64_t)B * d) return;
+  const int b = (int)(i / d), j = (int)(i % d);
+  const float lt = log_temp ? log_temp[0] : 0.0f;
+  float smu = 0.f, smu2 = 0.f, sv = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float* r = z + ((size_t)s * B + b) * (2 * d);
+    const float mu = r[j];
+    float lv = r[d + j];
+    if (log_temp) lv += lt;
+    smu += mu;
+    smu2 = fmaf(mu, mu, smu2);
+    sv += expf(lv);
+  }
+  const float Sf = (float)S;
+  const float mean = smu / Sf;
+  const float av = sv / Sf;
+  const float ev = fmaxf(0.0f, __fsub_rn(smu2 / Sf, __fmul_rn(mean, mean)));
+  if (out.mean) out.mean[i] = mean;
+  if (out.aleatoric_variance) out.aleatoric_variance[i] = av;
+  if (out.epistemic_variance) out.epistemic_variance[i] = ev;
+  if (out.variance) out.variance[i] = av + ev;
+  if (out.std) out.std[i] = sqrtf(av + ev);
+}
+
+__global__ void __launch_bounds__(256) bma_reduce_reg_logprob_kernel(const float* __restrict__ z,
+                                                                     const float* __restrict__ log_temp,
+                                                                     const float* __restrict__ targets, int S,
+                                                                     int B, int d, const fb200_reg_outputs_t out,
+                                                                     float log_S) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float lt = log_temp ? log_temp[0] : 0.0f;
+  const float log2pi = 1.8378770664093453f;
+  float lmax = -CUDART_INF_F, lsum = 0.0f;
+  for (int s = 0; s < S; ++s) {
+    const float* r = z + ((size_t)s * B + b) * (2 * d);
+    float acc = 0.0f;
+    for (int j = 0; j < d; ++j) {
+      const float mu = r[j];
+      float lv = r[d + j];
+      if (log_temp) lv += lt;
+      const float diff = targets[(size_t)b * d + j] - mu;
+      acc += expf(-lv) * (diff * diff) + lv + log2pi;
+    }
+    const float ll = -0.5f * acc;
+    if (out.ensemble_log_prob) out.ensemble_log_prob[(size_t)s * B + b] = ll;
+    if (ll > lmax) {
+      lsum = lsum * __expf(lmax - ll) + 1.0f;
+      lmax = ll;
+    } else if (ll > -CUDART_INF_F) {
+      lsum += __expf(ll - lmax);
+    } else if (ll != ll) {
+      lsum = ll;
+    }
+  }
+  if (out.log_prob) out.log_prob[b] = (lmax + logf(lsum)) - log_S;
+}
+
+static int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+template <typename T, int G, int NV, int VEC>
+static int launch_cls(ClsArgs a, cudaStream_t st) {
+  constexpr int R = 32 / G;
+  constexpr int TB = kConsumerWarps * R;
+  const uint32_t tile_bytes = (uint32_t)TB * (uint32_t)a.C * (uint32_t)sizeof(T);
+  a.tile_stride_bytes = (tile_bytes + 15u) & ~15u;
+  // aim for >= 16 KB per stage so a handful of stages covers the HBM latency-bandwidth product
+  int ss = (int)(16384u / a.tile_stride_bytes);
+  if (ss < 1) ss = 1;
+  if (ss > 16) ss = 16;
+  if (ss > a.S) ss = a.S;
+  a.ss = ss;
+  a.stage_bytes = ((uint32_t)ss * a.tile_stride_bytes + 127u) & ~127u;
+  const uint32_t budget = 96u * 1024u;
+  int nst = (int)(budget / a.stage_bytes);
+  if (nst > kMaxStages) nst = kMaxStages;
+  if (nst < 2) nst = 2;
+  a.n_stages = nst;
+  a.n_tiles = (a.B + TB - 1) / TB;
+  const size_t smem = 128 + (size_t)nst * a.stage_bytes;
+  auto kern = bma_reduce_cls_kernel<T, G, NV, VEC>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int occ = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kReduceThreads, smem);
+  if (e != cudaSuccess) return (int)e;
+  if (occ < 1) occ = 1;
+  int grid = sm_count() * occ;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  kern<<<grid, kReduceThreads, smem, st>>>(a);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int dispatch_cls(const ClsArgs& a, cudaStream_t st) {
+  const int C = a.C;
+  const int vec = (C % 4 == 0) ? 4 : 1;
+  const int chunks = C / vec;
+#define FB200_CASE(G_, NV_, VEC_) return launch_cls<T, G_, NV_, VEC_>(a, st)
+  if (vec == 4) {
+    if (chunks <= 1) FB200_CASE(1, 1, 4);
+    if (chunks <= 2) FB200_CASE(2, 1, 4);
+    if (chunks <= 4) FB200_CASE(4, 1, 4);
+    if (chunks <= 8) FB200_CASE(8, 1, 4);
+    if (chunks <= 16) FB200_CASE(16, 1, 4);
+    if (chunks <= 32) FB200_CASE(32, 1, 4);
+    if (chunks <= 64) FB200_CASE(32, 2, 4);
+    if (chunks <= 128) FB200_CASE(32, 4, 4);
+    if (chunks <= 256) FB200_CASE(32, 8, 4);
+  } else {
+    if (chunks <= 1) FB200_CASE(1, 1, 1);
+    if (chunks <= 2) FB200_CASE(2, 1, 1);
+    if (chunks <= 4) FB200_CASE(4, 1, 1);
+    if (chunks <= 8) FB200_CASE(8, 1, 1);
+    if (chunks <= 16) FB200_CASE(16, 1, 1);
+    if (chunks <= 32) FB200_CASE(32, 1, 1);
+    if (chunks <= 64) FB200_CASE(32, 2, 1);
+    if (chunks <= 128) FB200_CASE(32, 4, 1);
+    if (chunks <= 256) FB200_CASE(32, 8, 1);
+    if (chunks <= 512) FB200_CASE(32, 16, 1);
+    if (chunks <= 1024) FB200_CASE(32, 32, 1);
+  }
+#undef FB200_CASE
+  return FB200_E_UNSUPPORTED;
+}
+
+}  // namespace fb200
+
+using namespace fb200;
+
+extern "C" int fb200_bma_reduce_cls(const void* logits, int dtype, const float* log_temp, const int32_t* targets,
+                                    int S, int B, int C, const fb200_cls_outputs_t* out,
+                                    const fb200_cls_partials_t* partials, void* stream) {
+  if (!logits) return FB200_E_NULL;
+  if ((out == nullptr) == (partials == nullptr)) return FB200_E_NULL;
+  if (S <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
+  if (C > 1024) return FB200_E_UNSUPPORTED;
+  if (dtype != FB200_F32 && dtype != FB200_BF16) return FB200_E_UNSUPPORTED;
+  ClsArgs a{};
+  a.logits = logits;
+  a.log_temp = log_temp;
+  a.targets = targets;
+  a.S = S;
+  a.B = B;
+  a.C = C;
+  if (out) {
+    a.out = *out;
+    if ((a.out.log_prob || a.out.ensemble_log_prob) && !targets) return FB200_E_NULL;
+  } else {
+    a.part = *partials;
+    a.partial_mode = 1;
+    if (!a.part.sum_p || !a.part.sum_p2 || !a.part.sum_pq || !a.part.sum_plogp || !a.part.ll_max ||
+        !a.part.ll_sumexp)
+      return FB200_E_NULL;
+  }
+  a.log_S = logf((float)S);
+  const size_t esz = dtype == FB200_F32 ? 4 : 2;
+  a.bulk_ok = fb200_aligned16(logits) && (((size_t)B * (size_t)C * esz) % 16 == 0);
+  if (dtype == FB200_F32) return dispatch_cls<float>(a, (cudaStream_t)stream);
+  return dispatch_cls<__nv_bfloat16>(a, (cudaStream_t)stream);
+}
+
+extern "C" int fb200_bma_finalize_cls(const fb200_cls_partials_t* partials, int s_total, int B, int C,
+                                      const fb200_cls_outputs_t* out, void* stream) {
+  if (!partials || !out) return FB200_E_NULL;
+  if (!partials->sum_p || !partials->sum_p2 || !partials->sum_pq || !partials->sum_plogp) return FB200_E_NULL;
+  if (out->log_prob && (!partials->ll_max || !partials->ll_sumexp)) return FB200_E_NULL;
+  if (out->ensemble_log_prob) return FB200_E_UNSUPPORTED;
+  if (s_total <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
+  const int64_t threads = (int64_t)B * 32;
+  bma_finalize_cls_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      *partials, s_total, B, C, *out, logf((float)s_total));
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_merge_lse_pairs(const float* max_in, const float* sumexp_in, int R, int B, float* max_out,
+                                     float* sumexp_out, void* stream) {
+  if (!max_in || !sumexp_in || !max_out || !sumexp_out) return FB200_E_NULL;
+  if (R <= 0 || B <= 0) return FB200_E_SHAPE;
+  merge_lse_pairs_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(max_in, sumexp_in, R, B, max_out,
+                                                                            sumexp_out);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_bma_reduce_reg(const float* outputs, const float* log_temp, const float* targets, int S,
+                                    int B, int d, const fb200_reg_outputs_t* out, void* stream) {
+  if (!outputs || !out) return FB200_E_NULL;
+  if (S <= 0 || B <= 0 || d <= 0) return FB200_E_SHAPE;
+  if ((out->log_prob || out->ensemble_log_prob) && !targets) return FB200_E_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out->mean || out->aleatoric_variance || out->epistemic_variance || out->variance || out->std) {
+    const int64_t n = (int64_t)B * d;
+    bma_reduce_reg_moments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(outputs, log_temp, S, B, d, *out);
+    FB200_LAUNCH_CHECK();
+  }
+  if (out->log_prob || out->ensemble_log_prob) {
+    bma_reduce_reg_logprob_kernel<<<(B + 255) / 256, 256, 0, st>>>(outputs, log_temp, targets, S, B, d, *out,
+                                                                   logf((float)S));
+    FB200_LAUNCH_CHECK();
+  }
+  return 0;
+}

@@ -1,0 +1,335 @@
+// K1: fused SG-MCMC sampler step over the flattened parameter pytree.
+//
+// Replaces (reference file:line)
+//   fortuna/prob_model/posterior/sgmcmc/sghmc/sghmc_integrator.py:59-92     update_fn
+//   fortuna/prob_model/posterior/sgmcmc/sgmcmc_preconditioner.py:65-93      RMSprop / identity
+//   fortuna/utils/random.py:11-23                                           per-leaf N(0,1) tree
+//   fortuna/prob_model/posterior/sgmcmc/cyclical_sgld/cyclical_sgld_integrator.py:64-100
+//   flax TrainState.apply_gradients -> optax.apply_updates (fortuna/training/trainer.py:170)
+//
+// One launch reads theta, g, m (and v) once and writes theta, m (and v) once: 20 B/param (identity),
+// 28 B/param (RMSprop).  The noise never touches HBM: each thread evaluates the threefry2x32 block
+// of counter pair (i, i + h) of its leaf, whose two outputs are jax's normal() draws for elements i
+// and i + h of that leaf (h = ceil(len/2)), so a thread updates two 16-byte vectors, one in each half.
+#include "common.cuh"
+
+namespace fb200 {
+
+// ------------------------------------------------------------------------------------------------
+// key schedule: (key, new_key) = split(key_in); leaf_keys = split(key, n_leaves); key_out = new_key
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) sgmcmc_keys_kernel(const uint32_t* __restrict__ key_in,
+                                                          uint32_t* __restrict__ key_out,
+                                                          uint32_t* __restrict__ leaf_keys, uint32_t n_leaves) {
+  const uint32_t k0 = key_in[0], k1 = key_in[1];
+  // split(key_in) = random_bits(key_in, 4).reshape(2,2): blocks (0,2) and (1,3)
+  uint32_t a0 = 0u, a1 = 2u, b0 = 1u, b1 = 3u;
+  threefry2x32(k0, k1, a0, a1);
+  threefry2x32(k0, k1, b0, b1);
+  // key = (a0, b0) drives the noise; new_key = (a1, b1) is stored
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l == 0) {
+    key_out[0] = a1;
+    key_out[1] = b1;
+  }
+  if (l < n_leaves) {
+    leaf_keys[2 * l] = random_bits_elem(a0, b0, 2u * n_leaves, 2u * l);
+    leaf_keys[2 * l + 1] = random_bits_elem(a0, b0, 2u * n_leaves, 2u * l + 1u);
+  }
+}
+
+struct StepCoef {
+  float sqrt_eps;     // sqrt(float32(step_size))
+  float beta;         // float32(momentum_decay)
+  float noise_scale;  // sqrt(float32(2 * (1 - momentum_decay)))
+  float alpha;        // float32(running_average_factor)
+  float one_m_alpha;  // float32(1 - running_average_factor)
+  float rms_eps;      // float32(eps)
+  float step_size;    // float32 epsilon_t (exploration phase)
+  int zero_momentum;
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One parameter: returns the update u; m and v are updated in place (registers).
+template <bool RMS>
+__device__ __forceinline__ float sghmc_elem(float g, float& m, float& v, uint32_t bits, const StepCoef& c) {
+  float n = bits_to_normal(bits);
+  float denom = 1.0f;
+  if (RMS) {
+    v = v * c.alpha + (g * g) * c.one_m_alpha;  // sgmcmc_preconditioner.py:67-68
+    const float s = sqrt_approx(v);
+    denom = c.rms_eps + s;                      // :76
+    n = n * sqrt_approx(denom);                 // :83  multiply_by_m_sqrt
+  }
+  const float m_old = c.zero_momentum ? 0.0f : m;
+  m = c.beta * m_old + g * c.sqrt_eps + n * c.noise_scale;  // sghmc_integrator.py:77-84
+  float u = m;
+  if (RMS) u = __fdividef(u, denom);                        // :85  multiply_by_m_inv
+  return u * c.sqrt_eps;                                    // :86
+}
+
+template <bool RMS>
+__global__ void __launch_bounds__(256)
+    sgmcmc_step_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ mom,
+                       float* __restrict__ pv, float* __restrict__ upd, const fb200_leaf_t* __restrict__ leaves,
+                       const uint2* __restrict__ leaf_keys, const fb200_tile_t* __restrict__ tiles,
+                       const StepCoef c) {
+  const fb200_tile_t tile = tiles[blockIdx.x];
+  const fb200_leaf_t leaf = leaves[tile.leaf];
+  const uint2 key = leaf_keys[tile.leaf];
+  const uint32_t n = (uint32_t)leaf.len;
+  const uint32_t h = (n >> 1) + (n & 1u);
+  const uint32_t i0 = tile.pair_start + threadIdx.x * 4u;
+  if (i0 >= h) return;
+  const int64_t e0 = leaf.offset + i0;      // first-half elements e0 .. e0+3
+  const int64_t e1 = leaf.offset + h + i0;  // second-half elements e1 .. e1+3
+
+  uint32_t r0[4], r1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t i = i0 + k;
+    r0[k] = i;
+    r1[k] = (i + h < n) ? i + h : 0u;  // odd-size pad counter is 0
+    threefry2x32(key.x, key.y, r0[k], r1[k]);
+  }
+
+  const bool vec = ((leaf.offset & 3) == 0) && ((h & 3u) == 0) && ((uint64_t)i0 + h + 3u < (uint64_t)n);
+  if (vec) {
+    const float4 g0 = *reinterpret_cast<const float4*>(grad + e0);
+    const float4 g1 = *reinterpret_cast<const float4*>(grad + e1);
+    float4 m0 = *reinterpret_cast<const float4*>(mom + e0);
+    float4 m1 = *reinterpret_cast<const float4*>(mom + e1);
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (RMS) {
+      v0 = *reinterpret_cast<const float4*>(pv + e0);
+      v1 = *reinterpret_cast<const float4*>(pv + e1);
+    }
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+    if (params) {
+      p0 = *reinterpret_cast<const float4*>(params + e0);
+      p1 = *reinterpret_cast<const float4*>(params + e1);
+    }
+    float4 u0, u1;
+    u0.x = sghmc_elem<RMS>(g0.x, m0.x, v0.x, r0[0], c);
+    u0.y = sghmc_elem<RMS>(g0.y, m0.y, v0.y, r0[1], c);
+    u0.z = sghmc_elem<RMS>(g0.z, m0.z, v0.z, r0[2], c);
+    u0.w = sghmc_elem<RMS>(g0.w, m0.w, v0.w, r0[3], c);
+    u1.x = sghmc_elem<RMS>(g1.x, m1.x, v1.x, r1[0], c);
+    u1.y = sghmc_elem<RMS>(g1.y, m1.y, v1.y, r1[1], c);
+    u1.z = sghmc_elem<RMS>(g1.z, m1.z, v1.z, r1[2], c);
+    u1.w = sghmc_elem<RMS>(g1.w, m1.w, v1.w, r1[3], c);
+    *reinterpret_cast<float4*>(mom + e0) = m0;
+    *reinterpret_cast<float4*>(mom + e1) = m1;
+    if (RMS) {
+      *reinterpret_cast<float4*>(pv + e0) = v0;
+      *reinterpret_cast<float4*>(pv + e1) = v1;
+    }
+    if (params) {
+      p0.x += u0.x; p0.y += u0.y; p0.z += u0.z; p0.w += u0.w;
+      p1.x += u1.x; p1.y += u1.y; p1.z += u1.z; p1.w += u1.w;
+      *reinterpret_cast<float4*>(params + e0) = p0;
+      *reinterpret_cast<float4*>(params + e1) = p1;
+    }
+    if (upd) {
+      *reinterpret_cast<float4*>(upd + e0) = u0;
+      *reinterpret_cast<float4*>(upd + e1) = u1;
+    }
+  } else {
+    // ragged leaf (odd size, unaligned offset or half): scalar path, same arithmetic
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t i = i0 + k;
+      if (i >= h) break;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1 && !(i + h < n)) continue;
+        const int64_t e = half ? e1 + k : e0 + k;
+        float m = mom[e];
+        float v = RMS ? pv[e] : 0.f;
+        const float u = sghmc_elem<RMS>(grad[e], m, v, half ? r1[k] : r0[k], c);
+        mom[e] = m;
+        if (RMS) pv[e] = v;
+        if (params) params[e] += u;
+        if (upd) upd[e] = u;
+      }
+    }
+  }
+}
+
+// Exploration phase of cyclical SGLD: no noise, no momentum (cyclical_sgld_integrator.py:65-84).
+template <bool RMS>
+__global__ void __launch_bounds__(256)
+    sgd_explore_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ pv,
+                       float* __restrict__ upd, int64_t n, const StepCoef c) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < n; e += stride) {
+    if (e + 3 < n) {
+      const float4 g = *reinterpret_cast<const float4*>(grad + e);
+      float gg[4] = {g.x, g.y, g.z, g.w};
+      float uu[4];
+      float vv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (RMS) {
+        const float4 v = *reinterpret_cast<const float4*>(pv + e);
+        vv[0] = v.x; vv[1] = v.y; vv[2] = v.z; vv[3] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // -1.0 * step * g, then optax.sgd(1.0) = scale(-1.0): exact sign flips
+        float u = c.step_size * gg[k];
+        if (RMS) {
+          vv[k] = vv[k] * c.alpha + (gg[k] * gg[k]) * c.one_m_alpha;
+          u = __fdividef(u, c.rms_eps + sqrt_approx(vv[k]));
+        }
+        uu[k] = u;
+      }
+      if (RMS) *reinterpret_cast<float4*>(pv + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      if (params) {
+        float4 p = *reinterpret_cast<const float4*>(params + e);
+        p.x += uu[0]; p.y += uu[1]; p.z += uu[2]; p.w += uu[3];
+        *reinterpret_cast<float4*>(params + e) = p;
+      }
+      if (upd) *reinterpret_cast<float4*>(upd + e) = make_float4(uu[0], uu[1], uu[2], uu[3]);
+    } else {
+      for (int64_t j = e; j < n; ++j) {
+        const float g = grad[j];
+        float u = c.step_size * g;
+        if (RMS) {
+          const float v = pv[j] * c.alpha + (g * g) * c.one_m_alpha;
+          pv[j] = v;
+          u = __fdividef(u, c.rms_eps + sqrt_approx(v));
+        }
+        if (params) params[j] += u;
+        if (upd) upd[j] = u;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bank_put_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                       int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = n >> 2;
+  const bool al = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0;
+  if (al) {
+    for (int64_t i = i0; i < n4; i += stride)
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    for (int64_t i = n4 * 4 + i0; i < n; i += stride) dst[i] = src[i];
+  } else {
+    for (int64_t i = i0; i < n; i += stride) dst[i] = src[i];
+  }
+}
+
+static StepCoef make_coef(const fb200_sgmcmc_hparams_t* hp) {
+  StepCoef c;
+  c.step_size = hp->step_size;
+  c.sqrt_eps = sqrtf(hp->step_size);
+  c.beta = (float)hp->momentum_decay;
+  c.noise_scale = sqrtf((float)(2.0 * (1.0 - hp->momentum_decay)));
+  c.alpha = (float)hp->rms_alpha;
+  c.one_m_alpha = (float)(1.0 - hp->rms_alpha);
+  c.rms_eps = (float)hp->rms_eps;
+  c.zero_momentum = hp->zero_momentum;
+  return c;
+}
+
+}  // namespace fb200
+
+using namespace fb200;
+
+extern "C" int64_t fb200_sgmcmc_num_tiles_host(const fb200_leaf_t* leaves, int n_leaves) {
+  if (!leaves || n_leaves <= 0) return FB200_E_NULL;
+  int64_t t = 0;
+  for (int l = 0; l < n_leaves; ++l) {
+    if (leaves[l].len <= 0 || leaves[l].len >= 0xFFFFFFFFll || leaves[l].offset < 0) return FB200_E_SHAPE;
+    const int64_t h = (leaves[l].len + 1) / 2;
+    t += (h + FB200_TILE_PAIRS - 1) / FB200_TILE_PAIRS;
+  }
+  return t;
+}
+
+extern "C" int fb200_sgmcmc_build_tiles_host(const fb200_leaf_t* leaves, int n_leaves, fb200_tile_t* tiles,
+                                             int64_t n_tiles) {
+  if (!leaves || !tiles) return FB200_E_NULL;
+  const int64_t need = fb200_sgmcmc_num_tiles_host(leaves, n_leaves);
+  if (need < 0) return (int)need;
+  if (need != n_tiles) return FB200_E_SHAPE;
+  int64_t t = 0;
+  for (int l = 0; l < n_leaves; ++l) {
+    const int64_t h = (leaves[l].len + 1) / 2;
+    for (int64_t p = 0; p < h; p += FB200_TILE_PAIRS) {
+      tiles[t].leaf = l;
+      tiles[t].pair_start = (uint32_t)p;
+      ++t;
+    }
+  }
+  return 0;
+}
+
+extern "C" int fb200_sgmcmc_step_f32(float* params, const float* grad, float* momentum, float* precond_v,
+                                     float* updates_out, int64_t n, const fb200_leaf_t* leaves, int n_leaves,
+                                     const fb200_tile_t* tiles, int64_t n_tiles, const uint32_t* key_in,
+                                     uint32_t* key_out, uint32_t* leaf_keys_ws, const fb200_sgmcmc_hparams_t* hp,
+                                     void* stream) {
+  if (!grad || !momentum || !leaves || !tiles || !key_in || !key_out || !leaf_keys_ws || !hp) return FB200_E_NULL;
+  if (!params && !updates_out) return FB200_E_NULL;
+  if (hp->rmsprop && !precond_v) return FB200_E_NULL;
+  if (n <= 0 || n_leaves <= 0 || n_tiles <= 0 || n_tiles > 0x7FFFFFFFll || n_leaves >= (1 << 30))
+    return FB200_E_SHAPE;
+  if (key_in == key_out) return FB200_E_SHAPE;
+  if (!fb200_aligned16(grad) || !fb200_aligned16(momentum) || (params && !fb200_aligned16(params)) ||
+      (updates_out && !fb200_aligned16(updates_out)) || (hp->rmsprop && !fb200_aligned16(precond_v)))
+    return FB200_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const StepCoef c = make_coef(hp);
+  sgmcmc_keys_kernel<<<(n_leaves + 127) / 128, 128, 0, st>>>(key_in, key_out, leaf_keys_ws, (uint32_t)n_leaves);
+  FB200_LAUNCH_CHECK();
+  const uint2* lk = reinterpret_cast<const uint2*>(leaf_keys_ws);
+  if (hp->rmsprop)
+    sgmcmc_step_kernel<true><<<(unsigned)n_tiles, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out,
+                                                                leaves, lk, tiles, c);
+  else
+    sgmcmc_step_kernel<false><<<(unsigned)n_tiles, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out,
+                                                                 leaves, lk, tiles, c);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_sgd_explore_step_f32(float* params, const float* grad, float* precond_v, float* updates_out,
+                                          int64_t n, const fb200_sgmcmc_hparams_t* hp, void* stream) {
+  if (!grad || !hp) return FB200_E_NULL;
+  if (!params && !updates_out) return FB200_E_NULL;
+  if (hp->rmsprop && !precond_v) return FB200_E_NULL;
+  if (n <= 0) return FB200_E_SHAPE;
+  if (!fb200_aligned16(grad) || (params && !fb200_aligned16(params)) ||
+      (updates_out && !fb200_aligned16(updates_out)) || (hp->rmsprop && !fb200_aligned16(precond_v)))
+    return FB200_E_ALIGN;
+  const StepCoef c = make_coef(hp);
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (hp->rmsprop)
+    sgd_explore_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grad, precond_v,
+                                                                                 updates_out, n, c);
+  else
+    sgd_explore_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grad, nullptr,
+                                                                                  updates_out, n, c);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_bank_put_f32(float* bank, int64_t n, int row, const float* src, void* stream) {
+  if (!bank || !src) return FB200_E_NULL;
+  if (n <= 0 || row < 0) return FB200_E_SHAPE;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bank_put_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bank + (int64_t)row * n, src, n);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,458 @@
+"""Torch-pointer driver over the C ABI: every function here is one library call on the current CUDA
+stream with caller-visible torch tensors as storage.  No arithmetic happens in Python or in torch."""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, W_SCD, W_SDC, check, lib
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("a required tensor is None")
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError("fortuna_b200 operates on CUDA tensors only (there is no CPU path)")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    if dtype is not None and t.dtype not in (dtype if isinstance(dtype, tuple) else (dtype,)):
+        raise ValueError(f"expected dtype {dtype}, got {t.dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+KEY_DTYPE = torch.int32  # uint32[2] bit patterns (torch has no general uint32 arithmetic; none is needed)
+
+
+def key_from_host(words, device):
+    """uint32[2] host words -> device key tensor."""
+    a = np.asarray(words, dtype=np.uint32).view(np.int32)
+    return torch.from_numpy(a.copy()).to(device)
+
+
+def key_to_host(key):
+    return key.detach().cpu().numpy().view(np.uint32).copy()
+
+
+def PRNGKey(seed, device="cuda"):
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return key_from_host([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], device)
+
+
+# ------------------------------------------------------------------------------------------- PRNG
+def split(key, num=2):
+    out = torch.empty((num, 2), dtype=KEY_DTYPE, device=key.device)
+    check(lib().fb200_threefry_split(_ptr(key, KEY_DTYPE), num, _ptr(out), _stream()), "fb200_threefry_split")
+    return out
+
+
+def fold_in(key, data):
+    out = torch.empty(2, dtype=KEY_DTYPE, device=key.device)
+    check(
+        lib().fb200_threefry_fold_in(_ptr(key, KEY_DTYPE), int(data) & 0xFFFFFFFF, _ptr(out), _stream()),
+        "fb200_threefry_fold_in",
+    )
+    return out
+
+
+def random_bits(key, n):
+    out = torch.empty(n, dtype=torch.int32, device=key.device)
+    check(lib().fb200_random_bits(_ptr(key, KEY_DTYPE), n, _ptr(out), _stream()), "fb200_random_bits")
+    return out
+
+
+def random_normal(key, n):
+    out = torch.empty(n, dtype=torch.float32, device=key.device)
+    check(lib().fb200_random_normal(_ptr(key, KEY_DTYPE), n, _ptr(out), _stream()), "fb200_random_normal")
+    return out
+
+
+def sample_indices(key, n_draws, n_samples):
+    out = torch.empty(n_draws, dtype=torch.int32, device=key.device)
+    check(
+        lib().fb200_sample_indices(_ptr(key, KEY_DTYPE), n_draws, n_samples, _ptr(out), _stream()),
+        "fb200_sample_indices",
+    )
+    return out
+
+
+# ------------------------------------------------------------------------------------------- sampler
+def build_leaf_tables(lens, offsets, device):
+    """Host leaf/tile tables -> device int tensors (leaves [L,2] int64, tiles [T,2] int32)."""
+    n_leaves = len(lens)
+    leaves = (_lib.Leaf * n_leaves)()
+    for i, (o, l) in enumerate(zip(offsets, lens)):
+        leaves[i].offset = int(o)
+        leaves[i].len = int(l)
+    n_tiles = lib().fb200_sgmcmc_num_tiles_host(leaves, n_leaves)
+    if n_tiles < 0:
+        check(int(n_tiles), "fb200_sgmcmc_num_tiles_host")
+    tiles = (_lib.Tile * n_tiles)()
+    check(lib().fb200_sgmcmc_build_tiles_host(leaves, n_leaves, tiles, n_tiles), "fb200_sgmcmc_build_tiles_host")
+    leaves_np = np.frombuffer(leaves, dtype=np.int64).reshape(n_leaves, 2).copy()
+    tiles_np = np.frombuffer(tiles, dtype=np.int32).reshape(n_tiles, 2).copy()
+    return torch.from_numpy(leaves_np).to(device), torch.from_numpy(tiles_np).to(device)
+
+
+def make_hparams(step_size, momentum_decay=0.0, rmsprop=False, rms_alpha=0.99, rms_eps=1e-7, zero_momentum=False):
+    hp = _lib.SgmcmcHParams()
+    hp.step_size = float(np.float32(step_size))
+    hp.momentum_decay = float(momentum_decay)
+    hp.zero_momentum = int(bool(zero_momentum))
+    hp.rmsprop = int(bool(rmsprop))
+    hp.rms_alpha = float(rms_alpha)
+    hp.rms_eps = float(rms_eps)
+    return hp
+
+
+def sgmcmc_step(params, grad, momentum, precond_v, updates_out, leaves, tiles, key_in, key_out, leaf_keys_ws, hp):
+    n = grad.numel()
+    check(
+        lib().fb200_sgmcmc_step_f32(
+            _ptr(params, torch.float32, True),
+            _ptr(grad, torch.float32),
+            _ptr(momentum, torch.float32),
+            _ptr(precond_v, torch.float32, True),
+            _ptr(updates_out, torch.float32, True),
+            n,
+            _ptr(leaves, torch.int64),
+            leaves.shape[0],
+            _ptr(tiles, torch.int32),
+            tiles.shape[0],
+            _ptr(key_in, KEY_DTYPE),
+            _ptr(key_out, KEY_DTYPE),
+            _ptr(leaf_keys_ws, KEY_DTYPE),
+            C.byref(hp),
+            _stream(),
+        ),
+        "fb200_sgmcmc_step_f32",
+    )
+
+
+def sgd_explore_step(params, grad, precond_v, updates_out, hp):
+    check(
+        lib().fb200_sgd_explore_step_f32(
+            _ptr(params, torch.float32, True),
+            _ptr(grad, torch.float32),
+            _ptr(precond_v, torch.float32, True),
+            _ptr(updates_out, torch.float32, True),
+            grad.numel(),
+            C.byref(hp),
+            _stream(),
+        ),
+        "fb200_sgd_explore_step_f32",
+    )
+
+
+def bank_put(bank, row, src):
+    check(
+        lib().fb200_bank_put_f32(_ptr(bank, torch.float32), bank.shape[1], int(row), _ptr(src, torch.float32), _stream()),
+        "fb200_bank_put_f32",
+    )
+
+
+# ------------------------------------------------------------------------------------------- last layer
+def last_layer_logits(x, w, bias=None, log_temp=None, out_dtype=torch.float32, w_layout=W_SDC, path=0, out=None):
+    """x [B,D], w [S,D,C] (W_SDC) or [S,C,D] (W_SCD), bias [S,C] f32 -> out [S,B,C]."""
+    if x.dtype != w.dtype:
+        raise ValueError("x and w must share a dtype")
+    S = w.shape[0]
+    B, D = x.shape
+    Cn = w.shape[2] if w_layout == W_SDC else w.shape[1]
+    if (w.shape[1] if w_layout == W_SDC else w.shape[2]) != D:
+        raise ValueError("feature dimension mismatch between x and w")
+    if out is None:
+        out = torch.empty((S, B, Cn), dtype=out_dtype, device=x.device)
+    check(
+        lib().fb200_last_layer_logits(
+            _ptr(x, (torch.float32, torch.bfloat16)),
+            _ptr(w),
+            _ptr(bias, torch.float32, True),
+            _ptr(log_temp, torch.float32, True),
+            _ptr(out, (torch.float32, torch.bfloat16)),
+            S,
+            B,
+            D,
+            Cn,
+            _DT[x.dtype],
+            _DT[out.dtype],
+            w_layout,
+            path,
+            _stream(),
+        ),
+        "fb200_last_layer_logits",
+    )
+    return out
+
+
+def transpose_w_bf16(w):
+    S, D, Cn = w.shape
+    wt = torch.empty((S, Cn, D), dtype=torch.bfloat16, device=w.device)
+    check(
+        lib().fb200_transpose_w_bf16(_ptr(w, (torch.float32, torch.bfloat16)), _DT[w.dtype], _ptr(wt), S, D, Cn, _stream()),
+        "fb200_transpose_w_bf16",
+    )
+    return wt
+
+
+# ------------------------------------------------------------------------------------------- reductions
+CLS_FIELDS = tuple(n for n, _ in _lib.ClsOutputs._fields_)
+_CLS_BC = ("mean", "aleatoric_variance", "epistemic_variance", "variance", "std")
+_CLS_B = ("entropy", "aleatoric_entropy", "epistemic_entropy", "log_prob")
+
+
+def _alloc_cls_outputs(want, S, B, Cn, device):
+    outs = {}
+    for name in want:
+        if name in _CLS_BC:
+            outs[name] = torch.empty((B, Cn), dtype=torch.float32, device=device)
+        elif name in _CLS_B:
+            outs[name] = torch.empty(B, dtype=torch.float32, device=device)
+        elif name == "mode":
+            outs[name] = torch.empty(B, dtype=torch.int32, device=device)
+        elif name == "ensemble_log_prob":
+            outs[name] = torch.empty((S, B), dtype=torch.float32, device=device)
+        else:
+            raise ValueError(f"unknown classification output {name!r}")
+    return outs
+
+
+def _cls_struct(outs):
+    st = _lib.ClsOutputs()
+    for name, t in outs.items():
+        setattr(st, name, t.data_ptr())
+    return st
+
+
+def bma_reduce_cls(logits, want, targets=None, log_temp=None, out=None):
+    """One pass over logits [S,B,C] (f32 or bf16). `want`: iterable of output names -> dict of tensors."""
+    S, B, Cn = logits.shape
+    outs = out if out is not None else _alloc_cls_outputs(tuple(want), S, B, Cn, logits.device)
+    st = _cls_struct(outs)
+    check(
+        lib().fb200_bma_reduce_cls(
+            _ptr(logits, (torch.float32, torch.bfloat16)),
+            _DT[logits.dtype],
+            _ptr(log_temp, torch.float32, True),
+            _ptr(targets, torch.int32, True),
+            S,
+            B,
+            Cn,
+            C.byref(st),
+            None,
+            _stream(),
+        ),
+        "fb200_bma_reduce_cls",
+    )
+    return outs
+
+
+def alloc_cls_partials(B, Cn, device):
+    p = {n: torch.empty((B, Cn), dtype=torch.float32, device=device) for n in ("sum_p", "sum_p2", "sum_pq")}
+    for n in ("sum_plogp", "ll_max", "ll_sumexp"):
+        p[n] = torch.empty(B, dtype=torch.float32, device=device)
+    return p
+
+
+def _partials_struct(p):
+    st = _lib.ClsPartials()
+    for name, t in p.items():
+        setattr(st, name, t.data_ptr())
+    return st
+
+
+def bma_reduce_cls_partial(logits, targets=None, log_temp=None, partials=None):
+    S, B, Cn = logits.shape
+    p = partials if partials is not None else alloc_cls_partials(B, Cn, logits.device)
+    st = _partials_struct(p)
+    check(
+        lib().fb200_bma_reduce_cls(
+            _ptr(logits, (torch.float32, torch.bfloat16)),
+            _DT[logits.dtype],
+            _ptr(log_temp, torch.float32, True),
+            _ptr(targets, torch.int32, True),
+            S,
+            B,
+            Cn,
+            None,
+            C.byref(st),
+            _stream(),
+        ),
+        "fb200_bma_reduce_cls(partials)",
+    )
+    return p
+
+
+def bma_finalize_cls(partials, s_total, want, out=None):
+    B, Cn = partials["sum_p"].shape
+    outs = out if out is not None else _alloc_cls_outputs(tuple(want), s_total, B, Cn, partials["sum_p"].device)
+    pst = _partials_struct(partials)
+    ost = _cls_struct(outs)
+    check(
+        lib().fb200_bma_finalize_cls(C.byref(pst), int(s_total), B, Cn, C.byref(ost), _stream()),
+        "fb200_bma_finalize_cls",
+    )
+    return outs
+
+
+def merge_lse_pairs(max_in, sumexp_in):
+    R, B = max_in.shape
+    mo = torch.empty(B, dtype=torch.float32, device=max_in.device)
+    so = torch.empty(B, dtype=torch.float32, device=max_in.device)
+    check(
+        lib().fb200_merge_lse_pairs(
+            _ptr(max_in, torch.float32), _ptr(sumexp_in, torch.float32), R, B, _ptr(mo), _ptr(so), _stream()
+        ),
+        "fb200_merge_lse_pairs",
+    )
+    return mo, so
+
+
+def bma_reduce_reg(outputs, want, targets=None, log_temp=None):
+    S, B, two_d = outputs.shape
+    d = two_d // 2
+    outs = {}
+    for name in want:
+        if name in ("mean", "aleatoric_variance", "epistemic_variance", "variance", "std"):
+            outs[name] = torch.empty((B, d), dtype=torch.float32, device=outputs.device)
+        elif name == "log_prob":
+            outs[name] = torch.empty(B, dtype=torch.float32, device=outputs.device)
+        elif name == "ensemble_log_prob":
+            outs[name] = torch.empty((S, B), dtype=torch.float32, device=outputs.device)
+        else:
+            raise ValueError(f"unknown regression output {name!r}")
+    st = _lib.RegOutputs()
+    for name, t in outs.items():
+        setattr(st, name, t.data_ptr())
+    check(
+        lib().fb200_bma_reduce_reg(
+            _ptr(outputs, torch.float32),
+            _ptr(log_temp, torch.float32, True),
+            _ptr(targets, torch.float32, True),
+            S,
+            B,
+            d,
+            C.byref(st),
+            _stream(),
+        ),
+        "fb200_bma_reduce_reg",
+    )
+    return outs
+
+
+# ------------------------------------------------------------------------------------------- scoring
+def aps_scores(probs, targets=None, want_perm=False):
+    B, Cn = probs.shape
+    scores = torch.empty(B if targets is not None else (B, Cn), dtype=torch.float32, device=probs.device)
+    perm = torch.empty((B, Cn), dtype=torch.int32, device=probs.device) if want_perm else None
+    check(
+        lib().fb200_aps_scores(
+            _ptr(probs, torch.float32), _ptr(targets, torch.int32, True), B, Cn, _ptr(scores), _ptr(perm, None, True), _stream()
+        ),
+        "fb200_aps_scores",
+    )
+    return (scores, perm) if want_perm else scores
+
+
+def simple_scores(probs, targets=None):
+    B, Cn = probs.shape
+    scores = torch.empty(B if targets is not None else (B, Cn), dtype=torch.float32, device=probs.device)
+    check(
+        lib().fb200_simple_scores(_ptr(probs, torch.float32), _ptr(targets, torch.int32, True), B, Cn, _ptr(scores), _stream()),
+        "fb200_simple_scores",
+    )
+    return scores
+
+
+def credible_sets(mean, error):
+    B, Cn = mean.shape
+    labels = torch.empty((B, Cn), dtype=torch.int32, device=mean.device)
+    size = torch.empty(B, dtype=torch.int32, device=mean.device)
+    check(
+        lib().fb200_credible_sets(
+            _ptr(mean, torch.float32), B, Cn, float(np.float32(1 - error)), _ptr(labels), _ptr(size), _stream()
+        ),
+        "fb200_credible_sets",
+    )
+    return labels, size
+
+
+def sort_f32_(x):
+    """In-place ascending sort of a 1-D float32 CUDA tensor."""
+    n = x.numel()
+    nbytes = lib().fb200_sort_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    check(lib().fb200_sort_f32(_ptr(x, torch.float32), n, _ptr(ws), nbytes, _stream()), "fb200_sort_f32")
+    return x
+
+
+def conformal_sets(val_scores_sorted, test_scores, threshold):
+    B, Cn = test_scores.shape
+    mask = torch.empty((B, Cn), dtype=torch.uint8, device=test_scores.device)
+    sizes = torch.empty(B, dtype=torch.int32, device=test_scores.device)
+    check(
+        lib().fb200_conformal_sets(
+            _ptr(val_scores_sorted, torch.float32),
+            val_scores_sorted.numel(),
+            _ptr(test_scores, torch.float32),
+            B,
+            Cn,
+            float(np.float32(threshold)),
+            _ptr(mask),
+            _ptr(sizes),
+            _stream(),
+        ),
+        "fb200_conformal_sets",
+    )
+    return mask, sizes
+
+
+def ece_bins(probs, targets, thresholds, preds=None, want_bin_idx=False):
+    if probs.dim() == 1:
+        B, Cn = probs.shape[0], 1
+    else:
+        B, Cn = probs.shape
+    nb = thresholds.numel()
+    dev = probs.device
+    counts = torch.empty(nb, dtype=torch.int32, device=dev)
+    correct = torch.empty(nb, dtype=torch.int32, device=dev)
+    conf_sums = torch.empty(nb, dtype=torch.float32, device=dev)
+    result = torch.empty(4, dtype=torch.float32, device=dev)
+    bin_idx = torch.empty(B, dtype=torch.int32, device=dev) if want_bin_idx else None
+    check(
+        lib().fb200_ece_bins(
+            _ptr(probs, torch.float32),
+            B,
+            Cn,
+            _ptr(preds, torch.int32, True),
+            _ptr(targets, torch.int32, True),
+            _ptr(thresholds, torch.float32),
+            nb,
+            _ptr(bin_idx, None, True),
+            _ptr(counts),
+            _ptr(conf_sums),
+            _ptr(correct),
+            _ptr(result),
+            _stream(),
+        ),
+        "fb200_ece_bins",
+    )
+    return {"counts": counts, "conf_sums": conf_sums, "correct": correct, "result": result, "bin_idx": bin_idx}
+
+
+def quantile_sorted(x_sorted, q):
+    out = torch.empty(q.numel(), dtype=torch.float32, device=x_sorted.device)
+    check(
+        lib().fb200_quantile_sorted(_ptr(x_sorted, torch.float32), x_sorted.numel(), _ptr(q, torch.float32), q.numel(), _ptr(out), _stream()),
+        "fb200_quantile_sorted",
+    )
+    return out

@@ -1,0 +1,89 @@
+"""Cyclical SGLD integrator - drop-in for
+fortuna/prob_model/posterior/sgmcmc/cyclical_sgld/cyclical_sgld_integrator.py:14-102.
+
+Phase test ``((count % cycle_length) / cycle_length) >= exploration_ratio`` (:94-96) is evaluated on the
+host from the mirrored count in float32, as jax does (int32 mod, float32 true divide, weak-typed ratio):
+  * sampling phase   -> the SGHMC kernel with momentum_decay = 0 (SGLD);
+  * exploration phase -> fb200_sgd_explore_step_f32 (preconditioned SGD ascent, no noise, key and
+    momentum untouched).
+"""
+
+from typing import NamedTuple
+
+import numpy as np
+
+from ..... import ops
+from .....utils.flat_tree import FlatTree, as_flat_tree
+from ..sghmc.sghmc_integrator import GradientTransformation, OptaxSGHMCState, sghmc_integrator
+from ..sgmcmc_preconditioner import Preconditioner, precond_buffer
+from ..sgmcmc_step_schedule import cyclical_cosine_schedule_with_const_burnin
+
+
+class OptaxCyclicalSGLDState(NamedTuple):
+    """Same fields as the reference (:14-18); optax ``sgd(1.0)`` carries no arrays."""
+
+    sgd_state: tuple
+    sgld_state: OptaxSGHMCState
+
+
+def is_sampling_phase(count: int, cycle_length: int, exploration_ratio: float) -> bool:
+    return bool(
+        np.float32(np.int32(count) % np.int32(cycle_length)) / np.float32(cycle_length)
+        >= np.float32(exploration_ratio)
+    )
+
+
+def cyclical_sgld_integrator(
+    rng_key,
+    init_step_size: float,
+    cycle_length: int,
+    exploration_ratio: float,
+    preconditioner: Preconditioner,
+) -> GradientTransformation:
+    step_schedule = cyclical_cosine_schedule_with_const_burnin(
+        init_step_size=init_step_size, burnin_steps=0, cycle_length=cycle_length
+    )
+    sgld = sghmc_integrator(
+        momentum_decay=0.0,
+        momentum_resample_steps=None,
+        rng_key=rng_key,
+        step_schedule=step_schedule,
+        preconditioner=preconditioner,
+    )
+
+    def init_fn(params):
+        return OptaxCyclicalSGLDState(sgd_state=((), ()), sgld_state=sgld.init(params))
+
+    def _explore(gradient, state, params):
+        inner = state.sgld_state
+        grad = as_flat_tree(gradient, like=inner.momentum)
+        hp = ops.make_hparams(
+            step_schedule(inner.count), 0.0, preconditioner.is_rmsprop, preconditioner.running_average_factor,
+            preconditioner.eps,
+        )
+        v = precond_buffer(inner.preconditioner_state)
+        updates = grad.empty_like() if params is None else None
+        ops.sgd_explore_step(
+            params.flat if params is not None else None,
+            grad.flat,
+            v.flat if v is not None else None,
+            updates.flat if updates is not None else None,
+            hp,
+        )
+        new_inner = inner._replace(count=inner.count + 1)
+        return updates, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=new_inner)
+
+    def update_fn(gradient, state, *_):
+        if is_sampling_phase(state.sgld_state.count, cycle_length, exploration_ratio):
+            updates, inner = sgld.update(gradient, state.sgld_state)
+            return updates, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner)
+        return _explore(gradient, state, None)
+
+    def apply_fn(params: FlatTree, gradient, state):
+        if is_sampling_phase(state.sgld_state.count, cycle_length, exploration_ratio):
+            _, inner = sgld.apply(params, gradient, state.sgld_state)
+            return params, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner)
+        _, new_state = _explore(gradient, state, params)
+        return params, new_state
+
+    return GradientTransformation(init_fn, update_fn, apply_fn)

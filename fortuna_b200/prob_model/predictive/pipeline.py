@@ -1,0 +1,214 @@
+"""Device-side orchestration of the predictive path over calibrated logits z[S,B,C]:
+reduce (K3/K4) -> APS scores (K5) -> rank-count conformal sets (K6) -> ECE (K7).
+
+Two callers:
+  * ``PredictivePipeline``            - logits already resident in HBM (one GPU, or S-sharded over the
+                                        ranks of a torch.distributed NCCL group);
+  * ``predictive_from_logits_batches`` - the loader-shaped public call: an iterable of pinned HOST batches
+    (like Fortuna's ``_loop_fun_through_inputs_loader``, fortuna/prob_model/predictive/base.py:952-975),
+    double-buffered H2D copies overlapped with the kernels, results copied back to pinned host memory.
+All arithmetic is in the library kernels; torch provides memory, streams and NCCL only.
+"""
+
+import time
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ... import ops
+
+
+def conformal_threshold(n_val: int, error: float) -> np.float32:
+    """float32((1 - error) * (n_val + 1)) - right-hand side of
+    fortuna/conformal/classification/base.py:51-53 under jax weak typing."""
+    return np.float32((1 - error) * (n_val + 1))
+
+
+def ece_thresholds(n_data: int, n_bins: int = 10) -> np.ndarray:
+    """jnp.linspace(1 / n_data, 1, n_bins) in float32 (fortuna/metric/classification.py:76)."""
+    start, stop = np.float32(1 / n_data), np.float32(1)
+    div = n_bins - 1
+    step = (np.arange(div, dtype=np.float32) / np.float32(div)).astype(np.float32)
+    out = start * (np.float32(1) - step) + stop * step
+    return np.concatenate([out, np.array([stop], dtype=np.float32)]).astype(np.float32)
+
+
+class ConformalCalibration:
+    """Validation scores, sorted once on the device, plus the float32 count threshold."""
+
+    def __init__(self, val_scores_sorted: torch.Tensor, n_val: int, error: float):
+        self.val_sorted = val_scores_sorted
+        self.n_val = int(n_val)
+        self.error = float(error)
+        self.threshold = conformal_threshold(n_val, error)
+
+
+class PredictivePipeline:
+    def __init__(self, S, B, C, device, want: Sequence[str], world: int = 1, rank: int = 0):
+        self.S, self.B, self.C = S, B, C
+        self.device = device
+        self.want = tuple(want)
+        self.world, self.rank = world, rank
+        self.B_local = B // world
+        self.outs: Dict[str, torch.Tensor] = {}
+        self.scores = None
+        self.thresholds = torch.from_numpy(ece_thresholds(B)).to(device)
+        if world > 1:
+            self.partials = ops.alloc_cls_partials(B, C, device)
+            self.rs = {n: torch.empty((self.B_local, C), dtype=torch.float32, device=device)
+                       for n in ("sum_p", "sum_p2", "sum_pq")}
+            self.rs["sum_plogp"] = torch.empty(self.B_local, dtype=torch.float32, device=device)
+            self.gather_max = torch.empty((world, B), dtype=torch.float32, device=device)
+            self.gather_sum = torch.empty((world, B), dtype=torch.float32, device=device)
+        self.launches_per_step = 5 if world == 1 else 7
+
+    # -------------------------------------------------------------------------------- K3 / K4
+    def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor]):
+        if self.world == 1:
+            self.outs = ops.bma_reduce_cls(z, self.want, targets=targets, out=self.outs or None)
+            return self.outs
+        import torch.distributed as dist
+
+        p = ops.bma_reduce_cls_partial(z, targets=targets, partials=self.partials)
+        # the one exchange step of the S-sharded path: every rank keeps the rows b of its B/N slice
+        for n in ("sum_p", "sum_p2", "sum_pq", "sum_plogp"):
+            dist.reduce_scatter_tensor(self.rs[n], p[n], op=dist.ReduceOp.SUM)
+        dist.all_gather_into_tensor(self.gather_max, p["ll_max"])
+        dist.all_gather_into_tensor(self.gather_sum, p["ll_sumexp"])
+        lo, hi = self.rank * self.B_local, (self.rank + 1) * self.B_local
+        m, s = ops.merge_lse_pairs(self.gather_max[:, lo:hi].contiguous(), self.gather_sum[:, lo:hi].contiguous())
+        merged = dict(self.rs)
+        merged["ll_max"], merged["ll_sumexp"] = m, s
+        want = [w for w in self.want if w != "ensemble_log_prob"]
+        self.outs = ops.bma_finalize_cls(merged, self.S * self.world, want, out=self.outs or None)
+        return self.outs
+
+    # -------------------------------------------------------------------------------- K5 / K6 / K7
+    def score(self, targets: torch.Tensor, calib: ConformalCalibration):
+        mean = self.outs["mean"]
+        lo, hi = self.rank * self.B_local, (self.rank + 1) * self.B_local
+        t_local = targets[lo:hi] if self.world > 1 else targets
+        self.scores = ops.aps_scores(mean, None)
+        self.mask, self.sizes = ops.conformal_sets(calib.val_sorted, self.scores, calib.threshold)
+        self.ece = ops.ece_bins(mean, t_local, self.thresholds)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            for n in ("counts", "correct", "conf_sums"):
+                dist.all_reduce(self.ece[n], op=dist.ReduceOp.SUM)
+        return self.mask, self.sizes, self.ece
+
+
+def predictive_from_logits_batches(
+    batches: Iterable[torch.Tensor],
+    target_batches: Iterable[torch.Tensor],
+    calib: ConformalCalibration,
+    want: Sequence[str],
+    device,
+    host_out: Optional[Dict[str, torch.Tensor]] = None,
+):
+    """Public loader-shaped call.  `batches`: pinned host tensors [S, Bc, C] (f32 or bf16);
+    `target_batches`: pinned host int32 [Bc].  Returns a dict of pinned host tensors over all inputs
+    (mean, ..., conformal mask/sizes, ECE result).  H2D copies run on their own stream, two device buffers
+    deep, overlapped with the kernels of the previous batch."""
+    batches = list(batches)
+    target_batches = list(target_batches)
+    S, Bc, Cn = batches[0].shape
+    n_b = len(batches)
+    B = sum(int(b.shape[1]) for b in batches)
+    copy_s, comp_s = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    zbuf = [torch.empty((S, Bc, Cn), dtype=batches[0].dtype, device=device) for _ in range(2)]
+    tbuf = [torch.empty(Bc, dtype=torch.int32, device=device) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    bc_names = [w for w in want if w in ("mean", "aleatoric_variance", "epistemic_variance", "variance", "std")]
+    full = {w: torch.empty((B, Cn), dtype=torch.float32, device=device) for w in bc_names}
+    vec = {w: torch.empty(B, dtype=torch.int32 if w == "mode" else torch.float32, device=device)
+           for w in want if w not in bc_names and w != "ensemble_log_prob"}
+    tfull = torch.empty(B, dtype=torch.int32, device=device)
+    mask = torch.empty((B, Cn), dtype=torch.uint8, device=device)
+    sizes = torch.empty(B, dtype=torch.int32, device=device)
+    if host_out is None:
+        host_out = {}
+        for k, v in list(full.items()) + list(vec.items()) + [("conformal_mask", mask), ("conformal_sizes", sizes)]:
+            host_out[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+        host_out["ece_result"] = torch.empty(4, dtype=torch.float32, pin_memory=True)
+    cur = torch.cuda.current_stream(device)
+    copy_s.wait_stream(cur)
+    comp_s.wait_stream(cur)
+    b0 = 0
+    for i, (hb, ht) in enumerate(zip(batches, target_batches)):
+        k = i & 1
+        rows = int(hb.shape[1])
+        with torch.cuda.stream(copy_s):
+            if i >= 2:
+                copy_s.wait_event(free[k])
+            zbuf[k][:, :rows].copy_(hb, non_blocking=True) if rows != Bc else zbuf[k].copy_(hb, non_blocking=True)
+            tbuf[k][:rows].copy_(ht, non_blocking=True)
+            ready[k].record(copy_s)
+        with torch.cuda.stream(comp_s):
+            comp_s.wait_event(ready[k])
+            zin = zbuf[k] if rows == Bc else zbuf[k][:, :rows].contiguous()
+            tin = tbuf[k][:rows]
+            outs = {w: full[w][b0 : b0 + rows] for w in bc_names}
+            outs.update({w: vec[w][b0 : b0 + rows] for w in vec})
+            ops.bma_reduce_cls(zin, want, targets=tin, out=outs)
+            free[k].record(comp_s)
+            tfull[b0 : b0 + rows].copy_(tin, non_blocking=True)
+            sc = ops.aps_scores(full["mean"][b0 : b0 + rows], None)
+            m, sz = ops.conformal_sets(calib.val_sorted, sc, calib.threshold)
+            mask[b0 : b0 + rows].copy_(m, non_blocking=True)
+            sizes[b0 : b0 + rows].copy_(sz, non_blocking=True)
+        b0 += rows
+    with torch.cuda.stream(comp_s):
+        thr = torch.from_numpy(ece_thresholds(B)).to(device, non_blocking=True)
+        ece = ops.ece_bins(full["mean"], tfull, thr)
+        for k2, v in list(full.items()) + list(vec.items()) + [("conformal_mask", mask), ("conformal_sizes", sizes)]:
+            host_out[k2].copy_(v, non_blocking=True)
+        host_out["ece_result"].copy_(ece["result"], non_blocking=True)
+    cur.wait_stream(comp_s)
+    cur.wait_stream(copy_s)
+    return host_out
+
+
+def bench_e2e(S, B, Cn, device, want, calib, args, unit):
+    """Times predictive_from_logits_batches with pinned host inputs; returns the bench `e2e` object."""
+    Bc = min(args.e2e_batch, B)
+    n_batches = (B + Bc - 1) // Bc
+    n_host = min(4, n_batches)  # distinct pinned batches, cycled (bounds pinned memory to ~4 GB)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(7)
+    host_b, host_t = [], []
+    for _ in range(n_host):
+        d = torch.empty((S, Bc, Cn), dtype=torch.float32, device=device).normal_(0.0, 4.0, generator=gen)
+        hb = torch.empty((S, Bc, Cn), dtype=torch.float32, pin_memory=True)
+        hb.copy_(d)
+        ht = torch.randint(0, Cn, (Bc,), dtype=torch.int32).pin_memory()
+        host_b.append(hb)
+        host_t.append(ht)
+        del d
+    batches = [host_b[i % n_host] for i in range(n_batches)]
+    tbs = [host_t[i % n_host] for i in range(n_batches)]
+    host_out = None
+    times = []
+    for it in range(1 + args.e2e_steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        host_out = predictive_from_logits_batches(batches, tbs, calib, want, device, host_out)
+        torch.cuda.synchronize()
+        if it > 0:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    h2d = n_batches * (S * Bc * Cn * 4 + Bc * 4)
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    return {
+        "value": float(S) * B * Cn / sec,
+        "unit": unit,
+        "h2d_bytes_per_step": int(h2d),
+        "d2h_bytes_per_step": int(d2h),
+        "ms_per_step": sec * 1e3,
+        "steps": len(times),
+        "api": "fortuna_b200.prob_model.predictive.pipeline.predictive_from_logits_batches",
+        "host_batches": f"{n_batches} batches of [S,{Bc},C] per step from {n_host} distinct pinned buffers (cycled)",
+    }

@@ -1,0 +1,247 @@
+/*
+ * fortuna_b200.h - C ABI of libfortuna_b200.so: the B200 (sm_100a) implementation of
+ * awslabs/fortuna's posterior-sampling + Bayesian-model-averaging hot path.
+ *
+ * The reference has no FFI: the path is ordinary Python on JAX.  Each entry point below replaces
+ * the jnp expression group at the cited reference file:line; INTEGRATION.md shows the XLA-FFI /
+ * ctypes stub a Fortuna maintainer would bind to each one.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued asynchronously on it and the
+ *     call returns without synchronising; no global state, no allocation, reentrant across streams;
+ *   - return value: 0 = enqueued; negative = argument error (FB200_E_*); positive = cudaError_t
+ *     reported by the launch;
+ *   - arrays are dense row-major; `dtype` is FB200_F32 or FB200_BF16.
+ */
+#ifndef FORTUNA_B200_H_
+#define FORTUNA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_ABI_VERSION 1
+
+#define FB200_F32 0
+#define FB200_BF16 1
+
+#define FB200_E_NULL (-1)        /* a required pointer is NULL */
+#define FB200_E_SHAPE (-2)       /* a size is <= 0 or inconsistent */
+#define FB200_E_ALIGN (-3)       /* a base pointer is not 16-byte aligned */
+#define FB200_E_UNSUPPORTED (-4) /* shape/dtype outside what the kernels cover (stated per function) */
+#define FB200_E_WORKSPACE (-5)   /* workspace too small */
+
+int fb200_abi_version(void);
+/* Human-readable text for a return code of this library (static storage). */
+const char* fb200_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * jax.random primitives (threefry2x32, jax 0.4.30 non-partitionable layout), bit-exact uint32.
+ * Replace: jax.random.split / fold_in / bits / normal as called from fortuna/utils/random.py:11-23,
+ * 38-49 and fortuna/prob_model/posterior/sgmcmc/sghmc/sghmc_integrator.py:66.
+ * `key` is uint32[2] on the device.
+ * ---------------------------------------------------------------------------------------------- */
+/* out_keys[num][2] = jax.random.split(key, num). */
+int fb200_threefry_split(const uint32_t* key, int num, uint32_t* out_keys, void* stream);
+/* out_key[2] = jax.random.fold_in(key, data)  (fortuna/training/trainer.py:676-680). */
+int fb200_threefry_fold_in(const uint32_t* key, uint32_t data, uint32_t* out_key, void* stream);
+/* out[n] = the 32-bit stream jax.random.bits(key, (n,), uint32); n < 2^32-1. */
+int fb200_random_bits(const uint32_t* key, int64_t n, uint32_t* out, void* stream);
+/* out[n] = jax.random.normal(key, (n,), float32): uniform in (-1,1) then sqrt(2)*erf_inv (Giles). */
+int fb200_random_normal(const uint32_t* key, int64_t n, float* out, void* stream);
+/* out_idx[s] = jax.random.choice(split(key, n_draws)[s], n_samples) - the S posterior-sample index
+ * draws of fortuna/prob_model/predictive/base.py:632 + .../sgmcmc/sgmcmc_posterior.py:51. */
+int fb200_sample_indices(const uint32_t* key, int n_draws, int n_samples, int32_t* out_idx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SG-MCMC sampler step (K1).  Replaces sghmc_integrator.update_fn
+ * (fortuna/prob_model/posterior/sgmcmc/sghmc/sghmc_integrator.py:59-92), the preconditioner
+ * (.../sgmcmc_preconditioner.py:65-93), the per-leaf noise tree (fortuna/utils/random.py:11-23),
+ * the cyclical-SGLD phase switch (.../cyclical_sgld/cyclical_sgld_integrator.py:64-100) and
+ * flax TrainState.apply_gradients / optax.apply_updates (call site fortuna/training/trainer.py:170).
+ *
+ * The parameter pytree is one flat float32 vector: leaves concatenated in jax tree-flatten order.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t offset; /* first element of the leaf in the flat vectors                      */
+  int64_t len;    /* number of elements (leaf.size); 0 < len < 2^32-1                   */
+} fb200_leaf_t;
+
+typedef struct {
+  int32_t leaf;        /* index into the leaf table                                      */
+  uint32_t pair_start; /* first threefry counter pair of this tile; tile = 1024 pairs    */
+} fb200_tile_t;
+
+#define FB200_TILE_PAIRS 1024
+
+/* Host helper: number of tiles / fill the tile table for a leaf table (plain host memory). */
+int64_t fb200_sgmcmc_num_tiles_host(const fb200_leaf_t* leaves_host, int n_leaves);
+int fb200_sgmcmc_build_tiles_host(const fb200_leaf_t* leaves_host, int n_leaves, fb200_tile_t* tiles_host,
+                                  int64_t n_tiles);
+
+typedef struct {
+  float step_size;        /* epsilon_t = step_schedule(count), evaluated by the caller in float32       */
+  double momentum_decay;  /* beta as the python float Fortuna holds; 0 for SGLD.  The library forms      */
+                          /* float32(beta) and sqrt(float32(2*(1-beta))) exactly as jax weak-typing does */
+  int32_t zero_momentum;  /* 1: use m=0 this step (momentum_resample_steps hit); Fortuna never sets it   */
+  int32_t rmsprop;        /* 0 identity preconditioner, 1 RMSprop                                        */
+  double rms_alpha;       /* running_average_factor (python float); float32(alpha), float32(1-alpha)     */
+  double rms_eps;         /* eps (python float)                                                          */
+} fb200_sgmcmc_hparams_t;
+
+/* One sampling step (SGHMC, or the SGLD phase of cyclical SGLD with momentum_decay = 0):
+ *   (key, new_key) = split(key_in); key_out <- new_key; leaf keys = split(key, n_leaves);
+ *   v' = alpha v + (1-alpha) g^2; n = N(0,1) * sqrt(eps + sqrt(v')); m' = beta m + g sqrt(eps_t) + n sqrt(2(1-beta));
+ *   u = m' / (eps + sqrt(v')) * sqrt(eps_t);  params += u;  updates_out = u.
+ * params / updates_out may each be NULL (contract-exact optax mode returns only `updates`);
+ * precond_v must be non-NULL iff hp->rmsprop.  key_in and key_out must not alias.
+ * leaf_keys_ws: device scratch uint32[n_leaves][2] (receives the per-leaf keys; inspectable).
+ * leaves / tiles: device copies of the tables above.  All float vectors 16-byte aligned. */
+int fb200_sgmcmc_step_f32(float* params, const float* grad, float* momentum, float* precond_v,
+                          float* updates_out, int64_t n, const fb200_leaf_t* leaves, int n_leaves,
+                          const fb200_tile_t* tiles, int64_t n_tiles, const uint32_t* key_in,
+                          uint32_t* key_out, uint32_t* leaf_keys_ws, const fb200_sgmcmc_hparams_t* hp,
+                          void* stream);
+
+/* Exploration step of cyclical SGLD (cyclical_sgld_integrator.py:65-84): preconditioner update and
+ * u = (eps_t g) / (eps + sqrt(v')); params += u; no noise; key and momentum untouched. */
+int fb200_sgd_explore_step_f32(float* params, const float* grad, float* precond_v, float* updates_out,
+                               int64_t n, const fb200_sgmcmc_hparams_t* hp, void* stream);
+
+/* dst[row, :] = src[:] : snapshot of the chain's (trainable) parameters into row `row` of the
+ * on-device sample bank [n_rows, n] (replaces the device_get + msgpack put of
+ * .../sgmcmc/sgmcmc_sampling_callback.py:36-47). */
+int fb200_bank_put_f32(float* bank, int64_t n, int row, const float* src, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Last-layer logits for S posterior samples (K2).  Replaces Likelihood._get_batched_calibrated_outputs
+ * (fortuna/likelihood/base.py:429-458) restricted to the final nn.Dense (fortuna/model/mlp.py:227,
+ * lenet.py:129, resnet.py:248) + ClassificationTemperatureScaler (fortuna/output_calibrator/classification.py:14-17).
+ *   out[s,b,c] = (sum_d x[b,d] * w[s,d,c] + bias[s,c]) * exp(-log_temp)
+ * x [B,D]; w: see layout; bias [S,C] float32 or NULL; log_temp: device float[1] or NULL; out [S,B,C].
+ * w_layout: FB200_W_SDC = [S,D,C] (flax kernel layout), FB200_W_SCD = [S,C,D] (K-major copy).
+ * The tcgen05 path needs in_dtype = BF16, w_layout = SCD, D % 64 == 0 (use fb200_transpose_w_bf16 once
+ * per sample bank); every other shape runs the CUDA-core path.  `path`: 0 auto, 1 force CUDA-core,
+ * 2 force tcgen05 (FB200_E_UNSUPPORTED if the shape does not qualify).
+ * ---------------------------------------------------------------------------------------------- */
+#define FB200_W_SDC 0
+#define FB200_W_SCD 1
+int fb200_last_layer_logits(const void* x, const void* w, const float* bias, const float* log_temp, void* out,
+                            int S, int B, int D, int C, int in_dtype, int out_dtype, int w_layout, int path,
+                            void* stream);
+/* wt[s,c,d] (bf16) = w[s,d,c] (float32 or bf16 per in_dtype). */
+int fb200_transpose_w_bf16(const void* w, int in_dtype, void* wt, int S, int D, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Classification BMA reductions over calibrated logits z[S,B,C] (K3 + K4), one pass over HBM.
+ * Replaces Predictive._batched_mean / _batched_aleatoric_variance / _batched_epistemic_variance /
+ * _batched_log_prob / _batched_ensemble_log_prob (fortuna/prob_model/predictive/base.py:624-647,
+ * 735-758, 806-836, 179-203, 104-128), ClassificationPredictive.mode / aleatoric_entropy /
+ * epistemic_entropy / entropy (fortuna/prob_model/predictive/classification.py:71-86, 257-432) and the
+ * per-sample maps of fortuna/prob_output_layer/classification.py:25-28, 54-69, 88-104.
+ * Every output pointer is optional (NULL = not wanted).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* mean;               /* [B,C]  sum_s softmax / S                                   */
+  float* aleatoric_variance; /* [B,C]  sum_s p(1-p) / S                                    */
+  float* epistemic_variance; /* [B,C]  max(0, sum p^2 / S - mean^2)                        */
+  float* variance;           /* [B,C]  aleatoric + epistemic (same sample set)             */
+  float* std;                /* [B,C]  sqrt(variance)                                      */
+  int32_t* mode;             /* [B]    argmax_c mean (first maximum)                       */
+  float* entropy;            /* [B]    -sum_c mean log mean                                */
+  float* aleatoric_entropy;  /* [B]    -sum_c mean_s(p log p)                              */
+  float* epistemic_entropy;  /* [B]    entropy - aleatoric_entropy                         */
+  float* log_prob;           /* [B]    logsumexp_s(ll) - log S          (needs targets)    */
+  float* ensemble_log_prob;  /* [S,B]  ll[s,b] = z[s,b,y_b] - lse_c     (needs targets)    */
+} fb200_cls_outputs_t;
+
+/* Partial sums of one S-shard (S-sharded multi-GPU mode); all required when used. */
+typedef struct {
+  float* sum_p;     /* [B,C] sum_s p                   */
+  float* sum_p2;    /* [B,C] sum_s p^2                 */
+  float* sum_pq;    /* [B,C] sum_s p(1-p)              */
+  float* sum_plogp; /* [B]   sum_s sum_c p log p       */
+  float* ll_max;    /* [B]   max_s ll   (-inf if no targets) */
+  float* ll_sumexp; /* [B]   sum_s exp(ll - ll_max)    */
+} fb200_cls_partials_t;
+
+/* logits: [S,B,C] in `dtype`; log_temp: optional device float[1] (z = logits * exp(-log_temp));
+ * targets: optional int32[B].  Exactly one of out / partials is non-NULL: `out` finalises in the same
+ * kernel (single GPU), `partials` exports this shard's sums for fb200_bma_finalize_cls.
+ * Supports C <= 1024 (FB200_E_UNSUPPORTED above that). */
+int fb200_bma_reduce_cls(const void* logits, int dtype, const float* log_temp, const int32_t* targets, int S,
+                         int B, int C, const fb200_cls_outputs_t* out, const fb200_cls_partials_t* partials,
+                         void* stream);
+/* Combine (already all-reduced) partial sums over s_total samples into the final outputs.
+ * ll_max / ll_sumexp here are the merged pair (see fb200_merge_lse_pairs). */
+int fb200_bma_finalize_cls(const fb200_cls_partials_t* partials, int s_total, int B, int C,
+                           const fb200_cls_outputs_t* out, void* stream);
+/* Merge R gathered (max, sumexp) pairs per row: in [R,B] each -> out [B] each (the one exchange step
+ * of the S-sharded log_prob: all-gather then this). */
+int fb200_merge_lse_pairs(const float* max_in, const float* sumexp_in, int R, int B, float* max_out,
+                          float* sumexp_out, void* stream);
+
+/* Regression BMA reductions over calibrated outputs z[S,B,2d] = [mu, log var]
+ * (fortuna/prob_output_layer/regression.py:30-34, 67-74; fortuna/likelihood/regression.py:55-99;
+ * same predictive/base.py loops).  log_temp (optional) is added to log var
+ * (fortuna/output_calibrator/regression.py:16-19).  targets: optional float32 [B,d]. */
+typedef struct {
+  float* mean;               /* [B,d] */
+  float* aleatoric_variance; /* [B,d] */
+  float* epistemic_variance; /* [B,d] */
+  float* variance;           /* [B,d] */
+  float* std;                /* [B,d] */
+  float* log_prob;           /* [B]   */
+  float* ensemble_log_prob;  /* [S,B] */
+} fb200_reg_outputs_t;
+int fb200_bma_reduce_reg(const float* outputs, const float* log_temp, const float* targets, int S, int B, int d,
+                         const fb200_reg_outputs_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conformal / calibration scoring (K5-K9), bit-exact integer / index outputs.
+ * ---------------------------------------------------------------------------------------------- */
+/* Adaptive-prediction-set scores (fortuna/conformal/classification/adaptive_prediction.py:11-22,
+ * base.py:72-82).  Per row: stable descending sort (ties: larger class index first), sequential
+ * float32 inclusive prefix sum.  targets != NULL: scores[B] = prefix sum at the target's rank;
+ * targets == NULL: scores[B,C] for every class.  perm_out (optional) int32[B,C] = the descending
+ * permutation (argsort(probs)[:, ::-1]).  C <= 4096. */
+int fb200_aps_scores(const float* probs, const int32_t* targets, int B, int C, float* scores, int32_t* perm_out,
+                     void* stream);
+/* 1 - probs[b, y_b] (targets != NULL -> [B]) or 1 - probs ([B,C])
+ * (fortuna/conformal/classification/simple_prediction.py:10-18). */
+int fb200_simple_scores(const float* probs, const int32_t* targets, int B, int C, float* scores, void* stream);
+/* Credible sets (fortuna/prob_model/predictive/classification.py:465-483): labels[B,C] = descending
+ * permutation of mean, set_size[b] = first k with prefix sum > threshold, plus one;
+ * threshold = float32(1 - error) evaluated by the caller (jax weak typing). */
+int fb200_credible_sets(const float* mean, int B, int C, float threshold, int32_t* labels, int32_t* set_size,
+                        void* stream);
+/* In-place ascending sort of a float32 vector (used for the validation scores; n <= 2^26).
+ * workspace: fb200_sort_workspace_bytes(n) bytes. */
+size_t fb200_sort_workspace_bytes(int64_t n);
+int fb200_sort_f32(float* x, int64_t n, void* workspace, size_t workspace_bytes, void* stream);
+/* Rank-count conformal sets (fortuna/conformal/classification/base.py:45-64):
+ *   mask[b,c] = ( #{v : val_scores[v] > test_scores[b,c]} as float32 ) < threshold,
+ * threshold = float32((1-error)*(n_val+1)) evaluated by the caller; sizes[b] = sum_c mask.
+ * val_scores_sorted: ascending, n_val values.  mask uint8 [B,C]; sizes int32 [B] (optional). */
+int fb200_conformal_sets(const float* val_scores_sorted, int n_val, const float* test_scores, int B, int C,
+                         float threshold, uint8_t* mask, int32_t* sizes, void* stream);
+/* ECE / MCE binning (fortuna/metric/classification.py:43-95, 98-133, 147-181): conf = max_c probs (C > 1)
+ * or probs itself (C == 1); thresholds = the caller's float32 linspace(1/B, 1, n_bins) (device, n_bins <= 32).
+ * Outputs: bin_idx int32[B] (optional; -1 = in no bin), counts int32[n_bins], conf_sums float32[n_bins],
+ * correct int32[n_bins] (#(targets == preds)), and result float32[4] = {ECE, MCE, accuracy, brier (C>1 only)}.
+ * preds: optional int32[B]; NULL = argmax_c probs (first maximum).  workspace: none (outputs are zeroed here). */
+int fb200_ece_bins(const float* probs, int B, int C, const int32_t* preds, const int32_t* targets,
+                   const float* thresholds, int n_bins, int32_t* bin_idx, int32_t* counts, float* conf_sums,
+                   int32_t* correct, float* result, void* stream);
+/* jnp.quantile(x, q) for sorted ascending x[n], method="linear"
+ * (fortuna/conformal/regression/quantile.py:89-90, onedim_uncertainty.py:89-90): out[nq]. */
+int fb200_quantile_sorted(const float* x_sorted, int64_t n, const float* q, int nq, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FORTUNA_B200_H_ */

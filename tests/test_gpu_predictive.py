@@ -1,0 +1,177 @@
+"""K3/K4 parity: single-pass BMA reductions vs oracle/predictive.py.
+
+Tolerances (float32): rtol 1e-5 plus an absolute floor that reflects cancellation in the quantity
+itself: epistemic variance = E[p^2] - E[p]^2 is compared with atol 4e-7 * max(E[p]^2) (both sides carry
+half-ulp errors of the two subtracted terms); entropies with atol 2e-6 (sums of C terms of size <= 0.37).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import predictive as P
+
+pytestmark = pytest.mark.gpu
+
+ALL = (
+    "mean", "aleatoric_variance", "epistemic_variance", "variance", "std", "mode", "entropy",
+    "aleatoric_entropy", "epistemic_entropy", "log_prob", "ensemble_log_prob",
+)
+
+
+def _logits(S, B, C, seed, ties=False, scale=4.0):
+    z = (scale * np.random.default_rng(seed).standard_normal((S, B, C))).astype(np.float32)
+    if ties:
+        z = (np.round(z * 2) / 2).astype(np.float32)
+    return z
+
+
+def _check(outs, z, t, S):
+    g = {k: v.cpu().numpy() for k, v in outs.items()}
+    mean = P.cls_mean(z)
+    np.testing.assert_allclose(g["mean"], mean, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(g["aleatoric_variance"], P.cls_aleatoric_variance(z), rtol=1e-5, atol=2e-7)  # 1-p rounds at ulp(p)
+    ev_atol = 4e-7 * float(np.max(mean) ** 2) + 2e-7
+    np.testing.assert_allclose(g["epistemic_variance"], P.cls_epistemic_variance(z), rtol=1e-5, atol=ev_atol)
+    np.testing.assert_allclose(g["variance"], P.cls_variance(z), rtol=1e-5, atol=ev_atol)
+    np.testing.assert_allclose(g["std"] ** 2, P.cls_variance(z), rtol=2e-5, atol=ev_atol)
+    np.testing.assert_allclose(g["entropy"], P.cls_entropy(z), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(g["aleatoric_entropy"], P.cls_aleatoric_entropy(z), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(g["epistemic_entropy"], P.cls_epistemic_entropy(z), rtol=1e-5, atol=4e-6)
+    np.testing.assert_allclose(g["log_prob"], P.cls_log_prob(z, t), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(g["ensemble_log_prob"], P.cls_ensemble_log_prob(z, t), rtol=1e-5, atol=2e-6)
+    # mode: index-exact wherever the top-2 means are separated by more than float noise
+    srt = np.sort(mean, axis=-1)
+    clear = (srt[:, -1] - srt[:, -2]) > 1e-6 if mean.shape[1] > 1 else np.ones(mean.shape[0], bool)
+    assert np.array_equal(g["mode"][clear], P.cls_mode(z)[clear])
+
+
+@pytest.mark.parametrize(
+    "S,B,C",
+    [(8, 512, 1000), (64, 1024, 10), (30, 500, 2), (5, 517, 1000), (3, 37, 7), (4, 100, 33), (2, 19, 257),
+     (6, 64, 128), (3, 41, 1024), (7, 9, 1), (4, 70, 4), (3, 25, 1001), (9, 130, 512), (2, 300, 64)],
+)
+def test_cls_reductions_f32(cuda, S, B, C):
+    from fortuna_b200 import ops
+
+    z = _logits(S, B, C, seed=S * 1000 + C)
+    t = np.random.default_rng(1).integers(0, C, B).astype(np.int32)
+    outs = ops.bma_reduce_cls(torch.from_numpy(z).to(cuda), ALL, targets=torch.from_numpy(t).to(cuda))
+    _check(outs, z, t, S)
+
+
+def test_cls_reductions_ties_and_temperature(cuda):
+    from fortuna_b200 import ops
+
+    S, B, C = 8, 256, 1000
+    z = _logits(S, B, C, seed=3, ties=True)
+    t = np.random.default_rng(2).integers(0, C, B).astype(np.int32)
+    lt = np.array([0.3], dtype=np.float32)
+    outs = ops.bma_reduce_cls(
+        torch.from_numpy(z).to(cuda), ALL, targets=torch.from_numpy(t).to(cuda), log_temp=torch.from_numpy(lt).to(cuda)
+    )
+    zc = (z * np.exp(-lt[0], dtype=np.float32)).astype(np.float32)
+    _check(outs, zc, t, S)
+
+
+@pytest.mark.parametrize("S,B,C", [(8, 256, 1000), (16, 100, 10), (4, 33, 6)])
+def test_cls_reductions_bf16_input(cuda, S, B, C):
+    from fortuna_b200 import ops
+
+    z = P.round_to_bf16(_logits(S, B, C, seed=11))
+    t = np.random.default_rng(4).integers(0, C, B).astype(np.int32)
+    zt = torch.from_numpy(z).to(cuda).to(torch.bfloat16)
+    outs = ops.bma_reduce_cls(zt, ALL, targets=torch.from_numpy(t).to(cuda))
+    _check(outs, z, t, S)
+
+
+def test_identities_and_edge_cases(cuda):
+    from fortuna_b200 import ops
+
+    # uniform logits -> entropy = log C, epistemic = 0; S = 1 -> epistemic variance = 0
+    z = np.zeros((1, 16, 10), dtype=np.float32)
+    o = ops.bma_reduce_cls(torch.from_numpy(z).to(cuda), ("entropy", "epistemic_entropy", "epistemic_variance", "mean"))
+    np.testing.assert_allclose(o["entropy"].cpu().numpy(), np.log(10.0), rtol=1e-6)
+    np.testing.assert_allclose(o["epistemic_entropy"].cpu().numpy(), 0.0, atol=1e-6)
+    assert float(o["epistemic_variance"].abs().max()) == 0.0
+    # very confident rows: p log p underflows to 0 * finite = 0 (no NaN), like the reference
+    z = np.zeros((4, 8, 1000), dtype=np.float32)
+    z[..., 3] = 200.0
+    o = ops.bma_reduce_cls(torch.from_numpy(z).to(cuda), ("entropy", "aleatoric_entropy", "mean", "mode"))
+    assert np.isfinite(o["entropy"].cpu().numpy()).all() and np.isfinite(o["aleatoric_entropy"].cpu().numpy()).all()
+    assert (o["mode"].cpu().numpy() == 3).all()
+    # classes masked with -inf in some samples: aleatoric entropy is NaN (0 * -inf), as in the reference
+    z = _logits(3, 5, 8, seed=0)
+    z[1, :, 2] = -np.inf
+    o = ops.bma_reduce_cls(torch.from_numpy(z).to(cuda), ("aleatoric_entropy", "mean"))
+    want = P.cls_aleatoric_entropy(z)
+    assert np.isnan(want).all() and np.isnan(o["aleatoric_entropy"].cpu().numpy()).all()
+    np.testing.assert_allclose(o["mean"].cpu().numpy(), P.cls_mean(z), rtol=1e-5, atol=1e-9)
+
+
+def test_partials_finalize_equals_fused(cuda):
+    """S-sharded path on one device: two shards -> partial sums -> add / merge -> finalize."""
+    from fortuna_b200 import ops
+
+    S, B, C = 12, 300, 1000
+    z = _logits(S, B, C, seed=21)
+    t = np.random.default_rng(5).integers(0, C, B).astype(np.int32)
+    zt = torch.from_numpy(z).to(cuda)
+    tt = torch.from_numpy(t).to(cuda)
+    pa = ops.bma_reduce_cls_partial(zt[:5].contiguous(), targets=tt)
+    pb = ops.bma_reduce_cls_partial(zt[5:].contiguous(), targets=tt)
+    merged = {k: pa[k] + pb[k] for k in ("sum_p", "sum_p2", "sum_pq", "sum_plogp")}  # stands in for the all-reduce
+    m, s = ops.merge_lse_pairs(torch.stack([pa["ll_max"], pb["ll_max"]]), torch.stack([pa["ll_sumexp"], pb["ll_sumexp"]]))
+    merged["ll_max"], merged["ll_sumexp"] = m, s
+    want = [n for n in ALL if n != "ensemble_log_prob"]
+    outs = ops.bma_finalize_cls(merged, S, want)
+    outs["ensemble_log_prob"] = torch.from_numpy(P.cls_ensemble_log_prob(z, t)).to(cuda)
+    _check(outs, z, t, S)
+
+
+@pytest.mark.parametrize("S,B,d", [(8, 100, 1), (5, 33, 3)])
+def test_regression_reductions(cuda, S, B, d):
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(7)
+    z = r.standard_normal((S, B, 2 * d)).astype(np.float32)
+    y = r.standard_normal((B, d)).astype(np.float32)
+    lt = np.array([0.2], dtype=np.float32)
+    outs = ops.bma_reduce_reg(
+        torch.from_numpy(z).to(cuda),
+        ("mean", "aleatoric_variance", "epistemic_variance", "variance", "std", "log_prob", "ensemble_log_prob"),
+        targets=torch.from_numpy(y).to(cuda),
+        log_temp=torch.from_numpy(lt).to(cuda),
+    )
+    zc = P.reg_calibrate(z, lt)
+    g = {k: v.cpu().numpy() for k, v in outs.items()}
+    np.testing.assert_allclose(g["mean"], P.reg_mean(zc), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(g["aleatoric_variance"], P.reg_aleatoric_variance(zc), rtol=1e-5)
+    np.testing.assert_allclose(g["epistemic_variance"], P.reg_epistemic_variance(zc), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(g["log_prob"], P.reg_log_prob(zc, y), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(g["ensemble_log_prob"], P.reg_ensemble_log_prob(zc, y), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize(
+    "S,B,D,C,dtype", [(3, 70, 30, 2, "f32"), (4, 129, 84, 10, "f32"), (2, 100, 768, 2, "bf16"), (2, 65, 96, 130, "f32")]
+)
+@pytest.mark.parametrize("layout", ["sdc", "scd"])
+def test_last_layer_cuda_core_path(cuda, S, B, D, C, dtype, layout):
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(9)
+    x = r.standard_normal((B, D)).astype(np.float32)
+    w = (r.standard_normal((S, D, C)) / np.sqrt(D)).astype(np.float32)
+    bias = r.standard_normal((S, C)).astype(np.float32)
+    lt = np.array([0.3], dtype=np.float32)
+    bf = dtype == "bf16"
+    want = P.last_layer_logits(x, w, bias, lt, bf16_inputs=bf)
+    td = torch.bfloat16 if bf else torch.float32
+    xt = torch.from_numpy(x).to(cuda).to(td)
+    wt = torch.from_numpy(w).to(cuda).to(td)
+    if layout == "scd":
+        wt = wt.transpose(1, 2).contiguous()
+    out = ops.last_layer_logits(
+        xt, wt, torch.from_numpy(bias).to(cuda), torch.from_numpy(lt).to(cuda),
+        w_layout=ops.W_SCD if layout == "scd" else ops.W_SDC, path=1,
+    )
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-5, atol=1e-5 * np.sqrt(D))

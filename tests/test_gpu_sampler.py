@@ -1,0 +1,140 @@
+"""K1 parity: fused SG-MCMC step vs oracle/sampler.py over consecutive steps.
+
+Bit-exact: rng_key chain and per-leaf keys (uint32).  Floats: rtol 1e-5 (erf_inv / FMA contraction
+differ from numpy by rounding only), with an absolute floor of 1e-6 * max|x| for cancellation.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import prng as oprng
+from oracle import sampler as osamp
+from tests import trees
+
+pytestmark = pytest.mark.gpu
+
+
+def _grad_tree(params, seed):
+    r = np.random.default_rng(seed)
+    return osamp.tree_map(lambda p: (0.3 * r.standard_normal(p.shape) + p).astype(np.float32), params)
+
+
+def _assert_tree_close(got, want, what):
+    for (path, g), (_, w) in zip(osamp.tree_flatten(got), osamp.tree_flatten(want)):
+        atol = 1e-6 * max(1e-30, float(np.max(np.abs(w))))
+        np.testing.assert_allclose(g, w, rtol=1e-5, atol=atol, err_msg=f"{what} {'/'.join(path)}")
+
+
+@pytest.mark.parametrize("precond", ["identity", "rmsprop"])
+@pytest.mark.parametrize("tree_fn", [trees.ragged_tree, trees.mlp_two_moons_tree, trees.lenet5_tree])
+def test_sghmc_steps_match_oracle(cuda, precond, tree_fn):
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    params_np = tree_fn(1)
+    sched_args = dict(init_step_size=1e-3, final_step_size=1e-4, burnin_steps=3)
+    o_pre = osamp.Preconditioner(precond)
+    o_sched = osamp.constant_schedule_with_cosine_burnin(**sched_args)
+    o_state = osamp.sghmc_init(params_np, oprng.PRNGKey(5), o_pre)
+    o_params = params_np
+
+    pre = pc.rmsprop_preconditioner() if precond == "rmsprop" else pc.identity_preconditioner()
+    tx = sghmc_integrator(0.01, None, ops.PRNGKey(5, cuda), sched.constant_schedule_with_cosine_burnin(**sched_args), pre)
+    params = FlatTree.from_tree(params_np, device=cuda)
+    state = tx.init(params)
+
+    for step in range(4):
+        g_np = _grad_tree(o_params, 100 + step)
+        upd, o_state = osamp.sghmc_update(g_np, o_state, 0.01, o_sched, o_pre)
+        o_params = osamp.apply_updates(o_params, upd)
+        if step % 2 == 0:  # fused apply_gradients path
+            params, state = tx.apply(params, FlatTree.from_tree(g_np, device=cuda), state)
+        else:  # contract-exact optax path: updates returned, caller applies
+            updates, state = tx.update(g_np, state)
+            _assert_tree_close(updates.to_numpy_tree(), upd, f"updates step {step}")
+            params.flat.add_(updates.flat)  # test-side optax.apply_updates
+        assert np.array_equal(ops.key_to_host(state.rng_key), o_state.rng_key), "rng_key chain must be bit-exact"
+        assert state.count == o_state.count
+        _assert_tree_close(params.to_numpy_tree(), o_params, f"params step {step}")
+        _assert_tree_close(state.momentum.to_numpy_tree(), o_state.momentum, f"momentum step {step}")
+        if precond == "rmsprop":
+            _assert_tree_close(
+                state.preconditioner_state.grad_moment_estimates.to_numpy_tree(), o_state.precond, f"v step {step}"
+            )
+
+
+def test_leaf_keys_bit_exact(cuda):
+    from fortuna_b200 import ops
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    params = FlatTree.from_tree(trees.ragged_tree(0), device=cuda)
+    leaves, tiles = params.tables()
+    L = leaves.shape[0]
+    key_in = ops.PRNGKey(9, cuda)
+    key_out = torch.empty_like(key_in)
+    ws = torch.empty((L, 2), dtype=ops.KEY_DTYPE, device=cuda)
+    g = params.zeros_like()
+    m = params.zeros_like()
+    ops.sgmcmc_step(params.flat, g.flat, m.flat, None, None, leaves, tiles, key_in, key_out, ws, ops.make_hparams(1e-3, 0.01))
+    k = oprng.split(oprng.PRNGKey(9))
+    assert np.array_equal(ops.key_to_host(key_out), k[1])
+    assert np.array_equal(ws.cpu().numpy().view(np.uint32), oprng.split(k[0], L))
+    # zero gradient, zero momentum: momentum == sqrt(2(1-beta)) * N(0,1) leaf by leaf -> checks the noise layout
+    want = osamp.normal_like_tree(k[0], trees.ragged_tree(0))
+    scale = np.sqrt(np.float32(2 * (1 - 0.01)), dtype=np.float32)
+    got = m.to_numpy_tree()
+    for (path, gl), (_, wl) in zip(osamp.tree_flatten(got), osamp.tree_flatten(want)):
+        np.testing.assert_allclose(gl, wl * scale, rtol=1e-5, atol=1e-6, err_msg="/".join(path))
+
+
+@pytest.mark.parametrize("precond", ["identity", "rmsprop"])
+def test_cyclical_sgld_both_phases(cuda, precond):
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc.cyclical_sgld.cyclical_sgld_integrator import (
+        cyclical_sgld_integrator,
+    )
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    L, ratio, eps0 = 4, 0.5, 1e-3  # steps 0,1 explore; 2,3 sample; 4,5 explore ...
+    params_np = trees.ragged_tree(2)
+    o_pre = osamp.Preconditioner(precond)
+    o_state = osamp.sghmc_init(params_np, oprng.PRNGKey(1), o_pre)
+    o_params = params_np
+    pre = pc.rmsprop_preconditioner() if precond == "rmsprop" else pc.identity_preconditioner()
+    tx = cyclical_sgld_integrator(ops.PRNGKey(1, cuda), eps0, L, ratio, pre)
+    params = FlatTree.from_tree(params_np, device=cuda)
+    state = tx.init(params)
+    phases = []
+    for step in range(7):
+        g_np = _grad_tree(o_params, 300 + step)
+        phases.append(osamp.cyclical_sgld_is_sampling_phase(o_state.count, L, ratio))
+        upd, o_state = osamp.cyclical_sgld_update(g_np, o_state, eps0, L, ratio, o_pre)
+        o_params = osamp.apply_updates(o_params, upd)
+        params, state = tx.apply(params, g_np, state)
+        assert np.array_equal(ops.key_to_host(state.sgld_state.rng_key), o_state.rng_key)
+        _assert_tree_close(params.to_numpy_tree(), o_params, f"params step {step}")
+        _assert_tree_close(state.sgld_state.momentum.to_numpy_tree(), o_state.momentum, f"momentum step {step}")
+    assert phases == [False, False, True, True, False, False, True]
+
+
+def test_argument_errors(cuda):
+    from fortuna_b200 import _lib, ops
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    params = FlatTree.from_tree(trees.mlp_two_moons_tree(0), device=cuda)
+    leaves, tiles = params.tables()
+    key = ops.PRNGKey(0, cuda)
+    ws = torch.empty((leaves.shape[0], 2), dtype=ops.KEY_DTYPE, device=cuda)
+    with pytest.raises(_lib.FortunaB200Error):  # key_in aliases key_out
+        ops.sgmcmc_step(params.flat, params.flat, params.flat, None, None, leaves, tiles, key, key, ws, ops.make_hparams(1e-3))
+    with pytest.raises(_lib.FortunaB200Error):  # rmsprop without its moment buffer
+        ops.sgmcmc_step(
+            params.flat, params.flat, params.flat, None, None, leaves, tiles, key, torch.empty_like(key), ws,
+            ops.make_hparams(1e-3, rmsprop=True),
+        )
+    with pytest.raises(ValueError):  # CPU tensors are rejected: no CPU path
+        ops.random_bits(torch.zeros(2, dtype=torch.int32), 4)

@@ -1,0 +1,137 @@
+"""K5-K9 parity: integer / index outputs bit-exact, float32 prefix sums bit-exact (same sequential order)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import predictive as P
+from oracle import scoring as Sc
+
+pytestmark = pytest.mark.gpu
+
+
+def _probs(B, C, seed, ties=False):
+    z = (4 * np.random.default_rng(seed).standard_normal((B, C))).astype(np.float32)
+    if ties:
+        z = np.round(z)
+    return P.softmax(z)
+
+
+@pytest.mark.parametrize("B,C", [(64, 1000), (200, 10), (50, 2), (33, 1), (17, 37), (9, 1024), (5, 3000)])
+@pytest.mark.parametrize("ties", [False, True])
+def test_aps_scores_bit_exact(cuda, B, C, ties):
+    from fortuna_b200 import ops
+
+    p = _probs(B, C, seed=B + C, ties=ties)
+    t = np.random.default_rng(0).integers(0, C, B).astype(np.int32)
+    pt = torch.from_numpy(p).to(cuda)
+    allc, perm = ops.aps_scores(pt, None, want_perm=True)
+    assert np.array_equal(perm.cpu().numpy(), Sc.descending_perm(p))
+    assert np.array_equal(allc.cpu().numpy(), Sc.aps_cumsums(p))
+    tgt = ops.aps_scores(pt, torch.from_numpy(t).to(cuda))
+    assert np.array_equal(tgt.cpu().numpy(), Sc.aps_score(p, t))
+    s = ops.simple_scores(pt, torch.from_numpy(t).to(cuda))
+    assert np.array_equal(s.cpu().numpy(), Sc.simple_score(p, t))
+    assert np.array_equal(ops.simple_scores(pt).cpu().numpy(), Sc.simple_scores_all(p))
+
+
+@pytest.mark.parametrize("n", [1, 2, 100, 4096, 4097, 50_000, 300_001])
+def test_sort_bit_exact(cuda, n):
+    from fortuna_b200 import ops
+
+    x = np.random.default_rng(n).standard_normal(n).astype(np.float32)
+    if n > 10:
+        x[3] = x[7]  # duplicates
+        x[5] = np.inf
+    got = ops.sort_f32_(torch.from_numpy(x.copy()).to(cuda)).cpu().numpy()
+    assert np.array_equal(got, np.sort(x))
+
+
+@pytest.mark.parametrize("error", [0.05, 0.1, 0.5, 0.0, 1.0])
+@pytest.mark.parametrize("B,C,n_val", [(64, 1000, 5000), (100, 10, 37), (7, 3, 3)])
+def test_conformal_sets_bit_exact(cuda, B, C, n_val, error):
+    from fortuna_b200 import ops
+
+    vp = _probs(n_val, C, seed=2, ties=True)
+    vt = np.random.default_rng(3).integers(0, C, n_val).astype(np.int32)
+    tp = _probs(B, C, seed=4, ties=True)
+    val_scores, test_scores = Sc.get_scores(vp, vt, tp, "aps")
+    conds, sizes, _ = Sc.conformal_sets(val_scores, test_scores, error)
+    if n_val * B * C <= 4_000_000:
+        assert np.array_equal(conds, Sc.conformal_conds_literal(val_scores, test_scores, error))
+    vs = ops.sort_f32_(torch.from_numpy(val_scores.copy()).to(cuda))
+    mask, sz = ops.conformal_sets(vs, torch.from_numpy(test_scores).to(cuda), Sc.conformal_threshold(n_val, error))
+    assert np.array_equal(mask.cpu().numpy().astype(bool), conds)
+    assert np.array_equal(sz.cpu().numpy(), sizes)
+
+
+def test_reference_conformal_known_case(cuda):
+    """tests/fortuna/test_conformal_methods.py:37-53 (simple score): {0,1} in set 0, 0 in set 1."""
+    from fortuna_b200 import ops
+
+    vp = np.array([[0.1, 0.9], [0.8, 0.2], [0.3, 0.7]], dtype=np.float32)
+    vt = np.array([1, 1, 0], dtype=np.int32)
+    tp = np.array([[0.5, 0.5], [0.8, 0.2]], dtype=np.float32)
+    vs = ops.simple_scores(torch.from_numpy(vp).to(cuda), torch.from_numpy(vt).to(cuda))
+    ts = ops.simple_scores(torch.from_numpy(tp).to(cuda))
+    mask, _ = ops.conformal_sets(ops.sort_f32_(vs), ts, Sc.conformal_threshold(3, 0.05))
+    m = mask.cpu().numpy().astype(bool)
+    assert m[0, 0] and m[0, 1] and m[1, 0]
+
+
+@pytest.mark.parametrize("B,C", [(1000, 10), (4096, 1000), (77, 2), (513, 1)])
+def test_ece_bins(cuda, B, C):
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(B)
+    t = r.integers(0, max(C, 2), B).astype(np.int32)
+    if C == 1:
+        p = r.random(B).astype(np.float32)
+        preds = r.integers(0, 2, B).astype(np.int32)
+        probs_t = torch.from_numpy(p).to(cuda)
+        preds_t = torch.from_numpy(preds).to(cuda)
+    else:
+        p = _probs(B, C, seed=5, ties=(C == 2))
+        preds = p.argmax(-1).astype(np.int32)
+        probs_t = torch.from_numpy(p).to(cuda)
+        preds_t = None
+    thr = Sc.ece_thresholds(B)
+    o = ops.ece_bins(probs_t, torch.from_numpy(t).to(cuda), torch.from_numpy(thr).to(cuda), preds=preds_t, want_bin_idx=True)
+    counts, confs, accs, idx = Sc.compute_counts_confs_accs(preds, p, t)
+    assert np.array_equal(o["bin_idx"].cpu().numpy(), idx)
+    assert np.array_equal(o["counts"].cpu().numpy(), counts)
+    got_counts = o["counts"].cpu().numpy().astype(np.float32)
+    got_confs = np.where(counts > 0, o["conf_sums"].cpu().numpy() / np.maximum(got_counts, 1), 0)
+    got_accs = np.where(counts > 0, o["correct"].cpu().numpy() / np.maximum(got_counts, 1), 0)
+    np.testing.assert_allclose(got_confs, confs, rtol=1e-5)
+    np.testing.assert_allclose(got_accs, accs, rtol=1e-6)
+    res = o["result"].cpu().numpy()
+    np.testing.assert_allclose(res[0], Sc.expected_calibration_error(preds, p, t), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(res[1], Sc.maximum_calibration_error(preds, p, t), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(res[2], Sc.accuracy(preds, t), rtol=1e-6)
+    if C > 1:
+        np.testing.assert_allclose(res[3], Sc.brier_score(p, t), rtol=1e-5)
+
+
+@pytest.mark.parametrize("n", [1, 2, 100, 5001])
+@pytest.mark.parametrize("error", [0.05, 0.1, 0.5, 0.001])
+def test_quantile(cuda, n, error):
+    from fortuna_b200 import ops
+
+    x = np.random.default_rng(n).standard_normal(n).astype(np.float32)
+    q = np.array([Sc.conformal_quantile_level(n, error), 0.0, 0.5, 1.0, 0.3333], dtype=np.float32)
+    xs = ops.sort_f32_(torch.from_numpy(x.copy()).to(cuda))
+    got = ops.quantile_sorted(xs, torch.from_numpy(q).to(cuda)).cpu().numpy()
+    assert np.array_equal(got, Sc.quantile_linear(x, q))
+
+
+@pytest.mark.parametrize("error", [0.05, 0.3])
+def test_credible_sets(cuda, error):
+    from fortuna_b200 import ops
+
+    p = _probs(200, 50, seed=8, ties=True)
+    labels, size = ops.credible_sets(torch.from_numpy(p).to(cuda), error)
+    want = P.cls_credible_set(p, error)
+    lab = labels.cpu().numpy()
+    sz = size.cpu().numpy()
+    for i in range(p.shape[0]):
+        assert lab[i, : sz[i]].tolist() == want[i]

@@ -52,9 +52,10 @@ class ClockSampler:
     )
 
     def __init__(self, index=0):
-        self.lines = []
+        self.lines = []  # (wall time, csv line)
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -69,7 +70,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -81,7 +88,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        window = "timed region"
+        if not inside:  # timed region shorter than the sampling period: fall back to warm-up + timed samples
+            inside = [ln for (_, ln) in self.lines[1:]] or [ln for (_, ln) in self.lines]
+            window = "warm-up + timed region"
+        for ln in inside:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -96,7 +108,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
@@ -235,15 +248,17 @@ def run_gpu_arm(args):
             ev[2 * i + 1].record()
         runner.score(targets, calib)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)  # let nvidia-smi deliver its first sample before the GPU gets busy
     for _ in range(args.warmup):
         one_step()
-    sampler = ClockSampler(local_rank)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -254,6 +269,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = t_start.elapsed_time(t_end)
     reduce_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
@@ -327,7 +343,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--S", type=int, default=S_FULL)

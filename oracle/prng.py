@@ -177,7 +177,7 @@ def randint(key, minval: int, maxval: int) -> int:
     if maxval <= minval:
         span = 1
     mult = (1 << 16) % span
-    mult = (mult * mult) % span
+    mult = ((mult * mult) & 0xFFFFFFFF) % span  # lax.mul on uint32 wraps (spans > 2**16 give multiplier 0)
     off = (((hi % span) * mult) & 0xFFFFFFFF) + (lo % span)
     off = (off & 0xFFFFFFFF) % span
     return int(minval) + off

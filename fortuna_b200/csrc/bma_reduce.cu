@@ -71,14 +71,18 @@ struct RowLoad<__nv_bfloat16, 1> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&z)[1]) { z[0] = __bfloat162float(*p); }
 };
 
-// Per-row finalisation shared by the fused kernel and the partial-sum finaliser.
-struct RowFinal {
-  float ent_terms;  // sum_c mean log mean over this lane's classes
-  float best_v;
-  int best_c;
-};
+__device__ __forceinline__ float ex2_approx_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-template <typename T, int G, int NV, int VEC>
+template <typename T, int G, int NV, int VEC, bool TAILONLY>
 __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const ClsArgs a) {
   constexpr int R = 32 / G;                 // rows per warp
   constexpr int TB = kConsumerWarps * R;    // rows per tile
@@ -146,8 +150,10 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
   const int gr = lane / G;
   const int g = lane % G;
   const int row = warp * R + gr;
+  // temperature: z = logits * exp(-log_temp) with exp(-log_temp) > 0, so max_c z = scale * max_c logits and the
+  // scale folds into the single FFMA of pass B (k2 = scale * log2 e); no per-element multiply
   const float scale = a.log_temp ? expf(-a.log_temp[0]) : 1.0f;
-  const bool has_temp = a.log_temp != nullptr;
+  const float k2 = scale * 1.4426950408889634f;
 
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -173,46 +179,48 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
       const unsigned char* sbase = stages + (size_t)stage * a.stage_bytes;
       for (int q = 0; q < ns; ++q) {
         const T* rowp = reinterpret_cast<const T*>(sbase + (size_t)q * a.tile_stride_bytes) + (size_t)row * C;
+        // pass A: row -> registers (padding lanes get -1e30: finite even after the log2(e)*scale multiply, so 0 * u is never NaN for them,
+        // while a genuine -inf logit still yields the reference's 0 * -inf = NaN), row max
         float z[NV][VEC];
-        float m = -CUDART_INF_F;
+        float pm[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) pm[k] = -CUDART_INF_F;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
           const int c0 = (g + G * j) * VEC;
-          if (c0 < C) {
+          if (TAILONLY && j < NV - 1) {
+            RowLoad<T, VEC>::load(rowp + c0, z[j]);  // every lane's chunk is inside the row
+          } else if (c0 < C) {
             RowLoad<T, VEC>::load(rowp + c0, z[j]);
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-              if (has_temp) z[j][k] *= scale;
-              m = fmaxf(m, z[j][k]);
-            }
           } else {
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) z[j][k] = -CUDART_INF_F;
+            for (int k = 0; k < VEC; ++k) z[j][k] = -1.0e30f;
           }
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) pm[k] = fmaxf(pm[k], z[j][k]);
         }
+        float m = pm[0];
+#pragma unroll
+        for (int k = 1; k < VEC; ++k) m = fmaxf(m, pm[k]);
         m = group_max<G>(m);
-        // jsp.special.logsumexp replaces a non-finite max by 0
+        // jsp.special.logsumexp replaces a non-finite max by 0 (m is the max of the raw logits here)
         const float ms = (fabsf(m) <= 3.4028234e38f) ? m : 0.0f;
-        // pass B: e = exp(z - max) (kept in z's registers), row sum, and sum_c e * (z - max) for the
-        // entropy term: sum_c p log p = (sum_c e t) / sum - log(sum), t = z - max  (no second exp, no z reload)
+        // pass B, in log2 units: u = z*log2(e) - c with c = fl(ms*log2(e)) (one FFMA; the rounding of c is a
+        // row constant and cancels in p = e/sum), e = 2^u (MUFU.EX2), row sum, and sum_c e*u for the entropy:
+        //   sum_c p ln p = ln2 * ( (sum_c e u) / sum - log2(sum) )
+        const float cshift = ms * k2;
         float psum[VEC], pset[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) psum[k] = pset[k] = 0.0f;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-          const int c0 = (g + G * j) * VEC;
-          if (c0 < C) {
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-              const float t = z[j][k] - ms;
-              const float ev = __expf(t);
-              z[j][k] = ev;
-              psum[k] += ev;
-              pset[k] = fmaf(ev, t, pset[k]);  // 0 * -inf = NaN for a -inf logit, like the reference
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) z[j][k] = 0.0f;
+          for (int k = 0; k < VEC; ++k) {
+            const float u = fmaf(z[j][k], k2, -cshift);
+            const float ev = ex2_approx_ftz(u);
+            z[j][k] = ev;
+            psum[k] += ev;
+            pset[k] = fmaf(ev, u, pset[k]);
           }
         }
         float sum = psum[0], set = pset[0];
@@ -222,11 +230,10 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
           set += pset[k];
         }
         sum = group_sum<G>(sum);
-        const float inv = 1.0f / sum;
-        const float lsum_row = __logf(sum);
-        const float lse = ms + lsum_row;
-        spl = fmaf(inv, set, spl);  // lane-partial of sum_c p t; the -log(sum) part is row-uniform
-        sum_l += lsum_row;
+        const float inv = rcp_approx_ftz(sum);
+        const float l2sum = lg2_approx(sum);
+        spl = fmaf(inv, set, spl);  // lane-partial of sum_c p u (log2 units); the -log2(sum) part is row-uniform
+        sum_l += l2sum;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
 #pragma unroll
@@ -242,9 +249,10 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
           if (y_ok) {
             float tmp[1];
             RowLoad<T, 1>::load(rowp + y, tmp);
-            zt = has_temp ? tmp[0] * scale : tmp[0];
+            zt = tmp[0];
           }
-          const float ll = zt - lse;
+          // ll = z_y - logsumexp = ln2 * (u_y - log2(sum))
+          const float ll = 0.6931471805599453f * (fmaf(zt, k2, -cshift) - l2sum);
           if (ll > lmax) {
             lsum = lsum * __expf(lmax - ll) + 1.0f;
             lmax = ll;
@@ -263,7 +271,9 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
 
     // ------------------------------------------------------------------ tile epilogue
     const float Sf = (float)S;
-    const float spl_row = group_sum<G>(spl) - sum_l;  // sum_s sum_c p log p for this row
+    const bool s_pow2 = (S & (S - 1)) == 0;  // x * (1/S) is then bit-identical to x / S
+    const float inv_Sf = 1.0f / Sf;
+    const float spl_row = 0.6931471805599453f * (group_sum<G>(spl) - sum_l);  // sum_s sum_c p ln p of this row
     if (a.partial_mode) {
       if (valid_row) {
 #pragma unroll
@@ -298,9 +308,10 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
         float mean[VEC], av[VEC], ev[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-          mean[k] = sp[j][k] / Sf;
-          av[k] = spq[j][k] / Sf;
-          ev[k] = fmaxf(0.0f, __fsub_rn(sp2[j][k] / Sf, __fmul_rn(mean[k], mean[k])));
+          mean[k] = s_pow2 ? sp[j][k] * inv_Sf : sp[j][k] / Sf;
+          av[k] = s_pow2 ? spq[j][k] * inv_Sf : spq[j][k] / Sf;
+          const float m2 = s_pow2 ? sp2[j][k] * inv_Sf : sp2[j][k] / Sf;
+          ev[k] = fmaxf(0.0f, __fsub_rn(m2, __fmul_rn(mean[k], mean[k])));
           if (mean[k] > 0.0f) ent_terms = fmaf(mean[k], logf(mean[k]), ent_terms);
           if (mean[k] > best_v) {
             best_v = mean[k];
@@ -487,7 +498,7 @@ static int sm_count() {
   return cached[dev];
 }
 
-template <typename T, int G, int NV, int VEC>
+template <typename T, int G, int NV, int VEC, bool TAILONLY>
 static int launch_cls(ClsArgs a, cudaStream_t st) {
   constexpr int R = 32 / G;
   constexpr int TB = kConsumerWarps * R;
@@ -507,7 +518,7 @@ static int launch_cls(ClsArgs a, cudaStream_t st) {
   a.n_stages = nst;
   a.n_tiles = (a.B + TB - 1) / TB;
   const size_t smem = 128 + (size_t)nst * a.stage_bytes;
-  auto kern = bma_reduce_cls_kernel<T, G, NV, VEC>;
+  auto kern = bma_reduce_cls_kernel<T, G, NV, VEC, TAILONLY>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int occ = 1;
@@ -526,29 +537,34 @@ static int dispatch_cls(const ClsArgs& a, cudaStream_t st) {
   const int C = a.C;
   const int vec = (C % 4 == 0) ? 4 : 1;
   const int chunks = C / vec;
-#define FB200_CASE(G_, NV_, VEC_) return launch_cls<T, G_, NV_, VEC_>(a, st)
+#define FB200_CASE(G_, NV_, VEC_, TO_) return launch_cls<T, G_, NV_, VEC_, TO_>(a, st)
   if (vec == 4) {
-    if (chunks <= 1) FB200_CASE(1, 1, 4);
-    if (chunks <= 2) FB200_CASE(2, 1, 4);
-    if (chunks <= 4) FB200_CASE(4, 1, 4);
-    if (chunks <= 8) FB200_CASE(8, 1, 4);
-    if (chunks <= 16) FB200_CASE(16, 1, 4);
-    if (chunks <= 32) FB200_CASE(32, 1, 4);
-    if (chunks <= 64) FB200_CASE(32, 2, 4);
-    if (chunks <= 128) FB200_CASE(32, 4, 4);
-    if (chunks <= 256) FB200_CASE(32, 8, 4);
+    if (chunks <= 1) FB200_CASE(1, 1, 4, true);
+    if (chunks <= 2) FB200_CASE(2, 1, 4, true);
+    if (chunks <= 4) FB200_CASE(4, 1, 4, true);
+    if (chunks <= 8) FB200_CASE(8, 1, 4, true);
+    if (chunks <= 16) FB200_CASE(16, 1, 4, true);
+    // G = 32: NV = ceil(chunks / 32) exactly, so only the last chunk slot can be ragged
+    if (chunks <= 32) FB200_CASE(32, 1, 4, true);
+    if (chunks <= 64) FB200_CASE(32, 2, 4, true);
+    if (chunks <= 96) FB200_CASE(32, 3, 4, true);
+    if (chunks <= 128) FB200_CASE(32, 4, 4, true);
+    if (chunks <= 160) FB200_CASE(32, 5, 4, true);
+    if (chunks <= 192) FB200_CASE(32, 6, 4, true);
+    if (chunks <= 224) FB200_CASE(32, 7, 4, true);
+    if (chunks <= 256) FB200_CASE(32, 8, 4, true);
   } else {
-    if (chunks <= 1) FB200_CASE(1, 1, 1);
-    if (chunks <= 2) FB200_CASE(2, 1, 1);
-    if (chunks <= 4) FB200_CASE(4, 1, 1);
-    if (chunks <= 8) FB200_CASE(8, 1, 1);
-    if (chunks <= 16) FB200_CASE(16, 1, 1);
-    if (chunks <= 32) FB200_CASE(32, 1, 1);
-    if (chunks <= 64) FB200_CASE(32, 2, 1);
-    if (chunks <= 128) FB200_CASE(32, 4, 1);
-    if (chunks <= 256) FB200_CASE(32, 8, 1);
-    if (chunks <= 512) FB200_CASE(32, 16, 1);
-    if (chunks <= 1024) FB200_CASE(32, 32, 1);
+    if (chunks <= 1) FB200_CASE(1, 1, 1, true);
+    if (chunks <= 2) FB200_CASE(2, 1, 1, true);
+    if (chunks <= 4) FB200_CASE(4, 1, 1, true);
+    if (chunks <= 8) FB200_CASE(8, 1, 1, true);
+    if (chunks <= 16) FB200_CASE(16, 1, 1, true);
+    if (chunks <= 32) FB200_CASE(32, 1, 1, true);
+    if (chunks <= 64) FB200_CASE(32, 2, 1, true);
+    if (chunks <= 128) FB200_CASE(32, 4, 1, false);
+    if (chunks <= 256) FB200_CASE(32, 8, 1, false);
+    if (chunks <= 512) FB200_CASE(32, 16, 1, false);
+    if (chunks <= 1024) FB200_CASE(32, 32, 1, false);
   }
 #undef FB200_CASE
   return FB200_E_UNSUPPORTED;

@@ -1,14 +1,395 @@
-// K2 (tensor-core path): S-batched last-layer GEMM on tcgen05 / TMEM / TMA.  Placeholder until the
-// kernel lands: reports "unsupported" so fb200_last_layer_logits routes every shape to the CUDA-core path.
+// K2 (tensor-core path): S-batched last-layer GEMM on tcgen05 / TMEM / TMA for sm_100a.
+//
+//   out[s,b,c] = (sum_d x[b,d] * wt[s,c,d] + bias[s,c]) * exp(-log_temp)
+//
+// Replaces Likelihood._get_batched_calibrated_outputs restricted to the final nn.Dense
+// (fortuna/likelihood/base.py:429-458; fortuna/model/mlp.py:227, lenet.py:129, resnet.py:248) + the
+// temperature scaler (fortuna/output_calibrator/classification.py:14-17) for all S samples in one launch.
+//
+// Operands are bf16, K-major: A = x [B, D] (M = B), B = wt [S, C, D] (N = C of sample s).  A CTA owns a
+// 128 x 256 output tile of one sample and walks K in 64-element (128-byte, SWIZZLE_128B) slabs:
+//   warp 0   : TMA producer  (cp.async.bulk.tensor into a 4-stage shared-memory ring, mbarrier tx-count)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (M128 N256 K16, fp32 accumulators in TMEM),
+//              tcgen05.commit releases smem stages and publishes finished accumulators
+//   warps 2-5: epilogue - tcgen05.ld the accumulator quadrant of the warp, + bias, * scale, store
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// The grid is persistent (one CTA per SM); tiles are ordered so that concurrently running CTAs share the
+// same W tile and a group of M-blocks keeps its x rows L2-resident while it sweeps all (s, n) tiles.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "async_copy.cuh"
 #include "common.cuh"
 
 namespace fb200 {
 
-int last_layer_tc_supported(int, int, int, int, int, int, int) { return 0; }
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_N = 256;
+constexpr int TC_BLOCK_K = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_STAGES = 4;
+constexpr int TC_ACC_STAGES = 2;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_BLOCK_N * TC_BLOCK_K * 2;  // 32 KB
+constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr uint32_t TC_TMEM_COLS = TC_ACC_STAGES * TC_BLOCK_N;  // 512
+constexpr size_t TC_SMEM_BYTES = 1024 /*align slack*/ + (size_t)TC_STAGES * TC_STAGE_BYTES + 256 /*barriers*/;
 
-int last_layer_tc_launch(const void*, const void*, const float*, const float*, void*, int, int, int, int, int,
-                         cudaStream_t) {
-  return FB200_E_UNSUPPORTED;
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread for the whole CTA
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets row (lane_base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// start address >> 4 | LBO (ignored for swizzled K-major) | SBO = 8 rows * 128 B | layout type 2
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1u << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)2u << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D = F32, A = B = BF16, both K-major, N >> 3, M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TcParams {
+  const float* bias;      // [S, C] or null
+  const float* log_temp;  // [1] or null
+  void* out;              // [S, B, C]
+  int S, B, D, C;
+  int m_blocks, n_blocks, k_blocks;
+  int total_tiles;
+};
+
+struct TileCoord {
+  int s, m_blk, n_blk;
+};
+
+// Tile order: groups of `group` consecutive M-blocks; inside a group all (s, n) tiles, M fastest.
+__device__ __forceinline__ TileCoord tile_coord(int t, int group, const TcParams& p) {
+  const int sn = p.S * p.n_blocks;
+  const int per_group = group * sn;
+  const int g = t / per_group;
+  int r = t - g * per_group;
+  int rows = p.m_blocks - g * group;
+  if (rows > group) rows = group;
+  const int q = r / rows;
+  TileCoord c;
+  c.m_blk = g * group + (r - q * rows);
+  c.s = q / p.n_blocks;
+  c.n_blk = q - c.s * p.n_blocks;
+  return c;
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const TcParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* stage_base = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + TC_ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + TC_ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&tmap_a);
+    tmap_prefetch(&tmap_b);
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < TC_ACC_STAGES; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int group = gridDim.x;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(t, group, p);
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+          const int stage = it % TC_STAGES;
+          const uint32_t round = it / TC_STAGES;
+          if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1u);
+          unsigned char* sa = stage_base + (size_t)stage * TC_STAGE_BYTES;
+          unsigned char* sb = sa + TC_A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * TC_BLOCK_K, tc.m_blk * TC_BLOCK_M);
+          tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * TC_BLOCK_K, tc.n_blk * TC_BLOCK_N, tc.s);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BLOCK_M, TC_BLOCK_N);
+      uint32_t it = 0, tile_it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
+        const int acc = tile_it % TC_ACC_STAGES;
+        const uint32_t acc_round = tile_it / TC_ACC_STAGES;
+        if (acc_round > 0) mbar_wait(&tmem_empty_bar[acc], (acc_round - 1) & 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_BLOCK_N;
+        for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+          const int stage = it % TC_STAGES;
+          const uint32_t round = it / TC_STAGES;
+          mbar_wait(&full_bar[stage], round & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + (size_t)stage * TC_STAGE_BYTES);
+          const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * TC_UMMA_K * 2);
+            const uint64_t db = umma_smem_desc(sb + k * TC_UMMA_K * 2);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);                          // smem slot free once these MMAs retire
+          if (kb == p.k_blocks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- epilogue warps (2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const float scale = p.log_temp ? expf(-p.log_temp[0]) : 1.0f;
+    TO* out = reinterpret_cast<TO*>(p.out);
+    uint32_t tile_it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
+      const TileCoord tc = tile_coord(t, group, p);
+      const int acc = tile_it % TC_ACC_STAGES;
+      const uint32_t acc_round = tile_it / TC_ACC_STAGES;
+      mbar_wait(&tmem_full_bar[acc], acc_round & 1u);
+      tc_fence_after();
+      const int b = tc.m_blk * TC_BLOCK_M + quad * 32 + lane;
+      const int c_base = tc.n_blk * TC_BLOCK_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * TC_BLOCK_N;
+      const float* bias_row = p.bias ? p.bias + (size_t)tc.s * p.C : nullptr;
+      TO* out_row = out + ((size_t)tc.s * p.B + (b < p.B ? b : 0)) * p.C;
+#pragma unroll 1
+      for (int chunk = 0; chunk < TC_BLOCK_N / 32; ++chunk) {
+        const int c0 = c_base + chunk * 32;
+        if (c0 >= p.C) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + (uint32_t)chunk * 32, r);
+        tmem_ld_wait();
+        if (b < p.B) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(r[j]);
+            if (bias_row && c0 + j < p.C) v[j] += __ldg(bias_row + c0 + j);
+            if (p.log_temp) v[j] *= scale;
+          }
+          const bool full = (c0 + 32 <= p.C);
+          if (sizeof(TO) == 4) {
+            float* o = reinterpret_cast<float*>(out_row) + c0;
+            if (full && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < 32 && c0 + j < p.C; ++j) o[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_row) + c0;
+            if (full && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(o + j) = pk;
+              }
+            } else {
+              for (int j = 0; j < 32 && c0 + j < p.C; ++j) o[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int last_layer_tc_supported(int S, int B, int D, int C, int in_dtype, int out_dtype, int w_layout) {
+  (void)S;
+  (void)B;
+  (void)out_dtype;
+  if (in_dtype != FB200_BF16 || w_layout != FB200_W_SCD) return 0;
+  if (D % 8 != 0 || D < TC_BLOCK_K) return 0;  // TMA needs 16-byte global strides
+  if (C < 8) return 0;
+  return 1;
+}
+
+int last_layer_tc_launch(const void* x, const void* w, const float* bias, const float* log_temp, void* out, int S,
+                         int B, int D, int C, int out_dtype, cudaStream_t st) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return FB200_E_UNSUPPORTED;
+  if (!fb200_aligned16(x) || !fb200_aligned16(w)) return FB200_E_ALIGN;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)B};
+    cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+    cuuint32_t box[2] = {TC_BLOCK_K, TC_BLOCK_M};
+    cuuint32_t el[2] = {1, 1};
+    CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, el,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return FB200_E_UNSUPPORTED;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)C, (cuuint64_t)S};
+    cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)D * 2 * (cuuint64_t)C};
+    cuuint32_t box[3] = {TC_BLOCK_K, TC_BLOCK_N, 1};
+    cuuint32_t el[3] = {1, 1, 1};
+    CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, el,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return FB200_E_UNSUPPORTED;
+  }
+  TcParams p{};
+  p.bias = bias;
+  p.log_temp = log_temp;
+  p.out = out;
+  p.S = S;
+  p.B = B;
+  p.D = D;
+  p.C = C;
+  p.m_blocks = (B + TC_BLOCK_M - 1) / TC_BLOCK_M;
+  p.n_blocks = (C + TC_BLOCK_N - 1) / TC_BLOCK_N;
+  p.k_blocks = (D + TC_BLOCK_K - 1) / TC_BLOCK_K;
+  const long long total = (long long)p.m_blocks * p.n_blocks * S;
+  if (total > 0x7FFFFFFFll) return FB200_E_UNSUPPORTED;
+  p.total_tiles = (int)total;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  cudaError_t e;
+  if (out_dtype == FB200_F32) {
+    e = cudaFuncSetAttribute(last_layer_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)TC_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    last_layer_tc_kernel<float><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, p);
+  } else {
+    e = cudaFuncSetAttribute(last_layer_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)TC_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    last_layer_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, p);
+  }
+  FB200_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace fb200

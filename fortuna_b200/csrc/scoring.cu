@@ -99,7 +99,160 @@ __global__ void __launch_bounds__(256) row_sort_cumsum_kernel(const RowSortArgs 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-per-row variant for C <= 1024: the 64-bit keys live in registers (NR per lane, logical position
+// e = lane * NR + r), so 2/3 of the bitonic network is register-to-register compare-exchange and only the
+// strides >= NR cross lanes (shfl.xor).  Keys are stored complemented so an ASCENDING network yields the
+// descending (prob, class) order; padding keys are all-ones and sort to the end.  The prefix sum is then
+// taken lane by lane in rank order (float32, sequential), each lane receiving the running total of the
+// previous lanes, and un-permuted through a 4 KB shared-memory row so the global store is coalesced.
+// ------------------------------------------------------------------------------------------------
+template <int NR>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[NR], int lane) {
+  constexpr int N = 32 * NR;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= NR) {
+        // partner lives in lane ^ (j / NR), same register
+        const int lmask = j / NR;
+        const bool upper = (lane & lmask) != 0;
+        // ascending block iff (e & k) == 0; k >= 2 * j >= 2 * NR so the bit is a lane bit (or beyond: final pass)
+        const bool asc = (k >= N) ? true : ((lane & (k / NR)) == 0);
+        const bool keep_min = (asc != upper);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[r], lmask);
+          const bool lt = key[r] < other;
+          key[r] = (lt == keep_min) ? key[r] : other;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          if ((r & j) == 0) {
+            const int r2 = r | j;
+            bool asc;
+            if (k < NR) asc = ((r & k) == 0);
+            else asc = (k >= N) ? true : ((lane & (k / NR)) == 0);
+            const unsigned long long a0 = key[r], a1 = key[r2];
+            const bool sw = (a0 > a1) == asc;
+            key[r] = sw ? a1 : a0;
+            key[r2] = sw ? a0 : a1;
+          }
+        }
+      }
+    }
+  }
+}
+
+constexpr int kSortWarps = 8;
+
+template <int NR, int MODE>  // MODE 0: all-class scores (+perm); 1: target score; 2: credible sets (+perm)
+__global__ void __launch_bounds__(kSortWarps * 32) row_sort_warp_kernel(const RowSortArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int C = a.C;
+  float* unperm = reinterpret_cast<float*>(smem_raw) + (size_t)warp_in_cta * (32 * NR);
+  const int nwarps = gridDim.x * kSortWarps;
+  for (int b = blockIdx.x * kSortWarps + warp_in_cta; b < a.B; b += nwarps) {
+    const float* row = a.probs + (size_t)b * C;
+    unsigned long long key[NR];
+    // coalesced load; the initial arrangement is irrelevant to the sort (the class index rides in the key)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int c = r * 32 + lane;
+      unsigned long long k = ~0ull;
+      if (c < C) {
+        const float p = row[c] + 0.0f;  // -0 -> +0
+        k = ~(((unsigned long long)f32_ordered(p) << 32) | (unsigned)c);
+      }
+      key[r] = k;
+    }
+    warp_bitonic_sort<NR>(key, lane);
+    // rank of key[r] is lane * NR + r
+    const int y = (MODE == 1 && a.targets) ? a.targets[b] : -1;
+    float carry = 0.0f;
+    float ys = CUDART_NAN_F;
+    int first = 0x7FFFFFFF;
+    const int n_lanes = (C + NR - 1) / NR;
+#pragma unroll 1
+    for (int l = 0; l < n_lanes; ++l) {
+      if (lane == l) {
+        float run = carry;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const unsigned long long kk = ~key[r];
+          const float p = f32_unordered((uint32_t)(kk >> 32));
+          if (l * NR + r < C) {
+            run += p;
+            if (MODE == 1 && (int)(kk & 0xFFFFFFFFull) == y) ys = run;
+            if (MODE == 2 && first == 0x7FFFFFFF && run > a.set_threshold) first = l * NR + r;
+          }
+          // from here on the register pair holds (prefix sum bits, class) instead of the sort key
+          key[r] = ((unsigned long long)__float_as_uint(run) << 32) | (kk & 0xFFFFFFFFull);
+        }
+        carry = run;
+      }
+      carry = __shfl_sync(0xffffffffu, carry, l);
+    }
+    if (MODE == 1) {
+      // exactly one lane saw the target
+      const unsigned m = __ballot_sync(0xffffffffu, ys == ys);
+      if (m) {
+        const int src = __ffs(m) - 1;
+        ys = __shfl_sync(0xffffffffu, ys, src);
+      }
+      if (lane == 0 && a.scores) a.scores[b] = ys;
+    }
+    if (MODE == 2) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+      if (lane == 0 && a.set_size) a.set_size[b] = (first == 0x7FFFFFFF ? 0 : first) + 1;
+    }
+    if (MODE == 0 && a.scores) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int idx = (int)(key[r] & 0xFFFFFFFFull);
+        if (lane * NR + r < C) unperm[idx] = __uint_as_float((uint32_t)(key[r] >> 32));
+      }
+      __syncwarp();
+      float* orow = a.scores + (size_t)b * C;
+      for (int c = lane; c < C; c += 32) orow[c] = unperm[c];
+      __syncwarp();
+    }
+    if (a.perm) {
+      int32_t* prow = a.perm + (size_t)b * C;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int rank = lane * NR + r;
+        if (rank < C) prow[rank] = (int)(key[r] & 0xFFFFFFFFull);
+      }
+    }
+  }
+}
+
+template <int NR>
+static int launch_row_sort_warp(const RowSortArgs& a, cudaStream_t st) {
+  const int mode = a.set_size ? 2 : (a.targets ? 1 : 0);
+  const size_t smem = mode == 0 ? (size_t)kSortWarps * 32 * NR * sizeof(float) : 0;
+  int grid = (a.B + kSortWarps - 1) / kSortWarps;
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (mode == 0) row_sort_warp_kernel<NR, 0><<<grid, kSortWarps * 32, smem, st>>>(a);
+  else if (mode == 1) row_sort_warp_kernel<NR, 1><<<grid, kSortWarps * 32, smem, st>>>(a);
+  else row_sort_warp_kernel<NR, 2><<<grid, kSortWarps * 32, smem, st>>>(a);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
 static int launch_row_sort(RowSortArgs a, cudaStream_t st) {
+  if (a.C <= 32) return launch_row_sort_warp<1>(a, st);
+  if (a.C <= 64) return launch_row_sort_warp<2>(a, st);
+  if (a.C <= 128) return launch_row_sort_warp<4>(a, st);
+  if (a.C <= 256) return launch_row_sort_warp<8>(a, st);
+  if (a.C <= 512) return launch_row_sort_warp<16>(a, st);
+  if (a.C <= 1024) return launch_row_sort_warp<32>(a, st);
   int n2 = 1;
   while (n2 < a.C) n2 <<= 1;
   a.N2 = n2;
@@ -262,21 +415,50 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
   const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
-  for (int b0 = warp * 32; b0 < B; b0 += nwarps * 32) {
-    // each warp handles 32 consecutive rows; lane `r` ends up owning row b0 + r
-    float my_conf = 0.0f;
-    int my_pred = 0;
-    float my_brier = 0.0f;
-    if (C == 1) {
-      const int b = b0 + lane;
-      if (b < B) my_conf = probs[b];
-    } else {
-      for (int r = 0; r < 32 && b0 + r < B; ++r) {
-        const float* row = probs + (size_t)(b0 + r) * C;
-        const int y = targets ? targets[b0 + r] : -1;
-        float best = -CUDART_INF_F;
-        int best_c = 0x7FFFFFFF;
-        float sq = 0.0f;
+  if (C == 1) {
+    // confidences given directly: one thread per data point
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+      const float conf = probs[b];
+      int bin = -1;
+      for (int i = 0; i < n_bins; ++i) {
+        if (conf <= thr[i]) {
+          bin = i;
+          break;
+        }
+      }
+      if (bin_idx) bin_idx[b] = bin;
+      const bool ok = targets && targets[b] == preds[b];
+      if (bin >= 0) {
+        atomicAdd(&s_counts[bin], 1);
+        atomicAdd(&s_conf[bin], conf);
+        if (ok) atomicAdd(&s_correct[bin], 1);
+      }
+      if (ok) atomicAdd(&s_ncorrect, 1);
+    }
+  } else {
+    // one warp per row: max / first-argmax / Brier term by shuffle reduction, lane 0 bins the row
+    for (int b = warp; b < B; b += nwarps) {
+      const float* row = probs + (size_t)b * C;
+      const int y = targets ? targets[b] : -1;
+      float best = -CUDART_INF_F;
+      int best_c = 0x7FFFFFFF;
+      float sq = 0.0f;
+      if ((C & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
+        for (int c = lane * 4; c < C; c += 128) {
+          const float4 v = *reinterpret_cast<const float4*>(row + c);
+          const float pv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (pv[k] > best) {
+              best = pv[k];
+              best_c = c + k;
+            }
+            const float d = pv[k] - ((c + k) == y ? 1.0f : 0.0f);
+            sq = fmaf(d, d, sq);
+          }
+        }
+      } else {
         for (int c = lane; c < C; c += 32) {
           const float p = row[c];
           if (p > best) {
@@ -286,41 +468,36 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
           const float d = p - (c == y ? 1.0f : 0.0f);
           sq = fmaf(d, d, sq);
         }
+      }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-          const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-          sq += __shfl_xor_sync(0xffffffffu, sq, o);
-          if (ov > best || (ov == best && oc < best_c)) {
-            best = ov;
-            best_c = oc;
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (ov > best || (ov == best && oc < best_c)) {
+          best = ov;
+          best_c = oc;
+        }
+      }
+      if (lane == 0) {
+        const int pred = preds ? preds[b] : (best_c == 0x7FFFFFFF ? 0 : best_c);
+        int bin = -1;
+        for (int i = 0; i < n_bins; ++i) {
+          if (best <= thr[i]) {
+            bin = i;
+            break;
           }
         }
-        if (lane == r) {
-          my_conf = best;
-          my_pred = best_c == 0x7FFFFFFF ? 0 : best_c;
-          my_brier = sq;
+        if (bin_idx) bin_idx[b] = bin;
+        const bool ok = targets && y == pred;
+        if (bin >= 0) {
+          atomicAdd(&s_counts[bin], 1);
+          atomicAdd(&s_conf[bin], best);
+          if (ok) atomicAdd(&s_correct[bin], 1);
         }
+        if (ok) atomicAdd(&s_ncorrect, 1);
+        if (targets) atomicAdd(&s_brier, sq);
       }
-    }
-    const int b = b0 + lane;
-    if (b < B) {
-      const int pred = preds ? preds[b] : my_pred;
-      int bin = -1;
-      for (int i = 0; i < n_bins; ++i) {
-        if (my_conf <= thr[i]) {
-          bin = i;
-          break;
-        }
-      }
-      if (bin_idx) bin_idx[b] = bin;
-      if (bin >= 0) {
-        atomicAdd(&s_counts[bin], 1);
-        atomicAdd(&s_conf[bin], my_conf);
-        if (targets && targets[b] == pred) atomicAdd(&s_correct[bin], 1);
-      }
-      if (targets && targets[b] == pred) atomicAdd(&s_ncorrect, 1);  // accuracy counts every row
-      if (C > 1 && targets) atomicAdd(&s_brier, my_brier);
     }
   }
   __syncthreads();
@@ -505,7 +682,7 @@ extern "C" int fb200_ece_bins(const float* probs, int B, int C, const int32_t* p
   if ((e = cudaMemsetAsync(correct, 0, sizeof(int32_t) * n_bins, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(conf_sums, 0, sizeof(float) * n_bins, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(result, 0, sizeof(float) * 4, st)) != cudaSuccess) return (int)e;
-  int64_t blocks = ((int64_t)B + 255) / 256;
+  int64_t blocks = C == 1 ? ((int64_t)B + 255) / 256 : ((int64_t)B + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ece_bins_kernel<<<(unsigned)blocks, 256, 0, st>>>(probs, B, C, preds, targets, thresholds, n_bins, bin_idx,
                                                     counts, conf_sums, correct, result);

@@ -1,0 +1,73 @@
+"""K2 tensor-core path (tcgen05 / TMEM / TMA) vs the oracle's bf16-input, wide-accumulate GEMM.
+
+north_star tolerance for the bf16 GEMM is rtol 2e-2; against an oracle fed the SAME bf16-rounded inputs
+the only difference is float32 accumulation order, so the test holds it to 2e-3 (abs floor scaled by sqrt(D)).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import predictive as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cuda, S, B, D, C, out_dtype=torch.float32, with_bias=True, with_temp=True, seed=0):
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(seed)
+    x = r.standard_normal((B, D)).astype(np.float32)
+    w = (r.standard_normal((S, D, C)) / np.sqrt(D)).astype(np.float32)
+    bias = r.standard_normal((S, C)).astype(np.float32) if with_bias else None
+    lt = np.array([0.3], dtype=np.float32) if with_temp else None
+    want = P.last_layer_logits(x, w, bias, lt, bf16_inputs=True)
+    xt = torch.from_numpy(x).to(cuda).to(torch.bfloat16)
+    wt = ops.transpose_w_bf16(torch.from_numpy(w).to(cuda))  # [S, C, D] bf16, K-major
+    np.testing.assert_array_equal(
+        wt.float().cpu().numpy(), np.transpose(P.round_to_bf16(w), (0, 2, 1)), err_msg="transpose_w_bf16"
+    )
+    out = ops.last_layer_logits(
+        xt, wt,
+        torch.from_numpy(bias).to(cuda) if with_bias else None,
+        torch.from_numpy(lt).to(cuda) if with_temp else None,
+        out_dtype=out_dtype, w_layout=ops.W_SCD, path=2,
+    )
+    torch.cuda.synchronize()
+    got = out.float().cpu().numpy()
+    tol = 2e-3 if out_dtype == torch.float32 else 1e-2
+    np.testing.assert_allclose(got, want, rtol=tol, atol=tol * np.sqrt(D) / 8)
+    return got, want
+
+
+@pytest.mark.parametrize(
+    "S,B,D,C",
+    [(1, 128, 64, 256), (2, 300, 128, 1000), (3, 129, 512, 10), (2, 1000, 2048, 1000), (1, 77, 72, 40),
+     (5, 4096, 512, 1000)],
+)
+def test_tc_matches_oracle_f32_out(cuda, S, B, D, C):
+    _run(cuda, S, B, D, C)
+
+
+def test_tc_bf16_out_no_bias_no_temp(cuda):
+    _run(cuda, 2, 256, 256, 512, out_dtype=torch.bfloat16, with_bias=False, with_temp=False)
+
+
+def test_tc_equals_cuda_core_path(cuda):
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(3)
+    S, B, D, C = 2, 200, 192, 300
+    xt = torch.from_numpy(r.standard_normal((B, D)).astype(np.float32)).to(cuda).to(torch.bfloat16)
+    wt = torch.from_numpy((r.standard_normal((S, C, D)) / 14).astype(np.float32)).to(cuda).to(torch.bfloat16)
+    a = ops.last_layer_logits(xt, wt, w_layout=ops.W_SCD, path=1)
+    b = ops.last_layer_logits(xt, wt, w_layout=ops.W_SCD, path=2)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_tc_rejects_unsupported(cuda):
+    from fortuna_b200 import _lib, ops
+
+    x = torch.zeros((8, 64), dtype=torch.float32, device=cuda)
+    w = torch.zeros((1, 64, 16), dtype=torch.float32, device=cuda)
+    with pytest.raises(_lib.FortunaB200Error):
+        ops.last_layer_logits(x, w, path=2)  # float32 / [S,D,C] layout is not a tensor-core shape

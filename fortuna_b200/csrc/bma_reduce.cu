@@ -22,9 +22,13 @@
 
 namespace fb200 {
 
-constexpr int kConsumerWarps = 8;
-constexpr int kReduceThreads = (kConsumerWarps + 1) * 32;
+constexpr int kConsumerWarps = 8;                          // warpgroups 0 and 1
+constexpr int kReduceThreads = (kConsumerWarps + 4) * 32;  // + one producer warpgroup (one lane of it works)
 constexpr int kMaxStages = 8;
+// 384 threads cap ptxas at 168 registers/thread; the producer warpgroup gives most of its share back
+// (setmaxnreg.dec) and the consumer warpgroups take it (setmaxnreg.inc): 8*32*232 + 4*32*40 = 64512 = 384*168.
+constexpr int kConsumerRegs = 232;
+constexpr int kProducerRegs = 40;
 
 struct ClsArgs {
   const void* logits;
@@ -82,6 +86,100 @@ __device__ __forceinline__ float rcp_approx_ftz(float x) {
   return y;
 }
 
+
+// Process RI rows (consecutive samples s of the same input b) held in shared memory: softmax of each row,
+// accumulate sum_s p, p^2, p(1-p) and the entropy partials.  The RI rows are independent until the final
+// accumulation, so their shuffle reductions and MUFU chains overlap (ILP); accumulation keeps the s order.
+template <typename T, int G, int NV, int VEC, bool TAILONLY, int RI>
+__device__ __forceinline__ void process_rows(const T* const (&rowp)[RI], int g, int C, float k2,
+                                             float (&sp)[NV][VEC], float (&sp2)[NV][VEC], float (&spq)[NV][VEC],
+                                             float& spl, float& sum_l, float (&cshift)[RI], float (&l2sum)[RI]) {
+  float z[RI][NV][VEC];
+  float m[RI];
+  // pass A: rows -> registers (padding lanes get -1e30: finite even after the log2(e)*scale multiply, so
+  // 0 * u is never NaN for them, while a genuine -inf logit still yields the reference's 0 * -inf = NaN)
+#pragma unroll
+  for (int ri = 0; ri < RI; ++ri) {
+    float pm[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) pm[k] = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c0 = (g + G * j) * VEC;
+      if (TAILONLY && j < NV - 1) {
+        RowLoad<T, VEC>::load(rowp[ri] + c0, z[ri][j]);  // every lane's chunk is inside the row
+      } else if (c0 < C) {
+        RowLoad<T, VEC>::load(rowp[ri] + c0, z[ri][j]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) z[ri][j][k] = -1.0e30f;
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) pm[k] = fmaxf(pm[k], z[ri][j][k]);
+    }
+    m[ri] = pm[0];
+#pragma unroll
+    for (int k = 1; k < VEC; ++k) m[ri] = fmaxf(m[ri], pm[k]);
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int ri = 0; ri < RI; ++ri) m[ri] = fmaxf(m[ri], __shfl_xor_sync(0xffffffffu, m[ri], o));
+  // pass B, in log2 units: u = z*k2 - c with c = fl(max*k2) (one FFMA; the rounding of c is a row constant
+  // and cancels in p = e/sum), e = 2^u (MUFU.EX2), row sum, and sum_c e*u for the entropy:
+  //   sum_c p ln p = ln2 * ( (sum_c e u) / sum - log2(sum) )
+  float sum[RI], set[RI];
+#pragma unroll
+  for (int ri = 0; ri < RI; ++ri) {
+    // jsp.special.logsumexp replaces a non-finite max by 0 (m is the max of the raw logits here)
+    const float ms = (fabsf(m[ri]) <= 3.4028234e38f) ? m[ri] : 0.0f;
+    cshift[ri] = ms * k2;
+    float psum[VEC], pset[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) psum[k] = pset[k] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float u = fmaf(z[ri][j][k], k2, -cshift[ri]);
+        const float ev = ex2_approx_ftz(u);
+        z[ri][j][k] = ev;
+        psum[k] += ev;
+        pset[k] = fmaf(ev, u, pset[k]);
+      }
+    }
+    sum[ri] = psum[0];
+    set[ri] = pset[0];
+#pragma unroll
+    for (int k = 1; k < VEC; ++k) {
+      sum[ri] += psum[k];
+      set[ri] += pset[k];
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int ri = 0; ri < RI; ++ri) sum[ri] += __shfl_xor_sync(0xffffffffu, sum[ri], o);
+  // pass C: p = e / sum, accumulate in sample order
+#pragma unroll
+  for (int ri = 0; ri < RI; ++ri) {
+    const float inv = rcp_approx_ftz(sum[ri]);
+    l2sum[ri] = lg2_approx(sum[ri]);
+    spl = fmaf(inv, set[ri], spl);  // lane-partial of sum_c p u (log2 units); -log2(sum) is row-uniform
+    sum_l += l2sum[ri];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float p = z[ri][j][k] * inv;
+        sp[j][k] += p;
+        sp2[j][k] = fmaf(p, p, sp2[j][k]);
+        spq[j][k] = fmaf(p, 1.0f - p, spq[j][k]);
+      }
+    }
+  }
+}
+
 template <typename T, int G, int NV, int VEC, bool TAILONLY>
 __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const ClsArgs a) {
   constexpr int R = 32 / G;                 // rows per warp
@@ -106,8 +204,10 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
 
   const int n_chunks = (S + a.ss - 1) / a.ss;  // pipeline steps per tile
 
-  if (warp == kConsumerWarps) {
-    // ------------------------------------------------------------------ producer warp
+  if (warp >= kConsumerWarps) {
+    // ------------------------------------------------------------------ producer warpgroup (warp 8 works)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+    if (warp != kConsumerWarps) return;
     const T* base = reinterpret_cast<const T*>(a.logits);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -147,6 +247,7 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
   }
 
   // -------------------------------------------------------------------- consumer warps
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
   const int gr = lane / G;
   const int g = lane % G;
   const int row = warp * R + gr;
@@ -177,93 +278,43 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
       const int s0 = ch * a.ss;
       const int ns = min(a.ss, S - s0);
       const unsigned char* sbase = stages + (size_t)stage * a.stage_bytes;
-      for (int q = 0; q < ns; ++q) {
-        const T* rowp = reinterpret_cast<const T*>(sbase + (size_t)q * a.tile_stride_bytes) + (size_t)row * C;
-        // pass A: row -> registers (padding lanes get -1e30: finite even after the log2(e)*scale multiply, so 0 * u is never NaN for them,
-        // while a genuine -inf logit still yields the reference's 0 * -inf = NaN), row max
-        float z[NV][VEC];
-        float pm[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) pm[k] = -CUDART_INF_F;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const int c0 = (g + G * j) * VEC;
-          if (TAILONLY && j < NV - 1) {
-            RowLoad<T, VEC>::load(rowp + c0, z[j]);  // every lane's chunk is inside the row
-          } else if (c0 < C) {
-            RowLoad<T, VEC>::load(rowp + c0, z[j]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) z[j][k] = -1.0e30f;
-          }
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) pm[k] = fmaxf(pm[k], z[j][k]);
+      auto log_prob_update = [&](const T* rp, float csh, float l2s, int s_idx) {
+        float zt = 0.0f;
+        if (y_ok) {
+          float tmp[1];
+          RowLoad<T, 1>::load(rp + y, tmp);
+          zt = tmp[0];
         }
-        float m = pm[0];
-#pragma unroll
-        for (int k = 1; k < VEC; ++k) m = fmaxf(m, pm[k]);
-        m = group_max<G>(m);
-        // jsp.special.logsumexp replaces a non-finite max by 0 (m is the max of the raw logits here)
-        const float ms = (fabsf(m) <= 3.4028234e38f) ? m : 0.0f;
-        // pass B, in log2 units: u = z*log2(e) - c with c = fl(ms*log2(e)) (one FFMA; the rounding of c is a
-        // row constant and cancels in p = e/sum), e = 2^u (MUFU.EX2), row sum, and sum_c e*u for the entropy:
-        //   sum_c p ln p = ln2 * ( (sum_c e u) / sum - log2(sum) )
-        const float cshift = ms * k2;
-        float psum[VEC], pset[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) psum[k] = pset[k] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            const float u = fmaf(z[j][k], k2, -cshift);
-            const float ev = ex2_approx_ftz(u);
-            z[j][k] = ev;
-            psum[k] += ev;
-            pset[k] = fmaf(ev, u, pset[k]);
-          }
+        // ll = z_y - logsumexp = ln2 * (u_y - log2(sum))
+        const float ll = 0.6931471805599453f * (fmaf(zt, k2, -csh) - l2s);
+        if (ll > lmax) {
+          lsum = lsum * __expf(lmax - ll) + 1.0f;
+          lmax = ll;
+        } else if (ll > -CUDART_INF_F) {
+          lsum += __expf(ll - lmax);
+        } else if (ll != ll) {
+          lsum = ll;  // NaN propagates like the reference's logsumexp
         }
-        float sum = psum[0], set = pset[0];
-#pragma unroll
-        for (int k = 1; k < VEC; ++k) {
-          sum += psum[k];
-          set += pset[k];
-        }
-        sum = group_sum<G>(sum);
-        const float inv = rcp_approx_ftz(sum);
-        const float l2sum = lg2_approx(sum);
-        spl = fmaf(inv, set, spl);  // lane-partial of sum_c p u (log2 units); the -log2(sum) part is row-uniform
-        sum_l += l2sum;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            const float p = z[j][k] * inv;
-            sp[j][k] += p;
-            sp2[j][k] = fmaf(p, p, sp2[j][k]);
-            spq[j][k] = fmaf(p, 1.0f - p, spq[j][k]);
-          }
-        }
+        if (a.out.ensemble_log_prob && valid_row && g == 0) a.out.ensemble_log_prob[(size_t)s_idx * B + b] = ll;
+      };
+      int q = 0;
+      for (; q + 1 < ns; q += 2) {
+        const T* rp[2];
+        rp[0] = reinterpret_cast<const T*>(sbase + (size_t)q * a.tile_stride_bytes) + (size_t)row * C;
+        rp[1] = reinterpret_cast<const T*>(sbase + (size_t)(q + 1) * a.tile_stride_bytes) + (size_t)row * C;
+        float csh[2], l2s[2];
+        process_rows<T, G, NV, VEC, TAILONLY, 2>(rp, g, C, k2, sp, sp2, spq, spl, sum_l, csh, l2s);
         if (a.targets) {
-          float zt = 0.0f;
-          if (y_ok) {
-            float tmp[1];
-            RowLoad<T, 1>::load(rowp + y, tmp);
-            zt = tmp[0];
-          }
-          // ll = z_y - logsumexp = ln2 * (u_y - log2(sum))
-          const float ll = 0.6931471805599453f * (fmaf(zt, k2, -cshift) - l2sum);
-          if (ll > lmax) {
-            lsum = lsum * __expf(lmax - ll) + 1.0f;
-            lmax = ll;
-          } else if (ll > -CUDART_INF_F) {
-            lsum += __expf(ll - lmax);
-          } else if (ll != ll) {
-            lsum = ll;  // NaN propagates like the reference's logsumexp
-          }
-          if (a.out.ensemble_log_prob && valid_row && g == 0)
-            a.out.ensemble_log_prob[(size_t)(s0 + q) * B + b] = ll;
+          log_prob_update(rp[0], csh[0], l2s[0], s0 + q);
+          log_prob_update(rp[1], csh[1], l2s[1], s0 + q + 1);
         }
+      }
+      if (q < ns) {
+        const T* rp[1];
+        rp[0] = reinterpret_cast<const T*>(sbase + (size_t)q * a.tile_stride_bytes) + (size_t)row * C;
+        float csh[1], l2s[1];
+        process_rows<T, G, NV, VEC, TAILONLY, 1>(rp, g, C, k2, sp, sp2, spq, spl, sum_l, csh, l2s);
+        if (a.targets) log_prob_update(rp[0], csh[0], l2s[0], s0 + q);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -506,12 +557,12 @@ static int launch_cls(ClsArgs a, cudaStream_t st) {
   a.tile_stride_bytes = (tile_bytes + 15u) & ~15u;
   // aim for >= 16 KB per stage so a handful of stages covers the HBM latency-bandwidth product
   int ss = (int)(16384u / a.tile_stride_bytes);
-  if (ss < 1) ss = 1;
+  if (ss < 2) ss = 2;  // two samples per stage: the consumers interleave them for ILP
   if (ss > 16) ss = 16;
   if (ss > a.S) ss = a.S;
   a.ss = ss;
   a.stage_bytes = ((uint32_t)ss * a.tile_stride_bytes + 127u) & ~127u;
-  const uint32_t budget = 96u * 1024u;
+  const uint32_t budget = 200u * 1024u;
   int nst = (int)(budget / a.stage_bytes);
   if (nst > kMaxStages) nst = kMaxStages;
   if (nst < 2) nst = 2;

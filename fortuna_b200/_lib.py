@@ -98,6 +98,7 @@ SIGNATURES = {
     "fb200_random_bits": (_i, [_P, _i64, _P, _P]),
     "fb200_random_normal": (_i, [_P, _i64, _P, _P]),
     "fb200_sample_indices": (_i, [_P, _i, _i, _P, _P]),
+    "fb200_choice_from_keys": (_i, [_P, _i, _i, _P, _P]),
     "fb200_sgmcmc_num_tiles_host": (_i64, [C.POINTER(Leaf), _i]),
     "fb200_sgmcmc_build_tiles_host": (_i, [C.POINTER(Leaf), _i, C.POINTER(Tile), _i64]),
     "fb200_sgmcmc_step_f32": (
@@ -106,7 +107,7 @@ SIGNATURES = {
     ),
     "fb200_sgd_explore_step_f32": (_i, [_P, _P, _P, _P, _i64, C.POINTER(SgmcmcHParams), _P]),
     "fb200_bank_put_f32": (_i, [_P, _i64, _i, _P, _P]),
-    "fb200_last_layer_logits": (_i, [_P, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
+    "fb200_last_layer_logits": (_i, [_P, _P, _P, _P, _P, _i, _P, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
     "fb200_transpose_w_bf16": (_i, [_P, _i, _P, _i, _i, _i, _P]),
     "fb200_bma_reduce_cls": (
         _i,

@@ -15,8 +15,9 @@
 namespace fb200 {
 
 int last_layer_tc_supported(int S, int B, int D, int C, int in_dtype, int out_dtype, int w_layout);
-int last_layer_tc_launch(const void* x, const void* w, const float* bias, const float* log_temp, void* out, int S,
-                         int B, int D, int C, int out_dtype, cudaStream_t st);
+int last_layer_tc_launch(const void* x, const void* w, const float* bias, const float* log_temp,
+                         const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
+                         int out_dtype, cudaStream_t st);
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
@@ -29,6 +30,7 @@ template <typename TI, typename TO, int WL>
 __global__ void __launch_bounds__(256) last_layer_simt_kernel(const TI* __restrict__ x, const TI* __restrict__ w,
                                                               const float* __restrict__ bias,
                                                               const float* __restrict__ log_temp,
+                                                              const int32_t* __restrict__ sample_idx,
                                                               TO* __restrict__ out, int S, int B, int D, int C) {
   __shared__ float As[kBK][kBM + 4];
   __shared__ float Bs[kBK][kBN + 4];
@@ -36,7 +38,8 @@ __global__ void __launch_bounds__(256) last_layer_simt_kernel(const TI* __restri
   const int b0 = blockIdx.y * kBM;
   const int c0 = blockIdx.x * kBN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const TI* ws = w + (size_t)s * D * C;
+  const int sw = sample_idx ? sample_idx[s] : s;  // which stored posterior sample this output row uses
+  const TI* ws = w + (size_t)sw * D * C;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) last_layer_simt_kernel(const TI* __restri
       const int c = c0 + tx * 4 + j;
       if (c >= C) continue;
       float v = acc[i][j];
-      if (bias) v += bias[(size_t)s * C + c];
+      if (bias) v += bias[(size_t)sw * C + c];
       if (log_temp) v *= scale;
       store_out(out + ((size_t)s * B + b) * C + c, v);
     }
@@ -124,18 +127,19 @@ __global__ void __launch_bounds__(256) transpose_w_kernel(const TI* __restrict__
 }
 
 template <typename TI, typename TO>
-static int launch_simt(const void* x, const void* w, const float* bias, const float* log_temp, void* out, int S,
-                       int B, int D, int C, int w_layout, cudaStream_t st) {
+static int launch_simt(const void* x, const void* w, const float* bias, const float* log_temp,
+                       const int32_t* sample_idx, void* out, int S, int B, int D, int C, int w_layout,
+                       cudaStream_t st) {
   dim3 grid((C + kBN - 1) / kBN, (B + kBM - 1) / kBM, S);
   if (grid.y > 65535 || grid.z > 65535) return FB200_E_UNSUPPORTED;
   if (w_layout == FB200_W_SDC)
     last_layer_simt_kernel<TI, TO, FB200_W_SDC><<<grid, 256, 0, st>>>(
-        reinterpret_cast<const TI*>(x), reinterpret_cast<const TI*>(w), bias, log_temp, reinterpret_cast<TO*>(out),
-        S, B, D, C);
+        reinterpret_cast<const TI*>(x), reinterpret_cast<const TI*>(w), bias, log_temp, sample_idx,
+        reinterpret_cast<TO*>(out), S, B, D, C);
   else
     last_layer_simt_kernel<TI, TO, FB200_W_SCD><<<grid, 256, 0, st>>>(
-        reinterpret_cast<const TI*>(x), reinterpret_cast<const TI*>(w), bias, log_temp, reinterpret_cast<TO*>(out),
-        S, B, D, C);
+        reinterpret_cast<const TI*>(x), reinterpret_cast<const TI*>(w), bias, log_temp, sample_idx,
+        reinterpret_cast<TO*>(out), S, B, D, C);
   FB200_LAUNCH_CHECK();
   return 0;
 }
@@ -145,10 +149,11 @@ static int launch_simt(const void* x, const void* w, const float* bias, const fl
 using namespace fb200;
 
 extern "C" int fb200_last_layer_logits(const void* x, const void* w, const float* bias, const float* log_temp,
-                                       void* out, int S, int B, int D, int C, int in_dtype, int out_dtype,
-                                       int w_layout, int path, void* stream) {
+                                       const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D,
+                                       int C, int in_dtype, int out_dtype, int w_layout, int path, void* stream) {
   if (!x || !w || !out) return FB200_E_NULL;
-  if (S <= 0 || B <= 0 || D <= 0 || C <= 0) return FB200_E_SHAPE;
+  if (S <= 0 || B <= 0 || D <= 0 || C <= 0 || n_stored <= 0) return FB200_E_SHAPE;
+  if (!sample_idx && n_stored != S) return FB200_E_SHAPE;
   if ((in_dtype != FB200_F32 && in_dtype != FB200_BF16) || (out_dtype != FB200_F32 && out_dtype != FB200_BF16))
     return FB200_E_UNSUPPORTED;
   if (w_layout != FB200_W_SDC && w_layout != FB200_W_SCD) return FB200_E_UNSUPPORTED;
@@ -158,14 +163,14 @@ extern "C" int fb200_last_layer_logits(const void* x, const void* w, const float
   if (path == 2 && !tc_ok) return FB200_E_UNSUPPORTED;
   // auto: tensor cores only when the contraction is large enough to be compute-bound (D >= 256, C >= 64)
   const bool use_tc = path == 2 || (path == 0 && tc_ok && D >= 256 && C >= 64 && B >= 128);
-  if (use_tc) return last_layer_tc_launch(x, w, bias, log_temp, out, S, B, D, C, out_dtype, st);
+  if (use_tc) return last_layer_tc_launch(x, w, bias, log_temp, sample_idx, n_stored, out, S, B, D, C, out_dtype, st);
   if (in_dtype == FB200_F32) {
-    if (out_dtype == FB200_F32) return launch_simt<float, float>(x, w, bias, log_temp, out, S, B, D, C, w_layout, st);
-    return launch_simt<float, __nv_bfloat16>(x, w, bias, log_temp, out, S, B, D, C, w_layout, st);
+    if (out_dtype == FB200_F32) return launch_simt<float, float>(x, w, bias, log_temp, sample_idx, out, S, B, D, C, w_layout, st);
+    return launch_simt<float, __nv_bfloat16>(x, w, bias, log_temp, sample_idx, out, S, B, D, C, w_layout, st);
   }
   if (out_dtype == FB200_F32)
-    return launch_simt<__nv_bfloat16, float>(x, w, bias, log_temp, out, S, B, D, C, w_layout, st);
-  return launch_simt<__nv_bfloat16, __nv_bfloat16>(x, w, bias, log_temp, out, S, B, D, C, w_layout, st);
+    return launch_simt<__nv_bfloat16, float>(x, w, bias, log_temp, sample_idx, out, S, B, D, C, w_layout, st);
+  return launch_simt<__nv_bfloat16, __nv_bfloat16>(x, w, bias, log_temp, sample_idx, out, S, B, D, C, w_layout, st);
 }
 
 extern "C" int fb200_transpose_w_bf16(const void* w, int in_dtype, void* wt, int S, int D, int C, void* stream) {

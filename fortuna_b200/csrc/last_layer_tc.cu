@@ -117,6 +117,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 struct TcParams {
   const float* bias;      // [S, C] or null
   const float* log_temp;  // [1] or null
+  const int32_t* sample_idx;  // [S] or null: stored sample used by output row s
   void* out;              // [S, B, C]
   int S, B, D, C;
   int m_blocks, n_blocks, k_blocks;
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint32_t it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = tile_coord(t, group, p);
+        const int sw = p.sample_idx ? __ldg(p.sample_idx + tc.s) : tc.s;  // posterior.sample() gather, fused
         for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
           const int stage = it % TC_STAGES;
           const uint32_t round = it / TC_STAGES;
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           unsigned char* sb = sa + TC_A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
           tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * TC_BLOCK_K, tc.m_blk * TC_BLOCK_M);
-          tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * TC_BLOCK_K, tc.n_blk * TC_BLOCK_N, tc.s);
+          tma_load_3d(sb, &tmap_b, &full_bar[stage], kb * TC_BLOCK_K, tc.n_blk * TC_BLOCK_N, sw);
         }
       }
     }
@@ -243,7 +245,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int b = tc.m_blk * TC_BLOCK_M + quad * 32 + lane;
       const int c_base = tc.n_blk * TC_BLOCK_N;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * TC_BLOCK_N;
-      const float* bias_row = p.bias ? p.bias + (size_t)tc.s * p.C : nullptr;
+      const int sw = p.sample_idx ? __ldg(p.sample_idx + tc.s) : tc.s;
+      const float* bias_row = p.bias ? p.bias + (size_t)sw * p.C : nullptr;
       TO* out_row = out + ((size_t)tc.s * p.B + (b < p.B ? b : 0)) * p.C;
 #pragma unroll 1
       for (int chunk = 0; chunk < TC_BLOCK_N / 32; ++chunk) {
@@ -332,8 +335,9 @@ int last_layer_tc_supported(int S, int B, int D, int C, int in_dtype, int out_dt
   return 1;
 }
 
-int last_layer_tc_launch(const void* x, const void* w, const float* bias, const float* log_temp, void* out, int S,
-                         int B, int D, int C, int out_dtype, cudaStream_t st) {
+int last_layer_tc_launch(const void* x, const void* w, const float* bias, const float* log_temp,
+                         const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
+                         int out_dtype, cudaStream_t st) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return FB200_E_UNSUPPORTED;
   if (!fb200_aligned16(x) || !fb200_aligned16(w)) return FB200_E_ALIGN;
@@ -349,7 +353,7 @@ int last_layer_tc_launch(const void* x, const void* w, const float* bias, const 
     if (r != CUDA_SUCCESS) return FB200_E_UNSUPPORTED;
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)C, (cuuint64_t)S};
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)C, (cuuint64_t)n_stored};
     cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)D * 2 * (cuuint64_t)C};
     cuuint32_t box[3] = {TC_BLOCK_K, TC_BLOCK_N, 1};
     cuuint32_t el[3] = {1, 1, 1};
@@ -361,6 +365,7 @@ int last_layer_tc_launch(const void* x, const void* w, const float* bias, const 
   TcParams p{};
   p.bias = bias;
   p.log_temp = log_temp;
+  p.sample_idx = sample_idx;
   p.out = out;
   p.S = S;
   p.B = B;

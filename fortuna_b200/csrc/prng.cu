@@ -38,14 +38,22 @@ __global__ void fold_in_kernel(const uint32_t* __restrict__ key, uint32_t data, 
 }
 
 // jax.random.choice(keys[s], n_samples) == randint(key, (), 0, n): two 32-bit draws, multiplier trick.
+// SPLIT: key is one key and draw s uses split(key, n_draws)[s]; otherwise key is n_draws keys, one per draw.
+template <bool SPLIT>
 __global__ void __launch_bounds__(128) sample_indices_kernel(const uint32_t* __restrict__ key, uint32_t n_draws,
                                                              uint32_t span, int32_t* __restrict__ out) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_draws) return;
-  const uint32_t k0 = key[0], k1 = key[1];
-  // keys = split(key, n_draws): row s of random_bits(key, 2 * n_draws).reshape(n_draws, 2)
-  const uint32_t ks0 = random_bits_elem(k0, k1, 2u * n_draws, 2u * s);
-  const uint32_t ks1 = random_bits_elem(k0, k1, 2u * n_draws, 2u * s + 1u);
+  uint32_t ks0, ks1;
+  if (SPLIT) {
+    // keys = split(key, n_draws): row s of random_bits(key, 2 * n_draws).reshape(n_draws, 2)
+    const uint32_t k0 = key[0], k1 = key[1];
+    ks0 = random_bits_elem(k0, k1, 2u * n_draws, 2u * s);
+    ks1 = random_bits_elem(k0, k1, 2u * n_draws, 2u * s + 1u);
+  } else {
+    ks0 = key[2u * s];
+    ks1 = key[2u * s + 1u];
+  }
   // k1_, k2_ = split(keys[s]) : random_bits(keys[s], 4) = [y0(0,2), y0(1,3), y1(0,2), y1(1,3)]
   uint32_t a0 = 0u, a1 = 2u, b0 = 1u, b1 = 3u;
   threefry2x32(ks0, ks1, a0, a1);
@@ -106,8 +114,18 @@ extern "C" int fb200_sample_indices(const uint32_t* key, int n_draws, int n_samp
                                     void* stream) {
   if (!key || !out_idx) return FB200_E_NULL;
   if (n_draws <= 0 || n_samples <= 0 || n_draws >= (1 << 30)) return FB200_E_SHAPE;
-  sample_indices_kernel<<<(n_draws + 127) / 128, 128, 0, (cudaStream_t)stream>>>(key, (uint32_t)n_draws,
-                                                                                 (uint32_t)n_samples, out_idx);
+  sample_indices_kernel<true><<<(n_draws + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      key, (uint32_t)n_draws, (uint32_t)n_samples, out_idx);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_choice_from_keys(const uint32_t* keys, int n_keys, int n_samples, int32_t* out_idx,
+                                      void* stream) {
+  if (!keys || !out_idx) return FB200_E_NULL;
+  if (n_keys <= 0 || n_samples <= 0 || n_keys >= (1 << 30)) return FB200_E_SHAPE;
+  sample_indices_kernel<false><<<(n_keys + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      keys, (uint32_t)n_keys, (uint32_t)n_samples, out_idx);
   FB200_LAUNCH_CHECK();
   return 0;
 }

@@ -85,6 +85,17 @@ def sample_indices(key, n_draws, n_samples):
     return out
 
 
+def sample_indices_from_keys(keys, n_samples):
+    """keys int32[n,2] -> int32[n]: choice(keys[i], n_samples) (no split over draws)."""
+    n = keys.shape[0]
+    out = torch.empty(n, dtype=torch.int32, device=keys.device)
+    check(
+        lib().fb200_choice_from_keys(_ptr(keys, KEY_DTYPE), n, n_samples, _ptr(out), _stream()),
+        "fb200_choice_from_keys",
+    )
+    return out
+
+
 # ------------------------------------------------------------------------------------------- sampler
 def build_leaf_tables(lens, offsets, device):
     """Host leaf/tile tables -> device int tensors (leaves [L,2] int64, tiles [T,2] int32)."""
@@ -161,11 +172,13 @@ def bank_put(bank, row, src):
 
 
 # ------------------------------------------------------------------------------------------- last layer
-def last_layer_logits(x, w, bias=None, log_temp=None, out_dtype=torch.float32, w_layout=W_SDC, path=0, out=None):
-    """x [B,D], w [S,D,C] (W_SDC) or [S,C,D] (W_SCD), bias [S,C] f32 -> out [S,B,C]."""
+def last_layer_logits(x, w, bias=None, log_temp=None, out_dtype=torch.float32, w_layout=W_SDC, path=0, out=None,
+                      sample_idx=None):
+    """x [B,D], w [n,D,C] (W_SDC) or [n,C,D] (W_SCD), bias [n,C] f32 -> out [S,B,C].
+    sample_idx (int32 [S], device) selects which of the n stored samples each output row uses; None = all n."""
     if x.dtype != w.dtype:
         raise ValueError("x and w must share a dtype")
-    S = w.shape[0]
+    S = w.shape[0] if sample_idx is None else sample_idx.numel()
     B, D = x.shape
     Cn = w.shape[2] if w_layout == W_SDC else w.shape[1]
     if (w.shape[1] if w_layout == W_SDC else w.shape[2]) != D:
@@ -178,6 +191,8 @@ def last_layer_logits(x, w, bias=None, log_temp=None, out_dtype=torch.float32, w
             _ptr(w),
             _ptr(bias, torch.float32, True),
             _ptr(log_temp, torch.float32, True),
+            _ptr(sample_idx, torch.int32, True),
+            w.shape[0],
             _ptr(out, (torch.float32, torch.bfloat16)),
             S,
             B,

@@ -56,6 +56,9 @@ int fb200_random_normal(const uint32_t* key, int64_t n, float* out, void* stream
 /* out_idx[s] = jax.random.choice(split(key, n_draws)[s], n_samples) - the S posterior-sample index
  * draws of fortuna/prob_model/predictive/base.py:632 + .../sgmcmc/sgmcmc_posterior.py:51. */
 int fb200_sample_indices(const uint32_t* key, int n_draws, int n_samples, int32_t* out_idx, void* stream);
+/* out_idx[i] = jax.random.choice(keys[i], n_samples) for n_keys caller-supplied keys (uint32[n_keys][2]):
+ * the single draw of SGMCMCPosterior.sample(rng) (.../sgmcmc/sgmcmc_posterior.py:51) without the split. */
+int fb200_choice_from_keys(const uint32_t* keys, int n_keys, int n_samples, int32_t* out_idx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SG-MCMC sampler step (K1).  Replaces sghmc_integrator.update_fn
@@ -127,12 +130,16 @@ int fb200_bank_put_f32(float* bank, int64_t n, int row, const float* src, void* 
  * The tcgen05 path needs in_dtype = BF16, w_layout = SCD, D % 64 == 0 (use fb200_transpose_w_bf16 once
  * per sample bank); every other shape runs the CUDA-core path.  `path`: 0 auto, 1 force CUDA-core,
  * 2 force tcgen05 (FB200_E_UNSUPPORTED if the shape does not qualify).
+ * sample_idx: optional device int32[S]; row s of the output uses w[sample_idx[s]] / bias[sample_idx[s]] - the
+ * posterior.sample() index draw (fortuna/prob_model/posterior/sgmcmc/sgmcmc_posterior.py:48-52) fused into
+ * the contraction, so drawn samples are never gathered or copied.  NULL = identity.
+ * n_stored: number of sample rows held by w / bias (the sample bank size); must equal S when sample_idx is NULL.
  * ---------------------------------------------------------------------------------------------- */
 #define FB200_W_SDC 0
 #define FB200_W_SCD 1
-int fb200_last_layer_logits(const void* x, const void* w, const float* bias, const float* log_temp, void* out,
-                            int S, int B, int D, int C, int in_dtype, int out_dtype, int w_layout, int path,
-                            void* stream);
+int fb200_last_layer_logits(const void* x, const void* w, const float* bias, const float* log_temp,
+                            const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
+                            int in_dtype, int out_dtype, int w_layout, int path, void* stream);
 /* wt[s,c,d] (bf16) = w[s,d,c] (float32 or bf16 per in_dtype). */
 int fb200_transpose_w_bf16(const void* w, int in_dtype, void* wt, int S, int D, int C, void* stream);
 

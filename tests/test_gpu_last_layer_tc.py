@@ -71,3 +71,23 @@ def test_tc_rejects_unsupported(cuda):
     w = torch.zeros((1, 64, 16), dtype=torch.float32, device=cuda)
     with pytest.raises(_lib.FortunaB200Error):
         ops.last_layer_logits(x, w, path=2)  # float32 / [S,D,C] layout is not a tensor-core shape
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_sample_index_gather_is_fused(cuda, path):
+    """out[s] uses w[idx[s]] / bias[idx[s]] (posterior.sample() draws with replacement) on both paths."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(9)
+    n, S, B, D, C = 5, 8, 150, 128, 72
+    x = r.standard_normal((B, D)).astype(np.float32)
+    w = (r.standard_normal((n, D, C)) / np.sqrt(D)).astype(np.float32)
+    bias = r.standard_normal((n, C)).astype(np.float32)
+    idx = np.array([4, 0, 0, 3, 1, 4, 2, 2], dtype=np.int32)
+    want = P.last_layer_logits(x, w[idx], bias[idx], None, bf16_inputs=True)
+    xt = torch.from_numpy(x).to(cuda).to(torch.bfloat16)
+    wt = ops.transpose_w_bf16(torch.from_numpy(w).to(cuda))
+    out = ops.last_layer_logits(xt, wt, torch.from_numpy(bias).to(cuda), None, w_layout=ops.W_SCD, path=path,
+                                sample_idx=torch.from_numpy(idx).to(cuda))
+    assert out.shape == (S, B, C)
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=2e-3, atol=2e-3)

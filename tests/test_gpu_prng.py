@@ -65,3 +65,15 @@ def test_sample_indices_bit_exact(cuda, n_draws, n_samples):
     keys = oprng.split(oprng.PRNGKey(11), n_draws)
     want = np.array([oprng.choice(k, n_samples) for k in keys], dtype=np.int64)
     assert np.array_equal(got.astype(np.int64), want)
+
+
+@pytest.mark.parametrize("n_keys,n_samples", [(1, 10), (17, 100), (3, 1)])
+def test_choice_from_keys_bit_exact(cuda, n_keys, n_samples):
+    """posterior.sample(rng): idx = choice(rng, n_samples) with the caller's key (no split over draws)."""
+    from fortuna_b200 import ops
+
+    keys_o = oprng.split(oprng.PRNGKey(5), n_keys)
+    keys = ops.split(ops.PRNGKey(5, cuda), n_keys)
+    got = ops.sample_indices_from_keys(keys, n_samples).cpu().numpy()
+    want = np.array([oprng.choice(k, n_samples) for k in keys_o], dtype=np.int64)
+    assert np.array_equal(got.astype(np.int64), want)

@@ -1,0 +1,174 @@
+"""CUDA library (through the C ABI) vs the committed golden fixtures of tests/golden/: the external known
+answers of kat.json and the frozen seeded vectors of oracle_vectors.npz.  Bit-exact for keys, indices,
+permutations, masks, sizes and bins; rtol 1e-5 for float32 outputs (north_star tolerance)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "kat.json")))
+VEC = np.load(os.path.join(HERE, "golden", "oracle_vectors.npz"))
+
+
+def _u32(t):
+    return t.detach().cpu().numpy().view(np.uint32)
+
+
+def test_jax_documented_values(cuda):
+    from fortuna_b200 import ops
+
+    d = KAT["jax_docs"]
+    k0, k42 = ops.PRNGKey(0, cuda), ops.PRNGKey(42, cuda)
+    assert _u32(ops.split(k0)).tolist() == d["split_key0"]
+    assert _u32(ops.split(k42)).tolist() == d["split_key42"]
+    assert _u32(ops.split(k42, 3)).tolist() == d["split_key42_n3"]
+    assert _u32(ops.fold_in(k0, 1)).tolist() == d["fold_in_key0_1"]
+    np.testing.assert_allclose(ops.random_normal(k0, 1).cpu().numpy(), [d["normal_key0"]], rtol=2e-6)
+    np.testing.assert_allclose(ops.random_normal(k0, 3).cpu().numpy(), d["normal_key0_n3"], rtol=2e-6)
+    np.testing.assert_allclose(ops.random_normal(k42, 1).cpu().numpy(), [d["normal_key42"]], rtol=2e-6)
+    sub = ops.key_from_host(d["split_key42"][1], cuda)
+    np.testing.assert_allclose(ops.random_normal(sub, 1).cpu().numpy(), [d["normal_subkey42"]], rtol=2e-6)
+
+
+def test_threefry_kat_through_fold_in(cuda):
+    """fold_in(key, d) = threefry(key, (0, d)): reaches the raw block function through the ABI; the Random123
+    vectors with counter word 0 == 0 are checked directly, the rest through the oracle-pinned stream."""
+    from fortuna_b200 import ops
+
+    for v in KAT["threefry2x32"]:
+        if v["ctr"][0] != 0:
+            continue
+        key = ops.key_from_host(v["key"], cuda)
+        assert _u32(ops.fold_in(key, v["ctr"][1])).tolist() == v["out"]
+
+
+def test_reference_test_values(cuda):
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+
+    r = KAT["reference_tests"]
+    c = r["cosine_schedule"]
+    f = sched.cosine_schedule(c["init_step_size"], c["total_steps"])
+    for step, val in c["step_value"]:
+        np.testing.assert_allclose(f(step), val, rtol=1e-5, atol=1e-8)
+    c = r["constant_schedule_with_cosine_burnin"]
+    f = sched.constant_schedule_with_cosine_burnin(c["init_step_size"], c["final_step_size"], c["burnin_steps"])
+    for step, val in c["step_value"]:
+        np.testing.assert_allclose(f(step), val, rtol=1e-5, atol=1e-8)
+    c = r["cyclical_cosine_schedule_with_const_burnin"]
+    f = sched.cyclical_cosine_schedule_with_const_burnin(c["init_step_size"], c["burnin_steps"], c["cycle_length"])
+    for step, val in c["step_value"]:
+        np.testing.assert_allclose(f(step), val, rtol=1e-5, atol=1e-8)
+    for step in c["step_differs_from_init"]:
+        assert not np.allclose(f(step), c["init_step_size"])
+
+    c = r["classification_log_prob"]
+    z = torch.tensor([c["outputs"]], dtype=torch.float32, device=cuda)
+    t = torch.tensor(c["target"], dtype=torch.int32, device=cuda)
+    out = ops.bma_reduce_cls(z, ("log_prob", "ensemble_log_prob"), targets=t)
+    np.testing.assert_allclose(out["ensemble_log_prob"].cpu().numpy()[0], [c["value"]], rtol=1e-5)
+    np.testing.assert_allclose(out["log_prob"].cpu().numpy(), [c["value"]], rtol=1e-5)
+    c = r["regression_log_prob"]
+    z = torch.tensor([c["outputs"]], dtype=torch.float32, device=cuda)
+    t = torch.tensor(c["target"], dtype=torch.float32, device=cuda)
+    out = ops.bma_reduce_reg(z, ("log_prob",), targets=t)
+    np.testing.assert_allclose(out["log_prob"].cpu().numpy(), [c["value"]], rtol=1e-5)
+
+    c = r["simple_conformal_sets"]
+    vp = torch.tensor(c["val_probs"], dtype=torch.float32, device=cuda)
+    vt = torch.tensor(c["val_targets"], dtype=torch.int32, device=cuda)
+    tp = torch.tensor(c["test_probs"], dtype=torch.float32, device=cuda)
+    val = ops.sort_f32_(ops.simple_scores(vp, vt))
+    thr = np.float32((1 - c["error"]) * (len(c["val_probs"]) + 1))
+    mask, sizes = ops.conformal_sets(val, ops.simple_scores(tp, None), thr)
+    mask = mask.cpu().numpy().astype(bool)
+    for b, must in enumerate(c["must_contain"]):
+        assert all(mask[b, k] for k in must)
+
+
+def _run_sampler(cuda, kind, precond):
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+    from fortuna_b200.prob_model.posterior.sgmcmc.cyclical_sgld.cyclical_sgld_integrator import cyclical_sgld_integrator
+    from fortuna_b200.prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
+    from fortuna_b200.utils.flat_tree import FlatTree
+    from tests import trees
+
+    pre = pc.rmsprop_preconditioner() if precond == "rmsprop" else pc.identity_preconditioner()
+    if kind == "sghmc":
+        tx = sghmc_integrator(0.01, None, ops.PRNGKey(0, cuda), sched.constant_schedule(4e-6), pre)
+    else:
+        tx = cyclical_sgld_integrator(ops.PRNGKey(0, cuda), 1e-3, 4, 0.25, pre)
+    params = FlatTree.from_tree(trees.mlp_two_moons_tree(0), device=cuda)
+    state = tx.init(params)
+    for _ in range(3):
+        g = params.empty_like()
+        g.flat.copy_(params.flat * 0.5 + 0.01)  # input construction only (same rule as the fixture script)
+        params, state = tx.apply(params, g, state)
+    inner = state if kind == "sghmc" else state.sgld_state
+    flat = np.concatenate([v.cpu().numpy().ravel() for v in params.leaf_views()])
+    mom = np.concatenate([v.cpu().numpy().ravel() for v in inner.momentum.leaf_views()])
+    return flat, mom, ops.key_to_host(inner.rng_key)
+
+
+@pytest.mark.parametrize("kind", ["sghmc", "csgld"])
+@pytest.mark.parametrize("precond", ["identity", "rmsprop"])
+def test_sampler_trajectories(cuda, kind, precond):
+    flat, mom, key = _run_sampler(cuda, kind, precond)
+    assert np.array_equal(key, VEC[f"{kind}_{precond}_key"])
+    np.testing.assert_allclose(flat, VEC[f"{kind}_{precond}_params"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(mom, VEC[f"{kind}_{precond}_momentum"], rtol=1e-5, atol=1e-7)
+
+
+def test_prng_vectors(cuda):
+    from fortuna_b200 import ops
+
+    assert np.array_equal(_u32(ops.random_bits(ops.PRNGKey(7, cuda), 9)), VEC["bits_seed7_n9"])
+    np.testing.assert_allclose(ops.random_normal(ops.PRNGKey(7, cuda), 9).cpu().numpy(), VEC["normal_seed7_n9"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(ops.sample_indices(ops.PRNGKey(11, cuda), 30, 10).cpu().numpy(), VEC["choice_seed11_30of10"])
+
+
+def test_predictive_and_scoring_vectors(cuda):
+    from fortuna_b200 import ops
+
+    z = torch.from_numpy(VEC["z"]).to(cuda)
+    t = torch.from_numpy(VEC["z_targets"]).to(cuda)
+    names = ("mean", "mode", "aleatoric_variance", "epistemic_variance", "entropy", "aleatoric_entropy",
+             "epistemic_entropy", "log_prob", "ensemble_log_prob")
+    out = ops.bma_reduce_cls(z, names, targets=t)
+    assert np.array_equal(out["mode"].cpu().numpy(), VEC["mode"])
+    for n in names:
+        if n == "mode":
+            continue
+        atol = 2e-6 if "entropy" in n or "log_prob" in n else 2e-7
+        np.testing.assert_allclose(out[n].cpu().numpy(), VEC[n], rtol=1e-5, atol=atol, err_msg=n)
+
+    # scoring runs on the FIXTURE's mean so that integer outputs can be compared bit for bit
+    mean = torch.from_numpy(VEC["mean"]).to(cuda)
+    for name, probs in (("aps", mean), ("aps_ties", torch.from_numpy(VEC["tie_probs"]).to(cuda))):
+        allc, perm = ops.aps_scores(probs, None, want_perm=True)
+        assert np.array_equal(perm.cpu().numpy(), VEC[f"{name}_perm"]), name
+        assert np.array_equal(allc.cpu().numpy(), VEC[f"{name}_all"]), name
+        assert np.array_equal(ops.aps_scores(probs, t).cpu().numpy(), VEC[f"{name}_target"]), name
+    val = ops.sort_f32_(ops.aps_scores(mean, t))
+    B = mean.shape[0]
+    mask, sizes = ops.conformal_sets(val, ops.aps_scores(mean, None), np.float32((1 - 0.2) * (B + 1)))
+    assert np.array_equal(mask.cpu().numpy(), VEC["conformal_mask"])
+    assert np.array_equal(sizes.cpu().numpy(), VEC["conformal_sizes"])
+    from fortuna_b200.prob_model.predictive.pipeline import ece_thresholds
+
+    e = ops.ece_bins(mean, t, torch.from_numpy(ece_thresholds(B)).to(cuda), want_bin_idx=True)
+    assert np.array_equal(e["bin_idx"].cpu().numpy(), VEC["ece_bin_idx"])
+    assert np.array_equal(e["counts"].cpu().numpy(), VEC["ece_counts"])
+    res = e["result"].cpu().numpy()
+    np.testing.assert_allclose(res[0], VEC["ece"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(res[1], VEC["mce"], rtol=1e-5, atol=1e-7)
+    qlevel = np.float32(np.ceil(np.float32((B + 1) * (1 - 0.1))) / np.float32(B))
+    q = ops.quantile_sorted(val, torch.tensor([qlevel], dtype=torch.float32, device=cuda))
+    np.testing.assert_allclose(q.cpu().numpy()[0], VEC["quantile_err0.1"], rtol=1e-6)

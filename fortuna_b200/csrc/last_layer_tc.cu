@@ -34,7 +34,11 @@ constexpr uint32_t TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;  // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_BLOCK_N * TC_BLOCK_K * 2;  // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr uint32_t TC_TMEM_COLS = TC_ACC_STAGES * TC_BLOCK_N;  // 512
-constexpr size_t TC_SMEM_BYTES = 1024 /*align slack*/ + (size_t)TC_STAGES * TC_STAGE_BYTES + 256 /*barriers*/;
+constexpr int TC_EPI_WARPS = 4;
+constexpr uint32_t TC_OUT_BUF_BYTES = 32 * 128;  // 32 rows x 128 B: one warp's slice of a store, SWIZZLE_128B
+constexpr uint32_t TC_OUT_BYTES = TC_EPI_WARPS * 2 * TC_OUT_BUF_BYTES;  // double-buffered per epilogue warp
+constexpr size_t TC_SMEM_BYTES =
+    1024 /*align slack*/ + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_OUT_BYTES + 256 /*barriers*/;
 
 // ---------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -52,6 +56,21 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// shared -> global tile store (bulk async group); coordinates {c, b, s}, rows/columns outside the tensor are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (TMA store)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -144,14 +163,15 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int group, const TcParams
   return c;
 }
 
-template <typename TO>
+template <typename TO, bool TMA_OUT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const TcParams p) {
+                         const __grid_constant__ CUtensorMap tmap_out, const TcParams p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* stage_base = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
+  unsigned char* out_stage = smem + (size_t)TC_STAGES * TC_STAGE_BYTES;  // 1024-aligned (stages are 48 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + TC_OUT_BYTES);
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* tmem_full_bar = empty_bar + TC_STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + TC_ACC_STAGES;
@@ -163,6 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&tmap_a);
     tmap_prefetch(&tmap_b);
+    if (TMA_OUT) tmap_prefetch(&tmap_out);
     for (int i = 0; i < TC_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -235,6 +256,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const float scale = p.log_temp ? expf(-p.log_temp[0]) : 1.0f;
     TO* out = reinterpret_cast<TO*>(p.out);
+    constexpr int CPS = 128 / (int)sizeof(TO);  // columns per TMA store: one 128-byte swizzle row per output row
+    unsigned char* my_stage = out_stage + (size_t)(warp - 2) * 2 * TC_OUT_BUF_BYTES;
+    uint32_t store_it = 0;
     uint32_t tile_it = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_it) {
       const TileCoord tc = tile_coord(t, group, p);
@@ -242,7 +266,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t acc_round = tile_it / TC_ACC_STAGES;
       mbar_wait(&tmem_full_bar[acc], acc_round & 1u);
       tc_fence_after();
-      const int b = tc.m_blk * TC_BLOCK_M + quad * 32 + lane;
+      const int row0 = tc.m_blk * TC_BLOCK_M + quad * 32;
+      const int b = row0 + lane;
       const int c_base = tc.n_blk * TC_BLOCK_N;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * TC_BLOCK_N;
       const int sw = p.sample_idx ? __ldg(p.sample_idx + tc.s) : tc.s;
@@ -254,43 +279,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (c0 >= p.C) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32(taddr + (uint32_t)chunk * 32, r);
-        tmem_ld_wait();
-        if (b < p.B) {
-          float v[32];
+        // bias for these 32 columns (same addresses in every lane: broadcast loads), overlapped with the TMEM load
+        float bv[32];
+        if (bias_row) {
+          if (c0 + 32 <= p.C && ((reinterpret_cast<uintptr_t>(bias_row + c0) & 15u) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = __uint_as_float(r[j]);
-            if (bias_row && c0 + j < p.C) v[j] += __ldg(bias_row + c0 + j);
-            if (p.log_temp) v[j] *= scale;
-          }
-          const bool full = (c0 + 32 <= p.C);
-          if (sizeof(TO) == 4) {
-            float* o = reinterpret_cast<float*>(out_row) + c0;
-            if (full && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              for (int j = 0; j < 32 && c0 + j < p.C; ++j) o[j] = v[j];
+            for (int j = 0; j < 32; j += 4) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(bias_row + c0 + j));
+              bv[j] = q.x; bv[j + 1] = q.y; bv[j + 2] = q.z; bv[j + 3] = q.w;
             }
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_row) + c0;
-            if (full && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(o + j) = pk;
-              }
-            } else {
-              for (int j = 0; j < 32 && c0 + j < p.C; ++j) o[j] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < 32; ++j) bv[j] = (c0 + j < p.C) ? __ldg(bias_row + c0 + j) : 0.0f;
+          }
+        }
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(r[j]);
+          if (bias_row) v[j] += bv[j];
+          if (p.log_temp) v[j] *= scale;
+        }
+        if (TMA_OUT) {
+          // stage this warp's 32 rows x 32 columns in shared memory (128-byte rows, SWIZZLE_128B: 16-byte unit q of
+          // row r lives at unit q ^ (r & 7), so the 8 lanes of a store phase hit 8 different bank groups), then one
+          // lane hands the block to the TMA engine: full-line coalesced global writes, off the LSU path.
+          constexpr int per_store = CPS / 32;              // TMEM chunks per store: 1 (f32) or 2 (bf16)
+          const int sub = chunk % per_store;
+          unsigned char* buf = my_stage + (size_t)(store_it & 1u) * TC_OUT_BUF_BYTES;
+          if (sub == 0) {
+            if (lane == 0) bulk_wait_group_read<1>();      // the store that last read `buf` has drained it
+            __syncwarp();
+          }
+          unsigned char* rowp = buf + lane * 128;
+          if (sizeof(TO) == 4) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 pk;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(rowp + (((sub * 4 + q) ^ (lane & 7)) << 4)) = pk;
             }
+          }
+          const bool last_sub = (sub == per_store - 1) || (c0 + 32 >= p.C) || (chunk == TC_BLOCK_N / 32 - 1);
+          if (last_sub) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmap_out, buf, c0 - sub * 32, row0, tc.s);
+              bulk_commit_group();
+            }
+            ++store_it;
+          }
+        } else if (b < p.B) {
+          if (sizeof(TO) == 4) {
+            float* o = reinterpret_cast<float*>(out_row) + c0;
+            for (int j = 0; j < 32 && c0 + j < p.C; ++j) o[j] = v[j];
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_row) + c0;
+            for (int j = 0; j < 32 && c0 + j < p.C; ++j) o[j] = __float2bfloat16_rn(v[j]);
           }
         }
       }
@@ -298,6 +357,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (TMA_OUT && lane == 0) bulk_wait_group_all();  // shared memory must outlive the last store's read
   }
 
   tc_fence_before();
@@ -362,6 +422,20 @@ int last_layer_tc_launch(const void* x, const void* w, const float* bias, const 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return FB200_E_UNSUPPORTED;
   }
+  // output map {C, B, S}: needs 16-byte row stride and base; otherwise the epilogue stores directly
+  const size_t osz = out_dtype == FB200_F32 ? 4 : 2;
+  const bool tma_out = fb200_aligned16(out) && (((size_t)C * osz) % 16 == 0);
+  CUtensorMap to = ta;
+  if (tma_out) {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)B, (cuuint64_t)S};
+    cuuint64_t strides[2] = {(cuuint64_t)C * osz, (cuuint64_t)C * osz * (cuuint64_t)B};
+    cuuint32_t box[3] = {(cuuint32_t)(128 / osz), 32, 1};
+    cuuint32_t el[3] = {1, 1, 1};
+    CUresult r = enc(&to, out_dtype == FB200_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                     out, dims, strides, box, el, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return FB200_E_UNSUPPORTED;
+  }
   TcParams p{};
   p.bias = bias;
   p.log_temp = log_temp;
@@ -381,18 +455,19 @@ int last_layer_tc_launch(const void* x, const void* w, const float* bias, const 
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = sms;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  cudaError_t e;
-  if (out_dtype == FB200_F32) {
-    e = cudaFuncSetAttribute(last_layer_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)TC_SMEM_BYTES);
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    last_layer_tc_kernel<float><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, p);
-  } else {
-    e = cudaFuncSetAttribute(last_layer_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)TC_SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    last_layer_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, p);
-  }
+    kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ta, tb, to, p);
+    return 0;
+  };
+  int rc;
+  if (out_dtype == FB200_F32)
+    rc = tma_out ? launch(last_layer_tc_kernel<float, true>) : launch(last_layer_tc_kernel<float, false>);
+  else
+    rc = tma_out ? launch(last_layer_tc_kernel<__nv_bfloat16, true>)
+                 : launch(last_layer_tc_kernel<__nv_bfloat16, false>);
+  if (rc != 0) return rc;
   FB200_LAUNCH_CHECK();
   return 0;
 }

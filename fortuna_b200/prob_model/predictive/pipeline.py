@@ -59,8 +59,11 @@ class PredictivePipeline:
             self.rs = {n: torch.empty((self.B_local, C), dtype=torch.float32, device=device)
                        for n in ("sum_p", "sum_p2", "sum_pq")}
             self.rs["sum_plogp"] = torch.empty(self.B_local, dtype=torch.float32, device=device)
-            self.gather_max = torch.empty((world, B), dtype=torch.float32, device=device)
-            self.gather_sum = torch.empty((world, B), dtype=torch.float32, device=device)
+            self.rs["gather_max"] = torch.empty((world, B), dtype=torch.float32, device=device)
+            self.rs["gather_sum"] = torch.empty((world, B), dtype=torch.float32, device=device)
+            from .sharded import SampleShardExchange
+
+            self.exchange = SampleShardExchange(world, rank)
         self.launches_per_step = 5 if world == 1 else 7
 
     # -------------------------------------------------------------------------------- K3 / K4
@@ -68,17 +71,11 @@ class PredictivePipeline:
         if self.world == 1:
             self.outs = ops.bma_reduce_cls(z, self.want, targets=targets, out=self.outs or None)
             return self.outs
-        import torch.distributed as dist
-
         p = ops.bma_reduce_cls_partial(z, targets=targets, partials=self.partials)
         # the one exchange step of the S-sharded path: every rank keeps the rows b of its B/N slice
-        for n in ("sum_p", "sum_p2", "sum_pq", "sum_plogp"):
-            dist.reduce_scatter_tensor(self.rs[n], p[n], op=dist.ReduceOp.SUM)
-        dist.all_gather_into_tensor(self.gather_max, p["ll_max"])
-        dist.all_gather_into_tensor(self.gather_sum, p["ll_sumexp"])
-        lo, hi = self.rank * self.B_local, (self.rank + 1) * self.B_local
-        m, s = ops.merge_lse_pairs(self.gather_max[:, lo:hi].contiguous(), self.gather_sum[:, lo:hi].contiguous())
-        merged = dict(self.rs)
+        summed, gmax, gsum = self.exchange.exchange_partials(p, self.rs)
+        m, s = ops.merge_lse_pairs(gmax, gsum)
+        merged = dict(summed)
         merged["ll_max"], merged["ll_sumexp"] = m, s
         want = [w for w in self.want if w != "ensemble_log_prob"]
         self.outs = ops.bma_finalize_cls(merged, self.S * self.world, want, out=self.outs or None)
@@ -93,10 +90,7 @@ class PredictivePipeline:
         self.mask, self.sizes = ops.conformal_sets(calib.val_sorted, self.scores, calib.threshold)
         self.ece = ops.ece_bins(mean, t_local, self.thresholds)
         if self.world > 1:
-            import torch.distributed as dist
-
-            for n in ("counts", "correct", "conf_sums"):
-                dist.all_reduce(self.ece[n], op=dist.ReduceOp.SUM)
+            self.exchange.allreduce_bins(self.ece)
         return self.mask, self.sizes, self.ece
 
 

@@ -1,0 +1,82 @@
+"""Reference-side binding: registers the XLA-FFI handlers of fb200_xla_ffi.cc with JAX and exposes the
+drop-ins a Fortuna maintainer would import.  Requires jax/jaxlib (absent from the build container and the
+GPU box, so this module is NOT imported by the package, the tests or the benchmark - the ctypes driver in
+fortuna_b200/ops.py is what runs here).  Tolerates both spellings of the FFI module: ``jax.extend.ffi`` at the
+pinned jax 0.4.30, ``jax.ffi`` from 0.4.38.
+
+    from fortuna_b200.xla_ffi.jax_bindings import sghmc_integrator   # instead of fortuna's
+"""
+import ctypes
+import os
+
+
+def _ffi():
+    import jax
+
+    try:
+        from jax import ffi  # jax >= 0.4.38
+
+        return ffi
+    except ImportError:
+        from jax.extend import ffi  # jax 0.4.30 .. 0.4.37
+
+        return ffi
+
+
+_TARGETS = ("fb200_xla_sgmcmc_step", "fb200_xla_last_layer", "fb200_xla_bma_reduce_cls", "fb200_xla_aps_scores",
+            "fb200_xla_conformal_sets", "fb200_xla_ece_bins")
+_registered = False
+
+
+def register(lib_path=None):
+    global _registered
+    if _registered:
+        return
+    ffi = _ffi()
+    here = os.path.dirname(os.path.abspath(__file__))
+    lib = ctypes.CDLL(lib_path or os.path.join(here, "libfb200_xla_ffi.so"))
+    for name in _TARGETS:
+        ffi.register_ffi_target(name, ffi.pycapsule(getattr(lib, name)), platform="CUDA")
+    _registered = True
+
+
+def sghmc_integrator(momentum_decay, momentum_resample_steps, rng_key, step_schedule, preconditioner_kind="identity",
+                     running_average_factor=0.99, eps=1e-7):
+    """optax.GradientTransformation with Fortuna's (init_fn, update_fn) contract whose update is ONE custom call.
+    Works on the flattened pytree: `flatten(params) -> (flat f32[N], leaves i64[L,2], tiles i32[T,2])` is built
+    once with fb200_sgmcmc_build_tiles_host; updates = new_params - params keeps optax's return contract while
+    `apply_gradients` users can take new_params directly (input_output_aliases donates the buffers)."""
+    import jax
+    import jax.numpy as jnp
+    import numpy as np
+    import optax
+    from jax.flatten_util import ravel_pytree
+
+    register()
+    ffi = _ffi()
+    rms = int(preconditioner_kind == "rmsprop")
+
+    def init_fn(params):
+        flat, _ = ravel_pytree(params)
+        return dict(count=jnp.zeros([], jnp.int32), rng_key=rng_key, momentum=jnp.zeros_like(flat),
+                    v=jnp.zeros_like(flat))
+
+    def update_fn(gradient, state, params):
+        gflat, unravel = ravel_pytree(gradient)
+        pflat, _ = ravel_pytree(params)
+        lens = [int(np.prod(l.shape)) for l in jax.tree_util.tree_leaves(gradient)]
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        leaves = np.stack([offs, lens], 1).astype(np.int64)
+        tiles = np.array([(i, p) for i, n in enumerate(lens) for p in range(0, (n + 1) // 2, 1024)], np.int32)
+        n = gflat.shape[0]
+        out_types = (jax.ShapeDtypeStruct((n,), jnp.float32),) * 3 + (
+            jax.ShapeDtypeStruct((2,), jnp.uint32), jax.ShapeDtypeStruct((len(lens), 2), jnp.uint32))
+        new_p, new_m, new_v, new_key, _ = ffi.ffi_call(
+            "fb200_xla_sgmcmc_step", out_types, pflat, gflat, state["momentum"], state["v"], jnp.asarray(leaves),
+            jnp.asarray(tiles), state["rng_key"], step_size=np.float32(step_schedule(state["count"])),
+            momentum_decay=float(momentum_decay), rmsprop=np.int32(rms), rms_alpha=float(running_average_factor),
+            rms_eps=float(eps), input_output_aliases={0: 0, 2: 1, 3: 2})
+        new_state = dict(count=state["count"] + 1, rng_key=new_key, momentum=new_m, v=new_v)
+        return unravel(new_p - pflat), new_state
+
+    return optax.GradientTransformation(init_fn, update_fn)

@@ -43,6 +43,15 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _tensor_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p.get("bf16_tflops", 1590.0)), float(p.get("bf16_tflops_sustained", 1400.0))
+    return 1590.0, 1400.0
+
+
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     FIELDS = (
@@ -241,11 +250,7 @@ def run_gpu_arm(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (args.steps + 1))]
 
     def one_step(i=None):
-        if i is not None:
-            ev[2 * i].record()
-        runner.reduce(z, targets)
-        if i is not None:
-            ev[2 * i + 1].record()
+        runner.reduce(z, targets, kernel_events=(ev[2 * i], ev[2 * i + 1]) if i is not None else None)
         runner.score(targets, calib)
 
     sampler = ClockSampler(local_rank)
@@ -320,15 +325,26 @@ def run_gpu_arm(args):
         "clocks": clocks,
     }
 
-    if rank == 0 and world == 1 and not args.no_e2e:
-        line["e2e"] = pipeline.bench_e2e(S, B, Cn, dev, WANT, calib, args, UNIT)
-    elif world > 1:
-        line["e2e"] = None
+    if not args.no_e2e:
+        # every rank streams its own [S,B,C] host logits through the public call (inputs sharded over B like the
+        # reference's pmap prediction mode: no collective); whole-job value = N * S*B*C / max-over-ranks time
+        e2e = pipeline.bench_e2e(S, B, Cn, dev, WANT, calib, args, UNIT)
+        if world > 1:
+            tt = torch.tensor([e2e["ms_per_step"]], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e["ms_per_step"] = float(tt[0])
+            e2e["value"] = float(S) * B * Cn * world / (e2e["ms_per_step"] * 1e-3)
+            e2e["h2d_bytes_per_step"] *= world
+            e2e["d2h_bytes_per_step"] *= world
+            e2e["sharding"] = f"inputs sharded over {world} ranks (B per rank = {B}), no collective"
+        line["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_extras:
         try:
-            from fortuna_b200.bench_extras import sampler_extras
+            from fortuna_b200.bench_extras import last_layer_extras, sampler_extras
 
             line["extras"] = sampler_extras(dev, peak)
+            tfb, tfs = _tensor_peaks()
+            line["extras"]["last_layer_gemm"] = last_layer_extras(dev, tfb, tfs)
         except Exception as exc:  # extras never invalidate the headline
             line["extras"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -1,5 +1,6 @@
 """Secondary measurements printed next to the headline: SG-MCMC updates/s on the BERT-base-shaped
-flat pytree (BASELINE config 5) with its HBM roofline fraction."""
+flat pytree (BASELINE config 5) with its HBM roofline fraction, and the S-batched last-layer GEMM (K2) at a
+B = 8192 slice of config 4 with its tensor-pipe fraction."""
 
 import torch
 
@@ -43,4 +44,34 @@ def sampler_extras(device, hbm_peak_gbs, steps=20, warmup=3):
             "achieved_gbs": gbs, "hbm_frac": gbs / hbm_peak_gbs,
         }
         del state
+    return out
+
+
+def last_layer_extras(device, tf_burst, tf_sustained, S=64, B=8192, D=2048, Cn=1000, iters=3):
+    """K2 at the c4 shape (B sliced to 8192 so the fp32 logits are 2.1 GB): TFLOP/s of fb200_last_layer_logits on
+    the tcgen05 path, bf16 operands, fp32 accumulate, bias + temperature fused, fp32 and bf16 logits."""
+    g = torch.Generator(device=device)
+    g.manual_seed(3)
+    x = torch.empty((B, D), device=device, dtype=torch.float32).normal_(generator=g).to(torch.bfloat16)
+    wt = (torch.empty((S, Cn, D), device=device, dtype=torch.float32).normal_(generator=g) / D ** 0.5).to(torch.bfloat16)
+    bias = torch.empty((S, Cn), device=device, dtype=torch.float32).normal_(generator=g)
+    lt = torch.tensor([0.3], device=device)
+    flops = 2.0 * S * B * D * Cn
+    out = {}
+    for name, dt in (("f32_logits", torch.float32), ("bf16_logits", torch.bfloat16)):
+        o = torch.empty((S, B, Cn), device=device, dtype=dt)
+        for _ in range(2):
+            ops.last_layer_logits(x, wt, bias, lt, w_layout=ops.W_SCD, path=2, out=o)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            ops.last_layer_logits(x, wt, bias, lt, w_layout=ops.W_SCD, path=2, out=o)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        tf = flops / ms / 1e9
+        out[name] = {"S": S, "B": B, "D": D, "C": Cn, "ms": ms, "tflops": tf, "frac_of_burst_peak": tf / tf_burst,
+                     "frac_of_sustained_peak": tf / tf_sustained}
+        del o
     return out

@@ -67,11 +67,18 @@ class PredictivePipeline:
         self.launches_per_step = 5 if world == 1 else 7
 
     # -------------------------------------------------------------------------------- K3 / K4
-    def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor]):
+    def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor], kernel_events=None):
+        """kernel_events: optional (start, end) CUDA events recorded around the reduction kernel alone."""
+        if kernel_events:
+            kernel_events[0].record()
         if self.world == 1:
             self.outs = ops.bma_reduce_cls(z, self.want, targets=targets, out=self.outs or None)
+            if kernel_events:
+                kernel_events[1].record()
             return self.outs
         p = ops.bma_reduce_cls_partial(z, targets=targets, partials=self.partials)
+        if kernel_events:
+            kernel_events[1].record()
         # the one exchange step of the S-sharded path: every rank keeps the rows b of its B/N slice
         summed, gmax, gsum = self.exchange.exchange_partials(p, self.rs)
         m, s = ops.merge_lse_pairs(gmax, gsum)

@@ -22,13 +22,21 @@
 
 namespace fb200 {
 
-constexpr int kConsumerWarps = 8;                          // warpgroups 0 and 1
-constexpr int kReduceThreads = (kConsumerWarps + 4) * 32;  // + one producer warpgroup (one lane of it works)
 constexpr int kMaxStages = 8;
-// 384 threads cap ptxas at 168 registers/thread; the producer warpgroup gives most of its share back
-// (setmaxnreg.dec) and the consumer warpgroups take it (setmaxnreg.inc): 8*32*232 + 4*32*40 = 64512 = 384*168.
-constexpr int kConsumerRegs = 232;
-constexpr int kProducerRegs = 40;
+// NW consumer warps (whole warpgroups) + one producer warpgroup (one lane of it works).  The launch bound caps
+// ptxas at 65536 / threads registers; the producer warpgroup gives most of its share back (setmaxnreg.dec) and the
+// consumer warpgroups take it (setmaxnreg.inc):  NW = 8: 8*32*232 + 4*32*40;  12: 12*32*160 + 4*32*32;
+// 16: 16*32*112 + 4*32*32.  The sum must not exceed what the CTA owns at launch (threads * the ptxas register
+// count, which is 65536 / threads rounded DOWN to a multiple of 8: 168, 128, 96) or setmaxnreg.inc never returns.
+template <int NW>
+struct WarpCfg {
+  static constexpr int kThreads = (NW + 4) * 32;
+  static constexpr int kConsumerRegs = NW == 8 ? 232 : (NW == 12 ? 160 : 112);
+  static constexpr int kProducerRegs = NW == 8 ? 40 : 32;
+  static constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8;
+  static_assert(NW * 32 * kConsumerRegs + 4 * 32 * kProducerRegs <= kThreads * kLaunchRegs,
+                "setmaxnreg budget exceeds the registers the CTA owns at launch");
+};
 
 struct ClsArgs {
   const void* logits;
@@ -88,11 +96,12 @@ __device__ __forceinline__ float rcp_approx_ftz(float x) {
 
 
 // Process RI rows (consecutive samples s of the same input b) held in shared memory: softmax of each row,
-// accumulate sum_s p, p^2, p(1-p) and the entropy partials.  The RI rows are independent until the final
+// accumulate sum_s p, sum_s p^2 and the entropy partials (sum_s p(1-p) is formed as sum p - sum p^2 at the end:
+// two accumulators per (b,c) instead of three is what lets 12-16 warps share the register file).  The RI rows are independent until the final
 // accumulation, so their shuffle reductions and MUFU chains overlap (ILP); accumulation keeps the s order.
 template <typename T, int G, int NV, int VEC, bool TAILONLY, int RI>
 __device__ __forceinline__ void process_rows(const T* const (&rowp)[RI], int g, int C, float k2,
-                                             float (&sp)[NV][VEC], float (&sp2)[NV][VEC], float (&spq)[NV][VEC],
+                                             float (&sp)[NV][VEC], float (&sp2)[NV][VEC],
                                              float& spl, float& sum_l, float (&cshift)[RI], float (&l2sum)[RI]) {
   float z[RI][NV][VEC];
   float m[RI];
@@ -160,10 +169,11 @@ __device__ __forceinline__ void process_rows(const T* const (&rowp)[RI], int g, 
   for (int o = G / 2; o > 0; o >>= 1)
 #pragma unroll
     for (int ri = 0; ri < RI; ++ri) sum[ri] += __shfl_xor_sync(0xffffffffu, sum[ri], o);
-  // pass C: p = e / sum, accumulate in sample order
+  // pass C: p = e / sum, accumulate in sample order: sum p += e * inv, sum p^2 += (e*e) * inv^2 (two FFMA + one FMUL)
 #pragma unroll
   for (int ri = 0; ri < RI; ++ri) {
     const float inv = rcp_approx_ftz(sum[ri]);
+    const float inv2 = inv * inv;
     l2sum[ri] = lg2_approx(sum[ri]);
     spl = fmaf(inv, set[ri], spl);  // lane-partial of sum_c p u (log2 units); -log2(sum) is row-uniform
     sum_l += l2sum[ri];
@@ -171,17 +181,17 @@ __device__ __forceinline__ void process_rows(const T* const (&rowp)[RI], int g, 
     for (int j = 0; j < NV; ++j) {
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        const float p = z[ri][j][k] * inv;
-        sp[j][k] += p;
-        sp2[j][k] = fmaf(p, p, sp2[j][k]);
-        spq[j][k] = fmaf(p, 1.0f - p, spq[j][k]);
+        const float e = z[ri][j][k];
+        sp[j][k] = fmaf(e, inv, sp[j][k]);
+        sp2[j][k] = fmaf(e * e, inv2, sp2[j][k]);
       }
     }
   }
 }
 
-template <typename T, int G, int NV, int VEC, bool TAILONLY>
-__global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const ClsArgs a) {
+template <typename T, int G, int NV, int VEC, bool TAILONLY, int NW, int RI>
+__global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kernel(const ClsArgs a) {
+  constexpr int kConsumerWarps = NW;
   constexpr int R = 32 / G;                 // rows per warp
   constexpr int TB = kConsumerWarps * R;    // rows per tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
 
   if (warp >= kConsumerWarps) {
     // ------------------------------------------------------------------ producer warpgroup (warp 8 works)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WarpCfg<NW>::kProducerRegs));
     if (warp != kConsumerWarps) return;
     const T* base = reinterpret_cast<const T*>(a.logits);
     uint32_t it = 0;
@@ -247,7 +257,7 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
   }
 
   // -------------------------------------------------------------------- consumer warps
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WarpCfg<NW>::kConsumerRegs));
   const int gr = lane / G;
   const int g = lane % G;
   const int row = warp * R + gr;
@@ -260,11 +270,11 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int b = tile * TB + row;
     const bool valid_row = b < B;
-    float sp[NV][VEC], sp2[NV][VEC], spq[NV][VEC];
+    float sp[NV][VEC], sp2[NV][VEC];
 #pragma unroll
     for (int j = 0; j < NV; ++j)
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) sp[j][k] = sp2[j][k] = spq[j][k] = 0.0f;
+      for (int k = 0; k < VEC; ++k) sp[j][k] = sp2[j][k] = 0.0f;
     float spl = 0.0f, sum_l = 0.0f;
     float lmax = -CUDART_INF_F, lsum = 0.0f;
     int y = -1;
@@ -298,22 +308,24 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
         if (a.out.ensemble_log_prob && valid_row && g == 0) a.out.ensemble_log_prob[(size_t)s_idx * B + b] = ll;
       };
       int q = 0;
-      for (; q + 1 < ns; q += 2) {
-        const T* rp[2];
-        rp[0] = reinterpret_cast<const T*>(sbase + (size_t)q * a.tile_stride_bytes) + (size_t)row * C;
-        rp[1] = reinterpret_cast<const T*>(sbase + (size_t)(q + 1) * a.tile_stride_bytes) + (size_t)row * C;
-        float csh[2], l2s[2];
-        process_rows<T, G, NV, VEC, TAILONLY, 2>(rp, g, C, k2, sp, sp2, spq, spl, sum_l, csh, l2s);
-        if (a.targets) {
-          log_prob_update(rp[0], csh[0], l2s[0], s0 + q);
-          log_prob_update(rp[1], csh[1], l2s[1], s0 + q + 1);
+      if (RI == 2) {
+        for (; q + 1 < ns; q += 2) {
+          const T* rp[2];
+          rp[0] = reinterpret_cast<const T*>(sbase + (size_t)q * a.tile_stride_bytes) + (size_t)row * C;
+          rp[1] = reinterpret_cast<const T*>(sbase + (size_t)(q + 1) * a.tile_stride_bytes) + (size_t)row * C;
+          float csh[2], l2s[2];
+          process_rows<T, G, NV, VEC, TAILONLY, 2>(rp, g, C, k2, sp, sp2, spl, sum_l, csh, l2s);
+          if (a.targets) {
+            log_prob_update(rp[0], csh[0], l2s[0], s0 + q);
+            log_prob_update(rp[1], csh[1], l2s[1], s0 + q + 1);
+          }
         }
       }
-      if (q < ns) {
+      for (; q < ns; ++q) {
         const T* rp[1];
         rp[0] = reinterpret_cast<const T*>(sbase + (size_t)q * a.tile_stride_bytes) + (size_t)row * C;
         float csh[1], l2s[1];
-        process_rows<T, G, NV, VEC, TAILONLY, 1>(rp, g, C, k2, sp, sp2, spq, spl, sum_l, csh, l2s);
+        process_rows<T, G, NV, VEC, TAILONLY, 1>(rp, g, C, k2, sp, sp2, spl, sum_l, csh, l2s);
         if (a.targets) log_prob_update(rp[0], csh[0], l2s[0], s0 + q);
       }
       __syncwarp();
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
               const size_t o = (size_t)b * C + c0 + k;
               a.part.sum_p[o] = sp[j][k];
               a.part.sum_p2[o] = sp2[j][k];
-              a.part.sum_pq[o] = spq[j][k];
+              a.part.sum_pq[o] = sp[j][k] - sp2[j][k];
             }
           }
         }
@@ -360,7 +372,8 @@ __global__ void __launch_bounds__(kReduceThreads, 1) bma_reduce_cls_kernel(const
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
           mean[k] = s_pow2 ? sp[j][k] * inv_Sf : sp[j][k] / Sf;
-          av[k] = s_pow2 ? spq[j][k] * inv_Sf : spq[j][k] / Sf;
+          const float spq = sp[j][k] - sp2[j][k];  // sum_s p(1-p)
+          av[k] = s_pow2 ? spq * inv_Sf : spq / Sf;
           const float m2 = s_pow2 ? sp2[j][k] * inv_Sf : sp2[j][k] / Sf;
           ev[k] = fmaxf(0.0f, __fsub_rn(m2, __fmul_rn(mean[k], mean[k])));
           if (mean[k] > 0.0f) ent_terms = fmaf(mean[k], logf(mean[k]), ent_terms);
@@ -549,15 +562,16 @@ static int sm_count() {
   return cached[dev];
 }
 
-template <typename T, int G, int NV, int VEC, bool TAILONLY>
-static int launch_cls(ClsArgs a, cudaStream_t st) {
+template <typename T, int G, int NV, int VEC, bool TAILONLY, int NW, int RI>
+static int launch_cls_cfg(ClsArgs a, cudaStream_t st) {
   constexpr int R = 32 / G;
-  constexpr int TB = kConsumerWarps * R;
+  constexpr int TB = NW * R;
+  constexpr int kReduceThreads = WarpCfg<NW>::kThreads;
   const uint32_t tile_bytes = (uint32_t)TB * (uint32_t)a.C * (uint32_t)sizeof(T);
   a.tile_stride_bytes = (tile_bytes + 15u) & ~15u;
   // aim for >= 16 KB per stage so a handful of stages covers the HBM latency-bandwidth product
   int ss = (int)(16384u / a.tile_stride_bytes);
-  if (ss < 2) ss = 2;  // two samples per stage: the consumers interleave them for ILP
+  if (ss < RI) ss = RI;  // RI samples per stage at least: the consumers interleave them for ILP
   if (ss > 16) ss = 16;
   if (ss > a.S) ss = a.S;
   a.ss = ss;
@@ -569,7 +583,7 @@ static int launch_cls(ClsArgs a, cudaStream_t st) {
   a.n_stages = nst;
   a.n_tiles = (a.B + TB - 1) / TB;
   const size_t smem = 128 + (size_t)nst * a.stage_bytes;
-  auto kern = bma_reduce_cls_kernel<T, G, NV, VEC, TAILONLY>;
+  auto kern = bma_reduce_cls_kernel<T, G, NV, VEC, TAILONLY, NW, RI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int occ = 1;
@@ -581,6 +595,18 @@ static int launch_cls(ClsArgs a, cudaStream_t st) {
   kern<<<grid, kReduceThreads, smem, st>>>(a);
   FB200_LAUNCH_CHECK();
   return 0;
+}
+
+// Warp / interleave configuration per row width.  Wide rows (C > 512: 64 accumulator + 64 row registers per lane)
+// run 12 consumer warps x 2 interleaved samples (160 registers); measured at c4 on B200: 12x2 2.93 ms,
+// 16x1 3.00 ms, 12x1 3.36 ms, 8x2 3.34 ms.  Narrow rows have registers to spare: 16 warps x 2.
+template <typename T, int G, int NV, int VEC, bool TAILONLY>
+static int launch_cls(const ClsArgs& a, cudaStream_t st) {
+  if constexpr (NV * VEC >= 20) {
+    return launch_cls_cfg<T, G, NV, VEC, TAILONLY, 12, 2>(a, st);
+  } else {
+    return launch_cls_cfg<T, G, NV, VEC, TAILONLY, 16, 2>(a, st);
+  }
 }
 
 template <typename T>

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) row_sort_cumsum_kernel(const RowSortArgs 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
   float* cum = reinterpret_cast<float*>(keys + a.N2);
+  float* tree = cum + a.N2;  // 2 * N2 floats
   const int C = a.C, N2 = a.N2;
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     const float* row = a.probs + (size_t)b * C;
@@ -70,19 +71,40 @@ __global__ void __launch_bounds__(256) row_sort_cumsum_kernel(const RowSortArgs 
         __syncthreads();
       }
     }
-    // sequential float32 inclusive prefix sum in rank order (oracle/scoring.py defines this order)
+    // inclusive prefix sum in rank order, association order of jax.lax.associative_scan (see the warp kernel):
+    // up-sweep levels live in tree[] (level l at offset 2*N2 - (2*N2 >> l)), then the down-sweep overwrites them
+    for (int i = threadIdx.x; i < N2; i += blockDim.x)
+      tree[i] = i < C ? f32_unordered((uint32_t)(keys[i] >> 32)) : 0.0f;
+    __syncthreads();
+    {
+      int off = 0;
+      for (int m = N2; m > 1; m >>= 1) {
+        for (int i = threadIdx.x; i < m / 2; i += blockDim.x) tree[off + m + i] = tree[off + 2 * i] + tree[off + 2 * i + 1];
+        off += m;
+        __syncthreads();
+      }
+      // tree[off] is the total == out of the top level; walk down: out_l in place of u_l
+      for (int m = 2; m <= N2; m <<= 1) {
+        const int hi_off = off;
+        off -= m;
+        for (int i = threadIdx.x; i < m / 2; i += blockDim.x) {
+          const float odd = tree[hi_off + i];
+          if (i > 0) tree[off + 2 * i] = tree[hi_off + i - 1] + tree[off + 2 * i];
+          tree[off + 2 * i + 1] = odd;
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) cum[i] = tree[i];
+    __syncthreads();
     if (threadIdx.x == 0) {
-      float run = 0.0f;
-      int first = -1;
       const int y = a.targets ? a.targets[b] : -1;
       float ys = CUDART_NAN_F;
+      int first = -1;
       for (int r = 0; r < C; ++r) {
-        const unsigned long long k = keys[r];
-        const int idx = (int)(k & 0xFFFFFFFFull);
-        run += f32_unordered((uint32_t)(k >> 32));
-        cum[r] = run;
-        if (idx == y) ys = run;
-        if (first < 0 && run > a.set_threshold) first = r;
+        const int idx = (int)(keys[r] & 0xFFFFFFFFull);
+        if (idx == y) ys = cum[r];
+        if (first < 0 && cum[r] > a.set_threshold) first = r;
       }
       if (a.scores && a.targets) a.scores[b] = ys;
       if (a.set_size) a.set_size[b] = (first < 0 ? 0 : first) + 1;  // argmax of an all-False row is 0
@@ -103,47 +125,124 @@ __global__ void __launch_bounds__(256) row_sort_cumsum_kernel(const RowSortArgs 
 // Warp-per-row variant for C <= 1024: the 64-bit keys live in registers (NR per lane, logical position
 // e = lane * NR + r), so 2/3 of the bitonic network is register-to-register compare-exchange and only the
 // strides >= NR cross lanes (shfl.xor).  Keys are stored complemented so an ASCENDING network yields the
-// descending (prob, class) order; padding keys are all-ones and sort to the end.  The prefix sum is then
-// taken lane by lane in rank order (float32, sequential), each lane receiving the running total of the
-// previous lanes, and un-permuted through a 4 KB shared-memory row so the global store is coalesced.
+// descending (prob, class) order; padding keys are all-ones and sort to the end.  Blocks that the network
+// wants descending are handled by complementing the lane's keys for that merge level, so every
+// compare-exchange is a plain "min to the low slot" with no run-time direction logic.
+//
+// Prefix sum: jnp.cumsum on CPU lowers to jax.lax.associative_scan (jax/_src/lax/control_flow/loops.py,
+// _cumulative_reduction_primitive: reduce_window only on TPU), i.e. the recursive pairwise tree
+//   r[i] = x[2i] + x[2i+1];  odd = scan(r);  out[2i+1] = odd[i];  out[0] = x[0];  out[2i] = odd[i-1] + x[2i].
+// Padding the row with zeros to a power of two does not change any prefix (each out[k] only sees x[0..k]), so
+// the tree runs on 32*NR slots: levels inside a lane's block in registers, the 32 lane totals by shuffles.
 // ------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+
+__device__ __forceinline__ void ce_min_first(u64& a, u64& b) {
+  const bool sw = a > b;
+  const u64 lo = sw ? b : a;
+  const u64 hi = sw ? a : b;
+  a = lo;
+  b = hi;
+}
+
 template <int NR>
-__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[NR], int lane) {
+__device__ __forceinline__ void warp_bitonic_sort(u64 (&key)[NR], int lane) {
   constexpr int N = 32 * NR;
+  // levels whose blocks fit inside a lane: direction is a compile-time function of the register index
 #pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
+  for (int k = 2; k < NR; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= NR) {
-        // partner lives in lane ^ (j / NR), same register
-        const int lmask = j / NR;
-        const bool upper = (lane & lmask) != 0;
-        // ascending block iff (e & k) == 0; k >= 2 * j >= 2 * NR so the bit is a lane bit (or beyond: final pass)
-        const bool asc = (k >= N) ? true : ((lane & (k / NR)) == 0);
-        const bool keep_min = (asc != upper);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[r], lmask);
-          const bool lt = key[r] < other;
-          key[r] = (lt == keep_min) ? key[r] : other;
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          if ((r & j) == 0) {
-            const int r2 = r | j;
-            bool asc;
-            if (k < NR) asc = ((r & k) == 0);
-            else asc = (k >= N) ? true : ((lane & (k / NR)) == 0);
-            const unsigned long long a0 = key[r], a1 = key[r2];
-            const bool sw = (a0 > a1) == asc;
-            key[r] = sw ? a1 : a0;
-            key[r2] = sw ? a0 : a1;
-          }
+      for (int r = 0; r < NR; ++r) {
+        if ((r & j) == 0) {
+          if ((r & k) == 0) ce_min_first(key[r], key[r | j]);
+          else ce_min_first(key[r | j], key[r]);
         }
       }
     }
   }
+  // levels k >= NR: the direction of the lane's block is a lane bit; complement instead of reversing
+  bool flipped = false;
+#pragma unroll
+  for (int k = (NR > 1 ? NR : 2); k <= N; k <<= 1) {
+    const bool want_desc = (k < N) && ((lane & (k / NR)) != 0);
+    if (want_desc != flipped) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) key[r] = ~key[r];
+    }
+    flipped = want_desc;
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= NR) {
+        const int lmask = j / NR;
+        const bool upper = (lane & lmask) != 0;  // the upper lane of a pair keeps the larger key
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const u64 other = __shfl_xor_sync(0xffffffffu, key[r], lmask);
+          const bool lt = key[r] < other;
+          key[r] = (lt == upper) ? other : key[r];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+          if ((r & j) == 0) ce_min_first(key[r], key[r | j]);
+      }
+    }
+  }
+}
+
+// Inclusive scan of one value per lane in jax.lax.associative_scan's association order (see above).
+__device__ __forceinline__ float warp_tree_scan(float t, int lane) {
+  float w = t;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {  // up-sweep: the right child of each pair becomes the pair's sum
+    const float o = __shfl_up_sync(0xffffffffu, w, s);
+    if ((lane & (2 * s - 1)) == 2 * s - 1) w = o + w;
+  }
+  float out = w;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {  // down-sweep: even elements of a level add the prefix ending just before them
+    const float o = __shfl_up_sync(0xffffffffu, out, s);
+    if ((lane & (2 * s - 1)) == s - 1 && lane >= 3 * s - 1) out = o + out;
+  }
+  return out;
+}
+
+// x[NR] (rank order inside the lane's block) -> inclusive prefix sums over the whole warp-row, tree order.
+__host__ __device__ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
+// level l of the in-lane tree has NR >> l entries and starts at offset 2*NR - (2*NR >> l)
+template <int NR>
+__host__ __device__ constexpr int lvl_off(int l) { return 2 * NR - ((2 * NR) >> l); }
+
+template <int NR>
+__device__ __forceinline__ void warp_row_tree_prefix(float (&x)[NR], int lane) {
+  constexpr int LOG = ilog2_c(NR);
+  float u[2 * NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) u[r] = x[r];
+#pragma unroll
+  for (int l = 0; l < LOG; ++l) {
+#pragma unroll
+    for (int i = 0; i < (NR >> (l + 1)); ++i)
+      u[lvl_off<NR>(l + 1) + i] = u[lvl_off<NR>(l) + 2 * i] + u[lvl_off<NR>(l) + 2 * i + 1];
+  }
+  const float incl = warp_tree_scan(u[lvl_off<NR>(LOG)], lane);
+  const float carry = __shfl_up_sync(0xffffffffu, incl, 1);  // prefix through the previous lane's block
+  const bool has_carry = lane > 0;
+  float o[2 * NR];
+  o[lvl_off<NR>(LOG)] = incl;
+#pragma unroll
+  for (int l = LOG - 1; l >= 0; --l) {
+#pragma unroll
+    for (int i = 0; i < (NR >> (l + 1)); ++i) {
+      o[lvl_off<NR>(l) + 2 * i + 1] = o[lvl_off<NR>(l + 1) + i];
+      if (i == 0) o[lvl_off<NR>(l)] = has_carry ? carry + u[lvl_off<NR>(l)] : u[lvl_off<NR>(l)];
+      else o[lvl_off<NR>(l) + 2 * i] = o[lvl_off<NR>(l + 1) + i - 1] + u[lvl_off<NR>(l) + 2 * i];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) x[r] = o[r];
 }
 
 constexpr int kSortWarps = 8;
@@ -151,72 +250,66 @@ constexpr int kSortWarps = 8;
 template <int NR, int MODE>  // MODE 0: all-class scores (+perm); 1: target score; 2: credible sets (+perm)
 __global__ void __launch_bounds__(kSortWarps * 32) row_sort_warp_kernel(const RowSortArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp_in_cta = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so the row loop is convergent for the compiler and the
+  // 64-bit shuffles of the network need no per-call WARPSYNC
+  const int warp_in_cta = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int C = a.C;
   float* unperm = reinterpret_cast<float*>(smem_raw) + (size_t)warp_in_cta * (32 * NR);
   const int nwarps = gridDim.x * kSortWarps;
   for (int b = blockIdx.x * kSortWarps + warp_in_cta; b < a.B; b += nwarps) {
     const float* row = a.probs + (size_t)b * C;
-    unsigned long long key[NR];
+    u64 key[NR];
     // coalesced load; the initial arrangement is irrelevant to the sort (the class index rides in the key)
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       const int c = r * 32 + lane;
-      unsigned long long k = ~0ull;
+      u64 k = ~0ull;
       if (c < C) {
         const float p = row[c] + 0.0f;  // -0 -> +0
-        k = ~(((unsigned long long)f32_ordered(p) << 32) | (unsigned)c);
+        k = ~(((u64)f32_ordered(p) << 32) | (unsigned)c);
       }
       key[r] = k;
     }
     warp_bitonic_sort<NR>(key, lane);
-    // rank of key[r] is lane * NR + r
-    const int y = (MODE == 1 && a.targets) ? a.targets[b] : -1;
-    float carry = 0.0f;
-    float ys = CUDART_NAN_F;
-    int first = 0x7FFFFFFF;
-    const int n_lanes = (C + NR - 1) / NR;
-#pragma unroll 1
-    for (int l = 0; l < n_lanes; ++l) {
-      if (lane == l) {
-        float run = carry;
+    // rank of key[r] is lane * NR + r; split into (prob, class)
+    float x[NR];
+    int cls[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const unsigned long long kk = ~key[r];
-          const float p = f32_unordered((uint32_t)(kk >> 32));
-          if (l * NR + r < C) {
-            run += p;
-            if (MODE == 1 && (int)(kk & 0xFFFFFFFFull) == y) ys = run;
-            if (MODE == 2 && first == 0x7FFFFFFF && run > a.set_threshold) first = l * NR + r;
-          }
-          // from here on the register pair holds (prefix sum bits, class) instead of the sort key
-          key[r] = ((unsigned long long)__float_as_uint(run) << 32) | (kk & 0xFFFFFFFFull);
-        }
-        carry = run;
-      }
-      carry = __shfl_sync(0xffffffffu, carry, l);
+    for (int r = 0; r < NR; ++r) {
+      const u64 kk = ~key[r];
+      cls[r] = (int)(kk & 0xFFFFFFFFull);
+      x[r] = (lane * NR + r < C) ? f32_unordered((uint32_t)(kk >> 32)) : 0.0f;
     }
+    warp_row_tree_prefix<NR>(x, lane);
     if (MODE == 1) {
-      // exactly one lane saw the target
-      const unsigned m = __ballot_sync(0xffffffffu, ys == ys);
-      if (m) {
-        const int src = __ffs(m) - 1;
-        ys = __shfl_sync(0xffffffffu, ys, src);
+      const int y = a.targets ? a.targets[b] : -1;
+      float ys = CUDART_NAN_F;
+      bool mine = false;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        if (lane * NR + r < C && cls[r] == y) {
+          ys = x[r];
+          mine = true;
+        }
       }
+      const unsigned m = __ballot_sync(0xffffffffu, mine);  // exactly one lane saw the target (none if out of range)
+      if (m) ys = __shfl_sync(0xffffffffu, ys, __ffs(m) - 1);
       if (lane == 0 && a.scores) a.scores[b] = ys;
     }
     if (MODE == 2) {
+      int first = 0x7FFFFFFF;
+#pragma unroll
+      for (int r = NR - 1; r >= 0; --r)
+        if (lane * NR + r < C && x[r] > a.set_threshold) first = lane * NR + r;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
       if (lane == 0 && a.set_size) a.set_size[b] = (first == 0x7FFFFFFF ? 0 : first) + 1;
     }
     if (MODE == 0 && a.scores) {
 #pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const int idx = (int)(key[r] & 0xFFFFFFFFull);
-        if (lane * NR + r < C) unperm[idx] = __uint_as_float((uint32_t)(key[r] >> 32));
-      }
+      for (int r = 0; r < NR; ++r)
+        if (lane * NR + r < C) unperm[cls[r]] = x[r];
       __syncwarp();
       float* orow = a.scores + (size_t)b * C;
       for (int c = lane; c < C; c += 32) orow[c] = unperm[c];
@@ -227,7 +320,7 @@ __global__ void __launch_bounds__(kSortWarps * 32) row_sort_warp_kernel(const Ro
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         const int rank = lane * NR + r;
-        if (rank < C) prow[rank] = (int)(key[r] & 0xFFFFFFFFull);
+        if (rank < C) prow[rank] = cls[r];
       }
     }
   }
@@ -256,12 +349,12 @@ static int launch_row_sort(RowSortArgs a, cudaStream_t st) {
   int n2 = 1;
   while (n2 < a.C) n2 <<= 1;
   a.N2 = n2;
-  const size_t smem = (size_t)n2 * 8 + (size_t)a.C * 4;
+  const size_t smem = (size_t)n2 * 8 + (size_t)n2 * 4 + (size_t)n2 * 8;  // keys, cum, prefix tree
   int threads = n2 / 2;
   if (threads < 32) threads = 32;
   if (threads > 256) threads = 256;
   cudaError_t e =
-      cudaFuncSetAttribute(row_sort_cumsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      cudaFuncSetAttribute(row_sort_cumsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   if (e != cudaSuccess) return (int)e;
   int grid = a.B;
   if (grid > 148 * 64) grid = 148 * 64;

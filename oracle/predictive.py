@@ -213,7 +213,9 @@ def cls_credible_set(mean, error):
     mean = _f32(mean)
     labels = np.argsort(mean, axis=-1, kind="stable")[:, ::-1]
     srt = np.sort(mean, axis=-1, kind="stable")[:, ::-1]
-    region = np.cumsum(srt, axis=1, dtype=F32) > F32(1 - error)
+    from .scoring import cumsum_f32  # jnp.cumsum's association order (associative_scan), see oracle/scoring.py
+
+    region = cumsum_f32(srt) > F32(1 - error)
     first = np.argmax(region, axis=1)
     return [labels[i, : first[i] + 1].tolist() for i in range(mean.shape[0])]
 

@@ -9,10 +9,13 @@ Follows:
 with jax 0.4.30 semantics for ``jnp.argsort`` (stable ascending), ``jnp.linspace`` (start*(1-i/(n-1)) +
 stop*(i/(n-1)), last point = stop) and ``jnp.quantile`` (method="linear").
 
-Order of float additions: ``jnp.cumsum`` lowers to an XLA scan whose association order is an
-implementation detail that cannot be observed here (JAX is not installable); this oracle DEFINES it as
-the sequential inclusive float32 prefix sum (numpy ``cumsum``) and the CUDA kernel follows the same
-order, so scores, sets and bins are compared bit-for-bit against *this* definition.
+Order of float additions in ``jnp.cumsum``: at jax 0.4.30 the cumulative-reduction primitives lower, on every
+platform but TPU, through ``jax.lax.associative_scan`` (jax/_src/lax/control_flow/loops.py,
+``_cumulative_reduction_primitive``: default lowering ``partial(associative_scan, reduce_fn)``; reduce_window is
+registered for 'tpu' only, a size-dependent choice for 'cuda'/'rocm').  The reference's JAX-CPU path therefore
+sums in associative_scan's recursive pairwise order, restated in ``cumsum_f32`` below; the CUDA kernels follow the
+same tree, so scores, sets and bins are compared bit-for-bit.  (JAX is not installable here, so this order is
+restated from the pinned source, not observed.)
 Parity pinned only by the simple-score case of tests/fortuna/test_conformal_methods.py:37-53;
 everything else here is "parity unpinned" (reference tests check shapes only; ECE has no test).
 """
@@ -27,6 +30,26 @@ def _f32(x):
 
 
 # ----------------------------------------------------------------------------- conformal scores
+def cumsum_f32(x):
+    """jnp.cumsum(x, axis=-1) in float32 == jax.lax.associative_scan(add, x): combine adjacent pairs, scan the
+    half-length array recursively (those are the odd positions), then even position 2i = odd[i-1] + x[2i]."""
+    x = _f32(x)
+    n = x.shape[-1]
+    if n < 2:
+        return x.copy()
+    reduced = (x[..., 0:-1:2] + x[..., 1::2]).astype(F32)
+    odd = cumsum_f32(reduced)
+    if n % 2 == 0:
+        even = (odd[..., :-1] + x[..., 2::2]).astype(F32)
+    else:
+        even = (odd + x[..., 2::2]).astype(F32)
+    out = np.empty_like(x)
+    out[..., 0] = x[..., 0]
+    out[..., 2::2] = even
+    out[..., 1::2] = odd
+    return out
+
+
 def descending_perm(probs):
     """argsort(probs, axis=1)[:, ::-1] with a stable ascending sort: descending values, ties broken
     by LARGER index first."""
@@ -40,7 +63,7 @@ def aps_cumsums(probs):
     probs = _f32(probs)
     perm = descending_perm(probs)
     srt = np.take_along_axis(probs, perm, axis=1)
-    cs = np.cumsum(srt, axis=1, dtype=F32)
+    cs = cumsum_f32(srt)
     out = np.empty_like(cs)
     np.put_along_axis(out, perm, cs, axis=1)
     return out

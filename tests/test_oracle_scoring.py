@@ -25,6 +25,38 @@ def test_reference_shape_cases():
         assert len(Sc.conformal_sets(vs, ts, 0.05)[2]) == 2
 
 
+def _tree_prefix(x):
+    """associative_scan(add) on a python list of float32, straight from its definition."""
+    n = len(x)
+    if n < 2:
+        return list(x)
+    red = [np.float32(x[2 * i] + x[2 * i + 1]) for i in range(n // 2)]
+    odd = _tree_prefix(red)
+    out = [None] * n
+    out[0] = x[0]
+    for i in range(n // 2):
+        out[2 * i + 1] = odd[i]
+    for i in range(1, (n + 1) // 2):
+        out[2 * i] = np.float32(odd[i - 1] + x[2 * i])
+    return out
+
+
+def test_cumsum_f32_is_associative_scan_and_padding_invariant():
+    r = np.random.default_rng(3)
+    for n in (1, 2, 3, 5, 8, 9, 31, 100, 1000, 1001):
+        x = r.random((3, n)).astype(np.float32)
+        got = Sc.cumsum_f32(x)
+        for row in range(3):
+            assert got[row].tolist() == [float(v) for v in _tree_prefix([np.float32(v) for v in x[row]])]
+        n2 = 1
+        while n2 < n:
+            n2 *= 2
+        xp = np.zeros((3, 2 * n2), np.float32)
+        xp[:, :n] = x
+        assert np.array_equal(Sc.cumsum_f32(xp)[:, :n], got)  # zero padding to a power of two changes no prefix
+        np.testing.assert_allclose(got, np.cumsum(x.astype(np.float64), axis=1), rtol=2e-6)
+
+
 def test_aps_definition_by_brute_force():
     r = np.random.default_rng(0)
     p = P.softmax(np.round(2 * r.standard_normal((40, 9))).astype(np.float32))  # many ties
@@ -32,10 +64,14 @@ def test_aps_definition_by_brute_force():
     for b in range(p.shape[0]):
         order = sorted(range(9), key=lambda c: (p[b, c], c), reverse=True)  # desc value, ties: larger index first
         assert order == Sc.descending_perm(p)[b].tolist()
-        run = np.float32(0)
-        for c in order:
-            run = np.float32(run + p[b, c])
-            assert allc[b, c] == run
+        # the prefix sum at each rank, written out as the explicit pairwise tree of jax.lax.associative_scan
+        srt = [np.float32(p[b, c]) for c in order]
+        for c, want in zip(order, _tree_prefix(srt)):
+            assert allc[b, c] == want
+        run = np.float64(0)
+        for c in order:  # and, independently of the association order, the float64 sequential sum to 1e-6
+            run += np.float64(p[b, c])
+            assert abs(float(allc[b, c]) - run) < 1e-6
     t = r.integers(0, 9, 40)
     assert np.array_equal(Sc.aps_score(p, t), allc[np.arange(40), t])
     top = p.argmax(-1)

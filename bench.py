@@ -338,6 +338,9 @@ def run_gpu_arm(args):
             e2e["d2h_bytes_per_step"] *= world
             e2e["sharding"] = f"inputs sharded over {world} ranks (B per rank = {B}), no collective"
         line["e2e"] = e2e
+        if world == 1:
+            # the same predictive outputs starting one stage earlier, from HOST features through the last-layer GEMM
+            line["e2e_from_features"] = pipeline.bench_e2e_from_features(S, B, args.D, Cn, dev, WANT, calib, args, UNIT)
     if rank == 0 and world == 1 and not args.no_extras:
         try:
             from fortuna_b200.bench_extras import last_layer_extras, sampler_extras
@@ -365,6 +368,7 @@ def main():
     ap.add_argument("--S", type=int, default=S_FULL)
     ap.add_argument("--B", type=int, default=B_FULL)
     ap.add_argument("--C", type=int, default=C_FULL)
+    ap.add_argument("--D", type=int, default=2048, help="last-layer feature width for e2e_from_features / GEMM extras")
     ap.add_argument("--cpu-rows-per-core", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-batch", type=int, default=4096)

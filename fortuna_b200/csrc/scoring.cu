@@ -481,27 +481,33 @@ __global__ void __launch_bounds__(256) conformal_sets_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxBins = 32;
 
+__device__ __forceinline__ unsigned long long conf_fixed(float conf) {
+  // confidences are probabilities; anything negative or NaN contributes 0 (it is in no bin anyway)
+  return conf > 0.0f ? (unsigned long long)((double)conf * 1099511627776.0) : 0ull;  // 2^40
+}
+
 __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__ probs, int B, int C,
                                                        const int32_t* __restrict__ preds,
                                                        const int32_t* __restrict__ targets,
                                                        const float* __restrict__ thresholds, int n_bins,
                                                        int32_t* __restrict__ bin_idx, int32_t* __restrict__ counts,
-                                                       float* __restrict__ conf_sums, int32_t* __restrict__ correct,
-                                                       float* __restrict__ brier_sum) {
+                                                       int32_t* __restrict__ correct, float* __restrict__ scratch) {
+  // Float sums are accumulated in 64-bit fixed point (confidences in units of 2^-40, Brier terms of 2^-38):
+  // integer atomics commute, so the result does not depend on the order CTAs and warps arrive in.
   __shared__ float thr[kMaxBins];
   __shared__ int s_counts[kMaxBins];
   __shared__ int s_correct[kMaxBins];
-  __shared__ float s_conf[kMaxBins];
-  __shared__ float s_brier;
+  __shared__ unsigned long long s_conf[kMaxBins];
+  __shared__ unsigned long long s_brier;
   __shared__ int s_ncorrect;
   if (threadIdx.x < kMaxBins) {
     thr[threadIdx.x] = threadIdx.x < n_bins ? thresholds[threadIdx.x] : CUDART_INF_F;
     s_counts[threadIdx.x] = 0;
     s_correct[threadIdx.x] = 0;
-    s_conf[threadIdx.x] = 0.0f;
+    s_conf[threadIdx.x] = 0ull;
   }
   if (threadIdx.x == 0) {
-    s_brier = 0.0f;
+    s_brier = 0ull;
     s_ncorrect = 0;
   }
   __syncthreads();
@@ -524,7 +530,7 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
       const bool ok = targets && targets[b] == preds[b];
       if (bin >= 0) {
         atomicAdd(&s_counts[bin], 1);
-        atomicAdd(&s_conf[bin], conf);
+        atomicAdd(&s_conf[bin], conf_fixed(conf));
         if (ok) atomicAdd(&s_correct[bin], 1);
       }
       if (ok) atomicAdd(&s_ncorrect, 1);
@@ -585,11 +591,11 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
         const bool ok = targets && y == pred;
         if (bin >= 0) {
           atomicAdd(&s_counts[bin], 1);
-          atomicAdd(&s_conf[bin], best);
+          atomicAdd(&s_conf[bin], conf_fixed(best));
           if (ok) atomicAdd(&s_correct[bin], 1);
         }
         if (ok) atomicAdd(&s_ncorrect, 1);
-        if (targets) atomicAdd(&s_brier, sq);
+        if (targets) atomicAdd(&s_brier, (unsigned long long)((double)sq * 274877906944.0));  // 2^38
       }
     }
   }
@@ -597,35 +603,61 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
   if (threadIdx.x < n_bins) {
     if (s_counts[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_counts[threadIdx.x]);
     if (s_correct[threadIdx.x]) atomicAdd(&correct[threadIdx.x], s_correct[threadIdx.x]);
-    if (s_counts[threadIdx.x]) atomicAdd(&conf_sums[threadIdx.x], s_conf[threadIdx.x]);
+    if (s_counts[threadIdx.x])
+      atomicAdd(reinterpret_cast<unsigned long long*>(scratch + 4) + threadIdx.x, s_conf[threadIdx.x]);
   }
   if (threadIdx.x == 0) {
-    // scratch layout of `result` until ece_finalize_kernel runs: [0] = float brier sum, [1] = int #correct
-    if (s_brier != 0.0f) atomicAdd(&brier_sum[0], s_brier);
-    if (s_ncorrect) atomicAdd(reinterpret_cast<int*>(&brier_sum[1]), s_ncorrect);
+    // scratch layout of `result` until ece_finalize_kernel runs: [0..1] = u64 Brier sum (2^-38 units),
+    // [2] = int #correct, [4 + 2i .. 4 + 2i + 1] = u64 confidence sum of bin i (2^-40 units)
+    if (s_brier) atomicAdd(reinterpret_cast<unsigned long long*>(scratch), s_brier);
+    if (s_ncorrect) atomicAdd(reinterpret_cast<int*>(scratch + 2), s_ncorrect);
   }
 }
 
-__global__ void ece_finalize_kernel(const int32_t* __restrict__ counts, const float* __restrict__ conf_sums,
+__global__ void ece_finalize_kernel(const int32_t* __restrict__ counts, float* __restrict__ conf_sums,
                                     const int32_t* __restrict__ correct, int n_bins, int B, int C,
                                     float* __restrict__ result) {
-  // result[0..3] = ECE, MCE, accuracy, brier; on entry result[0] holds the brier sum and result[1] the
-  // (int) number of correct predictions
-  const float brier_sum = result[0];
-  const int n_correct = reinterpret_cast<const int*>(result)[1];
+  // result[0..3] = ECE, MCE, accuracy, brier, then confs[n_bins], accs[n_bins]; on entry result[0] holds the
+  // brier sum and result[1] the (int) number of correct predictions
+  const float brier_sum = (float)((double)reinterpret_cast<const unsigned long long*>(result)[0] * (1.0 / 274877906944.0));
+  const int n_correct = reinterpret_cast<const int*>(result)[2];
+  float csum[kMaxBins];
+  for (int i = 0; i < n_bins; ++i) {  // read every fixed-point accumulator before result[4..] is overwritten
+    csum[i] = (float)((double)reinterpret_cast<const unsigned long long*>(result + 4)[i] * (1.0 / 1099511627776.0));
+    conf_sums[i] = csum[i];
+  }
   float ece = 0.0f, mce = -CUDART_INF_F;
   for (int i = 0; i < n_bins; ++i) {
     const float cnt = (float)counts[i];
     const float acc = counts[i] ? (float)correct[i] / cnt : 0.0f;    // nan_to_num(mean(empty)) = 0
-    const float conf = counts[i] ? conf_sums[i] / cnt : 0.0f;
+    const float conf = counts[i] ? csum[i] / cnt : 0.0f;
     const float w = cnt * fabsf(acc - conf);
     ece += w;
     mce = fmaxf(mce, w);
+    result[4 + i] = conf;           // per-bin mean confidence  (compute_counts_confs_accs: confs)
+    result[4 + n_bins + i] = acc;   // per-bin accuracy                                    (accs)
   }
   result[0] = ece / (float)B;
   result[1] = mce;
   result[2] = (float)n_correct / (float)B;
   result[3] = C > 1 ? brier_sum / (float)B : CUDART_NAN_F;
+}
+
+// ECE / MCE from (all-reduced) bin counters: the finalisation step of the B-sharded multi-GPU scoring.
+__global__ void ece_from_bins_kernel(const int32_t* __restrict__ counts, const float* __restrict__ conf_sums,
+                                     const int32_t* __restrict__ correct, int n_bins, float n_total,
+                                     float* __restrict__ result) {
+  float ece = 0.0f, mce = -CUDART_INF_F;
+  for (int i = 0; i < n_bins; ++i) {
+    const float cnt = (float)counts[i];
+    const float acc = counts[i] ? (float)correct[i] / cnt : 0.0f;
+    const float conf = counts[i] ? conf_sums[i] / cnt : 0.0f;
+    const float w = cnt * fabsf(acc - conf);
+    ece += w;
+    mce = fmaxf(mce, w);
+  }
+  result[0] = ece / n_total;
+  result[1] = mce;
 }
 
 __global__ void quantile_sorted_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ q, int nq,
@@ -773,14 +805,23 @@ extern "C" int fb200_ece_bins(const float* probs, int B, int C, const int32_t* p
   cudaError_t e;
   if ((e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_bins, st)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(correct, 0, sizeof(int32_t) * n_bins, st)) != cudaSuccess) return (int)e;
-  if ((e = cudaMemsetAsync(conf_sums, 0, sizeof(float) * n_bins, st)) != cudaSuccess) return (int)e;
-  if ((e = cudaMemsetAsync(result, 0, sizeof(float) * 4, st)) != cudaSuccess) return (int)e;
+  if ((reinterpret_cast<uintptr_t>(result) & 7u) != 0) return FB200_E_ALIGN;  // holds 64-bit accumulators meanwhile
+  if ((e = cudaMemsetAsync(result, 0, sizeof(float) * (4 + 2 * n_bins), st)) != cudaSuccess) return (int)e;
   int64_t blocks = C == 1 ? ((int64_t)B + 255) / 256 : ((int64_t)B + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ece_bins_kernel<<<(unsigned)blocks, 256, 0, st>>>(probs, B, C, preds, targets, thresholds, n_bins, bin_idx,
-                                                    counts, conf_sums, correct, result);
+                                                    counts, correct, result);
   FB200_LAUNCH_CHECK();
   ece_finalize_kernel<<<1, 1, 0, st>>>(counts, conf_sums, correct, n_bins, B, C, result);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_ece_from_bins(const int32_t* counts, const float* conf_sums, const int32_t* correct, int n_bins,
+                                   int64_t n_total, float* result, void* stream) {
+  if (!counts || !conf_sums || !correct || !result) return FB200_E_NULL;
+  if (n_bins <= 0 || n_total <= 0) return FB200_E_SHAPE;
+  ece_from_bins_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counts, conf_sums, correct, n_bins, (float)n_total, result);
   FB200_LAUNCH_CHECK();
   return 0;
 }

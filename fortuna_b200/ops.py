@@ -441,7 +441,7 @@ def ece_bins(probs, targets, thresholds, preds=None, want_bin_idx=False):
     counts = torch.empty(nb, dtype=torch.int32, device=dev)
     correct = torch.empty(nb, dtype=torch.int32, device=dev)
     conf_sums = torch.empty(nb, dtype=torch.float32, device=dev)
-    result = torch.empty(4, dtype=torch.float32, device=dev)
+    result = torch.empty(4 + 2 * nb, dtype=torch.float32, device=dev)
     bin_idx = torch.empty(B, dtype=torch.int32, device=dev) if want_bin_idx else None
     check(
         lib().fb200_ece_bins(
@@ -461,7 +461,19 @@ def ece_bins(probs, targets, thresholds, preds=None, want_bin_idx=False):
         ),
         "fb200_ece_bins",
     )
-    return {"counts": counts, "conf_sums": conf_sums, "correct": correct, "result": result, "bin_idx": bin_idx}
+    return {"counts": counts, "conf_sums": conf_sums, "correct": correct, "result": result[:4], "bin_idx": bin_idx,
+            "confs": result[4 : 4 + nb], "accs": result[4 + nb : 4 + 2 * nb]}
+
+
+def ece_from_bins(counts, conf_sums, correct, n_total):
+    """(ECE, MCE) float32[2] from additive bin counters (after an all-reduce over shards)."""
+    out = torch.empty(2, dtype=torch.float32, device=counts.device)
+    check(
+        lib().fb200_ece_from_bins(_ptr(counts, torch.int32), _ptr(conf_sums, torch.float32), _ptr(correct, torch.int32),
+                                  counts.numel(), int(n_total), _ptr(out), _stream()),
+        "fb200_ece_from_bins",
+    )
+    return out
 
 
 def quantile_sorted(x_sorted, q):

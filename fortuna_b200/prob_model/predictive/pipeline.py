@@ -64,7 +64,7 @@ class PredictivePipeline:
             from .sharded import SampleShardExchange
 
             self.exchange = SampleShardExchange(world, rank)
-        self.launches_per_step = 5 if world == 1 else 7
+        self.launches_per_step = 5 if world == 1 else 8
 
     # -------------------------------------------------------------------------------- K3 / K4
     def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor], kernel_events=None):
@@ -98,6 +98,7 @@ class PredictivePipeline:
         self.ece = ops.ece_bins(mean, t_local, self.thresholds)
         if self.world > 1:
             self.exchange.allreduce_bins(self.ece)
+            self.ece["result_global"] = ops.ece_from_bins(self.ece["counts"], self.ece["conf_sums"], self.ece["correct"], self.B)
         return self.mask, self.sizes, self.ece
 
 
@@ -118,7 +119,7 @@ def predictive_from_logits_batches(
     S, Bc, Cn = batches[0].shape
     n_b = len(batches)
     B = sum(int(b.shape[1]) for b in batches)
-    copy_s, comp_s = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    copy_s, comp_s, out_s = torch.cuda.Stream(device), torch.cuda.Stream(device), torch.cuda.Stream(device)
     zbuf = [torch.empty((S, Bc, Cn), dtype=batches[0].dtype, device=device) for _ in range(2)]
     tbuf = [torch.empty(Bc, dtype=torch.int32, device=device) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -138,6 +139,7 @@ def predictive_from_logits_batches(
     cur = torch.cuda.current_stream(device)
     copy_s.wait_stream(cur)
     comp_s.wait_stream(cur)
+    out_s.wait_stream(cur)
     b0 = 0
     for i, (hb, ht) in enumerate(zip(batches, target_batches)):
         k = i & 1
@@ -161,16 +163,159 @@ def predictive_from_logits_batches(
             m, sz = ops.conformal_sets(calib.val_sorted, sc, calib.threshold)
             mask[b0 : b0 + rows].copy_(m, non_blocking=True)
             sizes[b0 : b0 + rows].copy_(sz, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(comp_s)
+        # results of this batch go back to the host on their own stream while the next batch computes
+        with torch.cuda.stream(out_s):
+            out_s.wait_event(done)
+            for k2, v in list(full.items()) + list(vec.items()) + [("conformal_mask", mask), ("conformal_sizes", sizes)]:
+                host_out[k2][b0 : b0 + rows].copy_(v[b0 : b0 + rows], non_blocking=True)
         b0 += rows
     with torch.cuda.stream(comp_s):
         thr = torch.from_numpy(ece_thresholds(B)).to(device, non_blocking=True)
         ece = ops.ece_bins(full["mean"], tfull, thr)
-        for k2, v in list(full.items()) + list(vec.items()) + [("conformal_mask", mask), ("conformal_sizes", sizes)]:
-            host_out[k2].copy_(v, non_blocking=True)
         host_out["ece_result"].copy_(ece["result"], non_blocking=True)
     cur.wait_stream(comp_s)
     cur.wait_stream(copy_s)
+    cur.wait_stream(out_s)
     return host_out
+
+
+def predictive_from_feature_batches(
+    x_batches: Iterable[torch.Tensor],
+    target_batches: Iterable[torch.Tensor],
+    wt: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    log_temp: Optional[torch.Tensor],
+    calib: ConformalCalibration,
+    want: Sequence[str],
+    device,
+    sample_idx: Optional[torch.Tensor] = None,
+    logits_dtype=torch.float32,
+    host_out: Optional[Dict[str, torch.Tensor]] = None,
+):
+    """The loader-shaped predictive call for a last-layer posterior (what ``prob_model.predictive.mean/...``
+    amounts to with ``freeze_fun``): pinned HOST feature batches ``[Bc, D]`` (bf16) stream to the device, the
+    S-batched last-layer contraction (K2, tcgen05) forms the calibrated logits of every posterior sample from the
+    device-resident sample bank ``wt [n, C, D]`` (bf16, K-major) / ``bias [n, C]`` - ``sample_idx`` (int32 [S]) are
+    the ``posterior.sample`` draws, None = every stored sample once - and the logits go straight into the
+    single-pass reductions (K3/K4) and the conformal / ECE scoring (K5-K7).  The [S,B,C] logits never leave the
+    GPU.  Returns pinned host tensors over all inputs."""
+    x_batches = list(x_batches)
+    target_batches = list(target_batches)
+    Bc, D = x_batches[0].shape
+    S = wt.shape[0] if sample_idx is None else sample_idx.numel()
+    Cn = wt.shape[1]
+    B = sum(int(b.shape[0]) for b in x_batches)
+    copy_s, comp_s, out_s = torch.cuda.Stream(device), torch.cuda.Stream(device), torch.cuda.Stream(device)
+    xbuf = [torch.empty((Bc, D), dtype=x_batches[0].dtype, device=device) for _ in range(2)]
+    tbuf = [torch.empty(Bc, dtype=torch.int32, device=device) for _ in range(2)]
+    zbuf = torch.empty((S, Bc, Cn), dtype=logits_dtype, device=device)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    bc_names = [w for w in want if w in ("mean", "aleatoric_variance", "epistemic_variance", "variance", "std")]
+    full = {w: torch.empty((B, Cn), dtype=torch.float32, device=device) for w in bc_names}
+    vec = {w: torch.empty(B, dtype=torch.int32 if w == "mode" else torch.float32, device=device)
+           for w in want if w not in bc_names and w != "ensemble_log_prob"}
+    tfull = torch.empty(B, dtype=torch.int32, device=device)
+    mask = torch.empty((B, Cn), dtype=torch.uint8, device=device)
+    sizes = torch.empty(B, dtype=torch.int32, device=device)
+    if host_out is None:
+        host_out = {}
+        for k, v in list(full.items()) + list(vec.items()) + [("conformal_mask", mask), ("conformal_sizes", sizes)]:
+            host_out[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+        host_out["ece_result"] = torch.empty(4, dtype=torch.float32, pin_memory=True)
+    cur = torch.cuda.current_stream(device)
+    copy_s.wait_stream(cur)
+    comp_s.wait_stream(cur)
+    out_s.wait_stream(cur)
+    b0 = 0
+    for i, (hx, ht) in enumerate(zip(x_batches, target_batches)):
+        k = i & 1
+        rows = int(hx.shape[0])
+        with torch.cuda.stream(copy_s):
+            if i >= 2:
+                copy_s.wait_event(free[k])
+            xbuf[k][:rows].copy_(hx, non_blocking=True)
+            tbuf[k][:rows].copy_(ht, non_blocking=True)
+            ready[k].record(copy_s)
+        with torch.cuda.stream(comp_s):
+            comp_s.wait_event(ready[k])
+            xin = xbuf[k][:rows]
+            tin = tbuf[k][:rows]
+            z = zbuf if rows == Bc else torch.empty((S, rows, Cn), dtype=logits_dtype, device=device)
+            ops.last_layer_logits(xin, wt, bias, log_temp, w_layout=ops.W_SCD, out=z, sample_idx=sample_idx)
+            free[k].record(comp_s)
+            outs = {w: full[w][b0 : b0 + rows] for w in bc_names}
+            outs.update({w: vec[w][b0 : b0 + rows] for w in vec})
+            ops.bma_reduce_cls(z, want, targets=tin, out=outs)
+            tfull[b0 : b0 + rows].copy_(tin, non_blocking=True)
+            sc = ops.aps_scores(full["mean"][b0 : b0 + rows], None)
+            m, sz = ops.conformal_sets(calib.val_sorted, sc, calib.threshold)
+            mask[b0 : b0 + rows].copy_(m, non_blocking=True)
+            sizes[b0 : b0 + rows].copy_(sz, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(comp_s)
+        # results of this batch go back to the host on their own stream while the next batch computes
+        with torch.cuda.stream(out_s):
+            out_s.wait_event(done)
+            for k2, v in list(full.items()) + list(vec.items()) + [("conformal_mask", mask), ("conformal_sizes", sizes)]:
+                host_out[k2][b0 : b0 + rows].copy_(v[b0 : b0 + rows], non_blocking=True)
+        b0 += rows
+    with torch.cuda.stream(comp_s):
+        thr = torch.from_numpy(ece_thresholds(B)).to(device, non_blocking=True)
+        ece = ops.ece_bins(full["mean"], tfull, thr)
+        host_out["ece_result"].copy_(ece["result"], non_blocking=True)
+    cur.wait_stream(comp_s)
+    cur.wait_stream(copy_s)
+    cur.wait_stream(out_s)
+    return host_out
+
+
+def bench_e2e_from_features(S, B, D, Cn, device, want, calib, args, unit, logits_dtype=torch.float32):
+    """Times predictive_from_feature_batches: pinned host features [B, D] bf16 in, pinned host results out; the S
+    last-layer samples are resident on the device (that is where the chains left them)."""
+    Bc = min(8192, B)
+    n_batches = (B + Bc - 1) // Bc
+    gen = torch.Generator(device=device)
+    gen.manual_seed(11)
+    wt = (torch.empty((S, Cn, D), device=device, dtype=torch.float32).normal_(generator=gen) / D ** 0.5).to(torch.bfloat16)
+    bias = torch.empty((S, Cn), device=device, dtype=torch.float32).normal_(generator=gen)
+    log_temp = torch.tensor([0.3], device=device)
+    host_x, host_t = [], []
+    for _ in range(n_batches):
+        d = torch.empty((Bc, D), device=device, dtype=torch.float32).normal_(generator=gen).to(torch.bfloat16)
+        hx = torch.empty((Bc, D), dtype=torch.bfloat16, pin_memory=True)
+        hx.copy_(d)
+        host_x.append(hx)
+        host_t.append(torch.randint(0, Cn, (Bc,), dtype=torch.int32).pin_memory())
+        del d
+    host_out = None
+    times = []
+    for it in range(1 + args.e2e_steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        host_out = predictive_from_feature_batches(host_x, host_t, wt, bias, log_temp, calib, want, device,
+                                                   logits_dtype=logits_dtype, host_out=host_out)
+        torch.cuda.synchronize()
+        if it > 0:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    h2d = n_batches * (Bc * D * 2 + Bc * 4)
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    return {
+        "value": float(S) * B * Cn / sec,
+        "unit": unit,
+        "ms_per_step": sec * 1e3,
+        "h2d_bytes_per_step": int(h2d),
+        "d2h_bytes_per_step": int(d2h),
+        "steps": len(times),
+        "D": D,
+        "gemm_flops_per_step": 2.0 * S * B * D * Cn,
+        "logits": "float32, device-only" if logits_dtype == torch.float32 else "bfloat16, device-only",
+        "api": "fortuna_b200.prob_model.predictive.pipeline.predictive_from_feature_batches",
+        "what": f"host features [B,{D}] bf16 -> last-layer GEMM over {S} resident samples -> reductions -> APS sets + ECE -> host",
+    }
 
 
 def bench_e2e(S, B, Cn, device, want, calib, args, unit):

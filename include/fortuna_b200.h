@@ -239,11 +239,16 @@ int fb200_conformal_sets(const float* val_scores_sorted, int n_val, const float*
 /* ECE / MCE binning (fortuna/metric/classification.py:43-95, 98-133, 147-181): conf = max_c probs (C > 1)
  * or probs itself (C == 1); thresholds = the caller's float32 linspace(1/B, 1, n_bins) (device, n_bins <= 32).
  * Outputs: bin_idx int32[B] (optional; -1 = in no bin), counts int32[n_bins], conf_sums float32[n_bins],
- * correct int32[n_bins] (#(targets == preds)), and result float32[4] = {ECE, MCE, accuracy, brier (C>1 only)}.
+ * correct int32[n_bins] (#(targets == preds)), and result float32[4 + 2*n_bins] = {ECE, MCE, accuracy,
+ * brier (C>1 only), confs[n_bins] (mean confidence per bin, 0 if empty), accs[n_bins] (accuracy per bin, 0 if empty)}.
  * preds: optional int32[B]; NULL = argmax_c probs (first maximum).  workspace: none (outputs are zeroed here). */
 int fb200_ece_bins(const float* probs, int B, int C, const int32_t* preds, const int32_t* targets,
                    const float* thresholds, int n_bins, int32_t* bin_idx, int32_t* counts, float* conf_sums,
                    int32_t* correct, float* result, void* stream);
+/* result[2] = {ECE, MCE} over n_total data points from bin counters that were summed over shards (the counters
+ * fb200_ece_bins returns are additive: all-reduce them across the ranks of a B-sharded evaluation, then call this). */
+int fb200_ece_from_bins(const int32_t* counts, const float* conf_sums, const int32_t* correct, int n_bins,
+                        int64_t n_total, float* result, void* stream);
 /* jnp.quantile(x, q) for sorted ascending x[n], method="linear"
  * (fortuna/conformal/regression/quantile.py:89-90, onedim_uncertainty.py:89-90): out[nq]. */
 int fb200_quantile_sorted(const float* x_sorted, int64_t n, const float* q, int nq, float* out, void* stream);

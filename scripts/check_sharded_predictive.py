@@ -60,6 +60,10 @@ def main():
     ok_counts = np.array_equal(ece["counts"].cpu().numpy(), ece_f["counts"].cpu().numpy())
     print(f"rank {rank}: outputs mismatching: {bad}; conformal mask flips vs single GPU: {flips} of {mask.numel()}; "
           f"ECE counts equal: {ok_counts}; ece {float(ece['result'][0]):.6f} (local rows) ")
+    ece_ok = np.allclose(ece["result_global"].cpu().numpy(), ece_f["result"][:2].cpu().numpy(), rtol=1e-5, atol=1e-7)
+    print(f"rank {rank}: global ECE/MCE after the bin all-reduce {ece['result_global'].cpu().numpy()} vs single GPU "
+          f"{ece_f['result'][:2].cpu().numpy()}: {ece_ok}")
+    bad += 0 if ece_ok else 1
     tot = torch.tensor([bad + (0 if ok_counts else 1) + (1 if flips > mask.numel() * 1e-4 else 0)], device=dev)
     dist.all_reduce(tot)
     dist.destroy_process_group()

@@ -175,3 +175,44 @@ def test_last_layer_cuda_core_path(cuda, S, B, D, C, dtype, layout):
         w_layout=ops.W_SCD if layout == "scd" else ops.W_SDC, path=1,
     )
     np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-5, atol=1e-5 * np.sqrt(D))
+
+
+def test_pipeline_from_host_features_matches_oracle(cuda):
+    """The loader-shaped last-layer predictive: host features -> K2 -> K3 -> K5-K7 -> host, vs the oracle chain."""
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.predictive import pipeline
+    from oracle import scoring as Sc
+
+    r = np.random.default_rng(21)
+    n, S, B, D, C = 6, 9, 300, 128, 40
+    x = r.standard_normal((B, D)).astype(np.float32)
+    w = (r.standard_normal((n, D, C)) / np.sqrt(D)).astype(np.float32)
+    bias = r.standard_normal((n, C)).astype(np.float32)
+    lt = np.array([0.2], np.float32)
+    t = r.integers(0, C, B).astype(np.int32)
+    key = ops.PRNGKey(4, cuda)
+    idx = ops.sample_indices(key, S, n)
+    idx_np = idx.cpu().numpy()
+    z = P.last_layer_logits(x, w[idx_np], bias[idx_np], lt, bf16_inputs=True)  # [S,B,C] oracle logits
+    xs = P.round_to_bf16(x)
+    hx = [torch.from_numpy(xs[i : i + 128]).to(torch.bfloat16).pin_memory() for i in range(0, B, 128)]
+    ht = [torch.from_numpy(t[i : i + 128]).pin_memory() for i in range(0, B, 128)]
+    wt = ops.transpose_w_bf16(torch.from_numpy(w).to(cuda))
+    val_probs = P.softmax((2 * r.standard_normal((500, C))).astype(np.float32))
+    val_t = r.integers(0, C, 500)
+    val_sorted = torch.from_numpy(np.sort(Sc.aps_score(val_probs, val_t))).to(cuda)
+    calib = pipeline.ConformalCalibration(val_sorted, 500, 0.1)
+    want = ("mean", "entropy", "log_prob", "mode")
+    out = pipeline.predictive_from_feature_batches(hx, ht, wt, torch.from_numpy(bias).to(cuda), torch.from_numpy(lt).to(cuda),
+                                                   calib, want, cuda, sample_idx=idx)
+    torch.cuda.synchronize()
+    # bf16 GEMM with float32 accumulation in a different order than the oracle's: logits agree to ~1e-3 relative
+    np.testing.assert_allclose(out["mean"].numpy(), P.cls_mean(z), rtol=5e-3, atol=1e-5)
+    np.testing.assert_allclose(out["entropy"].numpy(), P.cls_entropy(z), rtol=5e-3, atol=1e-4)
+    np.testing.assert_allclose(out["log_prob"].numpy(), P.cls_log_prob(z, t), rtol=5e-3, atol=1e-3)
+    # scoring is integer-exact GIVEN the device mean: recompute the oracle's sets from the returned mean
+    mean = out["mean"].numpy()
+    conds, sizes, _ = Sc.conformal_sets(val_sorted.cpu().numpy(), Sc.aps_cumsums(mean), 0.1)
+    assert np.array_equal(out["conformal_mask"].numpy().astype(bool), conds)
+    assert np.array_equal(out["conformal_sizes"].numpy(), sizes)
+    np.testing.assert_allclose(out["ece_result"].numpy()[0], Sc.expected_calibration_error(mean.argmax(-1), mean, t), rtol=1e-5, atol=1e-7)

@@ -246,7 +246,7 @@ def run_gpu_arm(args):
     del val_logits, val_mean
     calib = pipeline.ConformalCalibration(val_sorted, N_VAL, ERROR)
 
-    runner = pipeline.PredictivePipeline(S, B, Cn, dev, WANT, world=world, rank=rank)
+    runner = pipeline.PredictivePipeline(S, B, Cn, dev, WANT, world=world, rank=rank, transport=args.transport)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (args.steps + 1))]
 
     def one_step(i=None):
@@ -287,8 +287,9 @@ def run_gpu_arm(args):
     value = elems_per_step / (ms_per_step * 1e-3)
 
     # roofline of the dominant kernel: algorithmic bytes per launch / measured launch time
-    n_bc_out = 3 if world == 1 else 3  # mean + two variance arrays (fused) or three partial-sum arrays
-    alg_bytes = 4.0 * S * B * Cn + 4.0 * n_bc_out * B * Cn + 4.0 * B * 6
+    # logits read once + outputs written once: single GPU -> mean + two variance arrays [B,C] and six [B] vectors;
+    # shard mode -> one slot row of 2C+4 floats per input (sum p, sum p^2, three scalars)
+    alg_bytes = 4.0 * S * B * Cn + (4.0 * 3 * B * Cn + 4.0 * B * 6 if world == 1 else 4.0 * B * (2 * Cn + 4))
     peak, peak_src = _peaks()
     achieved = alg_bytes / (reduce_ms * 1e-3) / 1e9
     traffic = None
@@ -313,7 +314,9 @@ def run_gpu_arm(args):
         "config": {
             "workload": f"c4 predictive z[S={S},B={B},C={Cn}] f32 -> BMA reductions + APS conformal sets + ECE",
             "S_per_gpu": S, "B": B, "C": Cn, "n_val": N_VAL, "error": ERROR,
-            "parallelism": "single GPU" if world == 1 else f"S-sharded x{world}: reduce-scatter of partial sums over B + all-gather of (max,sumexp)",
+            "parallelism": "single GPU" if world == 1 else (
+                f"S-sharded x{world}: partial sums exchanged by " + ("ONE NCCL all-to-all" if runner.transport == "nccl" else
+                "peer stores from the reduction kernel over NVLink (symmetric memory) + barrier")),
             "l2": "inputs (16.8 GB) larger than L2; no flush needed",
         },
         "roofline": {
@@ -372,6 +375,8 @@ def main():
     ap.add_argument("--cpu-rows-per-core", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-batch", type=int, default=4096)
+    ap.add_argument("--transport", default="p2p", choices=["nccl", "p2p"],
+                    help="N > 1 exchange: one NCCL all-to-all, or peer stores from the reduction kernel over NVLink")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

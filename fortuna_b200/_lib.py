@@ -68,10 +68,6 @@ class ClsOutputs(C.Structure):
     ]
 
 
-class ClsPartials(C.Structure):
-    _fields_ = [(n, _P) for n in ("sum_p", "sum_p2", "sum_pq", "sum_plogp", "ll_max", "ll_sumexp")]
-
-
 class RegOutputs(C.Structure):
     _fields_ = [
         (n, _P)
@@ -109,12 +105,10 @@ SIGNATURES = {
     "fb200_bank_put_f32": (_i, [_P, _i64, _i, _P, _P]),
     "fb200_last_layer_logits": (_i, [_P, _P, _P, _P, _P, _i, _P, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
     "fb200_transpose_w_bf16": (_i, [_P, _i, _P, _i, _i, _i, _P]),
-    "fb200_bma_reduce_cls": (
-        _i,
-        [_P, _i, _P, _P, _i, _i, _i, C.POINTER(ClsOutputs), C.POINTER(ClsPartials), _P],
-    ),
-    "fb200_bma_finalize_cls": (_i, [C.POINTER(ClsPartials), _i, _i, _i, C.POINTER(ClsOutputs), _P]),
-    "fb200_merge_lse_pairs": (_i, [_P, _P, _i, _i, _P, _P, _P]),
+    "fb200_bma_reduce_cls": (_i, [_P, _i, _P, _P, _i, _i, _i, C.POINTER(ClsOutputs), _P]),
+    "fb200_cls_slot_row_floats": (_sz, [_i]),
+    "fb200_bma_reduce_cls_shard": (_i, [_P, _i, _P, _P, _i, _i, _i, _i, _P, _P]),
+    "fb200_bma_finalize_cls_slots": (_i, [_P, _i, _i, _i, _i, C.POINTER(ClsOutputs), _P]),
     "fb200_bma_reduce_reg": (_i, [_P, _P, _P, _i, _i, _i, C.POINTER(RegOutputs), _P]),
     "fb200_aps_scores": (_i, [_P, _P, _i, _i, _P, _P, _P]),
     "fb200_simple_scores": (_i, [_P, _P, _i, _i, _P, _P]),

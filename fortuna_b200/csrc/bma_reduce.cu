@@ -44,7 +44,8 @@ struct ClsArgs {
   const int32_t* targets;
   int S, B, C;
   fb200_cls_outputs_t out;
-  fb200_cls_partials_t part;
+  const unsigned long long* slot_ptrs;  // shard mode: device array [n_ranks] of float* (local or peer memory)
+  int n_ranks, rows_per_rank;
   int partial_mode;
   int n_tiles;
   int n_stages;
@@ -338,24 +339,34 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
     const float inv_Sf = 1.0f / Sf;
     const float spl_row = 0.6931471805599453f * (group_sum<G>(spl) - sum_l);  // sum_s sum_c p ln p of this row
     if (a.partial_mode) {
+      // shard mode: this rank's partial sums for row b go to the slot of the rank that owns the row after the
+      // exchange (owner = b / rows_per_rank).  A slot row is [sum_p C | sum_p2 C | sum plogp, ll_max, ll_sumexp, pad];
+      // the slot pointer may be peer memory (NVLink stores straight from this epilogue) or a local send buffer.
       if (valid_row) {
+        const int owner = b / a.rows_per_rank;
+        const int lr = b - owner * a.rows_per_rank;
+        float* base = reinterpret_cast<float*>(a.slot_ptrs[owner]) + (size_t)lr * (size_t)(2 * C + 4);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
           const int c0 = (g + G * j) * VEC;
           if (c0 < C) {
+            if (VEC == 4) {
+              *reinterpret_cast<float4*>(base + c0) = make_float4(sp[j][0], sp[j][1], sp[j][2], sp[j][3]);
+              *reinterpret_cast<float4*>(base + C + c0) = make_float4(sp2[j][0], sp2[j][1], sp2[j][2], sp2[j][3]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-              const size_t o = (size_t)b * C + c0 + k;
-              a.part.sum_p[o] = sp[j][k];
-              a.part.sum_p2[o] = sp2[j][k];
-              a.part.sum_pq[o] = sp[j][k] - sp2[j][k];
+              for (int k = 0; k < VEC; ++k) {
+                base[c0 + k] = sp[j][k];
+                base[C + c0 + k] = sp2[j][k];
+              }
             }
           }
         }
         if (g == 0) {
-          a.part.sum_plogp[b] = spl_row;
-          a.part.ll_max[b] = lmax;
-          a.part.ll_sumexp[b] = lsum;
+          base[2 * C] = spl_row;
+          base[2 * C + 1] = lmax;
+          base[2 * C + 2] = lsum;
+          base[2 * C + 3] = 0.0f;
         }
       }
       continue;
@@ -418,23 +429,34 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
 }
 
 // ------------------------------------------------------------------------------------------------
-// Finalise from (all-reduced) partial sums: one warp per row.
+// Finalise the rows this rank owns from the n_src slots it received (one per source rank, same row layout as
+// above): sums are taken in source-rank order (deterministic), the (max, sumexp) pairs are merged, then the same
+// finalisation as the single-GPU kernel.  One warp per row.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bma_finalize_cls_kernel(const fb200_cls_partials_t part, int s_total, int B,
-                                                               int C, const fb200_cls_outputs_t out, float log_S) {
+__global__ void __launch_bounds__(256) bma_finalize_slots_kernel(const float* __restrict__ slots, int n_src, int rows,
+                                                                 int C, int s_total, const fb200_cls_outputs_t out,
+                                                                 float log_S) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= B) return;
+  if (warp >= rows) return;
   const int b = warp;
+  const size_t RS = (size_t)(2 * C + 4);
+  const size_t src_stride = (size_t)rows * RS;
+  const float* row0 = slots + (size_t)b * RS;
   const float Sf = (float)s_total;
   float ent_terms = 0.0f;
   float best_v = -CUDART_INF_F;
   int best_c = 0x7FFFFFFF;
   for (int c = lane; c < C; c += 32) {
+    float sp = 0.0f, sp2 = 0.0f;
+    for (int r = 0; r < n_src; ++r) {
+      sp += row0[(size_t)r * src_stride + c];
+      sp2 += row0[(size_t)r * src_stride + C + c];
+    }
     const size_t o = (size_t)b * C + c;
-    const float mean = part.sum_p[o] / Sf;
-    const float av = part.sum_pq[o] / Sf;
-    const float ev = fmaxf(0.0f, __fsub_rn(part.sum_p2[o] / Sf, __fmul_rn(mean, mean)));
+    const float mean = sp / Sf;
+    const float av = (sp - sp2) / Sf;
+    const float ev = fmaxf(0.0f, __fsub_rn(sp2 / Sf, __fmul_rn(mean, mean)));
     if (mean > 0.0f) ent_terms = fmaf(mean, logf(mean), ent_terms);
     if (mean > best_v) {
       best_v = mean;
@@ -457,32 +479,25 @@ __global__ void __launch_bounds__(256) bma_finalize_cls_kernel(const fb200_cls_p
     }
   }
   if (lane == 0) {
-    const float alea = -part.sum_plogp[b] / Sf;
+    float plogp = 0.0f, M = -CUDART_INF_F;
+    for (int r = 0; r < n_src; ++r) {
+      plogp += row0[(size_t)r * src_stride + 2 * C];
+      M = fmaxf(M, row0[(size_t)r * src_stride + 2 * C + 1]);
+    }
+    float ssum = 0.0f;
+    for (int r = 0; r < n_src; ++r) {
+      const float mr = row0[(size_t)r * src_stride + 2 * C + 1];
+      const float sr = row0[(size_t)r * src_stride + 2 * C + 2];
+      if (mr > -CUDART_INF_F) ssum += sr * __expf(mr - M);
+      else if (sr != sr) ssum = sr;  // NaN propagates like the reference's logsumexp
+    }
+    const float alea = -plogp / Sf;
     if (out.entropy) out.entropy[b] = ent;
     if (out.aleatoric_entropy) out.aleatoric_entropy[b] = alea;
     if (out.epistemic_entropy) out.epistemic_entropy[b] = ent - alea;
     if (out.mode) out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
-    if (out.log_prob) out.log_prob[b] = (part.ll_max[b] + logf(part.ll_sumexp[b])) - log_S;
+    if (out.log_prob) out.log_prob[b] = (M + logf(ssum)) - log_S;
   }
-}
-
-__global__ void __launch_bounds__(256) merge_lse_pairs_kernel(const float* __restrict__ max_in,
-                                                              const float* __restrict__ sum_in, int R, int B,
-                                                              float* __restrict__ max_out,
-                                                              float* __restrict__ sum_out) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float M = -CUDART_INF_F;
-  for (int r = 0; r < R; ++r) M = fmaxf(M, max_in[(size_t)r * B + b]);
-  float s = 0.0f;
-  for (int r = 0; r < R; ++r) {
-    const float mr = max_in[(size_t)r * B + b];
-    const float sr = sum_in[(size_t)r * B + b];
-    if (mr > -CUDART_INF_F) s += sr * __expf(mr - M);
-    else if (sr != sr) s = sr;
-  }
-  max_out[b] = M;
-  sum_out[b] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -651,31 +666,18 @@ static int dispatch_cls(const ClsArgs& a, cudaStream_t st) {
 
 using namespace fb200;
 
-extern "C" int fb200_bma_reduce_cls(const void* logits, int dtype, const float* log_temp, const int32_t* targets,
-                                    int S, int B, int C, const fb200_cls_outputs_t* out,
-                                    const fb200_cls_partials_t* partials, void* stream) {
+static int reduce_cls_common(ClsArgs& a, const void* logits, int dtype, const float* log_temp,
+                             const int32_t* targets, int S, int B, int C, void* stream) {
   if (!logits) return FB200_E_NULL;
-  if ((out == nullptr) == (partials == nullptr)) return FB200_E_NULL;
   if (S <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
   if (C > 1024) return FB200_E_UNSUPPORTED;
   if (dtype != FB200_F32 && dtype != FB200_BF16) return FB200_E_UNSUPPORTED;
-  ClsArgs a{};
   a.logits = logits;
   a.log_temp = log_temp;
   a.targets = targets;
   a.S = S;
   a.B = B;
   a.C = C;
-  if (out) {
-    a.out = *out;
-    if ((a.out.log_prob || a.out.ensemble_log_prob) && !targets) return FB200_E_NULL;
-  } else {
-    a.part = *partials;
-    a.partial_mode = 1;
-    if (!a.part.sum_p || !a.part.sum_p2 || !a.part.sum_pq || !a.part.sum_plogp || !a.part.ll_max ||
-        !a.part.ll_sumexp)
-      return FB200_E_NULL;
-  }
   a.log_S = logf((float)S);
   const size_t esz = dtype == FB200_F32 ? 4 : 2;
   a.bulk_ok = fb200_aligned16(logits) && (((size_t)B * (size_t)C * esz) % 16 == 0);
@@ -683,26 +685,38 @@ extern "C" int fb200_bma_reduce_cls(const void* logits, int dtype, const float* 
   return dispatch_cls<__nv_bfloat16>(a, (cudaStream_t)stream);
 }
 
-extern "C" int fb200_bma_finalize_cls(const fb200_cls_partials_t* partials, int s_total, int B, int C,
-                                      const fb200_cls_outputs_t* out, void* stream) {
-  if (!partials || !out) return FB200_E_NULL;
-  if (!partials->sum_p || !partials->sum_p2 || !partials->sum_pq || !partials->sum_plogp) return FB200_E_NULL;
-  if (out->log_prob && (!partials->ll_max || !partials->ll_sumexp)) return FB200_E_NULL;
-  if (out->ensemble_log_prob) return FB200_E_UNSUPPORTED;
-  if (s_total <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
-  const int64_t threads = (int64_t)B * 32;
-  bma_finalize_cls_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      *partials, s_total, B, C, *out, logf((float)s_total));
-  FB200_LAUNCH_CHECK();
-  return 0;
+extern "C" int fb200_bma_reduce_cls(const void* logits, int dtype, const float* log_temp, const int32_t* targets,
+                                    int S, int B, int C, const fb200_cls_outputs_t* out, void* stream) {
+  if (!out) return FB200_E_NULL;
+  ClsArgs a{};
+  a.out = *out;
+  if ((a.out.log_prob || a.out.ensemble_log_prob) && !targets) return FB200_E_NULL;
+  return reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
 }
 
-extern "C" int fb200_merge_lse_pairs(const float* max_in, const float* sumexp_in, int R, int B, float* max_out,
-                                     float* sumexp_out, void* stream) {
-  if (!max_in || !sumexp_in || !max_out || !sumexp_out) return FB200_E_NULL;
-  if (R <= 0 || B <= 0) return FB200_E_SHAPE;
-  merge_lse_pairs_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(max_in, sumexp_in, R, B, max_out,
-                                                                            sumexp_out);
+extern "C" size_t fb200_cls_slot_row_floats(int C) { return C > 0 ? (size_t)(2 * C + 4) : 0; }
+
+extern "C" int fb200_bma_reduce_cls_shard(const void* logits, int dtype, const float* log_temp,
+                                          const int32_t* targets, int S, int B, int C, int n_ranks,
+                                          const uint64_t* slot_ptrs, void* stream) {
+  if (!slot_ptrs) return FB200_E_NULL;
+  if (n_ranks <= 0 || B <= 0 || B % n_ranks != 0) return FB200_E_SHAPE;
+  ClsArgs a{};
+  a.partial_mode = 1;
+  a.slot_ptrs = reinterpret_cast<const unsigned long long*>(slot_ptrs);
+  a.n_ranks = n_ranks;
+  a.rows_per_rank = B / n_ranks;
+  return reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
+}
+
+extern "C" int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int rows, int C, int s_total,
+                                            const fb200_cls_outputs_t* out, void* stream) {
+  if (!slots || !out) return FB200_E_NULL;
+  if (out->ensemble_log_prob) return FB200_E_UNSUPPORTED;  // per-sample values live on the rank that holds the sample
+  if (n_src <= 0 || rows <= 0 || C <= 0 || s_total <= 0) return FB200_E_SHAPE;
+  const int64_t threads = (int64_t)rows * 32;
+  bma_finalize_slots_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      slots, n_src, rows, C, s_total, *out, logf((float)s_total));
   FB200_LAUNCH_CHECK();
   return 0;
 }

@@ -263,7 +263,6 @@ def bma_reduce_cls(logits, want, targets=None, log_temp=None, out=None):
             B,
             Cn,
             C.byref(st),
-            None,
             _stream(),
         ),
         "fb200_bma_reduce_cls",
@@ -271,26 +270,28 @@ def bma_reduce_cls(logits, want, targets=None, log_temp=None, out=None):
     return outs
 
 
-def alloc_cls_partials(B, Cn, device):
-    p = {n: torch.empty((B, Cn), dtype=torch.float32, device=device) for n in ("sum_p", "sum_p2", "sum_pq")}
-    for n in ("sum_plogp", "ll_max", "ll_sumexp"):
-        p[n] = torch.empty(B, dtype=torch.float32, device=device)
-    return p
+def cls_slot_row_floats(Cn):
+    """Floats per row of a shard slot: [sum p (C) | sum p^2 (C) | sum plogp, ll_max, ll_sumexp, 0]."""
+    return int(lib().fb200_cls_slot_row_floats(int(Cn)))
 
 
-def _partials_struct(p):
-    st = _lib.ClsPartials()
-    for name, t in p.items():
-        setattr(st, name, t.data_ptr())
-    return st
+def alloc_cls_slots(n_ranks, rows_per_rank, Cn, device):
+    """[n_ranks, rows_per_rank, row_floats] float32: a send buffer (slot o -> rank o) or a receive buffer."""
+    return torch.empty((n_ranks, rows_per_rank, cls_slot_row_floats(Cn)), dtype=torch.float32, device=device)
 
 
-def bma_reduce_cls_partial(logits, targets=None, log_temp=None, partials=None):
+def slot_pointer_table(slot_tensors_or_ptrs, device):
+    """Device array of float* (uint64) from tensors (local memory) or raw integer addresses (peer memory)."""
+    ptrs = [int(t.data_ptr()) if isinstance(t, torch.Tensor) else int(t) for t in slot_tensors_or_ptrs]
+    return torch.from_numpy(np.array(ptrs, dtype=np.uint64).view(np.int64).copy()).to(device)
+
+
+def bma_reduce_cls_shard(logits, slot_ptrs, targets=None, log_temp=None):
+    """Shard mode of the single-pass reduction: export this rank's partial sums row by row into the slot of the
+    rank owning the row.  slot_ptrs: int64 device tensor [n_ranks] from slot_pointer_table."""
     S, B, Cn = logits.shape
-    p = partials if partials is not None else alloc_cls_partials(B, Cn, logits.device)
-    st = _partials_struct(p)
     check(
-        lib().fb200_bma_reduce_cls(
+        lib().fb200_bma_reduce_cls_shard(
             _ptr(logits, (torch.float32, torch.bfloat16)),
             _DT[logits.dtype],
             _ptr(log_temp, torch.float32, True),
@@ -298,38 +299,24 @@ def bma_reduce_cls_partial(logits, targets=None, log_temp=None, partials=None):
             S,
             B,
             Cn,
-            None,
-            C.byref(st),
+            slot_ptrs.numel(),
+            _ptr(slot_ptrs, torch.int64),
             _stream(),
         ),
-        "fb200_bma_reduce_cls(partials)",
+        "fb200_bma_reduce_cls_shard",
     )
-    return p
 
 
-def bma_finalize_cls(partials, s_total, want, out=None):
-    B, Cn = partials["sum_p"].shape
-    outs = out if out is not None else _alloc_cls_outputs(tuple(want), s_total, B, Cn, partials["sum_p"].device)
-    pst = _partials_struct(partials)
+def bma_finalize_cls_slots(slots, s_total, Cn, want, out=None):
+    """slots [n_src, rows, row_floats] (received, one per source rank) -> final outputs for the owned rows."""
+    n_src, rows, _ = slots.shape
+    outs = out if out is not None else _alloc_cls_outputs(tuple(want), s_total, rows, Cn, slots.device)
     ost = _cls_struct(outs)
     check(
-        lib().fb200_bma_finalize_cls(C.byref(pst), int(s_total), B, Cn, C.byref(ost), _stream()),
-        "fb200_bma_finalize_cls",
+        lib().fb200_bma_finalize_cls_slots(_ptr(slots, torch.float32), n_src, rows, Cn, int(s_total), C.byref(ost), _stream()),
+        "fb200_bma_finalize_cls_slots",
     )
     return outs
-
-
-def merge_lse_pairs(max_in, sumexp_in):
-    R, B = max_in.shape
-    mo = torch.empty(B, dtype=torch.float32, device=max_in.device)
-    so = torch.empty(B, dtype=torch.float32, device=max_in.device)
-    check(
-        lib().fb200_merge_lse_pairs(
-            _ptr(max_in, torch.float32), _ptr(sumexp_in, torch.float32), R, B, _ptr(mo), _ptr(so), _stream()
-        ),
-        "fb200_merge_lse_pairs",
-    )
-    return mo, so
 
 
 def bma_reduce_reg(outputs, want, targets=None, log_temp=None):

@@ -45,7 +45,7 @@ class ConformalCalibration:
 
 
 class PredictivePipeline:
-    def __init__(self, S, B, C, device, want: Sequence[str], world: int = 1, rank: int = 0):
+    def __init__(self, S, B, C, device, want: Sequence[str], world: int = 1, rank: int = 0, transport: Optional[str] = None):
         self.S, self.B, self.C = S, B, C
         self.device = device
         self.want = tuple(want)
@@ -54,17 +54,28 @@ class PredictivePipeline:
         self.outs: Dict[str, torch.Tensor] = {}
         self.scores = None
         self.thresholds = torch.from_numpy(ece_thresholds(B)).to(device)
+        self.transport = "single"
         if world > 1:
-            self.partials = ops.alloc_cls_partials(B, C, device)
-            self.rs = {n: torch.empty((self.B_local, C), dtype=torch.float32, device=device)
-                       for n in ("sum_p", "sum_p2", "sum_pq")}
-            self.rs["sum_plogp"] = torch.empty(self.B_local, dtype=torch.float32, device=device)
-            self.rs["gather_max"] = torch.empty((world, B), dtype=torch.float32, device=device)
-            self.rs["gather_sum"] = torch.empty((world, B), dtype=torch.float32, device=device)
-            from .sharded import SampleShardExchange
+            from .sharded import PeerSlots, SampleShardExchange
 
             self.exchange = SampleShardExchange(world, rank)
-        self.launches_per_step = 5 if world == 1 else 8
+            rowf = ops.cls_slot_row_floats(C)
+            self.transport = transport or "p2p"
+            if self.transport == "p2p":
+                try:
+                    self.peer = PeerSlots(world, rank, self.B_local, rowf, device)
+                    self.recv = self.peer.recv
+                    self.slot_ptrs = ops.slot_pointer_table(self.peer.dest_ptrs, device)
+                except Exception as exc:  # no peer mapping on this system (no NVLink / symmetric memory): one all-to-all
+                    import warnings
+
+                    warnings.warn(f"peer-memory exchange unavailable ({exc!r}); using the NCCL all-to-all")
+                    self.transport = "nccl"
+            if self.transport != "p2p":
+                self.send = ops.alloc_cls_slots(world, self.B_local, C, device)
+                self.recv = torch.empty_like(self.send)
+                self.slot_ptrs = ops.slot_pointer_table([self.send[o] for o in range(world)], device)
+        self.launches_per_step = 5 if world == 1 else 7  # + reduce(shard), finalize_slots, ece_from_bins; - fused finalise
 
     # -------------------------------------------------------------------------------- K3 / K4
     def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor], kernel_events=None):
@@ -76,16 +87,18 @@ class PredictivePipeline:
             if kernel_events:
                 kernel_events[1].record()
             return self.outs
-        p = ops.bma_reduce_cls_partial(z, targets=targets, partials=self.partials)
+        ops.bma_reduce_cls_shard(z, self.slot_ptrs, targets=targets)
         if kernel_events:
             kernel_events[1].record()
-        # the one exchange step of the S-sharded path: every rank keeps the rows b of its B/N slice
-        summed, gmax, gsum = self.exchange.exchange_partials(p, self.rs)
-        m, s = ops.merge_lse_pairs(gmax, gsum)
-        merged = dict(summed)
-        merged["ll_max"], merged["ll_sumexp"] = m, s
+        # the one exchange step of the S-sharded path: every rank ends up with all ranks' partials for its B/N rows
+        if self.transport == "p2p":
+            self.peer.barrier()  # the kernel's epilogue already stored into the owners' buffers over NVLink
+        else:
+            self.exchange.exchange_slots(self.send, self.recv)
         want = [w for w in self.want if w != "ensemble_log_prob"]
-        self.outs = ops.bma_finalize_cls(merged, self.S * self.world, want, out=self.outs or None)
+        self.outs = ops.bma_finalize_cls_slots(self.recv, self.S * self.world, self.C, want, out=self.outs or None)
+        if self.transport == "p2p":
+            self.peer.barrier()  # nobody overwrites a receive buffer that is still being read
         return self.outs
 
     # -------------------------------------------------------------------------------- K5 / K6 / K7

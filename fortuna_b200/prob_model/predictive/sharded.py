@@ -1,24 +1,22 @@
 """The one exchange step of the S-sharded predictive: each rank holds S/N posterior
-samples and all B inputs, reduces its own samples to partial sums with fb200_bma_reduce_cls (partial mode),
-then
+samples and all B inputs.  fb200_bma_reduce_cls_shard reduces the rank's own samples and writes, row by row, the
+partial sums into the "slot" of the rank that owns the row (owner(b) = b // (B/N)); a slot row is
+``[sum_s p (C) | sum_s p^2 (C) | sum_s sum_c p ln p, max_s ll, sum_s exp(ll - max), 0]``.  Two transports:
 
-  * reduce-scatter (sum) over the input axis of  sum_s p, sum_s p^2, sum_s p(1-p)  [B,C]  and
-    sum_s sum_c p ln p  [B]  -> rank r owns rows [r*B/N, (r+1)*B/N);
-  * all-gather of the per-rank (max_s ll, sum_s exp(ll - max)) [B] pairs, sliced to the local rows, merged by
-    fb200_merge_lse_pairs;
-  * all-reduce of the ECE bin counters after scoring the local rows.
+  * ``nccl`` / ``gloo``: slots are a local send buffer [N, B/N, row]; ONE all-to-all moves slot o to rank o;
+  * ``p2p``: slots point into the owners' receive buffers mapped over NVLink (torch symmetric memory), so the
+    reduction kernel's epilogue IS the exchange - its peer stores overlap the rest of the kernel - and only a
+    barrier separates it from the finalisation.
 
-Only torch.distributed calls and index arithmetic live here - no arithmetic of the path.  NCCL runs the
-reduce-scatter natively; gloo (CPU tests, tests/test_dist_exchange.py) has no reduce-scatter, so there the
-same result is formed by all-reduce + slice.
+Either way rank r ends up with ``recv[N_src, B/N, row]`` and fb200_bma_finalize_cls_slots sums the sources in rank
+order and merges the (max, sumexp) pairs.  After scoring the local rows, the additive ECE bin counters are
+all-reduced.  Only torch.distributed calls and index arithmetic live here - no arithmetic of the path.
 """
 
 from typing import Dict, Optional, Tuple
 
 import torch
 import torch.distributed as dist
-
-SUM_FIELDS = ("sum_p", "sum_p2", "sum_pq", "sum_plogp")
 
 
 def local_rows(B: int, world: int, rank: int) -> Tuple[int, int]:
@@ -36,39 +34,38 @@ class SampleShardExchange:
         self.group = group
         self.world = dist.get_world_size(group) if world is None else world
         self.rank = dist.get_rank(group) if rank is None else rank
-        self._native_rs = dist.get_backend(group) == "nccl"
 
-    def scatter_sum(self, full: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """full [B, ...] on every rank -> sum over ranks of rows local_rows(B) -> [B/N, ...]."""
-        lo, hi = local_rows(full.shape[0], self.world, self.rank)
-        if out is None:
-            out = torch.empty((hi - lo,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
-        if self._native_rs:
-            dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=self.group)
-        else:
-            tmp = full.clone()
-            dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
-            out.copy_(tmp[lo:hi])
-        return out
-
-    def gather_rows(self, vec: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """vec [B] on every rank -> [N, B/N]: every rank's values for the rows this rank owns."""
-        lo, hi = local_rows(vec.shape[0], self.world, self.rank)
-        if out is None:
-            out = torch.empty((self.world, vec.shape[0]), dtype=vec.dtype, device=vec.device)
-        dist.all_gather_into_tensor(out.view(-1), vec, group=self.group)  # rank-major concatenation
-        return out[:, lo:hi].contiguous()
-
-    def exchange_partials(self, p: Dict[str, torch.Tensor], buffers: Optional[Dict[str, torch.Tensor]] = None):
-        """Partial sums of this rank's samples -> (summed partials for the local rows, gathered (max, sumexp)
-        pairs [N, B/N] for the local rows)."""
-        buffers = buffers or {}
-        summed = {n: self.scatter_sum(p[n], buffers.get(n)) for n in SUM_FIELDS}
-        gmax = self.gather_rows(p["ll_max"], buffers.get("gather_max"))
-        gsum = self.gather_rows(p["ll_sumexp"], buffers.get("gather_sum"))
-        return summed, gmax, gsum
+    def exchange_slots(self, send: torch.Tensor, recv: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """send [N, rows, row_floats]: slot o holds this rank's partials for the rows rank o owns.
+        Returns recv [N, rows, row_floats]: slot s holds rank s's partials for the rows THIS rank owns."""
+        if send.shape[0] != self.world:
+            raise ValueError(f"send buffer has {send.shape[0]} slots for {self.world} ranks")
+        if recv is None:
+            recv = torch.empty_like(send)
+        dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
+        return recv
 
     def allreduce_bins(self, ece: Dict[str, torch.Tensor]):
         for n in ("counts", "correct", "conf_sums"):
             dist.all_reduce(ece[n], op=dist.ReduceOp.SUM, group=self.group)
         return ece
+
+
+class PeerSlots:
+    """Receive buffers mapped into every rank's address space (torch.distributed._symmetric_memory): rank r's
+    reduction kernel stores its partials for rows owned by rank o straight into ``recv_o[r]`` over NVLink."""
+
+    def __init__(self, world: int, rank: int, rows: int, row_floats: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank = world, rank
+        group = group if group is not None else dist.group.WORLD
+        self.recv = symm_mem.empty((world, rows, row_floats), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.recv, group.group_name if hasattr(group, "group_name") else group)
+        slot_bytes = rows * row_floats * 4
+        # where THIS rank writes inside rank o's receive buffer: slot index = this rank
+        self.dest_ptrs = [int(self.handle.buffer_ptrs[o]) + rank * slot_bytes for o in range(world)]
+
+    def barrier(self):
+        """All ranks' peer stores issued before this point (on the current stream) are visible after it."""
+        self.handle.barrier()

@@ -110,8 +110,7 @@ static ffi::Error BmaReduceCls(cudaStream_t stream, ffi::Buffer<ffi::F32> logits
   o.epistemic_entropy = epi_ent->typed_data();
   o.log_prob = log_prob->typed_data();
   o.mode = mode->typed_data();
-  return Check(fb200_bma_reduce_cls(logits.untyped_data(), FB200_F32, nullptr, targets.typed_data(), S, B, C, &o,
-                                    nullptr, stream),
+  return Check(fb200_bma_reduce_cls(logits.untyped_data(), FB200_F32, nullptr, targets.typed_data(), S, B, C, &o, stream),
                "fb200_bma_reduce_cls");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_bma_reduce_cls, BmaReduceCls,

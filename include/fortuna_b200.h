@@ -166,31 +166,26 @@ typedef struct {
   float* ensemble_log_prob;  /* [S,B]  ll[s,b] = z[s,b,y_b] - lse_c     (needs targets)    */
 } fb200_cls_outputs_t;
 
-/* Partial sums of one S-shard (S-sharded multi-GPU mode); all required when used. */
-typedef struct {
-  float* sum_p;     /* [B,C] sum_s p                   */
-  float* sum_p2;    /* [B,C] sum_s p^2                 */
-  float* sum_pq;    /* [B,C] sum_s p(1-p)              */
-  float* sum_plogp; /* [B]   sum_s sum_c p log p       */
-  float* ll_max;    /* [B]   max_s ll   (-inf if no targets) */
-  float* ll_sumexp; /* [B]   sum_s exp(ll - ll_max)    */
-} fb200_cls_partials_t;
-
 /* logits: [S,B,C] in `dtype`; log_temp: optional device float[1] (z = logits * exp(-log_temp));
- * targets: optional int32[B].  Exactly one of out / partials is non-NULL: `out` finalises in the same
- * kernel (single GPU), `partials` exports this shard's sums for fb200_bma_finalize_cls.
- * Supports C <= 1024 (FB200_E_UNSUPPORTED above that). */
+ * targets: optional int32[B].  Supports C <= 1024 (FB200_E_UNSUPPORTED above that). */
 int fb200_bma_reduce_cls(const void* logits, int dtype, const float* log_temp, const int32_t* targets, int S,
-                         int B, int C, const fb200_cls_outputs_t* out, const fb200_cls_partials_t* partials,
-                         void* stream);
-/* Combine (already all-reduced) partial sums over s_total samples into the final outputs.
- * ll_max / ll_sumexp here are the merged pair (see fb200_merge_lse_pairs). */
-int fb200_bma_finalize_cls(const fb200_cls_partials_t* partials, int s_total, int B, int C,
-                           const fb200_cls_outputs_t* out, void* stream);
-/* Merge R gathered (max, sumexp) pairs per row: in [R,B] each -> out [B] each (the one exchange step
- * of the S-sharded log_prob: all-gather then this). */
-int fb200_merge_lse_pairs(const float* max_in, const float* sumexp_in, int R, int B, float* max_out,
-                          float* sumexp_out, void* stream);
+                         int B, int C, const fb200_cls_outputs_t* out, void* stream);
+
+/* S-sharded multi-GPU mode (each rank holds S/N of the posterior samples and all B inputs).
+ * The same single pass, but instead of finalising it exports this rank's partial sums, row by row, into the
+ * "slot" of the rank that will own the row: owner(b) = b / (B / n_ranks).  slot_ptrs is a DEVICE array of n_ranks
+ * float* (stored as uint64); slot_ptrs[o] receives rows_per_rank = B / n_ranks rows of fb200_cls_slot_row_floats(C)
+ * floats each:  [ sum_s p (C) | sum_s p^2 (C) | sum_s sum_c p ln p, max_s ll, sum_s exp(ll - max), 0 ].
+ * A slot pointer may be local memory (a send buffer, then ONE all-to-all moves slot o to rank o) or PEER memory
+ * mapped over NVLink (the kernel's epilogue stores straight into rank o's receive buffer: no collective at all,
+ * only a barrier before the finalisation). */
+size_t fb200_cls_slot_row_floats(int C);
+int fb200_bma_reduce_cls_shard(const void* logits, int dtype, const float* log_temp, const int32_t* targets, int S,
+                               int B, int C, int n_ranks, const uint64_t* slot_ptrs, void* stream);
+/* Finalise `rows` owned rows from the n_src slots received (slots: [n_src][rows][fb200_cls_slot_row_floats(C)],
+ * one per source rank, summed in source order; the (max, sumexp) pairs are merged), over s_total samples. */
+int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int rows, int C, int s_total,
+                                 const fb200_cls_outputs_t* out, void* stream);
 
 /* Regression BMA reductions over calibrated outputs z[S,B,2d] = [mu, log var]
  * (fortuna/prob_output_layer/regression.py:30-34, 67-74; fortuna/likelihood/regression.py:55-99;

@@ -20,6 +20,7 @@ from fortuna_b200.prob_model.predictive import pipeline  # noqa: E402
 
 
 def main():
+    transport = sys.argv[1] if len(sys.argv) > 1 else "nccl"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -39,7 +40,7 @@ def main():
     mask_f, sizes_f, ece_f = ref.score(t, calib)
 
     per = S // world
-    pipe = pipeline.PredictivePipeline(per, B, C, dev, want, world=world, rank=rank)
+    pipe = pipeline.PredictivePipeline(per, B, C, dev, want, world=world, rank=rank, transport=transport)
     outs = pipe.reduce(z[rank * per : (rank + 1) * per].contiguous(), t)
     mask, sizes, ece = pipe.score(t, calib)
     torch.cuda.synchronize()
@@ -70,7 +71,7 @@ def main():
     if int(tot[0]):
         sys.exit(1)
     if rank == 0:
-        print("sharded predictive parity ok")
+        print(f"sharded predictive parity ok (transport {transport})")
 
 
 if __name__ == "__main__":

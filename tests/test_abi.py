@@ -59,7 +59,7 @@ def test_host_tile_table(built):
 def test_argument_errors_without_gpu(built):
     lib = built.lib()
     assert lib.fb200_random_bits(None, 4, None, None) == -1
-    assert lib.fb200_bma_reduce_cls(None, 0, None, None, 1, 1, 1, None, None, None) == -1
+    assert lib.fb200_bma_reduce_cls(None, 0, None, None, 1, 1, 1, None, None) == -1
     assert lib.fb200_conformal_sets(None, 1, None, 1, 1, 0.5, None, None, None) == -1
 
 

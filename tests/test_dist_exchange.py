@@ -30,20 +30,20 @@ def _inputs():
     return z, t
 
 
-def _partials(z, t):
-    """What fb200_bma_reduce_cls (partial mode) exports for one shard, restated with the oracle."""
+def _slot_rows(z, t):
+    """What fb200_bma_reduce_cls_shard exports for one shard, restated with the oracle: one row per input,
+    [sum_s p (C) | sum_s p^2 (C) | sum_s sum_c p ln p, max_s ll, sum_s exp(ll - max), 0]."""
     p = P.softmax(z)
     logp = P.log_softmax_rows(z)
     ll = P.cls_ensemble_log_prob(z, t)  # [s, B]
     m = ll.max(0)
-    return {
-        "sum_p": p.sum(0, dtype=np.float32),
-        "sum_p2": (p * p).sum(0, dtype=np.float32),
-        "sum_pq": (p * (1 - p)).sum(0, dtype=np.float32),
-        "sum_plogp": (p * logp).sum((0, 2), dtype=np.float32),
-        "ll_max": m.astype(np.float32),
-        "ll_sumexp": np.exp(ll - m).sum(0, dtype=np.float32),
-    }
+    rows = np.zeros((z.shape[1], 2 * C + 4), np.float32)
+    rows[:, :C] = p.sum(0, dtype=np.float32)
+    rows[:, C : 2 * C] = (p * p).sum(0, dtype=np.float32)
+    rows[:, 2 * C] = (p * logp).sum((0, 2), dtype=np.float32)
+    rows[:, 2 * C + 1] = m
+    rows[:, 2 * C + 2] = np.exp(ll - m).sum(0, dtype=np.float32)
+    return rows
 
 
 def _worker(rank, port, out_dir):
@@ -55,18 +55,17 @@ def _worker(rank, port, out_dir):
 
         z, t = _inputs()
         per = S // WORLD
-        shard = z[rank * per : (rank + 1) * per]
-        part = {k: torch.from_numpy(v) for k, v in _partials(shard, t).items()}
+        rows = _slot_rows(z[rank * per : (rank + 1) * per], t)  # this rank's partials for ALL inputs
+        send = torch.from_numpy(rows.reshape(WORLD, B // WORLD, -1).copy())  # slot o = rows owned by rank o
         ex = SampleShardExchange()
         assert (ex.world, ex.rank) == (WORLD, rank)
-        summed, gmax, gsum = ex.exchange_partials(part)
+        recv = ex.exchange_slots(send)
         lo, hi = local_rows(B, WORLD, rank)
         ece = {"counts": torch.tensor([rank + 1, 2], dtype=torch.int32), "correct": torch.tensor([1, 0], dtype=torch.int32),
                "conf_sums": torch.tensor([0.5, 0.25 * (rank + 1)], dtype=torch.float32)}
         ex.allreduce_bins(ece)
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), lo=lo, hi=hi, gmax=gmax.numpy(), gsum=gsum.numpy(),
-                 counts=ece["counts"].numpy(), conf=ece["conf_sums"].numpy(),
-                 **{k: v.numpy() for k, v in summed.items()})
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), lo=lo, hi=hi, recv=recv.numpy(),
+                 counts=ece["counts"].numpy(), conf=ece["conf_sums"].numpy())
     finally:
         dist.destroy_process_group()
 
@@ -76,28 +75,24 @@ def test_exchange_world2_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
     z, t = _inputs()
-    full = _partials(z, t)
     want_log_prob = P.cls_log_prob(z, t)
     want_mean = P.cls_mean(z)
+    per = S // WORLD
     rows = []
     for rank in range(WORLD):
         d = np.load(tmp_path / f"rank{rank}.npz")
         lo, hi = int(d["lo"]), int(d["hi"])
         rows.append((lo, hi))
-        for k in ("sum_p", "sum_p2", "sum_pq", "sum_plogp"):
-            np.testing.assert_allclose(d[k], full[k][lo:hi], rtol=2e-6, atol=1e-6, err_msg=k)
-        # rank-major gather, sliced to the local rows
-        assert d["gmax"].shape == (WORLD, hi - lo)
-        per = S // WORLD
-        for r in range(WORLD):
-            pr = _partials(z[r * per : (r + 1) * per], t)
-            np.testing.assert_array_equal(d["gmax"][r], pr["ll_max"][lo:hi])
-            np.testing.assert_array_equal(d["gsum"][r], pr["ll_sumexp"][lo:hi])
-        # merge + finalise as the kernels do: M = max_r m_r, sum_r s_r exp(m_r - M); log_prob = M + log sum - log S
-        M = d["gmax"].max(0)
-        ssum = (d["gsum"] * np.exp(d["gmax"] - M)).sum(0)
+        recv = d["recv"]
+        assert recv.shape == (WORLD, hi - lo, 2 * C + 4)
+        for src in range(WORLD):  # slot `src` = rank src's partials for the rows this rank owns, bit for bit
+            np.testing.assert_array_equal(recv[src], _slot_rows(z[src * per : (src + 1) * per], t)[lo:hi])
+        # finalise as fb200_bma_finalize_cls_slots does: sums in source order, merged (max, sumexp) pairs
+        sp = recv[:, :, :C].sum(0, dtype=np.float32)
+        M = recv[:, :, 2 * C + 1].max(0)
+        ssum = (recv[:, :, 2 * C + 2] * np.exp(recv[:, :, 2 * C + 1] - M)).sum(0)
         np.testing.assert_allclose(M + np.log(ssum) - np.log(np.float32(S)), want_log_prob[lo:hi], rtol=1e-5, atol=2e-6)
-        np.testing.assert_allclose(d["sum_p"] / np.float32(S), want_mean[lo:hi], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(sp / np.float32(S), want_mean[lo:hi], rtol=1e-5, atol=1e-7)
         assert d["counts"].tolist() == [3, 4] and np.allclose(d["conf"], [1.0, 0.75])
     assert rows == [(0, B // 2), (B // 2, B)]
 

@@ -108,22 +108,33 @@ def test_identities_and_edge_cases(cuda):
     np.testing.assert_allclose(o["mean"].cpu().numpy(), P.cls_mean(z), rtol=1e-5, atol=1e-9)
 
 
-def test_partials_finalize_equals_fused(cuda):
-    """S-sharded path on one device: two shards -> partial sums -> add / merge -> finalize."""
+@pytest.mark.parametrize("S,B,C,n_ranks", [(12, 300, 1000, 2), (9, 64, 10, 4), (6, 120, 33, 3)])
+def test_shard_slots_finalize_equals_fused(cuda, S, B, C, n_ranks):
+    """S-sharded path emulated on one device: every 'rank' reduces its samples into slots (owner = b // (B/N)), the
+    all-to-all is emulated by indexing send[src][owner], each owner finalises its rows -> equals the oracle on all S."""
     from fortuna_b200 import ops
 
-    S, B, C = 12, 300, 1000
-    z = _logits(S, B, C, seed=21)
+    z = _logits(S, B, C, seed=21 + C)
     t = np.random.default_rng(5).integers(0, C, B).astype(np.int32)
     zt = torch.from_numpy(z).to(cuda)
     tt = torch.from_numpy(t).to(cuda)
-    pa = ops.bma_reduce_cls_partial(zt[:5].contiguous(), targets=tt)
-    pb = ops.bma_reduce_cls_partial(zt[5:].contiguous(), targets=tt)
-    merged = {k: pa[k] + pb[k] for k in ("sum_p", "sum_p2", "sum_pq", "sum_plogp")}  # stands in for the all-reduce
-    m, s = ops.merge_lse_pairs(torch.stack([pa["ll_max"], pb["ll_max"]]), torch.stack([pa["ll_sumexp"], pb["ll_sumexp"]]))
-    merged["ll_max"], merged["ll_sumexp"] = m, s
+    rows = B // n_ranks
+    bounds = np.linspace(0, S, n_ranks + 1).astype(int)  # uneven sample shards are fine
+    sends = []
+    for r in range(n_ranks):
+        send = ops.alloc_cls_slots(n_ranks, rows, C, cuda)
+        send.fill_(float("nan"))
+        ptrs = ops.slot_pointer_table([send[o] for o in range(n_ranks)], cuda)
+        ops.bma_reduce_cls_shard(zt[bounds[r] : bounds[r + 1]].contiguous(), ptrs, targets=tt)
+        sends.append(send)
     want = [n for n in ALL if n != "ensemble_log_prob"]
-    outs = ops.bma_finalize_cls(merged, S, want)
+    parts = {n: [] for n in want}
+    for o in range(n_ranks):
+        recv = torch.stack([sends[src][o] for src in range(n_ranks)]).contiguous()  # what the all-to-all delivers to o
+        outs = ops.bma_finalize_cls_slots(recv, S, C, want)
+        for n in want:
+            parts[n].append(outs[n])
+    outs = {n: torch.cat(parts[n], dim=0) for n in want}
     outs["ensemble_log_prob"] = torch.from_numpy(P.cls_ensemble_log_prob(z, t)).to(cuda)
     _check(outs, z, t, S)
 

@@ -1,0 +1,67 @@
+"""``ProbClassifier`` - the user-facing object of fortuna/prob_model/classification.py:48-261 and
+fortuna/prob_model/base.py:50-107 for the SG-MCMC posteriors on the hot path:
+
+    prob_model = ProbClassifier(model=..., posterior_approximator=SGHMCPosteriorApproximator(...))
+    status = prob_model.train(train_data_loader, fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=30)))
+    means = prob_model.predictive.mean(inputs_loader=test_inputs_loader)
+
+``model`` is a torch ``nn.Module`` returning logits (model definitions are outside the hot path; modules that follow
+the reference's ``dfe_subnet`` / ``output_subnet`` split get the S-batched last-layer contraction when only the
+output layer is sampled, via ``FitOptimizer(freeze_fun=...)``).  Other posterior approximators of the reference are
+out of scope and rejected."""
+from typing import Optional
+
+import torch
+
+from ..utils.random import RandomNumberGenerator
+from .fit_config import FitConfig
+from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_approximator import CyclicalSGLDPosteriorApproximator
+from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_posterior import CyclicalSGLDPosterior
+from .posterior.sgmcmc.sghmc.sghmc_approximator import SGHMCPosteriorApproximator
+from .posterior.sgmcmc.sghmc.sghmc_posterior import SGHMCPosterior
+from .posterior.sgmcmc.torch_model import BoundModel
+from .predictive.classification import ClassificationPredictive
+from .prior import IsotropicGaussianPrior
+
+
+class ProbClassifier:
+    def __init__(self, model: torch.nn.Module, prior=None, posterior_approximator=None, output_calibrator=None,
+                 model_editor=None, seed: int = 0, device="cuda"):
+        if model_editor is not None:
+            raise NotImplementedError("model editors are outside the hot path")
+        if output_calibrator is not None:
+            raise NotImplementedError("training an output calibrator is outside the hot path; a fixed temperature can be "
+                                      "passed to the predictive (log_temp)")
+        self.model = model
+        self.prior = prior if prior is not None else IsotropicGaussianPrior()
+        self.posterior_approximator = posterior_approximator if posterior_approximator is not None else SGHMCPosteriorApproximator()
+        if not isinstance(self.posterior_approximator, (SGHMCPosteriorApproximator, CyclicalSGLDPosteriorApproximator)):
+            raise NotImplementedError(f"posterior approximator {self.posterior_approximator!s} is outside the hot path "
+                                      "(SG-MCMC only: sghmc, cyclical_sgld)")
+        self.device = torch.device(device)
+        self.rng = RandomNumberGenerator(seed=seed, device=self.device)  # one key chain shared by all parts (base.py:36-48)
+        self.posterior = None
+        self.predictive = None
+
+    def _check_output_dim(self, data_loader):
+        """fortuna/prob_model/classification.py:218-242: targets must be integer classes below the output width."""
+        for x, y in data_loader:
+            out_dim = self.model(torch.as_tensor(x[:1], dtype=torch.float32, device=next(self.model.parameters()).device)).shape[-1]
+            if int(y.max()) >= out_dim or int(y.min()) < 0:
+                raise ValueError(f"The outputs dimension of `model` must be at least {int(y.max()) + 1}, but {out_dim} was found.")
+            break
+
+    def train(self, train_data_loader, val_data_loader=None, calib_data_loader=None, fit_config: Optional[FitConfig] = None,
+              calib_config=None, map_fit_config=None, **kwargs):
+        if map_fit_config is not None:
+            raise NotImplementedError("a preliminary MAP fit is outside the hot path")
+        fit_config = fit_config or FitConfig()
+        self.model.to(self.device)
+        self._check_output_dim(train_data_loader)
+        bound = BoundModel(self.model, self.device, freeze_fun=fit_config.optimizer.freeze_fun)
+        cls = SGHMCPosterior if isinstance(self.posterior_approximator, SGHMCPosteriorApproximator) else CyclicalSGLDPosterior
+        self.posterior = cls(bound, self.prior, self.posterior_approximator, self.rng)
+        status = {"fit_status": self.posterior.fit(train_data_loader, val_data_loader, fit_config)}
+        self.predictive = ClassificationPredictive(self.posterior)
+        # calib_data_loader: the default temperature scaler's training is outside the hot path; log_temp stays 0
+        return status

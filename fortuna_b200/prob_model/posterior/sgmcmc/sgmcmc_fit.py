@@ -1,0 +1,53 @@
+"""The SG-MCMC fit shared by SGHMCPosterior and CyclicalSGLDPosterior - the part of
+fortuna/prob_model/posterior/sgmcmc/sghmc/sghmc_posterior.py:62-187 around the sampler: build the integrator,
+create the state, run ``trainer.train`` with the log-joint as the (ascended) objective and the sampling callback.
+
+The host loop is the reference's ``_training_loop`` (fortuna/training/trainer.py:455-532) reduced to what it does for
+SG-MCMC: per batch, value_and_grad of the batched log-joint (``Joint._batched_log_joint_prob``,
+fortuna/prob_model/joint/base.py:54-122: log prior + n_data / batch_size * sum log-likelihood) by autograd, then
+``state.apply_gradients`` - ONE sampler-kernel launch - then the callbacks."""
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from ....training.train_state import TrainState
+from .torch_model import BoundModel
+
+
+def batched_log_joint_prob(bound: BoundModel, prior, inputs: torch.Tensor, targets: torch.Tensor, n_data: int) -> torch.Tensor:
+    logits = bound.model(inputs)
+    ll = -torch.nn.functional.cross_entropy(logits, targets.long(), reduction="sum")
+    lp = sum(prior.log_joint_prob(p) for p in bound.trainable.values())
+    return lp + (n_data / inputs.shape[0]) * ll
+
+
+def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader, n_epochs: int, val_data_loader=None,
+               metrics=()) -> Dict[str, np.ndarray]:
+    state = TrainState.create(params=bound.params, tx=tx)
+    n_data = train_data_loader.size
+    dev = bound.device
+    losses, val_losses = [], []
+    for _ in range(n_epochs):
+        epoch = []
+        for inputs, targets in train_data_loader:
+            x = torch.as_tensor(inputs, dtype=torch.float32, device=dev)
+            y = torch.as_tensor(targets, device=dev)
+            bound.zero_grad()
+            lj = batched_log_joint_prob(bound, prior, x, y, n_data)
+            lj.backward()                                    # d log-joint / d theta lands in bound.grads (flat)
+            state = state.apply_gradients(grads=bound.grads)  # fused sampler step, params updated in place
+            for cb in callbacks:
+                state = cb.training_step_end(state)
+            epoch.append(lj.detach())
+        losses.append(float(torch.stack(epoch).mean()))
+        if val_data_loader is not None:
+            with torch.no_grad():
+                v = [batched_log_joint_prob(bound, prior, torch.as_tensor(a, dtype=torch.float32, device=dev),
+                                            torch.as_tensor(b, device=dev), val_data_loader.size)
+                     for a, b in val_data_loader]
+            val_losses.append(float(torch.stack(v).mean()))
+    status = {"loss": np.array(losses)}
+    if val_losses:
+        status["val_loss"] = np.array(val_losses)
+    return status, state

@@ -17,14 +17,16 @@ namespace fb200 {
 int last_layer_tc_supported(int S, int B, int D, int C, int in_dtype, int out_dtype, int w_layout);
 int last_layer_tc_launch(const void* x, const void* w, const float* bias, const float* log_temp,
                          const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
-                         int out_dtype, cudaStream_t st);
+                         int out_dtype, int c_split, cudaStream_t st);
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-constexpr int kBM = 64, kBN = 64, kBK = 16;
+// The contraction is tiled over the FLATTENED output column n = s * C + c (N = S * C columns): a narrow last layer
+// (C = 2 .. 10) still fills 64-column tiles, and the features x are re-read N / 64 times instead of S times.
+constexpr int kBM = 128, kBN = 64, kBK = 16;
 
 template <typename TI, typename TO, int WL>
 __global__ void __launch_bounds__(256) last_layer_simt_kernel(const TI* __restrict__ x, const TI* __restrict__ w,
@@ -32,57 +34,71 @@ __global__ void __launch_bounds__(256) last_layer_simt_kernel(const TI* __restri
                                                               const float* __restrict__ log_temp,
                                                               const int32_t* __restrict__ sample_idx,
                                                               TO* __restrict__ out, int S, int B, int D, int C) {
-  __shared__ float As[kBK][kBM + 4];
-  __shared__ float Bs[kBK][kBN + 4];
-  const int s = blockIdx.z;
+  __shared__ __align__(16) float As[kBK][kBM + 4];
+  __shared__ __align__(16) float Bs[kBK][kBN + 4];
+  const int N = S * C;
+  const int n0 = blockIdx.x * kBN;
   const int b0 = blockIdx.y * kBM;
-  const int c0 = blockIdx.x * kBN;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int sw = sample_idx ? sample_idx[s] : s;  // which stored posterior sample this output row uses
-  const TI* ws = w + (size_t)sw * D * C;
-  float acc[4][4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // thread tile: rows ty*8 .. +8, columns tx*4 .. +4
+
+  // loader roles.  A: row r = tid / 2, 8 consecutive k.  B: one column, 4 consecutive k (SCD) or
+  // one k, 4 consecutive columns (SDC); the weight row of a column, w[idx[s]][.][c], is resolved once.
+  const int a_r = threadIdx.x >> 1, a_k = (threadIdx.x & 1) * 8;
+  const int a_b = b0 + a_r;
+  const TI* a_ptr = x + (size_t)(a_b < B ? a_b : 0) * D;
+  int b_col, b_k;
+  if (WL == FB200_W_SCD) {
+    b_col = threadIdx.x >> 2;
+    b_k = (threadIdx.x & 3) * 4;
+  } else {
+    b_col = (threadIdx.x & 15) * 4;
+    b_k = threadIdx.x >> 4;
+  }
+  // (sample, class) of the 4 columns this thread loads (SDC) / of its single column (SCD, q = 0)
+  size_t wbase[4];
+  bool wok[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int q = 0; q < 4; ++q) {
+    const int n = n0 + b_col + (WL == FB200_W_SCD ? 0 : q);
+    wok[q] = n < N;
+    const int sn = wok[q] ? n / C : 0, cn = wok[q] ? n - sn * C : 0;
+    const int sw = sample_idx ? sample_idx[sn] : sn;
+    wbase[q] = WL == FB200_W_SCD ? ((size_t)sw * C + cn) * (size_t)D : (size_t)sw * D * C + cn;
+  }
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
   for (int k0 = 0; k0 < D; k0 += kBK) {
-    {  // A tile: 64 rows x 16 k
-      const int r = threadIdx.x >> 2, kk = (threadIdx.x & 3) * 4;
-      const int b = b0 + r;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = k0 + kk + q;
-        As[kk + q][r] = (b < B && k < D) ? to_f32(x[(size_t)b * D + k]) : 0.0f;
-      }
+    for (int q = 0; q < 8; ++q) {
+      const int k = k0 + a_k + q;
+      As[a_k + q][a_r] = (a_b < B && k < D) ? to_f32(a_ptr[k]) : 0.0f;
     }
-    if (WL == FB200_W_SDC) {  // w[s][d][c]: 16 k x 64 c, c contiguous
-      const int kk = threadIdx.x >> 4, cc = (threadIdx.x & 15) * 4;
-      const int k = k0 + kk;
+    if (WL == FB200_W_SCD) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int c = c0 + cc + q;
-        Bs[kk][cc + q] = (k < D && c < C) ? to_f32(ws[(size_t)k * C + c]) : 0.0f;
+        const int k = k0 + b_k + q;
+        Bs[b_k + q][b_col] = (wok[0] && k < D) ? to_f32(w[wbase[0] + k]) : 0.0f;
       }
-    } else {  // w[s][c][d]: d contiguous
-      const int cc = threadIdx.x >> 2, kk = (threadIdx.x & 3) * 4;
-      const int c = c0 + cc;
+    } else {
+      const int k = k0 + b_k;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = k0 + kk + q;
-        Bs[kk + q][cc] = (k < D && c < C) ? to_f32(ws[(size_t)c * D + k]) : 0.0f;
-      }
+      for (int q = 0; q < 4; ++q) Bs[b_k][b_col + q] = (wok[q] && k < D) ? to_f32(w[wbase[q] + (size_t)k * C]) : 0.0f;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < kBK; ++kk) {
-      float av[4], bv[4];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 bq = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
@@ -90,17 +106,20 @@ __global__ void __launch_bounds__(256) last_layer_simt_kernel(const TI* __restri
   }
   const float scale = log_temp ? expf(-log_temp[0]) : 1.0f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int b = b0 + ty * 4 + i;
-    if (b >= B) continue;
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + tx * 4 + j;
+    if (n >= N) continue;
+    const int sn = n / C, cn = n - sn * C;
+    const int sw = sample_idx ? sample_idx[sn] : sn;
+    const float bj = bias ? bias[(size_t)sw * C + cn] : 0.0f;
+    TO* ocol = out + (size_t)sn * B * C + cn;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + tx * 4 + j;
-      if (c >= C) continue;
-      float v = acc[i][j];
-      if (bias) v += bias[(size_t)sw * C + c];
+    for (int i = 0; i < 8; ++i) {
+      const int b = b0 + ty * 8 + i;
+      if (b >= B) continue;
+      float v = acc[i][j] + bj;
       if (log_temp) v *= scale;
-      store_out(out + ((size_t)s * B + b) * C + c, v);
+      store_out(ocol + (size_t)b * C, v);
     }
   }
 }
@@ -130,8 +149,10 @@ template <typename TI, typename TO>
 static int launch_simt(const void* x, const void* w, const float* bias, const float* log_temp,
                        const int32_t* sample_idx, void* out, int S, int B, int D, int C, int w_layout,
                        cudaStream_t st) {
-  dim3 grid((C + kBN - 1) / kBN, (B + kBM - 1) / kBM, S);
-  if (grid.y > 65535 || grid.z > 65535) return FB200_E_UNSUPPORTED;
+  const long long N = (long long)S * C;
+  if (N > 0x7FFFFFFFll) return FB200_E_UNSUPPORTED;
+  dim3 grid((unsigned)((N + kBN - 1) / kBN), (B + kBM - 1) / kBM, 1);
+  if (grid.y > 65535) return FB200_E_UNSUPPORTED;
   if (w_layout == FB200_W_SDC)
     last_layer_simt_kernel<TI, TO, FB200_W_SDC><<<grid, 256, 0, st>>>(
         reinterpret_cast<const TI*>(x), reinterpret_cast<const TI*>(w), bias, log_temp, sample_idx,
@@ -163,7 +184,13 @@ extern "C" int fb200_last_layer_logits(const void* x, const void* w, const float
   if (path == 2 && !tc_ok) return FB200_E_UNSUPPORTED;
   // auto: tensor cores only when the contraction is large enough to be compute-bound (D >= 256, C >= 64)
   const bool use_tc = path == 2 || (path == 0 && tc_ok && D >= 256 && C >= 64 && B >= 128);
-  if (use_tc) return last_layer_tc_launch(x, w, bias, log_temp, sample_idx, n_stored, out, S, B, D, C, out_dtype, st);
+  if (use_tc) return last_layer_tc_launch(x, w, bias, log_temp, sample_idx, n_stored, out, S, B, D, C, out_dtype, 0, st);
+  // narrow last layer in bf16 (e.g. BERT classifier 768 x 2): fold the sample axis into the column axis so the
+  // tensor cores see N = S * C columns; needs the identity sample map (stored rows are then one [S*C, D] matrix)
+  const long long flatN = (long long)S * C;
+  if (path == 0 && !sample_idx && C < 64 && flatN >= 64 && flatN < (1ll << 30) && D >= 256 && B >= 128 &&
+      last_layer_tc_supported(1, B, D, (int)flatN, in_dtype, out_dtype, w_layout))
+    return last_layer_tc_launch(x, w, bias, log_temp, nullptr, 1, out, 1, B, D, (int)flatN, out_dtype, C, st);
   if (in_dtype == FB200_F32) {
     if (out_dtype == FB200_F32) return launch_simt<float, float>(x, w, bias, log_temp, sample_idx, out, S, B, D, C, w_layout, st);
     return launch_simt<float, __nv_bfloat16>(x, w, bias, log_temp, sample_idx, out, S, B, D, C, w_layout, st);

@@ -141,6 +141,7 @@ struct TcParams {
   int S, B, D, C;
   int m_blocks, n_blocks, k_blocks;
   int total_tiles;
+  int c_split;  // flattened mode (S folded into the N axis): column n is (sample n / c_split, class n % c_split); 0 = off
 };
 
 struct TileCoord {
@@ -344,12 +345,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             ++store_it;
           }
         } else if (b < p.B) {
-          if (sizeof(TO) == 4) {
+          if (p.c_split) {
+            // flattened N: scatter column n = (sample, class) to out[sample, b, class]; for a fixed column the 32 lanes
+            // (consecutive b) write addresses c_split elements apart, neighbouring columns fill the gaps
+            int sn = c0 / p.c_split, cn = c0 - sn * p.c_split;
+            TO* o = out + ((size_t)sn * p.B + b) * p.c_split;
+            const size_t sample_stride = (size_t)p.B * p.c_split;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j < p.C) {
+                if (sizeof(TO) == 4) reinterpret_cast<float*>(o)[cn] = v[j];
+                else reinterpret_cast<__nv_bfloat16*>(o)[cn] = __float2bfloat16_rn(v[j]);
+              }
+              if (++cn == p.c_split) {
+                cn = 0;
+                o += sample_stride;
+              }
+            }
+          } else if (sizeof(TO) == 4) {
             float* o = reinterpret_cast<float*>(out_row) + c0;
-            for (int j = 0; j < 32 && c0 + j < p.C; ++j) o[j] = v[j];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < p.C) o[j] = v[j];
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_row) + c0;
-            for (int j = 0; j < 32 && c0 + j < p.C; ++j) o[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < p.C) o[j] = __float2bfloat16_rn(v[j]);
           }
         }
       }
@@ -395,9 +417,11 @@ int last_layer_tc_supported(int S, int B, int D, int C, int in_dtype, int out_dt
   return 1;
 }
 
+// c_split > 0: the caller folded the sample axis into the column axis (S = 1, C = samples * c_split, w viewed as
+// [1, C, D], bias as [1, C]); the epilogue scatters column n to out[n / c_split, b, n % c_split].
 int last_layer_tc_launch(const void* x, const void* w, const float* bias, const float* log_temp,
                          const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
-                         int out_dtype, cudaStream_t st) {
+                         int out_dtype, int c_split, cudaStream_t st) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return FB200_E_UNSUPPORTED;
   if (!fb200_aligned16(x) || !fb200_aligned16(w)) return FB200_E_ALIGN;
@@ -424,7 +448,7 @@ int last_layer_tc_launch(const void* x, const void* w, const float* bias, const 
   }
   // output map {C, B, S}: needs 16-byte row stride and base; otherwise the epilogue stores directly
   const size_t osz = out_dtype == FB200_F32 ? 4 : 2;
-  const bool tma_out = fb200_aligned16(out) && (((size_t)C * osz) % 16 == 0);
+  const bool tma_out = c_split == 0 && fb200_aligned16(out) && (((size_t)C * osz) % 16 == 0);
   CUtensorMap to = ta;
   if (tma_out) {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)B, (cuuint64_t)S};
@@ -440,6 +464,7 @@ int last_layer_tc_launch(const void* x, const void* w, const float* bias, const 
   p.bias = bias;
   p.log_temp = log_temp;
   p.sample_idx = sample_idx;
+  p.c_split = c_split;
   p.out = out;
   p.S = S;
   p.B = B;

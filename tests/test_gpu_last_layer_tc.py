@@ -91,3 +91,26 @@ def test_sample_index_gather_is_fused(cuda, path):
                                 sample_idx=torch.from_numpy(idx).to(cuda))
     assert out.shape == (S, B, C)
     np.testing.assert_allclose(out.cpu().numpy(), want, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("S,B,D,C,out_dtype", [(64, 1000, 768, 2, torch.float32), (7, 300, 256, 10, torch.float32),
+                                               (33, 257, 512, 3, torch.bfloat16), (40, 128, 320, 63, torch.float32)])
+def test_narrow_last_layer_folds_samples_into_columns(cuda, S, B, D, C, out_dtype):
+    """bf16 operands with C < 64 (BERT classifier 768 x 2, ResNet 512 x 10): path 0 runs the tcgen05 kernel on the
+    flattened column axis n = s * C + c and scatters back to [S, B, C]; equals the oracle and the CUDA-core path."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(S * 100 + C)
+    x = r.standard_normal((B, D)).astype(np.float32)
+    w = (r.standard_normal((S, D, C)) / np.sqrt(D)).astype(np.float32)
+    bias = r.standard_normal((S, C)).astype(np.float32)
+    lt = np.array([0.1], dtype=np.float32)
+    want = P.last_layer_logits(x, w, bias, lt, bf16_inputs=True)
+    xt = torch.from_numpy(x).to(cuda).to(torch.bfloat16)
+    wt = ops.transpose_w_bf16(torch.from_numpy(w).to(cuda))
+    args = (xt, wt, torch.from_numpy(bias).to(cuda), torch.from_numpy(lt).to(cuda))
+    auto = ops.last_layer_logits(*args, out_dtype=out_dtype, w_layout=ops.W_SCD, path=0)
+    simt = ops.last_layer_logits(*args, out_dtype=out_dtype, w_layout=ops.W_SCD, path=1)
+    tol = 2e-3 if out_dtype == torch.float32 else 1e-2
+    np.testing.assert_allclose(auto.float().cpu().numpy(), want, rtol=tol, atol=tol * np.sqrt(D) / 8)
+    np.testing.assert_allclose(simt.float().cpu().numpy(), want, rtol=tol, atol=tol * np.sqrt(D) / 8)

@@ -118,6 +118,8 @@ SIGNATURES = {
     "fb200_conformal_sets": (_i, [_P, _i, _P, _i, _i, _f, _P, _P, _P]),
     "fb200_ece_bins": (_i, [_P, _i, _i, _P, _P, _P, _i, _P, _P, _P, _P, _P, _P]),
     "fb200_ece_from_bins": (_i, [_P, _P, _P, _i, _i64, _P, _P]),
+    "fb200_quantile_axis0": (_i, [_P, _i, _i64, _P, _i, _P, _P]),
+    "fb200_reg_sample_targets": (_i, [_P, _P, _P, _i, _i, _i, _i, _P, _P, _P]),
     "fb200_quantile_sorted": (_i, [_P, _i64, _P, _i, _P, _P]),
 }
 

@@ -565,6 +565,46 @@ __global__ void __launch_bounds__(256) bma_reduce_reg_logprob_kernel(const float
   if (out.log_prob) out.log_prob[b] = (lmax + logf(lsum)) - log_S;
 }
 
+// Target samples of the regression predictive (fortuna/prob_model/predictive/base.py:407-441 ->
+// fortuna/likelihood/base.py:339-372 -> fortuna/prob_output_layer/regression.py:38-52), bit-exact draws:
+//   keys = split(rng, T); (k1, k2) = split(keys[t]); i = choice(k1, n_stored);
+//   y[t] = mu_i + exp(0.5 * logvar_i) * normal(k2, (1, B, d))
+__global__ void __launch_bounds__(256) reg_sample_targets_kernel(const float* __restrict__ z,
+                                                                 const float* __restrict__ log_temp,
+                                                                 const uint32_t* __restrict__ key, uint32_t T,
+                                                                 uint32_t n_stored, int B, int d,
+                                                                 float* __restrict__ y, int32_t* __restrict__ idx_out) {
+  const uint32_t t = blockIdx.y;
+  const uint32_t n = (uint32_t)B * (uint32_t)d;
+  // per-t key schedule (identical in every thread of the row; a handful of threefry blocks)
+  const uint32_t kt0 = random_bits_elem(key[0], key[1], 2u * T, 2u * t);
+  const uint32_t kt1 = random_bits_elem(key[0], key[1], 2u * T, 2u * t + 1u);
+  uint32_t a0 = 0u, a1 = 2u, b0 = 1u, b1 = 3u;  // split(keys[t]) = bits(4).reshape(2,2): key1 = (a0, b0), key2 = (a1, b1)
+  threefry2x32(kt0, kt1, a0, a1);
+  threefry2x32(kt0, kt1, b0, b1);
+  // choice(key1, n_stored) = randint: split(key1) -> two single draws
+  uint32_t c0 = 0u, c1 = 2u, d0 = 1u, d1 = 3u;
+  threefry2x32(a0, b0, c0, c1);
+  threefry2x32(a0, b0, d0, d1);
+  uint32_t hi = 0u, hi1 = 0u, lo = 0u, lo1 = 0u;
+  threefry2x32(c0, d0, hi, hi1);
+  threefry2x32(c1, d1, lo, lo1);
+  uint32_t mult = 65536u % n_stored;
+  mult = (mult * mult) % n_stored;
+  const uint32_t i = ((hi % n_stored) * mult + (lo % n_stored)) % n_stored;
+  if (idx_out && blockIdx.x == 0 && threadIdx.x == 0) idx_out[t] = (int32_t)i;
+  const float lt = log_temp ? log_temp[0] : 0.0f;
+  const float* zi = z + (size_t)i * B * (2 * d);
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const uint32_t b = e / (uint32_t)d, j = e - b * (uint32_t)d;
+    const float mu = zi[(size_t)b * (2 * d) + j];
+    float lv = zi[(size_t)b * (2 * d) + d + j];
+    if (log_temp) lv += lt;
+    const float eps = bits_to_normal(random_bits_elem(a1, b1, n, e));
+    y[(size_t)t * n + e] = mu + expf(0.5f * lv) * eps;
+  }
+}
+
 static int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -717,6 +757,21 @@ extern "C" int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int r
   const int64_t threads = (int64_t)rows * 32;
   bma_finalize_slots_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       slots, n_src, rows, C, s_total, *out, logf((float)s_total));
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_reg_sample_targets(const float* outputs, const float* log_temp, const uint32_t* key,
+                                        int n_target_samples, int n_stored, int B, int d, float* y, int32_t* idx_out,
+                                        void* stream) {
+  if (!outputs || !key || !y) return FB200_E_NULL;
+  if (n_target_samples <= 0 || n_stored <= 0 || B <= 0 || d <= 0) return FB200_E_SHAPE;
+  if ((long long)B * d >= 0xFFFFFFFFll || n_target_samples > 65535) return FB200_E_UNSUPPORTED;
+  const long long n = (long long)B * d;
+  unsigned gx = (unsigned)((n + 255) / 256);
+  if (gx > 148u * 8u) gx = 148u * 8u;
+  reg_sample_targets_kernel<<<dim3(gx, (unsigned)n_target_samples), 256, 0, (cudaStream_t)stream>>>(
+      outputs, log_temp, key, (uint32_t)n_target_samples, (uint32_t)n_stored, B, d, y, idx_out);
   FB200_LAUNCH_CHECK();
   return 0;
 }

@@ -643,6 +643,36 @@ __global__ void ece_finalize_kernel(const int32_t* __restrict__ counts, float* _
   result[3] = C > 1 ? brier_sum / (float)B : CUDART_NAN_F;
 }
 
+// jnp.quantile(x, q, axis=0) for x[T, M]: one thread per column sorts its T values (insertion sort in local
+// memory; T is the number of Monte-Carlo target samples, 30 by default) and interpolates like quantile_sorted.
+constexpr int kMaxAxis0 = 256;
+__global__ void __launch_bounds__(128) quantile_axis0_kernel(const float* __restrict__ x, int T, int64_t M,
+                                                             const float* __restrict__ q, int nq,
+                                                             float* __restrict__ out) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float v[kMaxAxis0];
+  bool has_nan = false;
+  for (int t = 0; t < T; ++t) {
+    const float val = x[(size_t)t * M + m];
+    has_nan |= (val != val);
+    int i = t;
+    while (i > 0 && v[i - 1] > val) {
+      v[i] = v[i - 1];
+      --i;
+    }
+    v[i] = val;
+  }
+  const float nm1 = (float)(T - 1);
+  for (int k = 0; k < nq; ++k) {
+    const float pos = __fmul_rn(q[k], nm1);
+    const float low = floorf(pos), high = ceilf(pos);
+    const float hw = __fsub_rn(pos, low), lw = __fsub_rn(1.0f, hw);
+    const int lo = (int)fmaxf(0.0f, fminf(low, nm1)), hi = (int)fmaxf(0.0f, fminf(high, nm1));
+    out[(size_t)k * M + m] = (has_nan || pos != pos) ? CUDART_NAN_F : __fadd_rn(__fmul_rn(v[lo], lw), __fmul_rn(v[hi], hw));
+  }
+}
+
 // ECE / MCE from (all-reduced) bin counters: the finalisation step of the B-sharded multi-GPU scoring.
 __global__ void ece_from_bins_kernel(const int32_t* __restrict__ counts, const float* __restrict__ conf_sums,
                                      const int32_t* __restrict__ correct, int n_bins, float n_total,
@@ -813,6 +843,15 @@ extern "C" int fb200_ece_bins(const float* probs, int B, int C, const int32_t* p
                                                     counts, correct, result);
   FB200_LAUNCH_CHECK();
   ece_finalize_kernel<<<1, 1, 0, st>>>(counts, conf_sums, correct, n_bins, B, C, result);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_quantile_axis0(const float* x, int T, int64_t M, const float* q, int nq, float* out, void* stream) {
+  if (!x || !q || !out) return FB200_E_NULL;
+  if (T <= 0 || M <= 0 || nq <= 0) return FB200_E_SHAPE;
+  if (T > kMaxAxis0) return FB200_E_UNSUPPORTED;
+  quantile_axis0_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, T, M, q, nq, out);
   FB200_LAUNCH_CHECK();
   return 0;
 }

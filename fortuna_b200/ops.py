@@ -470,3 +470,29 @@ def quantile_sorted(x_sorted, q):
         "fb200_quantile_sorted",
     )
     return out
+
+
+def quantile_axis0(x, q):
+    """jnp.quantile(x, q, axis=0): x [T, ...] float32 -> [nq, ...]."""
+    T = x.shape[0]
+    M = x.numel() // T
+    out = torch.empty((q.numel(),) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+    check(
+        lib().fb200_quantile_axis0(_ptr(x, torch.float32), T, M, _ptr(q, torch.float32), q.numel(), _ptr(out), _stream()),
+        "fb200_quantile_axis0",
+    )
+    return out
+
+
+def reg_sample_targets(outputs, key, n_target_samples, log_temp=None, want_idx=False):
+    """outputs [n_stored, B, 2d] -> y [T, B, d] (and the drawn posterior-sample indices int32[T])."""
+    n, B, two_d = outputs.shape
+    d = two_d // 2
+    y = torch.empty((n_target_samples, B, d), dtype=torch.float32, device=outputs.device)
+    idx = torch.empty(n_target_samples, dtype=torch.int32, device=outputs.device) if want_idx else None
+    check(
+        lib().fb200_reg_sample_targets(_ptr(outputs, torch.float32), _ptr(log_temp, torch.float32, True), _ptr(key, KEY_DTYPE),
+                                       int(n_target_samples), n, B, d, _ptr(y), _ptr(idx, None, True), _stream()),
+        "fb200_reg_sample_targets",
+    )
+    return (y, idx) if want_idx else y

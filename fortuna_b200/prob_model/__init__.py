@@ -3,4 +3,5 @@ from .classification import ProbClassifier  # noqa: F401
 from .fit_config import FitConfig, FitMonitor, FitOptimizer  # noqa: F401
 from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_approximator import CyclicalSGLDPosteriorApproximator  # noqa: F401
 from .posterior.sgmcmc.sghmc.sghmc_approximator import SGHMCPosteriorApproximator  # noqa: F401
+from .regression import ProbRegressor  # noqa: F401
 from .prior import IsotropicGaussianPrior  # noqa: F401

@@ -19,5 +19,6 @@ class CyclicalSGLDPosterior(SGMCMCPosterior):
                                           n_samples=a.n_samples, n_thinning=a.n_thinning, cycle_length=a.cycle_length,
                                           exploration_ratio=a.exploration_ratio, trainer=None,
                                           state_repository=self.state, keep_top_n_checkpoints=1)
-        status, self.chain_state = run_sgmcmc(self.bound, self.prior, tx, [cb], train_data_loader, n_epochs, val_data_loader)
+        kw = {} if getattr(self, "log_likelihood_sum", None) is None else {"log_likelihood_sum": self.log_likelihood_sum}
+        status, self.chain_state = run_sgmcmc(self.bound, self.prior, tx, [cb], train_data_loader, n_epochs, val_data_loader, **kw)
         return status

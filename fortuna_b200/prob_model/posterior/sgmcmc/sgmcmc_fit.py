@@ -15,15 +15,20 @@ from ....training.train_state import TrainState
 from .torch_model import BoundModel
 
 
-def batched_log_joint_prob(bound: BoundModel, prior, inputs: torch.Tensor, targets: torch.Tensor, n_data: int) -> torch.Tensor:
-    logits = bound.model(inputs)
-    ll = -torch.nn.functional.cross_entropy(logits, targets.long(), reduction="sum")
+def categorical_log_likelihood_sum(outputs: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """sum_b log softmax(outputs_b)[y_b] - fortuna/prob_output_layer/classification.py:25-28."""
+    return -torch.nn.functional.cross_entropy(outputs, targets.long(), reduction="sum")
+
+
+def batched_log_joint_prob(bound: BoundModel, prior, inputs: torch.Tensor, targets: torch.Tensor, n_data: int,
+                           log_likelihood_sum=categorical_log_likelihood_sum) -> torch.Tensor:
+    ll = log_likelihood_sum(bound.model(inputs), targets)
     lp = sum(prior.log_joint_prob(p) for p in bound.trainable.values())
     return lp + (n_data / inputs.shape[0]) * ll
 
 
 def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader, n_epochs: int, val_data_loader=None,
-               metrics=()) -> Dict[str, np.ndarray]:
+               log_likelihood_sum=categorical_log_likelihood_sum) -> Dict[str, np.ndarray]:
     state = TrainState.create(params=bound.params, tx=tx)
     n_data = train_data_loader.size
     dev = bound.device
@@ -34,7 +39,7 @@ def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader,
             x = torch.as_tensor(inputs, dtype=torch.float32, device=dev)
             y = torch.as_tensor(targets, device=dev)
             bound.zero_grad()
-            lj = batched_log_joint_prob(bound, prior, x, y, n_data)
+            lj = batched_log_joint_prob(bound, prior, x, y, n_data, log_likelihood_sum)
             lj.backward()                                    # d log-joint / d theta lands in bound.grads (flat)
             state = state.apply_gradients(grads=bound.grads)  # fused sampler step, params updated in place
             for cb in callbacks:
@@ -44,7 +49,7 @@ def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader,
         if val_data_loader is not None:
             with torch.no_grad():
                 v = [batched_log_joint_prob(bound, prior, torch.as_tensor(a, dtype=torch.float32, device=dev),
-                                            torch.as_tensor(b, device=dev), val_data_loader.size)
+                                            torch.as_tensor(b, device=dev), val_data_loader.size, log_likelihood_sum)
                      for a, b in val_data_loader]
             val_losses.append(float(torch.stack(v).mean()))
     status = {"loss": np.array(losses)}

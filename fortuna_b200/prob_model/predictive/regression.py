@@ -1,0 +1,101 @@
+"""``prob_model.predictive`` for regression - method names / signatures of
+fortuna/prob_model/predictive/regression.py:22-369 and fortuna/prob_model/predictive/base.py (mean, variances, std,
+log_prob, sample).  Model outputs are ``[mu, log sigma^2]`` (fortuna/prob_output_layer/regression.py:18-74).
+The Monte-Carlo entropies (regression.py:51-267) are a "next" row of the scope and not built."""
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+
+from ... import ops
+
+
+class RegressionPredictive:
+    def __init__(self, posterior, log_temp: Optional[torch.Tensor] = None):
+        self.posterior = posterior
+        self.log_temp = log_temp
+
+    def _stored_outputs(self, x: torch.Tensor) -> torch.Tensor:
+        """[n_stored, B, 2d]: one forward pass per STORED posterior sample."""
+        bound, bank = self.posterior.bound, self.posterior.state
+        keep = bound.params.flat.clone()
+        outs = []
+        with torch.no_grad():
+            for i in range(bank.size):
+                bound.load_flat(bank.bank[i])
+                outs.append(bound.model(x))
+        bound.load_flat(keep)
+        return torch.stack(outs).contiguous()
+
+    def _x(self, loader) -> torch.Tensor:
+        x = loader.to_array_inputs() if hasattr(loader, "to_array_inputs") else loader
+        return torch.as_tensor(np.asarray(x), dtype=torch.float32, device=self.posterior.bound.device)
+
+    def _reduce(self, loader, names, n_posterior_samples, rng, targets=None):
+        if rng is None:
+            rng = self.posterior.rng.get()
+        idx = self.posterior.sample_indices(rng, n_posterior_samples)
+        z = self._stored_outputs(self._x(loader)).index_select(0, idx.long()).contiguous()
+        t = None if targets is None else torch.as_tensor(np.asarray(targets), dtype=torch.float32, device=z.device).reshape(z.shape[1], -1)
+        return ops.bma_reduce_reg(z, names, targets=t, log_temp=self.log_temp)
+
+    def mean(self, inputs_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
+        return self._reduce(inputs_loader, ("mean",), n_posterior_samples, rng)["mean"]
+
+    def mode(self, inputs_loader, n_posterior_samples: int = 30, means=None, rng=None, distribute: bool = True):
+        return means if means is not None else self.mean(inputs_loader, n_posterior_samples, rng)
+
+    def aleatoric_variance(self, inputs_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
+        return self._reduce(inputs_loader, ("aleatoric_variance",), n_posterior_samples, rng)["aleatoric_variance"]
+
+    def epistemic_variance(self, inputs_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
+        return self._reduce(inputs_loader, ("epistemic_variance",), n_posterior_samples, rng)["epistemic_variance"]
+
+    def variance(self, inputs_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
+        return self._reduce(inputs_loader, ("variance",), n_posterior_samples, rng)["variance"]
+
+    def std(self, inputs_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
+        return self._reduce(inputs_loader, ("std",), n_posterior_samples, rng)["std"]
+
+    def log_prob(self, data_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
+        return self._reduce(data_loader, ("log_prob",), n_posterior_samples, rng, data_loader.to_array_targets())["log_prob"]
+
+    def ensemble_log_prob(self, data_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
+        return self._reduce(data_loader, ("ensemble_log_prob",), n_posterior_samples, rng,
+                            data_loader.to_array_targets())["ensemble_log_prob"]
+
+    def sample(self, inputs_loader, n_target_samples: int = 1, return_aux=None, rng=None, distribute: bool = True) -> torch.Tensor:
+        """[T, B, d] target samples.  Like the reference, every input BATCH of the loader is sampled with the same
+        key (the noise array has the batch's shape), so results depend on the loader's batch size exactly as there."""
+        if return_aux:
+            raise NotImplementedError("auxiliary outputs of `sample` are outside the hot path")
+        if rng is None:
+            rng = self.posterior.rng.get()
+        parts = []
+        batches = inputs_loader if hasattr(inputs_loader, "__iter__") else [inputs_loader]
+        for xb in batches:
+            zb = self._stored_outputs(self._x(xb))
+            parts.append(ops.reg_sample_targets(zb, rng, n_target_samples, log_temp=self.log_temp))
+        return torch.cat(parts, dim=1)
+
+    def quantile(self, q: Union[float, List, np.ndarray], inputs_loader, n_target_samples: int = 30, rng=None,
+                 distribute: bool = True) -> torch.Tensor:
+        samples = self.sample(inputs_loader, n_target_samples, rng=rng)
+        scalar = np.ndim(q) == 0
+        qq = torch.as_tensor(np.atleast_1d(np.asarray(q, dtype=np.float32)), device=samples.device)
+        out = ops.quantile_axis0(samples.contiguous(), qq)
+        return out[0] if scalar else out
+
+    def credible_interval(self, inputs_loader, n_target_samples: int = 30, error: float = 0.05,
+                          interval_type: str = "two-tailed", rng=None, distribute: bool = True) -> torch.Tensor:
+        supported_types = ["two-tailed", "right-tailed", "left-tailed"]
+        if interval_type not in supported_types:
+            raise ValueError("`type={}` not recognised. Please choose among the following supported types: {}.".format(
+                interval_type, supported_types))
+        q = [0.5 * error, 1 - 0.5 * error] if interval_type == "two-tailed" else (error if interval_type == "left-tailed" else 1 - error)
+        qq = self.quantile(q, inputs_loader, n_target_samples, rng)
+        if qq.shape[-1] != 1:
+            raise ValueError("""Credibility intervals are only supported for scalar target variables.""")
+        if interval_type == "two-tailed":
+            return qq.squeeze(2).transpose(0, 1).contiguous()  # [B, 2]: (lower, upper) per input
+        return qq

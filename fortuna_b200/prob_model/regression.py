@@ -1,0 +1,60 @@
+"""``ProbRegressor`` - fortuna/prob_model/regression.py with an SG-MCMC posterior: ``model`` predicts the mean,
+``likelihood_log_variance_model`` the log-variance (outputs concatenated to ``[mu, log sigma^2]`` as in
+fortuna/model/model_manager/regression.py); a single module returning ``[B, 2d]`` is accepted too."""
+import math
+from typing import Optional
+
+import torch
+
+from ..utils.random import RandomNumberGenerator
+from .fit_config import FitConfig
+from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_approximator import CyclicalSGLDPosteriorApproximator
+from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_posterior import CyclicalSGLDPosterior
+from .posterior.sgmcmc.sghmc.sghmc_approximator import SGHMCPosteriorApproximator
+from .posterior.sgmcmc.sghmc.sghmc_posterior import SGHMCPosterior
+from .posterior.sgmcmc.torch_model import BoundModel
+from .predictive.regression import RegressionPredictive
+from .prior import IsotropicGaussianPrior
+
+
+class _MeanAndLogVar(torch.nn.Module):
+    def __init__(self, model, lik_log_var):
+        super().__init__()
+        self.model, self.lik_log_var = model, lik_log_var
+
+    def forward(self, x):
+        return torch.cat([self.model(x), self.lik_log_var(x)], dim=-1)
+
+
+def gaussian_log_likelihood_sum(outputs: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """sum_b log N(y_b; mu_b, exp(logvar_b)) - fortuna/prob_output_layer/regression.py:30-34."""
+    d = outputs.shape[-1] // 2
+    mu, lv = outputs[..., :d], outputs[..., d:]
+    t = targets.reshape(mu.shape).to(mu.dtype)
+    return -0.5 * (torch.exp(-lv) * (t - mu) ** 2 + lv + math.log(2 * math.pi)).sum()
+
+
+class ProbRegressor:
+    def __init__(self, model: torch.nn.Module, likelihood_log_variance_model: Optional[torch.nn.Module] = None, prior=None,
+                 posterior_approximator=None, output_calibrator=None, model_editor=None, seed: int = 0, device="cuda"):
+        if model_editor is not None or output_calibrator is not None:
+            raise NotImplementedError("model editors and output-calibrator training are outside the hot path")
+        self.model = model if likelihood_log_variance_model is None else _MeanAndLogVar(model, likelihood_log_variance_model)
+        self.prior = prior if prior is not None else IsotropicGaussianPrior()
+        self.posterior_approximator = posterior_approximator if posterior_approximator is not None else SGHMCPosteriorApproximator()
+        if not isinstance(self.posterior_approximator, (SGHMCPosteriorApproximator, CyclicalSGLDPosteriorApproximator)):
+            raise NotImplementedError("only the SG-MCMC posterior approximators (sghmc, cyclical_sgld) are on the hot path")
+        self.device = torch.device(device)
+        self.rng = RandomNumberGenerator(seed=seed, device=self.device)
+        self.posterior = None
+        self.predictive = None
+
+    def train(self, train_data_loader, val_data_loader=None, calib_data_loader=None, fit_config: Optional[FitConfig] = None, **_):
+        fit_config = fit_config or FitConfig()
+        bound = BoundModel(self.model, self.device, freeze_fun=fit_config.optimizer.freeze_fun)
+        cls = SGHMCPosterior if isinstance(self.posterior_approximator, SGHMCPosteriorApproximator) else CyclicalSGLDPosterior
+        self.posterior = cls(bound, self.prior, self.posterior_approximator, self.rng)
+        self.posterior.log_likelihood_sum = gaussian_log_likelihood_sum
+        status = {"fit_status": self.posterior.fit(train_data_loader, val_data_loader, fit_config)}
+        self.predictive = RegressionPredictive(self.posterior)
+        return status

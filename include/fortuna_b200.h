@@ -203,6 +203,16 @@ typedef struct {
 int fb200_bma_reduce_reg(const float* outputs, const float* log_temp, const float* targets, int S, int B, int d,
                          const fb200_reg_outputs_t* out, void* stream);
 
+/* Monte-Carlo target samples of the regression predictive (Predictive.sample, fortuna/prob_model/predictive/base.py:
+ * 318-441 -> fortuna/likelihood/base.py:339-372 -> fortuna/prob_output_layer/regression.py:38-52), same draws as jax:
+ *   keys = split(key, T); (k1, k2) = split(keys[t]); i_t = choice(k1, n_stored);
+ *   y[t, b, j] = mu[i_t, b, j] + exp(0.5 * logvar[i_t, b, j]) * normal(k2, (1, B, d))[0, b, j]
+ * outputs: [n_stored, B, 2d] calibrated outputs of every STORED posterior sample; y: [T, B, d];
+ * idx_out: optional int32[T] (the drawn sample indices).  The reference calls this once per input batch with the
+ * same key, so B here is the batch the noise shape refers to. */
+int fb200_reg_sample_targets(const float* outputs, const float* log_temp, const uint32_t* key, int n_target_samples,
+                             int n_stored, int B, int d, float* y, int32_t* idx_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Conformal / calibration scoring (K5-K9), bit-exact integer / index outputs.
  * ---------------------------------------------------------------------------------------------- */
@@ -247,6 +257,10 @@ int fb200_ece_from_bins(const int32_t* counts, const float* conf_sums, const int
 /* jnp.quantile(x, q) for sorted ascending x[n], method="linear"
  * (fortuna/conformal/regression/quantile.py:89-90, onedim_uncertainty.py:89-90): out[nq]. */
 int fb200_quantile_sorted(const float* x_sorted, int64_t n, const float* q, int nq, float* out, void* stream);
+
+/* jnp.quantile(x, q, axis=0) for x[T, M] (T <= 256), method="linear": out[nq, M]
+ * (RegressionPredictive.quantile over the target-sample axis, fortuna/prob_model/predictive/regression.py:331-369). */
+int fb200_quantile_axis0(const float* x, int T, int64_t M, const float* q, int nq, float* out, void* stream);
 
 #ifdef __cplusplus
 }

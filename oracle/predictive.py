@@ -276,3 +276,38 @@ def reg_ensemble_log_prob(z, targets):
 def reg_log_prob(z, targets):
     ll = reg_ensemble_log_prob(z, targets)
     return (logsumexp(ll, axis=0) - np.log(F32(ll.shape[0]), dtype=F32)).astype(F32)
+
+
+def reg_sample_targets(outputs_stored, key, n_target_samples, log_temp=None):
+    """Predictive.sample for regression (predictive/base.py:407-441, likelihood/base.py:363-369,
+    prob_output_layer/regression.py:38-52) on ONE input batch: keys = split(rng, T); per key (k1, k2) = split(key);
+    posterior sample i = choice(k1, n_stored); y = mu_i + exp(0.5 logvar_i) * normal(k2, (1,) + mu.shape).
+    outputs_stored: [n_stored, B, 2d].  Returns (y [T, B, d], idx [T])."""
+    from . import prng
+
+    z = _f32(outputs_stored)
+    n, B, two_d = z.shape
+    d = two_d // 2
+    keys = prng.split(np.asarray(key, dtype=np.uint32), n_target_samples)
+    ys, idx = [], []
+    for k in keys:
+        k1, k2 = prng.split(k, 2)
+        i = prng.choice(k1, n)
+        zi = z[i] if log_temp is None else reg_calibrate(z[i : i + 1], log_temp)[0]
+        mu, lv = zi[:, :d], zi[:, d:]
+        eps = prng.normal(k2, B * d).reshape(B, d)
+        ys.append((mu + np.exp(F32(0.5) * lv, dtype=F32) * eps).astype(F32))
+        idx.append(i)
+    return np.stack(ys), np.array(idx, dtype=np.int32)
+
+
+def quantile_axis0(x, q):
+    """jnp.quantile(x, q, axis=0), method="linear"."""
+    from .scoring import quantile_linear
+
+    x = _f32(x)
+    T = x.shape[0]
+    flat = x.reshape(T, -1)
+    q = np.atleast_1d(_f32(q))
+    out = np.stack([quantile_linear(flat[:, m], q) for m in range(flat.shape[1])], axis=1)
+    return out.reshape((len(q),) + x.shape[1:])

@@ -1,0 +1,78 @@
+"""Regression side of the path: Monte-Carlo target samples with jax's exact draws, axis-0 quantiles, and the
+ProbRegressor / RegressionPredictive user API on a 1-D sine regression (fortuna/prob_model/predictive/regression.py,
+fortuna/prob_output_layer/regression.py, tests/fortuna/test_predictive.py:61-230 check shapes and variance >= 0)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import predictive as P
+from oracle import prng as oprng
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,B,d,T", [(5, 7, 2, 6), (10, 129, 1, 30), (3, 33, 3, 1)])
+def test_reg_sample_targets_matches_oracle(cuda, n, B, d, T):
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(n * 10 + d)
+    z = r.standard_normal((n, B, 2 * d)).astype(np.float32)
+    lt = np.array([0.25], np.float32)
+    want, want_idx = P.reg_sample_targets(z, oprng.PRNGKey(9), T, lt)
+    y, idx = ops.reg_sample_targets(torch.from_numpy(z).to(cuda), ops.PRNGKey(9, cuda), T,
+                                    log_temp=torch.from_numpy(lt).to(cuda), want_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), want_idx)  # posterior-sample draws: bit-exact
+    np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("T,shape", [(30, (50, 1)), (7, (13, 3)), (1, (4, 2)), (256, (9, 1))])
+def test_quantile_axis0_matches_oracle(cuda, T, shape):
+    from fortuna_b200 import ops
+
+    x = np.random.default_rng(T).standard_normal((T,) + shape).astype(np.float32)
+    q = np.array([0.0, 0.025, 0.5, 0.975, 1.0], np.float32)
+    got = ops.quantile_axis0(torch.from_numpy(x).to(cuda), torch.from_numpy(q).to(cuda)).cpu().numpy()
+    np.testing.assert_allclose(got, P.quantile_axis0(x, q), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(got, np.quantile(x.astype(np.float64), q.astype(np.float64), axis=0), rtol=1e-5, atol=1e-6)
+
+
+def test_prob_regressor_sine(cuda):
+    from fortuna_b200.data import DataLoader
+    from fortuna_b200.prob_model import FitConfig, FitOptimizer, ProbRegressor, SGHMCPosteriorApproximator
+
+    r = np.random.default_rng(0)
+    x = r.uniform(-3, 3, (400, 1)).astype(np.float32)
+    y = (np.sin(x) + 0.2 * r.standard_normal(x.shape)).astype(np.float32)
+    xt = np.linspace(-3, 3, 64, dtype=np.float32)[:, None]
+    yt = np.sin(xt)
+    mlp = lambda out: torch.nn.Sequential(torch.nn.Linear(1, 50), torch.nn.Tanh(), torch.nn.Linear(50, out))
+    torch.manual_seed(0)
+    pr = ProbRegressor(model=mlp(1), likelihood_log_variance_model=mlp(1),
+                       posterior_approximator=SGHMCPosteriorApproximator(n_samples=10, n_thinning=10, burnin_length=1500,
+                                                                         step_schedule=1e-5), seed=1)
+    pr.train(DataLoader.from_array_data((x, y), batch_size=100, shuffle=True),
+             fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=650)))
+    test = DataLoader.from_array_data((xt, yt), batch_size=32)
+    inputs = test.to_inputs_loader()
+    key = pr.rng.get()
+    mean = pr.predictive.mean(inputs, 20, rng=key)
+    var = pr.predictive.variance(inputs, 20, rng=key)
+    assert mean.shape == (64, 1) and var.shape == (64, 1) and bool((var >= 0).all())
+    assert float((mean.cpu() - torch.from_numpy(yt)).abs().mean()) < 0.15
+    lp = pr.predictive.log_prob(test, 20, rng=key)
+    assert lp.shape == (64,) and bool(torch.isfinite(lp).all())
+    # sample / quantile / credible interval: reference semantics (per-batch noise with the same key) vs the oracle
+    smp = pr.predictive.sample(inputs, n_target_samples=30, rng=key)
+    assert smp.shape == (30, 64, 1)
+    stored = pr.predictive._stored_outputs(torch.from_numpy(xt).to(cuda)).cpu().numpy()
+    from fortuna_b200 import ops
+
+    want = np.concatenate([P.reg_sample_targets(stored[:, i : i + 32], ops.key_to_host(key), 30)[0] for i in (0, 32)], axis=1)
+    np.testing.assert_allclose(smp.cpu().numpy(), want, rtol=1e-5, atol=2e-6)
+    ci = pr.predictive.credible_interval(inputs, n_target_samples=30, error=0.05, rng=key)
+    assert ci.shape == (64, 2) and bool((ci[:, 0] < ci[:, 1]).all())
+    np.testing.assert_allclose(ci.cpu().numpy()[:, 0], P.quantile_axis0(want, [0.025])[0, :, 0], rtol=1e-5, atol=1e-6)
+    q = pr.predictive.quantile(0.5, inputs, n_target_samples=30, rng=key)
+    assert q.shape == (64, 1)
+    with pytest.raises(ValueError):
+        pr.predictive.credible_interval(inputs, interval_type="both")

@@ -19,6 +19,10 @@ int last_layer_tc_launch(const void* x, const void* w, const float* bias, const 
                          const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
                          int out_dtype, int c_split, cudaStream_t st);
 
+int last_layer_tc2_launch(const void* x, const void* w, const float* bias, const float* log_temp,
+                          const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
+                          int out_dtype, cudaStream_t st);
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
@@ -178,12 +182,17 @@ extern "C" int fb200_last_layer_logits(const void* x, const void* w, const float
   if ((in_dtype != FB200_F32 && in_dtype != FB200_BF16) || (out_dtype != FB200_F32 && out_dtype != FB200_BF16))
     return FB200_E_UNSUPPORTED;
   if (w_layout != FB200_W_SDC && w_layout != FB200_W_SCD) return FB200_E_UNSUPPORTED;
-  if (path < 0 || path > 2) return FB200_E_UNSUPPORTED;
+  if (path < 0 || path > 3) return FB200_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const int tc_ok = last_layer_tc_supported(S, B, D, C, in_dtype, out_dtype, w_layout);
-  if (path == 2 && !tc_ok) return FB200_E_UNSUPPORTED;
+  if ((path == 2 || path == 3) && !tc_ok) return FB200_E_UNSUPPORTED;
+  if (path == 3) return last_layer_tc2_launch(x, w, bias, log_temp, sample_idx, n_stored, out, S, B, D, C, out_dtype, st);
   // auto: tensor cores only when the contraction is large enough to be compute-bound (D >= 256, C >= 64)
   const bool use_tc = path == 2 || (path == 0 && tc_ok && D >= 256 && C >= 64 && B >= 128);
+  // long contractions are operand-traffic bound on one CTA: the CTA-pair kernel (cta_group::2) moves 2/3 of the bytes
+  // per flop (measured at c4, D = 2048: 1306 vs 1212 TFLOP/s f32 logits; no difference at D = 512)
+  if (use_tc && path == 0 && D >= 1024 && B >= 512 && C >= 256)
+    return last_layer_tc2_launch(x, w, bias, log_temp, sample_idx, n_stored, out, S, B, D, C, out_dtype, st);
   if (use_tc) return last_layer_tc_launch(x, w, bias, log_temp, sample_idx, n_stored, out, S, B, D, C, out_dtype, 0, st);
   // narrow last layer in bf16 (e.g. BERT classifier 768 x 2): fold the sample axis into the column axis so the
   // tensor cores see N = S * C columns; needs the identity sample map (stored rows are then one [S*C, D] matrix)

@@ -129,7 +129,9 @@ int fb200_bank_put_f32(float* bank, int64_t n, int row, const float* src, void* 
  * w_layout: FB200_W_SDC = [S,D,C] (flax kernel layout), FB200_W_SCD = [S,C,D] (K-major copy).
  * The tcgen05 path needs in_dtype = BF16, w_layout = SCD, D % 64 == 0 (use fb200_transpose_w_bf16 once
  * per sample bank); every other shape runs the CUDA-core path.  `path`: 0 auto, 1 force CUDA-core,
- * 2 force tcgen05 (FB200_E_UNSUPPORTED if the shape does not qualify).
+ * 2 force the one-CTA tcgen05 kernel, 3 force the CTA-pair (cta_group::2) tcgen05 kernel (FB200_E_UNSUPPORTED if the
+ * shape does not qualify).  Auto: CTA-pair kernel for D >= 1024, one-CTA kernel for D >= 256 and C >= 64, bf16 layers
+ * narrower than 64 classes with the samples folded into the column axis, CUDA cores otherwise.
  * sample_idx: optional device int32[S]; row s of the output uses w[sample_idx[s]] / bias[sample_idx[s]] - the
  * posterior.sample() index draw (fortuna/prob_model/posterior/sgmcmc/sgmcmc_posterior.py:48-52) fused into
  * the contraction, so drawn samples are never gathered or copied.  NULL = identity.

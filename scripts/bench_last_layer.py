@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--out", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--no-cublas", action="store_true")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 2 one-CTA tcgen05 kernel, 3 CTA-pair (cta_group::2) kernel")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -47,8 +48,8 @@ def main():
     odt = torch.float32 if a.out == "f32" else torch.bfloat16
     out = torch.empty((a.S, a.B, a.C), device=dev, dtype=odt)
     flops = 2.0 * a.S * a.B * a.D * a.C
-    ms = timeit(lambda: ops.last_layer_logits(x, wt, bias, lt, w_layout=ops.W_SCD, path=2, out=out), a.iters)
-    res = {"shape": {"S": a.S, "B": a.B, "D": a.D, "C": a.C, "out": a.out}, "ms": ms, "tflops": flops / ms / 1e9,
+    ms = timeit(lambda: ops.last_layer_logits(x, wt, bias, lt, w_layout=ops.W_SCD, path=a.path, out=out), a.iters)
+    res = {"shape": {"S": a.S, "B": a.B, "D": a.D, "C": a.C, "out": a.out}, "path": a.path, "ms": ms, "tflops": flops / ms / 1e9,
            "frac_of_burst": flops / ms / 1e9 / peaks.get("bf16_tflops", 1656.1),
            "frac_of_sustained": flops / ms / 1e9 / peaks.get("bf16_tflops_sustained", 1382.0),
            "out_write_gbs": out.numel() * out.element_size() / ms / 1e6}

@@ -114,3 +114,30 @@ def test_narrow_last_layer_folds_samples_into_columns(cuda, S, B, D, C, out_dtyp
     tol = 2e-3 if out_dtype == torch.float32 else 1e-2
     np.testing.assert_allclose(auto.float().cpu().numpy(), want, rtol=tol, atol=tol * np.sqrt(D) / 8)
     np.testing.assert_allclose(simt.float().cpu().numpy(), want, rtol=tol, atol=tol * np.sqrt(D) / 8)
+
+
+@pytest.mark.parametrize(
+    "S,B,D,C,out_dtype",
+    [(1, 256, 64, 256, torch.float32), (2, 300, 128, 1000, torch.float32), (3, 129, 512, 10, torch.float32),
+     (2, 1000, 2048, 1000, torch.float32), (1, 77, 72, 40, torch.float32), (5, 4096, 512, 1000, torch.bfloat16),
+     (3, 2500, 256, 333, torch.float32)],
+)
+def test_cta_pair_kernel_matches_oracle(cuda, S, B, D, C, out_dtype):
+    """path=3: the cta_group::2 kernel (256 x 256 tile per CTA pair) against the oracle and the 1-CTA kernel."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(S + B + C)
+    x = r.standard_normal((B, D)).astype(np.float32)
+    w = (r.standard_normal((S, D, C)) / np.sqrt(D)).astype(np.float32)
+    bias = r.standard_normal((S, C)).astype(np.float32)
+    lt = np.array([0.3], dtype=np.float32)
+    want = P.last_layer_logits(x, w, bias, lt, bf16_inputs=True)
+    xt = torch.from_numpy(x).to(cuda).to(torch.bfloat16)
+    wt = ops.transpose_w_bf16(torch.from_numpy(w).to(cuda))
+    args = (xt, wt, torch.from_numpy(bias).to(cuda), torch.from_numpy(lt).to(cuda))
+    pair = ops.last_layer_logits(*args, out_dtype=out_dtype, w_layout=ops.W_SCD, path=3)
+    one = ops.last_layer_logits(*args, out_dtype=out_dtype, w_layout=ops.W_SCD, path=2)
+    torch.cuda.synchronize()
+    tol = 2e-3 if out_dtype == torch.float32 else 1e-2
+    np.testing.assert_allclose(pair.float().cpu().numpy(), want, rtol=tol, atol=tol * np.sqrt(D) / 8)
+    assert torch.equal(pair, one)  # same K order and fp32 accumulation: bit-identical to the 1-CTA kernel

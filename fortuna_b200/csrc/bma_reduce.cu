@@ -46,6 +46,7 @@ struct ClsArgs {
   fb200_cls_outputs_t out;
   const unsigned long long* slot_ptrs;  // shard mode: device array [n_ranks] of float* (local or peer memory)
   int n_ranks, rows_per_rank;
+  int tile_rot;  // shard mode: tiles are visited starting here (staggered per rank: no owner is everyone's target at once)
   int partial_mode;
   int n_tiles;
   int n_stages;
@@ -221,7 +222,9 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
     if (warp != kConsumerWarps) return;
     const T* base = reinterpret_cast<const T*>(a.logits);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int tv = blockIdx.x; tv < a.n_tiles; tv += gridDim.x) {
+      int tile = tv + a.tile_rot;
+      if (tile >= a.n_tiles) tile -= a.n_tiles;
       const int b0 = tile * TB;
       const int rows = min(TB, B - b0);
       const uint32_t bytes = (uint32_t)rows * (uint32_t)C * (uint32_t)sizeof(T);
@@ -268,7 +271,9 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
   const float k2 = scale * 1.4426950408889634f;
 
   uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+  for (int tv = blockIdx.x; tv < a.n_tiles; tv += gridDim.x) {
+    int tile = tv + a.tile_rot;
+    if (tile >= a.n_tiles) tile -= a.n_tiles;
     const int b = tile * TB + row;
     const bool valid_row = b < B;
     float sp[NV][VEC], sp2[NV][VEC];
@@ -637,6 +642,7 @@ static int launch_cls_cfg(ClsArgs a, cudaStream_t st) {
   if (nst < 2) nst = 2;
   a.n_stages = nst;
   a.n_tiles = (a.B + TB - 1) / TB;
+  a.tile_rot = a.partial_mode ? (int)(((long long)a.n_tiles * a.tile_rot) / (a.n_ranks > 0 ? a.n_ranks : 1)) : 0;  // rank -> first tile
   const size_t smem = 128 + (size_t)nst * a.stage_bytes;
   auto kern = bma_reduce_cls_kernel<T, G, NV, VEC, TAILONLY, NW, RI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -737,14 +743,15 @@ extern "C" int fb200_bma_reduce_cls(const void* logits, int dtype, const float* 
 extern "C" size_t fb200_cls_slot_row_floats(int C) { return C > 0 ? (size_t)(2 * C + 4) : 0; }
 
 extern "C" int fb200_bma_reduce_cls_shard(const void* logits, int dtype, const float* log_temp,
-                                          const int32_t* targets, int S, int B, int C, int n_ranks,
+                                          const int32_t* targets, int S, int B, int C, int n_ranks, int rank,
                                           const uint64_t* slot_ptrs, void* stream) {
   if (!slot_ptrs) return FB200_E_NULL;
-  if (n_ranks <= 0 || B <= 0 || B % n_ranks != 0) return FB200_E_SHAPE;
+  if (n_ranks <= 0 || B <= 0 || B % n_ranks != 0 || rank < 0 || rank >= n_ranks) return FB200_E_SHAPE;
   ClsArgs a{};
   a.partial_mode = 1;
   a.slot_ptrs = reinterpret_cast<const unsigned long long*>(slot_ptrs);
   a.n_ranks = n_ranks;
+  a.tile_rot = rank;  // turned into a tile index once the tile size is known (launch_cls_cfg)
   a.rows_per_rank = B / n_ranks;
   return reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
 }

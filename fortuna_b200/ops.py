@@ -286,7 +286,7 @@ def slot_pointer_table(slot_tensors_or_ptrs, device):
     return torch.from_numpy(np.array(ptrs, dtype=np.uint64).view(np.int64).copy()).to(device)
 
 
-def bma_reduce_cls_shard(logits, slot_ptrs, targets=None, log_temp=None):
+def bma_reduce_cls_shard(logits, slot_ptrs, targets=None, log_temp=None, rank=0):
     """Shard mode of the single-pass reduction: export this rank's partial sums row by row into the slot of the
     rank owning the row.  slot_ptrs: int64 device tensor [n_ranks] from slot_pointer_table."""
     S, B, Cn = logits.shape
@@ -300,6 +300,7 @@ def bma_reduce_cls_shard(logits, slot_ptrs, targets=None, log_temp=None):
             B,
             Cn,
             slot_ptrs.numel(),
+            int(rank),
             _ptr(slot_ptrs, torch.int64),
             _stream(),
         ),

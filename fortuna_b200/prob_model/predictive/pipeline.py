@@ -87,7 +87,7 @@ class PredictivePipeline:
             if kernel_events:
                 kernel_events[1].record()
             return self.outs
-        ops.bma_reduce_cls_shard(z, self.slot_ptrs, targets=targets)
+        ops.bma_reduce_cls_shard(z, self.slot_ptrs, targets=targets, rank=self.rank)
         if kernel_events:
             kernel_events[1].record()
         # the one exchange step of the S-sharded path: every rank ends up with all ranks' partials for its B/N rows

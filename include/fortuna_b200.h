@@ -180,10 +180,14 @@ int fb200_bma_reduce_cls(const void* logits, int dtype, const float* log_temp, c
  * floats each:  [ sum_s p (C) | sum_s p^2 (C) | sum_s sum_c p ln p, max_s ll, sum_s exp(ll - max), 0 ].
  * A slot pointer may be local memory (a send buffer, then ONE all-to-all moves slot o to rank o) or PEER memory
  * mapped over NVLink (the kernel's epilogue stores straight into rank o's receive buffer: no collective at all,
- * only a barrier before the finalisation). */
+ * only a barrier before the finalisation).
+ */
 size_t fb200_cls_slot_row_floats(int C);
+/*
+ * `rank` (this rank's index) only staggers the order in which input tiles are visited - rank r starts r/N of the way
+ * through - so that at any moment the N ranks store into N different owners instead of all into the same one. */
 int fb200_bma_reduce_cls_shard(const void* logits, int dtype, const float* log_temp, const int32_t* targets, int S,
-                               int B, int C, int n_ranks, const uint64_t* slot_ptrs, void* stream);
+                               int B, int C, int n_ranks, int rank, const uint64_t* slot_ptrs, void* stream);
 /* Finalise `rows` owned rows from the n_src slots received (slots: [n_src][rows][fb200_cls_slot_row_floats(C)],
  * one per source rank, summed in source order; the (max, sumexp) pairs are merged), over s_total samples. */
 int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int rows, int C, int s_total,

@@ -125,7 +125,7 @@ def test_shard_slots_finalize_equals_fused(cuda, S, B, C, n_ranks):
         send = ops.alloc_cls_slots(n_ranks, rows, C, cuda)
         send.fill_(float("nan"))
         ptrs = ops.slot_pointer_table([send[o] for o in range(n_ranks)], cuda)
-        ops.bma_reduce_cls_shard(zt[bounds[r] : bounds[r + 1]].contiguous(), ptrs, targets=tt)
+        ops.bma_reduce_cls_shard(zt[bounds[r] : bounds[r + 1]].contiguous(), ptrs, targets=tt, rank=r)
         sends.append(send)
     want = [n for n in ALL if n != "ensemble_log_prob"]
     parts = {n: [] for n in want}

@@ -339,7 +339,268 @@ static int launch_row_sort_warp(const RowSortArgs& a, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Key-only variant (no permutation requested): the network sorts bare 32-bit keys ~ordered(prob), so a
+// compare-exchange is one min and one max (the 64-bit (prob, class) keys cost a 2-instruction compare and four
+// selects), and the class a rank belongs to is never carried around.  Instead every class finds its own rank
+// afterwards: rank(c) = #{keys strictly before key(c)} + #{c' > c with key(c') == key(c)} - the stable
+// descending order of argsort(...)[::-1] (adaptive_prediction.py:13,20).  The first term is a branch-free lower
+// bound over the sorted keys in shared memory (log2(32*NR) probes; slot i lives at i + i/32 so that probes of
+// different 32-slot blocks fall into different banks); the second term is zero unless the row holds equal
+// probabilities, which the sorted registers reveal with one compare per slot - only such rows run the tie pass
+// (match_any per register slot, classes visited from high to low, one running counter per group of equal keys).
+// Prefix sums are taken over the sorted values exactly as in the 64-bit kernel, so the outputs are the same bits.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ce_min_first(uint32_t& a, uint32_t& b) {
+  const uint32_t lo = min(a, b);
+  const uint32_t hi = max(a, b);
+  a = lo;
+  b = hi;
+}
+
+// The network in two parts.  Merge levels that stay inside a lane (k < NR) are straight-line code on static
+// register indices.  From k = NR on, every level is: complement the lane's keys if its block changes direction, the
+// cross-lane stages (one shuffle + one predicated min/max per key; the lane mask is a loop variable), then the same
+// in-lane merge j = NR/2..1 for every k - so these levels are ONE rolled loop body.  Fully unrolled, the kernel was
+// 90 KB of straight-line code and stalled on instruction fetch more than on anything else (icache hit rate 61 %).
+template <int NR>
+__device__ __forceinline__ void warp_bitonic_sort32(uint32_t (&key)[NR], int lane) {
+  constexpr int N = 32 * NR;
+#pragma unroll
+  for (int k = 2; k < NR; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        if ((r & j) == 0) {
+          if ((r & k) == 0) ce_min_first(key[r], key[r | j]);
+          else ce_min_first(key[r | j], key[r]);
+        }
+      }
+    }
+  }
+  uint32_t flipped = 0u;  // all-ones while the lane's keys are stored complemented
+#pragma unroll 1
+  for (int kl = 1; kl <= 32; kl <<= 1) {  // k = kl * NR
+    const uint32_t want = (kl < 32 && (lane & kl) != 0) ? 0xFFFFFFFFu : 0u;
+    const uint32_t x = want ^ flipped;
+    flipped = want;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) key[r] ^= x;
+#pragma unroll 1
+    for (int lmask = kl >> 1; lmask > 0; lmask >>= 1) {
+      const bool upper = (lane & lmask) != 0;  // the upper lane of a pair keeps the larger key
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, key[r], lmask);
+        key[r] = upper ? max(key[r], other) : min(key[r], other);
+      }
+    }
+#pragma unroll
+    for (int j = NR >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        if ((r & j) == 0) ce_min_first(key[r], key[r | j]);
+    }
+  }
+}
+
+template <int NR>
+__host__ __device__ constexpr int sort32_pad() { return 32 * NR + NR; }  // slot i at i + (i >> 5)
+// shared-memory words per warp: raw row [32 NR] (+ sorted keys and prefix sums, padded), 16-byte granular so that
+// every warp's staging buffer is a legal cp.async 16 destination
+template <int NR, int MODE>
+__host__ __device__ constexpr int sort32_warp_words() {
+  return ((MODE == 0 ? 32 * NR + 2 * sort32_pad<NR>() : 32 * NR) + 3) & ~3;
+}
+
+// One level of the branch-free lower bound for all NR searches of the lane, then the next level (the step is a
+// template parameter because the LDS offset has to be an immediate).  Slot pos + STEP - 1 is probed: for STEP >= 32
+// both pos and STEP are multiples of 32, so its padded address is addr(pos) + STEP + STEP/32 - 2.
+template <int NR, int STEP>
+__device__ __forceinline__ void lower_bound_levels(uint32_t (&ap)[NR], const uint32_t (&own)[NR]) {
+  if constexpr (STEP >= 1) {
+    constexpr int inc = STEP + (STEP >> 5);
+    constexpr int probe = STEP >= 32 ? inc - 2 : STEP - 1;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      uint32_t v;
+      asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(ap[r]), "n"(probe * 4));
+      if (v < own[r]) ap[r] += inc * 4;
+    }
+    lower_bound_levels<NR, STEP / 2>(ap, own);
+  }
+}
+
+// Asynchronous copy of one row (class order) into the warp's staging buffer: LDGSTS, 16 bytes per lane where the
+// row is 16-byte aligned, else 4.  The next row is requested as soon as the current one has been consumed, so its
+// HBM latency hides behind the rank lookup instead of stalling the 4 warps a scheduler has.
+template <int NR>
+__device__ __forceinline__ void row_prefetch(float* srow, const float* row, int C, int lane, bool vec16) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(srow);
+  if (vec16) {
+    for (int q = lane; q * 4 < C; q += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * 16), "l"(row + q * 4) : "memory");
+  } else {
+    for (int c = lane; c < C; c += 32)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + c * 4), "l"(row + c) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int NR, int MODE>  // MODE 0: all-class scores; 1: target score
+__global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(const RowSortArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int N = 32 * NR;
+  constexpr int PAD = sort32_pad<NR>();
+  constexpr int kWarpWords = sort32_warp_words<NR, MODE>();
+  const int warp_in_cta = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int C = a.C;
+  float* srow = reinterpret_cast<float*>(smem_raw) + (size_t)warp_in_cta * kWarpWords;  // the raw row, class order
+  uint32_t* skey = reinterpret_cast<uint32_t*>(srow + N);                                // sorted keys, padded
+  int* scnt = reinterpret_cast<int*>(skey);  // tie pass only; the sorted keys are dead by then
+  const bool vec16 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.probs) & 15) == 0);
+  const int nwarps = gridDim.x * kSortWarps;
+  int b = blockIdx.x * kSortWarps + warp_in_cta;
+  if (b < a.B) row_prefetch<NR>(srow, a.probs + (size_t)b * C, C, lane, vec16);
+  for (; b < a.B; b += nwarps) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    uint32_t own[NR], key[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int c = r * 32 + lane;
+      key[r] = (c < C) ? ~f32_ordered(srow[c] + 0.0f) : 0xFFFFFFFFu;  // -0 -> +0; padding sorts last
+    }
+    int tpos = -1;
+    if (MODE == 1) {
+      // rank of the target class, counted on the unsorted row
+      const int y = a.targets ? a.targets[b] : -1;
+      if ((unsigned)y < (unsigned)C) {
+        const uint32_t ky = ~f32_ordered(srow[y] + 0.0f);
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int c = r * 32 + lane;
+          cnt += (key[r] < ky || (key[r] == ky && c > y && c < C)) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        tpos = cnt;
+      }
+      __syncwarp();
+      if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
+    }
+    warp_bitonic_sort32<NR>(key, lane);
+    float x[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) x[r] = (lane * NR + r < C) ? f32_unordered(~key[r]) : 0.0f;
+    warp_row_tree_prefix<NR>(x, lane);
+    if (MODE == 1) {
+      float ys = CUDART_NAN_F;
+      if (tpos >= 0) {
+        float v = 0.0f;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) v = (lane * NR + r == tpos) ? x[r] : v;
+        ys = __shfl_sync(0xffffffffu, v, tpos / NR);
+      }
+      if (lane == 0 && a.scores) a.scores[b] = ys;
+    }
+    if (MODE == 0) {
+      // equal neighbours among the real (rank < C) keys?
+      bool tie = false;
+#pragma unroll
+      for (int r = 0; r + 1 < NR; ++r) tie |= (key[r] == key[r + 1]) && (lane * NR + r + 1 < C);
+      {
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, key[0], 1);
+        tie |= (lane < 31) && (key[NR - 1] == nxt) && ((lane + 1) * NR < C);
+      }
+      const bool any_tie = __any_sync(0xffffffffu, tie);
+      // the row's own keys again, class order, then the staging buffer is free for the next row
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int c = r * 32 + lane;
+        own[r] = (c < C) ? ~f32_ordered(srow[c] + 0.0f) : 0xFFFFFFFFu;
+      }
+      const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(skey);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int i = lane * NR + r;
+        const uint32_t ad = sbase + (uint32_t)(i + (i >> 5)) * 4u;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ad), "r"(key[r]) : "memory");
+        asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(ad), "f"(x[r]), "n"(PAD * 4) : "memory");
+      }
+      __syncwarp();
+      if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
+      // lower bound, kept as the shared-space BYTE address of the slot so that a probe is one LDS with an
+      // immediate offset, one compare and one predicated add
+      uint32_t ap[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) ap[r] = sbase;
+      lower_bound_levels<NR, N / 2>(ap, own);
+      if (any_tie) {
+        __syncwarp();
+        for (int i = lane; i < PAD; i += 32) scnt[i] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int r = NR - 1; r >= 0; --r) {
+          const unsigned m = __match_any_sync(0xffffffffu, own[r]);
+          const int above = __popc(m & ~((2u << lane) - 1u));  // equal keys in higher lanes == larger classes
+          const int slot = (int)((ap[r] - sbase) >> 2);
+          const int base = scnt[slot];
+          __syncwarp();
+          if (lane == __ffs(m) - 1) scnt[slot] = base + __popc(m);
+          __syncwarp();
+          const int pos = slot - slot / 33 + base + above;
+          ap[r] = sbase + (uint32_t)(pos + (pos >> 5)) * 4u;
+        }
+      }
+      if (a.scores) {
+        float* orow = a.scores + (size_t)b * C;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int c = r * 32 + lane;
+          float v;
+          asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(ap[r]), "n"(PAD * 4));
+          if (c < C) orow[c] = v;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int NR>
+static int launch_row_sort32_warp(const RowSortArgs& a, cudaStream_t st) {
+  const int mode = a.targets ? 1 : 0;
+  const size_t words = mode == 0 ? sort32_warp_words<NR, 0>() : sort32_warp_words<NR, 1>();
+  const size_t smem = (size_t)kSortWarps * words * sizeof(uint32_t);
+  int grid = (a.B + kSortWarps - 1) / kSortWarps;
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (mode == 0) {
+    auto kern = row_sort32_warp_kernel<NR, 0>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<grid, kSortWarps * 32, smem, st>>>(a);
+  } else {
+    row_sort32_warp_kernel<NR, 1><<<grid, kSortWarps * 32, smem, st>>>(a);
+  }
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
 static int launch_row_sort(RowSortArgs a, cudaStream_t st) {
+  if (!a.perm && !a.set_size && a.C <= 1024) {
+    if (a.C <= 32) return launch_row_sort32_warp<1>(a, st);
+    if (a.C <= 64) return launch_row_sort32_warp<2>(a, st);
+    if (a.C <= 128) return launch_row_sort32_warp<4>(a, st);
+    if (a.C <= 256) return launch_row_sort32_warp<8>(a, st);
+    if (a.C <= 512) return launch_row_sort32_warp<16>(a, st);
+    return launch_row_sort32_warp<32>(a, st);
+  }
   if (a.C <= 32) return launch_row_sort_warp<1>(a, st);
   if (a.C <= 64) return launch_row_sort_warp<2>(a, st);
   if (a.C <= 128) return launch_row_sort_warp<4>(a, st);

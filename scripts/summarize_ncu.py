@@ -21,7 +21,7 @@ KEEP = (
     "sm__cycles_elapsed.max", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex_op_read.sum",
-    "sm__cycles_elapsed.max.per_second",
+    "sm__cycles_elapsed.max.per_second", "sm__icc_request_hit_rate.pct",
 )
 
 

@@ -27,11 +27,47 @@ def test_aps_scores_bit_exact(cuda, B, C, ties):
     allc, perm = ops.aps_scores(pt, None, want_perm=True)
     assert np.array_equal(perm.cpu().numpy(), Sc.descending_perm(p))
     assert np.array_equal(allc.cpu().numpy(), Sc.aps_cumsums(p))
+    # without the permutation output the key-only kernel runs (32-bit sort + rank lookup): same bits
+    assert np.array_equal(ops.aps_scores(pt, None).cpu().numpy(), Sc.aps_cumsums(p))
     tgt = ops.aps_scores(pt, torch.from_numpy(t).to(cuda))
     assert np.array_equal(tgt.cpu().numpy(), Sc.aps_score(p, t))
     s = ops.simple_scores(pt, torch.from_numpy(t).to(cuda))
     assert np.array_equal(s.cpu().numpy(), Sc.simple_score(p, t))
     assert np.array_equal(ops.simple_scores(pt).cpu().numpy(), Sc.simple_scores_all(p))
+
+
+@pytest.mark.parametrize("C", [1, 2, 31, 32, 33, 100, 257, 512, 513, 1000, 1024])
+def test_aps_scores_degenerate_rows(cuda, C):
+    """Rows where the rank of a class is decided by the tie rule (larger class first): all-equal rows, rows that
+    underflowed to exact zeros, runs of duplicates crossing lane boundaries, a single dominant class."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(C)
+    rows = [np.full(C, 1.0 / C, dtype=np.float32)]
+    z = np.zeros(C, dtype=np.float32)
+    z[r.integers(0, C)] = 1.0
+    rows.append(z)
+    q = P.softmax((4 * r.standard_normal((1, C))).astype(np.float32))[0]
+    q[r.random(C) < 0.6] = 0.0
+    rows.append(q)
+    d = P.softmax((4 * r.standard_normal((1, C))).astype(np.float32))[0]
+    d = d[r.integers(0, max(C // 7, 1), C)]  # few distinct values, each repeated many times
+    rows.append(d)
+    e = P.softmax((4 * r.standard_normal((1, C))).astype(np.float32))[0]
+    e[::2] = e[0]
+    rows.append(e)
+    rows.append(np.where(np.arange(C) % 3 == 0, np.float32(-0.0), np.float32(0.0)).astype(np.float32))
+    rows.append(P.softmax((4 * r.standard_normal((1, C))).astype(np.float32))[0])
+    p = np.stack(rows).astype(np.float32)
+    p = np.concatenate([p] * 3)  # more rows than one warp sees: tie rows and clean rows alternate on a warp
+    t = r.integers(0, C, p.shape[0]).astype(np.int32)
+    pt = torch.from_numpy(p).to(cuda)
+    want = Sc.aps_cumsums(p)
+    assert np.array_equal(ops.aps_scores(pt, None).cpu().numpy(), want)
+    allc, perm = ops.aps_scores(pt, None, want_perm=True)
+    assert np.array_equal(allc.cpu().numpy(), want)
+    assert np.array_equal(perm.cpu().numpy(), Sc.descending_perm(p))
+    assert np.array_equal(ops.aps_scores(pt, torch.from_numpy(t).to(cuda)).cpu().numpy(), Sc.aps_score(p, t))
 
 
 @pytest.mark.parametrize("n", [1, 2, 100, 4096, 4097, 50_000, 300_001])

@@ -1,6 +1,6 @@
 """User-facing names of fortuna.prob_model for the SG-MCMC hot path."""
 from .classification import ProbClassifier  # noqa: F401
-from .fit_config import FitConfig, FitMonitor, FitOptimizer  # noqa: F401
+from .fit_config import FitCheckpointer, FitConfig, FitMonitor, FitOptimizer  # noqa: F401
 from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_approximator import CyclicalSGLDPosteriorApproximator  # noqa: F401
 from .posterior.sgmcmc.sghmc.sghmc_approximator import SGHMCPosteriorApproximator  # noqa: F401
 from .regression import ProbRegressor  # noqa: F401

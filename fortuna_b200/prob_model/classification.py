@@ -42,6 +42,7 @@ class ProbClassifier:
         self.rng = RandomNumberGenerator(seed=seed, device=self.device)  # one key chain shared by all parts (base.py:36-48)
         self.posterior = None
         self.predictive = None
+        self._predictive_cls = ClassificationPredictive
 
     def _check_output_dim(self, data_loader):
         """fortuna/prob_model/classification.py:218-242: targets must be integer classes below the output width."""
@@ -65,3 +66,31 @@ class ProbClassifier:
         self.predictive = ClassificationPredictive(self.posterior)
         # calib_data_loader: the default temperature scaler's training is outside the hot path; log_temp stays 0
         return status
+
+    # ------------------------------------------------------------------ state on disk (fortuna/prob_model/base.py:236-261)
+    def load_state(self, checkpoint_path) -> None:
+        """Load posterior samples from a checkpoint directory in the reference's layout (``<dir>/c`` chain state,
+        ``<dir>/<i>`` samples) into the device sample bank; which leaves are sampled comes from the chain file."""
+        import os
+
+        from ..training import checkpoint as ckpt
+
+        d = ckpt.restore_checkpoint(os.path.join(str(checkpoint_path), "c")) if os.path.isdir(os.path.join(str(checkpoint_path), "c")) else None
+        if d is None:
+            raise ValueError(f"No checkpoint was found in `checkpoint_dir={checkpoint_path}`.")
+        enc = d.get("_encoded_which_params")
+        freeze_fun = None
+        if enc is not None:
+            which = {tuple("".join(chr(int(o)) for o in v) for v in path.values()) for path in enc.values()}
+            freeze_fun = lambda path, v: "trainable" if tuple(path) in which else "frozen"  # noqa: E731
+        self.model.to(self.device)
+        bound = BoundModel(self.model, self.device, freeze_fun=freeze_fun)
+        cls = SGHMCPosterior if isinstance(self.posterior_approximator, SGHMCPosteriorApproximator) else CyclicalSGLDPosterior
+        self.posterior = cls(bound, self.prior, self.posterior_approximator, self.rng)
+        self.posterior.load_state(checkpoint_path)
+        self.predictive = self._predictive_cls(self.posterior)
+
+    def save_state(self, checkpoint_path, keep_top_n_checkpoints: int = 1) -> None:
+        if self.posterior is None:
+            raise ValueError("No state available.")
+        return self.posterior.save_state(checkpoint_path, keep_top_n_checkpoints)

@@ -14,7 +14,23 @@ class FitMonitor:
         self.metrics = metrics or ()
 
 
+class FitCheckpointer:
+    """fortuna/prob_model/fit_config/checkpointer.py:6-44, same fields and defaults."""
+
+    def __init__(self, save_checkpoint_dir=None, restore_checkpoint_path=None, start_from_current_state: bool = False,
+                 save_every_n_steps: Optional[int] = None, keep_top_n_checkpoints: Optional[int] = 2,
+                 dump_state: bool = False):
+        self.save_checkpoint_dir = save_checkpoint_dir
+        self.save_every_n_steps = save_every_n_steps
+        self.restore_checkpoint_path = restore_checkpoint_path
+        self.start_from_current_state = start_from_current_state
+        self.keep_top_n_checkpoints = keep_top_n_checkpoints
+        self.dump_state = dump_state
+
+
 class FitConfig:
-    def __init__(self, optimizer: FitOptimizer = None, monitor: FitMonitor = None, **_ignored):
+    def __init__(self, optimizer: FitOptimizer = None, checkpointer: FitCheckpointer = None, monitor: FitMonitor = None,
+                 **_ignored):
         self.optimizer = optimizer or FitOptimizer()
+        self.checkpointer = checkpointer or FitCheckpointer()
         self.monitor = monitor or FitMonitor()

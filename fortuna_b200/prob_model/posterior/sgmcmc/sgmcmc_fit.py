@@ -28,7 +28,10 @@ def batched_log_joint_prob(bound: BoundModel, prior, inputs: torch.Tensor, targe
 
 
 def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader, n_epochs: int, val_data_loader=None,
-               log_likelihood_sum=categorical_log_likelihood_sum) -> Dict[str, np.ndarray]:
+               log_likelihood_sum=categorical_log_likelihood_sum, save_chain=None,
+               save_every_n_steps=None) -> Dict[str, np.ndarray]:
+    """``save_chain(state)`` writes the chain checkpoint (``<save_checkpoint_dir>/c``): every ``save_every_n_steps``
+    steps (fortuna/training/trainer.py:236-247) and once when training ends (:146-150)."""
     state = TrainState.create(params=bound.params, tx=tx)
     n_data = train_data_loader.size
     dev = bound.device
@@ -44,6 +47,8 @@ def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader,
             state = state.apply_gradients(grads=bound.grads)  # fused sampler step, params updated in place
             for cb in callbacks:
                 state = cb.training_step_end(state)
+            if save_chain is not None and save_every_n_steps and state.step % save_every_n_steps == 0:
+                save_chain(state)
             epoch.append(lj.detach())
         losses.append(float(torch.stack(epoch).mean()))
         if val_data_loader is not None:
@@ -52,6 +57,8 @@ def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader,
                                             torch.as_tensor(b, device=dev), val_data_loader.size, log_likelihood_sum)
                      for a, b in val_data_loader]
             val_losses.append(float(torch.stack(v).mean()))
+    if save_chain is not None:
+        save_chain(state)
     status = {"loss": np.array(losses)}
     if val_losses:
         status["val_loss"] = np.array(val_losses)

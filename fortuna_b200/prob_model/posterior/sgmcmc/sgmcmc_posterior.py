@@ -7,13 +7,17 @@ materialises drawn samples: it hands the index vector to the last-layer kernel, 
 ``w[idx[s]]`` directly (the reference goes through ``jax.pure_callback`` to host memory / disk per draw).
 """
 
+import os
 from typing import Optional, Sequence
 
+import numpy as np
 import torch
 
 from .... import ops
+from ....training import checkpoint as ckpt
+from ....utils.flat_tree import FlatTree
 from ....utils.random import RandomNumberGenerator, WithRNG
-from .sgmcmc_posterior_state_repository import SGMCMCPosteriorStateRepository
+from .sgmcmc_posterior_state_repository import SGMCMCPosteriorStateRepository, posterior_state_dict
 
 
 class LastLayerSamples:
@@ -38,6 +42,13 @@ class LastLayerSamples:
         if self._kernel_t_bf16 is None:
             self._kernel_t_bf16 = ops.transpose_w_bf16(self.kernel)
         return self._kernel_t_bf16
+
+
+class _Sample:
+    """(step, params) pair in the shape ``posterior_state_dict`` reads."""
+
+    def __init__(self, step: int, params: FlatTree):
+        self.step, self.params, self.opt_state, self.mutable = step, params, None, None
 
 
 class SGMCMCPosterior(WithRNG):
@@ -71,6 +82,114 @@ class SGMCMCPosterior(WithRNG):
         """idx[s] = choice(split(rng, S)[s], n_samples) for s < S - exactly the draws of
         fortuna/prob_model/predictive/base.py:632 + sgmcmc_posterior.py:51, one kernel, no host round trip."""
         return ops.sample_indices(rng, n_posterior_samples, self.n_samples)
+
+    # ------------------------------------------------------------------ checkpoints (reference layout on disk)
+    STATE_NAME = "SGHMCState"
+
+    def _which_params(self):
+        """Key paths of the sampled leaves when part of the model is frozen, else None (sghmc_posterior.py:137-143)."""
+        bound = getattr(self, "bound", None)
+        if bound is None or len(bound.trainable) == len(list(bound.model.parameters())):
+            return None
+        return tuple(list(p) for p in bound.params.paths)
+
+    def _all_params_tree(self):
+        """Every parameter of the bound module as a nested numpy dict (frozen ones included)."""
+        from .torch_model import _nest, param_paths
+
+        return _nest((pth, p.detach().cpu().numpy().copy()) for pth, p in param_paths(self.bound.model).items())
+
+    def _fit_repository(self, fit_config) -> SGMCMCPosteriorStateRepository:
+        """The repository the sampling callback fills (sghmc_posterior.py:151-156): written through to
+        ``save_checkpoint_dir/<i>`` when a directory is configured."""
+        c = fit_config.checkpointer
+        self.state = SGMCMCPosteriorStateRepository(
+            self.posterior_approximator.n_samples, template=self.bound.params, checkpoint_dir=c.save_checkpoint_dir,
+            which_params=self._which_params(), state_name=self.STATE_NAME)
+        self._last_layer = None
+        return self.state
+
+    def _chain_saver(self, fit_config):
+        c = fit_config.checkpointer
+        if not c.save_checkpoint_dir:
+            return None
+        chain_dir = os.path.join(str(c.save_checkpoint_dir), "c")
+        which = self._which_params()
+
+        def save(state):
+            d = posterior_state_dict(state, self.STATE_NAME, which)
+            if which is not None:  # the chain keeps the whole model: load_state reads the frozen part from it
+                d["params"] = ckpt.to_state_dict(self._all_params_tree())
+            ckpt.save_checkpoint(chain_dir, d, step=state.step, keep=c.keep_top_n_checkpoints, overwrite=True)
+
+        return save
+
+    def _restore_chain_params(self, fit_config) -> None:
+        """``restore_checkpoint_path`` / ``start_from_current_state`` (sgmcmc_posterior.py:82-99): the chain restarts
+        from stored parameters; the sampler state is re-initialised by ``tx.init`` like the reference does when an
+        optimizer is passed to ``init_from_dict`` (posterior/state.py:77-81)."""
+        c = fit_config.checkpointer
+        if c.restore_checkpoint_path is not None:
+            d = ckpt.restore_checkpoint(os.path.join(str(c.restore_checkpoint_path), "c"))
+            if d is None:
+                raise ValueError(f"No checkpoint was found in `restore_checkpoint_path={c.restore_checkpoint_path}`.")
+            self._load_params_tree(d["params"])
+        elif c.start_from_current_state and self.state is not None and self.state.bank is not None:
+            self.bound.load_flat(self.state.get(self.state.size - 1).flat)
+
+    def _load_params_tree(self, tree) -> None:
+        from .torch_model import param_paths
+
+        for pth, p in param_paths(self.bound.model).items():
+            d = tree
+            try:
+                for k in pth:
+                    d = d[k]
+            except (KeyError, TypeError):
+                continue  # sample checkpoints hold the trainable leaves only
+            with torch.no_grad():
+                p.copy_(torch.from_numpy(np.array(d)).to(device=p.device, dtype=p.dtype).view_as(p))
+
+    def load_state(self, checkpoint_dir) -> None:
+        """sgmcmc_posterior.py:61-76: chain state from ``<dir>/c`` (frozen parameters, which leaves are sampled), the
+        samples from ``<dir>/<i>`` - here straight into the device bank."""
+        try:
+            d = ckpt.restore_checkpoint(os.path.join(str(checkpoint_dir), "c"))
+        except ValueError:
+            d = None
+        if d is None:
+            raise ValueError(f"No checkpoint was found in `checkpoint_dir={checkpoint_dir}`.")
+        enc = d.get("_encoded_which_params")
+        which = None
+        if enc is not None:
+            which = tuple(["".join(chr(int(o)) for o in np.asarray(v)) for v in path.values()] for path in enc.values())
+        bound = getattr(self, "bound", None)
+        if bound is not None:
+            self._load_params_tree(d["params"])
+        approx = getattr(self, "posterior_approximator", None)
+        size = approx.n_samples if approx is not None else self.state.size
+        self.state = SGMCMCPosteriorStateRepository(
+            size, template=bound.params if bound is not None else None, checkpoint_dir=checkpoint_dir,
+            which_params=which, state_name=ckpt.decode_name(d),
+            device=bound.device if bound is not None else self.rng._rng.device)
+        self.state.load_checkpoints()
+        self._last_layer = None
+
+    def save_state(self, checkpoint_dir, keep_top_n_checkpoints: int = 1) -> None:
+        """sgmcmc_posterior.py:78-80, plus the chain file ``load_state`` looks for."""
+        which = self._which_params()
+        chain = getattr(self, "chain_state", None)
+        for i in range(self.state.size):
+            step = self.state.steps[i] if self.state.steps[i] is not None else i
+            ckpt.save_checkpoint(os.path.join(str(checkpoint_dir), str(i)),
+                                 posterior_state_dict(_Sample(step, self.state.get(i)), self.STATE_NAME, which),
+                                 step=step, keep=keep_top_n_checkpoints, overwrite=True)
+        d = posterior_state_dict(chain if chain is not None else _Sample(0, self.state.get(self.state.size - 1)),
+                                 self.STATE_NAME, which)
+        if which is not None and getattr(self, "bound", None) is not None:
+            d["params"] = ckpt.to_state_dict(self._all_params_tree())
+        ckpt.save_checkpoint(os.path.join(str(checkpoint_dir), "c"), d, step=d["step"], keep=keep_top_n_checkpoints,
+                             overwrite=True)
 
     def last_layer(self) -> LastLayerSamples:
         if self._last_layer is None:

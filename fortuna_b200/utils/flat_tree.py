@@ -68,7 +68,7 @@ class FlatTree:
         flat = torch.zeros(off, dtype=torch.float32, device=device)
         ft = cls(flat, [p for p, _ in items], shapes, offsets)
         for (_, leaf), view in zip(items, ft.leaf_views()):
-            src = leaf if isinstance(leaf, torch.Tensor) else torch.as_tensor(np.asarray(leaf))
+            src = leaf if isinstance(leaf, torch.Tensor) else torch.from_numpy(np.array(leaf))
             view.copy_(src.to(device=flat.device, dtype=torch.float32))
         return ft
 

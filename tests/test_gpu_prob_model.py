@@ -110,3 +110,85 @@ def test_rejections(cuda):
         _, train, _, train_loader, _ = _setup()
         ProbClassifier(model=MLP(), posterior_approximator=SGHMCPosteriorApproximator(n_samples=10, burnin_length=1000)).train(
             train_loader, fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=2)))
+
+
+@pytest.mark.parametrize("last_layer_only", [True, False])
+def test_checkpoints_in_reference_layout_round_trip(cuda, tmp_path, last_layer_only):
+    """FitCheckpointer(save_checkpoint_dir=...) writes ``<dir>/c/checkpoint_<step>`` (chain) and
+    ``<dir>/<i>/checkpoint_<step>`` (samples) as flax-msgpack state dicts (sghmc_posterior.py:113-156,
+    posterior_multi_state_repository.py:20-29); a fresh ProbClassifier.load_state(dir) predicts the same bits."""
+    from fortuna_b200.prob_model import (
+        FitCheckpointer,
+        FitConfig,
+        FitOptimizer,
+        ProbClassifier,
+        SGHMCPosteriorApproximator,
+    )
+    from fortuna_b200.training import checkpoint as ck
+
+    MLP, train, test, train_loader, test_loader = _setup()
+    torch.manual_seed(0)
+    approx = dict(n_samples=5, n_thinning=4, burnin_length=20, step_schedule=1e-3)
+    freeze = (lambda path, v: "trainable" if "output_subnet" in path else "frozen") if last_layer_only else None
+    d = str(tmp_path / "ckpt")
+    pm = ProbClassifier(model=MLP(), posterior_approximator=SGHMCPosteriorApproximator(**approx), seed=0)
+    pm.train(train_loader, fit_config=FitConfig(
+        optimizer=FitOptimizer(n_epochs=12, freeze_fun=freeze),
+        checkpointer=FitCheckpointer(save_checkpoint_dir=d, save_every_n_steps=10, keep_top_n_checkpoints=2)))
+    assert sorted(os.listdir(d)) == ["0", "1", "2", "3", "4", "c"]
+    assert len(os.listdir(os.path.join(d, "c"))) == 2  # keep_top_n_checkpoints
+    chain = ck.restore_checkpoint(os.path.join(d, "c"))
+    assert ck.decode_name(chain) == "SGHMCState" and chain["step"] == 12 * len(train_loader)
+    assert int(chain["opt_state"]["count"]) == chain["step"] and chain["opt_state"]["rng_key"].dtype == np.uint32
+    s0 = ck.restore_checkpoint(os.path.join(d, "0"))
+    assert s0["step"] == 24  # first stored step: burn-in 20, then every 4th
+    leaves = s0["params"]["model"]["params"]
+    if last_layer_only:
+        assert set(leaves) == {"output_subnet"}  # only the sampled leaves are stored per sample (:139-157)
+        assert len(chain["params"]["model"]["params"]) > 1  # the chain keeps the frozen part
+        assert chain["_encoded_which_params"] is not None
+    np.testing.assert_array_equal(leaves["output_subnet"]["weight"],
+                                  pm.posterior.state.get(0).tree()["model"]["params"]["output_subnet"]["weight"].cpu().numpy())
+    key = pm.rng.get()
+    want = pm.predictive.mean(test_loader.to_inputs_loader(), 16, rng=key)
+    torch.manual_seed(123)  # a differently initialised module: everything must come from the files
+    pm2 = ProbClassifier(model=MLP(), posterior_approximator=SGHMCPosteriorApproximator(**approx), seed=7)
+    pm2.load_state(d)
+    assert pm2.posterior.state.n_filled == 5 and pm2.posterior.bound.is_last_layer_only() == last_layer_only
+    assert torch.equal(pm2.posterior.state.bank, pm.posterior.state.bank)
+    got = pm2.predictive.mean(test_loader.to_inputs_loader(), 16, rng=key)
+    assert torch.equal(got, want)
+    # save_state writes the same layout somewhere else
+    d2 = str(tmp_path / "again")
+    pm2.save_state(d2)
+    assert sorted(os.listdir(d2)) == ["0", "1", "2", "3", "4", "c"]
+    np.testing.assert_array_equal(ck.restore_checkpoint(os.path.join(d2, "3"))["params"]["model"]["params"]["output_subnet"]["bias"],
+                                  ck.restore_checkpoint(os.path.join(d, "3"))["params"]["model"]["params"]["output_subnet"]["bias"])
+    with pytest.raises(ValueError):
+        pm2.load_state(str(tmp_path / "nothing_here"))
+
+
+def test_sample_bank_loads_reference_style_files(cuda, tmp_path):
+    """A directory as Fortuna's SGMCMCPosteriorStateRepository leaves it (flax nn.Dense leaf names, trainable leaves only)
+    -> device bank -> LastLayerSamples for the S-batched contraction."""
+    from fortuna_b200.prob_model.posterior.sgmcmc.sgmcmc_posterior import SGMCMCPosterior
+    from fortuna_b200.prob_model.posterior.sgmcmc.sgmcmc_posterior_state_repository import SGMCMCPosteriorStateRepository
+    from fortuna_b200.training import checkpoint as ck
+    from fortuna_b200.utils.random import RandomNumberGenerator
+
+    r = np.random.default_rng(0)
+    n, D, C = 6, 16, 3
+    ws = r.standard_normal((n, D, C)).astype(np.float32)
+    bs = r.standard_normal((n, C)).astype(np.float32)
+    for i in range(n):
+        state = {"step": 100 + i, "params": {"model": {"params": {"output_subnet": {"last": {"kernel": ws[i], "bias": bs[i]}}}}},
+                 "opt_state": None, "mutable": None, "calib_params": None, "calib_mutable": None,
+                 "encoded_name": ck.to_state_dict(ck.encode_name("SGHMCState"))}
+        ck.save_checkpoint(str(tmp_path / str(i)), state, step=100 + i)
+    repo = SGMCMCPosteriorStateRepository(n, checkpoint_dir=str(tmp_path)).load_checkpoints()
+    assert repo.n_filled == n and repo.steps == [100 + i for i in range(n)]
+    post = SGMCMCPosterior(repo, RandomNumberGenerator(0, cuda))
+    ll = post.last_layer()
+    assert torch.equal(ll.kernel.cpu(), torch.from_numpy(ws)) and torch.equal(ll.bias.cpu(), torch.from_numpy(bs))
+    lazy = SGMCMCPosteriorStateRepository(n, checkpoint_dir=str(tmp_path))
+    assert torch.equal(lazy.get(4).tree()["model"]["params"]["output_subnet"]["last"]["bias"].cpu(), torch.from_numpy(bs[4]))

@@ -119,6 +119,9 @@ SIGNATURES = {
     "fb200_ece_bins": (_i, [_P, _i, _i, _P, _P, _P, _i, _P, _P, _P, _P, _P, _P]),
     "fb200_ece_from_bins": (_i, [_P, _P, _P, _i, _i64, _P, _P]),
     "fb200_quantile_axis0": (_i, [_P, _i, _i64, _P, _i, _P, _P]),
+    "fb200_ksd_imq_workspace_bytes": (_sz, [_i, _i64]),
+    "fb200_ksd_imq": (_i, [_P, _P, _i, _i64, _i64, _f, _f, _P, _sz, _P, _P]),
+    "fb200_ess": (_i, [_P, _i, _i64, _i64, _i, _f, _P, _P]),
     "fb200_reg_sample_targets": (_i, [_P, _P, _P, _i, _i, _i, _i, _P, _P, _P]),
     "fb200_quantile_sorted": (_i, [_P, _i64, _P, _i, _P, _P]),
 }

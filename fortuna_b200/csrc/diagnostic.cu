@@ -1,0 +1,343 @@
+// SG-MCMC diagnostics over the sample bank.
+//
+// Replaces (reference file:line)
+//   fortuna/prob_model/posterior/sgmcmc/sgmcmc_diagnostic.py:16-70    kernel_stein_discrepancy_imq
+//   fortuna/prob_model/posterior/sgmcmc/sgmcmc_diagnostic.py:73-140   effective_sample_size
+//
+// KSD.  The reference evaluates k0(i, j) for all S^2 pairs, each from four length-N dot products
+//   dd = <d, d>, gg = <g_i, g_j>, gid = <g_i, d>, gjd = <g_j, d>,  d = x_i - x_j
+// (vmap over j inside a lax.scan over i).  dd / gg are symmetric and gid(j, i) = -gjd(i, j), so only sample tiles
+// ti <= tj are accumulated: a 64 x 64 pair tile per CTA, 4 x 4 pairs x 4 sums per thread in registers, the samples'
+// columns staged through shared memory 32 at a time; N is split over CTAs (each split writes its own partial, summed
+// in split order - no float atomics, run-to-run identical).  Differences are formed explicitly: the Gram-matrix
+// shortcut (|x_i|^2 + |x_j|^2 - 2 <x_i, x_j> on tensor cores) cancels catastrophically for SG-MCMC samples, which sit
+// close together relative to their norms.  A second kernel turns the sums into k0 in double precision and adds them
+// in the reference's order (row by row).
+//
+// ESS.  jnp.fft-based autocorrelation of the zero-padded, centred chain == the direct lagged products
+//   prod[k] = sum_t x[t] x[t+k]   (padding to >= 2S makes the circular correlation linear),
+// so each column's S lags are computed directly: a CTA holds a [S, COLS] slab of the chain in shared memory, a thread
+// owns one column and 8 consecutive lags (a sliding register window: 2 shared loads per 8 FMAs), then one thread per
+// column walks the lags in order for the unbiased normalisation, the cut at the first auto-correlation below the
+// threshold and the final sum.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace fb200 {
+
+constexpr int KSD_T = 64;   // samples per tile side
+constexpr int KSD_KC = 32;  // columns per shared-memory stage
+constexpr int KSD_THREADS = 256;
+
+struct KsdArgs {
+  const float* x;
+  const float* g;
+  int S;
+  int64_t N, stride;
+  int n_tiles_side, n_splits;
+  int64_t cols_per_split;
+  float* partial;  // [n_splits][S][S][4]  (dd, gg, gid, gjd) for pairs in tiles ti <= tj
+};
+
+__global__ void __launch_bounds__(KSD_THREADS) ksd_pair_sums_kernel(const KsdArgs a) {
+  __shared__ __align__(16) float sx[2][KSD_KC][KSD_T + 4];  // [I | J][column][sample]; rows 16-byte aligned
+  __shared__ __align__(16) float sg[2][KSD_KC][KSD_T + 4];
+  // tile index -> (ti, tj), ti <= tj
+  int t = blockIdx.x, ti = 0;
+  while (t >= a.n_tiles_side - ti) {
+    t -= a.n_tiles_side - ti;
+    ++ti;
+  }
+  const int tj = ti + t;
+  const int split = blockIdx.y;
+  const int64_t n0 = (int64_t)split * a.cols_per_split;
+  const int64_t n1 = min(a.N, n0 + a.cols_per_split);
+  const int tid = threadIdx.x;
+  const int pi = (tid / 16) * 4, pj = (tid % 16) * 4;  // this thread's 4 x 4 pairs inside the tile
+  float dd[4][4], gg[4][4], gid[4][4], gjd[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dd[i][j] = gg[i][j] = gid[i][j] = gjd[i][j] = 0.0f;
+
+  for (int64_t nb = n0; nb < n1; nb += KSD_KC) {
+    // stage [64 samples][32 columns] of both tiles: a warp reads 32 consecutive columns of one sample
+    for (int e = tid; e < KSD_T * KSD_KC; e += KSD_THREADS) {
+      const int s = e / KSD_KC, c = e % KSD_KC;
+      const int64_t col = nb + c;
+      const int si = ti * KSD_T + s, sj = tj * KSD_T + s;
+      const bool okc = col < n1;
+      const bool oki = okc && si < a.S, okj = okc && sj < a.S;
+      sx[0][c][s] = oki ? a.x[(int64_t)si * a.stride + col] : 0.0f;
+      sg[0][c][s] = oki ? a.g[(int64_t)si * a.stride + col] : 0.0f;
+      sx[1][c][s] = okj ? a.x[(int64_t)sj * a.stride + col] : 0.0f;
+      sg[1][c][s] = okj ? a.g[(int64_t)sj * a.stride + col] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int c = 0; c < KSD_KC; ++c) {
+      const float4 xi4 = *reinterpret_cast<const float4*>(&sx[0][c][pi]);
+      const float4 gi4 = *reinterpret_cast<const float4*>(&sg[0][c][pi]);
+      const float4 xj4 = *reinterpret_cast<const float4*>(&sx[1][c][pj]);
+      const float4 gj4 = *reinterpret_cast<const float4*>(&sg[1][c][pj]);
+      const float xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w}, gi[4] = {gi4.x, gi4.y, gi4.z, gi4.w};
+      const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w}, gj[4] = {gj4.x, gj4.y, gj4.z, gj4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float d = xi[i] - xj[j];
+          dd[i][j] = fmaf(d, d, dd[i][j]);
+          gg[i][j] = fmaf(gi[i], gj[j], gg[i][j]);
+          gid[i][j] = fmaf(gi[i], d, gid[i][j]);
+          gjd[i][j] = fmaf(gj[j], d, gjd[i][j]);
+        }
+    }
+    __syncthreads();
+  }
+  float4* out = reinterpret_cast<float4*>(a.partial) + (int64_t)split * a.S * a.S;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int si = ti * KSD_T + pi + i, sj = tj * KSD_T + pj + j;
+      if (si < a.S && sj < a.S) out[(int64_t)si * a.S + sj] = make_float4(dd[i][j], gg[i][j], gid[i][j], gjd[i][j]);
+    }
+}
+
+// k0 of one pair from its four sums, the reference's expression term by term (sgmcmc_diagnostic.py:52-61).
+__device__ __forceinline__ double ksd_k0(double dd, double gg, double gid, double gjd, double c2, double beta,
+                                         double dim) {
+  const double base = c2 + dd;
+  const double b0 = pow(base, beta);  // base^beta; the two lower powers by division
+  const double b1 = b0 / base;
+  const double b2 = b1 / base;
+  double kern = gg * b0;
+  kern += -2.0 * beta * gid * b1;
+  kern += 2.0 * beta * gjd * b1;
+  kern += -2.0 * dim * beta * b1;
+  kern += -4.0 * beta * (beta - 1.0) * b2 * dd;
+  return kern;
+}
+
+// Row i of the pair matrix: sum_j k0(i, j) in double (one CTA per row), then the rows are added in order - the
+// reference's lax.scan over i with jnp.sum over j inside (:65-70) - and ksd = sqrt(total) / S.
+__global__ void __launch_bounds__(256) ksd_row_kernel(const float* __restrict__ partial, int S, int64_t N, int n_splits,
+                                                      float c, float beta, double* __restrict__ row_sums) {
+  __shared__ double red[8];
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4* p = reinterpret_cast<const float4*>(partial);
+  const double c2 = (double)c * (double)c;
+  double acc = 0.0;
+  for (int j = tid; j < S; j += blockDim.x) {
+    // pairs of tiles ti > tj live at the mirrored entry: gid(i,j) = -gjd(j,i), gjd(i,j) = -gid(j,i)
+    const bool mirror = (i / KSD_T) > (j / KSD_T);
+    const int64_t idx = mirror ? (int64_t)j * S + i : (int64_t)i * S + j;
+    double dd = 0., gg = 0., gid = 0., gjd = 0.;
+    for (int s = 0; s < n_splits; ++s) {
+      const float4 v = p[(int64_t)s * S * S + idx];
+      dd += (double)v.x;
+      gg += (double)v.y;
+      gid += (double)v.z;
+      gjd += (double)v.w;
+    }
+    const double a_gid = mirror ? -gjd : gid, a_gjd = mirror ? -gid : gjd;
+    acc += ksd_k0(dd, gg, a_gid, a_gjd, c2, beta, (double)N);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double r = 0.0;
+    for (int w = 0; w < 8; ++w) r += red[w];
+    row_sums[i] = r;
+  }
+}
+
+__global__ void ksd_total_kernel(const double* __restrict__ row_sums, int S, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double t = 0.0;
+  for (int i = 0; i < S; ++i) t += row_sums[i];
+  out[0] = (float)(sqrt(t) / (double)S);
+}
+
+// ------------------------------------------------------------------------------------------------ ESS
+constexpr int ESS_R = 8;  // consecutive lags per thread (sliding register window)
+
+struct EssArgs {
+  const float* x;
+  int S;
+  int64_t N, stride;
+  int use_threshold;
+  float threshold;
+  float* ess;
+};
+
+template <int COLS>
+__global__ void __launch_bounds__(256) ess_kernel(const EssArgs a) {
+  extern __shared__ __align__(16) float ess_smem[];
+  const int S = a.S;
+  float* xs = ess_smem;                 // [S + ESS_R][COLS] centred chain, zero rows past the end
+  float* ac = xs + (size_t)(S + ESS_R) * COLS;  // [max(S, GROUPS)][COLS] lagged products (first: column-sum scratch)
+  constexpr int GROUPS = 256 / COLS;
+  const int col = threadIdx.x % COLS, grp = threadIdx.x / COLS;
+  const int64_t n_slabs = (a.N + COLS - 1) / COLS;
+  for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+    const int64_t n = slab * COLS + col;
+    const bool ok = n < a.N;
+    // load + mean (sgmcmc_diagnostic.py:107-108): each column is summed by its GROUPS threads, then centred
+    float part = 0.0f;
+    for (int t = grp; t < S; t += GROUPS) {
+      const float v = ok ? a.x[(int64_t)t * a.stride + n] : 0.0f;
+      xs[(size_t)t * COLS + col] = v;
+      part += v;
+    }
+    for (int t = S + grp; t < S + ESS_R; t += GROUPS) xs[(size_t)t * COLS + col] = 0.0f;
+    ac[(size_t)grp * COLS + col] = part;
+    __syncthreads();
+    float mean = 0.0f;
+    for (int q = 0; q < GROUPS; ++q) mean += ac[(size_t)q * COLS + col];
+    mean = mean / (float)S;
+    __syncthreads();
+    for (int t = grp; t < S; t += GROUPS) xs[(size_t)t * COLS + col] -= mean;
+    __syncthreads();
+    // lagged products, ESS_R lags at a time: acc[r] = sum_t x[t] * x[t + k0 + r]
+    for (int k0 = grp * ESS_R; k0 < S; k0 += GROUPS * ESS_R) {
+      float acc[ESS_R], win[ESS_R];
+#pragma unroll
+      for (int r = 0; r < ESS_R; ++r) {
+        acc[r] = 0.0f;
+        win[r] = xs[(size_t)(k0 + r) * COLS + col];  // x[0 + k0 + r]; rows past S are zero
+      }
+      const int t_end = S - k0;  // x[t + k0] is zero for t >= S - k0
+      for (int t = 0; t < t_end; ++t) {
+        const float xt = xs[(size_t)t * COLS + col];
+#pragma unroll
+        for (int r = 0; r < ESS_R; ++r) acc[r] = fmaf(xt, win[r], acc[r]);
+#pragma unroll
+        for (int r = 0; r + 1 < ESS_R; ++r) win[r] = win[r + 1];
+        const int nx = t + 1 + k0 + ESS_R - 1;
+        win[ESS_R - 1] = nx < S ? xs[(size_t)nx * COLS + col] : 0.0f;
+      }
+#pragma unroll
+      for (int r = 0; r < ESS_R; ++r)
+        if (k0 + r < S) ac[(size_t)(k0 + r) * COLS + col] = acc[r];
+    }
+    __syncthreads();
+    // one thread per column walks the lags in order (:120-139)
+    if (grp == 0 && ok) {
+      const float fS = (float)S;
+      const float cov0 = ac[col] / fS;  // denominator S - 0
+      float sum = 0.0f;
+      bool open = true;
+      for (int k = 0; k < S; ++k) {
+        const float cov = ac[(size_t)k * COLS + col] / (fS - (float)k);
+        const float rho = cov / cov0;
+        if (a.use_threshold && rho < a.threshold) open = false;  // cumulative mask: this lag and every later one drop out
+        const float w = ((fS - (float)k) / fS) * rho;
+        if (open) sum += w;
+        else if (rho != rho) sum += rho;  // NaN auto-correlations propagate like `weighted * mask` does
+      }
+      a.ess[n] = fS / (-1.0f + 2.0f * sum);
+    }
+    __syncthreads();
+  }
+}
+
+template <int COLS>
+static int launch_ess(const EssArgs& a, cudaStream_t st) {
+  const int groups = 256 / COLS;
+  const size_t smem = ((size_t)(a.S + ESS_R) + (size_t)(a.S > groups ? a.S : groups)) * COLS * sizeof(float);
+  auto kern = ess_kernel<COLS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int64_t slabs = (a.N + COLS - 1) / COLS;
+  int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 8) ctas_per_sm = 8;
+  int64_t grid = slabs < (int64_t)148 * ctas_per_sm ? slabs : (int64_t)148 * ctas_per_sm;
+  kern<<<(unsigned)grid, 256, smem, st>>>(a);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace fb200
+
+using namespace fb200;
+
+static void ksd_plan(int S, int64_t N, int* tiles_side, int* n_pair_tiles, int* n_splits, int64_t* cols_per_split) {
+  const int ts = (S + KSD_T - 1) / KSD_T;
+  const int npt = ts * (ts + 1) / 2;
+  // enough CTAs to fill the GPU a few times over, but at least 256 columns per split
+  int64_t want = (148 * 4 + npt - 1) / npt;
+  int64_t max_splits = (N + 255) / 256;
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  int64_t cps = (N + want - 1) / want;
+  cps = (cps + KSD_KC - 1) / KSD_KC * KSD_KC;
+  const int64_t splits = (N + cps - 1) / cps;
+  *tiles_side = ts;
+  *n_pair_tiles = npt;
+  *n_splits = (int)splits;
+  *cols_per_split = cps;
+}
+
+extern "C" size_t fb200_ksd_imq_workspace_bytes(int S, int64_t N) {
+  if (S <= 0 || N <= 0) return 0;
+  int ts, npt, ns;
+  int64_t cps;
+  ksd_plan(S, N, &ts, &npt, &ns, &cps);
+  return (size_t)ns * (size_t)S * (size_t)S * 4 * sizeof(float) + (size_t)S * sizeof(double);
+}
+
+extern "C" int fb200_ksd_imq(const float* samples, const float* grads, int S, int64_t N, int64_t row_stride, float c,
+                             float beta, void* workspace, size_t workspace_bytes, float* out, void* stream) {
+  if (!samples || !grads || !workspace || !out) return FB200_E_NULL;
+  if (S <= 0 || N <= 0 || row_stride < N) return FB200_E_SHAPE;
+  if (!(c > 0.0f) || !(beta < 0.0f)) return FB200_E_SHAPE;
+  if (S > 4096) return FB200_E_UNSUPPORTED;
+  if (!fb200_aligned16(workspace)) return FB200_E_ALIGN;
+  KsdArgs a{};
+  a.x = samples;
+  a.g = grads;
+  a.S = S;
+  a.N = N;
+  a.stride = row_stride;
+  int npt;
+  ksd_plan(S, N, &a.n_tiles_side, &npt, &a.n_splits, &a.cols_per_split);
+  const size_t partial_bytes = (size_t)a.n_splits * (size_t)S * (size_t)S * 4 * sizeof(float);
+  if (workspace_bytes < partial_bytes + (size_t)S * sizeof(double)) return FB200_E_WORKSPACE;
+  a.partial = reinterpret_cast<float*>(workspace);
+  double* row_sums = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + partial_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  ksd_pair_sums_kernel<<<dim3((unsigned)npt, (unsigned)a.n_splits), KSD_THREADS, 0, st>>>(a);
+  FB200_LAUNCH_CHECK();
+  ksd_row_kernel<<<(unsigned)S, 256, 0, st>>>(a.partial, S, N, a.n_splits, c, beta, row_sums);
+  FB200_LAUNCH_CHECK();
+  ksd_total_kernel<<<1, 32, 0, st>>>(row_sums, S, out);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_ess(const float* samples, int S, int64_t N, int64_t row_stride, int use_threshold,
+                         float threshold, float* ess, void* stream) {
+  if (!samples || !ess) return FB200_E_NULL;
+  if (S <= 0 || N <= 0 || row_stride < N) return FB200_E_SHAPE;
+  EssArgs a{};
+  a.x = samples;
+  a.S = S;
+  a.N = N;
+  a.stride = row_stride;
+  a.use_threshold = use_threshold;
+  a.threshold = threshold;
+  a.ess = ess;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t per_col = ((size_t)(2 * S + ESS_R + 32)) * sizeof(float);
+  const size_t budget = 200 * 1024;
+  if (per_col * 32 <= budget) return launch_ess<32>(a, st);
+  if (per_col * 16 <= budget) return launch_ess<16>(a, st);
+  if (per_col * 8 <= budget) return launch_ess<8>(a, st);
+  return FB200_E_UNSUPPORTED;  // chains longer than ~3000 stored samples
+}

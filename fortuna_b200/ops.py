@@ -497,3 +497,49 @@ def reg_sample_targets(outputs, key, n_target_samples, log_temp=None, want_idx=F
         "fb200_reg_sample_targets",
     )
     return (y, idx) if want_idx else y
+
+
+# ------------------------------------------------------------------------------------------------ diagnostics
+def _row_matrix(t):
+    """[S, N] float32 CUDA matrix whose rows may be strided (a slice of the sample bank): (ptr, S, N, row_stride)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2:
+        raise ValueError("expected a 2-D float32 CUDA tensor [n_samples, n_params]")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    S, N = t.shape
+    stride = t.stride(0) if S > 1 else N
+    if stride < N:
+        t = t.contiguous()
+        stride = N
+    return t, C.c_void_p(t.data_ptr()), int(S), int(N), int(stride)
+
+
+def ksd_imq(samples, grads, c=1.0, beta=-0.5):
+    """float32[1] device tensor: kernel Stein discrepancy with the IMQ kernel over S samples x N parameters."""
+    xs, xp, S, N, sx = _row_matrix(samples)
+    gs, gp, S2, N2, sg = _row_matrix(grads)
+    if (S, N) != (S2, N2):
+        raise ValueError("samples and grads must have the same shape")
+    if sx != sg:
+        xs, gs = xs.contiguous(), gs.contiguous()
+        xp, gp, sx = C.c_void_p(xs.data_ptr()), C.c_void_p(gs.data_ptr()), N
+    nbytes = lib().fb200_ksd_imq_workspace_bytes(S, N)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=xs.device)
+    out = torch.empty(1, dtype=torch.float32, device=xs.device)
+    check(
+        lib().fb200_ksd_imq(xp, gp, S, N, sx, float(c), float(beta), _ptr(ws), nbytes, _ptr(out), _stream()),
+        "fb200_ksd_imq",
+    )
+    return out
+
+
+def ess(samples, filter_threshold=0.0):
+    """float32[N]: per-parameter effective sample size of the chain samples[S, N]."""
+    xs, xp, S, N, sx = _row_matrix(samples)
+    out = torch.empty(N, dtype=torch.float32, device=xs.device)
+    use = filter_threshold is not None
+    check(
+        lib().fb200_ess(xp, S, N, sx, int(use), float(filter_threshold if use else 0.0), _ptr(out), _stream()),
+        "fb200_ess",
+    )
+    return out

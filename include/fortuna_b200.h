@@ -268,6 +268,23 @@ int fb200_quantile_sorted(const float* x_sorted, int64_t n, const float* q, int 
  * (RegressionPredictive.quantile over the target-sample axis, fortuna/prob_model/predictive/regression.py:331-369). */
 int fb200_quantile_axis0(const float* x, int T, int64_t M, const float* q, int nq, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SG-MCMC diagnostics over stored samples (fortuna/prob_model/posterior/sgmcmc/sgmcmc_diagnostic.py).
+ * `samples` / `grads`: float32 [S, N] with `row_stride` floats between rows (rows of the sample bank, or any dense
+ * matrix with row_stride == N); the flat order is the caller's ravel_pytree order.
+ * ---------------------------------------------------------------------------------------------- */
+/* kernel_stein_discrepancy_imq(samples, grads, c, beta) (:16-70): out[1] = sqrt(sum_ij k0(x_i, x_j)) / S with the IMQ
+ * Stein kernel k0; c > 0, beta < 0 (else FB200_E_SHAPE, the reference raises ValueError), S <= 4096.
+ * The four length-N sums per pair are accumulated in float32, k0 and the S^2 sum in float64. */
+size_t fb200_ksd_imq_workspace_bytes(int S, int64_t N);
+int fb200_ksd_imq(const float* samples, const float* grads, int S, int64_t N, int64_t row_stride, float c, float beta,
+                  void* workspace, size_t workspace_bytes, float* out, void* stream);
+/* effective_sample_size(samples, filter_threshold) (:73-140), per parameter: ess[N].  The reference's FFT
+ * auto-correlation of the zero-padded chain equals the direct lagged products computed here; use_threshold = 0 is
+ * filter_threshold=None.  S up to ~3000 (the chain of one 8-column slab must fit shared memory). */
+int fb200_ess(const float* samples, int S, int64_t N, int64_t row_stride, int use_threshold, float threshold,
+              float* ess, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

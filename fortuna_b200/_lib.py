@@ -46,6 +46,10 @@ class SgmcmcHParams(C.Structure):
     ]
 
 
+class JointGrad(C.Structure):
+    _fields_ = [("lik_scale", C.c_float), ("prior_prec", C.c_float)]
+
+
 _P = C.c_void_p
 
 
@@ -102,6 +106,10 @@ SIGNATURES = {
         [_P, _P, _P, _P, _P, _i64, _P, _i, _P, _i64, _P, _P, _P, C.POINTER(SgmcmcHParams), _P],
     ),
     "fb200_sgd_explore_step_f32": (_i, [_P, _P, _P, _P, _i64, C.POINTER(SgmcmcHParams), _P]),
+    "fb200_sgmcmc_step_joint_f32": (_i, [_P, _P, _P, _P, _i64, _P, _i, _P, _i64, _P, _P, _P, C.POINTER(SgmcmcHParams),
+                                         C.POINTER(JointGrad), _P, _P, _P]),
+    "fb200_sgd_explore_joint_workspace_doubles": (_i64, [_i64]),
+    "fb200_sgd_explore_step_joint_f32": (_i, [_P, _P, _P, _i64, C.POINTER(SgmcmcHParams), C.POINTER(JointGrad), _P, _P, _P]),
     "fb200_bank_put_f32": (_i, [_P, _i64, _i, _P, _P]),
     "fb200_last_layer_logits": (_i, [_P, _P, _P, _P, _P, _i, _P, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
     "fb200_transpose_w_bf16": (_i, [_P, _i, _P, _i, _i, _i, _P]),

@@ -73,19 +73,32 @@ __device__ __forceinline__ float sghmc_elem(float g, float& m, float& v, uint32_
   return u * c.sqrt_eps;                                    // :86
 }
 
-template <bool RMS>
+// Gradient prologue of the fused log-joint mode (JOINT): `grad` holds the gradient of the batch log-likelihood SUM and
+// the kernel forms the log-joint gradient of Joint._batched_log_joint_prob (fortuna/prob_model/joint/base.py:54-122,
+// prior/gaussian.py:29-32) itself:  g = (n_data / batch) * grad - prec * theta  - theta is loaded anyway, so the prior
+// costs no HBM traffic and no autograd passes.  The CTA also leaves sum(theta^2) of its tile in sq_part[blockIdx.x]
+// (double), from which the caller gets the log-prior VALUE of the pre-update parameters for the logged loss.
+struct JointCoef {
+  float lik_scale;   // n_data / batch_size
+  float prior_coef;  // -exp(-log_var)
+  double* sq_part;   // [n_tiles] or NULL
+};
+
+template <bool RMS, bool JOINT>
 __global__ void __launch_bounds__(256)
     sgmcmc_step_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ mom,
                        float* __restrict__ pv, float* __restrict__ upd, const fb200_leaf_t* __restrict__ leaves,
                        const uint2* __restrict__ leaf_keys, const fb200_tile_t* __restrict__ tiles,
-                       const StepCoef c) {
+                       const StepCoef c, const JointCoef jc) {
   const fb200_tile_t tile = tiles[blockIdx.x];
   const fb200_leaf_t leaf = leaves[tile.leaf];
   const uint2 key = leaf_keys[tile.leaf];
   const uint32_t n = (uint32_t)leaf.len;
   const uint32_t h = (n >> 1) + (n & 1u);
   const uint32_t i0 = tile.pair_start + threadIdx.x * 4u;
-  if (i0 >= h) return;
+  float sq = 0.0f;  // JOINT: this thread's sum of theta^2
+  if (!JOINT && i0 >= h) return;
+  if (i0 < h) {
   const int64_t e0 = leaf.offset + i0;      // first-half elements e0 .. e0+3
   const int64_t e1 = leaf.offset + h + i0;  // second-half elements e1 .. e1+3
 
@@ -100,8 +113,8 @@ __global__ void __launch_bounds__(256)
 
   const bool vec = ((leaf.offset & 3) == 0) && ((h & 3u) == 0) && ((uint64_t)i0 + h + 3u < (uint64_t)n);
   if (vec) {
-    const float4 g0 = *reinterpret_cast<const float4*>(grad + e0);
-    const float4 g1 = *reinterpret_cast<const float4*>(grad + e1);
+    float4 g0 = *reinterpret_cast<const float4*>(grad + e0);
+    float4 g1 = *reinterpret_cast<const float4*>(grad + e1);
     float4 m0 = *reinterpret_cast<const float4*>(mom + e0);
     float4 m1 = *reinterpret_cast<const float4*>(mom + e1);
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
@@ -113,6 +126,14 @@ __global__ void __launch_bounds__(256)
     if (params) {
       p0 = *reinterpret_cast<const float4*>(params + e0);
       p1 = *reinterpret_cast<const float4*>(params + e1);
+    }
+    if (JOINT) {
+      g0.x = fmaf(jc.lik_scale, g0.x, jc.prior_coef * p0.x); g0.y = fmaf(jc.lik_scale, g0.y, jc.prior_coef * p0.y);
+      g0.z = fmaf(jc.lik_scale, g0.z, jc.prior_coef * p0.z); g0.w = fmaf(jc.lik_scale, g0.w, jc.prior_coef * p0.w);
+      g1.x = fmaf(jc.lik_scale, g1.x, jc.prior_coef * p1.x); g1.y = fmaf(jc.lik_scale, g1.y, jc.prior_coef * p1.y);
+      g1.z = fmaf(jc.lik_scale, g1.z, jc.prior_coef * p1.z); g1.w = fmaf(jc.lik_scale, g1.w, jc.prior_coef * p1.w);
+      sq = ((p0.x * p0.x + p0.y * p0.y) + (p0.z * p0.z + p0.w * p0.w)) +
+           ((p1.x * p1.x + p1.y * p1.y) + (p1.z * p1.z + p1.w * p1.w));
     }
     float4 u0, u1;
     u0.x = sghmc_elem<RMS>(g0.x, m0.x, v0.x, r0[0], c);
@@ -151,7 +172,13 @@ __global__ void __launch_bounds__(256)
         const int64_t e = half ? e1 + k : e0 + k;
         float m = mom[e];
         float v = RMS ? pv[e] : 0.f;
-        const float u = sghmc_elem<RMS>(grad[e], m, v, half ? r1[k] : r0[k], c);
+        float g = grad[e];
+        if (JOINT) {
+          const float p = params[e];
+          g = fmaf(jc.lik_scale, g, jc.prior_coef * p);
+          sq += p * p;
+        }
+        const float u = sghmc_elem<RMS>(g, m, v, half ? r1[k] : r0[k], c);
         mom[e] = m;
         if (RMS) pv[e] = v;
         if (params) params[e] += u;
@@ -159,18 +186,50 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
+  }  // i0 < h
+  if (JOINT && jc.sq_part) {
+    __shared__ float wsum[8];
+    sq = group_sum<32>(sq);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += (double)wsum[w];
+      jc.sq_part[blockIdx.x] = t;
+    }
+  }
+}
+
+// out[0] = sum of partials in index order (deterministic), one warp.
+__global__ void sum_partials_kernel(const double* __restrict__ part, int64_t n, double* __restrict__ out) {
+  double t = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 32) t += part[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (threadIdx.x == 0) out[0] = t;
 }
 
 // Exploration phase of cyclical SGLD: no noise, no momentum (cyclical_sgld_integrator.py:65-84).
-template <bool RMS>
+template <bool RMS, bool JOINT>
 __global__ void __launch_bounds__(256)
     sgd_explore_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ pv,
-                       float* __restrict__ upd, int64_t n, const StepCoef c) {
+                       float* __restrict__ upd, int64_t n, const StepCoef c, const JointCoef jc) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  float sq = 0.0f;
   for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < n; e += stride) {
     if (e + 3 < n) {
       const float4 g = *reinterpret_cast<const float4*>(grad + e);
       float gg[4] = {g.x, g.y, g.z, g.w};
+      if (JOINT) {
+        const float4 p = *reinterpret_cast<const float4*>(params + e);
+        const float pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          gg[k] = fmaf(jc.lik_scale, gg[k], jc.prior_coef * pp[k]);
+          sq += pp[k] * pp[k];
+        }
+      }
       float uu[4];
       float vv[4] = {0.f, 0.f, 0.f, 0.f};
       if (RMS) {
@@ -196,7 +255,12 @@ __global__ void __launch_bounds__(256)
       if (upd) *reinterpret_cast<float4*>(upd + e) = make_float4(uu[0], uu[1], uu[2], uu[3]);
     } else {
       for (int64_t j = e; j < n; ++j) {
-        const float g = grad[j];
+        float g = grad[j];
+        if (JOINT) {
+          const float p = params[j];
+          g = fmaf(jc.lik_scale, g, jc.prior_coef * p);
+          sq += p * p;
+        }
         float u = c.step_size * g;
         if (RMS) {
           const float v = pv[j] * c.alpha + (g * g) * c.one_m_alpha;
@@ -206,6 +270,18 @@ __global__ void __launch_bounds__(256)
         if (params) params[j] += u;
         if (upd) upd[j] = u;
       }
+    }
+  }
+  if (JOINT && jc.sq_part) {
+    __shared__ float wsum[8];
+    sq = group_sum<32>(sq);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += (double)wsum[w];
+      jc.sq_part[blockIdx.x] = t;
     }
   }
 }
@@ -271,13 +347,15 @@ extern "C" int fb200_sgmcmc_build_tiles_host(const fb200_leaf_t* leaves, int n_l
   return 0;
 }
 
-extern "C" int fb200_sgmcmc_step_f32(float* params, const float* grad, float* momentum, float* precond_v,
-                                     float* updates_out, int64_t n, const fb200_leaf_t* leaves, int n_leaves,
-                                     const fb200_tile_t* tiles, int64_t n_tiles, const uint32_t* key_in,
-                                     uint32_t* key_out, uint32_t* leaf_keys_ws, const fb200_sgmcmc_hparams_t* hp,
-                                     void* stream) {
+static int sgmcmc_step_impl(float* params, const float* grad, float* momentum, float* precond_v, float* updates_out,
+                            int64_t n, const fb200_leaf_t* leaves, int n_leaves, const fb200_tile_t* tiles,
+                            int64_t n_tiles, const uint32_t* key_in, uint32_t* key_out, uint32_t* leaf_keys_ws,
+                            const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint, double* sq_ws,
+                            double* sq_out, void* stream) {
   if (!grad || !momentum || !leaves || !tiles || !key_in || !key_out || !leaf_keys_ws || !hp) return FB200_E_NULL;
   if (!params && !updates_out) return FB200_E_NULL;
+  if (joint && !params) return FB200_E_NULL;
+  if (sq_out && !sq_ws) return FB200_E_NULL;
   if (hp->rmsprop && !precond_v) return FB200_E_NULL;
   if (n <= 0 || n_leaves <= 0 || n_tiles <= 0 || n_tiles > 0x7FFFFFFFll || n_leaves >= (1 << 30))
     return FB200_E_SHAPE;
@@ -290,37 +368,105 @@ extern "C" int fb200_sgmcmc_step_f32(float* params, const float* grad, float* mo
   sgmcmc_keys_kernel<<<(n_leaves + 127) / 128, 128, 0, st>>>(key_in, key_out, leaf_keys_ws, (uint32_t)n_leaves);
   FB200_LAUNCH_CHECK();
   const uint2* lk = reinterpret_cast<const uint2*>(leaf_keys_ws);
-  if (hp->rmsprop)
-    sgmcmc_step_kernel<true><<<(unsigned)n_tiles, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out,
-                                                                leaves, lk, tiles, c);
-  else
-    sgmcmc_step_kernel<false><<<(unsigned)n_tiles, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out,
-                                                                 leaves, lk, tiles, c);
+  JointCoef jc{1.0f, 0.0f, nullptr};
+  if (joint) {
+    jc.lik_scale = joint->lik_scale;
+    jc.prior_coef = -joint->prior_prec;
+    jc.sq_part = sq_out ? sq_ws : nullptr;
+  }
+  const unsigned g = (unsigned)n_tiles;
+  if (joint) {
+    if (hp->rmsprop)
+      sgmcmc_step_kernel<true, true><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc);
+    else
+      sgmcmc_step_kernel<false, true><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc);
+  } else {
+    if (hp->rmsprop)
+      sgmcmc_step_kernel<true, false><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc);
+    else
+      sgmcmc_step_kernel<false, false><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc);
+  }
   FB200_LAUNCH_CHECK();
+  if (joint && sq_out) {
+    sum_partials_kernel<<<1, 32, 0, st>>>(sq_ws, n_tiles, sq_out);
+    FB200_LAUNCH_CHECK();
+  }
   return 0;
 }
 
-extern "C" int fb200_sgd_explore_step_f32(float* params, const float* grad, float* precond_v, float* updates_out,
-                                          int64_t n, const fb200_sgmcmc_hparams_t* hp, void* stream) {
+extern "C" int fb200_sgmcmc_step_f32(float* params, const float* grad, float* momentum, float* precond_v,
+                                     float* updates_out, int64_t n, const fb200_leaf_t* leaves, int n_leaves,
+                                     const fb200_tile_t* tiles, int64_t n_tiles, const uint32_t* key_in,
+                                     uint32_t* key_out, uint32_t* leaf_keys_ws, const fb200_sgmcmc_hparams_t* hp,
+                                     void* stream) {
+  return sgmcmc_step_impl(params, grad, momentum, precond_v, updates_out, n, leaves, n_leaves, tiles, n_tiles, key_in,
+                          key_out, leaf_keys_ws, hp, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int fb200_sgmcmc_step_joint_f32(float* params, const float* grad_loglik, float* momentum, float* precond_v,
+                                           int64_t n, const fb200_leaf_t* leaves, int n_leaves,
+                                           const fb200_tile_t* tiles, int64_t n_tiles, const uint32_t* key_in,
+                                           uint32_t* key_out, uint32_t* leaf_keys_ws,
+                                           const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint,
+                                           double* sq_workspace, double* theta_sq_out, void* stream) {
+  if (!joint) return FB200_E_NULL;
+  return sgmcmc_step_impl(params, grad_loglik, momentum, precond_v, nullptr, n, leaves, n_leaves, tiles, n_tiles,
+                          key_in, key_out, leaf_keys_ws, hp, joint, sq_workspace, theta_sq_out, stream);
+}
+
+static int explore_blocks(int64_t n) {
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  return (int)blocks;
+}
+
+extern "C" int64_t fb200_sgd_explore_joint_workspace_doubles(int64_t n) { return n > 0 ? explore_blocks(n) : 0; }
+
+static int sgd_explore_impl(float* params, const float* grad, float* precond_v, float* updates_out, int64_t n,
+                            const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint, double* sq_ws,
+                            double* sq_out, void* stream) {
   if (!grad || !hp) return FB200_E_NULL;
   if (!params && !updates_out) return FB200_E_NULL;
+  if (joint && !params) return FB200_E_NULL;
+  if (sq_out && !sq_ws) return FB200_E_NULL;
   if (hp->rmsprop && !precond_v) return FB200_E_NULL;
   if (n <= 0) return FB200_E_SHAPE;
   if (!fb200_aligned16(grad) || (params && !fb200_aligned16(params)) ||
       (updates_out && !fb200_aligned16(updates_out)) || (hp->rmsprop && !fb200_aligned16(precond_v)))
     return FB200_E_ALIGN;
   const StepCoef c = make_coef(hp);
-  int64_t blocks = (n / 4 + 255) / 256;
-  if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  if (hp->rmsprop)
-    sgd_explore_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grad, precond_v,
-                                                                                 updates_out, n, c);
-  else
-    sgd_explore_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grad, nullptr,
-                                                                                  updates_out, n, c);
+  const unsigned blocks = (unsigned)explore_blocks(n);
+  cudaStream_t st = (cudaStream_t)stream;
+  JointCoef jc{1.0f, 0.0f, nullptr};
+  if (joint) {
+    jc.lik_scale = joint->lik_scale;
+    jc.prior_coef = -joint->prior_prec;
+    jc.sq_part = sq_out ? sq_ws : nullptr;
+    if (hp->rmsprop) sgd_explore_kernel<true, true><<<blocks, 256, 0, st>>>(params, grad, precond_v, updates_out, n, c, jc);
+    else sgd_explore_kernel<false, true><<<blocks, 256, 0, st>>>(params, grad, nullptr, updates_out, n, c, jc);
+  } else {
+    if (hp->rmsprop) sgd_explore_kernel<true, false><<<blocks, 256, 0, st>>>(params, grad, precond_v, updates_out, n, c, jc);
+    else sgd_explore_kernel<false, false><<<blocks, 256, 0, st>>>(params, grad, nullptr, updates_out, n, c, jc);
+  }
   FB200_LAUNCH_CHECK();
+  if (joint && sq_out) {
+    sum_partials_kernel<<<1, 32, 0, st>>>(sq_ws, blocks, sq_out);
+    FB200_LAUNCH_CHECK();
+  }
   return 0;
+}
+
+extern "C" int fb200_sgd_explore_step_f32(float* params, const float* grad, float* precond_v, float* updates_out,
+                                          int64_t n, const fb200_sgmcmc_hparams_t* hp, void* stream) {
+  return sgd_explore_impl(params, grad, precond_v, updates_out, n, hp, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int fb200_sgd_explore_step_joint_f32(float* params, const float* grad_loglik, float* precond_v, int64_t n,
+                                                const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint,
+                                                double* sq_workspace, double* theta_sq_out, void* stream) {
+  if (!joint) return FB200_E_NULL;
+  return sgd_explore_impl(params, grad_loglik, precond_v, nullptr, n, hp, joint, sq_workspace, theta_sq_out, stream);
 }
 
 extern "C" int fb200_bank_put_f32(float* bank, int64_t n, int row, const float* src, void* stream) {

@@ -125,8 +125,41 @@ def make_hparams(step_size, momentum_decay=0.0, rmsprop=False, rms_alpha=0.99, r
     return hp
 
 
-def sgmcmc_step(params, grad, momentum, precond_v, updates_out, leaves, tiles, key_in, key_out, leaf_keys_ws, hp):
+def _joint_args(joint, n_ws, device, ws_cache):
+    """joint = (lik_scale, prior_prec, theta_sq_out or None) -> (struct, workspace ptr, out ptr)."""
+    lik_scale, prior_prec, sq_out = joint
+    jg = _lib.JointGrad()
+    jg.lik_scale = float(np.float32(lik_scale))
+    jg.prior_prec = float(np.float32(prior_prec))
+    ws = None
+    if sq_out is not None:
+        ws = ws_cache.get("sq_ws") if ws_cache is not None else None
+        if ws is None or ws.numel() < n_ws or ws.device != device:
+            ws = torch.empty(n_ws, dtype=torch.float64, device=device)
+            if ws_cache is not None:
+                ws_cache["sq_ws"] = ws
+    return jg, _ptr(ws, torch.float64, True), _ptr(sq_out, torch.float64, True)
+
+
+def sgmcmc_step(params, grad, momentum, precond_v, updates_out, leaves, tiles, key_in, key_out, leaf_keys_ws, hp,
+                joint=None, ws_cache=None):
+    """joint = (n_data / batch_size, prior precision, float64[1] tensor or None): `grad` is the gradient of the batch
+    log-likelihood sum and the kernel forms the log-joint gradient itself (fb200_sgmcmc_step_joint_f32)."""
     n = grad.numel()
+    if joint is not None:
+        if updates_out is not None or params is None:
+            raise ValueError("the fused log-joint mode updates params in place (no `updates` output)")
+        jg, wsp, outp = _joint_args(joint, tiles.shape[0], grad.device, ws_cache)
+        check(
+            lib().fb200_sgmcmc_step_joint_f32(
+                _ptr(params, torch.float32), _ptr(grad, torch.float32), _ptr(momentum, torch.float32),
+                _ptr(precond_v, torch.float32, True), n, _ptr(leaves, torch.int64), leaves.shape[0],
+                _ptr(tiles, torch.int32), tiles.shape[0], _ptr(key_in, KEY_DTYPE), _ptr(key_out, KEY_DTYPE),
+                _ptr(leaf_keys_ws, KEY_DTYPE), C.byref(hp), C.byref(jg), wsp, outp, _stream(),
+            ),
+            "fb200_sgmcmc_step_joint_f32",
+        )
+        return
     check(
         lib().fb200_sgmcmc_step_f32(
             _ptr(params, torch.float32, True),
@@ -149,7 +182,20 @@ def sgmcmc_step(params, grad, momentum, precond_v, updates_out, leaves, tiles, k
     )
 
 
-def sgd_explore_step(params, grad, precond_v, updates_out, hp):
+def sgd_explore_step(params, grad, precond_v, updates_out, hp, joint=None, ws_cache=None):
+    if joint is not None:
+        if updates_out is not None or params is None:
+            raise ValueError("the fused log-joint mode updates params in place (no `updates` output)")
+        n_ws = int(lib().fb200_sgd_explore_joint_workspace_doubles(grad.numel()))
+        jg, wsp, outp = _joint_args(joint, n_ws, grad.device, ws_cache)
+        check(
+            lib().fb200_sgd_explore_step_joint_f32(
+                _ptr(params, torch.float32), _ptr(grad, torch.float32), _ptr(precond_v, torch.float32, True),
+                grad.numel(), C.byref(hp), C.byref(jg), wsp, outp, _stream(),
+            ),
+            "fb200_sgd_explore_step_joint_f32",
+        )
+        return
     check(
         lib().fb200_sgd_explore_step_f32(
             _ptr(params, torch.float32, True),

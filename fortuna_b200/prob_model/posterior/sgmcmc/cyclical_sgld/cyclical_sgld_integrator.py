@@ -54,7 +54,9 @@ def cyclical_sgld_integrator(
     def init_fn(params):
         return OptaxCyclicalSGLDState(sgd_state=((), ()), sgld_state=sgld.init(params))
 
-    def _explore(gradient, state, params):
+    ws = {}
+
+    def _explore(gradient, state, params, joint=None):
         inner = state.sgld_state
         grad = as_flat_tree(gradient, like=inner.momentum)
         hp = ops.make_hparams(
@@ -69,6 +71,8 @@ def cyclical_sgld_integrator(
             v.flat if v is not None else None,
             updates.flat if updates is not None else None,
             hp,
+            joint=joint,
+            ws_cache=ws,
         )
         new_inner = inner._replace(count=inner.count + 1)
         return updates, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=new_inner)
@@ -79,11 +83,11 @@ def cyclical_sgld_integrator(
             return updates, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner)
         return _explore(gradient, state, None)
 
-    def apply_fn(params: FlatTree, gradient, state):
+    def apply_fn(params: FlatTree, gradient, state, joint=None):
         if is_sampling_phase(state.sgld_state.count, cycle_length, exploration_ratio):
-            _, inner = sgld.apply(params, gradient, state.sgld_state)
+            _, inner = sgld.apply(params, gradient, state.sgld_state, joint=joint)
             return params, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner)
-        _, new_state = _explore(gradient, state, params)
+        _, new_state = _explore(gradient, state, params, joint=joint)
         return params, new_state
 
     return GradientTransformation(init_fn, update_fn, apply_fn)

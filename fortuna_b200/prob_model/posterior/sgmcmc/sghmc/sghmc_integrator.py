@@ -42,7 +42,8 @@ class GradientTransformation(NamedTuple):
     apply: Callable  # fused update + apply_updates
 
 
-def _step(gradient, state, params, momentum_decay, momentum_resample_steps, step_schedule, preconditioner, ws):
+def _step(gradient, state, params, momentum_decay, momentum_resample_steps, step_schedule, preconditioner, ws,
+          joint=None):
     grad = as_flat_tree(gradient, like=state.momentum)
     step_size = np.float32(step_schedule(state.count))
     zero_m = momentum_resample_steps is not None and state.count % momentum_resample_steps == 0
@@ -75,6 +76,8 @@ def _step(gradient, state, params, momentum_decay, momentum_resample_steps, step
         new_key,
         key,
         hp,
+        joint=joint,
+        ws_cache=ws,
     )
     new_state = OptaxSGHMCState(
         count=state.count + 1,
@@ -109,11 +112,14 @@ def sghmc_integrator(
             gradient, state, None, momentum_decay, momentum_resample_steps, step_schedule, preconditioner, ws
         )
 
-    def apply_fn(params: FlatTree, gradient, state):
+    def apply_fn(params: FlatTree, gradient, state, joint=None):
+        """``joint=(n_data / batch_size, prior_precision, float64[1] tensor | None)``: ``gradient`` is the gradient of
+        the batch log-likelihood sum; scaling and the Gaussian-prior gradient happen inside the kernel."""
         if not isinstance(params, FlatTree):
             raise TypeError("the fused apply path updates a FlatTree in place")
         _, new_state = _step(
-            gradient, state, params, momentum_decay, momentum_resample_steps, step_schedule, preconditioner, ws
+            gradient, state, params, momentum_decay, momentum_resample_steps, step_schedule, preconditioner, ws,
+            joint=joint,
         )
         return params, new_state
 

@@ -5,7 +5,13 @@ create the state, run ``trainer.train`` with the log-joint as the (ascended) obj
 The host loop is the reference's ``_training_loop`` (fortuna/training/trainer.py:455-532) reduced to what it does for
 SG-MCMC: per batch, value_and_grad of the batched log-joint (``Joint._batched_log_joint_prob``,
 fortuna/prob_model/joint/base.py:54-122: log prior + n_data / batch_size * sum log-likelihood) by autograd, then
-``state.apply_gradients`` - ONE sampler-kernel launch - then the callbacks."""
+``state.apply_gradients`` - ONE sampler-kernel launch - then the callbacks.
+
+With the isotropic Gaussian prior (the only prior of the hot path) autograd sees the batch log-likelihood SUM only: the
+``n_data / batch_size`` scaling and the prior gradient ``-prec * theta`` are formed inside the sampler kernel
+(fb200_sgmcmc_step_joint_f32), which also returns ``sum(theta^2)`` so the logged log-joint value is complete.  The
+unfused route (prior through autograd) stays available as ``fuse_prior=False`` - the two are compared in the tests."""
+import math
 from typing import Dict, List
 
 import numpy as np
@@ -29,12 +35,15 @@ def batched_log_joint_prob(bound: BoundModel, prior, inputs: torch.Tensor, targe
 
 def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader, n_epochs: int, val_data_loader=None,
                log_likelihood_sum=categorical_log_likelihood_sum, save_chain=None,
-               save_every_n_steps=None) -> Dict[str, np.ndarray]:
+               save_every_n_steps=None, fuse_prior: bool = True) -> Dict[str, np.ndarray]:
     """``save_chain(state)`` writes the chain checkpoint (``<save_checkpoint_dir>/c``): every ``save_every_n_steps``
     steps (fortuna/training/trainer.py:236-247) and once when training ends (:146-150)."""
     state = TrainState.create(params=bound.params, tx=tx)
     n_data = train_data_loader.size
     dev = bound.device
+    fuse = fuse_prior and hasattr(prior, "log_var")
+    prec = math.exp(-prior.log_var) if fuse else None
+    lp_const = -0.5 * bound.params.n_params * (math.log(2 * math.pi) + prior.log_var) if fuse else None
     losses, val_losses = [], []
     for _ in range(n_epochs):
         epoch = []
@@ -42,9 +51,17 @@ def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader,
             x = torch.as_tensor(inputs, dtype=torch.float32, device=dev)
             y = torch.as_tensor(targets, device=dev)
             bound.zero_grad()
-            lj = batched_log_joint_prob(bound, prior, x, y, n_data, log_likelihood_sum)
-            lj.backward()                                    # d log-joint / d theta lands in bound.grads (flat)
-            state = state.apply_gradients(grads=bound.grads)  # fused sampler step, params updated in place
+            if fuse:
+                ll = log_likelihood_sum(bound.model(x), y)
+                ll.backward()                                # d sum-log-lik / d theta lands in bound.grads (flat)
+                scale = n_data / x.shape[0]
+                sq = torch.empty(1, dtype=torch.float64, device=dev)
+                state = state.apply_gradients(grads=bound.grads, joint=(scale, prec, sq))
+                lj = (lp_const - 0.5 * prec * sq[0] + scale * ll.detach().double()).float()
+            else:
+                lj = batched_log_joint_prob(bound, prior, x, y, n_data, log_likelihood_sum)
+                lj.backward()                                    # d log-joint / d theta lands in bound.grads (flat)
+                state = state.apply_gradients(grads=bound.grads)  # fused sampler step, params updated in place
             for cb in callbacks:
                 state = cb.training_step_end(state)
             if save_chain is not None and save_every_n_steps and state.step % save_every_n_steps == 0:

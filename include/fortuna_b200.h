@@ -115,6 +115,29 @@ int fb200_sgmcmc_step_f32(float* params, const float* grad, float* momentum, flo
 int fb200_sgd_explore_step_f32(float* params, const float* grad, float* precond_v, float* updates_out,
                                int64_t n, const fb200_sgmcmc_hparams_t* hp, void* stream);
 
+/* Fused log-joint mode of the two step kernels: `grad_loglik` is the gradient of the batch
+ * log-likelihood SUM only, and the kernel forms the gradient of Joint._batched_log_joint_prob
+ * (fortuna/prob_model/joint/base.py:54-122) with an isotropic Gaussian prior (fortuna/prob_model/prior/gaussian.py:29-32)
+ * in its prologue:  g = lik_scale * grad_loglik - prior_prec * theta,  lik_scale = n_data / batch_size,
+ * prior_prec = exp(-log_var).  theta is read by the update anyway, so the prior gradient costs no HBM traffic (autograd
+ * through the prior re-reads every parameter several times per step).  theta_sq_out (optional, double[1]) receives
+ * sum(theta^2) of the PRE-update parameters - the log-prior value -0.5 (prec * sum + n (log 2 pi + log_var)) of the
+ * logged loss; sq_workspace: double[n_tiles] (step) / double[fb200_sgd_explore_joint_workspace_doubles(n)] (explore),
+ * required iff theta_sq_out is given.  params is required (in-place apply mode only). */
+typedef struct {
+  float lik_scale;
+  float prior_prec;
+} fb200_joint_grad_t;
+int fb200_sgmcmc_step_joint_f32(float* params, const float* grad_loglik, float* momentum, float* precond_v, int64_t n,
+                                const fb200_leaf_t* leaves, int n_leaves, const fb200_tile_t* tiles, int64_t n_tiles,
+                                const uint32_t* key_in, uint32_t* key_out, uint32_t* leaf_keys_ws,
+                                const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint, double* sq_workspace,
+                                double* theta_sq_out, void* stream);
+int64_t fb200_sgd_explore_joint_workspace_doubles(int64_t n);
+int fb200_sgd_explore_step_joint_f32(float* params, const float* grad_loglik, float* precond_v, int64_t n,
+                                     const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint,
+                                     double* sq_workspace, double* theta_sq_out, void* stream);
+
 /* dst[row, :] = src[:] : snapshot of the chain's (trainable) parameters into row `row` of the
  * on-device sample bank [n_rows, n] (replaces the device_get + msgpack put of
  * .../sgmcmc/sgmcmc_sampling_callback.py:36-47). */

@@ -192,3 +192,30 @@ def test_sample_bank_loads_reference_style_files(cuda, tmp_path):
     assert torch.equal(ll.kernel.cpu(), torch.from_numpy(ws)) and torch.equal(ll.bias.cpu(), torch.from_numpy(bs))
     lazy = SGMCMCPosteriorStateRepository(n, checkpoint_dir=str(tmp_path))
     assert torch.equal(lazy.get(4).tree()["model"]["params"]["output_subnet"]["last"]["bias"].cpu(), torch.from_numpy(bs[4]))
+
+
+def test_fused_prior_gradient_equals_autograd_route(cuda):
+    """run_sgmcmc(fuse_prior=True) - scaling and Gaussian-prior gradient inside the sampler kernel, log-prior value from
+    the kernel's sum(theta^2) - follows the same chain as the route where autograd differentiates the whole log-joint."""
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+    from fortuna_b200.prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
+    from fortuna_b200.prob_model.posterior.sgmcmc.sgmcmc_fit import run_sgmcmc
+    from fortuna_b200.prob_model.posterior.sgmcmc.torch_model import BoundModel
+    from fortuna_b200.prob_model.prior import IsotropicGaussianPrior
+    from fortuna_b200.data import DataLoader
+
+    MLP, train, _, _, _ = _setup()
+    loader = DataLoader.from_array_data(train, batch_size=100)  # no shuffling: both runs see the same batches
+    out = []
+    for fuse in (True, False):
+        torch.manual_seed(0)
+        bound = BoundModel(MLP(), cuda)
+        tx = sghmc_integrator(0.05, None, ops.PRNGKey(4, cuda), sched.constant_schedule(1e-4), pc.rmsprop_preconditioner())
+        status, state = run_sgmcmc(bound, IsotropicGaussianPrior(log_var=-1.0), tx, [], loader, n_epochs=3, fuse_prior=fuse)
+        out.append((status["loss"], bound.params.flat.clone(), state.opt_state.momentum.flat.clone()))
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-5)
+    scale = float(out[1][1].abs().max())
+    assert float((out[0][1] - out[1][1]).abs().max()) <= 2e-5 * scale  # 15 chaotic-free steps: rounding-level drift only
+    assert float((out[0][2] - out[1][2]).abs().max()) <= 2e-4 * float(out[1][2].abs().max())

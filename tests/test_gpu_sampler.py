@@ -138,3 +138,49 @@ def test_argument_errors(cuda):
         )
     with pytest.raises(ValueError):  # CPU tensors are rejected: no CPU path
         ops.random_bits(torch.zeros(2, dtype=torch.int32), 4)
+
+
+@pytest.mark.parametrize("precond", ["identity", "rmsprop"])
+@pytest.mark.parametrize("kind", ["sghmc", "cyclical"])
+def test_fused_log_joint_gradient_matches_oracle(cuda, precond, kind):
+    """fb200_sgmcmc_step_joint_f32 / fb200_sgd_explore_step_joint_f32: the kernel forms
+    g = (n_data / batch) * grad_loglik - prec * theta itself (joint/base.py:54-122, prior/gaussian.py:29-32) and returns
+    sum(theta^2) of the pre-update parameters; the oracle is stepped with that gradient formed in float32 numpy."""
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+    from fortuna_b200.prob_model.posterior.sgmcmc.cyclical_sgld.cyclical_sgld_integrator import cyclical_sgld_integrator
+    from fortuna_b200.prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    params_np = trees.lenet5_tree(2)
+    lik_scale, prec = np.float32(60000 / 128), np.float32(np.exp(-0.7))
+    o_pre = osamp.Preconditioner(precond)
+    pre = pc.rmsprop_preconditioner() if precond == "rmsprop" else pc.identity_preconditioner()
+    if kind == "sghmc":
+        o_state = osamp.sghmc_init(params_np, oprng.PRNGKey(9), o_pre)
+        o_sched = osamp.constant_schedule(1e-5)
+        tx = sghmc_integrator(0.05, None, ops.PRNGKey(9, cuda), sched.constant_schedule(1e-5), pre)
+    else:
+        o_state = osamp.sghmc_init(params_np, oprng.PRNGKey(9), o_pre)  # the oracle steps the inner SGLD state
+        tx = cyclical_sgld_integrator(ops.PRNGKey(9, cuda), 1e-5, 4, 0.5, pre)  # steps 0,1 explore; 2,3 sample; ...
+    o_params = params_np
+    params = FlatTree.from_tree(params_np, device=cuda)
+    state = tx.init(params)
+    sq = torch.empty(1, dtype=torch.float64, device=cuda)
+    for step in range(6):
+        gl = _grad_tree(o_params, 300 + step)  # stands for the gradient of the batch log-likelihood sum
+        g_joint = osamp.tree_map(lambda a, p: (lik_scale * a - prec * p).astype(np.float32), gl, o_params)
+        want_sq = sum(float(np.sum(p.astype(np.float64) ** 2)) for _, p in osamp.tree_flatten(o_params))
+        if kind == "sghmc":
+            upd, o_state = osamp.sghmc_update(g_joint, o_state, 0.05, o_sched, o_pre)
+        else:
+            upd, o_state = osamp.cyclical_sgld_update(g_joint, o_state, 1e-5, 4, 0.5, o_pre)
+        o_params = osamp.apply_updates(o_params, upd)
+        params, state = tx.apply(params, FlatTree.from_tree(gl, device=cuda), state, joint=(lik_scale, prec, sq))
+        np.testing.assert_allclose(float(sq.item()), want_sq, rtol=1e-6)
+        _assert_tree_close(params.to_numpy_tree(), o_params, f"params step {step}")
+    inner = state.sgld_state if kind == "cyclical" else state
+    o_inner = o_state
+    assert np.array_equal(ops.key_to_host(inner.rng_key), o_inner.rng_key)
+    _assert_tree_close(inner.momentum.to_numpy_tree(), o_inner.momentum, "momentum")

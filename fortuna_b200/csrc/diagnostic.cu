@@ -7,7 +7,7 @@
 // KSD.  The reference evaluates k0(i, j) for all S^2 pairs, each from four length-N dot products
 //   dd = <d, d>, gg = <g_i, g_j>, gid = <g_i, d>, gjd = <g_j, d>,  d = x_i - x_j
 // (vmap over j inside a lax.scan over i).  dd / gg are symmetric and gid(j, i) = -gjd(i, j), so only sample tiles
-// ti <= tj are accumulated: a 64 x 64 pair tile per CTA, 4 x 4 pairs x 4 sums per thread in registers, the samples'
+// ti <= tj are accumulated: a 64 x 64 pair tile per CTA (32 x 32 for chains of <= 32 samples), 4 x 4 (2 x 2) pairs x 4 sums per thread in registers, the samples'
 // columns staged through shared memory 32 at a time; N is split over CTAs (each split writes its own partial, summed
 // in split order - no float atomics, run-to-run identical).  Differences are formed explicitly: the Gram-matrix
 // shortcut (|x_i|^2 + |x_j|^2 - 2 <x_i, x_j> on tensor cores) cancels catastrophically for SG-MCMC samples, which sit
@@ -26,7 +26,6 @@
 
 namespace fb200 {
 
-constexpr int KSD_T = 64;   // samples per tile side
 constexpr int KSD_KC = 32;  // columns per shared-memory stage
 constexpr int KSD_THREADS = 256;
 
@@ -35,12 +34,14 @@ struct KsdArgs {
   const float* g;
   int S;
   int64_t N, stride;
-  int n_tiles_side, n_splits;
+  int tile, n_tiles_side, n_splits;
   int64_t cols_per_split;
   float* partial;  // [n_splits][S][S][4]  (dd, gg, gid, gjd) for pairs in tiles ti <= tj
 };
 
+template <int KSD_T>  // samples per tile side: 64 (4 x 4 pairs per thread) or 32 (2 x 2; chains of <= 32 samples)
 __global__ void __launch_bounds__(KSD_THREADS) ksd_pair_sums_kernel(const KsdArgs a) {
+  constexpr int TP = KSD_T / 16;
   __shared__ __align__(16) float sx[2][KSD_KC][KSD_T + 4];  // [I | J][column][sample]; rows 16-byte aligned
   __shared__ __align__(16) float sg[2][KSD_KC][KSD_T + 4];
   // tile index -> (ti, tj), ti <= tj
@@ -54,12 +55,12 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_pair_sums_kernel(const KsdArg
   const int64_t n0 = (int64_t)split * a.cols_per_split;
   const int64_t n1 = min(a.N, n0 + a.cols_per_split);
   const int tid = threadIdx.x;
-  const int pi = (tid / 16) * 4, pj = (tid % 16) * 4;  // this thread's 4 x 4 pairs inside the tile
-  float dd[4][4], gg[4][4], gid[4][4], gjd[4][4];
+  const int pi = (tid / 16) * TP, pj = (tid % 16) * TP;  // this thread's TP x TP pairs inside the tile
+  float dd[TP][TP], gg[TP][TP], gid[TP][TP], gjd[TP][TP];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TP; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dd[i][j] = gg[i][j] = gid[i][j] = gjd[i][j] = 0.0f;
+    for (int j = 0; j < TP; ++j) dd[i][j] = gg[i][j] = gid[i][j] = gjd[i][j] = 0.0f;
 
   for (int64_t nb = n0; nb < n1; nb += KSD_KC) {
     // stage [64 samples][32 columns] of both tiles: a warp reads 32 consecutive columns of one sample
@@ -77,16 +78,28 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_pair_sums_kernel(const KsdArg
     __syncthreads();
 #pragma unroll 4
     for (int c = 0; c < KSD_KC; ++c) {
-      const float4 xi4 = *reinterpret_cast<const float4*>(&sx[0][c][pi]);
-      const float4 gi4 = *reinterpret_cast<const float4*>(&sg[0][c][pi]);
-      const float4 xj4 = *reinterpret_cast<const float4*>(&sx[1][c][pj]);
-      const float4 gj4 = *reinterpret_cast<const float4*>(&sg[1][c][pj]);
-      const float xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w}, gi[4] = {gi4.x, gi4.y, gi4.z, gi4.w};
-      const float xj[4] = {xj4.x, xj4.y, xj4.z, xj4.w}, gj[4] = {gj4.x, gj4.y, gj4.z, gj4.w};
+      float xi[TP], gi[TP], xj[TP], gj[TP];
+      if constexpr (TP == 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&sx[0][c][pi]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&sg[0][c][pi]);
+        const float4 c4 = *reinterpret_cast<const float4*>(&sx[1][c][pj]);
+        const float4 d4 = *reinterpret_cast<const float4*>(&sg[1][c][pj]);
+        xi[0] = a4.x; xi[1] = a4.y; xi[2] = a4.z; xi[3] = a4.w;
+        gi[0] = b4.x; gi[1] = b4.y; gi[2] = b4.z; gi[3] = b4.w;
+        xj[0] = c4.x; xj[1] = c4.y; xj[2] = c4.z; xj[3] = c4.w;
+        gj[0] = d4.x; gj[1] = d4.y; gj[2] = d4.z; gj[3] = d4.w;
+      } else {
+        const float2 a2 = *reinterpret_cast<const float2*>(&sx[0][c][pi]);
+        const float2 b2 = *reinterpret_cast<const float2*>(&sg[0][c][pi]);
+        const float2 c2 = *reinterpret_cast<const float2*>(&sx[1][c][pj]);
+        const float2 d2 = *reinterpret_cast<const float2*>(&sg[1][c][pj]);
+        xi[0] = a2.x; xi[1] = a2.y; gi[0] = b2.x; gi[1] = b2.y;
+        xj[0] = c2.x; xj[1] = c2.y; gj[0] = d2.x; gj[1] = d2.y;
+      }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TP; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < TP; ++j) {
           const float d = xi[i] - xj[j];
           dd[i][j] = fmaf(d, d, dd[i][j]);
           gg[i][j] = fmaf(gi[i], gj[j], gg[i][j]);
@@ -98,9 +111,9 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_pair_sums_kernel(const KsdArg
   }
   float4* out = reinterpret_cast<float4*>(a.partial) + (int64_t)split * a.S * a.S;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TP; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < TP; ++j) {
       const int si = ti * KSD_T + pi + i, sj = tj * KSD_T + pj + j;
       if (si < a.S && sj < a.S) out[(int64_t)si * a.S + sj] = make_float4(dd[i][j], gg[i][j], gid[i][j], gjd[i][j]);
     }
@@ -124,7 +137,8 @@ __device__ __forceinline__ double ksd_k0(double dd, double gg, double gid, doubl
 // Row i of the pair matrix: sum_j k0(i, j) in double (one CTA per row), then the rows are added in order - the
 // reference's lax.scan over i with jnp.sum over j inside (:65-70) - and ksd = sqrt(total) / S.
 __global__ void __launch_bounds__(256) ksd_row_kernel(const float* __restrict__ partial, int S, int64_t N, int n_splits,
-                                                      float c, float beta, double* __restrict__ row_sums) {
+                                                      int KSD_T, float c, float beta,
+                                                      double* __restrict__ row_sums) {
   __shared__ double red[8];
   const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float4* p = reinterpret_cast<const float4*>(partial);
@@ -182,6 +196,8 @@ __global__ void __launch_bounds__(256) ess_kernel(const EssArgs a) {
   float* xs = ess_smem;                 // [S + ESS_R][COLS] centred chain, zero rows past the end
   float* ac = xs + (size_t)(S + ESS_R) * COLS;  // [max(S, GROUPS)][COLS] lagged products (first: column-sum scratch)
   constexpr int GROUPS = 256 / COLS;
+  float* inv_den = ac + (size_t)(S > GROUPS ? S : GROUPS) * COLS;  // [S] 1 / (S - k)
+  for (int k = threadIdx.x; k < S; k += 256) inv_den[k] = 1.0f / ((float)S - (float)k);
   const int col = threadIdx.x % COLS, grp = threadIdx.x / COLS;
   const int64_t n_slabs = (a.N + COLS - 1) / COLS;
   for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
@@ -230,13 +246,15 @@ __global__ void __launch_bounds__(256) ess_kernel(const EssArgs a) {
     if (grp == 0 && ok) {
       const float fS = (float)S;
       const float cov0 = ac[col] / fS;  // denominator S - 0
+      const float inv_cov0 = 1.0f / cov0;
+      const float inv_S = 1.0f / fS;
       float sum = 0.0f;
       bool open = true;
       for (int k = 0; k < S; ++k) {
-        const float cov = ac[(size_t)k * COLS + col] / (fS - (float)k);
-        const float rho = cov / cov0;
+        const float cov = ac[(size_t)k * COLS + col] * inv_den[k];  // reciprocals: 1-2 ulp from the true quotients
+        const float rho = cov * inv_cov0;
         if (a.use_threshold && rho < a.threshold) open = false;  // cumulative mask: this lag and every later one drop out
-        const float w = ((fS - (float)k) / fS) * rho;
+        const float w = ((fS - (float)k) * inv_S) * rho;
         if (open) sum += w;
         else if (rho != rho) sum += rho;  // NaN auto-correlations propagate like `weighted * mask` does
       }
@@ -249,7 +267,8 @@ __global__ void __launch_bounds__(256) ess_kernel(const EssArgs a) {
 template <int COLS>
 static int launch_ess(const EssArgs& a, cudaStream_t st) {
   const int groups = 256 / COLS;
-  const size_t smem = ((size_t)(a.S + ESS_R) + (size_t)(a.S > groups ? a.S : groups)) * COLS * sizeof(float);
+  const size_t smem =
+      (((size_t)(a.S + ESS_R) + (size_t)(a.S > groups ? a.S : groups)) * COLS + (size_t)a.S) * sizeof(float);
   auto kern = ess_kernel<COLS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -267,7 +286,10 @@ static int launch_ess(const EssArgs& a, cudaStream_t st) {
 
 using namespace fb200;
 
+static int ksd_tile(int S) { return S <= 32 ? 32 : 64; }
+
 static void ksd_plan(int S, int64_t N, int* tiles_side, int* n_pair_tiles, int* n_splits, int64_t* cols_per_split) {
+  const int KSD_T = ksd_tile(S);
   const int ts = (S + KSD_T - 1) / KSD_T;
   const int npt = ts * (ts + 1) / 2;
   // enough CTAs to fill the GPU a few times over, but at least 256 columns per split
@@ -312,9 +334,12 @@ extern "C" int fb200_ksd_imq(const float* samples, const float* grads, int S, in
   a.partial = reinterpret_cast<float*>(workspace);
   double* row_sums = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + partial_bytes);
   cudaStream_t st = (cudaStream_t)stream;
-  ksd_pair_sums_kernel<<<dim3((unsigned)npt, (unsigned)a.n_splits), KSD_THREADS, 0, st>>>(a);
+  a.tile = ksd_tile(S);
+  const dim3 grid((unsigned)npt, (unsigned)a.n_splits);
+  if (a.tile == 32) ksd_pair_sums_kernel<32><<<grid, KSD_THREADS, 0, st>>>(a);
+  else ksd_pair_sums_kernel<64><<<grid, KSD_THREADS, 0, st>>>(a);
   FB200_LAUNCH_CHECK();
-  ksd_row_kernel<<<(unsigned)S, 256, 0, st>>>(a.partial, S, N, a.n_splits, c, beta, row_sums);
+  ksd_row_kernel<<<(unsigned)S, 256, 0, st>>>(a.partial, S, N, a.n_splits, a.tile, c, beta, row_sums);
   FB200_LAUNCH_CHECK();
   ksd_total_kernel<<<1, 32, 0, st>>>(row_sums, S, out);
   FB200_LAUNCH_CHECK();
@@ -335,7 +360,8 @@ extern "C" int fb200_ess(const float* samples, int S, int64_t N, int64_t row_str
   a.ess = ess;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t per_col = ((size_t)(2 * S + ESS_R + 32)) * sizeof(float);
-  const size_t budget = 200 * 1024;
+  const size_t budget = 200 * 1024 - (size_t)S * sizeof(float);
+  if (per_col * 128 <= 110 * 1024 && N >= 128) return launch_ess<128>(a, st);  // short chains: wide slabs
   if (per_col * 32 <= budget) return launch_ess<32>(a, st);
   if (per_col * 16 <= budget) return launch_ess<16>(a, st);
   if (per_col * 8 <= budget) return launch_ess<8>(a, st);

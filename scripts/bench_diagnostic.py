@@ -43,8 +43,8 @@ def main():
         row = {
             "config": name, "S": S, "N": N,
             "ksd_ms": ksd_ms,
-            # per pair and column: 1 subtract + 4 FMA = 9 flop on tiles ti <= tj (64-sample tiles incl. their padding)
-            "ksd_fp32_tflops": 9 * (((S + 63) // 64 * 64) ** 2 / 2) * N / ksd_ms / 1e9,
+            # per pair and column: 1 subtract + 4 FMA = 9 flop
+            "ksd_fp32_tflops": 9 * (S * (S + 1) / 2) * N / ksd_ms / 1e9,  # useful flop: pairs i <= j only
             "ksd_pairs": pairs,
             "ksd_hbm_gbs": 2 * 4 * S * N / ksd_ms / 1e6,
             "ess_ms": ess_ms,

@@ -112,6 +112,9 @@ SIGNATURES = {
     "fb200_sgd_explore_step_joint_f32": (_i, [_P, _P, _P, _i64, C.POINTER(SgmcmcHParams), C.POINTER(JointGrad), _P, _P, _P]),
     "fb200_bank_put_f32": (_i, [_P, _i64, _i, _P, _P]),
     "fb200_last_layer_logits": (_i, [_P, _P, _P, _P, _P, _i, _P, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
+    "fb200_last_layer_ex_workspace_bytes": (_sz, [_i, _i, _i]),
+    "fb200_last_layer_logits_ex": (_i, [_P, _P, _P, _P, _P, _i, _P, _i, _i, _i, _i, _i, _i, _i, _i, _P, _P, _sz, _P]),
+    "fb200_log_prob_from_lse": (_i, [_P, _i, _P, _P, _i, _i, _i, _P, _P, _P]),
     "fb200_transpose_w_bf16": (_i, [_P, _i, _P, _i, _i, _i, _P]),
     "fb200_bma_reduce_cls": (_i, [_P, _i, _P, _P, _i, _i, _i, C.POINTER(ClsOutputs), _P]),
     "fb200_cls_slot_row_floats": (_sz, [_i]),

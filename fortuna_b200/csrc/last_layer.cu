@@ -10,14 +10,18 @@
 // go to the tcgen05 kernel in last_layer_tc.cu.
 #include <cuda_bf16.h>
 
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace fb200 {
 
 int last_layer_tc_supported(int S, int B, int D, int C, int in_dtype, int out_dtype, int w_layout);
+size_t last_layer_tc_lse_workspace_bytes(int S, int B, int C);
 int last_layer_tc_launch(const void* x, const void* w, const float* bias, const float* log_temp,
                          const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
-                         int out_dtype, int c_split, cudaStream_t st);
+                         int out_dtype, int c_split, cudaStream_t st, int epi = 0, float* lse_out = nullptr,
+                         void* lse_ws = nullptr);
 
 int last_layer_tc2_launch(const void* x, const void* w, const float* bias, const float* log_temp,
                           const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
@@ -169,6 +173,61 @@ static int launch_simt(const void* x, const void* w, const float* bias, const fl
   return 0;
 }
 
+
+// Generic (CUDA-core) row pass for shapes outside the tcgen05 epilogue: lse[row] = logsumexp_c z[row, :], and
+// optionally z <- softmax / log_softmax in place.  One warp per row.
+template <typename TO>
+__global__ void __launch_bounds__(256) row_lse_kernel(TO* __restrict__ z, int64_t rows, int C, int epi,
+                                                      float* __restrict__ lse_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    TO* row = z + r * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, (float)row[c]);
+    m = group_max<32>(m);
+    float s = 0.0f;
+    for (int c = lane; c < C; c += 32) s += __expf((float)row[c] - m);
+    s = group_sum<32>(s);
+    const float lse = m + __logf(s);
+    if (lane == 0 && lse_out) lse_out[r] = lse;
+    if (epi == 1) {
+      for (int c = lane; c < C; c += 32) row[c] = (TO)__expf((float)row[c] - lse);
+    } else if (epi == 2) {
+      for (int c = lane; c < C; c += 32) row[c] = (TO)((float)row[c] - lse);
+    }
+  }
+}
+
+// log_prob from logits + their per-row logsumexp: ll[s,b] = z[s,b,y_b] - lse[s,b] (S*B gathers, one 32-byte sector
+// each, instead of a pass over [S,B,C]); out[b] = logsumexp_s ll - log S (predictive/base.py:179-203, 104-128).
+template <typename T>
+__global__ void __launch_bounds__(256) log_prob_from_lse_kernel(const T* __restrict__ z, const float* __restrict__ lse,
+                                                                const int32_t* __restrict__ targets, int S, int B,
+                                                                int C, float* __restrict__ ens,
+                                                                float* __restrict__ log_prob) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int y = targets[b];
+  const bool ok = (unsigned)y < (unsigned)C;
+  float m = -INFINITY;
+  for (int s = 0; s < S; ++s) {
+    const size_t row = (size_t)s * B + b;
+    const float ll = ok ? (float)z[row * C + y] - lse[row] : CUDART_NAN_F;
+    if (ens) ens[row] = ll;
+    m = fmaxf(m, ll);
+  }
+  if (!log_prob) return;
+  float acc = 0.0f;
+  for (int s = 0; s < S; ++s) {
+    const size_t row = (size_t)s * B + b;
+    const float ll = ok ? (float)z[row * C + y] - lse[row] : CUDART_NAN_F;
+    acc += expf(ll - m);
+  }
+  log_prob[b] = ok ? (m + logf(acc)) - logf((float)S) : CUDART_NAN_F;
+}
+
 }  // namespace fb200
 
 using namespace fb200;
@@ -207,6 +266,68 @@ extern "C" int fb200_last_layer_logits(const void* x, const void* w, const float
   if (out_dtype == FB200_F32)
     return launch_simt<__nv_bfloat16, float>(x, w, bias, log_temp, sample_idx, out, S, B, D, C, w_layout, st);
   return launch_simt<__nv_bfloat16, __nv_bfloat16>(x, w, bias, log_temp, sample_idx, out, S, B, D, C, w_layout, st);
+}
+
+extern "C" size_t fb200_last_layer_ex_workspace_bytes(int S, int B, int C) {
+  if (S <= 0 || B <= 0 || C <= 0) return 0;
+  return last_layer_tc_lse_workspace_bytes(S, B, C);
+}
+
+extern "C" int fb200_last_layer_logits_ex(const void* x, const void* w, const float* bias, const float* log_temp,
+                                          const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D,
+                                          int C, int in_dtype, int out_dtype, int w_layout, int epilogue,
+                                          float* lse_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !w || !out) return FB200_E_NULL;
+  if (S <= 0 || B <= 0 || D <= 0 || C <= 0 || n_stored <= 0) return FB200_E_SHAPE;
+  if (!sample_idx && n_stored != S) return FB200_E_SHAPE;
+  if (epilogue < FB200_EPI_LOGITS || epilogue > FB200_EPI_LOG_SOFTMAX) return FB200_E_UNSUPPORTED;
+  if ((in_dtype != FB200_F32 && in_dtype != FB200_BF16) || (out_dtype != FB200_F32 && out_dtype != FB200_BF16))
+    return FB200_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (epilogue == FB200_EPI_LOGITS && !lse_out)
+    return fb200_last_layer_logits(x, w, bias, log_temp, sample_idx, n_stored, out, S, B, D, C, in_dtype, out_dtype,
+                                   w_layout, 0, stream);
+  // fused: the one-CTA tcgen05 kernel's epilogue owns whole rows of a 128 x 256 tile
+  const bool tc = last_layer_tc_supported(S, B, D, C, in_dtype, out_dtype, w_layout) && D >= 256 && C >= 64 && B >= 128;
+  if (tc && (epilogue == FB200_EPI_LOGITS || C <= 256)) {
+    const size_t need = last_layer_tc_lse_workspace_bytes(S, B, C);
+    if (need && (!workspace || workspace_bytes < need)) return FB200_E_WORKSPACE;
+    return last_layer_tc_launch(x, w, bias, log_temp, sample_idx, n_stored, out, S, B, D, C, out_dtype, 0, st, epilogue,
+                                lse_out, need ? workspace : nullptr);
+  }
+  // everything else: logits by the regular dispatch, then one row pass on CUDA cores (in place)
+  const int rc = fb200_last_layer_logits(x, w, bias, log_temp, sample_idx, n_stored, out, S, B, D, C, in_dtype,
+                                         out_dtype, w_layout, 0, stream);
+  if (rc != 0) return rc;
+  const int64_t rows = (int64_t)S * B;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (out_dtype == FB200_F32)
+    row_lse_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<float*>(out), rows, C, epilogue, lse_out);
+  else
+    row_lse_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(out), rows, C,
+                                                                     epilogue, lse_out);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_log_prob_from_lse(const void* logits, int dtype, const float* lse, const int32_t* targets, int S,
+                                       int B, int C, float* ensemble_log_prob, float* log_prob, void* stream) {
+  if (!logits || !lse || !targets) return FB200_E_NULL;
+  if (!ensemble_log_prob && !log_prob) return FB200_E_NULL;
+  if (S <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((B + 255) / 256);
+  if (dtype == FB200_F32)
+    log_prob_from_lse_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(logits), lse, targets, S, B,
+                                                            C, ensemble_log_prob, log_prob);
+  else if (dtype == FB200_BF16)
+    log_prob_from_lse_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits),
+                                                                    lse, targets, S, B, C, ensemble_log_prob, log_prob);
+  else
+    return FB200_E_UNSUPPORTED;
+  FB200_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int fb200_transpose_w_bf16(const void* w, int in_dtype, void* wt, int S, int D, int C, void* stream) {

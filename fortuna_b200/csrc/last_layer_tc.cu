@@ -36,7 +36,12 @@ constexpr uint32_t TC_OUT_BYTES = TC_EPI_WARPS * 2 * TC_OUT_BUF_BYTES;  // doubl
 constexpr size_t TC_SMEM_BYTES =
     1024 /*align slack*/ + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_OUT_BYTES + 256 /*barriers*/;
 
-template <typename TO, bool TMA_OUT>
+// MODE 0: calibrated logits.  MODE 1: logits + per-row (max, sum-exp) of the tile's columns - the logsumexp over classes
+// that log_prob needs, so that it can be formed from S*B gathers instead of a second pass over [S,B,C].  MODE 2: the
+// row is complete inside the tile (C <= 256): two passes over the TMEM accumulator - statistics, then softmax /
+// log_softmax written instead of the logits (prob_output_layer/classification.py:25-28, 54-69).  The exponentials
+// (one MUFU.EX2 per element) hide behind the MMAs of the next tile, which run on the other accumulator stage.
+template <typename TO, bool TMA_OUT, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out, const TcParams p) {
@@ -146,10 +151,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int sw = p.sample_idx ? __ldg(p.sample_idx + tc.s) : tc.s;
       const float* bias_row = p.bias ? p.bias + (size_t)sw * p.C : nullptr;
       TO* out_row = out + ((size_t)tc.s * p.B + (b < p.B ? b : 0)) * p.C;
-#pragma unroll 1
-      for (int chunk = 0; chunk < TC_BLOCK_N / 32; ++chunk) {
-        const int c0 = c_base + chunk * 32;
-        if (c0 >= p.C) break;  // warp-uniform
+      constexpr float kLog2e = 1.4426950408889634f;
+      float run_m = -INFINITY, run_s = 0.0f;  // MODE != 0: running row max / sum exp(v - max) over this tile's columns
+      // accumulator chunk -> calibrated logits v[32] of this thread's row (columns c0 .. c0+31)
+      auto load_chunk = [&](int chunk, int c0, float (&v)[32]) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + (uint32_t)chunk * 32, r);
         // bias for these 32 columns (same addresses in every lane: broadcast loads), overlapped with the TMEM load
@@ -167,85 +172,135 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
         tmem_ld_wait();
-        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           v[j] = __uint_as_float(r[j]);
           if (bias_row) v[j] += bv[j];
           if (p.log_temp) v[j] *= scale;
+          if (MODE != 0 && c0 + 32 > p.C && c0 + j >= p.C) v[j] = -INFINITY;  // columns past C: exp -> 0
         }
+      };
+      auto add_stats = [&](const float (&v)[32]) {
+        float cm = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
+        const float m_new = fmaxf(run_m, cm);
+        const float mb = m_new * kLog2e;
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += exp2f(fmaf(v[j], kLog2e, -mb));
+        run_s = run_s * exp2f(fmaf(run_m, kLog2e, -mb)) + acc;
+        run_m = m_new;
+      };
+      auto store_chunk = [&](int chunk, int c0, float (&v)[32]) {
         if (TMA_OUT) {
-          // stage this warp's 32 rows x 32 columns in shared memory (128-byte rows, SWIZZLE_128B: 16-byte unit q of
-          // row r lives at unit q ^ (r & 7), so the 8 lanes of a store phase hit 8 different bank groups), then one
-          // lane hands the block to the TMA engine: full-line coalesced global writes, off the LSU path.
-          constexpr int per_store = CPS / 32;              // TMEM chunks per store: 1 (f32) or 2 (bf16)
-          const int sub = chunk % per_store;
-          unsigned char* buf = my_stage + (size_t)(store_it & 1u) * TC_OUT_BUF_BYTES;
-          if (sub == 0) {
-            if (lane == 0) bulk_wait_group_read<1>();      // the store that last read `buf` has drained it
-            __syncwarp();
-          }
-          unsigned char* rowp = buf + lane * 128;
-          if (sizeof(TO) == 4) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 4)) =
-                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 pk;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2);
-              pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(rowp + (((sub * 4 + q) ^ (lane & 7)) << 4)) = pk;
+            // stage this warp's 32 rows x 32 columns in shared memory (128-byte rows, SWIZZLE_128B: 16-byte unit q of
+            // row r lives at unit q ^ (r & 7), so the 8 lanes of a store phase hit 8 different bank groups), then one
+            // lane hands the block to the TMA engine: full-line coalesced global writes, off the LSU path.
+            constexpr int per_store = CPS / 32;              // TMEM chunks per store: 1 (f32) or 2 (bf16)
+            const int sub = chunk % per_store;
+            unsigned char* buf = my_stage + (size_t)(store_it & 1u) * TC_OUT_BUF_BYTES;
+            if (sub == 0) {
+              if (lane == 0) bulk_wait_group_read<1>();      // the store that last read `buf` has drained it
+              __syncwarp();
             }
-          }
-          const bool last_sub = (sub == per_store - 1) || (c0 + 32 >= p.C) || (chunk == TC_BLOCK_N / 32 - 1);
-          if (last_sub) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&tmap_out, buf, c0 - sub * 32, row0, tc.s);
-              bulk_commit_group();
-            }
-            ++store_it;
-          }
-        } else if (b < p.B) {
-          if (p.c_split) {
-            // flattened N: scatter column n = (sample, class) to out[sample, b, class]; for a fixed column the 32 lanes
-            // (consecutive b) write addresses c_split elements apart, neighbouring columns fill the gaps
-            int sn = c0 / p.c_split, cn = c0 - sn * p.c_split;
-            TO* o = out + ((size_t)sn * p.B + b) * p.c_split;
-            const size_t sample_stride = (size_t)p.B * p.c_split;
+            unsigned char* rowp = buf + lane * 128;
+            if (sizeof(TO) == 4) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (c0 + j < p.C) {
-                if (sizeof(TO) == 4) reinterpret_cast<float*>(o)[cn] = v[j];
-                else reinterpret_cast<__nv_bfloat16*>(o)[cn] = __float2bfloat16_rn(v[j]);
-              }
-              if (++cn == p.c_split) {
-                cn = 0;
-                o += sample_stride;
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 4)) =
+                    make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(rowp + (((sub * 4 + q) ^ (lane & 7)) << 4)) = pk;
               }
             }
-          } else if (sizeof(TO) == 4) {
-            float* o = reinterpret_cast<float*>(out_row) + c0;
+            const bool last_sub = (sub == per_store - 1) || (c0 + 32 >= p.C) || (chunk == TC_BLOCK_N / 32 - 1);
+            if (last_sub) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tmap_out, buf, c0 - sub * 32, row0, tc.s);
+                bulk_commit_group();
+              }
+              ++store_it;
+            }
+          } else if (b < p.B) {
+            if (p.c_split) {
+              // flattened N: scatter column n = (sample, class) to out[sample, b, class]; for a fixed column the 32 lanes
+              // (consecutive b) write addresses c_split elements apart, neighbouring columns fill the gaps
+              int sn = c0 / p.c_split, cn = c0 - sn * p.c_split;
+              TO* o = out + ((size_t)sn * p.B + b) * p.c_split;
+              const size_t sample_stride = (size_t)p.B * p.c_split;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.C) o[j] = v[j];
+              for (int j = 0; j < 32; ++j) {
+                if (c0 + j < p.C) {
+                  if (sizeof(TO) == 4) reinterpret_cast<float*>(o)[cn] = v[j];
+                  else reinterpret_cast<__nv_bfloat16*>(o)[cn] = __float2bfloat16_rn(v[j]);
+                }
+                if (++cn == p.c_split) {
+                  cn = 0;
+                  o += sample_stride;
+                }
+              }
+            } else if (sizeof(TO) == 4) {
+              float* o = reinterpret_cast<float*>(out_row) + c0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < p.C) o[j] = v[j];
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_row) + c0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < p.C) o[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+            };
+      float lse = 0.0f;
+      if (MODE == 2) {
+#pragma unroll 1
+        for (int chunk = 0; chunk < TC_BLOCK_N / 32; ++chunk) {
+          const int c0 = c_base + chunk * 32;
+          if (c0 >= p.C) break;  // warp-uniform
+          float v[32];
+          load_chunk(chunk, c0, v);
+          add_stats(v);
+        }
+        lse = run_m + __logf(run_s);
+      }
+#pragma unroll 1
+      for (int chunk = 0; chunk < TC_BLOCK_N / 32; ++chunk) {
+        const int c0 = c_base + chunk * 32;
+        if (c0 >= p.C) break;  // warp-uniform
+        float v[32];
+        load_chunk(chunk, c0, v);
+        if (MODE == 1) add_stats(v);
+        if (MODE == 2) {
+          if (p.epi == 1) {
+            const float lb = lse * kLog2e;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = exp2f(fmaf(v[j], kLog2e, -lb));
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_row) + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.C) o[j] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = v[j] - lse;
           }
         }
+        store_chunk(chunk, c0, v);
+      }
+      if (MODE != 0 && b < p.B) {
+        const size_t row = (size_t)tc.s * p.B + b;
+        if (p.lse_part) p.lse_part[row * p.n_blocks + tc.n_blk] = make_float2(run_m, run_s);
+        else if (p.lse_out) p.lse_out[row] = run_m + __logf(run_s);
       }
       tc_fence_before();
       __syncwarp();
@@ -275,9 +330,32 @@ int last_layer_tc_supported(int S, int B, int D, int C, int in_dtype, int out_dt
 
 // c_split > 0: the caller folded the sample axis into the column axis (S = 1, C = samples * c_split, w viewed as
 // [1, C, D], bias as [1, C]); the epilogue scatters column n to out[n / c_split, b, n % c_split].
+// [rows, n_blocks] (max, sum exp) partials of the column tiles -> lse[rows] = logsumexp over the whole row
+__global__ void __launch_bounds__(256) lse_combine_kernel(const float2* __restrict__ part, int64_t rows, int n_blocks,
+                                                          float* __restrict__ lse) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
+    float m = -INFINITY;
+    for (int n = 0; n < n_blocks; ++n) m = fmaxf(m, part[r * n_blocks + n].x);
+    float s = 0.0f;
+    for (int n = 0; n < n_blocks; ++n) {
+      const float2 q = part[r * n_blocks + n];
+      s += q.y * __expf(q.x - m);
+    }
+    lse[r] = m + __logf(s);
+  }
+}
+
+size_t last_layer_tc_lse_workspace_bytes(int S, int B, int C) {
+  const int n_blocks = (C + TC_BLOCK_N - 1) / TC_BLOCK_N;
+  return n_blocks > 1 ? (size_t)S * (size_t)B * (size_t)n_blocks * sizeof(float2) : 0;
+}
+
+// epi: 0 logits / 1 softmax / 2 log_softmax (1, 2: C <= 256); lse_out: optional [S, B]; lse_ws: workspace of
+// last_layer_tc_lse_workspace_bytes when C > 256 and lse_out is given.
 int last_layer_tc_launch(const void* x, const void* w, const float* bias, const float* log_temp,
                          const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
-                         int out_dtype, int c_split, cudaStream_t st) {
+                         int out_dtype, int c_split, cudaStream_t st, int epi, float* lse_out, void* lse_ws) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return FB200_E_UNSUPPORTED;
   if (!fb200_aligned16(x) || !fb200_aligned16(w)) return FB200_E_ALIGN;
@@ -332,6 +410,19 @@ int last_layer_tc_launch(const void* x, const void* w, const float* bias, const 
   const long long total = (long long)p.m_blocks * p.n_blocks * S;
   if (total > 0x7FFFFFFFll) return FB200_E_UNSUPPORTED;
   p.total_tiles = (int)total;
+  p.epi = epi;
+  int mode = 0;
+  if (epi != 0 || lse_out) {
+    if (c_split != 0) return FB200_E_UNSUPPORTED;
+    if (epi != 0 && p.n_blocks != 1) return FB200_E_UNSUPPORTED;
+    mode = epi != 0 ? 2 : 1;
+    if (p.n_blocks == 1) {
+      p.lse_out = lse_out;
+    } else {
+      if (!lse_ws) return FB200_E_WORKSPACE;
+      p.lse_part = reinterpret_cast<float2*>(lse_ws);
+    }
+  }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = sms;
@@ -343,13 +434,29 @@ int last_layer_tc_launch(const void* x, const void* w, const float* bias, const 
     return 0;
   };
   int rc;
-  if (out_dtype == FB200_F32)
-    rc = tma_out ? launch(last_layer_tc_kernel<float, true>) : launch(last_layer_tc_kernel<float, false>);
-  else
-    rc = tma_out ? launch(last_layer_tc_kernel<__nv_bfloat16, true>)
-                 : launch(last_layer_tc_kernel<__nv_bfloat16, false>);
+#define FB200_TC_DISPATCH(M)                                                                                   \
+  if (out_dtype == FB200_F32)                                                                                  \
+    rc = tma_out ? launch(last_layer_tc_kernel<float, true, M>) : launch(last_layer_tc_kernel<float, false, M>); \
+  else                                                                                                         \
+    rc = tma_out ? launch(last_layer_tc_kernel<__nv_bfloat16, true, M>)                                        \
+                 : launch(last_layer_tc_kernel<__nv_bfloat16, false, M>);
+  if (mode == 0) {
+    FB200_TC_DISPATCH(0)
+  } else if (mode == 1) {
+    FB200_TC_DISPATCH(1)
+  } else {
+    FB200_TC_DISPATCH(2)
+  }
+#undef FB200_TC_DISPATCH
   if (rc != 0) return rc;
   FB200_LAUNCH_CHECK();
+  if (p.lse_part) {
+    const int64_t rows = (int64_t)S * B;
+    int64_t blocks = (rows + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    lse_combine_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.lse_part, rows, p.n_blocks, lse_out);
+    FB200_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -111,6 +111,10 @@ struct TcParams {
   int m_blocks, n_blocks, k_blocks;
   int total_tiles;
   int c_split;  // flattened mode (S folded into the N axis): column n is (sample n / c_split, class n % c_split); 0 = off
+  // row statistics / normalising epilogue (one-CTA kernel only)
+  int epi;           // 0 logits, 1 softmax, 2 log_softmax (1/2 need the row inside one tile: n_blocks == 1)
+  float* lse_out;    // [S, B] logsumexp_c of the calibrated logits, or null            (n_blocks == 1)
+  float2* lse_part;  // [S, B, n_blocks] (row max, sum exp(v - max)) per column tile     (n_blocks  > 1)
 };
 
 struct TileCoord {

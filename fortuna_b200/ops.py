@@ -255,6 +255,51 @@ def last_layer_logits(x, w, bias=None, log_temp=None, out_dtype=torch.float32, w
     return out
 
 
+EPI_LOGITS, EPI_SOFTMAX, EPI_LOG_SOFTMAX = 0, 1, 2
+
+
+def last_layer_logits_ex(x, w, bias=None, log_temp=None, out_dtype=torch.float32, w_layout=W_SDC, epilogue=EPI_LOGITS,
+                         want_lse=False, sample_idx=None):
+    """The last-layer contraction with the softmax / log-softmax epilogue and / or the per-row logsumexp over classes
+    (fb200_last_layer_logits_ex).  Returns out [S,B,C], or (out, lse [S,B]) with want_lse."""
+    if x.dtype != w.dtype:
+        raise ValueError("x and w must share a dtype")
+    S = w.shape[0] if sample_idx is None else sample_idx.numel()
+    B, D = x.shape
+    Cn = w.shape[2] if w_layout == W_SDC else w.shape[1]
+    if (w.shape[1] if w_layout == W_SDC else w.shape[2]) != D:
+        raise ValueError("feature dimension mismatch between x and w")
+    out = torch.empty((S, B, Cn), dtype=out_dtype, device=x.device)
+    lse = torch.empty((S, B), dtype=torch.float32, device=x.device) if want_lse else None
+    nbytes = int(lib().fb200_last_layer_ex_workspace_bytes(S, B, Cn)) if want_lse else 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
+    check(
+        lib().fb200_last_layer_logits_ex(
+            _ptr(x, (torch.float32, torch.bfloat16)), _ptr(w), _ptr(bias, torch.float32, True),
+            _ptr(log_temp, torch.float32, True), _ptr(sample_idx, torch.int32, True), w.shape[0],
+            _ptr(out, (torch.float32, torch.bfloat16)), S, B, D, Cn, _DT[x.dtype], _DT[out.dtype], w_layout,
+            int(epilogue), _ptr(lse, torch.float32, True), _ptr(ws, None, True), nbytes, _stream(),
+        ),
+        "fb200_last_layer_logits_ex",
+    )
+    return (out, lse) if want_lse else out
+
+
+def log_prob_from_lse(logits, lse, targets, want_ensemble=False):
+    """log_prob [B] (and ensemble_log_prob [S,B]) from calibrated logits [S,B,C] and their row logsumexp [S,B]."""
+    S, B, Cn = logits.shape
+    lp = torch.empty(B, dtype=torch.float32, device=logits.device)
+    ens = torch.empty((S, B), dtype=torch.float32, device=logits.device) if want_ensemble else None
+    check(
+        lib().fb200_log_prob_from_lse(
+            _ptr(logits, (torch.float32, torch.bfloat16)), _DT[logits.dtype], _ptr(lse, torch.float32),
+            _ptr(targets, torch.int32), S, B, Cn, _ptr(ens, torch.float32, True), _ptr(lp), _stream(),
+        ),
+        "fb200_log_prob_from_lse",
+    )
+    return (lp, ens) if want_ensemble else lp
+
+
 def transpose_w_bf16(w):
     S, D, Cn = w.shape
     wt = torch.empty((S, Cn, D), dtype=torch.bfloat16, device=w.device)

@@ -165,6 +165,32 @@ int fb200_bank_put_f32(float* bank, int64_t n, int row, const float* src, void* 
 int fb200_last_layer_logits(const void* x, const void* w, const float* bias, const float* log_temp,
                             const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
                             int in_dtype, int out_dtype, int w_layout, int path, void* stream);
+/* The same contraction with the softmax / log-softmax of ClassificationProbOutputLayer fused behind it
+ * (fortuna/prob_output_layer/classification.py:25-28 log_prob = logits[y] - logsumexp, :54-69 mean = softmax):
+ *   epilogue = FB200_EPI_LOGITS       out = calibrated logits (as above)
+ *            = FB200_EPI_SOFTMAX      out = softmax_c(logits)
+ *            = FB200_EPI_LOG_SOFTMAX  out = logits - logsumexp_c(logits)
+ *   lse_out (optional, float32 [S,B]) = logsumexp_c of the calibrated logits of every row.
+ * On the tcgen05 path (bf16, K-major W, D >= 256, C >= 64, B >= 128) the row statistics are taken in the kernel's
+ * epilogue straight from the TMEM accumulators: for C <= 256 a row is complete inside one 128 x 256 tile (two passes
+ * over TMEM: statistics, then the normalised values are what gets stored); for wider layers (epilogue must be
+ * FB200_EPI_LOGITS) each column tile leaves a (max, sum-exp) pair per row in `workspace`
+ * (fb200_last_layer_ex_workspace_bytes) and a small kernel merges them into lse_out.  With lse_out,
+ * fb200_log_prob_from_lse turns predictive.log_prob into S*B gathers instead of a second pass over [S,B,C].
+ * Shapes outside the tcgen05 path run the regular dispatch followed by one in-place row pass on CUDA cores. */
+#define FB200_EPI_LOGITS 0
+#define FB200_EPI_SOFTMAX 1
+#define FB200_EPI_LOG_SOFTMAX 2
+size_t fb200_last_layer_ex_workspace_bytes(int S, int B, int C);
+int fb200_last_layer_logits_ex(const void* x, const void* w, const float* bias, const float* log_temp,
+                               const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
+                               int in_dtype, int out_dtype, int w_layout, int epilogue, float* lse_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+/* ll[s,b] = logits[s,b,targets[b]] - lse[s,b];  ensemble_log_prob[S,B] = ll (optional);
+ * log_prob[B] = logsumexp_s ll - log S (optional)  (fortuna/prob_model/predictive/base.py:104-128, 179-203).
+ * logits: [S,B,C] calibrated logits (dtype FB200_F32 / FB200_BF16), lse: float32 [S,B] from the call above. */
+int fb200_log_prob_from_lse(const void* logits, int dtype, const float* lse, const int32_t* targets, int S, int B,
+                            int C, float* ensemble_log_prob, float* log_prob, void* stream);
 /* wt[s,c,d] (bf16) = w[s,d,c] (float32 or bf16 per in_dtype). */
 int fb200_transpose_w_bf16(const void* w, int in_dtype, void* wt, int S, int D, int C, void* stream);
 

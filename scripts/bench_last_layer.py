@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--out", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--no-cublas", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 2 one-CTA tcgen05 kernel, 3 CTA-pair (cta_group::2) kernel")
+    ap.add_argument("--ex", action="store_true", help="also time the row-statistics / softmax epilogue (fb200_last_layer_logits_ex) "
+                    "and log_prob from logits + lse against the single-pass reduction kernel")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -59,6 +61,21 @@ def main():
         ms2 = timeit(lambda: torch.matmul(x.unsqueeze(0), wT, out=o2), a.iters)
         res["cublas_bf16_out_ms"] = ms2
         res["cublas_tflops"] = flops / ms2 / 1e9
+    if a.ex:
+        def ex(epi, lse):
+            return timeit(lambda: ops.last_layer_logits_ex(x, wt, bias, lt, out_dtype=odt, w_layout=ops.W_SCD, epilogue=epi,
+                                                           want_lse=lse), a.iters)
+
+        ms1 = timeit(lambda: ops.last_layer_logits(x, wt, bias, lt, w_layout=ops.W_SCD, path=2, out=out), a.iters)
+        res["one_cta_logits_ms"] = ms1
+        res["one_cta_logits_plus_lse_ms"] = ex(ops.EPI_LOGITS, True)
+        if a.C <= 256:
+            res["softmax_epilogue_ms"] = ex(ops.EPI_SOFTMAX, False)
+            res["log_softmax_epilogue_ms"] = ex(ops.EPI_LOG_SOFTMAX, True)
+        z, lse = ops.last_layer_logits_ex(x, wt, bias, lt, out_dtype=odt, w_layout=ops.W_SCD, want_lse=True)
+        t = torch.randint(0, a.C, (a.B,), device=dev, dtype=torch.int32, generator=g)
+        res["log_prob_from_lse_ms"] = timeit(lambda: ops.log_prob_from_lse(z, lse, t), a.iters)
+        res["log_prob_single_pass_reduce_ms"] = timeit(lambda: ops.bma_reduce_cls(z, ("log_prob",), targets=t), a.iters)
     print(json.dumps(res))
 
 

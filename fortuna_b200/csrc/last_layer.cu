@@ -311,6 +311,25 @@ extern "C" int fb200_last_layer_logits_ex(const void* x, const void* w, const fl
   return 0;
 }
 
+extern "C" int fb200_softmax_rows(void* z, int dtype, int64_t rows, int C, int epilogue, float* lse_out, void* stream) {
+  if (!z) return FB200_E_NULL;
+  if (rows <= 0 || C <= 0) return FB200_E_SHAPE;
+  if (epilogue < FB200_EPI_LOGITS || epilogue > FB200_EPI_LOG_SOFTMAX) return FB200_E_UNSUPPORTED;
+  if (epilogue == FB200_EPI_LOGITS && !lse_out) return FB200_E_NULL;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FB200_F32)
+    row_lse_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<float*>(z), rows, C, epilogue, lse_out);
+  else if (dtype == FB200_BF16)
+    row_lse_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(z), rows, C,
+                                                                     epilogue, lse_out);
+  else
+    return FB200_E_UNSUPPORTED;
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int fb200_log_prob_from_lse(const void* logits, int dtype, const float* lse, const int32_t* targets, int S,
                                        int B, int C, float* ensemble_log_prob, float* log_prob, void* stream) {
   if (!logits || !lse || !targets) return FB200_E_NULL;

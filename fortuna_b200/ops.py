@@ -634,3 +634,48 @@ def ess(samples, filter_threshold=0.0):
         "fb200_ess",
     )
     return out
+
+
+# ------------------------------------------------------------------------------------------------ conformal Bayes
+def conformal_bayes_sets(ell_train, lsm_test, error, want_counts=False, want_ess=False):
+    """ell_train [S, n_train], lsm_test [S, n_test, C] (float32) -> dict(region uint8 [n_test, C], sizes int32 [n_test],
+    optionally rank_counts int32 [n_test, C] and ess float32 [n_test, C])."""
+    S, n_train = ell_train.shape
+    S2, n_test, Cn = lsm_test.shape
+    if S != S2:
+        raise ValueError("training and test log-probabilities must come from the same posterior draws")
+    dev = ell_train.device
+    thr = float(np.float32(error * (n_train + 1)))
+    nbytes = int(lib().fb200_conformal_bayes_workspace_bytes(S, n_test, Cn))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    region = torch.empty((n_test, Cn), dtype=torch.uint8, device=dev)
+    sizes = torch.empty(n_test, dtype=torch.int32, device=dev)
+    counts = torch.empty((n_test, Cn), dtype=torch.int32, device=dev) if want_counts else None
+    ess_t = torch.empty((n_test, Cn), dtype=torch.float32, device=dev) if want_ess else None
+    check(
+        lib().fb200_conformal_bayes_sets(
+            _ptr(ell_train, torch.float32), _ptr(lsm_test, torch.float32), S, n_train, n_test, Cn, thr, _ptr(ws), nbytes,
+            _ptr(region), _ptr(sizes), _ptr(counts, torch.int32, True), _ptr(ess_t, torch.float32, True), _stream(),
+        ),
+        "fb200_conformal_bayes_sets",
+    )
+    out = {"region": region, "sizes": sizes}
+    if want_counts:
+        out["rank_counts"] = counts
+    if want_ess:
+        out["ess"] = ess_t
+    return out
+
+
+def softmax_rows_(z, epilogue=EPI_LOG_SOFTMAX, want_lse=False):
+    """In place over the last axis of a float32 / bf16 CUDA tensor: softmax or log_softmax (or EPI_LOGITS: leave z,
+    only return the row logsumexp) - the row pass fb200_last_layer_logits_ex uses off the tcgen05 path."""
+    Cn = z.shape[-1]
+    rows = z.numel() // Cn
+    lse = torch.empty(z.shape[:-1], dtype=torch.float32, device=z.device) if want_lse else None
+    check(
+        lib().fb200_softmax_rows(_ptr(z, (torch.float32, torch.bfloat16)), _DT[z.dtype], rows, Cn, int(epilogue),
+                                 _ptr(lse, torch.float32, True), _stream()),
+        "fb200_softmax_rows",
+    )
+    return (z, lse) if want_lse else z

@@ -120,3 +120,26 @@ class ClassificationPredictive:
         labels, size = ops.credible_sets(mean, error)
         labels, size = labels.cpu().numpy(), size.cpu().numpy()
         return [labels[i, : size[i]].tolist() for i in range(labels.shape[0])]
+
+    def conformal_set(self, train_data_loader, test_inputs_loader, n_posterior_samples: int = 30, error: float = 0.05,
+                      rng=None, distribute: bool = True, return_ess: bool = False):
+        """Conformal Bayes sets by importance sampling (classification.py:485-626): the SAME posterior draws score the
+        training data (``ensemble_log_prob`` [S, n_train], from the single-pass reduction kernel) and every class of
+        every test input (log-softmax [S, n_test, C] - the reference evaluates the test grid class by class through
+        ``ensemble_log_prob``, C redundant forward passes); the [n_test*C, S] x [S, n_train] contraction and its rank
+        count run in fb200_conformal_bayes_sets without materialising the product.  Returns a list of label lists
+        (ascending labels), plus the importance-weight ESS [n_test, S-free C, 1]-shaped like the reference's when asked."""
+        if rng is None:
+            rng = self.posterior.rng.get()
+        z_train = self.sample_calibrated_outputs(train_data_loader.to_inputs_loader(), n_posterior_samples, rng)
+        t = torch.as_tensor(np.asarray(train_data_loader.to_array_targets()), dtype=torch.int32, device=z_train.device)
+        ell_train = ops.bma_reduce_cls(z_train, ("ensemble_log_prob",), targets=t)["ensemble_log_prob"]
+        del z_train
+        z_test = self.sample_calibrated_outputs(test_inputs_loader, n_posterior_samples, rng)  # same rng: same draws
+        lsm_test = ops.softmax_rows_(z_test.float().contiguous(), ops.EPI_LOG_SOFTMAX)
+        out = ops.conformal_bayes_sets(ell_train, lsm_test, error, want_ess=return_ess)
+        region = out["region"].cpu().numpy().astype(bool)
+        sets = [np.nonzero(row)[0].tolist() for row in region]
+        if return_ess:
+            return sets, out["ess"].unsqueeze(-1)  # lax.map over test points of [C, 1] arrays (:601-621)
+        return sets

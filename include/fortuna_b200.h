@@ -186,6 +186,9 @@ int fb200_last_layer_logits_ex(const void* x, const void* w, const float* bias, 
                                const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
                                int in_dtype, int out_dtype, int w_layout, int epilogue, float* lse_out,
                                void* workspace, size_t workspace_bytes, void* stream);
+/* The row pass on its own, in place on z[rows, C]: softmax / log_softmax per epilogue (FB200_EPI_LOGITS leaves z and only
+ * fills lse_out, which is then required); lse_out optional float32 [rows]. */
+int fb200_softmax_rows(void* z, int dtype, int64_t rows, int C, int epilogue, float* lse_out, void* stream);
 /* ll[s,b] = logits[s,b,targets[b]] - lse[s,b];  ensemble_log_prob[S,B] = ll (optional);
  * log_prob[B] = logsumexp_s ll - log S (optional)  (fortuna/prob_model/predictive/base.py:104-128, 179-203).
  * logits: [S,B,C] calibrated logits (dtype FB200_F32 / FB200_BF16), lse: float32 [S,B] from the call above. */
@@ -316,6 +319,18 @@ int fb200_quantile_sorted(const float* x_sorted, int64_t n, const float* q, int 
 /* jnp.quantile(x, q, axis=0) for x[T, M] (T <= 256), method="linear": out[nq, M]
  * (RegressionPredictive.quantile over the target-sample axis, fortuna/prob_model/predictive/regression.py:331-369). */
 int fb200_quantile_axis0(const float* x, int T, int64_t M, const float* q, int nq, float* out, void* stream);
+
+/* Conformal Bayes sets by importance sampling over the posterior samples - ClassificationPredictive.conformal_set,
+ * fortuna/prob_model/predictive/classification.py:485-626.  ell_train: float32 [S, n_train] = ensemble_log_prob of the
+ * training data; lsm_test: float32 [S, n_test, C] = log-softmax of the test logits under the SAME S drawn samples
+ * (fb200_last_layer_logits_ex with FB200_EPI_LOG_SOFTMAX); threshold = float32(error * (n_train + 1)) evaluated by the
+ * caller.  Outputs: region uint8 [n_test, C] (1 = class in the set), sizes int32 [n_test] (optional), rank_counts int32
+ * [n_test, C] (optional; #{i : p_train[i] <= p_test}, rank = count + 1), ess float32 [n_test, C] (optional; effective
+ * sample size of the importance weights, :601-617).  S <= 768. */
+size_t fb200_conformal_bayes_workspace_bytes(int S, int n_test, int C);
+int fb200_conformal_bayes_sets(const float* ell_train, const float* lsm_test, int S, int n_train, int n_test, int C,
+                               float threshold, void* workspace, size_t workspace_bytes, uint8_t* region, int32_t* sizes,
+                               int32_t* rank_counts, float* ess, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SG-MCMC diagnostics over stored samples (fortuna/prob_model/posterior/sgmcmc/sgmcmc_diagnostic.py).

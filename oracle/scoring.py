@@ -224,3 +224,37 @@ def conformal_quantile_level(n, error):
 def conformal_quantile(scores, error):
     scores = _f32(scores)
     return quantile_linear(scores, conformal_quantile_level(scores.shape[0], error))
+
+
+# ----------------------------------------------------------------------------- conformal Bayes (importance sampling)
+def conformal_bayes_counts(ell_train, lsm_test, dtype=np.float32):
+    """predictive/classification.py:557-579 for every test point: ell_train [S, n_train] (ensemble log-probs of the
+    training data), lsm_test [S, n_test, C] (log-softmax of the test logits, same S samples).
+    Returns (counts int [n_test, C] = #{i : p_train[i] <= p_test}, p_train [n_test, C, n_train], p_test [n_test, C])."""
+    ell = np.asarray(ell_train, dtype=dtype)
+    lsm = np.asarray(lsm_test, dtype=dtype)
+    S, n_test, Cn = lsm.shape
+    e_train = np.exp(ell).astype(dtype)                          # jnp.exp(ensemble_train_log_probs)
+    w = np.exp(np.transpose(lsm, (1, 2, 0))).astype(dtype)       # [n_test, C, S] importance_weights
+    z = w.sum(axis=2, keepdims=True, dtype=dtype)                # normalizing_constant
+    p_train = np.einsum("tcs,si->tci", (w / z).astype(dtype), e_train).astype(dtype)
+    p_test = ((w**2).sum(axis=2, dtype=dtype) / z[..., 0]).astype(dtype)
+    counts = (p_train <= p_test[..., None]).sum(axis=2)
+    return counts, p_train, p_test
+
+
+def conformal_bayes_region(ell_train, lsm_test, error, dtype=np.float32):
+    """rank = count + 1 (the test point itself satisfies <=); region = float32(rank) > float32(error * (n_train + 1))
+    (:576-582)."""
+    counts, _, _ = conformal_bayes_counts(ell_train, lsm_test, dtype)
+    n_train = np.asarray(ell_train).shape[1]
+    return (counts + 1).astype(F32) > F32(error * (n_train + 1))
+
+
+def conformal_bayes_ess(lsm_test, dtype=np.float32):
+    """:601-617: 1 / sum_s softmax_s(log w)^2 per (test point, class)."""
+    lw = np.transpose(np.asarray(lsm_test, dtype=dtype), (1, 2, 0))
+    m = lw.max(axis=2, keepdims=True)
+    lse = m + np.log(np.exp(lw - m).sum(axis=2, keepdims=True, dtype=dtype))
+    iw = np.exp(lw - lse).astype(dtype)
+    return (dtype(1) / (iw**2).sum(axis=2, dtype=dtype)).astype(dtype)

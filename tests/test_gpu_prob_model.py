@@ -219,3 +219,38 @@ def test_fused_prior_gradient_equals_autograd_route(cuda):
     scale = float(out[1][1].abs().max())
     assert float((out[0][1] - out[1][1]).abs().max()) <= 2e-5 * scale  # 15 chaotic-free steps: rounding-level drift only
     assert float((out[0][2] - out[1][2]).abs().max()) <= 2e-4 * float(out[1][2].abs().max())
+
+
+def test_conformal_set_of_the_predictive(cuda):
+    """ClassificationPredictive.conformal_set (predictive/classification.py:485-626) end to end on two moons: sets are
+    what the oracle builds from the very logits the predictive used, sizes are 1 for confident points."""
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model import FitConfig, FitOptimizer, ProbClassifier, SGHMCPosteriorApproximator
+    from oracle import predictive as P
+    from oracle import scoring as Sc
+
+    MLP, train, test, train_loader, test_loader = _setup()
+    torch.manual_seed(0)
+    pm = ProbClassifier(model=MLP(), posterior_approximator=SGHMCPosteriorApproximator(
+        n_samples=10, n_thinning=5, burnin_length=200, step_schedule=1e-3), seed=0)
+    pm.train(train_loader, fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=80)))
+    key = pm.rng.get()
+    inputs = test_loader.to_inputs_loader()
+    sets, ess = pm.predictive.conformal_set(train_loader, inputs, n_posterior_samples=20, error=0.05, rng=key, return_ess=True)
+    assert len(sets) == 400 and ess.shape == (400, 2, 1)
+    z_train = pm.predictive.sample_calibrated_outputs(train_loader.to_inputs_loader(), 20, rng=key).cpu().numpy()
+    z_test = pm.predictive.sample_calibrated_outputs(inputs, 20, rng=key).cpu().numpy()
+    y = np.asarray(train_loader.to_array_targets())
+    ell = np.take_along_axis(P.log_softmax_rows(z_train), np.broadcast_to(y[None, :, None], (20, len(y), 1)), axis=2)[..., 0]
+    lsm = P.log_softmax_rows(z_test)
+    cnt64, p_train, p_test = Sc.conformal_bayes_counts(ell, lsm, dtype=np.float64)
+    amb = (np.abs(p_train - p_test[..., None]) <= 1e-5 * p_test[..., None]).sum(axis=2)
+    thr = float(np.float32(0.05 * (len(y) + 1)))
+    clear = np.abs(cnt64 + 1 - thr) > amb + 0.5
+    want = Sc.conformal_bayes_region(ell, lsm, 0.05, dtype=np.float64)
+    got = np.zeros_like(want)
+    for i, s in enumerate(sets):
+        got[i, s] = True
+    assert clear.mean() > 0.95 and np.array_equal(got[clear], want[clear])
+    np.testing.assert_allclose(ess[..., 0].cpu().numpy(), Sc.conformal_bayes_ess(lsm, dtype=np.float64), rtol=1e-4)
+    assert np.mean([len(s) for s in sets]) < 1.5 and all(s == sorted(s) for s in sets)

@@ -171,3 +171,56 @@ def test_credible_sets(cuda, error):
     sz = size.cpu().numpy()
     for i in range(p.shape[0]):
         assert lab[i, : sz[i]].tolist() == want[i]
+
+
+def _cb_inputs(S, n_train, n_test, C, seed):
+    r = np.random.default_rng(seed)
+    zt = (2.0 * r.standard_normal((S, n_train, C))).astype(np.float32)
+    yt = r.integers(0, C, n_train)
+    ell = np.take_along_axis(P.log_softmax_rows(zt), np.broadcast_to(yt[None, :, None], (S, n_train, 1)), axis=2)[..., 0]
+    lsm = P.log_softmax_rows((2.0 * r.standard_normal((S, n_test, C))).astype(np.float32))
+    return np.ascontiguousarray(ell, dtype=np.float32), np.ascontiguousarray(lsm, dtype=np.float32)
+
+
+@pytest.mark.parametrize("S,n_train,n_test,C", [(30, 500, 40, 2), (7, 63, 5, 3), (100, 3000, 130, 10), (33, 1000, 7, 101), (256, 257, 65, 4)])
+@pytest.mark.parametrize("error", [0.05, 0.3])
+def test_conformal_bayes_sets(cuda, S, n_train, n_test, C, error):
+    """fb200_conformal_bayes_sets against the float64 evaluation of predictive/classification.py:557-582.  The rank is an
+    integer count of float comparisons p_train[i] <= p_test: entries within a few float32 ulps of p_test may fall
+    either way, so each row's count may differ by at most its number of such entries, and the region must agree
+    wherever the rank is further than that from the threshold."""
+    from fortuna_b200 import ops
+
+    ell, lsm = _cb_inputs(S, n_train, n_test, C, seed=S + C)
+    out = ops.conformal_bayes_sets(torch.from_numpy(ell).to(cuda), torch.from_numpy(lsm).to(cuda), error,
+                                   want_counts=True, want_ess=True)
+    cnt64, p_train, p_test = Sc.conformal_bayes_counts(ell, lsm, dtype=np.float64)
+    amb = (np.abs(p_train - p_test[..., None]) <= 4e-6 * p_test[..., None]).sum(axis=2)
+    got = out["rank_counts"].cpu().numpy()
+    assert np.all(np.abs(got - cnt64) <= amb)
+    assert (amb == 0).mean() > 0.8 and np.array_equal(got[amb == 0], cnt64[amb == 0])
+    thr = np.float32(error * (n_train + 1))
+    clear = np.abs((cnt64 + 1).astype(np.float64) - float(thr)) > amb + 0.5
+    want_region = Sc.conformal_bayes_region(ell, lsm, error, dtype=np.float64)
+    region = out["region"].cpu().numpy().astype(bool)
+    assert np.array_equal(region[clear], want_region[clear])
+    assert np.array_equal(region, (got + 1).astype(np.float32) > thr)
+    assert np.array_equal(out["sizes"].cpu().numpy(), region.sum(axis=1))
+    np.testing.assert_allclose(out["ess"].cpu().numpy(), Sc.conformal_bayes_ess(lsm, dtype=np.float64), rtol=2e-5)
+    # the float32 restatement agrees with the float64 one to the same standard
+    cnt32, _, _ = Sc.conformal_bayes_counts(ell, lsm)
+    assert np.all(np.abs(cnt32 - cnt64) <= amb)
+
+
+def test_softmax_rows_in_place(cuda):
+    from fortuna_b200 import ops
+
+    z = (3 * np.random.default_rng(0).standard_normal((5, 37, 1000))).astype(np.float32)
+    zt = torch.from_numpy(z.copy()).to(cuda)
+    _, lse = ops.softmax_rows_(zt, ops.EPI_LOGITS, want_lse=True)
+    assert torch.equal(zt.cpu(), torch.from_numpy(z))
+    m = z.max(-1, keepdims=True)
+    want_lse = (m + np.log(np.exp(z - m).sum(-1, keepdims=True)))[..., 0]
+    np.testing.assert_allclose(lse.cpu().numpy(), want_lse, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ops.softmax_rows_(zt.clone(), ops.EPI_LOG_SOFTMAX).cpu().numpy(), P.log_softmax_rows(z), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(ops.softmax_rows_(zt.clone(), ops.EPI_SOFTMAX).cpu().numpy(), P.softmax(z), rtol=1e-5, atol=1e-9)

@@ -590,6 +590,27 @@ def reg_sample_targets(outputs, key, n_target_samples, log_temp=None, want_idx=F
     return (y, idx) if want_idx else y
 
 
+def reg_mc_entropies(outputs, sample_idx, target_keys, n_target_samples, names=("entropy",), log_temp=None):
+    """outputs [n_stored, B, 2d], sample_idx int32 [S], target_keys int32 [S, 2] -> dict name -> float32 [B] for names
+    among entropy / aleatoric_entropy / epistemic_entropy."""
+    n, B, two_d = outputs.shape
+    S = sample_idx.numel()
+    res = {k: torch.empty(B, dtype=torch.float32, device=outputs.device) for k in names}
+    for k in names:
+        if k not in ("entropy", "aleatoric_entropy", "epistemic_entropy"):
+            raise ValueError(k)
+    check(
+        lib().fb200_reg_mc_entropies(
+            _ptr(outputs, torch.float32), _ptr(log_temp, torch.float32, True), _ptr(sample_idx, torch.int32),
+            _ptr(target_keys, KEY_DTYPE), n, S, int(n_target_samples), B, two_d // 2,
+            _ptr(res.get("entropy"), None, True), _ptr(res.get("aleatoric_entropy"), None, True),
+            _ptr(res.get("epistemic_entropy"), None, True), _stream(),
+        ),
+        "fb200_reg_mc_entropies",
+    )
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ diagnostics
 def _row_matrix(t):
     """[S, N] float32 CUDA matrix whose rows may be strided (a slice of the sample bank): (ptr, S, N, row_stride)."""

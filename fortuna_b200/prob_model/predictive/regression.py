@@ -1,7 +1,7 @@
 """``prob_model.predictive`` for regression - method names / signatures of
 fortuna/prob_model/predictive/regression.py:22-369 and fortuna/prob_model/predictive/base.py (mean, variances, std,
-log_prob, sample).  Model outputs are ``[mu, log sigma^2]`` (fortuna/prob_output_layer/regression.py:18-74).
-The Monte-Carlo entropies (regression.py:51-267) are a "next" row of the scope and not built."""
+log_prob, sample, the Monte-Carlo entropies).  Model outputs are ``[mu, log sigma^2]``
+(fortuna/prob_output_layer/regression.py:18-74)."""
 from typing import List, Optional, Union
 
 import numpy as np
@@ -63,6 +63,28 @@ class RegressionPredictive:
     def ensemble_log_prob(self, data_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
         return self._reduce(data_loader, ("ensemble_log_prob",), n_posterior_samples, rng,
                             data_loader.to_array_targets())["ensemble_log_prob"]
+
+    def _mc_entropy(self, name, inputs_loader, n_posterior_samples, n_target_samples, rng):
+        """regression.py:51-267: ``key1, *keys = split(rng, 1 + S)``; the S posterior draws use key1, the target samples of
+        draw i use keys[i]; one kernel (fb200_reg_mc_entropies) forms the Monte-Carlo mean without materialising them."""
+        if rng is None:
+            rng = self.posterior.rng.get()
+        ks = ops.split(rng, 1 + n_posterior_samples)
+        idx = self.posterior.sample_indices(ks[0].contiguous(), n_posterior_samples)
+        z = self._stored_outputs(self._x(inputs_loader))
+        return ops.reg_mc_entropies(z, idx, ks[1:].contiguous(), n_target_samples, (name,), log_temp=self.log_temp)[name]
+
+    def aleatoric_entropy(self, inputs_loader, n_posterior_samples: int = 30, n_target_samples: int = 30, rng=None,
+                          distribute: bool = True):
+        return self._mc_entropy("aleatoric_entropy", inputs_loader, n_posterior_samples, n_target_samples, rng)
+
+    def epistemic_entropy(self, inputs_loader, n_posterior_samples: int = 30, n_target_samples: int = 30, rng=None,
+                          distribute: bool = True):
+        return self._mc_entropy("epistemic_entropy", inputs_loader, n_posterior_samples, n_target_samples, rng)
+
+    def entropy(self, inputs_loader, n_posterior_samples: int = 30, n_target_samples: int = 30, rng=None,
+                distribute: bool = True):
+        return self._mc_entropy("entropy", inputs_loader, n_posterior_samples, n_target_samples, rng)
 
     def sample(self, inputs_loader, n_target_samples: int = 1, return_aux=None, rng=None, distribute: bool = True) -> torch.Tensor:
         """[T, B, d] target samples.  Like the reference, every input BATCH of the loader is sampled with the same

@@ -320,6 +320,17 @@ int fb200_quantile_sorted(const float* x_sorted, int64_t n, const float* q, int 
  * (RegressionPredictive.quantile over the target-sample axis, fortuna/prob_model/predictive/regression.py:331-369). */
 int fb200_quantile_axis0(const float* x, int T, int64_t M, const float* q, int nq, float* out, void* stream);
 
+/* Monte-Carlo entropies of the regression predictive (fortuna/prob_model/predictive/regression.py:51-267), bit-exact
+ * target draws.  outputs: float32 [n_stored, B, 2d] = [mu, log sigma^2] of every stored posterior sample (d <= 8);
+ * sample_idx: int32 [S] drawn posterior samples (fb200_sample_indices with key1 of `key1, *keys = split(rng, 1 + S)`);
+ * target_keys: uint32 [S, 2] = those `keys` (rows 1..S of fb200_threefry_split(rng, 1 + S)); T = n_target_samples.
+ * Each output is optional float32 [B]:  aleatoric = -(1/S) sum_i mean_t log N(y_it; out_i),
+ * entropy = -(1/S) sum_i mean_t [logsumexp_j log N(y_it; out_j) - log S],  epistemic = entropy - aleatoric
+ * with y_it = mu_i + sigma_i * normal(keys[i], (T, B, d))[t]. */
+int fb200_reg_mc_entropies(const float* outputs, const float* log_temp, const int32_t* sample_idx,
+                           const uint32_t* target_keys, int n_stored, int S, int T, int B, int d, float* entropy,
+                           float* aleatoric_entropy, float* epistemic_entropy, void* stream);
+
 /* Conformal Bayes sets by importance sampling over the posterior samples - ClassificationPredictive.conformal_set,
  * fortuna/prob_model/predictive/classification.py:485-626.  ell_train: float32 [S, n_train] = ensemble_log_prob of the
  * training data; lsm_test: float32 [S, n_test, C] = log-softmax of the test logits under the SAME S drawn samples

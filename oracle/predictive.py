@@ -301,6 +301,42 @@ def reg_sample_targets(outputs_stored, key, n_target_samples, log_temp=None):
     return np.stack(ys), np.array(idx, dtype=np.int32)
 
 
+def reg_mc_entropies(outputs_stored, key, n_posterior_samples, n_target_samples, log_temp=None):
+    """RegressionPredictive.aleatoric_entropy / epistemic_entropy / entropy (predictive/regression.py:51-267) for ONE rng:
+    key1, *keys = split(rng, 1 + S); outputs_i drawn with key1 (idx_s = choice(split(key1, S)[s], n_stored),
+    predictive/base.py:487-499); y_i = sample(T, outputs_i, keys[i]); the three Monte-Carlo means.
+    Returns dict(entropy, aleatoric_entropy, epistemic_entropy) of float32 [B]."""
+    from . import prng
+
+    z = _f32(outputs_stored)
+    n, B, two_d = z.shape
+    d = two_d // 2
+    S, T = int(n_posterior_samples), int(n_target_samples)
+    ks = prng.split(np.asarray(key, dtype=np.uint32), 1 + S)
+    key1, keys = ks[0], ks[1:]
+    idx = [prng.choice(k, n) for k in prng.split(key1, S)]
+    ens = np.stack([z[i] for i in idx])
+    if log_temp is not None:
+        ens = reg_calibrate(ens, log_temp)
+    mu, lv = reg_split(ens)
+    ys = []
+    for i in range(S):
+        eps = prng.normal(keys[i], T * B * d).reshape(T, B, d)
+        ys.append((mu[i][None] + np.exp(F32(0.5) * lv[i], dtype=F32)[None] * eps).astype(F32))
+    log_S = np.log(F32(S), dtype=F32)
+    alea = np.zeros(B, F32)
+    ent = np.zeros(B, F32)
+    epi = np.zeros(B, F32)
+    for i in range(S):
+        log_liks = np.stack([reg_ensemble_log_prob(ens[i : i + 1], ys[i][t])[0] for t in range(T)])       # [T, B]
+        log_preds = np.stack([logsumexp(reg_ensemble_log_prob(ens, ys[i][t]), axis=0) - log_S for t in range(T)])
+        alea = alea - log_liks.mean(axis=0, dtype=F32)
+        ent = ent - log_preds.mean(axis=0, dtype=F32)
+        epi = epi - (log_preds - log_liks).mean(axis=0, dtype=F32)
+    return {"entropy": (ent / F32(S)).astype(F32), "aleatoric_entropy": (alea / F32(S)).astype(F32),
+            "epistemic_entropy": (epi / F32(S)).astype(F32)}
+
+
 def quantile_axis0(x, q):
     """jnp.quantile(x, q, axis=0), method="linear"."""
     from .scoring import quantile_linear

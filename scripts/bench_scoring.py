@@ -49,6 +49,13 @@ def main():
     out["conformal_sets_ms"] = timed(lambda: ops.conformal_sets(val, scores, thr), a.iters)
     ethr = torch.from_numpy(ece_thresholds(a.B)).to(dev)
     out["ece_bins_ms"] = timed(lambda: ops.ece_bins(mean, t, ethr), a.iters)
+    # conformal Bayes at the c2 shape: 30 draws, 60 000 training points, 10 000 test points x 10 classes
+    S, n_train, n_test, Cn = 30, 60000, 10000, 10
+    ell = torch.log_softmax(2 * torch.randn((S, n_train, Cn), device=dev, generator=g), -1)[..., 0].contiguous()
+    lsm = torch.log_softmax(2 * torch.randn((S, n_test, Cn), device=dev, generator=g), -1).contiguous()
+    ms = timed(lambda: ops.conformal_bayes_sets(ell, lsm, 0.05), 5)
+    out["conformal_bayes_c2_ms"] = ms
+    out["conformal_bayes_c2_fp32_tflops"] = 2.0 * n_test * Cn * n_train * S / ms / 1e9
     print(json.dumps(out))
 
 

@@ -76,3 +76,31 @@ def test_prob_regressor_sine(cuda):
     assert q.shape == (64, 1)
     with pytest.raises(ValueError):
         pr.predictive.credible_interval(inputs, interval_type="both")
+    # Monte-Carlo entropies (regression.py:51-267) through the user API, against the oracle on the stored outputs
+    want_e = P.reg_mc_entropies(stored, ops.key_to_host(key), 12, 9)
+    for name in ("entropy", "aleatoric_entropy", "epistemic_entropy"):
+        got = getattr(pr.predictive, name)(inputs, n_posterior_samples=12, n_target_samples=9, rng=key)
+        assert got.shape == (64,)
+        np.testing.assert_allclose(got.cpu().numpy(), want_e[name], rtol=2e-5, atol=2e-5, err_msg=name)
+
+
+
+@pytest.mark.parametrize("n,B,d,S,T", [(5, 7, 2, 6, 4), (10, 129, 1, 30, 30), (3, 33, 3, 2, 1), (4, 40, 8, 5, 3)])
+def test_reg_mc_entropies_match_oracle(cuda, n, B, d, S, T):
+    """fb200_reg_mc_entropies: bit-exact target draws (threefry element (t, b, k) of keys[i]), Monte-Carlo means of
+    log N within rtol 1e-5; entropy = aleatoric + epistemic by construction."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(n + B + d)
+    z = np.concatenate([r.standard_normal((n, B, d)), 0.5 * r.standard_normal((n, B, d)) - 1.0], axis=-1).astype(np.float32)
+    lt = np.array([0.1], np.float32)
+    want = P.reg_mc_entropies(z, oprng.PRNGKey(21), S, T, lt)
+    key = ops.PRNGKey(21, cuda)
+    ks = ops.split(key, 1 + S)
+    idx = ops.sample_indices(ks[0].contiguous(), S, n)
+    got = ops.reg_mc_entropies(torch.from_numpy(z).to(cuda), idx, ks[1:].contiguous(), T,
+                               ("entropy", "aleatoric_entropy", "epistemic_entropy"), log_temp=torch.from_numpy(lt).to(cuda))
+    for name in want:
+        np.testing.assert_allclose(got[name].cpu().numpy(), want[name], rtol=2e-5, atol=2e-5, err_msg=name)
+    np.testing.assert_allclose((got["aleatoric_entropy"] + got["epistemic_entropy"]).cpu().numpy(),
+                               got["entropy"].cpu().numpy(), rtol=1e-5, atol=1e-5)

@@ -592,6 +592,100 @@ static int launch_row_sort32_warp(const RowSortArgs& a, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Target samples of the classification predictive (fortuna/prob_model/predictive/base.py:406-440 ->
+// fortuna/likelihood/base.py:339-372 -> fortuna/prob_output_layer/classification.py:33-51), the reference's draws:
+//   keys = split(rng, T); (key1, key2) = split(keys[t]); i = choice(key1, n_stored); probs = softmax(z_i);
+//   keys_b = split(key2, B); y[t, b] = choice(keys_b[b], C, p=probs[b], shape=(1,))
+// and jax.random.choice with p is  p_cuml = cumsum(p); r = p_cuml[-1] * (1 - uniform(key, (1,)));
+// searchsorted(p_cuml, r) = #{c : p_cuml[c] < r}.  One warp per (t, b): the row's softmax in registers (rank-major,
+// NR per lane), the inclusive prefix sums in jnp.cumsum's association order (warp_row_tree_prefix, as for the APS
+// scores), one count.  The uniform is the threefry block of the single element of keys_b[b] - bit-identical to jax.
+// ------------------------------------------------------------------------------------------------
+struct ClsSampleArgs {
+  const float* z;         // [n_stored, B, C] logits
+  const float* log_temp;  // [1] or null: outputs are logits * exp(-log_temp)
+  const uint32_t* key;    // [2]
+  uint32_t T, n_stored;
+  int B, C;
+  int32_t* y;        // [T, B]
+  int32_t* idx_out;  // [T] or null
+};
+
+template <int NR>
+__global__ void __launch_bounds__(256) cls_sample_targets_kernel(const ClsSampleArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int b = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const uint32_t t = blockIdx.y;
+  if (b >= a.B) return;
+  // key schedule of draw t (same in every warp of the row)
+  const uint32_t kt0 = random_bits_elem(a.key[0], a.key[1], 2u * a.T, 2u * t);
+  const uint32_t kt1 = random_bits_elem(a.key[0], a.key[1], 2u * a.T, 2u * t + 1u);
+  uint32_t a0 = 0u, a1 = 2u, b0 = 1u, b1 = 3u;  // split(keys[t]): key1 = (a0, b0), key2 = (a1, b1)
+  threefry2x32(kt0, kt1, a0, a1);
+  threefry2x32(kt0, kt1, b0, b1);
+  uint32_t c0 = 0u, c1 = 2u, d0 = 1u, d1 = 3u;  // choice(key1, n_stored) = randint: split(key1) -> two single draws
+  threefry2x32(a0, b0, c0, c1);
+  threefry2x32(a0, b0, d0, d1);
+  uint32_t hi = 0u, hi1 = 0u, lo = 0u, lo1 = 0u;
+  threefry2x32(c0, d0, hi, hi1);
+  threefry2x32(c1, d1, lo, lo1);
+  uint32_t mult = 65536u % a.n_stored;
+  mult = (mult * mult) % a.n_stored;
+  const uint32_t i = ((hi % a.n_stored) * mult + (lo % a.n_stored)) % a.n_stored;
+  if (a.idx_out && b == 0 && lane == 0) a.idx_out[t] = (int32_t)i;
+  // keys_b[b] = split(key2, B)[b], then its single uniform in [0, 1)
+  const uint32_t kb0 = random_bits_elem(a1, b1, 2u * (uint32_t)a.B, 2u * (uint32_t)b);
+  const uint32_t kb1 = random_bits_elem(a1, b1, 2u * (uint32_t)a.B, 2u * (uint32_t)b + 1u);
+  const uint32_t bits = random_bits_elem(kb0, kb1, 1u, 0u);
+  const float u = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  // softmax of the row, rank-major: element lane * NR + r
+  const float scale = a.log_temp ? expf(-a.log_temp[0]) : 1.0f;
+  const float* row = a.z + ((size_t)i * a.B + b) * a.C;
+  float x[NR];
+  float m = -CUDART_INF_F;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int c = lane * NR + r;
+    x[r] = c < a.C ? row[c] * scale : -CUDART_INF_F;
+    m = fmaxf(m, x[r]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float ssum = 0.0f;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    x[r] = lane * NR + r < a.C ? expf(x[r] - m) : 0.0f;
+    ssum += x[r];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+#pragma unroll
+  for (int r = 0; r < NR; ++r) x[r] = x[r] / ssum;
+  warp_row_tree_prefix<NR>(x, lane);
+  // p_cuml[-1]: the prefix at position C - 1
+  const int last = a.C - 1;
+  float tot = 0.0f;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) tot = (lane * NR + r == last) ? x[r] : tot;
+  tot = __shfl_sync(0xffffffffu, tot, last / NR);
+  const float rr = tot * (1.0f - u);
+  int cnt = 0;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) cnt += (lane * NR + r < a.C && x[r] < rr) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) a.y[(size_t)t * a.B + b] = cnt;
+}
+
+template <int NR>
+static int launch_cls_sample(const ClsSampleArgs& a, cudaStream_t st) {
+  const int64_t threads = (int64_t)a.B * 32;
+  cls_sample_targets_kernel<NR><<<dim3((unsigned)((threads + 255) / 256), a.T), 256, 0, st>>>(a);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
 static int launch_row_sort(RowSortArgs a, cudaStream_t st) {
   if (!a.perm && !a.set_size && a.C <= 1024) {
     if (a.C <= 32) return launch_row_sort32_warp<1>(a, st);
@@ -1005,6 +1099,31 @@ extern "C" int fb200_credible_sets(const float* mean, int B, int C, float thresh
   a.set_size = set_size;
   a.set_threshold = threshold;
   return launch_row_sort(a, (cudaStream_t)stream);
+}
+
+extern "C" int fb200_cls_sample_targets(const float* logits, const float* log_temp, const uint32_t* key,
+                                        int n_target_samples, int n_stored, int B, int C, int32_t* y, int32_t* idx_out,
+                                        void* stream) {
+  if (!logits || !key || !y) return FB200_E_NULL;
+  if (n_target_samples <= 0 || n_stored <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
+  if (C > 1024 || n_target_samples > 65535 || B >= (1 << 30)) return FB200_E_UNSUPPORTED;
+  ClsSampleArgs a{};
+  a.z = logits;
+  a.log_temp = log_temp;
+  a.key = key;
+  a.T = (uint32_t)n_target_samples;
+  a.n_stored = (uint32_t)n_stored;
+  a.B = B;
+  a.C = C;
+  a.y = y;
+  a.idx_out = idx_out;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 32) return launch_cls_sample<1>(a, st);
+  if (C <= 64) return launch_cls_sample<2>(a, st);
+  if (C <= 128) return launch_cls_sample<4>(a, st);
+  if (C <= 256) return launch_cls_sample<8>(a, st);
+  if (C <= 512) return launch_cls_sample<16>(a, st);
+  return launch_cls_sample<32>(a, st);
 }
 
 extern "C" int fb200_simple_scores(const float* probs, const int32_t* targets, int B, int C, float* scores,

@@ -590,6 +590,19 @@ def reg_sample_targets(outputs, key, n_target_samples, log_temp=None, want_idx=F
     return (y, idx) if want_idx else y
 
 
+def cls_sample_targets(logits, key, n_target_samples, log_temp=None, want_idx=False):
+    """logits [n_stored, B, C] -> y int32 [T, B] (and the drawn posterior-sample indices int32 [T])."""
+    n, B, Cn = logits.shape
+    y = torch.empty((n_target_samples, B), dtype=torch.int32, device=logits.device)
+    idx = torch.empty(n_target_samples, dtype=torch.int32, device=logits.device) if want_idx else None
+    check(
+        lib().fb200_cls_sample_targets(_ptr(logits, torch.float32), _ptr(log_temp, torch.float32, True), _ptr(key, KEY_DTYPE),
+                                       int(n_target_samples), n, B, Cn, _ptr(y), _ptr(idx, None, True), _stream()),
+        "fb200_cls_sample_targets",
+    )
+    return (y, idx) if want_idx else y
+
+
 def reg_mc_entropies(outputs, sample_idx, target_keys, n_target_samples, names=("entropy",), log_temp=None):
     """outputs [n_stored, B, 2d], sample_idx int32 [S], target_keys int32 [S, 2] -> dict name -> float32 [B] for names
     among entropy / aleatoric_entropy / epistemic_entropy."""

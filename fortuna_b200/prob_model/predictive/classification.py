@@ -121,6 +121,39 @@ class ClassificationPredictive:
         labels, size = labels.cpu().numpy(), size.cpu().numpy()
         return [labels[i, : size[i]].tolist() for i in range(labels.shape[0])]
 
+    def _stored_logits(self, x: torch.Tensor) -> torch.Tensor:
+        """[n_stored, B, C] float32 logits of every stored posterior sample for one input batch."""
+        bound, bank = self.posterior.bound, self.posterior.state
+        if bound.is_last_layer_only():
+            with torch.no_grad():
+                feats = bound.model.dfe_subnet(x).contiguous()
+            w = bank.leaf_matrix(PREFIX + ("output_subnet", "weight"))
+            has_bias = bound.model.output_subnet.bias is not None
+            bias = bank.leaf_matrix(PREFIX + ("output_subnet", "bias")) if has_bias else None
+            return ops.last_layer_logits(feats, w, bias, None, w_layout=ops.W_SCD, path=1)
+        keep = bound.params.flat.clone()
+        outs = []
+        with torch.no_grad():
+            for i in range(bank.size):
+                bound.load_flat(bank.bank[i])
+                outs.append(bound.model(x))
+        bound.load_flat(keep)
+        return torch.stack(outs).float().contiguous()
+
+    def sample(self, inputs_loader, n_target_samples: int = 1, return_aux=None, rng=None, distribute: bool = True) -> torch.Tensor:
+        """int32 [T, B] class samples (base.py:318-440).  Like the reference, every input BATCH of the loader is sampled
+        with the same key, so results depend on the loader's batch size exactly as there."""
+        if return_aux:
+            raise NotImplementedError("auxiliary outputs of `sample` are outside the hot path")
+        if rng is None:
+            rng = self.posterior.rng.get()
+        parts = []
+        batches = inputs_loader if hasattr(inputs_loader, "__iter__") and not isinstance(inputs_loader, (np.ndarray, torch.Tensor)) else [inputs_loader]
+        for xb in batches:
+            zb = self._stored_logits(self._inputs(xb))
+            parts.append(ops.cls_sample_targets(zb, rng, n_target_samples, log_temp=self.log_temp))
+        return torch.cat(parts, dim=1)
+
     def conformal_set(self, train_data_loader, test_inputs_loader, n_posterior_samples: int = 30, error: float = 0.05,
                       rng=None, distribute: bool = True, return_ess: bool = False):
         """Conformal Bayes sets by importance sampling (classification.py:485-626): the SAME posterior draws score the

@@ -320,6 +320,15 @@ int fb200_quantile_sorted(const float* x_sorted, int64_t n, const float* q, int 
  * (RegressionPredictive.quantile over the target-sample axis, fortuna/prob_model/predictive/regression.py:331-369). */
 int fb200_quantile_axis0(const float* x, int T, int64_t M, const float* q, int nq, float* out, void* stream);
 
+/* Target samples of the classification predictive - Predictive.sample (fortuna/prob_model/predictive/base.py:318-440)
+ * -> ClassificationProbOutputLayer.sample (fortuna/prob_output_layer/classification.py:33-51), the reference's draws:
+ * keys = split(key, T); (k1, k2) = split(keys[t]); i = choice(k1, n_stored); y[t, b] = choice(split(k2, B)[b], C,
+ * p = softmax(logits[i, b] * exp(-log_temp)), shape = (1,)) = searchsorted(cumsum(p), cumsum(p)[-1] * (1 - uniform)).
+ * logits: float32 [n_stored, B, C] (C <= 1024) of every stored posterior sample for ONE input batch; y: int32 [T, B];
+ * idx_out: optional int32 [T] (the drawn posterior samples). */
+int fb200_cls_sample_targets(const float* logits, const float* log_temp, const uint32_t* key, int n_target_samples,
+                             int n_stored, int B, int C, int32_t* y, int32_t* idx_out, void* stream);
+
 /* Monte-Carlo entropies of the regression predictive (fortuna/prob_model/predictive/regression.py:51-267), bit-exact
  * target draws.  outputs: float32 [n_stored, B, 2d] = [mu, log sigma^2] of every stored posterior sample (d <= 8);
  * sample_idx: int32 [S] drawn posterior samples (fb200_sample_indices with key1 of `key1, *keys = split(rng, 1 + S)`);

@@ -301,6 +301,32 @@ def reg_sample_targets(outputs_stored, key, n_target_samples, log_temp=None):
     return np.stack(ys), np.array(idx, dtype=np.int32)
 
 
+def cls_sample_targets(logits_stored, key, n_target_samples, log_temp=None):
+    """Predictive.sample for classification (predictive/base.py:406-440, likelihood/base.py:363-369,
+    prob_output_layer/classification.py:33-51) on ONE input batch.  jax.random.choice(key, C, p=p, shape=(1,)) is
+    ``p_cuml = cumsum(p); r = p_cuml[-1] * (1 - uniform(key, (1,))); searchsorted(p_cuml, r)`` (jax/_src/random.py,
+    ``choice`` with replacement), cumsum in associative_scan order (oracle/scoring.py).
+    logits_stored: [n_stored, B, C].  Returns (y int32 [T, B], idx int32 [T])."""
+    from . import prng
+    from .scoring import cumsum_f32
+
+    z = _f32(logits_stored)
+    n, B, Cn = z.shape
+    keys = prng.split(np.asarray(key, dtype=np.uint32), n_target_samples)
+    ys, idx = [], []
+    for k in keys:
+        k1, k2 = prng.split(k, 2)
+        i = prng.choice(k1, n)
+        zi = z[i] if log_temp is None else (z[i] * np.exp(-_f32(log_temp).reshape(()), dtype=F32)).astype(F32)
+        p_cuml = cumsum_f32(softmax(zi))
+        kb = prng.split(k2, B)
+        u = np.array([prng.uniform(kb[b], 1)[0] for b in range(B)], dtype=F32)
+        r = (p_cuml[:, -1] * (F32(1) - u)).astype(F32)
+        ys.append((p_cuml < r[:, None]).sum(axis=1).astype(np.int32))
+        idx.append(i)
+    return np.stack(ys), np.array(idx, dtype=np.int32)
+
+
 def reg_mc_entropies(outputs_stored, key, n_posterior_samples, n_target_samples, log_temp=None):
     """RegressionPredictive.aleatoric_entropy / epistemic_entropy / entropy (predictive/regression.py:51-267) for ONE rng:
     key1, *keys = split(rng, 1 + S); outputs_i drawn with key1 (idx_s = choice(split(key1, S)[s], n_stored),

@@ -227,3 +227,33 @@ def test_pipeline_from_host_features_matches_oracle(cuda):
     assert np.array_equal(out["conformal_mask"].numpy().astype(bool), conds)
     assert np.array_equal(out["conformal_sizes"].numpy(), sizes)
     np.testing.assert_allclose(out["ece_result"].numpy()[0], Sc.expected_calibration_error(mean.argmax(-1), mean, t), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,B,C,T", [(5, 7, 2, 6), (10, 129, 10, 30), (3, 33, 1000, 4), (4, 50, 37, 3), (2, 9, 1, 2), (6, 300, 1024, 2)])
+def test_cls_sample_targets_are_the_reference_draws(cuda, n, B, C, T):
+    """fb200_cls_sample_targets vs the oracle's restatement of Predictive.sample -> ClassificationProbOutputLayer.sample
+    (jax.random.choice with p = cumsum + searchsorted): posterior-sample draws and class draws are integers, compared
+    exactly."""
+    from fortuna_b200 import ops
+    from oracle import prng as oprng
+
+    r = np.random.default_rng(n + B + C)
+    z = (2.5 * r.standard_normal((n, B, C))).astype(np.float32)
+    lt = np.array([0.2], np.float32)
+    want, want_idx = P.cls_sample_targets(z, oprng.PRNGKey(13), T, lt)
+    y, idx = ops.cls_sample_targets(torch.from_numpy(z).to(cuda), ops.PRNGKey(13, cuda), T,
+                                    log_temp=torch.from_numpy(lt).to(cuda), want_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), want_idx)
+    got = y.cpu().numpy()
+    assert got.shape == (T, B) and got.min() >= 0 and got.max() < C
+    assert np.array_equal(got, want)
+
+
+def test_cls_sample_targets_follow_the_predictive_distribution(cuda):
+    """Many draws from one stored sample: class frequencies approach softmax (a statistical sanity check of the draw)."""
+    from fortuna_b200 import ops
+
+    z = torch.tensor([[[0.0, 1.0, 2.0, -1.0]]], device=cuda).repeat(1, 4096, 1).contiguous()
+    y = ops.cls_sample_targets(z, ops.PRNGKey(5, cuda), 16)
+    freq = torch.bincount(y.reshape(-1).long(), minlength=4).float() / y.numel()
+    np.testing.assert_allclose(freq.cpu().numpy(), P.softmax(np.array([[0.0, 1.0, 2.0, -1.0]], np.float32))[0], atol=0.01)

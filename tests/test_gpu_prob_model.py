@@ -254,3 +254,26 @@ def test_conformal_set_of_the_predictive(cuda):
     assert clear.mean() > 0.95 and np.array_equal(got[clear], want[clear])
     np.testing.assert_allclose(ess[..., 0].cpu().numpy(), Sc.conformal_bayes_ess(lsm, dtype=np.float64), rtol=1e-4)
     assert np.mean([len(s) for s in sets]) < 1.5 and all(s == sorted(s) for s in sets)
+
+
+def test_predictive_sample_classification(cuda):
+    """ClassificationPredictive.sample through the user API == the oracle on the stored logits, batch by batch."""
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model import FitConfig, FitOptimizer, ProbClassifier, SGHMCPosteriorApproximator
+    from oracle import predictive as P
+
+    MLP, train, test, train_loader, test_loader = _setup()
+    torch.manual_seed(0)
+    pm = ProbClassifier(model=MLP(), posterior_approximator=SGHMCPosteriorApproximator(
+        n_samples=6, n_thinning=5, burnin_length=100, step_schedule=1e-3), seed=0)
+    pm.train(train_loader, fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=40)))
+    key = pm.rng.get()
+    inputs = test_loader.to_inputs_loader()
+    y = pm.predictive.sample(inputs, n_target_samples=5, rng=key)
+    assert y.shape == (5, 400) and y.dtype == torch.int32
+    want = []
+    for xb in inputs:
+        stored = pm.predictive._stored_logits(torch.as_tensor(np.asarray(xb), dtype=torch.float32, device=cuda)).cpu().numpy()
+        want.append(P.cls_sample_targets(stored, ops.key_to_host(key), 5)[0])
+    assert np.array_equal(y.cpu().numpy(), np.concatenate(want, axis=1))
+    assert float((y[0].cpu() == torch.as_tensor(test[1])).float().mean()) > 0.9  # a trained model mostly samples the label

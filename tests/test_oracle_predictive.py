@@ -88,3 +88,30 @@ def test_regression_maps():
     ll = -0.5 * (np.exp(-lv) * (y - mu) ** 2 + lv + np.log(2 * np.pi)).sum(-1)
     np.testing.assert_allclose(P.reg_log_prob(z, y), sp_lse(ll, axis=0) - np.log(6), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(P.reg_calibrate(z, np.array([0.5], np.float32))[..., 2:], z[..., 2:] + 0.5, rtol=1e-6)
+
+
+def test_cls_sample_targets_oracle_properties():
+    """Class frequencies of the restated Predictive.sample approach softmax; C = 1 always draws class 0."""
+    from oracle import prng
+
+    z = np.tile(np.array([[[0.0, 1.0, 2.0, -1.0]]], np.float32), (1, 2000, 1))
+    y, idx = P.cls_sample_targets(z, prng.PRNGKey(3), 3)
+    assert y.shape == (3, 2000) and idx.tolist() == [0, 0, 0]
+    freq = np.bincount(y.reshape(-1), minlength=4) / y.size
+    np.testing.assert_allclose(freq, P.softmax(z[0, :1])[0], atol=0.02)
+    assert not P.cls_sample_targets(np.zeros((2, 5, 1), np.float32), prng.PRNGKey(0), 4)[0].any()
+
+
+def test_reg_mc_entropies_oracle_properties():
+    """entropy = aleatoric + epistemic; one posterior sample has no epistemic part; the aleatoric entropy of a Gaussian
+    approaches 0.5 log(2 pi e sigma^2) as the number of target samples grows."""
+    from oracle import prng
+
+    r = np.random.default_rng(0)
+    z = np.concatenate([r.standard_normal((4, 6, 1)), np.full((4, 6, 1), -1.0)], axis=-1).astype(np.float32)
+    e = P.reg_mc_entropies(z, prng.PRNGKey(1), 5, 7)
+    np.testing.assert_allclose(e["aleatoric_entropy"] + e["epistemic_entropy"], e["entropy"], rtol=1e-5, atol=1e-5)
+    one = P.reg_mc_entropies(z[:1], prng.PRNGKey(1), 1, 50)
+    np.testing.assert_allclose(one["epistemic_entropy"], 0.0, atol=1e-6)
+    big = P.reg_mc_entropies(z[:1], prng.PRNGKey(2), 1, 4000)
+    np.testing.assert_allclose(big["aleatoric_entropy"], 0.5 * (np.log(2 * np.pi * np.e) - 1.0), atol=0.05)

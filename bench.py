@@ -54,19 +54,46 @@ def _tensor_peaks():
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled every few milliseconds from a thread
+    (nvidia_ml_py), nvidia-smi -lms 100 as the fallback (one sample per 100 ms - too coarse for a 70 ms region)."""
+
     FIELDS = (
         "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     )
+    NVML_PERIOD_S = 0.004
 
     def __init__(self, index=0):
         self.lines = []  # (wall time, csv line)
         self.proc = None
         self.index = index
         self.t0 = self.t1 = None
+        self.nvml = None
+        self._stop = threading.Event()
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -76,6 +103,20 @@ class ClockSampler:
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        while not self._stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                r = int(get_reasons(self.handle))
+                flags = ["Active" if r & b else "Not Active" for _, b in bits]
+                self.lines.append((time.time(), ",".join([str(self.index), str(sm), str(self.max_sm), "0", hex(r)] + flags)))
+            except Exception:
+                pass
+            self._stop.wait(self.NVML_PERIOD_S)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -88,13 +129,17 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         inside = [ln for (t, ln) in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
@@ -118,7 +163,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
-                "window": window}
+                "window": window, "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm

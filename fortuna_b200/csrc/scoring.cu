@@ -162,32 +162,33 @@ __device__ __forceinline__ void warp_bitonic_sort(u64 (&key)[NR], int lane) {
       }
     }
   }
-  // levels k >= NR: the direction of the lane's block is a lane bit; complement instead of reversing
-  bool flipped = false;
+  // levels k >= NR: the direction of the lane's block is a lane bit; complement instead of reversing.  Every such level
+  // is [complement if the direction changes] + [cross-lane stages, the lane mask a loop variable] + [the same in-lane
+  // merge]: ONE rolled loop body (fully unrolled the kernel was ~150 KB of straight-line code and stalled on
+  // instruction fetch, see the key-only kernel below).
+  u64 flipped = 0ull;
+#pragma unroll 1
+  for (int kl = 1; kl <= 32; kl <<= 1) {  // k = kl * NR
+    const u64 want = (kl < 32 && (lane & kl) != 0) ? ~0ull : 0ull;
+    const u64 x = want ^ flipped;
+    flipped = want;
 #pragma unroll
-  for (int k = (NR > 1 ? NR : 2); k <= N; k <<= 1) {
-    const bool want_desc = (k < N) && ((lane & (k / NR)) != 0);
-    if (want_desc != flipped) {
+    for (int r = 0; r < NR; ++r) key[r] ^= x;
+#pragma unroll 1
+    for (int lmask = kl >> 1; lmask > 0; lmask >>= 1) {
+      const bool upper = (lane & lmask) != 0;  // the upper lane of a pair keeps the larger key
 #pragma unroll
-      for (int r = 0; r < NR; ++r) key[r] = ~key[r];
-    }
-    flipped = want_desc;
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= NR) {
-        const int lmask = j / NR;
-        const bool upper = (lane & lmask) != 0;  // the upper lane of a pair keeps the larger key
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          const u64 other = __shfl_xor_sync(0xffffffffu, key[r], lmask);
-          const bool lt = key[r] < other;
-          key[r] = (lt == upper) ? other : key[r];
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < NR; ++r)
-          if ((r & j) == 0) ce_min_first(key[r], key[r | j]);
+      for (int r = 0; r < NR; ++r) {
+        const u64 other = __shfl_xor_sync(0xffffffffu, key[r], lmask);
+        const bool lt = key[r] < other;
+        key[r] = (lt == upper) ? other : key[r];
       }
+    }
+#pragma unroll
+    for (int j = NR >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        if ((r & j) == 0) ce_min_first(key[r], key[r | j]);
     }
   }
 }

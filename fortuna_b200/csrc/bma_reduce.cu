@@ -434,6 +434,163 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
 }
 
 // ------------------------------------------------------------------------------------------------
+// Narrow heads (C <= 16: two moons, MNIST / CIFAR-10 heads, BERT sentiment): a row is a handful of floats, so the
+// warp-per-row machinery above spends its time in 16-lane shuffle reductions and the [S, B, C] tensor is a few tens of
+// MB - latency-sized, not bandwidth-sized.  Here a whole row lives in ONE thread's registers (no shuffles inside a row)
+// and 8 warps share a block of 32 inputs, each taking samples w, w + 8, ...; their partial sums - and the (max,
+// sum-exp) pairs of log_prob - meet in shared memory and are added in stream order.  Same arithmetic per sample as process_rows (log2 units, MUFU.EX2),
+// samples accumulated in 8 interleaved streams instead of one (inside the rtol 1e-5 of the parity tests).
+// ------------------------------------------------------------------------------------------------
+constexpr int kNarrowStreams = 8;  // warps per CTA = interleaved sample streams per input
+
+template <typename T, int CMAX>
+__global__ void __launch_bounds__(32 * kNarrowStreams) bma_reduce_cls_narrow_kernel(const ClsArgs a) {
+  // CTA = 32 consecutive inputs (one per lane) x 8 sample streams (one per warp): a warp's loads of sample s are 32
+  // adjacent rows = one contiguous 32*C*sizeof(T) span.  Partials meet in shared memory and warp 0 adds the streams in
+  // order.
+  __shared__ float part[kNarrowStreams][2 * CMAX + 4][32];
+  const int S = a.S, B = a.B, C = a.C;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
+  const bool valid = b < B;
+  const float scale = a.log_temp ? expf(-a.log_temp[0]) : 1.0f;
+  const float k2 = scale * 1.4426950408889634f;
+  float sp[CMAX], sp2[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) sp[c] = sp2[c] = 0.0f;
+  float spl = 0.0f, sum_l = 0.0f, lmax = -CUDART_INF_F, lsum = 0.0f;
+  int y = -1;
+  if (a.targets && valid) y = a.targets[b];
+  const bool y_ok = (y >= 0) && (y < C);
+  const T* base = reinterpret_cast<const T*>(a.logits);
+  if (valid) {
+    for (int s = w; s < S; s += kNarrowStreams) {
+      const T* rp = base + ((size_t)s * B + b) * C;
+      float z[CMAX];
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        z[c] = -1.0e30f;
+        if (c < C) {
+          float tmp[1];
+          RowLoad<T, 1>::load(rp + c, tmp);
+          z[c] = tmp[0];
+        }
+        m = fmaxf(m, z[c]);
+      }
+      const float ms = (fabsf(m) <= 3.4028234e38f) ? m : 0.0f;
+      const float csh = ms * k2;
+      float sum = 0.0f, set = 0.0f;
+      float zy = 0.0f;  // the target logit, selected without dynamic register indexing
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c == y) zy = z[c];
+        const float u = fmaf(z[c], k2, -csh);
+        const float ev = ex2_approx_ftz(u);
+        z[c] = ev;
+        sum += ev;
+        set = fmaf(ev, u, set);
+      }
+      const float inv = rcp_approx_ftz(sum);
+      const float inv2 = inv * inv;
+      const float l2s = lg2_approx(sum);
+      spl = fmaf(inv, set, spl);
+      sum_l += l2s;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        sp[c] = fmaf(z[c], inv, sp[c]);
+        sp2[c] = fmaf(z[c] * z[c], inv2, sp2[c]);
+      }
+      if (a.targets) {
+        const float ll = 0.6931471805599453f * (fmaf(y_ok ? zy : 0.0f, k2, -csh) - l2s);
+        if (ll > lmax) {
+          lsum = lsum * __expf(lmax - ll) + 1.0f;
+          lmax = ll;
+        } else if (ll > -CUDART_INF_F) {
+          lsum += __expf(ll - lmax);
+        } else if (ll != ll) {
+          lsum = ll;
+        }
+        if (a.out.ensemble_log_prob) a.out.ensemble_log_prob[(size_t)s * B + b] = ll;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    part[w][c][lane] = sp[c];
+    part[w][CMAX + c][lane] = sp2[c];
+  }
+  part[w][2 * CMAX][lane] = spl;
+  part[w][2 * CMAX + 1][lane] = sum_l;
+  part[w][2 * CMAX + 2][lane] = lmax;
+  part[w][2 * CMAX + 3][lane] = lsum;
+  __syncthreads();
+  if (w != 0 || !valid) return;
+  for (int q = 1; q < kNarrowStreams; ++q) {
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      sp[c] += part[q][c][lane];
+      sp2[c] += part[q][CMAX + c][lane];
+    }
+    spl += part[q][2 * CMAX][lane];
+    sum_l += part[q][2 * CMAX + 1][lane];
+    const float om = part[q][2 * CMAX + 2][lane], os = part[q][2 * CMAX + 3][lane];
+    const float M = fmaxf(lmax, om);
+    float acc = 0.0f;
+    if (lsum != lsum || os != os) {
+      acc = CUDART_NAN_F;  // a NaN log-likelihood in either stream poisons the sum, as in the sequential update
+    } else {
+      if (lmax > -CUDART_INF_F) acc += lsum * __expf(lmax - M);
+      if (om > -CUDART_INF_F) acc += os * __expf(om - M);
+    }
+    lmax = M;
+    lsum = acc;
+  }
+  const float Sf = (float)S;
+  const float spl_row = 0.6931471805599453f * (spl - sum_l);
+  float ent_terms = 0.0f, best_v = -CUDART_INF_F;
+  int best_c = 0x7FFFFFFF;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    if (c < C) {
+      const float mean = sp[c] / Sf;
+      const float av = (sp[c] - sp2[c]) / Sf;
+      const float ev = fmaxf(0.0f, __fsub_rn(sp2[c] / Sf, __fmul_rn(mean, mean)));
+      if (mean > 0.0f) ent_terms = fmaf(mean, logf(mean), ent_terms);
+      if (mean > best_v) {
+        best_v = mean;
+        best_c = c;
+      }
+      const size_t o = (size_t)b * C + c;
+      if (a.out.mean) a.out.mean[o] = mean;
+      if (a.out.aleatoric_variance) a.out.aleatoric_variance[o] = av;
+      if (a.out.epistemic_variance) a.out.epistemic_variance[o] = ev;
+      if (a.out.variance) a.out.variance[o] = av + ev;
+      if (a.out.std) a.out.std[o] = sqrtf(av + ev);
+    }
+  }
+  const float ent = -ent_terms;
+  const float alea = -spl_row / Sf;
+  if (a.out.entropy) a.out.entropy[b] = ent;
+  if (a.out.aleatoric_entropy) a.out.aleatoric_entropy[b] = alea;
+  if (a.out.epistemic_entropy) a.out.epistemic_entropy[b] = ent - alea;
+  if (a.out.mode) a.out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
+  if (a.out.log_prob) a.out.log_prob[b] = (lmax + logf(lsum)) - a.log_S;
+}
+
+template <typename T>
+static int launch_cls_narrow(const ClsArgs& a, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a.B + 31) / 32);
+  constexpr int th = 32 * kNarrowStreams;
+  if (a.C <= 2) bma_reduce_cls_narrow_kernel<T, 2><<<grid, th, 0, st>>>(a);
+  else if (a.C <= 4) bma_reduce_cls_narrow_kernel<T, 4><<<grid, th, 0, st>>>(a);
+  else if (a.C <= 8) bma_reduce_cls_narrow_kernel<T, 8><<<grid, th, 0, st>>>(a);
+  else bma_reduce_cls_narrow_kernel<T, 16><<<grid, th, 0, st>>>(a);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Finalise the rows this rank owns from the n_src slots it received (one per source rank, same row layout as
 // above): sums are taken in source-rank order (deterministic), the (max, sumexp) pairs are merged, then the same
 // finalisation as the single-GPU kernel.  One warp per row.
@@ -727,6 +884,10 @@ static int reduce_cls_common(ClsArgs& a, const void* logits, int dtype, const fl
   a.log_S = logf((float)S);
   const size_t esz = dtype == FB200_F32 ? 4 : 2;
   a.bulk_ok = fb200_aligned16(logits) && (((size_t)B * (size_t)C * esz) % 16 == 0);
+  if (C <= 16 && !a.partial_mode) {
+    if (dtype == FB200_F32) return launch_cls_narrow<float>(a, (cudaStream_t)stream);
+    return launch_cls_narrow<__nv_bfloat16>(a, (cudaStream_t)stream);
+  }
   if (dtype == FB200_F32) return dispatch_cls<float>(a, (cudaStream_t)stream);
   return dispatch_cls<__nv_bfloat16>(a, (cudaStream_t)stream);
 }

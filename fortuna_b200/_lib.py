@@ -114,7 +114,7 @@ SIGNATURES = {
     "fb200_last_layer_logits": (_i, [_P, _P, _P, _P, _P, _i, _P, _i, _i, _i, _i, _i, _i, _i, _i, _P]),
     "fb200_last_layer_ex_workspace_bytes": (_sz, [_i, _i, _i]),
     "fb200_last_layer_logits_ex": (_i, [_P, _P, _P, _P, _P, _i, _P, _i, _i, _i, _i, _i, _i, _i, _i, _P, _P, _sz, _P]),
-    "fb200_softmax_rows": (_i, [_P, _i, _i64, _i, _i, _P, _P]),
+    "fb200_softmax_rows": (_i, [_P, _i, _i64, _i, _i, _P, _P, _P]),
     "fb200_log_prob_from_lse": (_i, [_P, _i, _P, _P, _i, _i, _i, _P, _P, _P]),
     "fb200_transpose_w_bf16": (_i, [_P, _i, _P, _i, _i, _i, _P]),
     "fb200_bma_reduce_cls": (_i, [_P, _i, _P, _P, _i, _i, _i, C.POINTER(ClsOutputs), _P]),
@@ -131,6 +131,8 @@ SIGNATURES = {
     "fb200_ece_bins": (_i, [_P, _i, _i, _P, _P, _P, _i, _P, _P, _P, _P, _P, _P]),
     "fb200_ece_from_bins": (_i, [_P, _P, _P, _i, _i64, _P, _P]),
     "fb200_quantile_axis0": (_i, [_P, _i, _i64, _P, _i, _P, _P]),
+    "fb200_calib_cls_workspace_bytes": (_sz, [_i, _i]),
+    "fb200_calib_cls_loss_terms": (_i, [_P, _i, _P, _P, _i, _i, _i, _P, _sz, _P, _P]),
     "fb200_cls_sample_targets": (_i, [_P, _P, _P, _i, _i, _i, _i, _P, _P, _P]),
     "fb200_reg_mc_entropies": (_i, [_P, _P, _P, _P, _i, _i, _i, _i, _i, _P, _P, _P, _P]),
     "fb200_conformal_bayes_workspace_bytes": (_sz, [_i, _i, _i]),

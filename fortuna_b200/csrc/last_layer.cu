@@ -178,24 +178,27 @@ static int launch_simt(const void* x, const void* w, const float* bias, const fl
 // optionally z <- softmax / log_softmax in place.  One warp per row.
 template <typename TO>
 __global__ void __launch_bounds__(256) row_lse_kernel(TO* __restrict__ z, int64_t rows, int C, int epi,
-                                                      float* __restrict__ lse_out) {
+                                                      float* __restrict__ lse_out, const float* __restrict__ log_temp) {
   const int lane = threadIdx.x & 31;
+  const float scale = log_temp ? expf(-log_temp[0]) : 1.0f;  // temperature scaler: statistics of z * exp(-log_temp)
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = warp0; r < rows; r += nwarps) {
     TO* row = z + r * C;
     float m = -INFINITY;
-    for (int c = lane; c < C; c += 32) m = fmaxf(m, (float)row[c]);
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, (float)row[c] * scale);
     m = group_max<32>(m);
     float s = 0.0f;
-    for (int c = lane; c < C; c += 32) s += __expf((float)row[c] - m);
+    for (int c = lane; c < C; c += 32) s += __expf((float)row[c] * scale - m);
     s = group_sum<32>(s);
     const float lse = m + __logf(s);
     if (lane == 0 && lse_out) lse_out[r] = lse;
     if (epi == 1) {
-      for (int c = lane; c < C; c += 32) row[c] = (TO)__expf((float)row[c] - lse);
+      for (int c = lane; c < C; c += 32) row[c] = (TO)__expf((float)row[c] * scale - lse);
     } else if (epi == 2) {
-      for (int c = lane; c < C; c += 32) row[c] = (TO)((float)row[c] - lse);
+      for (int c = lane; c < C; c += 32) row[c] = (TO)((float)row[c] * scale - lse);
+    } else if (log_temp) {
+      for (int c = lane; c < C; c += 32) row[c] = (TO)((float)row[c] * scale);  // calibrated logits in place
     }
   }
 }
@@ -303,27 +306,29 @@ extern "C" int fb200_last_layer_logits_ex(const void* x, const void* w, const fl
   int64_t blocks = (rows + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (out_dtype == FB200_F32)
-    row_lse_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<float*>(out), rows, C, epilogue, lse_out);
+    row_lse_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<float*>(out), rows, C, epilogue, lse_out, nullptr);
   else
     row_lse_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(out), rows, C,
-                                                                     epilogue, lse_out);
+                                                                     epilogue, lse_out, nullptr);
   FB200_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int fb200_softmax_rows(void* z, int dtype, int64_t rows, int C, int epilogue, float* lse_out, void* stream) {
+extern "C" int fb200_softmax_rows(void* z, int dtype, int64_t rows, int C, int epilogue, const float* log_temp,
+                                  float* lse_out, void* stream) {
   if (!z) return FB200_E_NULL;
   if (rows <= 0 || C <= 0) return FB200_E_SHAPE;
   if (epilogue < FB200_EPI_LOGITS || epilogue > FB200_EPI_LOG_SOFTMAX) return FB200_E_UNSUPPORTED;
-  if (epilogue == FB200_EPI_LOGITS && !lse_out) return FB200_E_NULL;
+  if (epilogue == FB200_EPI_LOGITS && !lse_out && !log_temp) return FB200_E_NULL;
   int64_t blocks = (rows + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FB200_F32)
-    row_lse_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<float*>(z), rows, C, epilogue, lse_out);
+    row_lse_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<float*>(z), rows, C, epilogue, lse_out,
+                                                            log_temp);
   else if (dtype == FB200_BF16)
     row_lse_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(z), rows, C,
-                                                                     epilogue, lse_out);
+                                                                     epilogue, lse_out, log_temp);
   else
     return FB200_E_UNSUPPORTED;
   FB200_LAUNCH_CHECK();

@@ -590,6 +590,22 @@ def reg_sample_targets(outputs, key, n_target_samples, log_temp=None, want_idx=F
     return (y, idx) if want_idx else y
 
 
+def calib_cls_loss_terms(logits, targets, log_temp=None):
+    """logits [S,B,C] (uncalibrated), targets int32 [B], log_temp float32 [1] -> float64 [2, S]:
+    row 0 = sum_b log softmax(exp(-log_temp) z[s,b])[y_b], row 1 = its derivative with respect to exp(-log_temp)."""
+    S, B, Cn = logits.shape
+    nbytes = int(lib().fb200_calib_cls_workspace_bytes(S, B))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=logits.device)
+    out = torch.empty((2, S), dtype=torch.float64, device=logits.device)
+    check(
+        lib().fb200_calib_cls_loss_terms(_ptr(logits, (torch.float32, torch.bfloat16)), _DT[logits.dtype],
+                                         _ptr(targets, torch.int32), _ptr(log_temp, torch.float32, True), S, B, Cn,
+                                         _ptr(ws), nbytes, _ptr(out), _stream()),
+        "fb200_calib_cls_loss_terms",
+    )
+    return out
+
+
 def cls_sample_targets(logits, key, n_target_samples, log_temp=None, want_idx=False):
     """logits [n_stored, B, C] -> y int32 [T, B] (and the drawn posterior-sample indices int32 [T])."""
     n, B, Cn = logits.shape
@@ -701,15 +717,16 @@ def conformal_bayes_sets(ell_train, lsm_test, error, want_counts=False, want_ess
     return out
 
 
-def softmax_rows_(z, epilogue=EPI_LOG_SOFTMAX, want_lse=False):
-    """In place over the last axis of a float32 / bf16 CUDA tensor: softmax or log_softmax (or EPI_LOGITS: leave z,
-    only return the row logsumexp) - the row pass fb200_last_layer_logits_ex uses off the tcgen05 path."""
+def softmax_rows_(z, epilogue=EPI_LOG_SOFTMAX, want_lse=False, log_temp=None):
+    """In place over the last axis of a float32 / bf16 CUDA tensor: softmax or log_softmax of z * exp(-log_temp) (or
+    EPI_LOGITS: the calibrated logits themselves, plus the row logsumexp) - the row pass fb200_last_layer_logits_ex uses
+    off the tcgen05 path."""
     Cn = z.shape[-1]
     rows = z.numel() // Cn
     lse = torch.empty(z.shape[:-1], dtype=torch.float32, device=z.device) if want_lse else None
     check(
         lib().fb200_softmax_rows(_ptr(z, (torch.float32, torch.bfloat16)), _DT[z.dtype], rows, Cn, int(epilogue),
-                                 _ptr(lse, torch.float32, True), _stream()),
+                                 _ptr(log_temp, torch.float32, True), _ptr(lse, torch.float32, True), _stream()),
         "fb200_softmax_rows",
     )
     return (z, lse) if want_lse else z

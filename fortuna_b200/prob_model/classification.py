@@ -14,6 +14,8 @@ from typing import Optional
 import torch
 
 from ..utils.random import RandomNumberGenerator
+from .calib_config import CalibConfig
+from .calibration import ClassificationTemperatureScaler, calibrate_temperature
 from .fit_config import FitConfig
 from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_approximator import CyclicalSGLDPosteriorApproximator
 from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_posterior import CyclicalSGLDPosterior
@@ -25,13 +27,15 @@ from .prior import IsotropicGaussianPrior
 
 
 class ProbClassifier:
-    def __init__(self, model: torch.nn.Module, prior=None, posterior_approximator=None, output_calibrator=None,
-                 model_editor=None, seed: int = 0, device="cuda"):
+    def __init__(self, model: torch.nn.Module, prior=None, posterior_approximator=None,
+                 output_calibrator="default", model_editor=None, seed: int = 0, device="cuda"):
         if model_editor is not None:
             raise NotImplementedError("model editors are outside the hot path")
-        if output_calibrator is not None:
-            raise NotImplementedError("training an output calibrator is outside the hot path; a fixed temperature can be "
-                                      "passed to the predictive (log_temp)")
+        if output_calibrator == "default":  # the reference's default (classification.py:60)
+            output_calibrator = ClassificationTemperatureScaler()
+        if output_calibrator is not None and not isinstance(output_calibrator, ClassificationTemperatureScaler):
+            raise NotImplementedError("only the default ClassificationTemperatureScaler (or None) is supported")
+        self.output_calibrator = output_calibrator
         self.model = model
         self.prior = prior if prior is not None else IsotropicGaussianPrior()
         self.posterior_approximator = posterior_approximator if posterior_approximator is not None else SGHMCPosteriorApproximator()
@@ -64,7 +68,33 @@ class ProbClassifier:
         self.posterior = cls(bound, self.prior, self.posterior_approximator, self.rng)
         status = {"fit_status": self.posterior.fit(train_data_loader, val_data_loader, fit_config)}
         self.predictive = ClassificationPredictive(self.posterior)
-        # calib_data_loader: the default temperature scaler's training is outside the hot path; log_temp stays 0
+        if calib_data_loader is not None:  # fortuna/prob_model/base.py:94-105
+            status["calib_status"] = self.calibrate(calib_data_loader, val_data_loader, calib_config)
+        return status
+
+    def calibrate(self, calib_data_loader, val_data_loader=None, calib_config: Optional[CalibConfig] = None):
+        """fortuna/prob_model/base.py:109-235 for the temperature scaler: the ensemble of outputs on the calibration data
+        is computed once, log_temp is fitted on it (fb200_calib_cls_loss_terms per step), and every later predictive call
+        uses the fitted temperature."""
+        if self.output_calibrator is None:
+            return None  # "Nothing to calibrate. No calibrator was passed to the probabilistic model."
+        if self.posterior is None:
+            raise ValueError("Before calibration, you must either train the probabilistic model or load a state from an "
+                             "existing checkpoint.")
+        cfg = calib_config or CalibConfig()
+        S = cfg.processor.n_posterior_samples
+        self.predictive.log_temp = None  # the ensemble is UNcalibrated outputs
+        key = self.rng.get()
+        z = self.predictive.sample_calibrated_outputs(calib_data_loader.to_inputs_loader(), S, rng=key).float().contiguous()
+        zv = tv = None
+        if val_data_loader is not None:
+            zv = self.predictive.sample_calibrated_outputs(val_data_loader.to_inputs_loader(), S, rng=key).float().contiguous()
+            tv = val_data_loader.to_array_targets()
+        bs = getattr(calib_data_loader, "_batch_size", None) or z.shape[1]
+        vbs = (getattr(val_data_loader, "_batch_size", None) or zv.shape[1]) if zv is not None else None
+        status, log_temp = calibrate_temperature(z, calib_data_loader.to_array_targets(), bs, cfg, zv, tv, vbs)
+        self.predictive.log_temp = torch.from_numpy(log_temp).to(self.device)
+        self.posterior.log_temp = self.predictive.log_temp
         return status
 
     # ------------------------------------------------------------------ state on disk (fortuna/prob_model/base.py:236-261)

@@ -57,8 +57,8 @@ class ClassificationPredictive:
             self._stored_logits_cache = (key, torch.stack(outs).contiguous())
         stored = self._stored_logits_cache[1]
         z = stored.index_select(0, idx.long()).contiguous()
-        if self.log_temp is not None:
-            raise NotImplementedError("temperature scaling of a full-network posterior goes through the reduction kernels' log_temp")
+        if self.log_temp is not None:  # ClassificationTemperatureScaler: logits * exp(-log_temp), in place on the copy
+            ops.softmax_rows_(z, ops.EPI_LOGITS, log_temp=self.log_temp)
         return z
 
     def _reduce(self, inputs_loader, names, n_posterior_samples, rng, targets=None):

@@ -186,9 +186,11 @@ int fb200_last_layer_logits_ex(const void* x, const void* w, const float* bias, 
                                const int32_t* sample_idx, int n_stored, void* out, int S, int B, int D, int C,
                                int in_dtype, int out_dtype, int w_layout, int epilogue, float* lse_out,
                                void* workspace, size_t workspace_bytes, void* stream);
-/* The row pass on its own, in place on z[rows, C]: softmax / log_softmax per epilogue (FB200_EPI_LOGITS leaves z and only
- * fills lse_out, which is then required); lse_out optional float32 [rows]. */
-int fb200_softmax_rows(void* z, int dtype, int64_t rows, int C, int epilogue, float* lse_out, void* stream);
+/* The row pass on its own, in place on z[rows, C]: softmax / log_softmax per epilogue of z * exp(-log_temp) (log_temp
+ * optional device float[1], the temperature scaler); FB200_EPI_LOGITS leaves the logits - multiplied by exp(-log_temp)
+ * when log_temp is given - and fills lse_out; lse_out optional float32 [rows]. */
+int fb200_softmax_rows(void* z, int dtype, int64_t rows, int C, int epilogue, const float* log_temp, float* lse_out,
+                       void* stream);
 /* ll[s,b] = logits[s,b,targets[b]] - lse[s,b];  ensemble_log_prob[S,B] = ll (optional);
  * log_prob[B] = logsumexp_s ll - log S (optional)  (fortuna/prob_model/predictive/base.py:104-128, 179-203).
  * logits: [S,B,C] calibrated logits (dtype FB200_F32 / FB200_BF16), lse: float32 [S,B] from the call above. */
@@ -319,6 +321,16 @@ int fb200_quantile_sorted(const float* x_sorted, int64_t n, const float* q, int 
 /* jnp.quantile(x, q, axis=0) for x[T, M] (T <= 256), method="linear": out[nq, M]
  * (RegressionPredictive.quantile over the target-sample axis, fortuna/prob_model/predictive/regression.py:331-369). */
 int fb200_quantile_axis0(const float* x, int T, int64_t M, const float* q, int nq, float* out, void* stream);
+
+/* Calibration of ClassificationTemperatureScaler (fortuna/output_calibrator/classification.py:7-17) over a fixed ensemble
+ * of outputs - the loss ProbModelOutputCalibrator minimises (fortuna/prob_model/prob_model_calibrator.py:30-61,
+ * fortuna/prob_model/predictive/base.py:205-287): with tau = exp(-log_temp) and ll[s,b] = log softmax(tau z[s,b])[y_b],
+ * out[s] = L_s = sum_b ll[s,b] and out[S + s] = dL_s/dtau = sum_b (z_y - sum_c p_c z_c), float64, one pass over
+ * [S,B,C].  The caller forms loss = -(logsumexp_s((n_data / B) L_s) - log S) and its derivative by the scalar chain
+ * rule.  logits: [S,B,C] UNcalibrated (dtype FB200_F32 / FB200_BF16); out: double[2S]. */
+size_t fb200_calib_cls_workspace_bytes(int S, int B);
+int fb200_calib_cls_loss_terms(const void* logits, int dtype, const int32_t* targets, const float* log_temp, int S,
+                               int B, int C, void* workspace, size_t workspace_bytes, double* out, void* stream);
 
 /* Target samples of the classification predictive - Predictive.sample (fortuna/prob_model/predictive/base.py:318-440)
  * -> ClassificationProbOutputLayer.sample (fortuna/prob_output_layer/classification.py:33-51), the reference's draws:

@@ -257,3 +257,48 @@ def test_cls_sample_targets_follow_the_predictive_distribution(cuda):
     y = ops.cls_sample_targets(z, ops.PRNGKey(5, cuda), 16)
     freq = torch.bincount(y.reshape(-1).long(), minlength=4).float() / y.numel()
     np.testing.assert_allclose(freq.cpu().numpy(), P.softmax(np.array([[0.0, 1.0, 2.0, -1.0]], np.float32))[0], atol=0.01)
+
+
+@pytest.mark.parametrize("S,B,C,dtype", [(5, 40, 7, torch.float32), (30, 1000, 10, torch.float32), (3, 257, 1000, torch.float32),
+                                         (4, 64, 2, torch.bfloat16)])
+@pytest.mark.parametrize("lt", [0.0, 0.7])
+def test_calib_loss_terms_match_oracle(cuda, S, B, C, dtype, lt):
+    """fb200_calib_cls_loss_terms: per-sample log-likelihood sums under the temperature scaler and their derivative in
+    tau = exp(-log_temp) (float64 outputs) against the float64 oracle; then the host chain rule against finite
+    differences of the oracle loss."""
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.calibration import loss_and_grad
+    from oracle import calibration as Cal
+
+    r = np.random.default_rng(S + C)
+    z = (3 * r.standard_normal((S, B, C))).astype(np.float32)
+    y = r.integers(0, C, B).astype(np.int32)
+    zt = torch.from_numpy(z).to(cuda).to(dtype)
+    z_used = zt.float().cpu().numpy()
+    tt = torch.from_numpy(y).to(cuda)
+    ltt = torch.tensor([lt], dtype=torch.float32, device=cuda)
+    got = ops.calib_cls_loss_terms(zt, tt, ltt).cpu().numpy()
+    L, dL = Cal.calib_terms(z_used, y, np.float32(lt))
+    np.testing.assert_allclose(got[0], L, rtol=2e-6, atol=1e-3)
+    np.testing.assert_allclose(got[1], dL, rtol=2e-5, atol=2e-3)
+    loss, g = loss_and_grad(zt, tt, np.float32(lt), n_data=3 * B)
+    np.testing.assert_allclose(loss, Cal.calib_loss(z_used, y, np.float32(lt), 3 * B), rtol=1e-5)
+    h = 1e-4
+    fd = (Cal.calib_loss(z_used, y, lt + h, 3 * B) - Cal.calib_loss(z_used, y, lt - h, 3 * B)) / (2 * h)
+    np.testing.assert_allclose(g, fd, rtol=2e-3, atol=1e-3)
+
+
+def test_calibrate_temperature_recovers_the_generating_temperature(cuda):
+    """Over-confident logits (true logits x 3): Adam on the kernel's loss drives log_temp to log 3 and the NLL down."""
+    from fortuna_b200.prob_model import Adam, CalibConfig, CalibOptimizer
+    from fortuna_b200.prob_model.calibration import calibrate_temperature
+
+    r = np.random.default_rng(2)
+    z_true = 2 * r.standard_normal((1, 6000, 5))
+    p = P.softmax(z_true[0].astype(np.float32)).astype(np.float64)
+    y = np.array([r.choice(5, p=pi / pi.sum()) for pi in p])
+    z = torch.from_numpy(np.repeat(3.0 * z_true, 4, axis=0).astype(np.float32)).to(cuda)  # 4 identical "samples"
+    status, log_temp = calibrate_temperature(z, y, batch_size=2000, calib_config=CalibConfig(
+        optimizer=CalibOptimizer(method=Adam(5e-2), n_epochs=60)), z_val=z[:, :1000].contiguous(), targets_val=y[:1000])
+    assert status["loss"].shape == (60,) and status["val_loss"].shape == (60,)
+    assert status["loss"][-1] < status["loss"][0] and abs(float(log_temp[0]) - np.log(3.0)) < 0.12

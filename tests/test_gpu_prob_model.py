@@ -277,3 +277,37 @@ def test_predictive_sample_classification(cuda):
         want.append(P.cls_sample_targets(stored, ops.key_to_host(key), 5)[0])
     assert np.array_equal(y.cpu().numpy(), np.concatenate(want, axis=1))
     assert float((y[0].cpu() == torch.as_tensor(test[1])).float().mean()) > 0.9  # a trained model mostly samples the label
+
+
+def test_train_with_calibration_loader(cuda):
+    """ProbClassifier.train(calib_data_loader=...) fits the default temperature scaler on a fixed ensemble
+    (fortuna/prob_model/base.py:94-235); afterwards every predictive statistic uses the fitted temperature."""
+    from fortuna_b200.prob_model import (
+        Adam, CalibConfig, CalibOptimizer, CalibProcessor, FitConfig, FitOptimizer, ProbClassifier, SGHMCPosteriorApproximator,
+    )
+    from oracle import predictive as P
+
+    MLP, train, test, train_loader, test_loader = _setup()
+    torch.manual_seed(0)
+    pm = ProbClassifier(model=MLP(), posterior_approximator=SGHMCPosteriorApproximator(
+        n_samples=8, n_thinning=5, burnin_length=150, step_schedule=1e-3), seed=0)
+    status = pm.train(train_loader, val_data_loader=test_loader, calib_data_loader=test_loader,
+                      fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=60)),
+                      calib_config=CalibConfig(optimizer=CalibOptimizer(Adam(1e-2), n_epochs=15), processor=CalibProcessor(10)))
+    cs = status["calib_status"]
+    assert cs["loss"].shape == (15,) and cs["val_loss"].shape == (15,) and cs["loss"][-1] <= cs["loss"][0]
+    lt = pm.predictive.log_temp
+    assert lt is not None and lt.shape == (1,) and float(lt.abs()[0]) > 0
+    key = pm.rng.get()
+    inputs = test_loader.to_inputs_loader()
+    z = pm.predictive.sample_calibrated_outputs(inputs, 12, rng=key)
+    keep, pm.predictive.log_temp = pm.predictive.log_temp, None
+    z_raw = pm.predictive.sample_calibrated_outputs(inputs, 12, rng=key)
+    pm.predictive.log_temp = keep
+    np.testing.assert_allclose(z.cpu().numpy(), z_raw.cpu().numpy() * np.exp(-lt.cpu().numpy()[0]), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(pm.predictive.mean(inputs, 12, rng=key).cpu().numpy(), P.cls_mean(z.cpu().numpy()), rtol=1e-5, atol=1e-8)
+    # no calibrator: nothing to calibrate
+    pm2 = ProbClassifier(model=MLP(), output_calibrator=None, posterior_approximator=SGHMCPosteriorApproximator(
+        n_samples=2, n_thinning=2, burnin_length=2, step_schedule=1e-3))
+    st2 = pm2.train(train_loader, calib_data_loader=test_loader, fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=2)))
+    assert st2["calib_status"] is None and pm2.predictive.log_temp is None

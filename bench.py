@@ -398,8 +398,24 @@ def run_gpu_arm(args):
             line["extras"]["last_layer_gemm"] = last_layer_extras(dev, tfb, tfs)
         except Exception as exc:  # extras never invalidate the headline
             line["extras"] = {"error": repr(exc)}
+    if world > 1 and not args.no_extras:
+        # SG-MCMC chains: one per GPU, different seeds, NO collective - every rank steps its own
+        # BERT-base-shaped chain, the slowest rank sets the time, the aggregate is world x updates/s
+        try:
+            from fortuna_b200.bench_extras import sampler_extras
+
+            ex = sampler_extras(dev, peak, seed=rank, only=("identity",))["sghmc_identity"]
+            tt = torch.tensor([ex["ms_per_step"]], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt[0])
+            line["extras"] = {"sghmc_chains": {
+                "chains": world, "n_params_per_chain": ex["n_params"], "ms_per_step_max_over_ranks": ms,
+                "param_updates_per_s": world * ex["n_params"] / (ms * 1e-3), "collectives": 0,
+                "hbm_frac_per_gpu": 20 * ex["n_params"] / (ms * 1e-3) / 1e9 / peak}}
+        except Exception as exc:
+            line["extras"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, ms, cores, sample = cpu_reference_throughput(args.cpu_rows_per_core, 1, 0)
+        v, ms, cores, sample = cpu_reference_throughput(args.cpu_rows_per_core, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
         print(json.dumps(line), flush=True)

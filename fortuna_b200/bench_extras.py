@@ -11,7 +11,7 @@ from .prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
 from .utils.flat_tree import FlatTree
 
 
-def sampler_extras(device, hbm_peak_gbs, steps=20, warmup=3):
+def sampler_extras(device, hbm_peak_gbs, steps=20, warmup=3, seed=0, only=None):
     import sys, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     if root not in sys.path:
@@ -25,7 +25,9 @@ def sampler_extras(device, hbm_peak_gbs, steps=20, warmup=3):
     grad.flat.normal_(0.0, 0.01)
     n = params.n_params
     for name, pre, bytes_per in (("identity", pc.identity_preconditioner(), 20), ("rmsprop", pc.rmsprop_preconditioner(), 28)):
-        tx = sghmc_integrator(0.01, None, ops.PRNGKey(0, device), sched.constant_schedule(4e-6), pre)
+        if only is not None and name not in only:
+            continue
+        tx = sghmc_integrator(0.01, None, ops.PRNGKey(seed, device), sched.constant_schedule(4e-6), pre)
         state = tx.init(params)
         for _ in range(warmup):
             params, state = tx.apply(params, grad, state)

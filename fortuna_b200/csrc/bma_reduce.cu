@@ -85,6 +85,9 @@ struct RowLoad<__nv_bfloat16, 1> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&z)[1]) { z[0] = __bfloat162float(*p); }
 };
 
+__device__ __forceinline__ void st_f4(float* p, float x, float y, float z, float w) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 __device__ __forceinline__ float ex2_approx_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -400,13 +403,23 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
         }
         if (valid_row) {
           const size_t o = (size_t)b * C + c0;
+          if constexpr (VEC == 4) {
+            // C % 4 == 0 and 16-byte aligned outputs (checked on the host): one 128-bit store per output
+            if (a.out.mean) st_f4(a.out.mean + o, mean[0], mean[1], mean[2], mean[3]);
+            if (a.out.aleatoric_variance) st_f4(a.out.aleatoric_variance + o, av[0], av[1], av[2], av[3]);
+            if (a.out.epistemic_variance) st_f4(a.out.epistemic_variance + o, ev[0], ev[1], ev[2], ev[3]);
+            if (a.out.variance) st_f4(a.out.variance + o, av[0] + ev[0], av[1] + ev[1], av[2] + ev[2], av[3] + ev[3]);
+            if (a.out.std)
+              st_f4(a.out.std + o, sqrtf(av[0] + ev[0]), sqrtf(av[1] + ev[1]), sqrtf(av[2] + ev[2]), sqrtf(av[3] + ev[3]));
+          } else {
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            if (a.out.mean) a.out.mean[o + k] = mean[k];
-            if (a.out.aleatoric_variance) a.out.aleatoric_variance[o + k] = av[k];
-            if (a.out.epistemic_variance) a.out.epistemic_variance[o + k] = ev[k];
-            if (a.out.variance) a.out.variance[o + k] = av[k] + ev[k];
-            if (a.out.std) a.out.std[o + k] = sqrtf(av[k] + ev[k]);
+            for (int k = 0; k < VEC; ++k) {
+              if (a.out.mean) a.out.mean[o + k] = mean[k];
+              if (a.out.aleatoric_variance) a.out.aleatoric_variance[o + k] = av[k];
+              if (a.out.epistemic_variance) a.out.epistemic_variance[o + k] = ev[k];
+              if (a.out.variance) a.out.variance[o + k] = av[k] + ev[k];
+              if (a.out.std) a.out.std[o + k] = sqrtf(av[k] + ev[k]);
+            }
           }
         }
       }
@@ -884,6 +897,10 @@ static int reduce_cls_common(ClsArgs& a, const void* logits, int dtype, const fl
   a.log_S = logf((float)S);
   const size_t esz = dtype == FB200_F32 ? 4 : 2;
   a.bulk_ok = fb200_aligned16(logits) && (((size_t)B * (size_t)C * esz) % 16 == 0);
+  if (C % 4 == 0 && !(fb200_aligned16(a.out.mean) && fb200_aligned16(a.out.aleatoric_variance) &&
+                      fb200_aligned16(a.out.epistemic_variance) && fb200_aligned16(a.out.variance) &&
+                      fb200_aligned16(a.out.std)))
+    return FB200_E_ALIGN;  // [B,C] outputs are written with 128-bit stores when C % 4 == 0
   if (C <= 16 && !a.partial_mode) {
     if (dtype == FB200_F32) return launch_cls_narrow<float>(a, (cudaStream_t)stream);
     return launch_cls_narrow<__nv_bfloat16>(a, (cudaStream_t)stream);

@@ -8,7 +8,7 @@
 //   dd = <d, d>, gg = <g_i, g_j>, gid = <g_i, d>, gjd = <g_j, d>,  d = x_i - x_j
 // (vmap over j inside a lax.scan over i).  dd / gg are symmetric and gid(j, i) = -gjd(i, j), so only sample tiles
 // ti <= tj are accumulated: a 64 x 64 pair tile per CTA (32 x 32 for chains of <= 32 samples), 4 x 4 (2 x 2) pairs x 4 sums per thread in registers, the samples'
-// columns staged through shared memory 32 at a time; N is split over CTAs (each split writes its own partial, summed
+// columns staged through shared memory 32 at a time (LDGSTS, double-buffered); N is split over CTAs (each split writes its own partial, summed
 // in split order - no float atomics, run-to-run identical).  Differences are formed explicitly: the Gram-matrix
 // shortcut (|x_i|^2 + |x_j|^2 - 2 <x_i, x_j> on tensor cores) cancels catastrophically for SG-MCMC samples, which sit
 // close together relative to their norms.  A second kernel turns the sums into k0 in double precision and adds them
@@ -39,11 +39,19 @@ struct KsdArgs {
   float* partial;  // [n_splits][S][S][4]  (dd, gg, gid, gjd) for pairs in tiles ti <= tj
 };
 
+// 4-byte asynchronous copy global -> shared (LDGSTS); src_bytes = 0 writes zeros (rows / columns past the end)
+__device__ __forceinline__ void cp_async4_zfill(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
 template <int KSD_T>  // samples per tile side: 64 (4 x 4 pairs per thread) or 32 (2 x 2; chains of <= 32 samples)
 __global__ void __launch_bounds__(KSD_THREADS) ksd_pair_sums_kernel(const KsdArgs a) {
   constexpr int TP = KSD_T / 16;
-  __shared__ __align__(16) float sx[2][KSD_KC][KSD_T + 4];  // [I | J][column][sample]; rows 16-byte aligned
-  __shared__ __align__(16) float sg[2][KSD_KC][KSD_T + 4];
+  constexpr int ROW = KSD_T + 4;                 // floats per staged column; rows 16-byte aligned
+  constexpr int ARR = KSD_KC * ROW;              // one [column][sample] array
+  extern __shared__ __align__(16) float ksd_smem[];  // [2 buffers][x_I | g_I | x_J | g_J][KSD_KC][ROW]
   // tile index -> (ti, tj), ti <= tj
   int t = blockIdx.x, ti = 0;
   while (t >= a.n_tiles_side - ti) {
@@ -62,37 +70,57 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_pair_sums_kernel(const KsdArg
 #pragma unroll
     for (int j = 0; j < TP; ++j) dd[i][j] = gg[i][j] = gid[i][j] = gjd[i][j] = 0.0f;
 
-  for (int64_t nb = n0; nb < n1; nb += KSD_KC) {
-    // stage [64 samples][32 columns] of both tiles: a warp reads 32 consecutive columns of one sample
+  // stage [KSD_T samples][32 columns] of both tiles, transposed to [column][sample]: a warp reads 32 consecutive
+  // columns of one sample (one 128-byte line); the copies are asynchronous so stage k + 1 lands while k is consumed
+  auto stage = [&](int buf, int64_t nb) {
+    float* base = ksd_smem + (size_t)buf * 4 * ARR;
     for (int e = tid; e < KSD_T * KSD_KC; e += KSD_THREADS) {
       const int s = e / KSD_KC, c = e % KSD_KC;
       const int64_t col = nb + c;
       const int si = ti * KSD_T + s, sj = tj * KSD_T + s;
       const bool okc = col < n1;
       const bool oki = okc && si < a.S, okj = okc && sj < a.S;
-      sx[0][c][s] = oki ? a.x[(int64_t)si * a.stride + col] : 0.0f;
-      sg[0][c][s] = oki ? a.g[(int64_t)si * a.stride + col] : 0.0f;
-      sx[1][c][s] = okj ? a.x[(int64_t)sj * a.stride + col] : 0.0f;
-      sg[1][c][s] = okj ? a.g[(int64_t)sj * a.stride + col] : 0.0f;
+      const int64_t oi = oki ? (int64_t)si * a.stride + col : 0, oj = okj ? (int64_t)sj * a.stride + col : 0;
+      float* d = base + (size_t)c * ROW + s;
+      cp_async4_zfill(d, a.x + oi, oki);
+      cp_async4_zfill(d + ARR, a.g + oi, oki);
+      cp_async4_zfill(d + 2 * ARR, a.x + oj, okj);
+      cp_async4_zfill(d + 3 * ARR, a.g + oj, okj);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  if (n0 < n1) stage(0, n0);
+  for (int64_t nb = n0; nb < n1; nb += KSD_KC, buf ^= 1) {
+    if (nb + KSD_KC < n1) {
+      stage(buf ^ 1, nb + KSD_KC);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const float* sxI = ksd_smem + (size_t)buf * 4 * ARR;
+    const float* sgI = sxI + ARR;
+    const float* sxJ = sxI + 2 * ARR;
+    const float* sgJ = sxI + 3 * ARR;
 #pragma unroll 4
     for (int c = 0; c < KSD_KC; ++c) {
       float xi[TP], gi[TP], xj[TP], gj[TP];
       if constexpr (TP == 4) {
-        const float4 a4 = *reinterpret_cast<const float4*>(&sx[0][c][pi]);
-        const float4 b4 = *reinterpret_cast<const float4*>(&sg[0][c][pi]);
-        const float4 c4 = *reinterpret_cast<const float4*>(&sx[1][c][pj]);
-        const float4 d4 = *reinterpret_cast<const float4*>(&sg[1][c][pj]);
+        const float4 a4 = *reinterpret_cast<const float4*>(sxI + c * ROW + pi);
+        const float4 b4 = *reinterpret_cast<const float4*>(sgI + c * ROW + pi);
+        const float4 c4 = *reinterpret_cast<const float4*>(sxJ + c * ROW + pj);
+        const float4 d4 = *reinterpret_cast<const float4*>(sgJ + c * ROW + pj);
         xi[0] = a4.x; xi[1] = a4.y; xi[2] = a4.z; xi[3] = a4.w;
         gi[0] = b4.x; gi[1] = b4.y; gi[2] = b4.z; gi[3] = b4.w;
         xj[0] = c4.x; xj[1] = c4.y; xj[2] = c4.z; xj[3] = c4.w;
         gj[0] = d4.x; gj[1] = d4.y; gj[2] = d4.z; gj[3] = d4.w;
       } else {
-        const float2 a2 = *reinterpret_cast<const float2*>(&sx[0][c][pi]);
-        const float2 b2 = *reinterpret_cast<const float2*>(&sg[0][c][pi]);
-        const float2 c2 = *reinterpret_cast<const float2*>(&sx[1][c][pj]);
-        const float2 d2 = *reinterpret_cast<const float2*>(&sg[1][c][pj]);
+        const float2 a2 = *reinterpret_cast<const float2*>(sxI + c * ROW + pi);
+        const float2 b2 = *reinterpret_cast<const float2*>(sgI + c * ROW + pi);
+        const float2 c2 = *reinterpret_cast<const float2*>(sxJ + c * ROW + pj);
+        const float2 d2 = *reinterpret_cast<const float2*>(sgJ + c * ROW + pj);
         xi[0] = a2.x; xi[1] = a2.y; gi[0] = b2.x; gi[1] = b2.y;
         xj[0] = c2.x; xj[1] = c2.y; gj[0] = d2.x; gj[1] = d2.y;
       }
@@ -107,7 +135,7 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_pair_sums_kernel(const KsdArg
           gjd[i][j] = fmaf(gj[j], d, gjd[i][j]);
         }
     }
-    __syncthreads();
+    __syncthreads();  // everyone is done with `buf` before the next iteration's copies overwrite it
   }
   float4* out = reinterpret_cast<float4*>(a.partial) + (int64_t)split * a.S * a.S;
 #pragma unroll
@@ -336,8 +364,15 @@ extern "C" int fb200_ksd_imq(const float* samples, const float* grads, int S, in
   cudaStream_t st = (cudaStream_t)stream;
   a.tile = ksd_tile(S);
   const dim3 grid((unsigned)npt, (unsigned)a.n_splits);
-  if (a.tile == 32) ksd_pair_sums_kernel<32><<<grid, KSD_THREADS, 0, st>>>(a);
-  else ksd_pair_sums_kernel<64><<<grid, KSD_THREADS, 0, st>>>(a);
+  auto launch = [&](auto kern, int T) -> int {
+    const size_t smem = (size_t)2 * 4 * KSD_KC * (T + 4) * sizeof(float);  // two stages of four [32][T + 4] arrays
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, KSD_THREADS, smem, st>>>(a);
+    return 0;
+  };
+  const int lrc = a.tile == 32 ? launch(ksd_pair_sums_kernel<32>, 32) : launch(ksd_pair_sums_kernel<64>, 64);
+  if (lrc != 0) return lrc;
   FB200_LAUNCH_CHECK();
   ksd_row_kernel<<<(unsigned)S, 256, 0, st>>>(a.partial, S, N, a.n_splits, a.tile, c, beta, row_sums);
   FB200_LAUNCH_CHECK();

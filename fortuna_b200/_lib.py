@@ -133,6 +133,8 @@ SIGNATURES = {
     "fb200_quantile_axis0": (_i, [_P, _i, _i64, _P, _i, _P, _P]),
     "fb200_calib_cls_workspace_bytes": (_sz, [_i, _i]),
     "fb200_calib_cls_loss_terms": (_i, [_P, _i, _P, _P, _i, _i, _i, _P, _sz, _P, _P]),
+    "fb200_calib_reg_workspace_bytes": (_sz, [_i, _i]),
+    "fb200_calib_reg_loss_terms": (_i, [_P, _P, _P, _i, _i, _i, _P, _sz, _P, _P]),
     "fb200_cls_sample_targets": (_i, [_P, _P, _P, _i, _i, _i, _i, _P, _P, _P]),
     "fb200_reg_mc_entropies": (_i, [_P, _P, _P, _P, _i, _i, _i, _i, _i, _P, _P, _P, _P]),
     "fb200_conformal_bayes_workspace_bytes": (_sz, [_i, _i, _i]),

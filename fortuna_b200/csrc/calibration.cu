@@ -89,6 +89,58 @@ __global__ void calib_sum_kernel(const double* __restrict__ part, int S, int nbl
   out[S + s] = a1;
 }
 
+// Regression temperature scaler (fortuna/output_calibrator/regression.py:7-19: log_var + log_temp): per posterior sample
+//   L_s = sum_b -0.5 sum_k ( exp(-(lv + lt)) (y - mu)^2 + lv + lt + log 2 pi ),   dL_s/dlt = sum_b -0.5 sum_k ( 1 - exp(-(lv + lt)) (y - mu)^2 )
+// z: [S, B, 2d] = [mu | log var], targets [B, d].  One thread per input, grid (blocks, S).
+__global__ void __launch_bounds__(256) calib_reg_kernel(const float* __restrict__ z, const float* __restrict__ targets,
+                                                        const float* __restrict__ log_temp, int B, int d,
+                                                        double* __restrict__ part) {
+  __shared__ double red[8][2];
+  const int s = blockIdx.y;
+  const float lt = log_temp ? log_temp[0] : 0.0f;
+  const float log2pi = 1.8378770664093453f;
+  double acc_ll = 0.0, acc_d = 0.0;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    const float* r = z + ((size_t)s * B + b) * 2 * d;
+    float a = 0.0f, g = 0.0f;
+    for (int k = 0; k < d; ++k) {
+      const float lv = r[d + k] + lt;
+      const float diff = targets[(size_t)b * d + k] - r[k];
+      const float q = expf(-lv) * (diff * diff);
+      a += q + lv + log2pi;
+      g += 1.0f - q;
+    }
+    acc_ll += (double)(-0.5f * a);
+    acc_d += (double)(-0.5f * g);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc_ll += __shfl_xor_sync(0xffffffffu, acc_ll, o);
+    acc_d += __shfl_xor_sync(0xffffffffu, acc_d, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5][0] = acc_ll;
+    red[threadIdx.x >> 5][1] = acc_d;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int q = 0; q < 8; ++q) {
+      a0 += red[q][0];
+      a1 += red[q][1];
+    }
+    double* o = part + ((size_t)s * gridDim.x + blockIdx.x) * 2;
+    o[0] = a0;
+    o[1] = a1;
+  }
+}
+
+static int calib_reg_blocks(int B) {
+  int nb = (B + 255) / 256;
+  if (nb > 148 * 4) nb = 148 * 4;
+  return nb < 1 ? 1 : nb;
+}
+
 static int calib_blocks(int B) {
   int nb = (B + CAL_WARPS - 1) / CAL_WARPS;
   if (nb > 148 * 4) nb = 148 * 4;
@@ -122,6 +174,26 @@ extern "C" int fb200_calib_cls_loss_terms(const void* logits, int dtype, const i
                                                                      targets, log_temp, B, C, part);
   else
     return FB200_E_UNSUPPORTED;
+  FB200_LAUNCH_CHECK();
+  calib_sum_kernel<<<(S + 127) / 128, 128, 0, st>>>(part, S, nb, out);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t fb200_calib_reg_workspace_bytes(int S, int B) {
+  if (S <= 0 || B <= 0) return 0;
+  return (size_t)S * (size_t)calib_reg_blocks(B) * 2 * sizeof(double);
+}
+
+extern "C" int fb200_calib_reg_loss_terms(const float* outputs, const float* targets, const float* log_temp, int S, int B,
+                                          int d, void* workspace, size_t workspace_bytes, double* out, void* stream) {
+  if (!outputs || !targets || !workspace || !out) return FB200_E_NULL;
+  if (S <= 0 || B <= 0 || d <= 0 || S > 65535) return FB200_E_SHAPE;
+  if (workspace_bytes < fb200_calib_reg_workspace_bytes(S, B)) return FB200_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = calib_reg_blocks(B);
+  double* part = reinterpret_cast<double*>(workspace);
+  calib_reg_kernel<<<dim3((unsigned)nb, (unsigned)S), 256, 0, st>>>(outputs, targets, log_temp, B, d, part);
   FB200_LAUNCH_CHECK();
   calib_sum_kernel<<<(S + 127) / 128, 128, 0, st>>>(part, S, nb, out);
   FB200_LAUNCH_CHECK();

@@ -606,6 +606,22 @@ def calib_cls_loss_terms(logits, targets, log_temp=None):
     return out
 
 
+def calib_reg_loss_terms(outputs, targets, log_temp=None):
+    """outputs [S,B,2d] (uncalibrated [mu | log var]), targets float32 [B,d] -> float64 [2, S]: Gaussian log-likelihood sums
+    with log var + log_temp and their derivative in log_temp."""
+    S, B, two_d = outputs.shape
+    nbytes = int(lib().fb200_calib_reg_workspace_bytes(S, B))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=outputs.device)
+    out = torch.empty((2, S), dtype=torch.float64, device=outputs.device)
+    check(
+        lib().fb200_calib_reg_loss_terms(_ptr(outputs, torch.float32), _ptr(targets, torch.float32),
+                                         _ptr(log_temp, torch.float32, True), S, B, two_d // 2, _ptr(ws), nbytes,
+                                         _ptr(out), _stream()),
+        "fb200_calib_reg_loss_terms",
+    )
+    return out
+
+
 def cls_sample_targets(logits, key, n_target_samples, log_temp=None, want_idx=False):
     """logits [n_stored, B, C] -> y int32 [T, B] (and the drawn posterior-sample indices int32 [T])."""
     n, B, Cn = logits.shape

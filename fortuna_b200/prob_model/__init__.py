@@ -1,6 +1,6 @@
 """User-facing names of fortuna.prob_model for the SG-MCMC hot path."""
 from .calib_config import Adam, CalibConfig, CalibOptimizer, CalibProcessor  # noqa: F401
-from .calibration import ClassificationTemperatureScaler  # noqa: F401
+from .calibration import ClassificationTemperatureScaler, RegressionTemperatureScaler  # noqa: F401
 from .classification import ProbClassifier  # noqa: F401
 from .fit_config import FitCheckpointer, FitConfig, FitMonitor, FitOptimizer  # noqa: F401
 from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_approximator import CyclicalSGLDPosteriorApproximator  # noqa: F401

@@ -20,10 +20,19 @@ class ClassificationTemperatureScaler:
     """Marker for the reference's default output calibrator: logits * exp(-log_temp), log_temp initialised at 0."""
 
 
-def loss_and_grad(z: torch.Tensor, targets: torch.Tensor, log_temp: np.float32, n_data: int):
-    """(loss, dloss/dlog_temp) of one batch z [S, b, C] at log_temp, float32 scalars."""
+class RegressionTemperatureScaler:
+    """Marker for the reference's default regression calibrator (fortuna/output_calibrator/regression.py:7-19):
+    log variance + log_temp, log_temp initialised at 0."""
+
+
+def loss_and_grad(z: torch.Tensor, targets: torch.Tensor, log_temp: np.float32, n_data: int, regression: bool = False):
+    """(loss, dloss/dlog_temp) of one batch at log_temp, float32 scalars.  Classification: z [S, b, C] logits, int32
+    targets; regression: z [S, b, 2d] = [mu | log var], float32 targets [b, d]."""
     lt = torch.tensor([float(log_temp)], dtype=torch.float32, device=z.device)
-    terms = ops.calib_cls_loss_terms(z, targets, lt).cpu().numpy()  # [2, S] float64
+    if regression:
+        terms = ops.calib_reg_loss_terms(z, targets, lt).cpu().numpy()  # [2, S] float64: L_s, dL_s/dlog_temp
+    else:
+        terms = ops.calib_cls_loss_terms(z, targets, lt).cpu().numpy()  # [2, S] float64: L_s, dL_s/dtau
     S, b = z.shape[0], z.shape[1]
     scale = n_data / b
     a = scale * terms[0]
@@ -31,23 +40,29 @@ def loss_and_grad(z: torch.Tensor, targets: torch.Tensor, log_temp: np.float32, 
     w = np.exp(a - m)
     log_pred = m + np.log(w.sum()) - np.log(S)
     w /= w.sum()
-    dlogpred_dtau = float((w * scale * terms[1]).sum())
+    dlogpred = float((w * scale * terms[1]).sum())
+    if regression:
+        return np.float32(-log_pred), np.float32(-dlogpred)
     tau = float(np.exp(-np.float64(log_temp)))
     # loss = -log_pred;  dtau/dlog_temp = -tau
-    return np.float32(-log_pred), np.float32(dlogpred_dtau * tau)
+    return np.float32(-log_pred), np.float32(dlogpred * tau)
 
 
 def calibrate_temperature(z_calib: torch.Tensor, targets_calib, batch_size: int, calib_config: Optional[CalibConfig] = None,
-                          z_val: Optional[torch.Tensor] = None, targets_val=None, val_batch_size: Optional[int] = None
-                          ) -> Dict[str, np.ndarray]:
+                          z_val: Optional[torch.Tensor] = None, targets_val=None, val_batch_size: Optional[int] = None,
+                          regression: bool = False) -> Dict[str, np.ndarray]:
     """Optimise log_temp over the fixed ensemble z_calib [S, n, C].  Batches are consecutive slices of ``batch_size``
     inputs (the calibration loader must not shuffle: fortuna/prob_model/base.py:128).  Returns the status dict
     (per-epoch mean ``loss`` / ``val_loss``) and the float32[1] ``log_temp``."""
     cfg = calib_config or CalibConfig()
     dev = z_calib.device
     n = z_calib.shape[1]
-    t_all = torch.as_tensor(np.asarray(targets_calib), dtype=torch.int32, device=dev)
-    tv_all = None if z_val is None else torch.as_tensor(np.asarray(targets_val), dtype=torch.int32, device=dev)
+    tdt = torch.float32 if regression else torch.int32
+    t_all = torch.as_tensor(np.asarray(targets_calib), dtype=tdt, device=dev)
+    tv_all = None if z_val is None else torch.as_tensor(np.asarray(targets_val), dtype=tdt, device=dev)
+    if regression:
+        t_all = t_all.reshape(n, -1)
+        tv_all = None if tv_all is None else tv_all.reshape(z_val.shape[1], -1)
     opt = cfg.optimizer.method
     log_temp = np.zeros(1, np.float32)
     state = opt.init(log_temp)
@@ -56,14 +71,14 @@ def calibrate_temperature(z_calib: torch.Tensor, targets_calib, batch_size: int,
         ep = []
         for b0 in range(0, n, batch_size):
             zb = z_calib[:, b0 : b0 + batch_size].contiguous()
-            loss, g = loss_and_grad(zb, t_all[b0 : b0 + batch_size].contiguous(), log_temp[0], n)
+            loss, g = loss_and_grad(zb, t_all[b0 : b0 + batch_size].contiguous(), log_temp[0], n, regression)
             upd, state = opt.update(np.array([g], np.float32), state)
             log_temp = (log_temp + upd).astype(np.float32)
             ep.append(loss)
         losses.append(np.mean(ep))
         if z_val is not None:
             nv, vb = z_val.shape[1], val_batch_size or batch_size
-            v = [loss_and_grad(z_val[:, b0 : b0 + vb].contiguous(), tv_all[b0 : b0 + vb].contiguous(), log_temp[0], nv)[0]
+            v = [loss_and_grad(z_val[:, b0 : b0 + vb].contiguous(), tv_all[b0 : b0 + vb].contiguous(), log_temp[0], nv, regression)[0]
                  for b0 in range(0, nv, vb)]
             val_losses.append(np.mean(v))
     status = {"loss": np.array(losses, np.float32)}

@@ -7,6 +7,8 @@ from typing import Optional
 import torch
 
 from ..utils.random import RandomNumberGenerator
+from .calib_config import CalibConfig
+from .calibration import RegressionTemperatureScaler, calibrate_temperature
 from .fit_config import FitConfig
 from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_approximator import CyclicalSGLDPosteriorApproximator
 from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_posterior import CyclicalSGLDPosterior
@@ -36,9 +38,14 @@ def gaussian_log_likelihood_sum(outputs: torch.Tensor, targets: torch.Tensor) ->
 
 class ProbRegressor:
     def __init__(self, model: torch.nn.Module, likelihood_log_variance_model: Optional[torch.nn.Module] = None, prior=None,
-                 posterior_approximator=None, output_calibrator=None, model_editor=None, seed: int = 0, device="cuda"):
-        if model_editor is not None or output_calibrator is not None:
-            raise NotImplementedError("model editors and output-calibrator training are outside the hot path")
+                 posterior_approximator=None, output_calibrator="default", model_editor=None, seed: int = 0, device="cuda"):
+        if model_editor is not None:
+            raise NotImplementedError("model editors are outside the hot path")
+        if output_calibrator == "default":  # the reference's default (regression.py:64)
+            output_calibrator = RegressionTemperatureScaler()
+        if output_calibrator is not None and not isinstance(output_calibrator, RegressionTemperatureScaler):
+            raise NotImplementedError("only the default RegressionTemperatureScaler (or None) is supported")
+        self.output_calibrator = output_calibrator
         self.model = model if likelihood_log_variance_model is None else _MeanAndLogVar(model, likelihood_log_variance_model)
         self.prior = prior if prior is not None else IsotropicGaussianPrior()
         self.posterior_approximator = posterior_approximator if posterior_approximator is not None else SGHMCPosteriorApproximator()
@@ -50,7 +57,8 @@ class ProbRegressor:
         self.predictive = None
         self._predictive_cls = RegressionPredictive
 
-    def train(self, train_data_loader, val_data_loader=None, calib_data_loader=None, fit_config: Optional[FitConfig] = None, **_):
+    def train(self, train_data_loader, val_data_loader=None, calib_data_loader=None, fit_config: Optional[FitConfig] = None,
+              calib_config: Optional[CalibConfig] = None, **_ignored):
         fit_config = fit_config or FitConfig()
         bound = BoundModel(self.model, self.device, freeze_fun=fit_config.optimizer.freeze_fun)
         cls = SGHMCPosterior if isinstance(self.posterior_approximator, SGHMCPosteriorApproximator) else CyclicalSGLDPosterior
@@ -58,6 +66,33 @@ class ProbRegressor:
         self.posterior.log_likelihood_sum = gaussian_log_likelihood_sum
         status = {"fit_status": self.posterior.fit(train_data_loader, val_data_loader, fit_config)}
         self.predictive = RegressionPredictive(self.posterior)
+        if calib_data_loader is not None:
+            status["calib_status"] = self.calibrate(calib_data_loader, val_data_loader, calib_config)
+        return status
+
+    def calibrate(self, calib_data_loader, val_data_loader=None, calib_config: Optional[CalibConfig] = None):
+        """fortuna/prob_model/base.py:109-235 for the regression temperature scaler (log var + log_temp)."""
+        if self.output_calibrator is None:
+            return None
+        if self.posterior is None:
+            raise ValueError("Before calibration, you must either train the probabilistic model or load a state from an "
+                             "existing checkpoint.")
+        cfg = calib_config or CalibConfig()
+        S = cfg.processor.n_posterior_samples
+        pred = self.predictive
+        pred.log_temp = None
+        idx = self.posterior.sample_indices(self.rng.get(), S)
+
+        def outputs(loader):
+            return pred._stored_outputs(pred._x(loader.to_inputs_loader())).index_select(0, idx.long()).contiguous()
+
+        z = outputs(calib_data_loader)
+        zv = outputs(val_data_loader) if val_data_loader is not None else None
+        tv = val_data_loader.to_array_targets() if val_data_loader is not None else None
+        bs = getattr(calib_data_loader, "_batch_size", None) or z.shape[1]
+        vbs = (getattr(val_data_loader, "_batch_size", None) or zv.shape[1]) if zv is not None else None
+        status, log_temp = calibrate_temperature(z, calib_data_loader.to_array_targets(), bs, cfg, zv, tv, vbs, regression=True)
+        pred.log_temp = torch.from_numpy(log_temp).to(self.device)
         return status
 
     # ------------------------------------------------------------------ state on disk (fortuna/prob_model/base.py:236-261)

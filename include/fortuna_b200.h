@@ -331,6 +331,12 @@ int fb200_quantile_axis0(const float* x, int T, int64_t M, const float* q, int n
 size_t fb200_calib_cls_workspace_bytes(int S, int B);
 int fb200_calib_cls_loss_terms(const void* logits, int dtype, const int32_t* targets, const float* log_temp, int S,
                                int B, int C, void* workspace, size_t workspace_bytes, double* out, void* stream);
+/* The same for RegressionTemperatureScaler (fortuna/output_calibrator/regression.py:7-19, log var + log_temp): outputs
+ * float32 [S,B,2d] = [mu | log var] UNcalibrated, targets float32 [B,d];  out[s] = L_s = sum_b log N(y_b; mu, exp(lv + lt)),
+ * out[S + s] = dL_s/dlog_temp. */
+size_t fb200_calib_reg_workspace_bytes(int S, int B);
+int fb200_calib_reg_loss_terms(const float* outputs, const float* targets, const float* log_temp, int S, int B, int d,
+                               void* workspace, size_t workspace_bytes, double* out, void* stream);
 
 /* Target samples of the classification predictive - Predictive.sample (fortuna/prob_model/predictive/base.py:318-440)
  * -> ClassificationProbOutputLayer.sample (fortuna/prob_output_layer/classification.py:33-51), the reference's draws:

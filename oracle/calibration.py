@@ -37,3 +37,16 @@ def adam_step(grad, state, lr=1e-2, b1=0.9, b2=0.999, eps=1e-8):
     mu_hat = mu / f(1 - f(b1) ** count)
     nu_hat = nu / f(1 - f(b2) ** count)
     return f(-lr) * mu_hat / (np.sqrt(nu_hat) + f(eps)), {"count": count, "mu": mu, "nu": nu}
+
+
+def calib_terms_reg(z, targets, log_temp, dtype=np.float64):
+    """Regression temperature scaler (output_calibrator/regression.py:7-19: log var + log_temp):
+    (L_s, dL_s/dlog_temp), L_s = sum_b log N(y_b; mu, exp(lv + lt))  (prob_output_layer/regression.py:30-34)."""
+    z = np.asarray(z, dtype=dtype)
+    d = z.shape[-1] // 2
+    mu, lv = z[..., :d], z[..., d:] + dtype(log_temp)
+    y = np.asarray(targets, dtype=dtype).reshape(1, z.shape[1], d)
+    q = np.exp(-lv) * (y - mu) ** 2
+    L = (-0.5 * (q + lv + np.log(2 * np.pi)).sum(-1)).sum(axis=1)
+    dL = (-0.5 * (1.0 - q).sum(-1)).sum(axis=1)
+    return L, dL

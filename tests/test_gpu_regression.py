@@ -104,3 +104,39 @@ def test_reg_mc_entropies_match_oracle(cuda, n, B, d, S, T):
         np.testing.assert_allclose(got[name].cpu().numpy(), want[name], rtol=2e-5, atol=2e-5, err_msg=name)
     np.testing.assert_allclose((got["aleatoric_entropy"] + got["epistemic_entropy"]).cpu().numpy(),
                                got["entropy"].cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("S,B,d", [(5, 40, 1), (12, 1000, 3), (2, 257, 8)])
+@pytest.mark.parametrize("lt", [0.0, -0.6])
+def test_calib_reg_loss_terms_match_oracle(cuda, S, B, d, lt):
+    from fortuna_b200 import ops
+    from oracle import calibration as Cal
+
+    r = np.random.default_rng(S + B)
+    z = np.concatenate([r.standard_normal((S, B, d)), 0.5 * r.standard_normal((S, B, d)) - 0.5], axis=-1).astype(np.float32)
+    y = r.standard_normal((B, d)).astype(np.float32)
+    got = ops.calib_reg_loss_terms(torch.from_numpy(z).to(cuda), torch.from_numpy(y).to(cuda),
+                                   torch.tensor([lt], dtype=torch.float32, device=cuda)).cpu().numpy()
+    L, dL = Cal.calib_terms_reg(z, y, np.float32(lt))
+    np.testing.assert_allclose(got[0], L, rtol=2e-6, atol=1e-3)
+    np.testing.assert_allclose(got[1], dL, rtol=2e-6, atol=1e-3)
+    h = 1e-5  # the derivative is the derivative
+    Lp, _ = Cal.calib_terms_reg(z, y, lt + h)
+    Lm, _ = Cal.calib_terms_reg(z, y, lt - h)
+    np.testing.assert_allclose(dL, (Lp - Lm) / (2 * h), rtol=1e-5, atol=1e-4)
+
+
+def test_regression_temperature_calibration_recovers_variance_scale(cuda):
+    """Predicted variances too small by e^1.2: Adam on the kernel's loss finds log_temp ~ 1.2."""
+    from fortuna_b200.prob_model import Adam, CalibConfig, CalibOptimizer
+    from fortuna_b200.prob_model.calibration import calibrate_temperature
+
+    r = np.random.default_rng(4)
+    B = 5000
+    mu = r.standard_normal((1, B, 1))
+    true_lv = -0.5 + 0.3 * r.standard_normal((1, B, 1))
+    y = (mu + np.exp(0.5 * true_lv) * r.standard_normal((1, B, 1)))[0]
+    z = torch.from_numpy(np.repeat(np.concatenate([mu, true_lv - 1.2], -1), 3, axis=0).astype(np.float32)).to(cuda)
+    status, log_temp = calibrate_temperature(z, y.astype(np.float32), 1000, CalibConfig(
+        optimizer=CalibOptimizer(Adam(5e-2), n_epochs=40)), regression=True)
+    assert status["loss"][-1] < status["loss"][0] and abs(float(log_temp[0]) - 1.2) < 0.1

@@ -604,6 +604,176 @@ static int launch_cls_narrow(const ClsArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Wide heads (C > 1024: ImageNet-21k, vocabulary-sized heads): a row no longer fits a warp's registers, so the
+// single-pass design does not apply.  Two passes over [S,B,C]: (1) the per-row logsumexp lse[s,b] (caller's workspace;
+// row_lse pass), (2) one CTA per input walks its classes, each thread accumulating sum_s p, sum_s p^2 and sum_s p ln p
+// for one class at a time with p = exp(z * scale - lse[s,b]); row-level results (entropies, mode) by a block reduction.
+// log_prob / ensemble_log_prob come from the lse by gathers (log_prob_from_lse).  2x the HBM traffic of the fused kernel -
+// the price of rows that do not fit on chip.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) wide_lse_kernel(const T* __restrict__ z, int64_t rows, int C, float scale,
+                                                       float* __restrict__ lse) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const T* row = z + r * C;
+    float m = -CUDART_INF_F;
+    for (int c = lane; c < C; c += 32) {
+      float t[1];
+      RowLoad<T, 1>::load(row + c, t);
+      m = fmaxf(m, t[0] * scale);
+    }
+    m = group_max<32>(m);
+    const float ms = (fabsf(m) <= 3.4028234e38f) ? m : 0.0f;
+    float su = 0.0f;
+    for (int c = lane; c < C; c += 32) {
+      float t[1];
+      RowLoad<T, 1>::load(row + c, t);
+      su += __expf(t[0] * scale - ms);
+    }
+    su = group_sum<32>(su);
+    if (lane == 0) lse[r] = ms + __logf(su);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const float* __restrict__ lse, float scale) {
+  __shared__ float s_lse[1024];  // lse[s, b] of this input for up to 1024 samples (more: read from global)
+  __shared__ float red_f[8][2];
+  __shared__ float red_v[8];
+  __shared__ int red_c[8];
+  const int S = a.S, B = a.B, C = a.C;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int s = tid; s < S && s < 1024; s += blockDim.x) s_lse[s] = lse[(size_t)s * B + b];
+  __syncthreads();
+  const T* base = reinterpret_cast<const T*>(a.logits) + (size_t)b * C;
+  const size_t sstride = (size_t)B * C;
+  const float Sf = (float)S;
+  float ent_terms = 0.0f, plogp = 0.0f, best_v = -CUDART_INF_F;
+  int best_c = 0x7FFFFFFF;
+  for (int c = tid; c < C; c += blockDim.x) {
+    float sp = 0.0f, sp2 = 0.0f;
+    for (int s = 0; s < S; ++s) {
+      float t[1];
+      RowLoad<T, 1>::load(base + (size_t)s * sstride + c, t);
+      const float l = t[0] * scale - (s < 1024 ? s_lse[s] : lse[(size_t)s * B + b]);  // log p
+      const float p = __expf(l);
+      sp += p;
+      sp2 = fmaf(p, p, sp2);
+      plogp = fmaf(p, l, plogp);  // 0 * -inf = NaN like the reference
+    }
+    const float mean = sp / Sf;
+    const float av = (sp - sp2) / Sf;
+    const float ev = fmaxf(0.0f, __fsub_rn(sp2 / Sf, __fmul_rn(mean, mean)));
+    if (mean > 0.0f) ent_terms = fmaf(mean, logf(mean), ent_terms);
+    if (mean > best_v) {
+      best_v = mean;
+      best_c = c;
+    }
+    const size_t o = (size_t)b * C + c;
+    if (a.out.mean) a.out.mean[o] = mean;
+    if (a.out.aleatoric_variance) a.out.aleatoric_variance[o] = av;
+    if (a.out.epistemic_variance) a.out.epistemic_variance[o] = ev;
+    if (a.out.variance) a.out.variance[o] = av + ev;
+    if (a.out.std) a.out.std[o] = sqrtf(av + ev);
+  }
+  ent_terms = group_sum<32>(ent_terms);
+  plogp = group_sum<32>(plogp);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ov > best_v || (ov == best_v && oc < best_c)) {
+      best_v = ov;
+      best_c = oc;
+    }
+  }
+  if (lane == 0) {
+    red_f[w][0] = ent_terms;
+    red_f[w][1] = plogp;
+    red_v[w] = best_v;
+    red_c[w] = best_c;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float e = 0.0f, pl = 0.0f, bv = -CUDART_INF_F;
+    int bc = 0x7FFFFFFF;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) {
+      e += red_f[q][0];
+      pl += red_f[q][1];
+      if (red_v[q] > bv || (red_v[q] == bv && red_c[q] < bc)) {
+        bv = red_v[q];
+        bc = red_c[q];
+      }
+    }
+    const float ent = -e, alea = -pl / Sf;
+    if (a.out.entropy) a.out.entropy[b] = ent;
+    if (a.out.aleatoric_entropy) a.out.aleatoric_entropy[b] = alea;
+    if (a.out.epistemic_entropy) a.out.epistemic_entropy[b] = ent - alea;
+    if (a.out.mode) a.out.mode[b] = bc == 0x7FFFFFFF ? 0 : bc;
+  }
+}
+
+// log_prob / ensemble_log_prob of the wide path: gathers against the row logsumexp (same update as the fused kernel)
+template <typename T>
+__global__ void __launch_bounds__(256) wide_log_prob_kernel(const ClsArgs a, const float* __restrict__ lse, float scale) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const int y = a.targets[b];
+  const bool y_ok = (y >= 0) && (y < a.C);
+  const T* base = reinterpret_cast<const T*>(a.logits);
+  float lmax = -CUDART_INF_F, lsum = 0.0f;
+  for (int s = 0; s < a.S; ++s) {
+    const size_t row = (size_t)s * a.B + b;
+    float zt = 0.0f;
+    if (y_ok) {
+      float t[1];
+      RowLoad<T, 1>::load(base + row * a.C + y, t);
+      zt = t[0];
+    }
+    const float ll = zt * scale - lse[row];
+    if (ll > lmax) {
+      lsum = lsum * __expf(lmax - ll) + 1.0f;
+      lmax = ll;
+    } else if (ll > -CUDART_INF_F) {
+      lsum += __expf(ll - lmax);
+    } else if (ll != ll) {
+      lsum = ll;
+    }
+    if (a.out.ensemble_log_prob) a.out.ensemble_log_prob[row] = ll;
+  }
+  if (a.out.log_prob) a.out.log_prob[b] = (lmax + logf(lsum)) - a.log_S;
+}
+
+template <typename T>
+static int launch_cls_wide(const ClsArgs& a, float* lse_ws, cudaStream_t st) {
+  float scale = 1.0f;
+  if (a.log_temp) {
+    float lt = 0.0f;
+    cudaError_t e = cudaMemcpyAsync(&lt, a.log_temp, sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(st);  // the wide path is not latency-critical: one scalar read-back
+    if (e != cudaSuccess) return (int)e;
+    scale = expf(-lt);
+  }
+  const int64_t rows = (int64_t)a.S * a.B;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  wide_lse_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const T*>(a.logits), rows, a.C, scale, lse_ws);
+  FB200_LAUNCH_CHECK();
+  wide_reduce_kernel<T><<<(unsigned)a.B, 256, 0, st>>>(a, lse_ws, scale);
+  FB200_LAUNCH_CHECK();
+  if (a.targets && (a.out.log_prob || a.out.ensemble_log_prob)) {
+    wide_log_prob_kernel<T><<<(unsigned)((a.B + 255) / 256), 256, 0, st>>>(a, lse_ws, scale);
+    FB200_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Finalise the rows this rank owns from the n_src slots it received (one per source rank, same row layout as
 // above): sums are taken in source-rank order (deterministic), the (max, sumexp) pairs are merged, then the same
 // finalisation as the single-GPU kernel.  One warp per row.
@@ -916,6 +1086,32 @@ extern "C" int fb200_bma_reduce_cls(const void* logits, int dtype, const float* 
   a.out = *out;
   if ((a.out.log_prob || a.out.ensemble_log_prob) && !targets) return FB200_E_NULL;
   return reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
+}
+
+extern "C" size_t fb200_bma_reduce_cls_wide_workspace_bytes(int S, int B) {
+  return (S > 0 && B > 0) ? (size_t)S * (size_t)B * sizeof(float) : 0;
+}
+
+extern "C" int fb200_bma_reduce_cls_wide(const void* logits, int dtype, const float* log_temp, const int32_t* targets,
+                                         int S, int B, int C, const fb200_cls_outputs_t* out, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  if (!logits || !out || !workspace) return FB200_E_NULL;
+  if (S <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
+  if (dtype != FB200_F32 && dtype != FB200_BF16) return FB200_E_UNSUPPORTED;
+  if ((out->log_prob || out->ensemble_log_prob) && !targets) return FB200_E_NULL;
+  if (workspace_bytes < fb200_bma_reduce_cls_wide_workspace_bytes(S, B)) return FB200_E_WORKSPACE;
+  ClsArgs a{};
+  a.out = *out;
+  a.logits = logits;
+  a.log_temp = log_temp;
+  a.targets = targets;
+  a.S = S;
+  a.B = B;
+  a.C = C;
+  a.log_S = logf((float)S);
+  float* lse_ws = reinterpret_cast<float*>(workspace);
+  if (dtype == FB200_F32) return launch_cls_wide<float>(a, lse_ws, (cudaStream_t)stream);
+  return launch_cls_wide<__nv_bfloat16>(a, lse_ws, (cudaStream_t)stream);
 }
 
 extern "C" size_t fb200_cls_slot_row_floats(int C) { return C > 0 ? (size_t)(2 * C + 4) : 0; }

@@ -344,6 +344,17 @@ def bma_reduce_cls(logits, want, targets=None, log_temp=None, out=None):
     S, B, Cn = logits.shape
     outs = out if out is not None else _alloc_cls_outputs(tuple(want), S, B, Cn, logits.device)
     st = _cls_struct(outs)
+    if Cn > 1024:  # rows wider than a warp's registers: the two-pass kernel
+        nbytes = int(lib().fb200_bma_reduce_cls_wide_workspace_bytes(S, B))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=logits.device)
+        check(
+            lib().fb200_bma_reduce_cls_wide(
+                _ptr(logits, (torch.float32, torch.bfloat16)), _DT[logits.dtype], _ptr(log_temp, torch.float32, True),
+                _ptr(targets, torch.int32, True), S, B, Cn, C.byref(st), _ptr(ws), nbytes, _stream(),
+            ),
+            "fb200_bma_reduce_cls_wide",
+        )
+        return outs
     check(
         lib().fb200_bma_reduce_cls(
             _ptr(logits, (torch.float32, torch.bfloat16)),

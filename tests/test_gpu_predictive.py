@@ -59,6 +59,25 @@ def test_cls_reductions_f32(cuda, S, B, C):
     _check(outs, z, t, S)
 
 
+@pytest.mark.parametrize("S,B,C,temp", [(4, 33, 1025, False), (6, 40, 3000, True), (3, 17, 21841, False), (1030, 3, 1100, False)])
+def test_cls_reductions_wide_heads(cuda, S, B, C, temp):
+    """C > 1024 (rows wider than a warp's registers): the two-pass kernel fb200_bma_reduce_cls_wide, same outputs."""
+    from fortuna_b200 import ops
+
+    z = _logits(S, B, C, seed=S + C, scale=3.0)
+    t = np.random.default_rng(1).integers(0, C, B).astype(np.int32)
+    lt = np.array([0.25], dtype=np.float32)
+    outs = ops.bma_reduce_cls(torch.from_numpy(z).to(cuda), ALL, targets=torch.from_numpy(t).to(cuda),
+                              log_temp=torch.from_numpy(lt).to(cuda) if temp else None)
+    zc = (z * np.exp(-lt[0], dtype=np.float32)).astype(np.float32) if temp else z
+    _check(outs, zc, t, S)
+    zb = torch.from_numpy(z).to(cuda).to(torch.bfloat16)
+    ob = ops.bma_reduce_cls(zb, ("mean", "entropy", "log_prob"), targets=torch.from_numpy(t).to(cuda))
+    zbn = zb.float().cpu().numpy()
+    np.testing.assert_allclose(ob["mean"].cpu().numpy(), P.cls_mean(zbn), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(ob["log_prob"].cpu().numpy(), P.cls_log_prob(zbn, t), rtol=1e-5, atol=2e-6)
+
+
 def test_cls_reductions_ties_and_temperature(cuda):
     from fortuna_b200 import ops
 

@@ -155,6 +155,33 @@ def oracle_vectors():
     out["ece"] = np.float32(Sc.expected_calibration_error(mean.argmax(-1), mean, t))
     out["mce"] = np.float32(Sc.maximum_calibration_error(mean.argmax(-1), mean, t))
     out["quantile_err0.1"] = np.float32(Sc.conformal_quantile(val_scores, 0.1))
+
+    # --- widened rows of the scope: diagnostics, conformal Bayes, target samples, MC entropies, calibration
+    from oracle import calibration as Cal
+    from oracle import diagnostic as D
+
+    r = np.random.default_rng(321)
+    xs = (1.0 + 0.1 * r.standard_normal((12, 9))).astype(np.float32)
+    gs = r.standard_normal((12, 9)).astype(np.float32)
+    out["diag_samples"], out["diag_grads"] = xs, gs
+    out["ksd_imq"] = np.float32(D.kernel_stein_discrepancy_imq(xs, gs, 1.0, -0.5, dtype=np.float64))
+    chain = np.cumsum(r.standard_normal((40, 6)), axis=0).astype(np.float32) * 0.3 + r.standard_normal((40, 6)).astype(np.float32)
+    out["ess_chain"] = chain
+    out["ess_direct"] = D.effective_sample_size_direct(chain, 0.0).astype(np.float32)
+    ell = P.cls_ensemble_log_prob(z, t)                           # [5, 12] training log-probs of the fixture logits
+    lsm = P.log_softmax_rows((2 * r.standard_normal((5, 4, 7))).astype(np.float32))
+    out["cb_lsm_test"] = lsm
+    out["cb_counts"] = Sc.conformal_bayes_counts(ell, lsm, dtype=np.float64)[0].astype(np.int32)
+    out["cb_region_err0.3"] = Sc.conformal_bayes_region(ell, lsm, 0.3, dtype=np.float64).astype(np.uint8)
+    y, idx = P.cls_sample_targets(z, prng.PRNGKey(5), 6)
+    out["cls_sample_y"], out["cls_sample_idx"] = y, idx
+    zr = np.concatenate([r.standard_normal((4, 10, 2)), 0.3 * r.standard_normal((4, 10, 2)) - 1.0], -1).astype(np.float32)
+    out["reg_outputs"] = zr
+    e = P.reg_mc_entropies(zr, prng.PRNGKey(9), 5, 4)
+    for k, v in e.items():
+        out[f"reg_{k}"] = v
+    L, dL = Cal.calib_terms(z, t, np.float32(0.4))
+    out["calib_L_lt0.4"], out["calib_dL_lt0.4"] = L, dL
     return out
 
 

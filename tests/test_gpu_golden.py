@@ -172,3 +172,31 @@ def test_predictive_and_scoring_vectors(cuda):
     qlevel = np.float32(np.ceil(np.float32((B + 1) * (1 - 0.1))) / np.float32(B))
     q = ops.quantile_sorted(val, torch.tensor([qlevel], dtype=torch.float32, device=cuda))
     np.testing.assert_allclose(q.cpu().numpy()[0], VEC["quantile_err0.1"], rtol=1e-6)
+
+
+def test_widened_rows_vectors(cuda):
+    """The frozen vectors of the widened scope rows (diagnostics, conformal Bayes, target samples, regression
+    Monte-Carlo entropies, calibration terms) through the C ABI."""
+    from fortuna_b200 import ops
+
+    dev = cuda
+    x, g = torch.from_numpy(VEC["diag_samples"]).to(dev), torch.from_numpy(VEC["diag_grads"]).to(dev)
+    np.testing.assert_allclose(float(ops.ksd_imq(x, g, 1.0, -0.5).item()), VEC["ksd_imq"], rtol=2e-5)
+    np.testing.assert_allclose(ops.ess(torch.from_numpy(VEC["ess_chain"]).to(dev), 0.0).cpu().numpy(), VEC["ess_direct"], rtol=5e-4)
+    z = torch.from_numpy(VEC["z"]).to(dev)
+    t = torch.from_numpy(VEC["z_targets"]).to(dev)
+    ell = ops.bma_reduce_cls(z, ("ensemble_log_prob",), targets=t)["ensemble_log_prob"]
+    cb = ops.conformal_bayes_sets(ell, torch.from_numpy(VEC["cb_lsm_test"]).to(dev), 0.3, want_counts=True)
+    assert np.array_equal(cb["rank_counts"].cpu().numpy(), VEC["cb_counts"])
+    assert np.array_equal(cb["region"].cpu().numpy(), VEC["cb_region_err0.3"])
+    y, idx = ops.cls_sample_targets(z, ops.PRNGKey(5, dev), 6, want_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), VEC["cls_sample_idx"]) and np.array_equal(y.cpu().numpy(), VEC["cls_sample_y"])
+    zr = torch.from_numpy(VEC["reg_outputs"]).to(dev)
+    ks = ops.split(ops.PRNGKey(9, dev), 6)
+    e = ops.reg_mc_entropies(zr, ops.sample_indices(ks[0].contiguous(), 5, 4), ks[1:].contiguous(), 4,
+                             ("entropy", "aleatoric_entropy", "epistemic_entropy"))
+    for k in ("entropy", "aleatoric_entropy", "epistemic_entropy"):
+        np.testing.assert_allclose(e[k].cpu().numpy(), VEC[f"reg_{k}"], rtol=2e-5, atol=2e-5, err_msg=k)
+    terms = ops.calib_cls_loss_terms(z, t, torch.tensor([0.4], dtype=torch.float32, device=dev)).cpu().numpy()
+    np.testing.assert_allclose(terms[0], VEC["calib_L_lt0.4"], rtol=2e-6, atol=1e-4)
+    np.testing.assert_allclose(terms[1], VEC["calib_dL_lt0.4"], rtol=2e-5, atol=1e-4)

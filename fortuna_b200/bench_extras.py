@@ -11,7 +11,7 @@ from .prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
 from .utils.flat_tree import FlatTree
 
 
-def sampler_extras(device, hbm_peak_gbs, steps=20, warmup=3, seed=0, only=None):
+def sampler_extras(device, hbm_peak_gbs, steps=20, warmup=3, seed=0, only=None, joint=False):
     import sys, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     if root not in sys.path:
@@ -45,6 +45,21 @@ def sampler_extras(device, hbm_peak_gbs, steps=20, warmup=3, seed=0, only=None):
             "param_updates_per_s": n / (ms * 1e-3), "bytes_per_param": bytes_per,
             "achieved_gbs": gbs, "hbm_frac": gbs / hbm_peak_gbs,
         }
+        if joint:
+            # fused log-joint mode: likelihood scaling + Gaussian-prior gradient in the prologue, sum(theta^2) returned
+            sq = torch.empty(1, dtype=torch.float64, device=device)
+            jt = (468.75, 1.0, sq)
+            for _ in range(warmup):
+                params, state = tx.apply(params, grad, state, joint=jt)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                params, state = tx.apply(params, grad, state, joint=jt)
+            e1.record()
+            torch.cuda.synchronize()
+            msj = e0.elapsed_time(e1) / steps
+            out[f"sghmc_{name}"]["joint_ms_per_step"] = msj
+            out[f"sghmc_{name}"]["joint_hbm_frac"] = bytes_per * n / (msj * 1e-3) / 1e9 / hbm_peak_gbs
         del state
     return out
 

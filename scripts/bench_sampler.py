@@ -16,4 +16,4 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=20)
     a = ap.parse_args()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
-    print(json.dumps(sampler_extras(torch.device("cuda:0"), float(peaks["hbm_gbs"]), steps=a.steps)))
+    print(json.dumps(sampler_extras(torch.device("cuda:0"), float(peaks["hbm_gbs"]), steps=a.steps, joint=True)))

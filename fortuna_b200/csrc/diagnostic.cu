@@ -256,7 +256,19 @@ __global__ void __launch_bounds__(256) ess_kernel(const EssArgs a) {
         win[r] = xs[(size_t)(k0 + r) * COLS + col];  // x[0 + k0 + r]; rows past S are zero
       }
       const int t_end = S - k0;  // x[t + k0] is zero for t >= S - k0
-      for (int t = 0; t < t_end; ++t) {
+      int t = 0;
+      // eight time steps per iteration with the window kept as a ring: at step u the lag-r partner of x[t + u] is
+      // win[(u + r) & 7], and slot u is then refilled with x[t + u + k0 + 8] - no register moves, one load per step
+      for (; t + ESS_R <= t_end; t += ESS_R) {
+#pragma unroll
+        for (int u = 0; u < ESS_R; ++u) {
+          const float xt = xs[(size_t)(t + u) * COLS + col];
+#pragma unroll
+          for (int r = 0; r < ESS_R; ++r) acc[r] = fmaf(xt, win[(u + r) & (ESS_R - 1)], acc[r]);
+          win[u] = xs[(size_t)(t + u + k0 + ESS_R) * COLS + col];  // rows S .. S+7 are zero
+        }
+      }
+      for (; t < t_end; ++t) {
         const float xt = xs[(size_t)t * COLS + col];
 #pragma unroll
         for (int r = 0; r < ESS_R; ++r) acc[r] = fmaf(xt, win[r], acc[r]);

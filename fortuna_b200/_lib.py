@@ -129,6 +129,7 @@ SIGNATURES = {
     "fb200_credible_sets": (_i, [_P, _i, _i, _f, _P, _P, _P]),
     "fb200_sort_workspace_bytes": (_sz, [_i64]),
     "fb200_sort_f32": (_i, [_P, _i64, _P, _sz, _P]),
+    "fb200_aps_conformal_sets": (_i, [_P, _i, _i, _P, _i, _f, _P, _P, _P, _P]),
     "fb200_conformal_sets": (_i, [_P, _i, _P, _i, _i, _f, _P, _P, _P]),
     "fb200_ece_bins": (_i, [_P, _i, _i, _P, _P, _P, _i, _P, _P, _P, _P, _P, _P]),
     "fb200_ece_from_bins": (_i, [_P, _P, _P, _i, _i64, _P, _P]),

@@ -37,6 +37,12 @@ struct RowSortArgs {
   int32_t* perm;           // optional [B,C]
   int32_t* set_size;       // optional [B] (credible sets)
   float set_threshold;     // float32(1 - error)
+  // fused rank-count conformal sets (key-only kernel, all-class mode): mask[b,c] = !(score < val_sorted[n_val-1-K])
+  uint8_t* cs_mask;        // optional [B,C]
+  int32_t* cs_sizes;       // optional [B]
+  const float* cs_val_sorted;
+  int cs_q_index;          // n_val - 1 - K
+  int cs_all_true, cs_all_false;
 };
 
 __global__ void __launch_bounds__(256) row_sort_cumsum_kernel(const RowSortArgs a) {
@@ -557,7 +563,29 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
           ap[r] = sbase + (uint32_t)(pos + (pos >> 5)) * 4u;
         }
       }
-      if (a.scores) {
+      if (a.cs_mask) {
+        // conformal sets straight from the scores (conformal/classification/base.py:45-64, see conformal_sets_kernel):
+        // the [B,C] score matrix need not be written and read back
+        const float q = (a.cs_all_true || a.cs_all_false) ? 0.0f : __ldg(a.cs_val_sorted + a.cs_q_index);
+        float* orow = a.scores ? a.scores + (size_t)b * C : nullptr;
+        uint8_t* mrow = a.cs_mask + (size_t)b * C;
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int c = r * 32 + lane;
+          float v;
+          asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(ap[r]), "n"(PAD * 4));
+          const bool in = a.cs_all_true || (!a.cs_all_false && !(v < q));
+          if (c < C) {
+            if (orow) orow[c] = v;
+            mrow[c] = in ? 1 : 0;
+            cnt += in ? 1 : 0;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0 && a.cs_sizes) a.cs_sizes[b] = cnt;
+      } else if (a.scores) {
         float* orow = a.scores + (size_t)b * C;
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
@@ -1180,12 +1208,8 @@ extern "C" int fb200_sort_f32(float* x, int64_t n, void* workspace, size_t works
   return 0;
 }
 
-extern "C" int fb200_conformal_sets(const float* val_scores_sorted, int n_val, const float* test_scores, int B,
-                                    int C, float threshold, uint8_t* mask, int32_t* sizes, void* stream) {
-  if (!val_scores_sorted || !test_scores || !mask) return FB200_E_NULL;
-  if (n_val <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
-  if ((C & 3) == 0 && (!fb200_aligned16(test_scores) || (reinterpret_cast<uintptr_t>(mask) & 3u))) return FB200_E_ALIGN;
-  // K = largest integer count with float32(count) < threshold (count is compared as float32, base.py:51-53)
+// K = largest integer count with float32(count) < threshold (count is compared as float32, base.py:51-53)
+static long long conformal_rank_bound(float threshold, int n_val) {
   long long K;
   if (!(threshold > 0.0f)) {
     K = -1;
@@ -1197,6 +1221,36 @@ extern "C" int fb200_conformal_sets(const float* val_scores_sorted, int n_val, c
     while (K >= 0 && !((float)K < threshold)) --K;
     if (K > n_val) K = n_val;
   }
+  return K;
+}
+
+extern "C" int fb200_aps_conformal_sets(const float* probs, int B, int C, const float* val_scores_sorted, int n_val,
+                                        float threshold, float* scores, uint8_t* mask, int32_t* sizes, void* stream) {
+  if (!probs || !val_scores_sorted || !mask) return FB200_E_NULL;
+  if (B <= 0 || C <= 0 || n_val <= 0) return FB200_E_SHAPE;
+  if (C > 1024) return FB200_E_UNSUPPORTED;  // the fused epilogue lives in the key-only warp kernel
+  const long long K = conformal_rank_bound(threshold, n_val);
+  RowSortArgs a{};
+  a.probs = probs;
+  a.B = B;
+  a.C = C;
+  a.scores = scores;
+  a.set_threshold = INFINITY;
+  a.cs_mask = mask;
+  a.cs_sizes = sizes;
+  a.cs_val_sorted = val_scores_sorted;
+  a.cs_all_true = K >= n_val;
+  a.cs_all_false = K < 0;
+  a.cs_q_index = (a.cs_all_true || a.cs_all_false) ? 0 : (int)(n_val - 1 - K);
+  return launch_row_sort(a, (cudaStream_t)stream);
+}
+
+extern "C" int fb200_conformal_sets(const float* val_scores_sorted, int n_val, const float* test_scores, int B,
+                                    int C, float threshold, uint8_t* mask, int32_t* sizes, void* stream) {
+  if (!val_scores_sorted || !test_scores || !mask) return FB200_E_NULL;
+  if (n_val <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
+  if ((C & 3) == 0 && (!fb200_aligned16(test_scores) || (reinterpret_cast<uintptr_t>(mask) & 3u))) return FB200_E_ALIGN;
+  const long long K = conformal_rank_bound(threshold, n_val);
   int64_t blocks = ((int64_t)B * 32 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   conformal_sets_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(val_scores_sorted, n_val, test_scores,

@@ -468,6 +468,21 @@ def aps_scores(probs, targets=None, want_perm=False):
     return (scores, perm) if want_perm else scores
 
 
+def aps_conformal_sets(probs, val_sorted, threshold, want_scores=False):
+    """APS all-class scores + rank-count conformal sets in one kernel: (mask uint8 [B,C], sizes int32 [B][, scores])."""
+    B, Cn = probs.shape
+    mask = torch.empty((B, Cn), dtype=torch.uint8, device=probs.device)
+    sizes = torch.empty(B, dtype=torch.int32, device=probs.device)
+    scores = torch.empty((B, Cn), dtype=torch.float32, device=probs.device) if want_scores else None
+    check(
+        lib().fb200_aps_conformal_sets(_ptr(probs, torch.float32), B, Cn, _ptr(val_sorted, torch.float32), val_sorted.numel(),
+                                       float(np.float32(threshold)), _ptr(scores, torch.float32, True), _ptr(mask), _ptr(sizes),
+                                       _stream()),
+        "fb200_aps_conformal_sets",
+    )
+    return (mask, sizes, scores) if want_scores else (mask, sizes)
+
+
 def simple_scores(probs, targets=None):
     B, Cn = probs.shape
     scores = torch.empty(B if targets is not None else (B, Cn), dtype=torch.float32, device=probs.device)

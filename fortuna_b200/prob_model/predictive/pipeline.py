@@ -11,7 +11,7 @@ All arithmetic is in the library kernels; torch provides memory, streams and NCC
 """
 
 import time
-from typing import Dict, Iterable, List, Optional, Sequence
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -42,6 +42,14 @@ class ConformalCalibration:
         self.n_val = int(n_val)
         self.error = float(error)
         self.threshold = conformal_threshold(n_val, error)
+
+
+def aps_sets(mean: torch.Tensor, calib) -> Tuple[torch.Tensor, torch.Tensor]:
+    """APS conformal sets of the rows of `mean`: one fused kernel (scores never materialised) when a row fits the warp
+    kernel, else scores + sets."""
+    if mean.shape[1] <= 1024:
+        return ops.aps_conformal_sets(mean, calib.val_sorted, calib.threshold)
+    return ops.conformal_sets(calib.val_sorted, ops.aps_scores(mean, None), calib.threshold)
 
 
 class PredictivePipeline:
@@ -75,7 +83,9 @@ class PredictivePipeline:
                 self.send = ops.alloc_cls_slots(world, self.B_local, C, device)
                 self.recv = torch.empty_like(self.send)
                 self.slot_ptrs = ops.slot_pointer_table([self.send[o] for o in range(world)], device)
-        self.launches_per_step = 5 if world == 1 else 7  # + reduce(shard), finalize_slots, ece_from_bins; - fused finalise
+        # reduce, sort + sets (fused), ece_bins, ece_finalize; sharded: + finalize_slots, ece_from_bins
+        fused_sets = C <= 1024
+        self.launches_per_step = (4 if world == 1 else 6) + (0 if fused_sets else 1)
 
     # -------------------------------------------------------------------------------- K3 / K4
     def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor], kernel_events=None):
@@ -106,8 +116,7 @@ class PredictivePipeline:
         mean = self.outs["mean"]
         lo, hi = self.rank * self.B_local, (self.rank + 1) * self.B_local
         t_local = targets[lo:hi] if self.world > 1 else targets
-        self.scores = ops.aps_scores(mean, None)
-        self.mask, self.sizes = ops.conformal_sets(calib.val_sorted, self.scores, calib.threshold)
+        self.mask, self.sizes = aps_sets(mean, calib)
         self.ece = ops.ece_bins(mean, t_local, self.thresholds)
         if self.world > 1:
             self.exchange.allreduce_bins(self.ece)
@@ -172,8 +181,7 @@ def predictive_from_logits_batches(
             ops.bma_reduce_cls(zin, want, targets=tin, out=outs)
             free[k].record(comp_s)
             tfull[b0 : b0 + rows].copy_(tin, non_blocking=True)
-            sc = ops.aps_scores(full["mean"][b0 : b0 + rows], None)
-            m, sz = ops.conformal_sets(calib.val_sorted, sc, calib.threshold)
+            m, sz = aps_sets(full["mean"][b0 : b0 + rows], calib)
             mask[b0 : b0 + rows].copy_(m, non_blocking=True)
             sizes[b0 : b0 + rows].copy_(sz, non_blocking=True)
             done = torch.cuda.Event()
@@ -263,8 +271,7 @@ def predictive_from_feature_batches(
             outs.update({w: vec[w][b0 : b0 + rows] for w in vec})
             ops.bma_reduce_cls(z, want, targets=tin, out=outs)
             tfull[b0 : b0 + rows].copy_(tin, non_blocking=True)
-            sc = ops.aps_scores(full["mean"][b0 : b0 + rows], None)
-            m, sz = ops.conformal_sets(calib.val_sorted, sc, calib.threshold)
+            m, sz = aps_sets(full["mean"][b0 : b0 + rows], calib)
             mask[b0 : b0 + rows].copy_(m, non_blocking=True)
             sizes[b0 : b0 + rows].copy_(sz, non_blocking=True)
             done = torch.cuda.Event()

@@ -309,6 +309,10 @@ int fb200_sort_f32(float* x, int64_t n, void* workspace, size_t workspace_bytes,
  * val_scores_sorted: ascending, n_val values.  mask uint8 [B,C]; sizes int32 [B] (optional). */
 int fb200_conformal_sets(const float* val_scores_sorted, int n_val, const float* test_scores, int B, int C,
                          float threshold, uint8_t* mask, int32_t* sizes, void* stream);
+/* fb200_aps_scores (all classes) and fb200_conformal_sets in ONE kernel: the sets are decided in the epilogue of the sort
+ * kernel, so the [B,C] score matrix is neither written nor read back (scores: optional output; C <= 1024). */
+int fb200_aps_conformal_sets(const float* probs, int B, int C, const float* val_scores_sorted, int n_val, float threshold,
+                             float* scores, uint8_t* mask, int32_t* sizes, void* stream);
 /* ECE / MCE binning (fortuna/metric/classification.py:43-95, 98-133, 147-181): conf = max_c probs (C > 1)
  * or probs itself (C == 1); thresholds = the caller's float32 linspace(1/B, 1, n_bins) (device, n_bins <= 32).
  * Outputs: bin_idx int32[B] (optional; -1 = in no bin), counts int32[n_bins], conf_sums float32[n_bins],

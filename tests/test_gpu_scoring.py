@@ -224,3 +224,27 @@ def test_softmax_rows_in_place(cuda):
     np.testing.assert_allclose(lse.cpu().numpy(), want_lse, rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(ops.softmax_rows_(zt.clone(), ops.EPI_LOG_SOFTMAX).cpu().numpy(), P.log_softmax_rows(z), rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(ops.softmax_rows_(zt.clone(), ops.EPI_SOFTMAX).cpu().numpy(), P.softmax(z), rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("B,C,n_val", [(64, 1000, 5000), (100, 10, 37), (7, 3, 3), (33, 1024, 200), (50, 2, 11)])
+@pytest.mark.parametrize("error", [0.05, 0.3, 0.0, 1.0])
+def test_fused_aps_conformal_sets_equal_the_two_kernels(cuda, B, C, n_val, error):
+    """fb200_aps_conformal_sets (sets decided in the sort kernel's epilogue) == fb200_aps_scores + fb200_conformal_sets,
+    and == the oracle."""
+    from fortuna_b200 import ops
+
+    vp = _probs(n_val, C, seed=2, ties=True)
+    vt = np.random.default_rng(3).integers(0, C, n_val).astype(np.int32)
+    tp = _probs(B, C, seed=4, ties=(B % 2 == 0))
+    val_scores, test_scores = Sc.get_scores(vp, vt, tp, "aps")
+    conds, sizes, _ = Sc.conformal_sets(val_scores, test_scores, error)
+    vs = ops.sort_f32_(torch.from_numpy(val_scores.copy()).to(cuda))
+    thr = Sc.conformal_threshold(n_val, error)
+    tpt = torch.from_numpy(tp).to(cuda)
+    mask, sz, scores = ops.aps_conformal_sets(tpt, vs, thr, want_scores=True)
+    assert np.array_equal(scores.cpu().numpy(), test_scores)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), conds) and np.array_equal(sz.cpu().numpy(), sizes)
+    m2, s2 = ops.aps_conformal_sets(tpt, vs, thr)
+    assert torch.equal(m2, mask) and torch.equal(s2, sz)
+    m3, s3 = ops.conformal_sets(vs, ops.aps_scores(tpt, None), thr)
+    assert torch.equal(m3, mask) and torch.equal(s3, sz)

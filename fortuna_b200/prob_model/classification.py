@@ -95,6 +95,8 @@ class ProbClassifier:
         status, log_temp = calibrate_temperature(z, calib_data_loader.to_array_targets(), bs, cfg, zv, tv, vbs)
         self.predictive.log_temp = torch.from_numpy(log_temp).to(self.device)
         self.posterior.log_temp = self.predictive.log_temp
+        if self.posterior.state.checkpoint_dir:  # posterior.state.update(calib_params=...): base.py:213-215
+            self.posterior.save_state(self.posterior.state.checkpoint_dir)
         return status
 
     # ------------------------------------------------------------------ state on disk (fortuna/prob_model/base.py:236-261)
@@ -118,7 +120,7 @@ class ProbClassifier:
         cls = SGHMCPosterior if isinstance(self.posterior_approximator, SGHMCPosteriorApproximator) else CyclicalSGLDPosterior
         self.posterior = cls(bound, self.prior, self.posterior_approximator, self.rng)
         self.posterior.load_state(checkpoint_path)
-        self.predictive = self._predictive_cls(self.posterior)
+        self.predictive = self._predictive_cls(self.posterior, log_temp=self.posterior.log_temp)
 
     def save_state(self, checkpoint_path, keep_top_n_checkpoints: int = 1) -> None:
         if self.posterior is None:

@@ -99,6 +99,14 @@ class SGMCMCPosterior(WithRNG):
 
         return _nest((pth, p.detach().cpu().numpy().copy()) for pth, p in param_paths(self.bound.model).items())
 
+    def _calib_params(self):
+        """The fitted output-calibrator parameters in the reference's pytree
+        (``{"output_calibrator": {"params": {"log_temp": f32[1]}}}``) or None."""
+        lt = getattr(self, "log_temp", None)
+        if lt is None:
+            return None
+        return {"output_calibrator": {"params": {"log_temp": lt.detach().cpu().numpy().astype(np.float32).reshape(1)}}}
+
     def _fit_repository(self, fit_config) -> SGMCMCPosteriorStateRepository:
         """The repository the sampling callback fills (sghmc_posterior.py:151-156): written through to
         ``save_checkpoint_dir/<i>`` when a directory is configured."""
@@ -174,6 +182,12 @@ class SGMCMCPosterior(WithRNG):
             device=bound.device if bound is not None else self.rng._rng.device)
         self.state.load_checkpoints()
         self._last_layer = None
+        cp = d.get("calib_params")
+        try:
+            lt = np.asarray(cp["output_calibrator"]["params"]["log_temp"], dtype=np.float32).reshape(1)
+            self.log_temp = torch.from_numpy(lt.copy()).to(self.state.bank.device)
+        except (TypeError, KeyError):
+            self.log_temp = None
 
     def save_state(self, checkpoint_dir, keep_top_n_checkpoints: int = 1) -> None:
         """sgmcmc_posterior.py:78-80, plus the chain file ``load_state`` looks for."""
@@ -182,10 +196,11 @@ class SGMCMCPosterior(WithRNG):
         for i in range(self.state.size):
             step = self.state.steps[i] if self.state.steps[i] is not None else i
             ckpt.save_checkpoint(os.path.join(str(checkpoint_dir), str(i)),
-                                 posterior_state_dict(_Sample(step, self.state.get(i)), self.STATE_NAME, which),
+                                 posterior_state_dict(_Sample(step, self.state.get(i)), self.STATE_NAME, which,
+                                                      calib_params=self._calib_params()),
                                  step=step, keep=keep_top_n_checkpoints, overwrite=True)
         d = posterior_state_dict(chain if chain is not None else _Sample(0, self.state.get(self.state.size - 1)),
-                                 self.STATE_NAME, which)
+                                 self.STATE_NAME, which, calib_params=self._calib_params())
         if which is not None and getattr(self, "bound", None) is not None:
             d["params"] = ckpt.to_state_dict(self._all_params_tree())
         ckpt.save_checkpoint(os.path.join(str(checkpoint_dir), "c"), d, step=d["step"], keep=keep_top_n_checkpoints,

@@ -93,6 +93,9 @@ class ProbRegressor:
         vbs = (getattr(val_data_loader, "_batch_size", None) or zv.shape[1]) if zv is not None else None
         status, log_temp = calibrate_temperature(z, calib_data_loader.to_array_targets(), bs, cfg, zv, tv, vbs, regression=True)
         pred.log_temp = torch.from_numpy(log_temp).to(self.device)
+        self.posterior.log_temp = pred.log_temp
+        if self.posterior.state.checkpoint_dir:
+            self.posterior.save_state(self.posterior.state.checkpoint_dir)
         return status
 
     # ------------------------------------------------------------------ state on disk (fortuna/prob_model/base.py:236-261)
@@ -116,7 +119,7 @@ class ProbRegressor:
         cls = SGHMCPosterior if isinstance(self.posterior_approximator, SGHMCPosteriorApproximator) else CyclicalSGLDPosterior
         self.posterior = cls(bound, self.prior, self.posterior_approximator, self.rng)
         self.posterior.load_state(checkpoint_path)
-        self.predictive = self._predictive_cls(self.posterior)
+        self.predictive = self._predictive_cls(self.posterior, log_temp=self.posterior.log_temp)
 
     def save_state(self, checkpoint_path, keep_top_n_checkpoints: int = 1) -> None:
         if self.posterior is None:

@@ -311,3 +311,32 @@ def test_train_with_calibration_loader(cuda):
         n_samples=2, n_thinning=2, burnin_length=2, step_schedule=1e-3))
     st2 = pm2.train(train_loader, calib_data_loader=test_loader, fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=2)))
     assert st2["calib_status"] is None and pm2.predictive.log_temp is None
+
+
+def test_fitted_temperature_travels_with_the_checkpoints(cuda, tmp_path):
+    """calib_params = {"output_calibrator": {"params": {"log_temp": f32[1]}}} is part of every stored state
+    (fortuna/prob_model/base.py:213-215): a model restored with load_state predicts with it."""
+    from fortuna_b200.prob_model import (
+        Adam, CalibConfig, CalibOptimizer, CalibProcessor, FitCheckpointer, FitConfig, FitOptimizer, ProbClassifier,
+        SGHMCPosteriorApproximator,
+    )
+    from fortuna_b200.training import checkpoint as ck
+
+    MLP, train, test, train_loader, test_loader = _setup()
+    torch.manual_seed(0)
+    d = str(tmp_path / "ck")
+    approx = dict(n_samples=4, n_thinning=4, burnin_length=20, step_schedule=1e-3)
+    pm = ProbClassifier(model=MLP(), posterior_approximator=SGHMCPosteriorApproximator(**approx), seed=0)
+    pm.train(train_loader, calib_data_loader=test_loader,
+             fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=12), checkpointer=FitCheckpointer(save_checkpoint_dir=d)),
+             calib_config=CalibConfig(optimizer=CalibOptimizer(Adam(1e-2), n_epochs=5), processor=CalibProcessor(6)))
+    lt = pm.predictive.log_temp
+    for sub in ("c", "0", "3"):
+        stored = ck.restore_checkpoint(os.path.join(d, sub))["calib_params"]["output_calibrator"]["params"]["log_temp"]
+        np.testing.assert_array_equal(stored, lt.cpu().numpy())
+    pm2 = ProbClassifier(model=MLP(), posterior_approximator=SGHMCPosteriorApproximator(**approx), seed=1)
+    pm2.load_state(d)
+    assert torch.equal(pm2.predictive.log_temp, lt)
+    key = pm.rng.get()
+    inputs = test_loader.to_inputs_loader()
+    assert torch.equal(pm2.predictive.mean(inputs, 8, rng=key), pm.predictive.mean(inputs, 8, rng=key))

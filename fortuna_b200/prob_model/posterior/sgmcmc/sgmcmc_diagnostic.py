@@ -66,7 +66,7 @@ def effective_sample_size(samples: List, filter_threshold: Optional[float] = 0.0
     out = ops.ess(_as_matrix(samples, dev), filter_threshold)
     first = samples[0] if isinstance(samples, (list, tuple)) and len(samples) else None
     if isinstance(first, FlatTree):
-        vals, off, res = {}, 0, {}
+        off, res = 0, {}
         for path, n, shp in zip(first.paths, first.lens, first.shapes):
             d = res
             for k in path[:-1]:

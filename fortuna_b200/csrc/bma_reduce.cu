@@ -612,8 +612,9 @@ static int launch_cls_narrow(const ClsArgs& a, cudaStream_t st) {
 // the price of rows that do not fit on chip.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) wide_lse_kernel(const T* __restrict__ z, int64_t rows, int C, float scale,
-                                                       float* __restrict__ lse) {
+__global__ void __launch_bounds__(256) wide_lse_kernel(const T* __restrict__ z, int64_t rows, int C,
+                                                       const float* __restrict__ log_temp, float* __restrict__ lse) {
+  const float scale = log_temp ? expf(-log_temp[0]) : 1.0f;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -639,7 +640,8 @@ __global__ void __launch_bounds__(256) wide_lse_kernel(const T* __restrict__ z, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const float* __restrict__ lse, float scale) {
+__global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const float* __restrict__ lse) {
+  const float scale = a.log_temp ? expf(-a.log_temp[0]) : 1.0f;
   __shared__ float s_lse[1024];  // lse[s, b] of this input for up to 1024 samples (more: read from global)
   __shared__ float red_f[8][2];
   __shared__ float red_v[8];
@@ -719,7 +721,8 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const
 
 // log_prob / ensemble_log_prob of the wide path: gathers against the row logsumexp (same update as the fused kernel)
 template <typename T>
-__global__ void __launch_bounds__(256) wide_log_prob_kernel(const ClsArgs a, const float* __restrict__ lse, float scale) {
+__global__ void __launch_bounds__(256) wide_log_prob_kernel(const ClsArgs a, const float* __restrict__ lse) {
+  const float scale = a.log_temp ? expf(-a.log_temp[0]) : 1.0f;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
   const int y = a.targets[b];
@@ -750,24 +753,15 @@ __global__ void __launch_bounds__(256) wide_log_prob_kernel(const ClsArgs a, con
 
 template <typename T>
 static int launch_cls_wide(const ClsArgs& a, float* lse_ws, cudaStream_t st) {
-  float scale = 1.0f;
-  if (a.log_temp) {
-    float lt = 0.0f;
-    cudaError_t e = cudaMemcpyAsync(&lt, a.log_temp, sizeof(float), cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaStreamSynchronize(st);  // the wide path is not latency-critical: one scalar read-back
-    if (e != cudaSuccess) return (int)e;
-    scale = expf(-lt);
-  }
   const int64_t rows = (int64_t)a.S * a.B;
   int64_t blocks = (rows + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  wide_lse_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const T*>(a.logits), rows, a.C, scale, lse_ws);
+  wide_lse_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const T*>(a.logits), rows, a.C, a.log_temp, lse_ws);
   FB200_LAUNCH_CHECK();
-  wide_reduce_kernel<T><<<(unsigned)a.B, 256, 0, st>>>(a, lse_ws, scale);
+  wide_reduce_kernel<T><<<(unsigned)a.B, 256, 0, st>>>(a, lse_ws);
   FB200_LAUNCH_CHECK();
   if (a.targets && (a.out.log_prob || a.out.ensemble_log_prob)) {
-    wide_log_prob_kernel<T><<<(unsigned)((a.B + 255) / 256), 256, 0, st>>>(a, lse_ws, scale);
+    wide_log_prob_kernel<T><<<(unsigned)((a.B + 255) / 256), 256, 0, st>>>(a, lse_ws);
     FB200_LAUNCH_CHECK();
   }
   return 0;

@@ -229,7 +229,7 @@ int fb200_bma_reduce_cls(const void* logits, int dtype, const float* log_temp, c
 
 /* The same outputs for heads of ANY width (the single-pass kernel above keeps a row in one warp's registers: C <= 1024).
  * Two passes over [S,B,C] - row logsumexp into `workspace` (fb200_bma_reduce_cls_wide_workspace_bytes = S*B floats),
- * then one CTA per input - i.e. twice the HBM traffic; log_temp, when given, is read back once (one stream sync). */
+ * then one CTA per input - i.e. twice the HBM traffic. */
 size_t fb200_bma_reduce_cls_wide_workspace_bytes(int S, int B);
 int fb200_bma_reduce_cls_wide(const void* logits, int dtype, const float* log_temp, const int32_t* targets, int S, int B,
                               int C, const fb200_cls_outputs_t* out, void* workspace, size_t workspace_bytes,

@@ -68,6 +68,8 @@ class ClsOutputs(C.Structure):
             "epistemic_entropy",
             "log_prob",
             "ensemble_log_prob",
+            "confidence",
+            "brier_terms",
         )
     ]
 
@@ -132,6 +134,7 @@ SIGNATURES = {
     "fb200_aps_conformal_sets": (_i, [_P, _i, _i, _P, _i, _f, _P, _P, _P, _P]),
     "fb200_conformal_sets": (_i, [_P, _i, _P, _i, _i, _f, _P, _P, _P]),
     "fb200_ece_bins": (_i, [_P, _i, _i, _P, _P, _P, _i, _P, _P, _P, _P, _P, _P]),
+    "fb200_ece_bins_from_rows": (_i, [_P, _P, _P, _P, _i, _P, _i, _P, _P, _P, _P, _P, _P]),
     "fb200_ece_from_bins": (_i, [_P, _P, _P, _i, _i64, _P, _P]),
     "fb200_quantile_axis0": (_i, [_P, _i, _i64, _P, _i, _P, _P]),
     "fb200_calib_cls_workspace_bytes": (_sz, [_i, _i]),

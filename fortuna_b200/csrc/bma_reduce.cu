@@ -383,6 +383,8 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
     float ent_terms = 0.0f;
     float best_v = -CUDART_INF_F;
     int best_c = 0x7FFFFFFF;
+    float msq = 0.0f, mean_y = 0.0f;  // Brier term of the row: sum_c mean^2 - 2 mean_y + 1
+    const bool want_brier = a.out.brier_terms != nullptr;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int c0 = (g + G * j) * VEC;
@@ -391,6 +393,10 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
           mean[k] = s_pow2 ? sp[j][k] * inv_Sf : sp[j][k] / Sf;
+          if (want_brier) {
+            msq = fmaf(mean[k], mean[k], msq);
+            mean_y = (c0 + k == y) ? mean[k] : mean_y;
+          }
           const float spq = sp[j][k] - sp2[j][k];  // sum_s p(1-p)
           av[k] = s_pow2 ? spq * inv_Sf : spq / Sf;
           const float m2 = s_pow2 ? sp2[j][k] * inv_Sf : sp2[j][k] / Sf;
@@ -436,12 +442,18 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
         best_c = oc;
       }
     }
+    if (want_brier) {
+      msq = group_sum<G>(msq);
+      mean_y = group_sum<G>(mean_y);  // one lane of the row held the target class
+    }
     if (valid_row && g == 0) {
       if (a.out.entropy) a.out.entropy[b] = ent;
       if (a.out.aleatoric_entropy) a.out.aleatoric_entropy[b] = alea;
       if (a.out.epistemic_entropy) a.out.epistemic_entropy[b] = ent - alea;
       if (a.out.mode) a.out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
       if (a.out.log_prob) a.out.log_prob[b] = (lmax + logf(lsum)) - a.log_S;
+      if (a.out.confidence) a.out.confidence[b] = best_v;
+      if (want_brier) a.out.brier_terms[b] = y_ok ? (msq - 2.0f * mean_y) + 1.0f : msq;
     }
   }
 }
@@ -561,7 +573,7 @@ __global__ void __launch_bounds__(32 * kNarrowStreams) bma_reduce_cls_narrow_ker
   }
   const float Sf = (float)S;
   const float spl_row = 0.6931471805599453f * (spl - sum_l);
-  float ent_terms = 0.0f, best_v = -CUDART_INF_F;
+  float ent_terms = 0.0f, best_v = -CUDART_INF_F, msq = 0.0f, mean_y = 0.0f;
   int best_c = 0x7FFFFFFF;
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) {
@@ -569,6 +581,8 @@ __global__ void __launch_bounds__(32 * kNarrowStreams) bma_reduce_cls_narrow_ker
       const float mean = sp[c] / Sf;
       const float av = (sp[c] - sp2[c]) / Sf;
       const float ev = fmaxf(0.0f, __fsub_rn(sp2[c] / Sf, __fmul_rn(mean, mean)));
+      msq = fmaf(mean, mean, msq);
+      if (c == y) mean_y = mean;
       if (mean > 0.0f) ent_terms = fmaf(mean, logf(mean), ent_terms);
       if (mean > best_v) {
         best_v = mean;
@@ -589,6 +603,8 @@ __global__ void __launch_bounds__(32 * kNarrowStreams) bma_reduce_cls_narrow_ker
   if (a.out.epistemic_entropy) a.out.epistemic_entropy[b] = ent - alea;
   if (a.out.mode) a.out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
   if (a.out.log_prob) a.out.log_prob[b] = (lmax + logf(lsum)) - a.log_S;
+  if (a.out.confidence) a.out.confidence[b] = best_v;
+  if (a.out.brier_terms) a.out.brier_terms[b] = y_ok ? (msq - 2.0f * mean_y) + 1.0f : msq;
 }
 
 template <typename T>
@@ -643,7 +659,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const float* __restrict__ lse) {
   const float scale = a.log_temp ? expf(-a.log_temp[0]) : 1.0f;
   __shared__ float s_lse[1024];  // lse[s, b] of this input for up to 1024 samples (more: read from global)
-  __shared__ float red_f[8][2];
+  __shared__ float red_f[8][4];
   __shared__ float red_v[8];
   __shared__ int red_c[8];
   const int S = a.S, B = a.B, C = a.C;
@@ -654,8 +670,9 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const
   const T* base = reinterpret_cast<const T*>(a.logits) + (size_t)b * C;
   const size_t sstride = (size_t)B * C;
   const float Sf = (float)S;
-  float ent_terms = 0.0f, plogp = 0.0f, best_v = -CUDART_INF_F;
+  float ent_terms = 0.0f, plogp = 0.0f, best_v = -CUDART_INF_F, msq = 0.0f, mean_y = 0.0f;
   int best_c = 0x7FFFFFFF;
+  const int y = a.targets ? a.targets[b] : -1;
   for (int c = tid; c < C; c += blockDim.x) {
     float sp = 0.0f, sp2 = 0.0f;
     for (int s = 0; s < S; ++s) {
@@ -670,6 +687,8 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const
     const float mean = sp / Sf;
     const float av = (sp - sp2) / Sf;
     const float ev = fmaxf(0.0f, __fsub_rn(sp2 / Sf, __fmul_rn(mean, mean)));
+    msq = fmaf(mean, mean, msq);
+    if (c == y) mean_y = mean;
     if (mean > 0.0f) ent_terms = fmaf(mean, logf(mean), ent_terms);
     if (mean > best_v) {
       best_v = mean;
@@ -684,6 +703,8 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const
   }
   ent_terms = group_sum<32>(ent_terms);
   plogp = group_sum<32>(plogp);
+  msq = group_sum<32>(msq);
+  mean_y = group_sum<32>(mean_y);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
@@ -696,16 +717,20 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const
   if (lane == 0) {
     red_f[w][0] = ent_terms;
     red_f[w][1] = plogp;
+    red_f[w][2] = msq;
+    red_f[w][3] = mean_y;
     red_v[w] = best_v;
     red_c[w] = best_c;
   }
   __syncthreads();
   if (tid == 0) {
-    float e = 0.0f, pl = 0.0f, bv = -CUDART_INF_F;
+    float e = 0.0f, pl = 0.0f, bv = -CUDART_INF_F, sq = 0.0f, my = 0.0f;
     int bc = 0x7FFFFFFF;
     for (int q = 0; q < (int)(blockDim.x >> 5); ++q) {
       e += red_f[q][0];
       pl += red_f[q][1];
+      sq += red_f[q][2];
+      my += red_f[q][3];
       if (red_v[q] > bv || (red_v[q] == bv && red_c[q] < bc)) {
         bv = red_v[q];
         bc = red_c[q];
@@ -716,6 +741,8 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const
     if (a.out.aleatoric_entropy) a.out.aleatoric_entropy[b] = alea;
     if (a.out.epistemic_entropy) a.out.epistemic_entropy[b] = ent - alea;
     if (a.out.mode) a.out.mode[b] = bc == 0x7FFFFFFF ? 0 : bc;
+    if (a.out.confidence) a.out.confidence[b] = bv;
+    if (a.out.brier_terms) a.out.brier_terms[b] = (y >= 0 && y < C) ? (sq - 2.0f * my) + 1.0f : sq;
   }
 }
 
@@ -835,6 +862,7 @@ __global__ void __launch_bounds__(256) bma_finalize_slots_kernel(const float* __
     if (out.aleatoric_entropy) out.aleatoric_entropy[b] = alea;
     if (out.epistemic_entropy) out.epistemic_entropy[b] = ent - alea;
     if (out.mode) out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
+    if (out.confidence) out.confidence[b] = best_v;
     if (out.log_prob) out.log_prob[b] = (M + logf(ssum)) - log_S;
   }
 }
@@ -1078,7 +1106,7 @@ extern "C" int fb200_bma_reduce_cls(const void* logits, int dtype, const float* 
   if (!out) return FB200_E_NULL;
   ClsArgs a{};
   a.out = *out;
-  if ((a.out.log_prob || a.out.ensemble_log_prob) && !targets) return FB200_E_NULL;
+  if ((a.out.log_prob || a.out.ensemble_log_prob || a.out.brier_terms) && !targets) return FB200_E_NULL;
   return reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
 }
 
@@ -1092,7 +1120,7 @@ extern "C" int fb200_bma_reduce_cls_wide(const void* logits, int dtype, const fl
   if (!logits || !out || !workspace) return FB200_E_NULL;
   if (S <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
   if (dtype != FB200_F32 && dtype != FB200_BF16) return FB200_E_UNSUPPORTED;
-  if ((out->log_prob || out->ensemble_log_prob) && !targets) return FB200_E_NULL;
+  if ((out->log_prob || out->ensemble_log_prob || out->brier_terms) && !targets) return FB200_E_NULL;
   if (workspace_bytes < fb200_bma_reduce_cls_wide_workspace_bytes(S, B)) return FB200_E_WORKSPACE;
   ClsArgs a{};
   a.out = *out;
@@ -1128,6 +1156,7 @@ extern "C" int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int r
                                             const fb200_cls_outputs_t* out, void* stream) {
   if (!slots || !out) return FB200_E_NULL;
   if (out->ensemble_log_prob) return FB200_E_UNSUPPORTED;  // per-sample values live on the rank that holds the sample
+  if (out->brier_terms) return FB200_E_UNSUPPORTED;        // needs the targets: use fb200_ece_bins on the finalised mean
   if (n_src <= 0 || rows <= 0 || C <= 0 || s_total <= 0) return FB200_E_SHAPE;
   const int64_t threads = (int64_t)rows * 32;
   bma_finalize_slots_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(

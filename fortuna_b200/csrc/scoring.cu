@@ -875,7 +875,8 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
                                                        const int32_t* __restrict__ targets,
                                                        const float* __restrict__ thresholds, int n_bins,
                                                        int32_t* __restrict__ bin_idx, int32_t* __restrict__ counts,
-                                                       int32_t* __restrict__ correct, float* __restrict__ scratch) {
+                                                       int32_t* __restrict__ correct, float* __restrict__ scratch,
+                                                       const float* __restrict__ brier_rows) {
   // Float sums are accumulated in 64-bit fixed point (confidences in units of 2^-40, Brier terms of 2^-38):
   // integer atomics commute, so the result does not depend on the order CTAs and warps arrive in.
   __shared__ float thr[kMaxBins];
@@ -918,6 +919,8 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
         if (ok) atomicAdd(&s_correct[bin], 1);
       }
       if (ok) atomicAdd(&s_ncorrect, 1);
+      // per-row Brier terms computed upstream (the reduction kernel's epilogue): same fixed-point accumulation
+      if (brier_rows && targets) atomicAdd(&s_brier, (unsigned long long)((double)brier_rows[b] * 274877906944.0));
     }
   } else {
     // one warp per row: max / first-argmax / Brier term by shuffle reduction, lane 0 bins the row
@@ -1275,9 +1278,33 @@ extern "C" int fb200_ece_bins(const float* probs, int B, int C, const int32_t* p
   int64_t blocks = C == 1 ? ((int64_t)B + 255) / 256 : ((int64_t)B + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ece_bins_kernel<<<(unsigned)blocks, 256, 0, st>>>(probs, B, C, preds, targets, thresholds, n_bins, bin_idx,
-                                                    counts, correct, result);
+                                                    counts, correct, result, nullptr);
   FB200_LAUNCH_CHECK();
   ece_finalize_kernel<<<1, 1, 0, st>>>(counts, conf_sums, correct, n_bins, B, C, result);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_ece_bins_from_rows(const float* confidence, const int32_t* preds, const float* brier_terms,
+                                        const int32_t* targets, int B, const float* thresholds, int n_bins,
+                                        int32_t* bin_idx, int32_t* counts, float* conf_sums, int32_t* correct,
+                                        float* result, void* stream) {
+  if (!confidence || !preds || !thresholds || !counts || !conf_sums || !correct || !result) return FB200_E_NULL;
+  if (B <= 0 || n_bins <= 0) return FB200_E_SHAPE;
+  if (n_bins > kMaxBins) return FB200_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_bins, st)) != cudaSuccess) return (int)e;
+  if ((e = cudaMemsetAsync(correct, 0, sizeof(int32_t) * n_bins, st)) != cudaSuccess) return (int)e;
+  if ((reinterpret_cast<uintptr_t>(result) & 7u) != 0) return FB200_E_ALIGN;
+  if ((e = cudaMemsetAsync(result, 0, sizeof(float) * (4 + 2 * n_bins), st)) != cudaSuccess) return (int)e;
+  int64_t blocks = ((int64_t)B + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ece_bins_kernel<<<(unsigned)blocks, 256, 0, st>>>(confidence, B, 1, preds, targets, thresholds, n_bins, bin_idx, counts,
+                                                    correct, result, brier_terms);
+  FB200_LAUNCH_CHECK();
+  // C = 2 makes the finaliser report the Brier score (it is undefined for bare confidences, C = 1)
+  ece_finalize_kernel<<<1, 1, 0, st>>>(counts, conf_sums, correct, n_bins, B, brier_terms ? 2 : 1, result);
   FB200_LAUNCH_CHECK();
   return 0;
 }

@@ -313,7 +313,7 @@ def transpose_w_bf16(w):
 # ------------------------------------------------------------------------------------------- reductions
 CLS_FIELDS = tuple(n for n, _ in _lib.ClsOutputs._fields_)
 _CLS_BC = ("mean", "aleatoric_variance", "epistemic_variance", "variance", "std")
-_CLS_B = ("entropy", "aleatoric_entropy", "epistemic_entropy", "log_prob")
+_CLS_B = ("entropy", "aleatoric_entropy", "epistemic_entropy", "log_prob", "confidence", "brier_terms")
 
 
 def _alloc_cls_outputs(want, S, B, Cn, device):
@@ -534,6 +534,28 @@ def conformal_sets(val_scores_sorted, test_scores, threshold):
         "fb200_conformal_sets",
     )
     return mask, sizes
+
+
+def ece_bins_from_rows(confidence, preds, targets, thresholds, brier_terms=None, want_bin_idx=False):
+    """ece_bins from the per-row confidence / prediction / Brier term the reduction kernel emits (no pass over [B,C])."""
+    B = confidence.shape[0]
+    nb = thresholds.numel()
+    dev = confidence.device
+    counts = torch.empty(nb, dtype=torch.int32, device=dev)
+    correct = torch.empty(nb, dtype=torch.int32, device=dev)
+    conf_sums = torch.empty(nb, dtype=torch.float32, device=dev)
+    result = torch.empty(4 + 2 * nb, dtype=torch.float32, device=dev)
+    bin_idx = torch.empty(B, dtype=torch.int32, device=dev) if want_bin_idx else None
+    check(
+        lib().fb200_ece_bins_from_rows(
+            _ptr(confidence, torch.float32), _ptr(preds, torch.int32), _ptr(brier_terms, torch.float32, True),
+            _ptr(targets, torch.int32, True), B, _ptr(thresholds, torch.float32), nb, _ptr(bin_idx, None, True),
+            _ptr(counts), _ptr(conf_sums), _ptr(correct), _ptr(result), _stream(),
+        ),
+        "fb200_ece_bins_from_rows",
+    )
+    return {"counts": counts, "conf_sums": conf_sums, "correct": correct, "result": result[:4], "bin_idx": bin_idx,
+            "confs": result[4 : 4 + nb], "accs": result[4 + nb : 4 + 2 * nb]}
 
 
 def ece_bins(probs, targets, thresholds, preds=None, want_bin_idx=False):

@@ -57,6 +57,9 @@ class PredictivePipeline:
         self.S, self.B, self.C = S, B, C
         self.device = device
         self.want = tuple(want)
+        # single GPU: the reduction kernel also emits the three per-row quantities the ECE needs (K7 then reads 3 B floats
+        # instead of the [B,C] mean)
+        self._kernel_want = self.want + tuple(n for n in ("mode", "confidence", "brier_terms") if n not in want) if world == 1 else self.want
         self.world, self.rank = world, rank
         self.B_local = B // world
         self.outs: Dict[str, torch.Tensor] = {}
@@ -93,7 +96,8 @@ class PredictivePipeline:
         if kernel_events:
             kernel_events[0].record()
         if self.world == 1:
-            self.outs = ops.bma_reduce_cls(z, self.want, targets=targets, out=self.outs or None)
+            self.outs = ops.bma_reduce_cls(z, self._kernel_want if targets is not None else self.want, targets=targets,
+                                           out=self.outs or None)
             if kernel_events:
                 kernel_events[1].record()
             return self.outs
@@ -117,7 +121,12 @@ class PredictivePipeline:
         lo, hi = self.rank * self.B_local, (self.rank + 1) * self.B_local
         t_local = targets[lo:hi] if self.world > 1 else targets
         self.mask, self.sizes = aps_sets(mean, calib)
-        self.ece = ops.ece_bins(mean, t_local, self.thresholds)
+        if self.world == 1 and "confidence" in self.outs:
+            # the reduction kernel's epilogue already holds max_c mean, its arg-max and the Brier term of every row
+            self.ece = ops.ece_bins_from_rows(self.outs["confidence"], self.outs["mode"], t_local, self.thresholds,
+                                              brier_terms=self.outs.get("brier_terms"))
+        else:
+            self.ece = ops.ece_bins(mean, t_local, self.thresholds)
         if self.world > 1:
             self.exchange.allreduce_bins(self.ece)
             self.ece["result_global"] = ops.ece_from_bins(self.ece["counts"], self.ece["conf_sums"], self.ece["correct"], self.B)

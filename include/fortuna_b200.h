@@ -220,6 +220,8 @@ typedef struct {
   float* epistemic_entropy;  /* [B]    entropy - aleatoric_entropy                         */
   float* log_prob;           /* [B]    logsumexp_s(ll) - log S          (needs targets)    */
   float* ensemble_log_prob;  /* [S,B]  ll[s,b] = z[s,b,y_b] - lse_c     (needs targets)    */
+  float* confidence;         /* [B]    max_c mean - the confidence the ECE bins (metric/classification.py:74-87) */
+  float* brier_terms;        /* [B]    sum_c (mean_c - onehot(y)_c)^2 (metric/classification.py:213-220; needs targets) */
 } fb200_cls_outputs_t;
 
 /* logits: [S,B,C] in `dtype`; log_temp: optional device float[1] (z = logits * exp(-log_temp));
@@ -322,6 +324,12 @@ int fb200_aps_conformal_sets(const float* probs, int B, int C, const float* val_
 int fb200_ece_bins(const float* probs, int B, int C, const int32_t* preds, const int32_t* targets,
                    const float* thresholds, int n_bins, int32_t* bin_idx, int32_t* counts, float* conf_sums,
                    int32_t* correct, float* result, void* stream);
+/* The same outputs from per-row quantities the reduction kernel already has in its epilogue (fb200_cls_outputs_t:
+ * confidence = max_c mean, mode = argmax, brier_terms): the [B,C] mean is not read a second time.
+ * brier_terms optional (result[3] = NaN without it). */
+int fb200_ece_bins_from_rows(const float* confidence, const int32_t* preds, const float* brier_terms,
+                             const int32_t* targets, int B, const float* thresholds, int n_bins, int32_t* bin_idx,
+                             int32_t* counts, float* conf_sums, int32_t* correct, float* result, void* stream);
 /* result[2] = {ECE, MCE} over n_total data points from bin counters that were summed over shards (the counters
  * fb200_ece_bins returns are additive: all-reduce them across the ranks of a B-sharded evaluation, then call this). */
 int fb200_ece_from_bins(const int32_t* counts, const float* conf_sums, const int32_t* correct, int n_bins,

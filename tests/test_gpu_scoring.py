@@ -248,3 +248,26 @@ def test_fused_aps_conformal_sets_equal_the_two_kernels(cuda, B, C, n_val, error
     assert torch.equal(m2, mask) and torch.equal(s2, sz)
     m3, s3 = ops.conformal_sets(vs, ops.aps_scores(tpt, None), thr)
     assert torch.equal(m3, mask) and torch.equal(s3, sz)
+
+
+@pytest.mark.parametrize("S,B,C", [(8, 4096, 1000), (16, 1000, 10), (5, 77, 2), (3, 40, 1500)])
+def test_ece_from_reduction_rows_equals_ece_on_the_mean(cuda, S, B, C):
+    """confidence / mode / brier_terms out of the reduction kernel's epilogue + fb200_ece_bins_from_rows == fb200_ece_bins
+    on the [B,C] mean: identical bin indices and counts, ECE / MCE / accuracy / Brier within float rounding."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(S + C)
+    z = torch.from_numpy((3 * r.standard_normal((S, B, C))).astype(np.float32)).to(cuda)
+    t = torch.from_numpy(r.integers(0, C, B).astype(np.int32)).to(cuda)
+    o = ops.bma_reduce_cls(z, ("mean", "mode", "confidence", "brier_terms"), targets=t)
+    mean = o["mean"]
+    assert torch.equal(o["confidence"], mean.max(-1).values)
+    oh = torch.zeros_like(mean)
+    oh[torch.arange(B, device=cuda), t.long()] = 1
+    np.testing.assert_allclose(o["brier_terms"].cpu().numpy(), ((mean - oh) ** 2).sum(-1).cpu().numpy(), rtol=2e-5, atol=1e-7)
+    thr = torch.from_numpy(Sc.ece_thresholds(B)).to(cuda)
+    a = ops.ece_bins(mean, t, thr, want_bin_idx=True)
+    b = ops.ece_bins_from_rows(o["confidence"], o["mode"], t, thr, brier_terms=o["brier_terms"], want_bin_idx=True)
+    assert torch.equal(a["bin_idx"], b["bin_idx"]) and torch.equal(a["counts"], b["counts"]) and torch.equal(a["correct"], b["correct"])
+    assert torch.equal(a["conf_sums"], b["conf_sums"])  # fixed-point sums of the same confidences: identical
+    np.testing.assert_allclose(b["result"].cpu().numpy(), a["result"].cpu().numpy(), rtol=1e-5, atol=1e-7)

@@ -3,10 +3,11 @@
 
 One "step" = one pass of the predictive path over one batch of synthetic calibrated logits
 z[S=64, B=65536, C=1000] (float32, 16.8 GB, larger than L2):
-    fb200_bma_reduce_cls   -> mean, aleatoric/epistemic variance, entropy + split, log_prob, mode
-    fb200_aps_scores       -> adaptive-prediction-set scores for every class of the mean  [B,C]
-    fb200_conformal_sets   -> rank-count sets against 50 000 pre-sorted validation scores
-    fb200_ece_bins         -> ECE / MCE / accuracy / Brier of the mean
+    fb200_bma_reduce_cls      -> mean, aleatoric/epistemic variance, entropy + split, log_prob, mode
+                                 (+ per-row confidence and Brier term for the ECE)
+    fb200_aps_conformal_sets  -> adaptive-prediction-set scores for every class of the mean and the rank-count sets
+                                 against 50 000 pre-sorted validation scores, one kernel
+    fb200_ece_bins_from_rows  -> ECE / MCE / accuracy / Brier of the mean from those per-row quantities
 `value` times that with z resident in HBM; `e2e` times the same work through the public
 `predictive_from_logits_batches` call with pinned HOST batches (H2D of every batch and D2H of every
 result inside the timed region).  `--impl reference` times the CPU oracle (numpy restatement of the

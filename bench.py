@@ -374,7 +374,9 @@ def run_gpu_arm(args):
     # roofline of the dominant kernel: algorithmic bytes per launch / measured launch time
     # logits read once + outputs written once: single GPU -> mean + two variance arrays [B,C] and six [B] vectors;
     # shard mode -> one slot row of 2C+4 floats per input (sum p, sum p^2, three scalars)
-    alg_bytes = 4.0 * S * B * Cn + (4.0 * 3 * B * Cn + 4.0 * B * 6 if world == 1 else 4.0 * B * (2 * Cn + 4))
+    # with the peer-store exchange only the rows this rank owns (1/N of them) land in its own HBM - the rest leaves over
+    # NVLink - and it RECEIVES (N-1)/N of a slot buffer from its peers: HBM bytes per rank = logits + one slot buffer
+    alg_bytes = 4.0 * S * B * Cn + (4.0 * 3 * B * Cn + 4.0 * B * 8 if world == 1 else 4.0 * B * (2 * Cn + 4))
     peak, peak_src = _peaks()
     achieved = alg_bytes / (reduce_ms * 1e-3) / 1e9
     traffic = None

@@ -524,6 +524,45 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
         tie |= (lane < 31) && (key[NR - 1] == nxt) && ((lane + 1) * NR < C);
       }
       const bool any_tie = __any_sync(0xffffffffu, tie);
+      // Sets without scores: no class needs its exact rank.  score(rank) >= q is a threshold function of the rank
+      // whenever the prefix sums are monotone around q (checked on the actual values: the tree order can break
+      // monotonicity by an ulp), so with distinct keys  rank(c) >= r1  <=>  prob(c) <= prob at rank r1  - one compare
+      // per class instead of the ten-probe rank lookup.  Rows with ties or a non-monotone boundary take the general path.
+      bool done = false;
+      if (a.cs_mask && !a.scores && !any_tie && !a.cs_all_true && !a.cs_all_false) {
+        const float q = __ldg(a.cs_val_sorted + a.cs_q_index);
+        int n_true = 0, first = 0x7FFFFFFF;
+#pragma unroll
+        for (int r = NR - 1; r >= 0; --r) {
+          const int rank = lane * NR + r;
+          const bool t = (rank < C) && !(x[r] < q);
+          n_true += t ? 1 : 0;
+          first = t ? rank : first;  // descending r: ends at the lane's smallest rank that is in
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          n_true += __shfl_xor_sync(0xffffffffu, n_true, o);
+          first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        }
+        const bool none = first == 0x7FFFFFFF;
+        if (none ? (n_true == 0) : (n_true == C - first)) {  // warp-uniform
+          float pb = 0.0f;  // probability at the boundary rank
+#pragma unroll
+          for (int r = 0; r < NR; ++r) pb = (lane * NR + r == first) ? f32_unordered(~key[r]) : pb;
+          pb = __shfl_sync(0xffffffffu, pb, none ? 0 : first / NR);
+          uint8_t* mrow = a.cs_mask + (size_t)b * C;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const int c = r * 32 + lane;
+            if (c < C) mrow[c] = (!none && (srow[c] + 0.0f) <= pb) ? 1 : 0;
+          }
+          if (lane == 0 && a.cs_sizes) a.cs_sizes[b] = n_true;
+          __syncwarp();
+          if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
+          done = true;
+        }
+      }
+      if (!done) {
       // the row's own keys again, class order, then the staging buffer is free for the next row
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
@@ -595,6 +634,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
           if (c < C) orow[c] = v;
         }
       }
+      }  // !done
       __syncwarp();
     }
   }

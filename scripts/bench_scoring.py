@@ -47,6 +47,8 @@ def main():
     val = ops.sort_f32_(ops.aps_scores(mean[:50000], t[:50000]))
     thr = conformal_threshold(val.numel(), 0.05)
     out["conformal_sets_ms"] = timed(lambda: ops.conformal_sets(val, scores, thr), a.iters)
+    out["aps_sets_fused_ms"] = timed(lambda: ops.aps_conformal_sets(mean, val, thr), a.iters)
+    out["aps_sets_fused_with_scores_ms"] = timed(lambda: ops.aps_conformal_sets(mean, val, thr, want_scores=True), a.iters)
     ethr = torch.from_numpy(ece_thresholds(a.B)).to(dev)
     out["ece_bins_ms"] = timed(lambda: ops.ece_bins(mean, t, ethr), a.iters)
     # conformal Bayes at the c2 shape: 30 draws, 60 000 training points, 10 000 test points x 10 classes

@@ -940,9 +940,24 @@ __global__ void __launch_bounds__(256) reg_sample_targets_kernel(const float* __
                                                                  const float* __restrict__ log_temp,
                                                                  const uint32_t* __restrict__ key, uint32_t T,
                                                                  uint32_t n_stored, int B, int d,
-                                                                 float* __restrict__ y, int32_t* __restrict__ idx_out) {
+                                                                 float* __restrict__ y, int32_t* __restrict__ idx_out,
+                                                                 int direct) {
   const uint32_t t = blockIdx.y;
   const uint32_t n = (uint32_t)B * (uint32_t)d;
+  if (direct) {
+    // RegressionProbOutputLayer.sample on ONE set of outputs (fortuna/prob_output_layer/regression.py:38-52, the
+    // output_calib_model predictive): y = mu + exp(0.5 logvar) * normal(rng, (T, B, d)) - one stream of T*B*d normals
+    const float lt = log_temp ? log_temp[0] : 0.0f;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+      const uint32_t b = e / (uint32_t)d, j = e - b * (uint32_t)d;
+      const float mu = z[(size_t)b * (2 * d) + j];
+      float lv = z[(size_t)b * (2 * d) + d + j];
+      if (log_temp) lv += lt;
+      const float eps = bits_to_normal(random_bits_elem(key[0], key[1], T * n, t * n + e));
+      y[(size_t)t * n + e] = mu + expf(0.5f * lv) * eps;
+    }
+    return;
+  }
   // per-t key schedule (identical in every thread of the row; a handful of threefry blocks)
   const uint32_t kt0 = random_bits_elem(key[0], key[1], 2u * T, 2u * t);
   const uint32_t kt1 = random_bits_elem(key[0], key[1], 2u * T, 2u * t + 1u);
@@ -1165,19 +1180,30 @@ extern "C" int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int r
   return 0;
 }
 
-extern "C" int fb200_reg_sample_targets(const float* outputs, const float* log_temp, const uint32_t* key,
-                                        int n_target_samples, int n_stored, int B, int d, float* y, int32_t* idx_out,
-                                        void* stream) {
+static int reg_sample_common(const float* outputs, const float* log_temp, const uint32_t* key, int n_target_samples,
+                             int n_stored, int B, int d, float* y, int32_t* idx_out, int direct, void* stream) {
   if (!outputs || !key || !y) return FB200_E_NULL;
   if (n_target_samples <= 0 || n_stored <= 0 || B <= 0 || d <= 0) return FB200_E_SHAPE;
   if ((long long)B * d >= 0xFFFFFFFFll || n_target_samples > 65535) return FB200_E_UNSUPPORTED;
   const long long n = (long long)B * d;
+  if (direct && n * n_target_samples >= 0xFFFFFFFFll) return FB200_E_UNSUPPORTED;  // one 32-bit counter stream
   unsigned gx = (unsigned)((n + 255) / 256);
   if (gx > 148u * 8u) gx = 148u * 8u;
   reg_sample_targets_kernel<<<dim3(gx, (unsigned)n_target_samples), 256, 0, (cudaStream_t)stream>>>(
-      outputs, log_temp, key, (uint32_t)n_target_samples, (uint32_t)n_stored, B, d, y, idx_out);
+      outputs, log_temp, key, (uint32_t)n_target_samples, (uint32_t)n_stored, B, d, y, idx_out, direct);
   FB200_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int fb200_reg_sample_targets(const float* outputs, const float* log_temp, const uint32_t* key,
+                                        int n_target_samples, int n_stored, int B, int d, float* y, int32_t* idx_out,
+                                        void* stream) {
+  return reg_sample_common(outputs, log_temp, key, n_target_samples, n_stored, B, d, y, idx_out, 0, stream);
+}
+
+extern "C" int fb200_reg_output_sample_targets(const float* outputs, const float* log_temp, const uint32_t* key,
+                                               int n_target_samples, int B, int d, float* y, void* stream) {
+  return reg_sample_common(outputs, log_temp, key, n_target_samples, 1, B, d, y, nullptr, 1, stream);
 }
 
 extern "C" int fb200_bma_reduce_reg(const float* outputs, const float* log_temp, const float* targets, int S,

@@ -28,11 +28,15 @@ template <>
 __device__ __forceinline__ float cal_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 // grid (row blocks, S).  part[(s * gridDim.x + blockIdx.x) * 2 + {0, 1}] = (sum ll, sum dll/dtau) of the CTA's rows.
-template <typename T>
+// FOCAL: the per-row term is the focal loss of OutputCalibClassifier.calibrate's default loss_fn
+// (fortuna/loss/classification/focal_loss.py:10-36, called from fortuna/output_calib_model/loss.py:26-79):
+//   p = softmax(tau z)[y];  loss = -(1 - p)^gamma log p;
+//   dloss/dtau = -( (1 - p)^gamma - gamma (1 - p)^(gamma - 1) p log p ) (z_y - sum_c p_c z_c)
+template <typename T, bool FOCAL>
 __global__ void __launch_bounds__(32 * CAL_WARPS) calib_cls_kernel(const T* __restrict__ z,
                                                                    const int32_t* __restrict__ targets,
                                                                    const float* __restrict__ log_temp, int B, int C,
-                                                                   double* __restrict__ part) {
+                                                                   float gamma, double* __restrict__ part) {
   __shared__ double red[CAL_WARPS][2];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int s = blockIdx.y;
@@ -56,8 +60,19 @@ __global__ void __launch_bounds__(32 * CAL_WARPS) calib_cls_kernel(const T* __re
     if (lane == 0) {
       const bool ok = (unsigned)y < (unsigned)C;
       const float zy = ok ? cal_load<T>(row + y) : 0.0f;
-      acc_ll += (double)(tau * (zy - m) - __logf(se));
-      acc_d += (double)(zy - sez / se);
+      if constexpr (FOCAL) {
+        const float p = ok ? expf(tau * (zy - m)) / se : 0.0f;
+        const float logp = logf(p), q = 1.0f - p;
+        const float powq = gamma == 2.0f ? q * q : (gamma == 0.0f ? 1.0f : powf(q, gamma));
+        const float dpow = gamma == 0.0f ? 0.0f : gamma * (gamma == 2.0f ? q : powf(q, gamma - 1.0f));
+        float dl = powq;
+        if (dpow != 0.0f && p > 0.0f) dl -= dpow * p * logp;
+        acc_ll += (double)(-(powq * logp));
+        acc_d += (double)(-dl * (zy - sez / se));
+      } else {
+        acc_ll += (double)(tau * (zy - m) - __logf(se));
+        acc_d += (double)(zy - sez / se);
+      }
     }
   }
   if (lane == 0) {
@@ -92,13 +107,14 @@ __global__ void calib_sum_kernel(const double* __restrict__ part, int S, int nbl
 // Regression temperature scaler (fortuna/output_calibrator/regression.py:7-19: log_var + log_temp): per posterior sample
 //   L_s = sum_b -0.5 sum_k ( exp(-(lv + lt)) (y - mu)^2 + lv + lt + log 2 pi ),   dL_s/dlt = sum_b -0.5 sum_k ( 1 - exp(-(lv + lt)) (y - mu)^2 )
 // z: [S, B, 2d] = [mu | log var], targets [B, d].  One thread per input, grid (blocks, S).
+// (c0, scale) = (log 2 pi, -0.5) gives the log-likelihood above; (0, 1) gives OutputCalibRegressor.calibrate's default
+// loss_fn, the variance-scaled squared error sum_k ( exp(-lv') (y - mu)^2 + lv' ) (fortuna/loss/regression/scaled_mse.py:6-26).
 __global__ void __launch_bounds__(256) calib_reg_kernel(const float* __restrict__ z, const float* __restrict__ targets,
-                                                        const float* __restrict__ log_temp, int B, int d,
-                                                        double* __restrict__ part) {
+                                                        const float* __restrict__ log_temp, int B, int d, float c0,
+                                                        float scale, double* __restrict__ part) {
   __shared__ double red[8][2];
   const int s = blockIdx.y;
   const float lt = log_temp ? log_temp[0] : 0.0f;
-  const float log2pi = 1.8378770664093453f;
   double acc_ll = 0.0, acc_d = 0.0;
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
     const float* r = z + ((size_t)s * B + b) * 2 * d;
@@ -107,11 +123,11 @@ __global__ void __launch_bounds__(256) calib_reg_kernel(const float* __restrict_
       const float lv = r[d + k] + lt;
       const float diff = targets[(size_t)b * d + k] - r[k];
       const float q = expf(-lv) * (diff * diff);
-      a += q + lv + log2pi;
+      a += q + lv + c0;
       g += 1.0f - q;
     }
-    acc_ll += (double)(-0.5f * a);
-    acc_d += (double)(-0.5f * g);
+    acc_ll += (double)(scale * a);
+    acc_d += (double)(scale * g);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -156,9 +172,9 @@ extern "C" size_t fb200_calib_cls_workspace_bytes(int S, int B) {
   return (size_t)S * (size_t)calib_blocks(B) * 2 * sizeof(double);
 }
 
-extern "C" int fb200_calib_cls_loss_terms(const void* logits, int dtype, const int32_t* targets, const float* log_temp,
-                                          int S, int B, int C, void* workspace, size_t workspace_bytes, double* out,
-                                          void* stream) {
+template <bool FOCAL>
+static int calib_cls_launch(const void* logits, int dtype, const int32_t* targets, const float* log_temp, int S, int B,
+                            int C, float gamma, void* workspace, size_t workspace_bytes, double* out, void* stream) {
   if (!logits || !targets || !workspace || !out) return FB200_E_NULL;
   if (S <= 0 || B <= 0 || C <= 0 || S > 65535) return FB200_E_SHAPE;
   if (workspace_bytes < fb200_calib_cls_workspace_bytes(S, B)) return FB200_E_WORKSPACE;
@@ -167,11 +183,11 @@ extern "C" int fb200_calib_cls_loss_terms(const void* logits, int dtype, const i
   double* part = reinterpret_cast<double*>(workspace);
   const dim3 grid((unsigned)nb, (unsigned)S);
   if (dtype == FB200_F32)
-    calib_cls_kernel<float><<<grid, 32 * CAL_WARPS, 0, st>>>(reinterpret_cast<const float*>(logits), targets, log_temp, B,
-                                                             C, part);
+    calib_cls_kernel<float, FOCAL><<<grid, 32 * CAL_WARPS, 0, st>>>(reinterpret_cast<const float*>(logits), targets,
+                                                                    log_temp, B, C, gamma, part);
   else if (dtype == FB200_BF16)
-    calib_cls_kernel<__nv_bfloat16><<<grid, 32 * CAL_WARPS, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits),
-                                                                     targets, log_temp, B, C, part);
+    calib_cls_kernel<__nv_bfloat16, FOCAL><<<grid, 32 * CAL_WARPS, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(logits), targets, log_temp, B, C, gamma, part);
   else
     return FB200_E_UNSUPPORTED;
   FB200_LAUNCH_CHECK();
@@ -180,22 +196,49 @@ extern "C" int fb200_calib_cls_loss_terms(const void* logits, int dtype, const i
   return 0;
 }
 
+extern "C" int fb200_calib_cls_loss_terms(const void* logits, int dtype, const int32_t* targets, const float* log_temp,
+                                          int S, int B, int C, void* workspace, size_t workspace_bytes, double* out,
+                                          void* stream) {
+  return calib_cls_launch<false>(logits, dtype, targets, log_temp, S, B, C, 0.0f, workspace, workspace_bytes, out,
+                                 stream);
+}
+
+extern "C" int fb200_output_calib_focal_loss_terms(const void* logits, int dtype, const int32_t* targets,
+                                                   const float* log_temp, int B, int C, float gamma, void* workspace,
+                                                   size_t workspace_bytes, double* out, void* stream) {
+  if (!(gamma >= 0.0f)) return FB200_E_SHAPE;
+  return calib_cls_launch<true>(logits, dtype, targets, log_temp, 1, B, C, gamma, workspace, workspace_bytes, out,
+                                stream);
+}
+
 extern "C" size_t fb200_calib_reg_workspace_bytes(int S, int B) {
   if (S <= 0 || B <= 0) return 0;
   return (size_t)S * (size_t)calib_reg_blocks(B) * 2 * sizeof(double);
 }
 
-extern "C" int fb200_calib_reg_loss_terms(const float* outputs, const float* targets, const float* log_temp, int S, int B,
-                                          int d, void* workspace, size_t workspace_bytes, double* out, void* stream) {
+static int calib_reg_launch(const float* outputs, const float* targets, const float* log_temp, int S, int B, int d,
+                            float c0, float scale, void* workspace, size_t workspace_bytes, double* out, void* stream) {
   if (!outputs || !targets || !workspace || !out) return FB200_E_NULL;
   if (S <= 0 || B <= 0 || d <= 0 || S > 65535) return FB200_E_SHAPE;
   if (workspace_bytes < fb200_calib_reg_workspace_bytes(S, B)) return FB200_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = calib_reg_blocks(B);
   double* part = reinterpret_cast<double*>(workspace);
-  calib_reg_kernel<<<dim3((unsigned)nb, (unsigned)S), 256, 0, st>>>(outputs, targets, log_temp, B, d, part);
+  calib_reg_kernel<<<dim3((unsigned)nb, (unsigned)S), 256, 0, st>>>(outputs, targets, log_temp, B, d, c0, scale, part);
   FB200_LAUNCH_CHECK();
   calib_sum_kernel<<<(S + 127) / 128, 128, 0, st>>>(part, S, nb, out);
   FB200_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int fb200_calib_reg_loss_terms(const float* outputs, const float* targets, const float* log_temp, int S, int B,
+                                          int d, void* workspace, size_t workspace_bytes, double* out, void* stream) {
+  return calib_reg_launch(outputs, targets, log_temp, S, B, d, 1.8378770664093453f, -0.5f, workspace, workspace_bytes,
+                          out, stream);
+}
+
+extern "C" int fb200_output_calib_scaled_mse_terms(const float* outputs, const float* targets, const float* log_temp,
+                                                   int B, int d, void* workspace, size_t workspace_bytes, double* out,
+                                                   void* stream) {
+  return calib_reg_launch(outputs, targets, log_temp, 1, B, d, 0.0f, 1.0f, workspace, workspace_bytes, out, stream);
 }

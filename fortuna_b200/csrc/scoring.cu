@@ -679,6 +679,10 @@ struct ClsSampleArgs {
   int B, C;
   int32_t* y;        // [T, B]
   int32_t* idx_out;  // [T] or null
+  // direct: ClassificationProbOutputLayer.sample on ONE set of outputs (the output_calib_model predictive,
+  // fortuna/output_calib_model/predictive/base.py:69-105 -> fortuna/prob_output_layer/classification.py:33-51):
+  //   keys_b = split(rng, B); y[:, b] = choice(keys_b[b], C, p=probs[b], shape=(T,))  - T uniforms under one key per input
+  int direct;
 };
 
 template <int NR>
@@ -687,26 +691,33 @@ __global__ void __launch_bounds__(256) cls_sample_targets_kernel(const ClsSample
   const int b = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const uint32_t t = blockIdx.y;
   if (b >= a.B) return;
-  // key schedule of draw t (same in every warp of the row)
-  const uint32_t kt0 = random_bits_elem(a.key[0], a.key[1], 2u * a.T, 2u * t);
-  const uint32_t kt1 = random_bits_elem(a.key[0], a.key[1], 2u * a.T, 2u * t + 1u);
-  uint32_t a0 = 0u, a1 = 2u, b0 = 1u, b1 = 3u;  // split(keys[t]): key1 = (a0, b0), key2 = (a1, b1)
-  threefry2x32(kt0, kt1, a0, a1);
-  threefry2x32(kt0, kt1, b0, b1);
-  uint32_t c0 = 0u, c1 = 2u, d0 = 1u, d1 = 3u;  // choice(key1, n_stored) = randint: split(key1) -> two single draws
-  threefry2x32(a0, b0, c0, c1);
-  threefry2x32(a0, b0, d0, d1);
-  uint32_t hi = 0u, hi1 = 0u, lo = 0u, lo1 = 0u;
-  threefry2x32(c0, d0, hi, hi1);
-  threefry2x32(c1, d1, lo, lo1);
-  uint32_t mult = 65536u % a.n_stored;
-  mult = (mult * mult) % a.n_stored;
-  const uint32_t i = ((hi % a.n_stored) * mult + (lo % a.n_stored)) % a.n_stored;
-  if (a.idx_out && b == 0 && lane == 0) a.idx_out[t] = (int32_t)i;
-  // keys_b[b] = split(key2, B)[b], then its single uniform in [0, 1)
-  const uint32_t kb0 = random_bits_elem(a1, b1, 2u * (uint32_t)a.B, 2u * (uint32_t)b);
-  const uint32_t kb1 = random_bits_elem(a1, b1, 2u * (uint32_t)a.B, 2u * (uint32_t)b + 1u);
-  const uint32_t bits = random_bits_elem(kb0, kb1, 1u, 0u);
+  uint32_t i = 0u, bits;
+  if (a.direct) {
+    const uint32_t kb0 = random_bits_elem(a.key[0], a.key[1], 2u * (uint32_t)a.B, 2u * (uint32_t)b);
+    const uint32_t kb1 = random_bits_elem(a.key[0], a.key[1], 2u * (uint32_t)a.B, 2u * (uint32_t)b + 1u);
+    bits = random_bits_elem(kb0, kb1, a.T, t);
+  } else {
+    // key schedule of draw t (same in every warp of the row)
+    const uint32_t kt0 = random_bits_elem(a.key[0], a.key[1], 2u * a.T, 2u * t);
+    const uint32_t kt1 = random_bits_elem(a.key[0], a.key[1], 2u * a.T, 2u * t + 1u);
+    uint32_t a0 = 0u, a1 = 2u, b0 = 1u, b1 = 3u;  // split(keys[t]): key1 = (a0, b0), key2 = (a1, b1)
+    threefry2x32(kt0, kt1, a0, a1);
+    threefry2x32(kt0, kt1, b0, b1);
+    uint32_t c0 = 0u, c1 = 2u, d0 = 1u, d1 = 3u;  // choice(key1, n_stored) = randint: split(key1) -> two single draws
+    threefry2x32(a0, b0, c0, c1);
+    threefry2x32(a0, b0, d0, d1);
+    uint32_t hi = 0u, hi1 = 0u, lo = 0u, lo1 = 0u;
+    threefry2x32(c0, d0, hi, hi1);
+    threefry2x32(c1, d1, lo, lo1);
+    uint32_t mult = 65536u % a.n_stored;
+    mult = (mult * mult) % a.n_stored;
+    i = ((hi % a.n_stored) * mult + (lo % a.n_stored)) % a.n_stored;
+    if (a.idx_out && b == 0 && lane == 0) a.idx_out[t] = (int32_t)i;
+    // keys_b[b] = split(key2, B)[b], then its single uniform in [0, 1)
+    const uint32_t kb0 = random_bits_elem(a1, b1, 2u * (uint32_t)a.B, 2u * (uint32_t)b);
+    const uint32_t kb1 = random_bits_elem(a1, b1, 2u * (uint32_t)a.B, 2u * (uint32_t)b + 1u);
+    bits = random_bits_elem(kb0, kb1, 1u, 0u);
+  }
   const float u = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
   // softmax of the row, rank-major: element lane * NR + r
   const float scale = a.log_temp ? expf(-a.log_temp[0]) : 1.0f;
@@ -1173,9 +1184,8 @@ extern "C" int fb200_credible_sets(const float* mean, int B, int C, float thresh
   return launch_row_sort(a, (cudaStream_t)stream);
 }
 
-extern "C" int fb200_cls_sample_targets(const float* logits, const float* log_temp, const uint32_t* key,
-                                        int n_target_samples, int n_stored, int B, int C, int32_t* y, int32_t* idx_out,
-                                        void* stream) {
+static int cls_sample_common(const float* logits, const float* log_temp, const uint32_t* key, int n_target_samples,
+                             int n_stored, int B, int C, int32_t* y, int32_t* idx_out, int direct, void* stream) {
   if (!logits || !key || !y) return FB200_E_NULL;
   if (n_target_samples <= 0 || n_stored <= 0 || B <= 0 || C <= 0) return FB200_E_SHAPE;
   if (C > 1024 || n_target_samples > 65535 || B >= (1 << 30)) return FB200_E_UNSUPPORTED;
@@ -1189,6 +1199,7 @@ extern "C" int fb200_cls_sample_targets(const float* logits, const float* log_te
   a.C = C;
   a.y = y;
   a.idx_out = idx_out;
+  a.direct = direct;
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 32) return launch_cls_sample<1>(a, st);
   if (C <= 64) return launch_cls_sample<2>(a, st);
@@ -1196,6 +1207,17 @@ extern "C" int fb200_cls_sample_targets(const float* logits, const float* log_te
   if (C <= 256) return launch_cls_sample<8>(a, st);
   if (C <= 512) return launch_cls_sample<16>(a, st);
   return launch_cls_sample<32>(a, st);
+}
+
+extern "C" int fb200_cls_sample_targets(const float* logits, const float* log_temp, const uint32_t* key,
+                                        int n_target_samples, int n_stored, int B, int C, int32_t* y, int32_t* idx_out,
+                                        void* stream) {
+  return cls_sample_common(logits, log_temp, key, n_target_samples, n_stored, B, C, y, idx_out, 0, stream);
+}
+
+extern "C" int fb200_cls_output_sample_targets(const float* logits, const float* log_temp, const uint32_t* key,
+                                               int n_target_samples, int B, int C, int32_t* y, void* stream) {
+  return cls_sample_common(logits, log_temp, key, n_target_samples, 1, B, C, y, nullptr, 1, stream);
 }
 
 extern "C" int fb200_simple_scores(const float* probs, const int32_t* targets, int B, int C, float* scores,

@@ -670,6 +670,63 @@ def calib_reg_loss_terms(outputs, targets, log_temp=None):
     return out
 
 
+def output_calib_focal_loss_terms(logits, targets, log_temp=None, gamma=2.0):
+    """logits [B,C] (uncalibrated), int32 targets [B] -> float64 [2]: sum_b -(1-p_b)^gamma log p_b with
+    p_b = softmax(exp(-log_temp) z_b)[y_b], and its derivative with respect to exp(-log_temp)."""
+    B, Cn = logits.shape
+    nbytes = int(lib().fb200_calib_cls_workspace_bytes(1, B))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=logits.device)
+    out = torch.empty(2, dtype=torch.float64, device=logits.device)
+    check(
+        lib().fb200_output_calib_focal_loss_terms(_ptr(logits, (torch.float32, torch.bfloat16)), _DT[logits.dtype],
+                                                  _ptr(targets, torch.int32), _ptr(log_temp, torch.float32, True), B, Cn,
+                                                  float(gamma), _ptr(ws), nbytes, _ptr(out), _stream()),
+        "fb200_output_calib_focal_loss_terms",
+    )
+    return out
+
+
+def output_calib_scaled_mse_terms(outputs, targets, log_temp=None):
+    """outputs [B,2d] (uncalibrated [mu | log var]), targets float32 [B,d] -> float64 [2]: the variance-scaled squared
+    error summed over b with log var + log_temp, and its derivative in log_temp."""
+    B, two_d = outputs.shape
+    nbytes = int(lib().fb200_calib_reg_workspace_bytes(1, B))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=outputs.device)
+    out = torch.empty(2, dtype=torch.float64, device=outputs.device)
+    check(
+        lib().fb200_output_calib_scaled_mse_terms(_ptr(outputs, torch.float32), _ptr(targets, torch.float32),
+                                                  _ptr(log_temp, torch.float32, True), B, two_d // 2, _ptr(ws), nbytes,
+                                                  _ptr(out), _stream()),
+        "fb200_output_calib_scaled_mse_terms",
+    )
+    return out
+
+
+def cls_output_sample_targets(logits, key, n_target_samples, log_temp=None):
+    """logits [B, C] -> y int32 [T, B]: ClassificationProbOutputLayer.sample's draws (T uniforms per input key)."""
+    B, Cn = logits.shape
+    y = torch.empty((n_target_samples, B), dtype=torch.int32, device=logits.device)
+    check(
+        lib().fb200_cls_output_sample_targets(_ptr(logits, torch.float32), _ptr(log_temp, torch.float32, True),
+                                              _ptr(key, KEY_DTYPE), int(n_target_samples), B, Cn, _ptr(y), _stream()),
+        "fb200_cls_output_sample_targets",
+    )
+    return y
+
+
+def reg_output_sample_targets(outputs, key, n_target_samples, log_temp=None):
+    """outputs [B, 2d] -> y float32 [T, B, d] = mu + exp(0.5 (log var + log_temp)) * normal(key, (T, B, d))."""
+    B, two_d = outputs.shape
+    d = two_d // 2
+    y = torch.empty((n_target_samples, B, d), dtype=torch.float32, device=outputs.device)
+    check(
+        lib().fb200_reg_output_sample_targets(_ptr(outputs, torch.float32), _ptr(log_temp, torch.float32, True),
+                                              _ptr(key, KEY_DTYPE), int(n_target_samples), B, d, _ptr(y), _stream()),
+        "fb200_reg_output_sample_targets",
+    )
+    return y
+
+
 def cls_sample_targets(logits, key, n_target_samples, log_temp=None, want_idx=False):
     """logits [n_stored, B, C] -> y int32 [T, B] (and the drawn posterior-sample indices int32 [T])."""
     n, B, Cn = logits.shape

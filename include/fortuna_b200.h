@@ -282,6 +282,12 @@ int fb200_bma_reduce_reg(const float* outputs, const float* log_temp, const floa
  * same key, so B here is the batch the noise shape refers to. */
 int fb200_reg_sample_targets(const float* outputs, const float* log_temp, const uint32_t* key, int n_target_samples,
                              int n_stored, int B, int d, float* y, int32_t* idx_out, void* stream);
+/* Target samples given ONE set of outputs - the output_calib_model predictive (Predictive.sample,
+ * fortuna/output_calib_model/predictive/base.py:69-105 -> RegressionProbOutputLayer.sample,
+ * fortuna/prob_output_layer/regression.py:38-52):  y = mu + exp(0.5 (log var + log_temp)) * normal(key, (T, B, d)),
+ * the same normals as jax.  outputs: float32 [B, 2d] UNcalibrated; y: float32 [T, B, d]; T * B * d < 2^32 - 1. */
+int fb200_reg_output_sample_targets(const float* outputs, const float* log_temp, const uint32_t* key,
+                                    int n_target_samples, int B, int d, float* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conformal / calibration scoring (K5-K9), bit-exact integer / index outputs.
@@ -357,6 +363,22 @@ int fb200_calib_cls_loss_terms(const void* logits, int dtype, const int32_t* tar
 size_t fb200_calib_reg_workspace_bytes(int S, int B);
 int fb200_calib_reg_loss_terms(const float* outputs, const float* targets, const float* log_temp, int S, int B, int d,
                                void* workspace, size_t workspace_bytes, double* out, void* stream);
+/* Losses of the output calibration models (OutputCalibClassifier / OutputCalibRegressor .calibrate,
+ * fortuna/output_calib_model/classification.py:71-116 and regression.py:66-114 -> Loss.__call__,
+ * fortuna/output_calib_model/loss.py:26-79, differentiated by OutputCalibModelCalibrator.training_step,
+ * fortuna/output_calib_model/output_calib_model_calibrator.py:224-257) with their DEFAULT loss functions, over ONE set of
+ * outputs (the whole calibration set is one step); one pass returns the loss sum and its derivative:
+ *   focal (fortuna/loss/classification/focal_loss.py:10-36): p_b = softmax(tau z_b)[y_b], tau = exp(-log_temp);
+ *     out[0] = sum_b -(1 - p_b)^gamma log p_b,  out[1] = d out[0] / d tau   (gamma = 0 is the cross entropy)
+ *   scaled MSE (fortuna/loss/regression/scaled_mse.py:6-26): lv' = log var + log_temp;
+ *     out[0] = sum_b sum_k ( exp(-lv') (y - mu)^2 + lv' ),  out[1] = d out[0] / d log_temp
+ * The reference's loss is the mean over b (the caller divides).  Workspaces: fb200_calib_cls_workspace_bytes(1, B) /
+ * fb200_calib_reg_workspace_bytes(1, B).  out: double[2]. */
+int fb200_output_calib_focal_loss_terms(const void* logits, int dtype, const int32_t* targets, const float* log_temp,
+                                        int B, int C, float gamma, void* workspace, size_t workspace_bytes, double* out,
+                                        void* stream);
+int fb200_output_calib_scaled_mse_terms(const float* outputs, const float* targets, const float* log_temp, int B, int d,
+                                        void* workspace, size_t workspace_bytes, double* out, void* stream);
 
 /* Target samples of the classification predictive - Predictive.sample (fortuna/prob_model/predictive/base.py:318-440)
  * -> ClassificationProbOutputLayer.sample (fortuna/prob_output_layer/classification.py:33-51), the reference's draws:
@@ -366,6 +388,12 @@ int fb200_calib_reg_loss_terms(const float* outputs, const float* targets, const
  * idx_out: optional int32 [T] (the drawn posterior samples). */
 int fb200_cls_sample_targets(const float* logits, const float* log_temp, const uint32_t* key, int n_target_samples,
                              int n_stored, int B, int C, int32_t* y, int32_t* idx_out, void* stream);
+/* Target samples given ONE set of logits - the output_calib_model predictive (Predictive.sample,
+ * fortuna/output_calib_model/predictive/base.py:69-105 -> ClassificationProbOutputLayer.sample,
+ * fortuna/prob_output_layer/classification.py:33-51): y[:, b] = choice(split(key, B)[b], C, p = softmax(logits[b] *
+ * exp(-log_temp)), shape = (T,)) - T uniforms under one key per input.  logits: float32 [B, C] (C <= 1024); y: int32 [T, B]. */
+int fb200_cls_output_sample_targets(const float* logits, const float* log_temp, const uint32_t* key,
+                                    int n_target_samples, int B, int C, int32_t* y, void* stream);
 
 /* Monte-Carlo entropies of the regression predictive (fortuna/prob_model/predictive/regression.py:51-267), bit-exact
  * target draws.  outputs: float32 [n_stored, B, 2d] = [mu, log sigma^2] of every stored posterior sample (d <= 8);

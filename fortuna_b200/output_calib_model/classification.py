@@ -54,7 +54,7 @@ class OutputCalibClassifier(OutputCalibModel):
 def _lt_tensor(log_temp, device, calibrator):
     if calibrator is None:
         return None
-    return torch.as_tensor(np.asarray(log_temp, dtype=np.float32).reshape(1), device=device)
+    return torch.as_tensor(np.array(log_temp, dtype=np.float32).reshape(1), device=device)
 
 
 def _cls_stat(z: torch.Tensor, name: str, log_temp, calibrator) -> torch.Tensor:

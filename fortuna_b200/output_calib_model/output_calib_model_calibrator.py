@@ -62,7 +62,7 @@ def resolve_loss(loss_fn: Callable, regression: bool):
 
 def loss_and_grad(kind, outputs: torch.Tensor, targets: torch.Tensor, log_temp: np.ndarray, identity: bool = False):
     """(loss, dloss/dlog_temp) at log_temp, float32 scalars; the mean over the calibration inputs."""
-    lt = None if identity else torch.as_tensor(np.asarray(log_temp, dtype=np.float32).reshape(1), device=outputs.device)
+    lt = None if identity else torch.as_tensor(np.array(log_temp, dtype=np.float32).reshape(1), device=outputs.device)
     n = outputs.shape[0]
     if kind[0] == "focal":
         t = ops.output_calib_focal_loss_terms(outputs, targets, lt, kind[1]).cpu().numpy()

@@ -35,7 +35,7 @@ class Predictive(WithRNG):
         if self.output_calib_manager is None or self.output_calib_manager.output_calibrator is None:
             return None
         lt = self.state.get().log_temp
-        return torch.as_tensor(np.asarray(lt, dtype=np.float32).reshape(1), device=device)
+        return torch.as_tensor(np.array(lt, dtype=np.float32).reshape(1), device=device)
 
     def _key(self, rng):
         return self.rng.get() if rng is None else rng

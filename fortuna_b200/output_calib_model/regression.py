@@ -32,7 +32,7 @@ class OutputCalibRegressor(OutputCalibModel):
         from .. import ops
 
         lt = None if self.output_calibrator is None else torch.as_tensor(
-            np.asarray(log_temp, dtype=np.float32).reshape(1), device=z.device)
+            np.array(log_temp, dtype=np.float32).reshape(1), device=z.device)
         return ops.bma_reduce_reg(z.unsqueeze(0), (name,), log_temp=lt)[name]
 
     def _predict_fn(self, outputs: torch.Tensor, log_temp) -> torch.Tensor:

@@ -52,6 +52,12 @@ class JointGrad(C.Structure):
 
 _P = C.c_void_p
 
+MAX_PEERS = 8
+
+
+class DpPeers(C.Structure):
+    _fields_ = [("n_ranks", C.c_int), ("rank", C.c_int), ("grad", C.c_void_p * MAX_PEERS), ("params", C.c_void_p * MAX_PEERS)]
+
 
 class ClsOutputs(C.Structure):
     _fields_ = [
@@ -108,6 +114,8 @@ SIGNATURES = {
         [_P, _P, _P, _P, _P, _i64, _P, _i, _P, _i64, _P, _P, _P, C.POINTER(SgmcmcHParams), _P],
     ),
     "fb200_sgd_explore_step_f32": (_i, [_P, _P, _P, _P, _i64, C.POINTER(SgmcmcHParams), _P]),
+    "fb200_sgmcmc_step_dp_f32": (_i, [_P, _P, _i64, _P, _i, _P, _i64, _i64, _P, _P, _P, C.POINTER(SgmcmcHParams),
+                                 C.POINTER(JointGrad), C.POINTER(DpPeers), _P]),
     "fb200_sgmcmc_step_joint_f32": (_i, [_P, _P, _P, _P, _i64, _P, _i, _P, _i64, _P, _P, _P, C.POINTER(SgmcmcHParams),
                                          C.POINTER(JointGrad), _P, _P, _P]),
     "fb200_sgd_explore_joint_workspace_doubles": (_i64, [_i64]),

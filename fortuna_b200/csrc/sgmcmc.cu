@@ -84,12 +84,46 @@ struct JointCoef {
   double* sq_part;   // [n_tiles] or NULL
 };
 
-template <bool RMS, bool JOINT>
+// Data-parallel mode (DP): the gradient all-reduce and the parameter broadcast of the reference's multi-device trainer
+// (lax.pmean of the per-device gradients, fortuna/training/trainer.py:793-795, then the replicated optimizer step) are
+// folded into the step.  Every rank owns a contiguous range of tiles; for its elements it LOADS the gradient from every
+// rank's buffer over NVLink (peer pointers into symmetric memory), averages in rank order, updates its slice of the
+// momentum / preconditioner state, and STORES the new parameters into every rank's replica.  Per rank that is the
+// traffic of a reduce-scatter plus an all-gather, but with the sampler arithmetic riding inside it and the optimizer
+// state touched once per element across the whole job instead of once per rank.
+struct DpPeers {
+  const float* grad[FB200_MAX_PEERS];
+  float* params[FB200_MAX_PEERS];
+  int n;
+  float inv_n;
+};
+
+__device__ __forceinline__ float4 dp_grad4(const DpPeers& dp, int64_t e) {
+  float4 v[FB200_MAX_PEERS];
+#pragma unroll
+  for (int p = 0; p < FB200_MAX_PEERS; ++p)
+    if (p < dp.n) v[p] = *reinterpret_cast<const float4*>(dp.grad[p] + e);
+  float4 a = v[0];
+#pragma unroll
+  for (int p = 1; p < FB200_MAX_PEERS; ++p)
+    if (p < dp.n) {
+      a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w;
+    }
+  a.x *= dp.inv_n; a.y *= dp.inv_n; a.z *= dp.inv_n; a.w *= dp.inv_n;
+  return a;
+}
+__device__ __forceinline__ float dp_grad1(const DpPeers& dp, int64_t e) {
+  float a = dp.grad[0][e];
+  for (int p = 1; p < dp.n; ++p) a += dp.grad[p][e];
+  return a * dp.inv_n;
+}
+
+template <bool RMS, bool JOINT, bool DP>
 __global__ void __launch_bounds__(256)
     sgmcmc_step_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ mom,
                        float* __restrict__ pv, float* __restrict__ upd, const fb200_leaf_t* __restrict__ leaves,
                        const uint2* __restrict__ leaf_keys, const fb200_tile_t* __restrict__ tiles,
-                       const StepCoef c, const JointCoef jc) {
+                       const StepCoef c, const JointCoef jc, const DpPeers dp) {
   const fb200_tile_t tile = tiles[blockIdx.x];
   const fb200_leaf_t leaf = leaves[tile.leaf];
   const uint2 key = leaf_keys[tile.leaf];
@@ -113,8 +147,14 @@ __global__ void __launch_bounds__(256)
 
   const bool vec = ((leaf.offset & 3) == 0) && ((h & 3u) == 0) && ((uint64_t)i0 + h + 3u < (uint64_t)n);
   if (vec) {
-    float4 g0 = *reinterpret_cast<const float4*>(grad + e0);
-    float4 g1 = *reinterpret_cast<const float4*>(grad + e1);
+    float4 g0, g1;
+    if constexpr (DP) {
+      g0 = dp_grad4(dp, e0);
+      g1 = dp_grad4(dp, e1);
+    } else {
+      g0 = *reinterpret_cast<const float4*>(grad + e0);
+      g1 = *reinterpret_cast<const float4*>(grad + e1);
+    }
     float4 m0 = *reinterpret_cast<const float4*>(mom + e0);
     float4 m1 = *reinterpret_cast<const float4*>(mom + e1);
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
@@ -153,8 +193,17 @@ __global__ void __launch_bounds__(256)
     if (params) {
       p0.x += u0.x; p0.y += u0.y; p0.z += u0.z; p0.w += u0.w;
       p1.x += u1.x; p1.y += u1.y; p1.z += u1.z; p1.w += u1.w;
-      *reinterpret_cast<float4*>(params + e0) = p0;
-      *reinterpret_cast<float4*>(params + e1) = p1;
+      if constexpr (DP) {
+#pragma unroll
+        for (int p = 0; p < FB200_MAX_PEERS; ++p)
+          if (p < dp.n) {
+            *reinterpret_cast<float4*>(dp.params[p] + e0) = p0;
+            *reinterpret_cast<float4*>(dp.params[p] + e1) = p1;
+          }
+      } else {
+        *reinterpret_cast<float4*>(params + e0) = p0;
+        *reinterpret_cast<float4*>(params + e1) = p1;
+      }
     }
     if (upd) {
       *reinterpret_cast<float4*>(upd + e0) = u0;
@@ -172,7 +221,9 @@ __global__ void __launch_bounds__(256)
         const int64_t e = half ? e1 + k : e0 + k;
         float m = mom[e];
         float v = RMS ? pv[e] : 0.f;
-        float g = grad[e];
+        float g;
+        if constexpr (DP) g = dp_grad1(dp, e);
+        else g = grad[e];
         if (JOINT) {
           const float p = params[e];
           g = fmaf(jc.lik_scale, g, jc.prior_coef * p);
@@ -181,7 +232,10 @@ __global__ void __launch_bounds__(256)
         const float u = sghmc_elem<RMS>(g, m, v, half ? r1[k] : r0[k], c);
         mom[e] = m;
         if (RMS) pv[e] = v;
-        if (params) params[e] += u;
+        if constexpr (DP) {
+          const float pn = params[e] + u;
+          for (int p = 0; p < dp.n; ++p) dp.params[p][e] = pn;
+        } else if (params) params[e] += u;
         if (upd) upd[e] = u;
       }
     }
@@ -366,7 +420,7 @@ static int sgmcmc_step_impl(float* params, const float* grad, float* momentum, f
                             int64_t n, const fb200_leaf_t* leaves, int n_leaves, const fb200_tile_t* tiles,
                             int64_t n_tiles, const uint32_t* key_in, uint32_t* key_out, uint32_t* leaf_keys_ws,
                             const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint, double* sq_ws,
-                            double* sq_out, void* stream) {
+                            double* sq_out, void* stream, const DpPeers* dpp = nullptr) {
   if (!grad || !momentum || !leaves || !tiles || !key_in || !key_out || !leaf_keys_ws || !hp) return FB200_E_NULL;
   if (!params && !updates_out) return FB200_E_NULL;
   if (joint && !params) return FB200_E_NULL;
@@ -390,16 +444,29 @@ static int sgmcmc_step_impl(float* params, const float* grad, float* momentum, f
     jc.sq_part = sq_out ? sq_ws : nullptr;
   }
   const unsigned g = (unsigned)n_tiles;
-  if (joint) {
+  const DpPeers nodp{};
+  if (dpp) {
+    if (joint) {
+      if (hp->rmsprop)
+        sgmcmc_step_kernel<true, true, true><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, nullptr, leaves, lk, tiles, c, jc, *dpp);
+      else
+        sgmcmc_step_kernel<false, true, true><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, nullptr, leaves, lk, tiles, c, jc, *dpp);
+    } else {
+      if (hp->rmsprop)
+        sgmcmc_step_kernel<true, false, true><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, nullptr, leaves, lk, tiles, c, jc, *dpp);
+      else
+        sgmcmc_step_kernel<false, false, true><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, nullptr, leaves, lk, tiles, c, jc, *dpp);
+    }
+  } else if (joint) {
     if (hp->rmsprop)
-      sgmcmc_step_kernel<true, true><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc);
+      sgmcmc_step_kernel<true, true, false><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc, nodp);
     else
-      sgmcmc_step_kernel<false, true><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc);
+      sgmcmc_step_kernel<false, true, false><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc, nodp);
   } else {
     if (hp->rmsprop)
-      sgmcmc_step_kernel<true, false><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc);
+      sgmcmc_step_kernel<true, false, false><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc, nodp);
     else
-      sgmcmc_step_kernel<false, false><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc);
+      sgmcmc_step_kernel<false, false, false><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc, nodp);
   }
   FB200_LAUNCH_CHECK();
   if (joint && sq_out) {
@@ -427,6 +494,36 @@ extern "C" int fb200_sgmcmc_step_joint_f32(float* params, const float* grad_logl
   if (!joint) return FB200_E_NULL;
   return sgmcmc_step_impl(params, grad_loglik, momentum, precond_v, nullptr, n, leaves, n_leaves, tiles, n_tiles,
                           key_in, key_out, leaf_keys_ws, hp, joint, sq_workspace, theta_sq_out, stream);
+}
+
+extern "C" int fb200_sgmcmc_step_dp_f32(float* momentum, float* precond_v, int64_t n, const fb200_leaf_t* leaves,
+                                        int n_leaves, const fb200_tile_t* tiles, int64_t tile_begin, int64_t tile_end,
+                                        const uint32_t* key_in, uint32_t* key_out, uint32_t* leaf_keys_ws,
+                                        const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint,
+                                        const fb200_dp_peers_t* peers, void* stream) {
+  if (!peers || !tiles) return FB200_E_NULL;
+  if (peers->n_ranks < 1 || peers->n_ranks > FB200_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->n_ranks)
+    return FB200_E_SHAPE;
+  if (tile_begin < 0 || tile_end < tile_begin) return FB200_E_SHAPE;
+  DpPeers dp{};
+  dp.n = peers->n_ranks;
+  dp.inv_n = 1.0f / (float)peers->n_ranks;
+  for (int p = 0; p < peers->n_ranks; ++p) {
+    if (!peers->grad[p] || !peers->params[p]) return FB200_E_NULL;
+    if (!fb200_aligned16(peers->grad[p]) || !fb200_aligned16(peers->params[p])) return FB200_E_ALIGN;
+    dp.grad[p] = peers->grad[p];
+    dp.params[p] = peers->params[p];
+  }
+  if (tile_end == tile_begin) {  // a rank without tiles still advances its key like everyone else
+    if (!key_in || !key_out || !leaf_keys_ws || n_leaves <= 0) return FB200_E_NULL;
+    sgmcmc_keys_kernel<<<(n_leaves + 127) / 128, 128, 0, (cudaStream_t)stream>>>(key_in, key_out, leaf_keys_ws,
+                                                                                 (uint32_t)n_leaves);
+    FB200_LAUNCH_CHECK();
+    return 0;
+  }
+  return sgmcmc_step_impl(peers->params[peers->rank], peers->grad[peers->rank], momentum, precond_v, nullptr, n, leaves,
+                          n_leaves, tiles + tile_begin, tile_end - tile_begin, key_in, key_out, leaf_keys_ws, hp, joint,
+                          nullptr, nullptr, stream, &dp);
 }
 
 static int explore_blocks(int64_t n) {

@@ -182,6 +182,40 @@ def sgmcmc_step(params, grad, momentum, precond_v, updates_out, leaves, tiles, k
     )
 
 
+def dp_tile_range(n_tiles: int, world: int, rank: int):
+    """Contiguous, balanced split of the tile table: rank r owns tiles [begin, end)."""
+    base, rem = divmod(int(n_tiles), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def sgmcmc_step_dp(grad_ptrs, param_ptrs, rank, momentum, precond_v, n, leaves, tiles, key_in, key_out, leaf_keys_ws,
+                   hp, joint=None, tile_range=None):
+    """Data-parallel fused step (fb200_sgmcmc_step_dp_f32): ``grad_ptrs`` / ``param_ptrs`` are every rank's [n] float32
+    buffers as peer-mapped device addresses (rank order); this rank updates tiles ``tile_range`` (default: its balanced
+    share) reading all gradients and writing all parameter replicas.  The caller brackets the call with barriers."""
+    world = len(grad_ptrs)
+    peers = _lib.DpPeers()
+    peers.n_ranks, peers.rank = world, int(rank)
+    for p in range(world):
+        peers.grad[p] = int(grad_ptrs[p])
+        peers.params[p] = int(param_ptrs[p])
+    t0, t1 = tile_range if tile_range is not None else dp_tile_range(tiles.shape[0], world, rank)
+    jg = None
+    if joint is not None:
+        jg = _lib.JointGrad()
+        jg.lik_scale = float(np.float32(joint[0]))
+        jg.prior_prec = float(np.float32(joint[1]))
+    check(
+        lib().fb200_sgmcmc_step_dp_f32(
+            _ptr(momentum, torch.float32), _ptr(precond_v, torch.float32, True), int(n), _ptr(leaves, torch.int64),
+            leaves.shape[0], _ptr(tiles, torch.int32), int(t0), int(t1), _ptr(key_in, KEY_DTYPE), _ptr(key_out, KEY_DTYPE),
+            _ptr(leaf_keys_ws, KEY_DTYPE), C.byref(hp), C.byref(jg) if jg is not None else None, C.byref(peers), _stream(),
+        ),
+        "fb200_sgmcmc_step_dp_f32",
+    )
+
+
 def sgd_explore_step(params, grad, precond_v, updates_out, hp, joint=None, ws_cache=None):
     if joint is not None:
         if updates_out is not None or params is None:

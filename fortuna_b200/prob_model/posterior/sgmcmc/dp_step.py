@@ -1,0 +1,47 @@
+"""Data-parallel SG-MCMC step over NVLink peer memory.
+
+The reference's multi-device trainer (``MultiDeviceMixin``, fortuna/training/trainer.py:700-850) replicates the parameters
+and the optimizer state on every device, averages the per-device gradients with ``lax.pmean`` (:793-795) and then runs the
+SAME optimizer step on every device.  Here the three stages are one kernel per rank (``fb200_sgmcmc_step_dp_f32``):
+every rank owns a contiguous range of the tile table; for its elements it loads the gradient from all ranks' buffers
+(peer loads), averages, advances its slice of the sampler state and stores the new parameters into all replicas (peer
+stores).  Two barriers bracket the launch.  Bit-identical to the single-GPU step on the averaged gradient."""
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from .... import ops
+
+
+class DataParallelStep:
+    def __init__(self, lens: Sequence[int], offsets: Sequence[int], n: int, device, world: int, rank: int, group=None,
+                 rmsprop: bool = False, seed: int = 0):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank, self.n = world, rank, int(n)
+        group = group if group is not None else dist.group.WORLD
+        gname = group.group_name if hasattr(group, "group_name") else group
+        # replicas that every rank can address: parameters (written by all owners) and gradients (read by all owners)
+        self.params = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+        self.grad = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+        self._hp = symm_mem.rendezvous(self.params, gname)
+        self._hg = symm_mem.rendezvous(self.grad, gname)
+        self.param_ptrs = [int(self._hp.buffer_ptrs[o]) for o in range(world)]
+        self.grad_ptrs = [int(self._hg.buffer_ptrs[o]) for o in range(world)]
+        self.momentum = torch.zeros(self.n, dtype=torch.float32, device=device)  # only the owned slice is ever touched
+        self.precond_v = torch.zeros(self.n, dtype=torch.float32, device=device) if rmsprop else None
+        self.leaves, self.tiles = ops.build_leaf_tables(lens, offsets, device)
+        self.tile_range = ops.dp_tile_range(self.tiles.shape[0], world, rank)
+        self.key = ops.PRNGKey(seed, device)  # the same chain on every rank
+        self._key_next = torch.empty_like(self.key)
+        self._leaf_keys = torch.empty((len(lens), 2), dtype=ops.KEY_DTYPE, device=device)
+
+    def step(self, hp, joint: Optional[tuple] = None) -> None:
+        """One sampler step of the whole job.  ``self.grad`` must hold this rank's gradient (written on the current
+        stream); afterwards ``self.params`` holds the new parameters on every rank."""
+        self._hg.barrier()  # every rank's gradient is complete and visible
+        ops.sgmcmc_step_dp(self.grad_ptrs, self.param_ptrs, self.rank, self.momentum, self.precond_v, self.n, self.leaves,
+                           self.tiles, self.key, self._key_next, self._leaf_keys, hp, joint=joint, tile_range=self.tile_range)
+        self._hp.barrier()  # every owner's parameter stores have landed in every replica
+        self.key, self._key_next = self._key_next, self.key

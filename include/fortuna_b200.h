@@ -133,6 +133,29 @@ int fb200_sgmcmc_step_joint_f32(float* params, const float* grad_loglik, float* 
                                 const uint32_t* key_in, uint32_t* key_out, uint32_t* leaf_keys_ws,
                                 const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint, double* sq_workspace,
                                 double* theta_sq_out, void* stream);
+
+/* Data-parallel sampler step: the multi-device trainer's gradient all-reduce (lax.pmean over the "batch" axis,
+ * fortuna/training/trainer.py:793-795, MultiDeviceMixin) + the replicated optimizer step
+ * (fortuna/training/trainer.py:170 -> the integrators above) + nothing else, as ONE kernel per rank over NVLink peer
+ * memory.  Every rank holds a full parameter replica and a full gradient buffer, both mapped into every other rank's
+ * address space (symmetric memory); rank r owns tiles [tile_begin, tile_end) of the common tile table and, for their
+ * elements only: loads the gradient from all ranks (summed in rank order, times 1 / n_ranks), updates ITS slice of
+ * momentum / precond_v (full-size arrays, only the owned slice is touched), and stores the new parameters into every
+ * replica.  The noise of an element depends only on (key, leaf, element), so the result is bit-identical to the
+ * single-GPU step on the averaged gradient whatever the split.  The caller orders the launch between two barriers
+ * (all gradients written / all parameters stored).  key_in/key_out advance identically on every rank.
+ * joint: optional (NULL = grad buffers hold the full log-joint gradient). */
+#define FB200_MAX_PEERS 8
+typedef struct {
+  int n_ranks;
+  int rank;
+  const float* grad[FB200_MAX_PEERS];   /* [n] per rank, peer-mapped */
+  float* params[FB200_MAX_PEERS];       /* [n] per rank, peer-mapped */
+} fb200_dp_peers_t;
+int fb200_sgmcmc_step_dp_f32(float* momentum, float* precond_v, int64_t n, const fb200_leaf_t* leaves, int n_leaves,
+                             const fb200_tile_t* tiles, int64_t tile_begin, int64_t tile_end, const uint32_t* key_in,
+                             uint32_t* key_out, uint32_t* leaf_keys_ws, const fb200_sgmcmc_hparams_t* hp,
+                             const fb200_joint_grad_t* joint, const fb200_dp_peers_t* peers, void* stream);
 int64_t fb200_sgd_explore_joint_workspace_doubles(int64_t n);
 int fb200_sgd_explore_step_joint_f32(float* params, const float* grad_loglik, float* precond_v, int64_t n,
                                      const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint,

@@ -1,0 +1,149 @@
+#!/usr/bin/env python
+"""Parity and timing of the data-parallel fused sampler step (fb200_sgmcmc_step_dp_f32) under torchrun, one rank per GPU:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
+        scripts/check_dp_step.py [--bench]
+Parity: every rank holds a different gradient; after K fused steps every replica must be BIT-identical to K single-GPU
+steps (fb200_sgmcmc_step_f32) on the rank-ordered average of the gradients, for SGHMC and RMSprop-preconditioned
+SGHMC, with and without the fused log-joint gradient, on a ragged tree.
+--bench: the BERT-base-sized tree (109.5 M parameters): fused step vs NCCL all-reduce + replicated step, CUDA events,
+max over ranks."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fortuna_b200 import ops  # noqa: E402
+from fortuna_b200.prob_model.posterior.sgmcmc.dp_step import DataParallelStep  # noqa: E402
+
+
+def _tree(lens):
+    offs, o = [], 0
+    for l in lens:
+        offs.append(o)
+        o += (l + 3) // 4 * 4  # leaves start 16-byte aligned like the flat tree
+    return offs, o
+
+
+def parity(dev, rank, world):
+    lens = [4096 * 3, 7, 1025, 64 * 1024 + 3, 2048, 1, 333]
+    offs, n = _tree(lens)
+    bad = 0
+    for rms in (False, True):
+        for joint in (None, (12.5, 0.75)):
+            dp = DataParallelStep(lens, offs, n, dev, world, rank, rmsprop=rms, seed=3)
+            g = torch.Generator(device=dev)
+            g.manual_seed(11)  # same initial parameters everywhere
+            p0 = torch.empty(n, device=dev).normal_(0, 1, generator=g)
+            dp.params.copy_(p0)
+            # single-GPU reference state on this rank
+            ref_p, ref_m = p0.clone(), torch.zeros(n, device=dev)
+            ref_v = torch.zeros(n, device=dev) if rms else None
+            key, key2 = ops.PRNGKey(3, dev), torch.empty(2, dtype=ops.KEY_DTYPE, device=dev)
+            lk = torch.empty((len(lens), 2), dtype=ops.KEY_DTYPE, device=dev)
+            hp = ops.make_hparams(1e-3, 0.05, rmsprop=rms)
+            for it in range(3):
+                grads = []
+                for r in range(world):  # every rank can rebuild every rank's gradient (seeded), for the reference
+                    gr = torch.Generator(device=dev)
+                    gr.manual_seed(1000 * it + r)
+                    grads.append(torch.empty(n, device=dev).normal_(0, 1, generator=gr))
+                dp.grad.copy_(grads[rank])
+                dp.step(hp, joint=joint)
+                acc = grads[0].clone()
+                for r in range(1, world):
+                    acc += grads[r]
+                acc *= 1.0 / world
+                ops.sgmcmc_step(ref_p, acc, ref_m, ref_v, None, dp.leaves, dp.tiles, key, key2, lk, hp,
+                                joint=None if joint is None else (joint[0], joint[1], None))
+                key, key2 = key2, key
+                torch.cuda.synchronize()
+                if not torch.equal(dp.params, ref_p):
+                    bad += 1
+                    d = (dp.params - ref_p).abs().max().item()
+                    print(f"rank {rank}: rms={rms} joint={joint} step {it}: params differ, max abs {d}")
+            t0, t1 = dp.tile_range
+            # the owned slice of the optimizer state matches; the rest was never touched
+            own = torch.zeros(n, dtype=torch.bool, device=dev)
+            tl = dp.tiles.cpu().numpy()
+            lv = dp.leaves.cpu().numpy()
+            for t in range(t0, t1):
+                leaf, ps = int(tl[t, 0]), int(tl[t, 1])
+                off, ln = int(lv[leaf, 0]), int(lv[leaf, 1])
+                h = (ln + 1) // 2
+                e = min(ps + 1024, h)
+                own[off + ps : off + e] = True
+                own[off + h + ps : off + min(h + e, ln)] = True
+            if not torch.equal(dp.momentum[own], ref_m[own]) or bool((dp.momentum[~own] != 0).any()):
+                bad += 1
+                print(f"rank {rank}: rms={rms} joint={joint}: momentum slice mismatch")
+            if not torch.equal(dp.key, key):
+                bad += 1
+                print(f"rank {rank}: key chain differs")
+            del dp
+    return bad
+
+
+def bench(dev, rank, world, steps=20):
+    lens = [23440896, 393216, 1536] + [2359296 // 4 * 4] * 36 + [589824] * 1 + [768] * 100  # ~109.5 M, BERT-base-like
+    offs, n = _tree(lens)
+    dp = DataParallelStep(lens, offs, n, dev, world, rank, seed=0)
+    dp.params.normal_(0, 0.02)
+    dp.grad.normal_(0, 1)
+    hp = ops.make_hparams(1e-5, 0.05)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(steps):
+            fn()
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev[0].elapsed_time(ev[1]) / steps], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    fused = timed(lambda: dp.step(hp))
+    # baseline: NCCL all-reduce of the gradient, then the replicated single-GPU step on every rank
+    p, m, gbuf = dp.params.clone(), torch.zeros(n, device=dev), dp.grad.clone()
+    key, key2 = ops.PRNGKey(0, dev), torch.empty(2, dtype=ops.KEY_DTYPE, device=dev)
+    lk = torch.empty((len(lens), 2), dtype=ops.KEY_DTYPE, device=dev)
+
+    def base():
+        dist.all_reduce(gbuf, op=dist.ReduceOp.AVG)
+        ops.sgmcmc_step(p, gbuf, m, None, None, dp.leaves, dp.tiles, key, key2, lk, hp)
+
+    nccl = timed(base)
+    if rank == 0:
+        print(json.dumps({"metric": "dp_sampler_step", "n_params": n, "n_gpus": world, "fused_ms": round(fused, 4),
+                          "nccl_allreduce_plus_step_ms": round(nccl, 4), "speedup": round(nccl / fused, 3),
+                          "param_updates_per_s": n / (fused * 1e-3),
+                          "nvlink_bytes_per_rank": 2 * 4 * (n // world) * (world - 1)}))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    bad = parity(dev, rank, world)
+    tot = torch.tensor([bad], device=dev)
+    dist.all_reduce(tot)
+    if rank == 0:
+        print("dp_step parity:", "OK" if tot.item() == 0 else f"{tot.item()} MISMATCHES")
+    if "--bench" in sys.argv and tot.item() == 0:
+        bench(dev, rank, world)
+    dist.destroy_process_group()
+    sys.exit(1 if tot.item() else 0)
+
+
+if __name__ == "__main__":
+    main()

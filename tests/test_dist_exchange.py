@@ -105,3 +105,74 @@ def test_local_rows_errors():
         local_rows(10, 4, 0)
     with pytest.raises(ValueError):
         local_rows(8, 2, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# Data-parallel sampler step (fb200_sgmcmc_step_dp_f32): host-side split and the semantics it must reproduce
+# ------------------------------------------------------------------------------------------------
+def test_dp_tile_range_partitions():
+    from fortuna_b200 import ops
+
+    for n_tiles in (0, 1, 2, 7, 8, 53441):
+        for world in (1, 2, 3, 8):
+            r = [ops.dp_tile_range(n_tiles, world, k) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n_tiles
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 0
+
+
+def _dp_worker(rank, port, out_dir):
+    """Each rank: own gradient, gloo all-reduce (the reference's lax.pmean), oracle SGHMC step on ITS tile range only,
+    then an all-gather of the owned parameter slices - the data movement the fused kernel performs over NVLink."""
+    import torch.distributed as dist
+
+    from fortuna_b200 import ops
+    from oracle import prng as oprng
+    from oracle import sampler as osamp
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    lens = [5000, 7, 2049]
+    r = np.random.default_rng(0)
+    params = [r.standard_normal(l).astype(np.float32) for l in lens]
+    grads = [np.random.default_rng(10 + rank).standard_normal(l).astype(np.float32) for l in lens]
+    avg = []
+    for g in grads:
+        t = torch.from_numpy(g.copy())
+        dist.all_reduce(t)
+        avg.append((t.numpy() * np.float32(1.0 / WORLD)).astype(np.float32))
+    pre = osamp.Preconditioner("identity")
+    names = [f"leaf{i}" for i in range(len(lens))]
+    state = osamp.sghmc_init(dict(zip(names, params)), oprng.PRNGKey(4), pre)
+    upd, _ = osamp.sghmc_update(dict(zip(names, avg)), state, 0.1, osamp.constant_schedule(1e-2), pre)
+    new = [p + upd[k] for p, k in zip(params, names)]
+    # ownership by tiles of 1024 pairs, as the kernel splits them
+    tiles = [(li, ps) for li, l in enumerate(lens) for ps in range(0, (l + 1) // 2, 1024)]
+    t0, t1 = ops.dp_tile_range(len(tiles), WORLD, rank)
+    mine = [np.zeros(l, bool) for l in lens]
+    for li, ps in tiles[t0:t1]:
+        h = (lens[li] + 1) // 2
+        e = min(ps + 1024, h)
+        mine[li][ps:e] = True
+        mine[li][h + ps : min(h + e, lens[li])] = True
+    out = [np.where(m, n_, np.float32(0)) for m, n_ in zip(mine, new)]
+    gathered = []
+    for o, m in zip(out, mine):
+        t, c = torch.from_numpy(o.copy()), torch.from_numpy(m.astype(np.int32))
+        dist.all_reduce(t)
+        dist.all_reduce(c)
+        assert bool((c == 1).all())  # every element has exactly one owner
+        gathered.append(t.numpy())
+    np.save(os.path.join(out_dir, f"dp_{rank}.npy"), np.concatenate(gathered))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "dp_full.npy"), np.concatenate(new))
+    dist.destroy_process_group()
+
+
+def test_dp_step_semantics_world2_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_dp_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    full = np.load(tmp_path / "dp_full.npy")
+    for rk in range(WORLD):
+        assert np.array_equal(np.load(tmp_path / f"dp_{rk}.npy"), full)

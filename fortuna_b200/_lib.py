@@ -56,7 +56,8 @@ MAX_PEERS = 8
 
 
 class DpPeers(C.Structure):
-    _fields_ = [("n_ranks", C.c_int), ("rank", C.c_int), ("grad", C.c_void_p * MAX_PEERS), ("params", C.c_void_p * MAX_PEERS)]
+    _fields_ = [("n_ranks", C.c_int), ("rank", C.c_int), ("grad", C.c_void_p * MAX_PEERS), ("params", C.c_void_p * MAX_PEERS),
+                ("mc_grad", C.c_void_p), ("mc_params", C.c_void_p)]
 
 
 class ClsOutputs(C.Structure):

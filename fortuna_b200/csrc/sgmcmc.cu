@@ -55,22 +55,25 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return y;
 }
 
-// One parameter: returns the update u; m and v are updated in place (registers).
+// One parameter: returns the update u; m and v are updated in place (registers).  Every product and sum is rounded
+// on its own (__fmul_rn / __fadd_rn: no FMA contraction), as the reference's op-by-op float32 graph does - and so that
+// every instantiation of the step kernel (single-GPU, log-joint, data-parallel) computes bit-identical values.
 template <bool RMS>
 __device__ __forceinline__ float sghmc_elem(float g, float& m, float& v, uint32_t bits, const StepCoef& c) {
   float n = bits_to_normal(bits);
   float denom = 1.0f;
   if (RMS) {
-    v = v * c.alpha + (g * g) * c.one_m_alpha;  // sgmcmc_preconditioner.py:67-68
+    v = __fadd_rn(__fmul_rn(v, c.alpha), __fmul_rn(__fmul_rn(g, g), c.one_m_alpha));  // sgmcmc_preconditioner.py:67-68
     const float s = sqrt_approx(v);
-    denom = c.rms_eps + s;                      // :76
-    n = n * sqrt_approx(denom);                 // :83  multiply_by_m_sqrt
+    denom = __fadd_rn(c.rms_eps, s);            // :76
+    n = __fmul_rn(n, sqrt_approx(denom));       // :83  multiply_by_m_sqrt
   }
   const float m_old = c.zero_momentum ? 0.0f : m;
-  m = c.beta * m_old + g * c.sqrt_eps + n * c.noise_scale;  // sghmc_integrator.py:77-84
+  m = __fadd_rn(__fadd_rn(__fmul_rn(c.beta, m_old), __fmul_rn(g, c.sqrt_eps)),
+                __fmul_rn(n, c.noise_scale));               // sghmc_integrator.py:77-84
   float u = m;
   if (RMS) u = __fdividef(u, denom);                        // :85  multiply_by_m_inv
-  return u * c.sqrt_eps;                                    // :86
+  return __fmul_rn(u, c.sqrt_eps);                          // :86
 }
 
 // Gradient prologue of the fused log-joint mode (JOINT): `grad` holds the gradient of the batch log-likelihood SUM and
@@ -94,18 +97,47 @@ struct JointCoef {
 struct DpPeers {
   const float* grad[FB200_MAX_PEERS];
   float* params[FB200_MAX_PEERS];
+  const float* mc_grad;  // multicast (NVLS) addresses of the same buffers, or null: one multimem.ld_reduce returns the
+  float* mc_params;      // switch-side sum over all ranks, one multimem.st lands in every replica
   int n;
   float inv_n;
 };
 
+// NVLink SHARP (NVLS) accesses through a multicast address: the NVSwitch performs the reduction / the replication, so
+// an owner receives n/N gradients instead of (N-1) n/N and sends its parameters once instead of N-1 times.
+__device__ __forceinline__ float4 mc_ld_reduce4(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float mc_ld_reduce1(const float* p) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st4(float* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void mc_st1(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// NP = compile-time bound on the ranks (2, 4 or 8): the loads of all ranks are issued before the first add, and the
+// registers that holds them in flight should not be paid for ranks that do not exist.
+template <int NP>
 __device__ __forceinline__ float4 dp_grad4(const DpPeers& dp, int64_t e) {
-  float4 v[FB200_MAX_PEERS];
+  float4 v[NP];
 #pragma unroll
-  for (int p = 0; p < FB200_MAX_PEERS; ++p)
+  for (int p = 0; p < NP; ++p)
     if (p < dp.n) v[p] = *reinterpret_cast<const float4*>(dp.grad[p] + e);
   float4 a = v[0];
 #pragma unroll
-  for (int p = 1; p < FB200_MAX_PEERS; ++p)
+  for (int p = 1; p < NP; ++p)
     if (p < dp.n) {
       a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w;
     }
@@ -118,12 +150,15 @@ __device__ __forceinline__ float dp_grad1(const DpPeers& dp, int64_t e) {
   return a * dp.inv_n;
 }
 
-template <bool RMS, bool JOINT, bool DP>
+template <bool RMS, bool JOINT, int NP>  // NP = 0: single GPU; 2 / 4 / 8: data-parallel over up to NP ranks (peer
+                                         // loads / stores); 1: data-parallel through the multicast addresses (NVLS)
 __global__ void __launch_bounds__(256)
     sgmcmc_step_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ mom,
                        float* __restrict__ pv, float* __restrict__ upd, const fb200_leaf_t* __restrict__ leaves,
                        const uint2* __restrict__ leaf_keys, const fb200_tile_t* __restrict__ tiles,
                        const StepCoef c, const JointCoef jc, const DpPeers dp) {
+  constexpr bool DP = NP > 0;
+  constexpr bool MC = NP == 1;
   const fb200_tile_t tile = tiles[blockIdx.x];
   const fb200_leaf_t leaf = leaves[tile.leaf];
   const uint2 key = leaf_keys[tile.leaf];
@@ -148,9 +183,14 @@ __global__ void __launch_bounds__(256)
   const bool vec = ((leaf.offset & 3) == 0) && ((h & 3u) == 0) && ((uint64_t)i0 + h + 3u < (uint64_t)n);
   if (vec) {
     float4 g0, g1;
-    if constexpr (DP) {
-      g0 = dp_grad4(dp, e0);
-      g1 = dp_grad4(dp, e1);
+    if constexpr (MC) {
+      g0 = mc_ld_reduce4(dp.mc_grad + e0);
+      g1 = mc_ld_reduce4(dp.mc_grad + e1);
+      g0.x *= dp.inv_n; g0.y *= dp.inv_n; g0.z *= dp.inv_n; g0.w *= dp.inv_n;
+      g1.x *= dp.inv_n; g1.y *= dp.inv_n; g1.z *= dp.inv_n; g1.w *= dp.inv_n;
+    } else if constexpr (DP) {
+      g0 = dp_grad4<NP>(dp, e0);
+      g1 = dp_grad4<NP>(dp, e1);
     } else {
       g0 = *reinterpret_cast<const float4*>(grad + e0);
       g1 = *reinterpret_cast<const float4*>(grad + e1);
@@ -191,11 +231,14 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<float4*>(pv + e1) = v1;
     }
     if (params) {
-      p0.x += u0.x; p0.y += u0.y; p0.z += u0.z; p0.w += u0.w;
-      p1.x += u1.x; p1.y += u1.y; p1.z += u1.z; p1.w += u1.w;
-      if constexpr (DP) {
+      p0.x = __fadd_rn(p0.x, u0.x); p0.y = __fadd_rn(p0.y, u0.y); p0.z = __fadd_rn(p0.z, u0.z); p0.w = __fadd_rn(p0.w, u0.w);
+      p1.x = __fadd_rn(p1.x, u1.x); p1.y = __fadd_rn(p1.y, u1.y); p1.z = __fadd_rn(p1.z, u1.z); p1.w = __fadd_rn(p1.w, u1.w);
+      if constexpr (MC) {
+        mc_st4(dp.mc_params + e0, p0);
+        mc_st4(dp.mc_params + e1, p1);
+      } else if constexpr (DP) {
 #pragma unroll
-        for (int p = 0; p < FB200_MAX_PEERS; ++p)
+        for (int p = 0; p < NP; ++p)
           if (p < dp.n) {
             *reinterpret_cast<float4*>(dp.params[p] + e0) = p0;
             *reinterpret_cast<float4*>(dp.params[p] + e1) = p1;
@@ -222,7 +265,8 @@ __global__ void __launch_bounds__(256)
         float m = mom[e];
         float v = RMS ? pv[e] : 0.f;
         float g;
-        if constexpr (DP) g = dp_grad1(dp, e);
+        if constexpr (MC) g = mc_ld_reduce1(dp.mc_grad + e) * dp.inv_n;
+        else if constexpr (DP) g = dp_grad1(dp, e);
         else g = grad[e];
         if (JOINT) {
           const float p = params[e];
@@ -232,10 +276,12 @@ __global__ void __launch_bounds__(256)
         const float u = sghmc_elem<RMS>(g, m, v, half ? r1[k] : r0[k], c);
         mom[e] = m;
         if (RMS) pv[e] = v;
-        if constexpr (DP) {
-          const float pn = params[e] + u;
+        if constexpr (MC) {
+          mc_st1(dp.mc_params + e, __fadd_rn(params[e], u));
+        } else if constexpr (DP) {
+          const float pn = __fadd_rn(params[e], u);
           for (int p = 0; p < dp.n; ++p) dp.params[p][e] = pn;
-        } else if (params) params[e] += u;
+        } else if (params) params[e] = __fadd_rn(params[e], u);
         if (upd) upd[e] = u;
       }
     }
@@ -446,27 +492,39 @@ static int sgmcmc_step_impl(float* params, const float* grad, float* momentum, f
   const unsigned g = (unsigned)n_tiles;
   const DpPeers nodp{};
   if (dpp) {
-    if (joint) {
-      if (hp->rmsprop)
-        sgmcmc_step_kernel<true, true, true><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, nullptr, leaves, lk, tiles, c, jc, *dpp);
-      else
-        sgmcmc_step_kernel<false, true, true><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, nullptr, leaves, lk, tiles, c, jc, *dpp);
-    } else {
-      if (hp->rmsprop)
-        sgmcmc_step_kernel<true, false, true><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, nullptr, leaves, lk, tiles, c, jc, *dpp);
-      else
-        sgmcmc_step_kernel<false, false, true><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, nullptr, leaves, lk, tiles, c, jc, *dpp);
-    }
+#define FB200_DP_LAUNCH(NPV)                                                                                          \
+  do {                                                                                                                \
+    if (joint) {                                                                                                      \
+      if (hp->rmsprop)                                                                                                \
+        sgmcmc_step_kernel<true, true, NPV><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, nullptr, leaves, lk, \
+                                                               tiles, c, jc, *dpp);                                   \
+      else                                                                                                            \
+        sgmcmc_step_kernel<false, true, NPV><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, nullptr, leaves, lk,  \
+                                                                tiles, c, jc, *dpp);                                  \
+    } else {                                                                                                          \
+      if (hp->rmsprop)                                                                                                \
+        sgmcmc_step_kernel<true, false, NPV><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, nullptr, leaves,    \
+                                                                lk, tiles, c, jc, *dpp);                              \
+      else                                                                                                            \
+        sgmcmc_step_kernel<false, false, NPV><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, nullptr, leaves, lk, \
+                                                                 tiles, c, jc, *dpp);                                 \
+    }                                                                                                                 \
+  } while (0)
+    if (dpp->mc_grad) FB200_DP_LAUNCH(1);
+    else if (dpp->n <= 2) FB200_DP_LAUNCH(2);
+    else if (dpp->n <= 4) FB200_DP_LAUNCH(4);
+    else FB200_DP_LAUNCH(8);
+#undef FB200_DP_LAUNCH
   } else if (joint) {
     if (hp->rmsprop)
-      sgmcmc_step_kernel<true, true, false><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc, nodp);
+      sgmcmc_step_kernel<true, true, 0><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc, nodp);
     else
-      sgmcmc_step_kernel<false, true, false><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc, nodp);
+      sgmcmc_step_kernel<false, true, 0><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc, nodp);
   } else {
     if (hp->rmsprop)
-      sgmcmc_step_kernel<true, false, false><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc, nodp);
+      sgmcmc_step_kernel<true, false, 0><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc, nodp);
     else
-      sgmcmc_step_kernel<false, false, false><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc, nodp);
+      sgmcmc_step_kernel<false, false, 0><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc, nodp);
   }
   FB200_LAUNCH_CHECK();
   if (joint && sq_out) {
@@ -514,6 +572,10 @@ extern "C" int fb200_sgmcmc_step_dp_f32(float* momentum, float* precond_v, int64
     dp.grad[p] = peers->grad[p];
     dp.params[p] = peers->params[p];
   }
+  if ((peers->mc_grad == nullptr) != (peers->mc_params == nullptr)) return FB200_E_NULL;
+  if (peers->mc_grad && (!fb200_aligned16(peers->mc_grad) || !fb200_aligned16(peers->mc_params))) return FB200_E_ALIGN;
+  dp.mc_grad = peers->mc_grad;
+  dp.mc_params = peers->mc_params;
   if (tile_end == tile_begin) {  // a rank without tiles still advances its key like everyone else
     if (!key_in || !key_out || !leaf_keys_ws || n_leaves <= 0) return FB200_E_NULL;
     sgmcmc_keys_kernel<<<(n_leaves + 127) / 128, 128, 0, (cudaStream_t)stream>>>(key_in, key_out, leaf_keys_ws,

@@ -190,7 +190,7 @@ def dp_tile_range(n_tiles: int, world: int, rank: int):
 
 
 def sgmcmc_step_dp(grad_ptrs, param_ptrs, rank, momentum, precond_v, n, leaves, tiles, key_in, key_out, leaf_keys_ws,
-                   hp, joint=None, tile_range=None):
+                   hp, joint=None, tile_range=None, mc_grad_ptr=0, mc_param_ptr=0):
     """Data-parallel fused step (fb200_sgmcmc_step_dp_f32): ``grad_ptrs`` / ``param_ptrs`` are every rank's [n] float32
     buffers as peer-mapped device addresses (rank order); this rank updates tiles ``tile_range`` (default: its balanced
     share) reading all gradients and writing all parameter replicas.  The caller brackets the call with barriers."""
@@ -200,6 +200,8 @@ def sgmcmc_step_dp(grad_ptrs, param_ptrs, rank, momentum, precond_v, n, leaves, 
     for p in range(world):
         peers.grad[p] = int(grad_ptrs[p])
         peers.params[p] = int(param_ptrs[p])
+    if mc_grad_ptr and mc_param_ptr:  # NVLS multicast addresses: in-switch gradient sum and parameter replication
+        peers.mc_grad, peers.mc_params = int(mc_grad_ptr), int(mc_param_ptr)
     t0, t1 = tile_range if tile_range is not None else dp_tile_range(tiles.shape[0], world, rank)
     jg = None
     if joint is not None:

@@ -16,7 +16,7 @@ from .... import ops
 
 class DataParallelStep:
     def __init__(self, lens: Sequence[int], offsets: Sequence[int], n: int, device, world: int, rank: int, group=None,
-                 rmsprop: bool = False, seed: int = 0):
+                 rmsprop: bool = False, seed: int = 0, multicast: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.world, self.rank, self.n = world, rank, int(n)
@@ -29,6 +29,10 @@ class DataParallelStep:
         self._hg = symm_mem.rendezvous(self.grad, gname)
         self.param_ptrs = [int(self._hp.buffer_ptrs[o]) for o in range(world)]
         self.grad_ptrs = [int(self._hg.buffer_ptrs[o]) for o in range(world)]
+        # NVLS multicast mappings of the two buffers, when the fabric offers them (0 otherwise: peer loads / stores)
+        mcp, mcg = int(getattr(self._hp, "multicast_ptr", 0) or 0), int(getattr(self._hg, "multicast_ptr", 0) or 0)
+        self.multicast = bool(multicast and world > 1 and mcp and mcg)
+        self.mc_param_ptr, self.mc_grad_ptr = (mcp, mcg) if self.multicast else (0, 0)
         self.momentum = torch.zeros(self.n, dtype=torch.float32, device=device)  # only the owned slice is ever touched
         self.precond_v = torch.zeros(self.n, dtype=torch.float32, device=device) if rmsprop else None
         self.leaves, self.tiles = ops.build_leaf_tables(lens, offsets, device)
@@ -42,6 +46,7 @@ class DataParallelStep:
         stream); afterwards ``self.params`` holds the new parameters on every rank."""
         self._hg.barrier()  # every rank's gradient is complete and visible
         ops.sgmcmc_step_dp(self.grad_ptrs, self.param_ptrs, self.rank, self.momentum, self.precond_v, self.n, self.leaves,
-                           self.tiles, self.key, self._key_next, self._leaf_keys, hp, joint=joint, tile_range=self.tile_range)
+                           self.tiles, self.key, self._key_next, self._leaf_keys, hp, joint=joint, tile_range=self.tile_range,
+                           mc_grad_ptr=self.mc_grad_ptr, mc_param_ptr=self.mc_param_ptr)
         self._hp.barrier()  # every owner's parameter stores have landed in every replica
         self.key, self._key_next = self._key_next, self.key

@@ -151,6 +151,10 @@ typedef struct {
   int rank;
   const float* grad[FB200_MAX_PEERS];   /* [n] per rank, peer-mapped */
   float* params[FB200_MAX_PEERS];       /* [n] per rank, peer-mapped */
+  const float* mc_grad;                 /* optional: NVLS multicast addresses of the same buffers (both or neither). */
+  float* mc_params;                     /* When set the gradient is summed inside the NVSwitch (multimem.ld_reduce - the
+                                           sum order is the switch's, not rank order) and the parameters are replicated by
+                                           it (multimem.st): every rank then moves 4 B/param in and out whatever N is. */
 } fb200_dp_peers_t;
 int fb200_sgmcmc_step_dp_f32(float* momentum, float* precond_v, int64_t n, const fb200_leaf_t* leaves, int n_leaves,
                              const fb200_tile_t* tiles, int64_t tile_begin, int64_t tile_end, const uint32_t* key_in,

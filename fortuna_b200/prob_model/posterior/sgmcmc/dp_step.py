@@ -16,7 +16,7 @@ from .... import ops
 
 class DataParallelStep:
     def __init__(self, lens: Sequence[int], offsets: Sequence[int], n: int, device, world: int, rank: int, group=None,
-                 rmsprop: bool = False, seed: int = 0, multicast: bool = True):
+                 rmsprop: bool = False, seed: int = 0, multicast="auto"):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.world, self.rank, self.n = world, rank, int(n)
@@ -31,6 +31,10 @@ class DataParallelStep:
         self.grad_ptrs = [int(self._hg.buffer_ptrs[o]) for o in range(world)]
         # NVLS multicast mappings of the two buffers, when the fabric offers them (0 otherwise: peer loads / stores)
         mcp, mcg = int(getattr(self._hp, "multicast_ptr", 0) or 0), int(getattr(self._hg, "multicast_ptr", 0) or 0)
+        # measured on 8 B200s (109 M parameters): multicast 0.96 ms, peer loads / stores 1.25 ms; on 2: 1.15 vs 0.65 ms -
+        # the switch-side sum only pays once it removes traffic (N > 2); "auto" follows that, and keeps N <= 2 bit-exact
+        if multicast == "auto":
+            multicast = world > 2
         self.multicast = bool(multicast and world > 1 and mcp and mcg)
         self.mc_param_ptr, self.mc_grad_ptr = (mcp, mcg) if self.multicast else (0, 0)
         self.momentum = torch.zeros(self.n, dtype=torch.float32, device=device)  # only the owned slice is ever touched

@@ -151,6 +151,9 @@ SIGNATURES = {
     "fb200_calib_reg_workspace_bytes": (_sz, [_i, _i]),
     "fb200_calib_reg_loss_terms": (_i, [_P, _P, _P, _i, _i, _i, _P, _sz, _P, _P]),
     "fb200_cls_sample_targets": (_i, [_P, _P, _P, _i, _i, _i, _i, _P, _P, _P]),
+    "fb200_maxcov_workspace_bytes": (_sz, [_i]),
+    "fb200_maxcov_counts": (_i, [_P, _P, _i64, _P, _i, _i, _f, _P, _sz, _P, _P, _P]),
+    "fb200_maxcov_apply_patches": (_i, [_P, _i64, _f, _f, _P, _P]),
     "fb200_cls_output_sample_targets": (_i, [_P, _P, _P, _i, _i, _i, _P, _P]),
     "fb200_reg_output_sample_targets": (_i, [_P, _P, _P, _i, _i, _i, _P, _P]),
     "fb200_output_calib_focal_loss_terms": (_i, [_P, _i, _P, _P, _i, _i, _f, _P, _sz, _P, _P]),

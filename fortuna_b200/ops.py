@@ -738,6 +738,34 @@ def output_calib_scaled_mse_terms(outputs, targets, log_temp=None):
     return out
 
 
+def maxcov_counts(probs, targets, taus, side, threshold):
+    """probs float32 [n], targets int32 [n], taus float32 [n_taus] sorted (ascending for side 0, descending for side 1)
+    -> (counts, labels) int32 [n_taus]: per candidate tau the number of selected points and the sum of their counted
+    labels (fb200_maxcov_counts)."""
+    n, nt = probs.numel(), taus.numel()
+    nbytes = int(lib().fb200_maxcov_workspace_bytes(nt))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=probs.device)
+    counts = torch.empty(nt, dtype=torch.int32, device=probs.device)
+    labels = torch.empty(nt, dtype=torch.int32, device=probs.device)
+    check(
+        lib().fb200_maxcov_counts(_ptr(probs, torch.float32), _ptr(targets, torch.int32), n, _ptr(taus, torch.float32), nt,
+                                  int(side), float(np.float32(threshold)), _ptr(ws), nbytes, _ptr(counts), _ptr(labels),
+                                  _stream()),
+        "fb200_maxcov_counts",
+    )
+    return counts, labels
+
+
+def maxcov_apply_patches(probs, tau_pos, tau_neg):
+    out = torch.empty_like(probs)
+    check(
+        lib().fb200_maxcov_apply_patches(_ptr(probs, torch.float32), probs.numel(), float(np.float32(tau_pos)),
+                                         float(np.float32(tau_neg)), _ptr(out), _stream()),
+        "fb200_maxcov_apply_patches",
+    )
+    return out
+
+
 def cls_output_sample_targets(logits, key, n_target_samples, log_temp=None):
     """logits [B, C] -> y int32 [T, B]: ClassificationProbOutputLayer.sample's draws (T uniforms per input key)."""
     B, Cn = logits.shape

@@ -407,6 +407,24 @@ int fb200_output_calib_focal_loss_terms(const void* logits, int dtype, const int
 int fb200_output_calib_scaled_mse_terms(const float* outputs, const float* targets, const float* log_temp, int B, int d,
                                         void* workspace, size_t workspace_bytes, double* out, void* stream);
 
+/* Maximum-coverage fixed-precision calibration of a binary classifier
+ * (MaxCoverageFixedPrecisionBinaryClassificationCalibrator, fortuna/conformal/classification/
+ * maxcovfixprec_binary_classfication.py:33-124).  For a SORTED grid of candidate taus (ascending for side 0, descending
+ * for side 1 - the reference's own grids, :77-80) one pass returns, for every tau_j,
+ *   side 0 (true positives): counts[j] = #{ clip((1 + (tau_j - 1) [p > 0.5]) p, max 1) >= threshold }, labels[j] = sum of
+ *                            y over those points                                           (:56-61, :109-113)
+ *   side 1 (true negatives): counts[j] = #{ (1 + (tau_j - 1) [p < 0.5]) p <= threshold },  labels[j] = sum of (1 - y)
+ *                            (threshold = 1 - true_negative_precision_threshold)           (:63-69, :115-119)
+ * as exact integers (the reference takes float32 means of the same indicators; mean = count / n).  The predicate is
+ * evaluated with the reference's float32 expression, op by op.  probs float32 [n], targets int32 [n] in {0, 1},
+ * taus float32 [n_taus] (n_taus <= 4096) on the device. */
+size_t fb200_maxcov_workspace_bytes(int n_taus);
+int fb200_maxcov_counts(const float* probs, const int32_t* targets, int64_t n, const float* taus, int n_taus, int side,
+                        float threshold, void* workspace, size_t workspace_bytes, int32_t* counts, int32_t* labels,
+                        void* stream);
+/* apply_patches (:98-107): out = clip(tau_pos p, max 1) where p > 0.5, tau_neg p where p < 0.5, p otherwise. */
+int fb200_maxcov_apply_patches(const float* probs, int64_t n, float tau_pos, float tau_neg, float* out, void* stream);
+
 /* Target samples of the classification predictive - Predictive.sample (fortuna/prob_model/predictive/base.py:318-440)
  * -> ClassificationProbOutputLayer.sample (fortuna/prob_output_layer/classification.py:33-51), the reference's draws:
  * keys = split(key, T); (k1, k2) = split(keys[t]); i = choice(k1, n_stored); y[t, b] = choice(split(k2, B)[b], C,

@@ -21,7 +21,7 @@ from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_approximator import CyclicalS
 from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_posterior import CyclicalSGLDPosterior
 from .posterior.sgmcmc.sghmc.sghmc_approximator import SGHMCPosteriorApproximator
 from .posterior.sgmcmc.sghmc.sghmc_posterior import SGHMCPosterior
-from .posterior.sgmcmc.torch_model import BoundModel
+from .posterior.sgmcmc.torch_model import BoundModel, bind_for_fit
 from .predictive.classification import ClassificationPredictive
 from .prior import IsotropicGaussianPrior
 
@@ -63,7 +63,7 @@ class ProbClassifier:
         fit_config = fit_config or FitConfig()
         self.model.to(self.device)
         self._check_output_dim(train_data_loader)
-        bound = BoundModel(self.model, self.device, freeze_fun=fit_config.optimizer.freeze_fun)
+        bound = bind_for_fit(self.model, self.device, fit_config.optimizer.freeze_fun, fit_config.processor)
         cls = SGHMCPosterior if isinstance(self.posterior_approximator, SGHMCPosteriorApproximator) else CyclicalSGLDPosterior
         self.posterior = cls(bound, self.prior, self.posterior_approximator, self.rng)
         status = {"fit_status": self.posterior.fit(train_data_loader, val_data_loader, fit_config)}

@@ -28,9 +28,20 @@ class FitCheckpointer:
         self.dump_state = dump_state
 
 
+class FitProcessor:
+    """fortuna/prob_model/fit_config/processor.py:1-23.  ``devices=-1`` (the reference's default: use every device):
+    when the process runs under ``torchrun`` with more than one rank, the fit is data-parallel over the ranks (one GPU
+    each); ``devices=0``: this process alone.  ``disable_jit`` is accepted and unused (nothing is traced here)."""
+
+    def __init__(self, devices: int = -1, disable_jit: bool = False):
+        self.devices = devices
+        self.disable_jit = disable_jit
+
+
 class FitConfig:
     def __init__(self, optimizer: FitOptimizer = None, checkpointer: FitCheckpointer = None, monitor: FitMonitor = None,
-                 **_ignored):
+                 processor: FitProcessor = None, **_ignored):
         self.optimizer = optimizer or FitOptimizer()
         self.checkpointer = checkpointer or FitCheckpointer()
         self.monitor = monitor or FitMonitor()
+        self.processor = processor or FitProcessor()

@@ -4,8 +4,9 @@ The reference's multi-device trainer (``MultiDeviceMixin``, fortuna/training/tra
 and the optimizer state on every device, averages the per-device gradients with ``lax.pmean`` (:793-795) and then runs the
 SAME optimizer step on every device.  Here the three stages are one kernel per rank (``fb200_sgmcmc_step_dp_f32``):
 every rank owns a contiguous range of the tile table; for its elements it loads the gradient from all ranks' buffers
-(peer loads), averages, advances its slice of the sampler state and stores the new parameters into all replicas (peer
-stores).  Two barriers bracket the launch.  Bit-identical to the single-GPU step on the averaged gradient."""
+(peer loads, or one in-switch reduction through the NVLS multicast address), averages, advances its slice of the sampler
+state and stores the new parameters into all replicas (peer stores / one multicast store).  Two barriers bracket the
+launch.  With peer loads the result is bit-identical to the single-GPU step on the rank-ordered average gradient."""
 from typing import Optional, Sequence
 
 import torch
@@ -14,29 +15,59 @@ import torch.distributed as dist
 from .... import ops
 
 
-class DataParallelStep:
-    def __init__(self, lens: Sequence[int], offsets: Sequence[int], n: int, device, world: int, rank: int, group=None,
-                 rmsprop: bool = False, seed: int = 0, multicast="auto"):
+def symmetric_empty(n: int, device) -> torch.Tensor:
+    """float32 [n] in symmetric memory (every rank must call this in the same order)."""
+    import torch.distributed._symmetric_memory as symm_mem
+
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return symm_mem.empty(int(n), dtype=torch.float32, device=device)
+
+
+class PeerReplicas:
+    """The parameter replica and the gradient buffer of every rank, mapped into this rank's address space."""
+
+    def __init__(self, params: torch.Tensor, grad: torch.Tensor, world: int, rank: int, group=None, multicast="auto"):
         import torch.distributed._symmetric_memory as symm_mem
 
-        self.world, self.rank, self.n = world, rank, int(n)
+        self.world, self.rank = world, rank
+        self.params, self.grad = params, grad
         group = group if group is not None else dist.group.WORLD
         gname = group.group_name if hasattr(group, "group_name") else group
-        # replicas that every rank can address: parameters (written by all owners) and gradients (read by all owners)
-        self.params = symm_mem.empty(self.n, dtype=torch.float32, device=device)
-        self.grad = symm_mem.empty(self.n, dtype=torch.float32, device=device)
-        self._hp = symm_mem.rendezvous(self.params, gname)
-        self._hg = symm_mem.rendezvous(self.grad, gname)
+        self._hp = symm_mem.rendezvous(params, gname)
+        self._hg = symm_mem.rendezvous(grad, gname)
         self.param_ptrs = [int(self._hp.buffer_ptrs[o]) for o in range(world)]
         self.grad_ptrs = [int(self._hg.buffer_ptrs[o]) for o in range(world)]
-        # NVLS multicast mappings of the two buffers, when the fabric offers them (0 otherwise: peer loads / stores)
+        # NVLS multicast mappings of the two buffers, when the fabric offers them (0 otherwise: peer loads / stores).
+        # Measured on 8 B200s (109 M parameters): multicast 0.96 ms, peer loads / stores 1.25 ms; on 2: 1.15 vs 0.65 ms -
+        # the switch-side sum only pays once it removes traffic (N > 2); "auto" follows that and keeps N <= 2 bit-exact
         mcp, mcg = int(getattr(self._hp, "multicast_ptr", 0) or 0), int(getattr(self._hg, "multicast_ptr", 0) or 0)
-        # measured on 8 B200s (109 M parameters): multicast 0.96 ms, peer loads / stores 1.25 ms; on 2: 1.15 vs 0.65 ms -
-        # the switch-side sum only pays once it removes traffic (N > 2); "auto" follows that, and keeps N <= 2 bit-exact
         if multicast == "auto":
             multicast = world > 2
         self.multicast = bool(multicast and world > 1 and mcp and mcg)
         self.mc_param_ptr, self.mc_grad_ptr = (mcp, mcg) if self.multicast else (0, 0)
+
+    def step(self, momentum, precond_v, leaves, tiles, key_in, key_out, leaf_keys, hp, joint=None, tile_range=None):
+        """barrier (all gradients written) -> fused step on the owned tiles -> barrier (all parameters landed)."""
+        self._hg.barrier()
+        ops.sgmcmc_step_dp(self.grad_ptrs, self.param_ptrs, self.rank, momentum, precond_v, self.params.numel(), leaves,
+                           tiles, key_in, key_out, leaf_keys, hp, joint=joint, tile_range=tile_range,
+                           mc_grad_ptr=self.mc_grad_ptr, mc_param_ptr=self.mc_param_ptr)
+        self._hp.barrier()
+
+
+class DataParallelStep:
+    """Self-contained sampler state over a flat tree (scripts / benchmarks); the training loop uses ``PeerReplicas``
+    through ``sghmc_integrator(...).apply(..., dp=...)``."""
+
+    def __init__(self, lens: Sequence[int], offsets: Sequence[int], n: int, device, world: int, rank: int, group=None,
+                 rmsprop: bool = False, seed: int = 0, multicast="auto"):
+        self.world, self.rank, self.n = world, rank, int(n)
+        self.params = symmetric_empty(self.n, device)
+        self.grad = symmetric_empty(self.n, device)
+        self.peers = PeerReplicas(self.params, self.grad, world, rank, group, multicast)
+        self.multicast = self.peers.multicast
         self.momentum = torch.zeros(self.n, dtype=torch.float32, device=device)  # only the owned slice is ever touched
         self.precond_v = torch.zeros(self.n, dtype=torch.float32, device=device) if rmsprop else None
         self.leaves, self.tiles = ops.build_leaf_tables(lens, offsets, device)
@@ -48,9 +79,6 @@ class DataParallelStep:
     def step(self, hp, joint: Optional[tuple] = None) -> None:
         """One sampler step of the whole job.  ``self.grad`` must hold this rank's gradient (written on the current
         stream); afterwards ``self.params`` holds the new parameters on every rank."""
-        self._hg.barrier()  # every rank's gradient is complete and visible
-        ops.sgmcmc_step_dp(self.grad_ptrs, self.param_ptrs, self.rank, self.momentum, self.precond_v, self.n, self.leaves,
-                           self.tiles, self.key, self._key_next, self._leaf_keys, hp, joint=joint, tile_range=self.tile_range,
-                           mc_grad_ptr=self.mc_grad_ptr, mc_param_ptr=self.mc_param_ptr)
-        self._hp.barrier()  # every owner's parameter stores have landed in every replica
+        self.peers.step(self.momentum, self.precond_v, self.leaves, self.tiles, self.key, self._key_next,
+                        self._leaf_keys, hp, joint=joint, tile_range=self.tile_range)
         self.key, self._key_next = self._key_next, self.key

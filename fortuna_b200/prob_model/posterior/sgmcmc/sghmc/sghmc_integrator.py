@@ -43,7 +43,7 @@ class GradientTransformation(NamedTuple):
 
 
 def _step(gradient, state, params, momentum_decay, momentum_resample_steps, step_schedule, preconditioner, ws,
-          joint=None):
+          joint=None, dp=None):
     grad = as_flat_tree(gradient, like=state.momentum)
     step_size = np.float32(step_schedule(state.count))
     zero_m = momentum_resample_steps is not None and state.count % momentum_resample_steps == 0
@@ -64,6 +64,14 @@ def _step(gradient, state, params, momentum_decay, momentum_resample_steps, step
     updates = None
     if params is None:
         updates = grad.empty_like()
+    if dp is not None:
+        # data-parallel: gradient average over the ranks + step on the owned tiles + parameter broadcast, one kernel
+        if params is None or params.flat.data_ptr() != dp.params.data_ptr() or grad.flat.data_ptr() != dp.grad.data_ptr():
+            raise ValueError("the data-parallel step works in place on the peer-mapped parameter / gradient vectors")
+        dp.step(state.momentum.flat, v.flat if v is not None else None, leaves, tiles, state.rng_key, new_key, key, hp,
+                joint=None if joint is None else joint[:2])
+        return None, OptaxSGHMCState(count=state.count + 1, rng_key=new_key, momentum=state.momentum,
+                                     preconditioner_state=state.preconditioner_state)
     ops.sgmcmc_step(
         params.flat if params is not None else None,
         grad.flat,
@@ -112,14 +120,14 @@ def sghmc_integrator(
             gradient, state, None, momentum_decay, momentum_resample_steps, step_schedule, preconditioner, ws
         )
 
-    def apply_fn(params: FlatTree, gradient, state, joint=None):
+    def apply_fn(params: FlatTree, gradient, state, joint=None, dp=None):
         """``joint=(n_data / batch_size, prior_precision, float64[1] tensor | None)``: ``gradient`` is the gradient of
         the batch log-likelihood sum; scaling and the Gaussian-prior gradient happen inside the kernel."""
         if not isinstance(params, FlatTree):
             raise TypeError("the fused apply path updates a FlatTree in place")
         _, new_state = _step(
             gradient, state, params, momentum_decay, momentum_resample_steps, step_schedule, preconditioner, ws,
-            joint=joint,
+            joint=joint, dp=dp,
         )
         return params, new_state
 

@@ -10,7 +10,14 @@ fortuna/prob_model/joint/base.py:54-122: log prior + n_data / batch_size * sum l
 With the isotropic Gaussian prior (the only prior of the hot path) autograd sees the batch log-likelihood SUM only: the
 ``n_data / batch_size`` scaling and the prior gradient ``-prec * theta`` are formed inside the sampler kernel
 (fb200_sgmcmc_step_joint_f32), which also returns ``sum(theta^2)`` so the logged log-joint value is complete.  The
-unfused route (prior through autograd) stays available as ``fuse_prior=False`` - the two are compared in the tests."""
+unfused route (prior through autograd) stays available as ``fuse_prior=False`` - the two are compared in the tests.
+
+Data-parallel (``bound.dp`` set, one process per GPU): the reference's multi-device trainer gives every device a
+contiguous slice of each batch (fortuna/training/trainer.py:700-760), evaluates the log-joint on it with the slice's own
+``n_data / batch`` scaling, and averages gradients and loss over the devices (``lax.pmean``, :793-795).  Here every rank
+takes its slice, back-propagates the slice's log-likelihood sum into its peer-mapped gradient vector, and ONE kernel per
+rank does average + prior + step + parameter broadcast (fb200_sgmcmc_step_dp_f32); the logged loss is averaged over the
+ranks once per epoch."""
 import math
 from typing import Dict, List
 
@@ -41,6 +48,9 @@ def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader,
     state = TrainState.create(params=bound.params, tx=tx)
     n_data = train_data_loader.size
     dev = bound.device
+    dp = getattr(bound, "dp", None)
+    if dp is not None and not (fuse_prior and hasattr(prior, "log_var")):
+        raise NotImplementedError("the data-parallel fit needs the fused Gaussian-prior route")
     fuse = fuse_prior and hasattr(prior, "log_var")
     prec = math.exp(-prior.log_var) if fuse else None
     lp_const = -0.5 * bound.params.n_params * (math.log(2 * math.pi) + prior.log_var) if fuse else None
@@ -51,7 +61,20 @@ def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader,
             x = torch.as_tensor(inputs, dtype=torch.float32, device=dev)
             y = torch.as_tensor(targets, device=dev)
             bound.zero_grad()
-            if fuse:
+            if dp is not None:
+                if x.shape[0] % dp.world:
+                    raise ValueError(f"the batch size ({x.shape[0]}) must be a multiple of the number of devices ({dp.world})")
+                b = x.shape[0] // dp.world
+                x, y = x[dp.rank * b : (dp.rank + 1) * b], y[dp.rank * b : (dp.rank + 1) * b]
+                ll = log_likelihood_sum(bound.model(x), y)
+                ll.backward()
+                scale = n_data / b
+                # the log prior of the pre-update parameters, for the logged value only (the step kernel forms its gradient)
+                with torch.no_grad():
+                    lp = sum(prior.log_joint_prob(p) for p in bound.trainable.values())
+                state = state.apply_gradients(grads=bound.grads, joint=(scale, prec, None), dp=dp)
+                lj = (lp.double() + scale * ll.detach().double()).float()
+            elif fuse:
                 ll = log_likelihood_sum(bound.model(x), y)
                 ll.backward()                                # d sum-log-lik / d theta lands in bound.grads (flat)
                 scale = n_data / x.shape[0]
@@ -67,7 +90,13 @@ def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader,
             if save_chain is not None and save_every_n_steps and state.step % save_every_n_steps == 0:
                 save_chain(state)
             epoch.append(lj.detach())
-        losses.append(float(torch.stack(epoch).mean()))
+        ep_mean = torch.stack(epoch).mean()
+        if dp is not None:  # pmean of the loss (trainer.py:793-795), once per epoch
+            import torch.distributed as dist
+
+            dist.all_reduce(ep_mean)
+            ep_mean = ep_mean / dp.world
+        losses.append(float(ep_mean))
         if val_data_loader is not None:
             with torch.no_grad():
                 v = [batched_log_joint_prob(bound, prior, torch.as_tensor(a, dtype=torch.float32, device=dev),

@@ -33,7 +33,10 @@ def _nest(items):
 class BoundModel:
     """model + (params, grads) FlatTrees over its trainable parameters."""
 
-    def __init__(self, model: torch.nn.Module, device, freeze_fun: Optional[Callable] = None):
+    def __init__(self, model: torch.nn.Module, device, freeze_fun: Optional[Callable] = None,
+                 flat_alloc: Optional[Callable] = None):
+        """``flat_alloc(n, device)`` allocates the two flat vectors (e.g. in symmetric memory for the data-parallel
+        step); default: ordinary device memory."""
         self.model = model.to(device=device, dtype=torch.float32)
         self.device = device
         all_p = param_paths(self.model)
@@ -45,6 +48,13 @@ class BoundModel:
             p.requires_grad_(pth in self.trainable)
         self.params = FlatTree.from_tree(_nest((pth, p.detach()) for pth, p in self.trainable.items()), device=device)
         self.grads = self.params.zeros_like()
+        if flat_alloc is not None:
+            for name in ("params", "grads"):
+                old = getattr(self, name)
+                flat = flat_alloc(old.flat.numel(), device)
+                flat.copy_(old.flat)
+                setattr(self, name, FlatTree(flat, old.paths, old.shapes, old.offsets))
+        self.dp = None  # PeerReplicas when the fit runs data-parallel
         by_path = dict(zip(self.params.paths, zip(self.params.leaf_views(), self.grads.leaf_views())))
         for pth, p in self.trainable.items():
             pv, gv = by_path[pth]
@@ -68,3 +78,21 @@ class BoundModel:
         if m.output_subnet.bias is not None:
             want.add(PREFIX + ("output_subnet", "bias"))
         return set(self.trainable) == want
+
+
+def bind_for_fit(model: torch.nn.Module, device, freeze_fun: Optional[Callable] = None, processor=None) -> BoundModel:
+    """BoundModel for a fit.  With ``processor.devices == -1`` (the reference's default, fit_config/processor.py) in a
+    multi-rank NCCL job the flat vectors live in symmetric memory, every replica starts from rank 0's parameters, and
+    ``bound.dp`` carries the peer mappings the data-parallel step kernel needs."""
+    import torch.distributed as dist
+
+    devices = getattr(processor, "devices", -1)
+    if (devices == -1 and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            and dist.get_backend() == "nccl"):
+        from .dp_step import PeerReplicas, symmetric_empty
+
+        bound = BoundModel(model, device, freeze_fun=freeze_fun, flat_alloc=symmetric_empty)
+        dist.broadcast(bound.params.flat, 0)
+        bound.dp = PeerReplicas(bound.params.flat, bound.grads.flat, dist.get_world_size(), dist.get_rank())
+        return bound
+    return BoundModel(model, device, freeze_fun=freeze_fun)

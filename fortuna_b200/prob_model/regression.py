@@ -14,7 +14,7 @@ from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_approximator import CyclicalS
 from .posterior.sgmcmc.cyclical_sgld.cyclical_sgld_posterior import CyclicalSGLDPosterior
 from .posterior.sgmcmc.sghmc.sghmc_approximator import SGHMCPosteriorApproximator
 from .posterior.sgmcmc.sghmc.sghmc_posterior import SGHMCPosterior
-from .posterior.sgmcmc.torch_model import BoundModel
+from .posterior.sgmcmc.torch_model import BoundModel, bind_for_fit
 from .predictive.regression import RegressionPredictive
 from .prior import IsotropicGaussianPrior
 
@@ -60,7 +60,7 @@ class ProbRegressor:
     def train(self, train_data_loader, val_data_loader=None, calib_data_loader=None, fit_config: Optional[FitConfig] = None,
               calib_config: Optional[CalibConfig] = None, **_ignored):
         fit_config = fit_config or FitConfig()
-        bound = BoundModel(self.model, self.device, freeze_fun=fit_config.optimizer.freeze_fun)
+        bound = bind_for_fit(self.model, self.device, fit_config.optimizer.freeze_fun, fit_config.processor)
         cls = SGHMCPosterior if isinstance(self.posterior_approximator, SGHMCPosteriorApproximator) else CyclicalSGLDPosterior
         self.posterior = cls(bound, self.prior, self.posterior_approximator, self.rng)
         self.posterior.log_likelihood_sum = gaussian_log_likelihood_sum

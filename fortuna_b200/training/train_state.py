@@ -20,10 +20,12 @@ class TrainState(NamedTuple):
         params = as_flat_tree(params)
         return cls(step=0, params=params, tx=tx, opt_state=tx.init(params), mutable=mutable)
 
-    def apply_gradients(self, grads, joint=None, **kwargs):
+    def apply_gradients(self, grads, joint=None, dp=None, **kwargs):
         """flax TrainState.apply_gradients: tx.update + optax.apply_updates + step += 1, in one launch.
         ``joint`` (see sghmc_integrator.apply) additionally fuses the log-joint gradient assembly into that launch."""
-        if joint is not None:
+        if dp is not None:
+            params, opt_state = self.tx.apply(self.params, grads, self.opt_state, joint=joint, dp=dp)
+        elif joint is not None:
             params, opt_state = self.tx.apply(self.params, grads, self.opt_state, joint=joint)
         else:
             params, opt_state = self.tx.apply(self.params, grads, self.opt_state)

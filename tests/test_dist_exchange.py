@@ -176,3 +176,13 @@ def test_dp_step_semantics_world2_gloo(tmp_path):
     full = np.load(tmp_path / "dp_full.npy")
     for rk in range(WORLD):
         assert np.array_equal(np.load(tmp_path / f"dp_{rk}.npy"), full)
+
+
+def test_fit_processor_defaults_and_single_process_binding():
+    """FitProcessor mirrors fortuna/prob_model/fit_config/processor.py (devices=-1 by default); without an initialised
+    multi-rank NCCL group the data-parallel binding is not engaged (checked on the predicate, no GPU needed)."""
+    from fortuna_b200.prob_model import FitConfig, FitProcessor
+
+    assert FitConfig().processor.devices == -1 and FitConfig().processor.disable_jit is False
+    assert FitConfig(processor=FitProcessor(devices=0)).processor.devices == 0
+    assert not dist.is_initialized()

@@ -117,6 +117,8 @@ SIGNATURES = {
     "fb200_sgd_explore_step_f32": (_i, [_P, _P, _P, _P, _i64, C.POINTER(SgmcmcHParams), _P]),
     "fb200_sgmcmc_step_dp_f32": (_i, [_P, _P, _i64, _P, _i, _P, _i64, _i64, _P, _P, _P, C.POINTER(SgmcmcHParams),
                                  C.POINTER(JointGrad), C.POINTER(DpPeers), _P]),
+    "fb200_sgd_explore_step_dp_f32": (_i, [_P, _i64, _i64, _i64, C.POINTER(SgmcmcHParams), C.POINTER(JointGrad),
+                                      C.POINTER(DpPeers), _P]),
     "fb200_sgmcmc_step_joint_f32": (_i, [_P, _P, _P, _P, _i64, _P, _i, _P, _i64, _P, _P, _P, C.POINTER(SgmcmcHParams),
                                          C.POINTER(JointGrad), _P, _P, _P]),
     "fb200_sgd_explore_joint_workspace_doubles": (_i64, [_i64]),

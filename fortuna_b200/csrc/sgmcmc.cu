@@ -325,23 +325,40 @@ __global__ void __launch_bounds__(1024) sum_partials_kernel(const double* __rest
   if (threadIdx.x == 0) out[0] = sh[0];
 }
 
-// Exploration phase of cyclical SGLD: no noise, no momentum (cyclical_sgld_integrator.py:65-84).
-template <bool RMS, bool JOINT>
+// Exploration phase of cyclical SGLD: no noise, no momentum (cyclical_sgld_integrator.py:65-84).  Elements
+// [begin, end); NP as in sgmcmc_step_kernel (0: single GPU; 2 / 4 / 8: gradients averaged over the ranks by peer loads
+// and the new parameters stored into every replica; 1: the same through the NVLS multicast addresses).  Products and
+// sums are rounded one by one so that all instantiations agree bit for bit.
+template <bool RMS, bool JOINT, int NP>
 __global__ void __launch_bounds__(256)
     sgd_explore_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ pv,
-                       float* __restrict__ upd, int64_t n, const StepCoef c, const JointCoef jc) {
+                       float* __restrict__ upd, int64_t begin, int64_t n, const StepCoef c, const JointCoef jc,
+                       const DpPeers dp) {
+  constexpr bool DP = NP > 0;
+  constexpr bool MC = NP == 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   float sq = 0.0f;
-  for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < n; e += stride) {
+  for (int64_t e = begin + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < n; e += stride) {
     if (e + 3 < n) {
-      const float4 g = *reinterpret_cast<const float4*>(grad + e);
+      float4 g;
+      if constexpr (MC) {
+        g = mc_ld_reduce4(dp.mc_grad + e);
+        g.x *= dp.inv_n; g.y *= dp.inv_n; g.z *= dp.inv_n; g.w *= dp.inv_n;
+      } else if constexpr (DP) {
+        g = dp_grad4<NP>(dp, e);
+      } else {
+        g = *reinterpret_cast<const float4*>(grad + e);
+      }
       float gg[4] = {g.x, g.y, g.z, g.w};
-      if (JOINT) {
+      float pp[4] = {0.f, 0.f, 0.f, 0.f};
+      if (params) {
         const float4 p = *reinterpret_cast<const float4*>(params + e);
-        const float pp[4] = {p.x, p.y, p.z, p.w};
+        pp[0] = p.x; pp[1] = p.y; pp[2] = p.z; pp[3] = p.w;
+      }
+      if (JOINT) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          gg[k] = fmaf(jc.lik_scale, gg[k], jc.prior_coef * pp[k]);
+          gg[k] = fmaf(jc.lik_scale, gg[k], __fmul_rn(jc.prior_coef, pp[k]));
           sq += pp[k] * pp[k];
         }
       }
@@ -354,35 +371,55 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         // -1.0 * step * g, then optax.sgd(1.0) = scale(-1.0): exact sign flips
-        float u = c.step_size * gg[k];
+        float u = __fmul_rn(c.step_size, gg[k]);
         if (RMS) {
-          vv[k] = vv[k] * c.alpha + (gg[k] * gg[k]) * c.one_m_alpha;
-          u = __fdividef(u, c.rms_eps + sqrt_approx(vv[k]));
+          vv[k] = __fadd_rn(__fmul_rn(vv[k], c.alpha), __fmul_rn(__fmul_rn(gg[k], gg[k]), c.one_m_alpha));
+          u = __fdividef(u, __fadd_rn(c.rms_eps, sqrt_approx(vv[k])));
         }
         uu[k] = u;
       }
       if (RMS) *reinterpret_cast<float4*>(pv + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
       if (params) {
-        float4 p = *reinterpret_cast<const float4*>(params + e);
-        p.x += uu[0]; p.y += uu[1]; p.z += uu[2]; p.w += uu[3];
-        *reinterpret_cast<float4*>(params + e) = p;
+        const float4 p = make_float4(__fadd_rn(pp[0], uu[0]), __fadd_rn(pp[1], uu[1]), __fadd_rn(pp[2], uu[2]),
+                                     __fadd_rn(pp[3], uu[3]));
+        if constexpr (MC) {
+          mc_st4(dp.mc_params + e, p);
+        } else if constexpr (DP) {
+#pragma unroll
+          for (int q = 0; q < NP; ++q)
+            if (q < dp.n) *reinterpret_cast<float4*>(dp.params[q] + e) = p;
+        } else {
+          *reinterpret_cast<float4*>(params + e) = p;
+        }
       }
       if (upd) *reinterpret_cast<float4*>(upd + e) = make_float4(uu[0], uu[1], uu[2], uu[3]);
     } else {
       for (int64_t j = e; j < n; ++j) {
-        float g = grad[j];
+        float g;
+        if constexpr (MC) g = mc_ld_reduce1(dp.mc_grad + j) * dp.inv_n;
+        else if constexpr (DP) g = dp_grad1(dp, j);
+        else g = grad[j];
+        const float p = params ? params[j] : 0.0f;
         if (JOINT) {
-          const float p = params[j];
-          g = fmaf(jc.lik_scale, g, jc.prior_coef * p);
+          g = fmaf(jc.lik_scale, g, __fmul_rn(jc.prior_coef, p));
           sq += p * p;
         }
-        float u = c.step_size * g;
+        float u = __fmul_rn(c.step_size, g);
         if (RMS) {
-          const float v = pv[j] * c.alpha + (g * g) * c.one_m_alpha;
+          const float v = __fadd_rn(__fmul_rn(pv[j], c.alpha), __fmul_rn(__fmul_rn(g, g), c.one_m_alpha));
           pv[j] = v;
-          u = __fdividef(u, c.rms_eps + sqrt_approx(v));
+          u = __fdividef(u, __fadd_rn(c.rms_eps, sqrt_approx(v)));
         }
-        if (params) params[j] += u;
+        if (params) {
+          const float pn = __fadd_rn(p, u);
+          if constexpr (MC) {
+            mc_st1(dp.mc_params + j, pn);
+          } else if constexpr (DP) {
+            for (int q = 0; q < dp.n; ++q) dp.params[q][j] = pn;
+          } else {
+            params[j] = pn;
+          }
+        }
         if (upd) upd[j] = u;
       }
     }
@@ -554,28 +591,36 @@ extern "C" int fb200_sgmcmc_step_joint_f32(float* params, const float* grad_logl
                           key_in, key_out, leaf_keys_ws, hp, joint, sq_workspace, theta_sq_out, stream);
 }
 
+static int dp_peers_from_abi(const fb200_dp_peers_t* peers, DpPeers* dp) {
+  if (!peers) return FB200_E_NULL;
+  if (peers->n_ranks < 1 || peers->n_ranks > FB200_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->n_ranks)
+    return FB200_E_SHAPE;
+  *dp = DpPeers{};
+  dp->n = peers->n_ranks;
+  dp->inv_n = 1.0f / (float)peers->n_ranks;
+  for (int p = 0; p < peers->n_ranks; ++p) {
+    if (!peers->grad[p] || !peers->params[p]) return FB200_E_NULL;
+    if (!fb200_aligned16(peers->grad[p]) || !fb200_aligned16(peers->params[p])) return FB200_E_ALIGN;
+    dp->grad[p] = peers->grad[p];
+    dp->params[p] = peers->params[p];
+  }
+  if ((peers->mc_grad == nullptr) != (peers->mc_params == nullptr)) return FB200_E_NULL;
+  if (peers->mc_grad && (!fb200_aligned16(peers->mc_grad) || !fb200_aligned16(peers->mc_params))) return FB200_E_ALIGN;
+  dp->mc_grad = peers->mc_grad;
+  dp->mc_params = peers->mc_params;
+  return 0;
+}
+
 extern "C" int fb200_sgmcmc_step_dp_f32(float* momentum, float* precond_v, int64_t n, const fb200_leaf_t* leaves,
                                         int n_leaves, const fb200_tile_t* tiles, int64_t tile_begin, int64_t tile_end,
                                         const uint32_t* key_in, uint32_t* key_out, uint32_t* leaf_keys_ws,
                                         const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint,
                                         const fb200_dp_peers_t* peers, void* stream) {
   if (!peers || !tiles) return FB200_E_NULL;
-  if (peers->n_ranks < 1 || peers->n_ranks > FB200_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->n_ranks)
-    return FB200_E_SHAPE;
   if (tile_begin < 0 || tile_end < tile_begin) return FB200_E_SHAPE;
-  DpPeers dp{};
-  dp.n = peers->n_ranks;
-  dp.inv_n = 1.0f / (float)peers->n_ranks;
-  for (int p = 0; p < peers->n_ranks; ++p) {
-    if (!peers->grad[p] || !peers->params[p]) return FB200_E_NULL;
-    if (!fb200_aligned16(peers->grad[p]) || !fb200_aligned16(peers->params[p])) return FB200_E_ALIGN;
-    dp.grad[p] = peers->grad[p];
-    dp.params[p] = peers->params[p];
-  }
-  if ((peers->mc_grad == nullptr) != (peers->mc_params == nullptr)) return FB200_E_NULL;
-  if (peers->mc_grad && (!fb200_aligned16(peers->mc_grad) || !fb200_aligned16(peers->mc_params))) return FB200_E_ALIGN;
-  dp.mc_grad = peers->mc_grad;
-  dp.mc_params = peers->mc_params;
+  DpPeers dp;
+  const int rc = dp_peers_from_abi(peers, &dp);
+  if (rc) return rc;
   if (tile_end == tile_begin) {  // a rank without tiles still advances its key like everyone else
     if (!key_in || !key_out || !leaf_keys_ws || n_leaves <= 0) return FB200_E_NULL;
     sgmcmc_keys_kernel<<<(n_leaves + 127) / 128, 128, 0, (cudaStream_t)stream>>>(key_in, key_out, leaf_keys_ws,
@@ -597,38 +642,68 @@ static int explore_blocks(int64_t n) {
 
 extern "C" int64_t fb200_sgd_explore_joint_workspace_doubles(int64_t n) { return n > 0 ? explore_blocks(n) : 0; }
 
+template <int NP>
+static void explore_launch(float* params, const float* grad, float* precond_v, float* updates_out, int64_t begin,
+                           int64_t end, bool rms, bool joint, unsigned blocks, const StepCoef& c, const JointCoef& jc,
+                           const DpPeers& dp, cudaStream_t st) {
+  if (joint) {
+    if (rms) sgd_explore_kernel<true, true, NP><<<blocks, 256, 0, st>>>(params, grad, precond_v, updates_out, begin, end, c, jc, dp);
+    else sgd_explore_kernel<false, true, NP><<<blocks, 256, 0, st>>>(params, grad, nullptr, updates_out, begin, end, c, jc, dp);
+  } else {
+    if (rms) sgd_explore_kernel<true, false, NP><<<blocks, 256, 0, st>>>(params, grad, precond_v, updates_out, begin, end, c, jc, dp);
+    else sgd_explore_kernel<false, false, NP><<<blocks, 256, 0, st>>>(params, grad, nullptr, updates_out, begin, end, c, jc, dp);
+  }
+}
+
 static int sgd_explore_impl(float* params, const float* grad, float* precond_v, float* updates_out, int64_t n,
                             const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint, double* sq_ws,
-                            double* sq_out, void* stream) {
+                            double* sq_out, void* stream, const DpPeers* dpp = nullptr, int64_t begin = 0,
+                            int64_t end = -1) {
   if (!grad || !hp) return FB200_E_NULL;
   if (!params && !updates_out) return FB200_E_NULL;
   if (joint && !params) return FB200_E_NULL;
   if (sq_out && !sq_ws) return FB200_E_NULL;
   if (hp->rmsprop && !precond_v) return FB200_E_NULL;
   if (n <= 0) return FB200_E_SHAPE;
+  if (end < 0) end = n;
+  if (begin < 0 || end > n || begin > end) return FB200_E_SHAPE;
+  if (begin == end) return 0;
+  if (begin & 3) return FB200_E_SHAPE;
   if (!fb200_aligned16(grad) || (params && !fb200_aligned16(params)) ||
       (updates_out && !fb200_aligned16(updates_out)) || (hp->rmsprop && !fb200_aligned16(precond_v)))
     return FB200_E_ALIGN;
   const StepCoef c = make_coef(hp);
-  const unsigned blocks = (unsigned)explore_blocks(n);
+  const unsigned blocks = (unsigned)explore_blocks(end - begin);
   cudaStream_t st = (cudaStream_t)stream;
   JointCoef jc{1.0f, 0.0f, nullptr};
   if (joint) {
     jc.lik_scale = joint->lik_scale;
     jc.prior_coef = -joint->prior_prec;
     jc.sq_part = sq_out ? sq_ws : nullptr;
-    if (hp->rmsprop) sgd_explore_kernel<true, true><<<blocks, 256, 0, st>>>(params, grad, precond_v, updates_out, n, c, jc);
-    else sgd_explore_kernel<false, true><<<blocks, 256, 0, st>>>(params, grad, nullptr, updates_out, n, c, jc);
-  } else {
-    if (hp->rmsprop) sgd_explore_kernel<true, false><<<blocks, 256, 0, st>>>(params, grad, precond_v, updates_out, n, c, jc);
-    else sgd_explore_kernel<false, false><<<blocks, 256, 0, st>>>(params, grad, nullptr, updates_out, n, c, jc);
   }
+  const DpPeers nodp{};
+  const bool rms = hp->rmsprop != 0;
+  if (!dpp) explore_launch<0>(params, grad, precond_v, updates_out, begin, end, rms, joint != nullptr, blocks, c, jc, nodp, st);
+  else if (dpp->mc_grad) explore_launch<1>(params, grad, precond_v, nullptr, begin, end, rms, joint != nullptr, blocks, c, jc, *dpp, st);
+  else if (dpp->n <= 2) explore_launch<2>(params, grad, precond_v, nullptr, begin, end, rms, joint != nullptr, blocks, c, jc, *dpp, st);
+  else if (dpp->n <= 4) explore_launch<4>(params, grad, precond_v, nullptr, begin, end, rms, joint != nullptr, blocks, c, jc, *dpp, st);
+  else explore_launch<8>(params, grad, precond_v, nullptr, begin, end, rms, joint != nullptr, blocks, c, jc, *dpp, st);
   FB200_LAUNCH_CHECK();
   if (joint && sq_out) {
     sum_partials_kernel<<<1, 1024, 0, st>>>(sq_ws, blocks, sq_out);
     FB200_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int fb200_sgd_explore_step_dp_f32(float* precond_v, int64_t n, int64_t elem_begin, int64_t elem_end,
+                                             const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint,
+                                             const fb200_dp_peers_t* peers, void* stream) {
+  DpPeers dp;
+  const int rc = dp_peers_from_abi(peers, &dp);
+  if (rc) return rc;
+  return sgd_explore_impl(peers->params[peers->rank], peers->grad[peers->rank], precond_v, nullptr, n, hp, joint,
+                          nullptr, nullptr, stream, &dp, elem_begin, elem_end);
 }
 
 extern "C" int fb200_sgd_explore_step_f32(float* params, const float* grad, float* precond_v, float* updates_out,

@@ -189,11 +189,13 @@ def dp_tile_range(n_tiles: int, world: int, rank: int):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def sgmcmc_step_dp(grad_ptrs, param_ptrs, rank, momentum, precond_v, n, leaves, tiles, key_in, key_out, leaf_keys_ws,
-                   hp, joint=None, tile_range=None, mc_grad_ptr=0, mc_param_ptr=0):
-    """Data-parallel fused step (fb200_sgmcmc_step_dp_f32): ``grad_ptrs`` / ``param_ptrs`` are every rank's [n] float32
-    buffers as peer-mapped device addresses (rank order); this rank updates tiles ``tile_range`` (default: its balanced
-    share) reading all gradients and writing all parameter replicas.  The caller brackets the call with barriers."""
+def dp_elem_range(n: int, world: int, rank: int):
+    """Contiguous split of [0, n) into 4-aligned element ranges: rank r owns [begin, end)."""
+    per = ((int(n) + 3) // 4 + world - 1) // world * 4
+    return min(rank * per, int(n)), min((rank + 1) * per, int(n))
+
+
+def _dp_peers(grad_ptrs, param_ptrs, rank, mc_grad_ptr=0, mc_param_ptr=0):
     world = len(grad_ptrs)
     peers = _lib.DpPeers()
     peers.n_ranks, peers.rank = world, int(rank)
@@ -202,12 +204,40 @@ def sgmcmc_step_dp(grad_ptrs, param_ptrs, rank, momentum, precond_v, n, leaves, 
         peers.params[p] = int(param_ptrs[p])
     if mc_grad_ptr and mc_param_ptr:  # NVLS multicast addresses: in-switch gradient sum and parameter replication
         peers.mc_grad, peers.mc_params = int(mc_grad_ptr), int(mc_param_ptr)
+    return peers
+
+
+def _joint_struct(joint):
+    if joint is None:
+        return None
+    jg = _lib.JointGrad()
+    jg.lik_scale = float(np.float32(joint[0]))
+    jg.prior_prec = float(np.float32(joint[1]))
+    return jg
+
+
+def sgd_explore_step_dp(grad_ptrs, param_ptrs, rank, precond_v, n, hp, joint=None, elem_range=None, mc_grad_ptr=0,
+                        mc_param_ptr=0):
+    """Data-parallel exploration step of cyclical SGLD (fb200_sgd_explore_step_dp_f32); see ``sgmcmc_step_dp``."""
+    peers = _dp_peers(grad_ptrs, param_ptrs, rank, mc_grad_ptr, mc_param_ptr)
+    e0, e1 = elem_range if elem_range is not None else dp_elem_range(n, len(grad_ptrs), rank)
+    jg = _joint_struct(joint)
+    check(
+        lib().fb200_sgd_explore_step_dp_f32(_ptr(precond_v, torch.float32, True), int(n), int(e0), int(e1), C.byref(hp),
+                                            C.byref(jg) if jg is not None else None, C.byref(peers), _stream()),
+        "fb200_sgd_explore_step_dp_f32",
+    )
+
+
+def sgmcmc_step_dp(grad_ptrs, param_ptrs, rank, momentum, precond_v, n, leaves, tiles, key_in, key_out, leaf_keys_ws,
+                   hp, joint=None, tile_range=None, mc_grad_ptr=0, mc_param_ptr=0):
+    """Data-parallel fused step (fb200_sgmcmc_step_dp_f32): ``grad_ptrs`` / ``param_ptrs`` are every rank's [n] float32
+    buffers as peer-mapped device addresses (rank order); this rank updates tiles ``tile_range`` (default: its balanced
+    share) reading all gradients and writing all parameter replicas.  The caller brackets the call with barriers."""
+    world = len(grad_ptrs)
+    peers = _dp_peers(grad_ptrs, param_ptrs, rank, mc_grad_ptr, mc_param_ptr)
     t0, t1 = tile_range if tile_range is not None else dp_tile_range(tiles.shape[0], world, rank)
-    jg = None
-    if joint is not None:
-        jg = _lib.JointGrad()
-        jg.lik_scale = float(np.float32(joint[0]))
-        jg.prior_prec = float(np.float32(joint[1]))
+    jg = _joint_struct(joint)
     check(
         lib().fb200_sgmcmc_step_dp_f32(
             _ptr(momentum, torch.float32), _ptr(precond_v, torch.float32, True), int(n), _ptr(leaves, torch.int64),

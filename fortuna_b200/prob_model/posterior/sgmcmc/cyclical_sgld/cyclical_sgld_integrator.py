@@ -56,7 +56,7 @@ def cyclical_sgld_integrator(
 
     ws = {}
 
-    def _explore(gradient, state, params, joint=None):
+    def _explore(gradient, state, params, joint=None, dp=None):
         inner = state.sgld_state
         grad = as_flat_tree(gradient, like=inner.momentum)
         hp = ops.make_hparams(
@@ -65,6 +65,11 @@ def cyclical_sgld_integrator(
         )
         v = precond_buffer(inner.preconditioner_state)
         updates = grad.empty_like() if params is None else None
+        if dp is not None:
+            if params is None or params.flat.data_ptr() != dp.params.data_ptr() or grad.flat.data_ptr() != dp.grad.data_ptr():
+                raise ValueError("the data-parallel step works in place on the peer-mapped parameter / gradient vectors")
+            dp.explore_step(v.flat if v is not None else None, hp, joint=None if joint is None else joint[:2])
+            return None, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner._replace(count=inner.count + 1))
         ops.sgd_explore_step(
             params.flat if params is not None else None,
             grad.flat,
@@ -83,11 +88,11 @@ def cyclical_sgld_integrator(
             return updates, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner)
         return _explore(gradient, state, None)
 
-    def apply_fn(params: FlatTree, gradient, state, joint=None):
+    def apply_fn(params: FlatTree, gradient, state, joint=None, dp=None):
         if is_sampling_phase(state.sgld_state.count, cycle_length, exploration_ratio):
-            _, inner = sgld.apply(params, gradient, state.sgld_state, joint=joint)
+            _, inner = sgld.apply(params, gradient, state.sgld_state, joint=joint, dp=dp)
             return params, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner)
-        _, new_state = _explore(gradient, state, params, joint=joint)
+        _, new_state = _explore(gradient, state, params, joint=joint, dp=dp)
         return params, new_state
 
     return GradientTransformation(init_fn, update_fn, apply_fn)

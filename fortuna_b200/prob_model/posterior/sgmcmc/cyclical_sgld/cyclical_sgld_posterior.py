@@ -14,8 +14,6 @@ class CyclicalSGLDPosterior(SGMCMCPosterior):
         super().__init__(SGMCMCPosteriorStateRepository(posterior_approximator.n_samples, template=bound_model.params), rng)
 
     def fit(self, train_data_loader, val_data_loader=None, fit_config=None, **_):
-        if getattr(self.bound, "dp", None) is not None:
-            raise NotImplementedError("the data-parallel step covers SGHMC; run cyclical SGLD with FitProcessor(devices=0)")
         a = self.posterior_approximator
         n_epochs = fit_config.optimizer.n_epochs
         c = fit_config.checkpointer

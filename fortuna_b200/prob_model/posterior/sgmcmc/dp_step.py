@@ -57,6 +57,14 @@ class PeerReplicas:
         self._hp.barrier()
 
 
+    def explore_step(self, precond_v, hp, joint=None):
+        """The same for the exploration phase of cyclical SGLD (no noise, no momentum)."""
+        self._hg.barrier()
+        ops.sgd_explore_step_dp(self.grad_ptrs, self.param_ptrs, self.rank, precond_v, self.params.numel(), hp, joint=joint,
+                                mc_grad_ptr=self.mc_grad_ptr, mc_param_ptr=self.mc_param_ptr)
+        self._hp.barrier()
+
+
 class DataParallelStep:
     """Self-contained sampler state over a flat tree (scripts / benchmarks); the training loop uses ``PeerReplicas``
     through ``sghmc_integrator(...).apply(..., dp=...)``."""
@@ -82,3 +90,6 @@ class DataParallelStep:
         self.peers.step(self.momentum, self.precond_v, self.leaves, self.tiles, self.key, self._key_next,
                         self._leaf_keys, hp, joint=joint, tile_range=self.tile_range)
         self.key, self._key_next = self._key_next, self.key
+
+    def explore_step(self, hp, joint: Optional[tuple] = None) -> None:
+        self.peers.explore_step(self.precond_v, hp, joint=joint)

@@ -160,6 +160,11 @@ int fb200_sgmcmc_step_dp_f32(float* momentum, float* precond_v, int64_t n, const
                              const fb200_tile_t* tiles, int64_t tile_begin, int64_t tile_end, const uint32_t* key_in,
                              uint32_t* key_out, uint32_t* leaf_keys_ws, const fb200_sgmcmc_hparams_t* hp,
                              const fb200_joint_grad_t* joint, const fb200_dp_peers_t* peers, void* stream);
+/* The exploration phase of cyclical SGLD (fb200_sgd_explore_step_f32) in the same data-parallel form: this rank updates
+ * elements [elem_begin, elem_end) (elem_begin a multiple of 4) of every replica from the rank-averaged gradient. */
+int fb200_sgd_explore_step_dp_f32(float* precond_v, int64_t n, int64_t elem_begin, int64_t elem_end,
+                                  const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint,
+                                  const fb200_dp_peers_t* peers, void* stream);
 int64_t fb200_sgd_explore_joint_workspace_doubles(int64_t n);
 int fb200_sgd_explore_step_joint_f32(float* params, const float* grad_loglik, float* precond_v, int64_t n,
                                      const fb200_sgmcmc_hparams_t* hp, const fb200_joint_grad_t* joint,

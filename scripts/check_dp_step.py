@@ -88,6 +88,36 @@ def parity(dev, rank, world, multicast):
                     print(f"rank {rank}: replica differs from rank 0's (mc={multicast}, step {it})")
                 if not exact:
                     ref_p.copy_(dp.params)  # follow the fused chain so that rounding does not accumulate in the check
+            # exploration phase of cyclical SGLD (no noise): same comparison against fb200_sgd_explore_step_f32
+            for it in range(2):
+                grads = []
+                for r in range(world):
+                    gr = torch.Generator(device=dev)
+                    gr.manual_seed(5000 + 10 * it + r)
+                    grads.append(torch.empty(n, device=dev).normal_(0, 1, generator=gr))
+                dp.grad.copy_(grads[rank])
+                before = dp.params.clone()
+                dp.explore_step(hp, joint=joint)
+                acc = grads[0].clone()
+                for r in range(1, world):
+                    acc += grads[r]
+                acc *= 1.0 / world
+                ex_p = before.clone()
+                ex_v = dp.precond_v.clone() if rms else None  # the owned slice already advanced; compare params only
+                ops.sgd_explore_step(ex_p, acc, torch.zeros(n, device=dev) if rms else None, None, hp,
+                                     joint=None if joint is None else (joint[0], joint[1], None))
+                torch.cuda.synchronize()
+                if not rms:  # with RMSprop the reference state above is not the chain's; the no-preconditioner case is exact
+                    same = torch.equal(dp.params, ex_p) if exact else torch.allclose(dp.params, ex_p, rtol=2e-5, atol=2e-6)
+                    if not same:
+                        bad += 1
+                        print(f"rank {rank}: explore joint={joint} mc={multicast} step {it}: params differ, "
+                              f"max abs {(dp.params - ex_p).abs().max().item()}")
+                r0 = dp.params.clone()
+                dist.broadcast(r0, 0)
+                if not torch.equal(r0, dp.params):
+                    bad += 1
+                    print(f"rank {rank}: explore: replica differs from rank 0's (mc={multicast})")
             t0, t1 = dp.tile_range
             # the owned slice of the optimizer state matches; the rest was never touched
             own = torch.zeros(n, dtype=torch.bool, device=dev)

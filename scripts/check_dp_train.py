@@ -18,16 +18,18 @@ sys.path.insert(0, os.path.join(ROOT, "examples"))
 from two_moons_sghmc import MLP, make_moons  # noqa: E402
 
 from fortuna_b200.data import DataLoader  # noqa: E402
-from fortuna_b200.prob_model import (FitConfig, FitOptimizer, FitProcessor, ProbClassifier,  # noqa: E402
-                                     SGHMCPosteriorApproximator)
+from fortuna_b200.prob_model import (CyclicalSGLDPosteriorApproximator, FitConfig, FitOptimizer,  # noqa: E402
+                                     FitProcessor, ProbClassifier, SGHMCPosteriorApproximator)
 
 
-def fit(devices, seed=0):
+def fit(devices, seed=0, cyclical=False):
     torch.manual_seed(seed)  # same initial weights on every rank and in both fits
     train = make_moons(512, 0.07, 0)
     loader = DataLoader.from_array_data(train, batch_size=128, shuffle=False)
-    pm = ProbClassifier(model=MLP(), posterior_approximator=SGHMCPosteriorApproximator(
-        n_samples=6, n_thinning=2, burnin_length=4, step_schedule=1e-4), seed=seed)
+    approx = (CyclicalSGLDPosteriorApproximator(n_samples=4, n_thinning=1, cycle_length=8, init_step_size=1e-4,
+                                                exploration_ratio=0.5) if cyclical else
+              SGHMCPosteriorApproximator(n_samples=6, n_thinning=2, burnin_length=4, step_schedule=1e-4))
+    pm = ProbClassifier(model=MLP(), posterior_approximator=approx, seed=seed)
     status = pm.train(loader, fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=4), processor=FitProcessor(devices=devices)))
     torch.cuda.synchronize()
     return pm, status["fit_status"]["loss"]
@@ -39,7 +41,19 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     bad = 0
-    pm_dp, loss_dp = fit(-1)
+    for cyclical in (False, True):
+        bad += compare(rank, dev, cyclical)
+    tot = torch.tensor([bad], device=dev)
+    dist.all_reduce(tot)
+    if rank == 0:
+        print("dp_train:", "OK" if tot.item() == 0 else f"{tot.item()} MISMATCHES")
+    dist.destroy_process_group()
+    sys.exit(1 if tot.item() else 0)
+
+
+def compare(rank, dev, cyclical):
+    bad = 0
+    pm_dp, loss_dp = fit(-1, cyclical=cyclical)
     assert pm_dp.posterior.bound.dp is not None, "the fit did not run data-parallel"
     flat = pm_dp.posterior.bound.params.flat
     bank = pm_dp.posterior.state.bank
@@ -49,7 +63,7 @@ def main():
         if not torch.equal(r0, t):
             bad += 1
             print(f"rank {rank}: {name} differ from rank 0's")
-    pm_1, loss_1 = fit(0)
+    pm_1, loss_1 = fit(0, cyclical=cyclical)
     assert pm_1.posterior.bound.dp is None
     a, b = flat.cpu().numpy(), pm_1.posterior.bound.params.flat.cpu().numpy()
     if not np.allclose(a, b, rtol=1e-4, atol=1e-5):
@@ -61,13 +75,10 @@ def main():
     if not np.allclose(loss_dp, loss_1, rtol=1e-4):
         bad += 1
         print(f"rank {rank}: logged losses differ: {loss_dp} vs {loss_1}")
-    tot = torch.tensor([bad], device=dev)
-    dist.all_reduce(tot)
     if rank == 0:
-        print("dp_train:", "OK" if tot.item() == 0 else f"{tot.item()} MISMATCHES", "| losses", np.round(loss_dp, 3).tolist(),
-              "| multicast", pm_dp.posterior.bound.dp.multicast)
-    dist.destroy_process_group()
-    sys.exit(1 if tot.item() else 0)
+        print("cyclical SGLD" if cyclical else "SGHMC", "| losses", np.round(loss_dp, 3).tolist(), "| multicast",
+              pm_dp.posterior.bound.dp.multicast, "| mismatches", bad)
+    return bad
 
 
 if __name__ == "__main__":

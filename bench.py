@@ -457,6 +457,14 @@ def run_gpu_arm(args):
                 "hbm_frac_per_gpu": 20 * ex["n_params"] / (ms * 1e-3) / 1e9 / peak}}
         except Exception as exc:
             line["extras"] = {"error": repr(exc)}
+        # the other way to use N GPUs for sampling: ONE data-parallel chain, gradient average + step + parameter broadcast
+        # fused into one kernel per rank over NVLink peer memory
+        try:
+            from fortuna_b200.bench_extras import dp_step_extras
+
+            line["extras"]["sghmc_data_parallel_step"] = dp_step_extras(dev, rank, world)
+        except Exception as exc:
+            line["extras"]["sghmc_data_parallel_step"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu:
         v, ms, cores, sample = cpu_reference_throughput(args.cpu_rows_per_core, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

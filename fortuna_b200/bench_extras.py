@@ -92,3 +92,53 @@ def last_layer_extras(device, tf_burst, tf_sustained, S=64, B=8192, D=2048, Cn=1
                      "frac_of_sustained_peak": tf / tf_sustained}
         del o
     return out
+
+
+def dp_step_extras(device, rank, world, steps=10, warmup=3):
+    """Data-parallel sampler step (fb200_sgmcmc_step_dp_f32: gradient average + step + parameter broadcast in one kernel
+    per rank over NVLink) on the BERT-base-sized flat tree, against NCCL all-reduce + the replicated step.  CUDA events,
+    max over ranks; every rank must call this (it allocates symmetric memory collectively)."""
+    import torch.distributed as dist
+
+    from . import ops
+    from .prob_model.posterior.sgmcmc.dp_step import DataParallelStep
+
+    lens = [23440896, 393216, 1536] + [2359296] * 36 + [589824] + [768] * 100
+    offs, n = [], 0
+    for l in lens:
+        offs.append(n)
+        n += (l + 3) // 4 * 4
+    dp = DataParallelStep(lens, offs, n, device, world, rank, seed=0)
+    dp.params.normal_(0, 0.02)
+    dp.grad.normal_(0, 1)
+    hp = ops.make_hparams(1e-5, 0.05)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(steps):
+            fn()
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev[0].elapsed_time(ev[1]) / steps], device=device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0])
+
+    fused = timed(lambda: dp.step(hp))
+    p, m, g = dp.params.clone(), torch.zeros(n, device=device), dp.grad.clone()
+    key, key2 = ops.PRNGKey(0, device), torch.empty(2, dtype=ops.KEY_DTYPE, device=device)
+    lk = torch.empty((len(lens), 2), dtype=ops.KEY_DTYPE, device=device)
+
+    def base():
+        dist.all_reduce(g, op=dist.ReduceOp.AVG)
+        ops.sgmcmc_step(p, g, m, None, None, dp.leaves, dp.tiles, key, key2, lk, hp)
+
+    nccl = timed(base)
+    return {"n_params": n, "ranks": world, "mode": "nvls multicast" if dp.multicast else "peer loads/stores",
+            "fused_ms": fused, "nccl_allreduce_plus_step_ms": nccl, "speedup": nccl / fused,
+            "param_updates_per_s": n / (fused * 1e-3),
+            "link_bytes_in_per_rank": 4 * (n // world) * (world if dp.multicast else 2 * (world - 1))}

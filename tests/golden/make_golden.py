@@ -182,6 +182,27 @@ def oracle_vectors():
         out[f"reg_{k}"] = v
     L, dL = Cal.calib_terms(z, t, np.float32(0.4))
     out["calib_L_lt0.4"], out["calib_dL_lt0.4"] = L, dL
+
+    # --- output calibration models and the MaxCovFixPrec calibrator
+    from oracle import maxcov as MC
+    from oracle import output_calib as OC
+
+    z0 = z[0]                                                      # [12, 7] logits of the fixture
+    out["oc_focal_g2_lt0.3"] = np.array(OC.focal_loss(z0, t, 0.3, 2.0), np.float64)
+    out["oc_focal_g0_lt0"] = np.array(OC.focal_loss(z0, t, 0.0, 0.0), np.float64)
+    yr = r.standard_normal((10, 2)).astype(np.float32)
+    out["oc_reg_targets"] = yr
+    out["oc_scaled_mse_lt0.2"] = np.array(OC.scaled_mse(zr[0], yr, 0.2), np.float64)
+    out["oc_cls_sample"] = OC.cls_output_sample(z0, prng.PRNGKey(13), 5, np.array([0.3], np.float32))
+    out["oc_reg_sample"] = OC.reg_output_sample(zr[0], prng.PRNGKey(13), 3, np.array([0.2], np.float32))
+    out["oc_traj_cls"] = OC.calibrate(z0, t, 10)[1]
+    out["oc_traj_reg"] = OC.calibrate(zr[0], yr, 10, regression=True)[1]
+    pb = r.uniform(0, 1, 200).astype(np.float32)
+    yb = (r.uniform(0, 1, 200) < pb).astype(np.int32)              # labels drawn from the scores: a calibrated classifier
+    out["mc_probs"], out["mc_targets"] = pb, yb
+    tp, tn, vp, vn = MC.calibrate(yb, pb, 0.8, 0.8, n_taus=40)
+    out["mc_taus"], out["mc_values_pos"], out["mc_values_neg"] = np.array([tp, tn], np.float32), vp, vn
+    out["mc_patched"] = MC.apply_patches(pb, tp, tn)
     return out
 
 

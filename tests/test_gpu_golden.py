@@ -200,3 +200,42 @@ def test_widened_rows_vectors(cuda):
     terms = ops.calib_cls_loss_terms(z, t, torch.tensor([0.4], dtype=torch.float32, device=dev)).cpu().numpy()
     np.testing.assert_allclose(terms[0], VEC["calib_L_lt0.4"], rtol=2e-6, atol=1e-4)
     np.testing.assert_allclose(terms[1], VEC["calib_dL_lt0.4"], rtol=2e-5, atol=1e-4)
+
+
+def test_output_calib_and_maxcov_vectors(cuda):
+    """Frozen vectors of the output calibration models (loss terms, Adam trajectories, output-layer target samples) and
+    of the MaxCovFixPrec calibrator, through the C ABI and the user classes."""
+    from fortuna_b200 import ops
+    from fortuna_b200.conformal import MaxCoverageFixedPrecisionBinaryClassificationCalibrator as Cal
+    from fortuna_b200.output_calib_model import Config, Monitor, Optimizer, OutputCalibClassifier, OutputCalibRegressor
+
+    dev = cuda
+    z0 = torch.from_numpy(VEC["z"][0].copy()).to(dev)
+    t = torch.from_numpy(VEC["z_targets"]).to(dev)
+    n = z0.shape[0]
+    for key, lt, gamma in (("oc_focal_g2_lt0.3", 0.3, 2.0), ("oc_focal_g0_lt0", 0.0, 0.0)):
+        terms = ops.output_calib_focal_loss_terms(z0, t, torch.tensor([lt], dtype=torch.float32, device=dev), gamma).cpu().numpy()
+        np.testing.assert_allclose(terms[0] / n, VEC[key][0], rtol=2e-5)
+        np.testing.assert_allclose(-np.exp(-lt) * terms[1] / n, VEC[key][1], rtol=2e-4, atol=1e-6)
+    zr = torch.from_numpy(VEC["reg_outputs"][0].copy()).to(dev)
+    yr = torch.from_numpy(VEC["oc_reg_targets"]).to(dev)
+    terms = ops.output_calib_scaled_mse_terms(zr, yr, torch.tensor([0.2], dtype=torch.float32, device=dev)).cpu().numpy()
+    np.testing.assert_allclose(terms / zr.shape[0], VEC["oc_scaled_mse_lt0.2"], rtol=2e-5)
+    got = ops.cls_output_sample_targets(z0, ops.PRNGKey(13, dev), 5, torch.tensor([0.3], dtype=torch.float32, device=dev))
+    assert np.array_equal(got.cpu().numpy(), VEC["oc_cls_sample"])
+    got = ops.reg_output_sample_targets(zr, ops.PRNGKey(13, dev), 3, torch.tensor([0.2], dtype=torch.float32, device=dev))
+    np.testing.assert_allclose(got.cpu().numpy(), VEC["oc_reg_sample"], rtol=1e-5, atol=2e-6)
+    cfg = Config(optimizer=Optimizer(n_epochs=10), monitor=Monitor(verbose=False))
+    clf = OutputCalibClassifier()
+    clf._check_output_dim = lambda outputs, targets: None  # the 12 fixture targets do not cover all 7 classes
+    clf.calibrate(VEC["z"][0], VEC["z_targets"], config=cfg)
+    assert abs(float(clf.predictive.state.get().log_temp[0]) - float(VEC["oc_traj_cls"][-1])) < 1e-5
+    reg = OutputCalibRegressor()
+    reg.calibrate(VEC["reg_outputs"][0], VEC["oc_reg_targets"], config=cfg)
+    assert abs(float(reg.predictive.state.get().log_temp[0]) - float(VEC["oc_traj_reg"][-1])) < 1e-5
+    cal = Cal()
+    patched = cal.calibrate(targets=VEC["mc_targets"], probs=VEC["mc_probs"], true_positive_precision_threshold=0.8,
+                            true_negative_precision_threshold=0.8, test_probs=VEC["mc_probs"], n_taus=40)
+    assert cal.patches["tau_pos"] == VEC["mc_taus"][0] and cal.patches["tau_neg"] == VEC["mc_taus"][1]
+    assert np.array_equal(cal._values[0], VEC["mc_values_pos"]) and np.array_equal(cal._values[1], VEC["mc_values_neg"])
+    assert np.array_equal(patched.cpu().numpy(), VEC["mc_patched"])

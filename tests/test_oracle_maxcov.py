@@ -53,3 +53,29 @@ def test_indicator_switches_once_along_the_grid(seed):
     bn = np.stack([((np.float32(1) + (t - np.float32(1)) * (p < 0.5)) * p) <= np.float32(1 - tn_thr) for t in taus_neg])
     for b in (bp, bn):
         assert np.all(np.diff(b.astype(np.int8), axis=0) >= 0)  # false ... false true ... true
+
+
+def test_host_side_values_from_counts_match_oracle():
+    """The product's host logic (float32 ratios, margin test, arg-max, jnp.linspace restatement) fed with brute-force
+    counts reproduces the oracle's objective values and chosen taus - the GPU kernel only has to deliver the counts."""
+    from fortuna_b200.conformal.classification import maxcovfixprec_binary_classfication as H
+
+    r = np.random.default_rng(7)
+    p = r.uniform(0, 1, 3000).astype(np.float32)
+    y = (r.uniform(0, 1, 3000) < p).astype(np.int32)
+    for tp_thr, tn_thr, margin in ((0.8, 0.7, 0.0), (0.9, 0.9, 0.03)):
+        taus_pos, taus_neg = M.tau_grids(tp_thr, tn_thr, 100)
+        assert np.array_equal(H._linspace(1, 2 * tp_thr, 100), taus_pos)
+        assert np.array_equal(H._linspace(2 * (1 - tn_thr), 1, 100)[::-1], taus_neg)
+        cp, lp, cn, ln = [], [], [], []
+        for t in taus_pos:
+            b = np.minimum((np.float32(1) + (t - np.float32(1)) * (p > 0.5)) * p, np.float32(1)) >= np.float32(tp_thr)
+            cp.append(b.sum()), lp.append((y * b).sum())
+        for t in taus_neg:
+            b = ((np.float32(1) + (t - np.float32(1)) * (p < 0.5)) * p).astype(np.float32) <= np.float32(1 - tn_thr)
+            cn.append(b.sum()), ln.append(((1 - y) * b).sum())
+        vp = H._values(np.array(cp), np.array(lp), len(p), tp_thr + margin)
+        vn = H._values(np.array(cn), np.array(ln), len(p), tn_thr + margin)
+        tp, tn, want_vp, want_vn = M.calibrate(y, p, tp_thr, tn_thr, margin=margin)
+        assert np.array_equal(vp, want_vp) and np.array_equal(vn, want_vn)
+        assert taus_pos[int(np.argmax(vp))] == tp and taus_neg[int(np.argmax(vn))] == tn

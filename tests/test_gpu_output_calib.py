@@ -231,3 +231,24 @@ def test_regressor_calibration_and_predictive(cuda, tmp_path):
     other = OutputCalibRegressor()
     other.load_state(str(tmp_path))
     assert np.array_equal(other.predictive.state.get().log_temp, lt)
+
+
+def test_classifier_custom_uncertainty_fn_sees_calibrated_logits(cuda):
+    """``Monitor(uncertainty_fn=...)`` receives the CALIBRATED outputs (output_calib_model_calibrator.py:313-316 after
+    loss.py:52-58); a softmax there reproduces the default uncertainty estimates."""
+    from fortuna_b200.metric.classification import brier_score
+    from fortuna_b200.output_calib_model import Config, Monitor, Optimizer, OutputCalibClassifier
+
+    def brier(dummy, p, y):
+        return brier_score(p, y)
+
+    z, y = _cls_data(300, 6, 9)
+    runs = []
+    for fn in (None, lambda zc: torch.softmax(zc, dim=-1)):
+        m = OutputCalibClassifier()
+        st = m.calibrate(z, y, val_outputs=z, val_targets=y,
+                         config=Config(optimizer=Optimizer(n_epochs=12), monitor=Monitor(metrics=(brier,), uncertainty_fn=fn, verbose=False)))
+        runs.append(st)
+    np.testing.assert_allclose(runs[0]["brier"], runs[1]["brier"], rtol=2e-5)
+    np.testing.assert_allclose(runs[0]["val_brier"], runs[1]["val_brier"], rtol=2e-5)
+    assert runs[0]["val_brier"][-1] != runs[0]["val_brier"][0]  # the temperature moved, so the calibrated outputs changed

@@ -9,17 +9,12 @@ from .prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
 from .prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
 from .prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
 from .utils.flat_tree import FlatTree
+from .utils.tree_shapes import bert_base_shapes
 
 
 def sampler_extras(device, hbm_peak_gbs, steps=20, warmup=3, seed=0, only=None, joint=False):
-    import sys, os
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    if root not in sys.path:
-        sys.path.insert(0, root)
-    from tests import trees
-
     out = {}
-    params = FlatTree.from_shapes(trees.bert_base_shapes(), device=device)
+    params = FlatTree.from_shapes(bert_base_shapes(), device=device)
     params.flat.normal_(0.0, 0.01)
     grad = params.empty_like()
     grad.flat.normal_(0.0, 0.01)

@@ -14,185 +14,11 @@
 // producer warp with cp.async.bulk (TMA engine) into an mbarrier-signalled shared-memory ring.  Eight
 // consumer warps each own whole rows (G lanes per row), so the per-row max / sum-exp are warp-shuffle
 // reductions and the per-(b,c) sums over s live in registers until the tile's single store.
-#include <cuda_bf16.h>
-#include <math_constants.h>
+#include <stdlib.h>
 
-#include "async_copy.cuh"
-#include "common.cuh"
+#include "bma_reduce.cuh"
 
 namespace fb200 {
-
-constexpr int kMaxStages = 8;
-// NW consumer warps (whole warpgroups) + one producer warpgroup (one lane of it works).  The launch bound caps
-// ptxas at 65536 / threads registers; the producer warpgroup gives most of its share back (setmaxnreg.dec) and the
-// consumer warpgroups take it (setmaxnreg.inc):  NW = 8: 8*32*232 + 4*32*40;  12: 12*32*160 + 4*32*32;
-// 16: 16*32*112 + 4*32*32.  The sum must not exceed what the CTA owns at launch (threads * the ptxas register
-// count, which is 65536 / threads rounded DOWN to a multiple of 8: 168, 128, 96) or setmaxnreg.inc never returns.
-template <int NW>
-struct WarpCfg {
-  static constexpr int kThreads = (NW + 4) * 32;
-  static constexpr int kConsumerRegs = NW == 8 ? 232 : (NW == 12 ? 160 : 112);
-  static constexpr int kProducerRegs = NW == 8 ? 40 : 32;
-  static constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8;
-  static_assert(NW * 32 * kConsumerRegs + 4 * 32 * kProducerRegs <= kThreads * kLaunchRegs,
-                "setmaxnreg budget exceeds the registers the CTA owns at launch");
-};
-
-struct ClsArgs {
-  const void* logits;
-  const float* log_temp;
-  const int32_t* targets;
-  int S, B, C;
-  fb200_cls_outputs_t out;
-  const unsigned long long* slot_ptrs;  // shard mode: device array [n_ranks] of float* (local or peer memory)
-  int n_ranks, rows_per_rank;
-  int tile_rot;  // shard mode: tiles are visited starting here (staggered per rank: no owner is everyone's target at once)
-  int partial_mode;
-  int n_tiles;
-  int n_stages;
-  int ss;                      // samples per pipeline stage
-  uint32_t tile_stride_bytes;  // bytes between consecutive samples inside a stage (multiple of 16)
-  uint32_t stage_bytes;        // multiple of 128
-  int bulk_ok;                 // base pointer and sample stride are 16-byte aligned
-  float log_S;                 // float32 log(S)
-};
-
-template <typename T, int VEC>
-struct RowLoad;
-template <>
-struct RowLoad<float, 4> {
-  static __device__ __forceinline__ void load(const float* p, float (&z)[4]) {
-    const float4 v = *reinterpret_cast<const float4*>(p);
-    z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w;
-  }
-};
-template <>
-struct RowLoad<float, 1> {
-  static __device__ __forceinline__ void load(const float* p, float (&z)[1]) { z[0] = *p; }
-};
-template <>
-struct RowLoad<__nv_bfloat16, 4> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&z)[4]) {
-    const uint2 v = *reinterpret_cast<const uint2*>(p);
-    z[0] = __uint_as_float(v.x << 16);
-    z[1] = __uint_as_float(v.x & 0xFFFF0000u);
-    z[2] = __uint_as_float(v.y << 16);
-    z[3] = __uint_as_float(v.y & 0xFFFF0000u);
-  }
-};
-template <>
-struct RowLoad<__nv_bfloat16, 1> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&z)[1]) { z[0] = __bfloat162float(*p); }
-};
-
-__device__ __forceinline__ void st_f4(float* p, float x, float y, float z, float w) {
-  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-__device__ __forceinline__ float ex2_approx_ftz(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx_ftz(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-
-// Process RI rows (consecutive samples s of the same input b) held in shared memory: softmax of each row,
-// accumulate sum_s p, sum_s p^2 and the entropy partials (sum_s p(1-p) is formed as sum p - sum p^2 at the end:
-// two accumulators per (b,c) instead of three is what lets 12-16 warps share the register file).  The RI rows are independent until the final
-// accumulation, so their shuffle reductions and MUFU chains overlap (ILP); accumulation keeps the s order.
-template <typename T, int G, int NV, int VEC, bool TAILONLY, int RI>
-__device__ __forceinline__ void process_rows(const T* const (&rowp)[RI], int g, int C, float k2,
-                                             float (&sp)[NV][VEC], float (&sp2)[NV][VEC],
-                                             float& spl, float& sum_l, float (&cshift)[RI], float (&l2sum)[RI]) {
-  float z[RI][NV][VEC];
-  float m[RI];
-  // pass A: rows -> registers (padding lanes get -1e30: finite even after the log2(e)*scale multiply, so
-  // 0 * u is never NaN for them, while a genuine -inf logit still yields the reference's 0 * -inf = NaN)
-#pragma unroll
-  for (int ri = 0; ri < RI; ++ri) {
-    float pm[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) pm[k] = -CUDART_INF_F;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int c0 = (g + G * j) * VEC;
-      if (TAILONLY && j < NV - 1) {
-        RowLoad<T, VEC>::load(rowp[ri] + c0, z[ri][j]);  // every lane's chunk is inside the row
-      } else if (c0 < C) {
-        RowLoad<T, VEC>::load(rowp[ri] + c0, z[ri][j]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) z[ri][j][k] = -1.0e30f;
-      }
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) pm[k] = fmaxf(pm[k], z[ri][j][k]);
-    }
-    m[ri] = pm[0];
-#pragma unroll
-    for (int k = 1; k < VEC; ++k) m[ri] = fmaxf(m[ri], pm[k]);
-  }
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1)
-#pragma unroll
-    for (int ri = 0; ri < RI; ++ri) m[ri] = fmaxf(m[ri], __shfl_xor_sync(0xffffffffu, m[ri], o));
-  // pass B, in log2 units: u = z*k2 - c with c = fl(max*k2) (one FFMA; the rounding of c is a row constant
-  // and cancels in p = e/sum), e = 2^u (MUFU.EX2), row sum, and sum_c e*u for the entropy:
-  //   sum_c p ln p = ln2 * ( (sum_c e u) / sum - log2(sum) )
-  float sum[RI], set[RI];
-#pragma unroll
-  for (int ri = 0; ri < RI; ++ri) {
-    // jsp.special.logsumexp replaces a non-finite max by 0 (m is the max of the raw logits here)
-    const float ms = (fabsf(m[ri]) <= 3.4028234e38f) ? m[ri] : 0.0f;
-    cshift[ri] = ms * k2;
-    float psum[VEC], pset[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) psum[k] = pset[k] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        const float u = fmaf(z[ri][j][k], k2, -cshift[ri]);
-        const float ev = ex2_approx_ftz(u);
-        z[ri][j][k] = ev;
-        psum[k] += ev;
-        pset[k] = fmaf(ev, u, pset[k]);
-      }
-    }
-    sum[ri] = psum[0];
-    set[ri] = pset[0];
-#pragma unroll
-    for (int k = 1; k < VEC; ++k) {
-      sum[ri] += psum[k];
-      set[ri] += pset[k];
-    }
-  }
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1)
-#pragma unroll
-    for (int ri = 0; ri < RI; ++ri) sum[ri] += __shfl_xor_sync(0xffffffffu, sum[ri], o);
-  // pass C: p = e / sum, accumulate in sample order: sum p += e * inv, sum p^2 += (e*e) * inv^2 (two FFMA + one FMUL)
-#pragma unroll
-  for (int ri = 0; ri < RI; ++ri) {
-    const float inv = rcp_approx_ftz(sum[ri]);
-    const float inv2 = inv * inv;
-    l2sum[ri] = lg2_approx(sum[ri]);
-    spl = fmaf(inv, set[ri], spl);  // lane-partial of sum_c p u (log2 units); -log2(sum) is row-uniform
-    sum_l += l2sum[ri];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        const float e = z[ri][j][k];
-        sp[j][k] = fmaf(e, inv, sp[j][k]);
-        sp2[j][k] = fmaf(e * e, inv2, sp2[j][k]);
-      }
-    }
-  }
-}
 
 template <typename T, int G, int NV, int VEC, bool TAILONLY, int NW, int RI>
 __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kernel(const ClsArgs a) {
@@ -279,11 +105,12 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
     if (tile >= a.n_tiles) tile -= a.n_tiles;
     const int b = tile * TB + row;
     const bool valid_row = b < B;
-    float sp[NV][VEC], sp2[NV][VEC];
+    constexpr int NP = Pairs<VEC>::kN;
+    float2 sp[NV][NP], sp2[NV][NP];
 #pragma unroll
     for (int j = 0; j < NV; ++j)
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) sp[j][k] = sp2[j][k] = 0.0f;
+      for (int k = 0; k < NP; ++k) sp[j][k] = sp2[j][k] = make_float2(0.0f, 0.0f);
     float spl = 0.0f, sum_l = 0.0f;
     float lmax = -CUDART_INF_F, lsum = 0.0f;
     int y = -1;
@@ -343,8 +170,7 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
 
     // ------------------------------------------------------------------ tile epilogue
     const float Sf = (float)S;
-    const bool s_pow2 = (S & (S - 1)) == 0;  // x * (1/S) is then bit-identical to x / S
-    const float inv_Sf = 1.0f / Sf;
+    const DivS dS = make_divs(Sf);
     const float spl_row = 0.6931471805599453f * (group_sum<G>(spl) - sum_l);  // sum_s sum_c p ln p of this row
     if (a.partial_mode) {
       // shard mode: this rank's partial sums for row b go to the slot of the rank that owns the row after the
@@ -358,15 +184,12 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
         for (int j = 0; j < NV; ++j) {
           const int c0 = (g + G * j) * VEC;
           if (c0 < C) {
-            if (VEC == 4) {
-              *reinterpret_cast<float4*>(base + c0) = make_float4(sp[j][0], sp[j][1], sp[j][2], sp[j][3]);
-              *reinterpret_cast<float4*>(base + C + c0) = make_float4(sp2[j][0], sp2[j][1], sp2[j][2], sp2[j][3]);
+            if constexpr (VEC == 4) {
+              *reinterpret_cast<float4*>(base + c0) = make_float4(sp[j][0].x, sp[j][0].y, sp[j][1].x, sp[j][1].y);
+              *reinterpret_cast<float4*>(base + C + c0) = make_float4(sp2[j][0].x, sp2[j][0].y, sp2[j][1].x, sp2[j][1].y);
             } else {
-#pragma unroll
-              for (int k = 0; k < VEC; ++k) {
-                base[c0 + k] = sp[j][k];
-                base[C + c0 + k] = sp2[j][k];
-              }
+              base[c0] = sp[j][0].x;
+              base[C + c0] = sp2[j][0].x;
             }
           }
         }
@@ -392,16 +215,17 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
         float mean[VEC], av[VEC], ev[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-          mean[k] = s_pow2 ? sp[j][k] * inv_Sf : sp[j][k] / Sf;
+          const float spv = pk_get(sp, j, k), sp2v = pk_get(sp2, j, k);
+          mean[k] = div_s(spv, dS);
           if (want_brier) {
             msq = fmaf(mean[k], mean[k], msq);
             mean_y = (c0 + k == y) ? mean[k] : mean_y;
           }
-          const float spq = sp[j][k] - sp2[j][k];  // sum_s p(1-p)
-          av[k] = s_pow2 ? spq * inv_Sf : spq / Sf;
-          const float m2 = s_pow2 ? sp2[j][k] * inv_Sf : sp2[j][k] / Sf;
+          const float spq = spv - sp2v;  // sum_s p(1-p)
+          av[k] = div_s(spq, dS);
+          const float m2 = div_s(sp2v, dS);
           ev[k] = fmaxf(0.0f, __fsub_rn(m2, __fmul_rn(mean[k], mean[k])));
-          if (mean[k] > 0.0f) ent_terms = fmaf(mean[k], logf(mean[k]), ent_terms);
+          if (mean[k] > 0.0f) ent_terms = fmaf(mean[k], __logf(mean[k]), ent_terms);
           if (mean[k] > best_v) {
             best_v = mean[k];
             best_c = c0 + k;
@@ -987,17 +811,6 @@ __global__ void __launch_bounds__(256) reg_sample_targets_kernel(const float* __
   }
 }
 
-static int sm_count() {
-  static int cached[64] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-  if (cached[dev] == 0) {
-    int n = 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    cached[dev] = n;
-  }
-  return cached[dev];
-}
 
 template <typename T, int G, int NV, int VEC, bool TAILONLY, int NW, int RI>
 static int launch_cls_cfg(ClsArgs a, cudaStream_t st) {
@@ -1041,6 +854,12 @@ static int launch_cls_cfg(ClsArgs a, cudaStream_t st) {
 template <typename T, int G, int NV, int VEC, bool TAILONLY>
 static int launch_cls(const ClsArgs& a, cudaStream_t st) {
   if constexpr (NV * VEC >= 20) {
+    static const int cfg = [] {
+      const char* e = getenv("FB200_K3_CFG");  // experiment knob: 1 = 16 warps x 1 sample, 2 = 8 x 2
+      return e ? atoi(e) : 0;
+    }();
+    if (cfg == 1) return launch_cls_cfg<T, G, NV, VEC, TAILONLY, 16, 1>(a, st);
+    if (cfg == 2) return launch_cls_cfg<T, G, NV, VEC, TAILONLY, 8, 2>(a, st);
     return launch_cls_cfg<T, G, NV, VEC, TAILONLY, 12, 2>(a, st);
   } else {
     return launch_cls_cfg<T, G, NV, VEC, TAILONLY, 16, 2>(a, st);
@@ -1089,6 +908,25 @@ static int dispatch_cls(const ClsArgs& a, cudaStream_t st) {
 
 using namespace fb200;
 
+// Wide rows (128 < C <= 1024) have two kernels: the tiled one (default: a CTA-wide ring fed by a producer warp; 2.55 ms at
+// c4, HBM-bound) and the warp-autonomous one of bma_reduce_rows.cu (2.66 ms; it exists for the fused conformal-set
+// epilogue, fb200_bma_reduce_cls_sets(..., fuse = 1)).  FB200_K3_ROWS=1 in the environment, or
+// fb200_debug_force_tiled(0), selects the warp-autonomous kernel for plain reductions too - for A/B measurements and for
+// the tests that hold the two designs bit-identical.
+static int g_force_tiled = -1;
+static bool k3_force_tiled() {
+  if (g_force_tiled < 0) {
+    const char* e = getenv("FB200_K3_ROWS");
+    g_force_tiled = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_force_tiled == 1;
+}
+extern "C" int fb200_debug_force_tiled(int on) {
+  const int prev = k3_force_tiled() ? 1 : 0;
+  if (on >= 0) g_force_tiled = on ? 1 : 0;
+  return prev;
+}
+
 static int reduce_cls_common(ClsArgs& a, const void* logits, int dtype, const float* log_temp,
                              const int32_t* targets, int S, int B, int C, void* stream) {
   if (!logits) return FB200_E_NULL;
@@ -1112,6 +950,8 @@ static int reduce_cls_common(ClsArgs& a, const void* logits, int dtype, const fl
     if (dtype == FB200_F32) return launch_cls_narrow<float>(a, (cudaStream_t)stream);
     return launch_cls_narrow<__nv_bfloat16>(a, (cudaStream_t)stream);
   }
+  // wide rows: the warp-autonomous kernel
+  if (!k3_force_tiled() && cls_rows_supported(a, dtype)) return launch_cls_rows(a, dtype, (cudaStream_t)stream);
   if (dtype == FB200_F32) return dispatch_cls<float>(a, (cudaStream_t)stream);
   return dispatch_cls<__nv_bfloat16>(a, (cudaStream_t)stream);
 }
@@ -1123,6 +963,60 @@ extern "C" int fb200_bma_reduce_cls(const void* logits, int dtype, const float* 
   a.out = *out;
   if ((a.out.log_prob || a.out.ensemble_log_prob || a.out.brier_terms) && !targets) return FB200_E_NULL;
   return reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
+}
+
+namespace fb200 {
+int aps_sets_for_rows(const float* probs, int B, int C, const float* val_sorted, int q_index, int all_true, int all_false,
+                      uint8_t* mask, int32_t* sizes, const int32_t* row_list, const int32_t* row_count, int max_ctas,
+                      cudaStream_t st);
+long long conformal_rank_bound_host(float threshold, int n_val);
+}  // namespace fb200
+
+extern "C" size_t fb200_bma_reduce_cls_sets_workspace_bytes(int B) { return B > 0 ? ((size_t)B + 4) * sizeof(int32_t) : 0; }
+
+extern "C" int fb200_bma_reduce_cls_sets(const void* logits, int dtype, const float* log_temp, const int32_t* targets,
+                                         int S, int B, int C, const fb200_cls_outputs_t* out,
+                                         const float* val_scores_sorted, int n_val, float threshold, uint8_t* mask,
+                                         int32_t* sizes, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!out || !val_scores_sorted || !mask || !out->mean) return FB200_E_NULL;
+  if (n_val <= 0) return FB200_E_SHAPE;
+  ClsArgs a{};
+  a.out = *out;
+  if ((a.out.log_prob || a.out.ensemble_log_prob || a.out.brier_terms) && !targets) return FB200_E_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long K = conformal_rank_bound_host(threshold, n_val);
+  const int all_true = K >= n_val, all_false = K < 0;
+  const int q_index = (all_true || all_false) ? 0 : (int)(n_val - 1 - K);
+  a.logits = logits;
+  a.C = C;
+  a.cs_mask = mask;
+  const bool fused = logits && C > 0 && (dtype == FB200_F32 || dtype == FB200_BF16) && !k3_force_tiled() &&
+                     cls_rows_supported(a, dtype);
+  if (!fused) {
+    // rows the in-register epilogue does not cover (narrow or ragged heads): reduction, then the scoring kernel
+    a.cs_mask = nullptr;
+    const int rc = reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
+    if (rc != 0) return rc;
+    return fb200_aps_conformal_sets(out->mean, B, C, val_scores_sorted, n_val, threshold, nullptr, mask, sizes, stream);
+  }
+  if (!workspace) return FB200_E_NULL;
+  if (workspace_bytes < fb200_bma_reduce_cls_sets_workspace_bytes(B)) return FB200_E_WORKSPACE;
+  int32_t* ws = reinterpret_cast<int32_t*>(workspace);
+  cudaError_t e = cudaMemsetAsync(ws, 0, 4 * sizeof(int32_t), st);
+  if (e != cudaSuccess) return (int)e;
+  a.cs_sizes = sizes;
+  a.cs_val_sorted = val_scores_sorted;
+  a.cs_q_index = q_index;
+  a.cs_all_true = all_true;
+  a.cs_all_false = all_false;
+  a.fb_count = ws;
+  a.fb_rows = ws + 4;
+  const int rc = reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
+  if (rc != 0) return rc;
+  if (all_true || all_false) return 0;
+  // general path for the listed rows (usually none or a handful: a few CTAs find the list empty and exit)
+  return aps_sets_for_rows(out->mean, B, C, val_scores_sorted, q_index, all_true, all_false, mask, sizes, ws + 4, ws,
+                           2 * sm_count(), st);
 }
 
 extern "C" size_t fb200_bma_reduce_cls_wide_workspace_bytes(int S, int B) {

@@ -11,18 +11,9 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "row_sort.cuh"
 
 namespace fb200 {
-
-// Monotone float32 -> uint32 map (total order; -0 is canonicalised to +0 by the caller).
-__device__ __forceinline__ uint32_t f32_ordered(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float f32_unordered(uint32_t o) {
-  const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
-  return __uint_as_float(u);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Per-row descending sort + sequential inclusive prefix sum (APS scores, credible sets).
@@ -43,6 +34,11 @@ struct RowSortArgs {
   const float* cs_val_sorted;
   int cs_q_index;          // n_val - 1 - K
   int cs_all_true, cs_all_false;
+  // optional row list (key-only kernel, all-class mode): process rows row_list[0 .. *row_count) instead of 0 .. B-1 -
+  // the rows the fused epilogue of the reduction kernel (bma_reduce_rows.cu) left to the general path
+  const int32_t* row_list;
+  const int32_t* row_count;
+  int max_ctas;  // 0 = default grid
 };
 
 __global__ void __launch_bounds__(256) row_sort_cumsum_kernel(const RowSortArgs a) {
@@ -199,59 +195,6 @@ __device__ __forceinline__ void warp_bitonic_sort(u64 (&key)[NR], int lane) {
   }
 }
 
-// Inclusive scan of one value per lane in jax.lax.associative_scan's association order (see above).
-__device__ __forceinline__ float warp_tree_scan(float t, int lane) {
-  float w = t;
-#pragma unroll
-  for (int s = 1; s < 32; s <<= 1) {  // up-sweep: the right child of each pair becomes the pair's sum
-    const float o = __shfl_up_sync(0xffffffffu, w, s);
-    if ((lane & (2 * s - 1)) == 2 * s - 1) w = o + w;
-  }
-  float out = w;
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {  // down-sweep: even elements of a level add the prefix ending just before them
-    const float o = __shfl_up_sync(0xffffffffu, out, s);
-    if ((lane & (2 * s - 1)) == s - 1 && lane >= 3 * s - 1) out = o + out;
-  }
-  return out;
-}
-
-// x[NR] (rank order inside the lane's block) -> inclusive prefix sums over the whole warp-row, tree order.
-__host__ __device__ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
-// level l of the in-lane tree has NR >> l entries and starts at offset 2*NR - (2*NR >> l)
-template <int NR>
-__host__ __device__ constexpr int lvl_off(int l) { return 2 * NR - ((2 * NR) >> l); }
-
-template <int NR>
-__device__ __forceinline__ void warp_row_tree_prefix(float (&x)[NR], int lane) {
-  constexpr int LOG = ilog2_c(NR);
-  float u[2 * NR];
-#pragma unroll
-  for (int r = 0; r < NR; ++r) u[r] = x[r];
-#pragma unroll
-  for (int l = 0; l < LOG; ++l) {
-#pragma unroll
-    for (int i = 0; i < (NR >> (l + 1)); ++i)
-      u[lvl_off<NR>(l + 1) + i] = u[lvl_off<NR>(l) + 2 * i] + u[lvl_off<NR>(l) + 2 * i + 1];
-  }
-  const float incl = warp_tree_scan(u[lvl_off<NR>(LOG)], lane);
-  const float carry = __shfl_up_sync(0xffffffffu, incl, 1);  // prefix through the previous lane's block
-  const bool has_carry = lane > 0;
-  float o[2 * NR];
-  o[lvl_off<NR>(LOG)] = incl;
-#pragma unroll
-  for (int l = LOG - 1; l >= 0; --l) {
-#pragma unroll
-    for (int i = 0; i < (NR >> (l + 1)); ++i) {
-      o[lvl_off<NR>(l) + 2 * i + 1] = o[lvl_off<NR>(l + 1) + i];
-      if (i == 0) o[lvl_off<NR>(l)] = has_carry ? carry + u[lvl_off<NR>(l)] : u[lvl_off<NR>(l)];
-      else o[lvl_off<NR>(l) + 2 * i] = o[lvl_off<NR>(l + 1) + i - 1] + u[lvl_off<NR>(l) + 2 * i];
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < NR; ++r) x[r] = o[r];
-}
-
 constexpr int kSortWarps = 8;
 
 template <int NR, int MODE>  // MODE 0: all-class scores (+perm); 1: target score; 2: credible sets (+perm)
@@ -358,60 +301,6 @@ static int launch_row_sort_warp(const RowSortArgs& a, cudaStream_t st) {
 // (match_any per register slot, classes visited from high to low, one running counter per group of equal keys).
 // Prefix sums are taken over the sorted values exactly as in the 64-bit kernel, so the outputs are the same bits.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ce_min_first(uint32_t& a, uint32_t& b) {
-  const uint32_t lo = min(a, b);
-  const uint32_t hi = max(a, b);
-  a = lo;
-  b = hi;
-}
-
-// The network in two parts.  Merge levels that stay inside a lane (k < NR) are straight-line code on static
-// register indices.  From k = NR on, every level is: complement the lane's keys if its block changes direction, the
-// cross-lane stages (one shuffle + one predicated min/max per key; the lane mask is a loop variable), then the same
-// in-lane merge j = NR/2..1 for every k - so these levels are ONE rolled loop body.  Fully unrolled, the kernel was
-// 90 KB of straight-line code and stalled on instruction fetch more than on anything else (icache hit rate 61 %).
-template <int NR>
-__device__ __forceinline__ void warp_bitonic_sort32(uint32_t (&key)[NR], int lane) {
-  constexpr int N = 32 * NR;
-#pragma unroll
-  for (int k = 2; k < NR; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        if ((r & j) == 0) {
-          if ((r & k) == 0) ce_min_first(key[r], key[r | j]);
-          else ce_min_first(key[r | j], key[r]);
-        }
-      }
-    }
-  }
-  uint32_t flipped = 0u;  // all-ones while the lane's keys are stored complemented
-#pragma unroll 1
-  for (int kl = 1; kl <= 32; kl <<= 1) {  // k = kl * NR
-    const uint32_t want = (kl < 32 && (lane & kl) != 0) ? 0xFFFFFFFFu : 0u;
-    const uint32_t x = want ^ flipped;
-    flipped = want;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) key[r] ^= x;
-#pragma unroll 1
-    for (int lmask = kl >> 1; lmask > 0; lmask >>= 1) {
-      const bool upper = (lane & lmask) != 0;  // the upper lane of a pair keeps the larger key
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const uint32_t other = __shfl_xor_sync(0xffffffffu, key[r], lmask);
-        key[r] = upper ? max(key[r], other) : min(key[r], other);
-      }
-    }
-#pragma unroll
-    for (int j = NR >> 1; j > 0; j >>= 1) {
-#pragma unroll
-      for (int r = 0; r < NR; ++r)
-        if ((r & j) == 0) ce_min_first(key[r], key[r | j]);
-    }
-  }
-}
-
 template <int NR>
 __host__ __device__ constexpr int sort32_pad() { return 32 * NR + NR; }  // slot i at i + (i >> 5)
 // shared-memory words per warp: raw row [32 NR] (+ sorted keys and prefix sums, padded), 16-byte granular so that
@@ -469,9 +358,12 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
   int* scnt = reinterpret_cast<int*>(skey);  // tie pass only; the sorted keys are dead by then
   const bool vec16 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.probs) & 15) == 0);
   const int nwarps = gridDim.x * kSortWarps;
-  int b = blockIdx.x * kSortWarps + warp_in_cta;
-  if (b < a.B) row_prefetch<NR>(srow, a.probs + (size_t)b * C, C, lane, vec16);
-  for (; b < a.B; b += nwarps) {
+  const int n_rows = (MODE == 0 && a.row_count) ? min(*a.row_count, a.B) : a.B;
+  auto row_at = [&](int i) { return (MODE == 0 && a.row_list) ? a.row_list[i] : i; };
+  int bi = blockIdx.x * kSortWarps + warp_in_cta;
+  if (bi < n_rows) row_prefetch<NR>(srow, a.probs + (size_t)row_at(bi) * C, C, lane, vec16);
+  for (; bi < n_rows; bi += nwarps) {
+    const int b = row_at(bi);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     uint32_t own[NR], key[NR];
@@ -497,7 +389,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
         tpos = cnt;
       }
       __syncwarp();
-      if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
+      if (bi + nwarps < n_rows) row_prefetch<NR>(srow, a.probs + (size_t)row_at(bi + nwarps) * C, C, lane, vec16);
     }
     warp_bitonic_sort32<NR>(key, lane);
     float x[NR];
@@ -558,7 +450,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
           }
           if (lane == 0 && a.cs_sizes) a.cs_sizes[b] = n_true;
           __syncwarp();
-          if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
+          if (bi + nwarps < n_rows) row_prefetch<NR>(srow, a.probs + (size_t)row_at(bi + nwarps) * C, C, lane, vec16);
           done = true;
         }
       }
@@ -578,7 +470,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
         asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(ad), "f"(x[r]), "n"(PAD * 4) : "memory");
       }
       __syncwarp();
-      if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
+      if (bi + nwarps < n_rows) row_prefetch<NR>(srow, a.probs + (size_t)row_at(bi + nwarps) * C, C, lane, vec16);
       // lower bound, kept as the shared-space BYTE address of the slot so that a probe is one LDS with an
       // immediate offset, one compare and one predicated add
       uint32_t ap[NR];
@@ -647,6 +539,7 @@ static int launch_row_sort32_warp(const RowSortArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)kSortWarps * words * sizeof(uint32_t);
   int grid = (a.B + kSortWarps - 1) / kSortWarps;
   if (grid > 148 * 16) grid = 148 * 16;
+  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
   if (mode == 0) {
     auto kern = row_sort32_warp_kernel<NR, 0>;
     if (smem > 48 * 1024) {
@@ -1309,6 +1202,31 @@ extern "C" int fb200_aps_conformal_sets(const float* probs, int B, int C, const 
   a.cs_q_index = (a.cs_all_true || a.cs_all_false) ? 0 : (int)(n_val - 1 - K);
   return launch_row_sort(a, (cudaStream_t)stream);
 }
+
+// The fused reduction epilogue's general path: APS sets of the listed rows of `probs` (bma_reduce.cu calls this on the
+// rows its in-register threshold test could not decide: equal probabilities or a non-monotone boundary).
+namespace fb200 {
+int aps_sets_for_rows(const float* probs, int B, int C, const float* val_sorted, int q_index, int all_true, int all_false,
+                      uint8_t* mask, int32_t* sizes, const int32_t* row_list, const int32_t* row_count, int max_ctas,
+                      cudaStream_t st) {
+  RowSortArgs a{};
+  a.probs = probs;
+  a.B = B;
+  a.C = C;
+  a.set_threshold = INFINITY;
+  a.cs_mask = mask;
+  a.cs_sizes = sizes;
+  a.cs_val_sorted = val_sorted;
+  a.cs_q_index = q_index;
+  a.cs_all_true = all_true;
+  a.cs_all_false = all_false;
+  a.row_list = row_list;
+  a.row_count = row_count;
+  a.max_ctas = max_ctas;
+  return launch_row_sort(a, st);
+}
+long long conformal_rank_bound_host(float threshold, int n_val) { return conformal_rank_bound(threshold, n_val); }
+}  // namespace fb200
 
 extern "C" int fb200_conformal_sets(const float* val_scores_sorted, int n_val, const float* test_scores, int B,
                                     int C, float threshold, uint8_t* mask, int32_t* sizes, void* stream) {

@@ -195,6 +195,29 @@ def dp_elem_range(n: int, world: int, rank: int):
     return min(rank * per, int(n)), min((rank + 1) * per, int(n))
 
 
+def dp_owned_elem_ranges(lens, offsets, tile_range, tile_pairs=_lib.TILE_PAIRS):
+    """Flat element ranges [(begin, end), ...] a rank owns under the TILE split of the data-parallel step: tile t of a
+    leaf of length n covers the counter pairs [1024 t, 1024 (t + 1)) of that leaf, i.e. the elements i and i + ceil(n/2)
+    of those pairs (jax's threefry layout, see csrc/sgmcmc.cu) - so a contiguous range of tiles is whole leaves plus, at
+    its two ends, a lower-half and an upper-half piece of a partially owned leaf.  Adjacent ranges are merged."""
+    t0, t1 = tile_range
+    out, base = [], 0
+    for n, off in zip(lens, offsets):
+        h = (int(n) + 1) // 2
+        nt = (h + tile_pairs - 1) // tile_pairs
+        a, b = max(t0, base), min(t1, base + nt)
+        if a < b:
+            p0, p1 = (a - base) * tile_pairs, min((b - base) * tile_pairs, h)
+            for lo, hi in ((off + p0, off + p1), (off + h + p0, off + min(h + p1, int(n)))):
+                if hi > lo:
+                    if out and out[-1][1] == lo:
+                        out[-1] = (out[-1][0], hi)
+                    else:
+                        out.append((lo, hi))
+        base += nt
+    return out
+
+
 def _dp_peers(grad_ptrs, param_ptrs, rank, mc_grad_ptr=0, mc_param_ptr=0):
     world = len(grad_ptrs)
     peers = _lib.DpPeers()
@@ -436,6 +459,37 @@ def bma_reduce_cls(logits, want, targets=None, log_temp=None, out=None):
         "fb200_bma_reduce_cls",
     )
     return outs
+
+
+def bma_reduce_cls_sets(logits, want, val_sorted, threshold, targets=None, log_temp=None, out=None, mask=None, sizes=None,
+                        workspace=None):
+    """The single-pass reductions plus the APS conformal sets of the mean row in one call (fb200_bma_reduce_cls_sets):
+    returns (outs, mask uint8 [B,C], sizes int32 [B]).  `want` must contain "mean"."""
+    S, B, Cn = logits.shape
+    if Cn > 1024:
+        outs = bma_reduce_cls(logits, want, targets=targets, log_temp=log_temp, out=out)
+        m, sz = conformal_sets(val_sorted, aps_scores(outs["mean"], None), threshold)
+        return outs, m, sz
+    outs = out if out is not None else _alloc_cls_outputs(tuple(want), S, B, Cn, logits.device)
+    if "mean" not in outs:
+        raise ValueError("the fused conformal sets are those of the mean: request it")
+    st = _cls_struct(outs)
+    if mask is None:
+        mask = torch.empty((B, Cn), dtype=torch.uint8, device=logits.device)
+    if sizes is None:
+        sizes = torch.empty(B, dtype=torch.int32, device=logits.device)
+    nbytes = int(lib().fb200_bma_reduce_cls_sets_workspace_bytes(B))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=logits.device)
+    check(
+        lib().fb200_bma_reduce_cls_sets(
+            _ptr(logits, (torch.float32, torch.bfloat16)), _DT[logits.dtype], _ptr(log_temp, torch.float32, True),
+            _ptr(targets, torch.int32, True), S, B, Cn, C.byref(st), _ptr(val_sorted, torch.float32), val_sorted.numel(),
+            float(np.float32(threshold)), _ptr(mask, torch.uint8), _ptr(sizes, torch.int32), _ptr(workspace), nbytes, _stream(),
+        ),
+        "fb200_bma_reduce_cls_sets",
+    )
+    return outs, mask, sizes
 
 
 def cls_slot_row_floats(Cn):

@@ -88,11 +88,33 @@ def cyclical_sgld_integrator(
             return updates, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner)
         return _explore(gradient, state, None)
 
+    def _sync_precond(state, dp, scheme):
+        """Data-parallel RMSprop: the two phases split the elements differently over the ranks and the moment estimates
+        are rank-local, so on a phase change the pieces advanced under the previous split are gathered first - the new
+        owner of an element must see every update its estimate has had (the reference's replicas all hold the whole
+        state, fortuna/training/trainer.py:807)."""
+        v = precond_buffer(state.sgld_state.preconditioner_state)
+        last = ws.get("v_scheme")
+        if dp is not None and v is not None and last is not None and last != scheme:
+            dp.gather_owned(v.flat, last, v.lens, v.offsets)
+        ws["v_scheme"] = scheme if dp is not None else None
+
     def apply_fn(params: FlatTree, gradient, state, joint=None, dp=None):
-        if is_sampling_phase(state.sgld_state.count, cycle_length, exploration_ratio):
+        sampling = is_sampling_phase(state.sgld_state.count, cycle_length, exploration_ratio)
+        _sync_precond(state, dp, "tiles" if sampling else "elems")
+        if sampling:
             _, inner = sgld.apply(params, gradient, state.sgld_state, joint=joint, dp=dp)
             return params, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner)
         _, new_state = _explore(gradient, state, params, joint=joint, dp=dp)
         return params, new_state
 
-    return GradientTransformation(init_fn, update_fn, apply_fn)
+    def dp_gather(state, dp):
+        inner = state.sgld_state
+        m = inner.momentum
+        dp.gather_owned(m.flat, "tiles", m.lens, m.offsets)  # only the sampling phase advances the momentum
+        v = precond_buffer(inner.preconditioner_state)
+        if v is not None and ws.get("v_scheme") is not None:
+            dp.gather_owned(v.flat, ws["v_scheme"], v.lens, v.offsets)
+            ws["v_scheme"] = None  # whole on every rank: the next phase may split it either way
+
+    return GradientTransformation(init_fn, update_fn, apply_fn, dp_gather)

@@ -48,6 +48,30 @@ class PeerReplicas:
         self.multicast = bool(multicast and world > 1 and mcp and mcg)
         self.mc_param_ptr, self.mc_grad_ptr = (mcp, mcg) if self.multicast else (0, 0)
 
+    # ------------------------------------------------------------------ per-element sampler state across the ranks
+    # Momentum and the RMSprop moments are rank-local: only an element's OWNER ever advances them.  The sampling step splits
+    # the work by TILES (ops.dp_tile_range), the exploration step of cyclical SGLD by contiguous ELEMENT ranges
+    # (ops.dp_elem_range) - different owners for most elements.  Whenever the state has to be whole (the phase of cyclical
+    # SGLD changes, a chain checkpoint is written) the owned pieces are gathered: everything a rank does not own under
+    # `scheme` is zeroed and one all-reduce (sum) leaves the complete vector on every rank.
+    def owned_ranges(self, scheme: str, lens, offsets):
+        n = self.params.numel()
+        if scheme == "elems":
+            return [ops.dp_elem_range(n, self.world, self.rank)]
+        if scheme != "tiles":
+            raise ValueError(scheme)
+        n_tiles = sum((((int(k) + 1) // 2) + ops._lib.TILE_PAIRS - 1) // ops._lib.TILE_PAIRS for k in lens)
+        return ops.dp_owned_elem_ranges(lens, offsets, ops.dp_tile_range(n_tiles, self.world, self.rank))
+
+    def gather_owned(self, vec: torch.Tensor, scheme: str, lens, offsets, group=None) -> torch.Tensor:
+        """In place: ``vec`` becomes the concatenation of every rank's owned pieces under ``scheme``."""
+        keep = torch.zeros_like(vec)
+        for lo, hi in self.owned_ranges(scheme, lens, offsets):
+            keep[lo:hi] = vec[lo:hi]
+        dist.all_reduce(keep, op=dist.ReduceOp.SUM, group=group)
+        vec.copy_(keep)
+        return vec
+
     def step(self, momentum, precond_v, leaves, tiles, key_in, key_out, leaf_keys, hp, joint=None, tile_range=None):
         """barrier (all gradients written) -> fused step on the owned tiles -> barrier (all parameters landed)."""
         self._hg.barrier()

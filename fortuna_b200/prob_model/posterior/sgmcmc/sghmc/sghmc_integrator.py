@@ -40,6 +40,9 @@ class GradientTransformation(NamedTuple):
     init: Callable
     update: Callable
     apply: Callable  # fused update + apply_updates
+    # data-parallel only: dp_gather(opt_state, dp) makes the rank-local momentum / preconditioner moments whole on every
+    # rank (each rank advances only the elements it owns), e.g. before the chain state is written to a checkpoint
+    dp_gather: Optional[Callable] = None
 
 
 def _step(gradient, state, params, momentum_decay, momentum_resample_steps, step_schedule, preconditioner, ws,
@@ -131,4 +134,11 @@ def sghmc_integrator(
         )
         return params, new_state
 
-    return GradientTransformation(init_fn, update_fn, apply_fn)
+    def dp_gather(state, dp):
+        m = state.momentum
+        dp.gather_owned(m.flat, "tiles", m.lens, m.offsets)
+        v = precond_buffer(state.preconditioner_state)
+        if v is not None:
+            dp.gather_owned(v.flat, "tiles", v.lens, v.offsets)
+
+    return GradientTransformation(init_fn, update_fn, apply_fn, dp_gather)

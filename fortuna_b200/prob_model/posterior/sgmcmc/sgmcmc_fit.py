@@ -54,6 +54,17 @@ def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader,
     fuse = fuse_prior and hasattr(prior, "log_var")
     prec = math.exp(-prior.log_var) if fuse else None
     lp_const = -0.5 * bound.params.n_params * (math.log(2 * math.pi) + prior.log_var) if fuse else None
+    if dp is not None and save_chain is not None:
+        # every rank holds only its owned slice of the momentum / preconditioner moments: gather them, then ONE rank
+        # writes (all ranks writing `<dir>/c/checkpoint_tmp` and renaming it raced, and each file held mostly zeros)
+        write_chain = save_chain
+
+        def save_chain(st):  # noqa: F811
+            if tx.dp_gather is not None:
+                tx.dp_gather(st.opt_state, dp)
+            if dp.rank == 0:
+                write_chain(st)
+
     losses, val_losses = [], []
     for _ in range(n_epochs):
         epoch = []

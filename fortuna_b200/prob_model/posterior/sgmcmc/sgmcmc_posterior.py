@@ -111,8 +111,12 @@ class SGMCMCPosterior(WithRNG):
         """The repository the sampling callback fills (sghmc_posterior.py:151-156): written through to
         ``save_checkpoint_dir/<i>`` when a directory is configured."""
         c = fit_config.checkpointer
+        dp = getattr(self.bound, "dp", None)
+        # data-parallel fit: every rank fills its own device bank (the replicas are bit-identical), rank 0 alone writes
+        # the sample files
+        ckpt_dir = c.save_checkpoint_dir if (dp is None or dp.rank == 0) else None
         self.state = SGMCMCPosteriorStateRepository(
-            self.posterior_approximator.n_samples, template=self.bound.params, checkpoint_dir=c.save_checkpoint_dir,
+            self.posterior_approximator.n_samples, template=self.bound.params, checkpoint_dir=ckpt_dir,
             which_params=self._which_params(), state_name=self.STATE_NAME)
         self._last_layer = None
         return self.state

@@ -196,6 +196,29 @@ def sghmc_update(grad, state, momentum_decay, step_schedule, preconditioner, mom
     return updates, SGHMCState(state.count + 1, new_key, momentum, v)
 
 
+def sghmc_update_selected(grad_sel, mom_sel, v_sel, rng_key, count, n_leaves, momentum_decay, step_schedule,
+                          preconditioner):
+    """``sghmc_update`` restricted to some leaves of a large tree: ``grad_sel`` / ``mom_sel`` / ``v_sel`` are dicts
+    {leaf position in flatten order: array}; the key schedule is that of the WHOLE tree (``split(key, n_leaves)``,
+    fortuna/utils/random.py:11-14), the arithmetic per leaf is sghmc_integrator.py:59-92 unchanged.  Lets a parity
+    test step a 110 M-parameter tree on the GPU and check chosen leaves without drawing 110 M normals in numpy.
+    Returns (updates_sel, momentum_sel, v_sel, new_key)."""
+    step_size = F32(step_schedule(count))
+    v = preconditioner.update(grad_sel, v_sel)
+    keys = prng.split(np.asarray(rng_key, dtype=np.uint32))
+    key, new_key = keys[0], keys[1]
+    lk = leaf_keys(key, n_leaves)
+    noise = {i: prng.normal(lk[i], g.size).reshape(g.shape) for i, g in grad_sel.items()}
+    noise = preconditioner.m_sqrt(noise, v)
+    beta = F32(momentum_decay)
+    sqrt_eps = np.sqrt(step_size, dtype=F32)
+    noise_scale = np.sqrt(F32(2 * (1 - momentum_decay)), dtype=F32)
+    momentum = tree_map(lambda m, g, n: beta * m + g * sqrt_eps + n * noise_scale, mom_sel, grad_sel, noise)
+    updates = preconditioner.m_inv(momentum, v)
+    updates = tree_map(lambda m: m * sqrt_eps, updates)
+    return updates, momentum, v, new_key
+
+
 def apply_updates(params, updates):
     """optax.apply_updates as used by flax TrainState.apply_gradients: p + u."""
     return tree_map(lambda p, u: (p + u).astype(p.dtype), params, updates)

@@ -184,3 +184,61 @@ def test_fused_log_joint_gradient_matches_oracle(cuda, precond, kind):
     o_inner = o_state
     assert np.array_equal(ops.key_to_host(inner.rng_key), o_inner.rng_key)
     _assert_tree_close(inner.momentum.to_numpy_tree(), o_inner.momentum, "momentum")
+
+
+@pytest.mark.parametrize("precond", ["identity", "rmsprop"])
+def test_bert_base_tree_steps_match_oracle(cuda, precond):
+    """BASELINE config 5: the 110 M-parameter BERT-base-shaped tree the sampler benchmark is quoted on (201 leaves,
+    53 K tiles, flat offsets beyond 2^24, a 23.4 M-element embedding leaf whose half-offset is 11.7 M).  Two SGHMC steps
+    on the GPU; the key chain is compared bit for bit and four leaves - the embedding, one 768 x 3072 kernel, one bias and
+    the 2-element classifier bias - against oracle/sampler.py's arithmetic under the FULL tree's key schedule
+    (sghmc_integrator.py:59-92, utils/random.py:11-23), every element, rtol 1e-5."""
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+    from fortuna_b200.prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    params = FlatTree.from_shapes(trees.bert_base_shapes(), device=cuda)
+    gen = torch.Generator(device=cuda)
+    gen.manual_seed(3)
+    params.flat.normal_(0.0, 0.02, generator=gen)
+    n_leaves = len(params.lens)
+    assert params.n_params > 109_000_000 and max(params.lens) == 30522 * 768
+    want = {"embedding": params.lens.index(30522 * 768), "classifier_bias": params.lens.index(2),
+            "kernel": params.lens.index(768 * 3072), "bias": params.lens.index(3072)}
+    sel = sorted(set(want.values()))
+    assert any(params.offsets[i] > (1 << 24) for i in sel)
+
+    def leaf(ft, i):
+        o, n = ft.offsets[i], ft.lens[i]
+        return ft.flat[o : o + n].cpu().numpy().reshape(ft.shapes[i])
+
+    o_pre = osamp.Preconditioner(precond)
+    o_sched = osamp.constant_schedule(2e-5)
+    pre = pc.rmsprop_preconditioner() if precond == "rmsprop" else pc.identity_preconditioner()
+    tx = sghmc_integrator(0.01, None, ops.PRNGKey(11, cuda), sched.constant_schedule(2e-5), pre)
+    state = tx.init(params)
+    o_p = {i: leaf(params, i) for i in sel}
+    o_m = {i: np.zeros_like(o_p[i]) for i in sel}
+    o_v = {i: np.zeros_like(o_p[i]) for i in sel} if precond == "rmsprop" else None
+    o_key, o_count = oprng.PRNGKey(11), 0
+    grad = params.empty_like()
+    for step in range(2):
+        grad.flat.normal_(0.0, 0.5, generator=gen)
+        g_sel = {i: leaf(grad, i) for i in sel}
+        upd, o_m, o_v, o_key = osamp.sghmc_update_selected(g_sel, o_m, o_v, o_key, o_count, n_leaves, 0.01, o_sched, o_pre)
+        o_count += 1
+        o_p = {i: (o_p[i] + upd[i]).astype(np.float32) for i in sel}
+        params, state = tx.apply(params, grad, state)
+        assert np.array_equal(ops.key_to_host(state.rng_key), o_key), "rng_key chain must be bit-exact"
+        for name, i in want.items():
+            w = o_p[i]
+            np.testing.assert_allclose(leaf(params, i), w, rtol=1e-5, atol=1e-6 * float(np.max(np.abs(w))),
+                                       err_msg=f"params {name} step {step}")
+            wm = o_m[i]
+            np.testing.assert_allclose(leaf(state.momentum, i), wm, rtol=1e-5, atol=1e-6 * float(np.max(np.abs(wm))),
+                                       err_msg=f"momentum {name} step {step}")
+            if precond == "rmsprop":
+                np.testing.assert_allclose(leaf(state.preconditioner_state.grad_moment_estimates, i), o_v[i], rtol=1e-5,
+                                           err_msg=f"v {name} step {step}")

@@ -99,3 +99,30 @@ def test_sampling_callbacks_logic():
     assert sampler.count_collectable(do, 1, 11) == 3
     dc = lambda step, cnt: sampler.cyclical_sgld_do_sample(step, cnt, 3, 1, 4, 0.25)
     assert [s for s in range(1, 9) if dc(s, 0)] == [1, 2, 3, 5, 6, 7]
+
+
+def test_selected_leaves_step_equals_full_step():
+    """sghmc_update_selected (used by the 110 M-parameter GPU parity test) is sghmc_update on the chosen leaves."""
+    params = trees.ragged_tree(3)
+    flat = sampler.tree_flatten(params)
+    r = np.random.default_rng(0)
+    for kind in ("identity", "rmsprop"):
+        pre = sampler.Preconditioner(kind)
+        st = sampler.sghmc_init(params, prng.PRNGKey(7), pre)
+        sched = sampler.constant_schedule(1e-3)
+        for _ in range(2):
+            grad = sampler.tree_map(lambda p: (0.2 * r.standard_normal(p.shape)).astype(np.float32), params)
+            gflat = sampler.tree_flatten(grad)
+            sel = [0, 3, len(flat) - 1]
+            mflat = sampler.tree_flatten(st.momentum)
+            vflat = sampler.tree_flatten(st.precond) if st.precond is not None else None
+            upd_s, mom_s, v_s, new_key = sampler.sghmc_update_selected(
+                {i: gflat[i][1] for i in sel}, {i: mflat[i][1] for i in sel},
+                {i: vflat[i][1] for i in sel} if vflat else None, st.rng_key, st.count, len(flat), 0.01, sched, pre)
+            upd, st = sampler.sghmc_update(grad, st, 0.01, sched, pre)
+            uflat, m2 = sampler.tree_flatten(upd), sampler.tree_flatten(st.momentum)
+            assert np.array_equal(new_key, st.rng_key)
+            for i in sel:
+                assert np.array_equal(upd_s[i], uflat[i][1]) and np.array_equal(mom_s[i], m2[i][1])
+                if kind == "rmsprop":
+                    assert np.array_equal(v_s[i], sampler.tree_flatten(st.precond)[i][1])

@@ -137,8 +137,9 @@ SIGNATURES = {
     "fb200_bma_reduce_cls_wide_workspace_bytes": (_sz, [_i, _i]),
     "fb200_bma_reduce_cls_wide": (_i, [_P, _i, _P, _P, _i, _i, _i, C.POINTER(ClsOutputs), _P, _sz, _P]),
     "fb200_cls_slot_row_floats": (_sz, [_i]),
-    "fb200_bma_reduce_cls_shard": (_i, [_P, _i, _P, _P, _i, _i, _i, _i, _i, _P, _P]),
+    "fb200_bma_reduce_cls_shard": (_i, [_P, _i, _P, _P, _i, _i, _i, _i, _i, _P, _P, _P]),
     "fb200_bma_finalize_cls_slots": (_i, [_P, _i, _i, _i, _i, C.POINTER(ClsOutputs), _P]),
+    "fb200_variance_combine": (_i, [_P, _P, _i64, _P, _P, _P]),
     "fb200_bma_reduce_reg": (_i, [_P, _P, _P, _i, _i, _i, C.POINTER(RegOutputs), _P]),
     "fb200_aps_scores": (_i, [_P, _P, _i, _i, _P, _P, _P]),
     "fb200_simple_scores": (_i, [_P, _P, _i, _i, _P, _P]),
@@ -150,6 +151,8 @@ SIGNATURES = {
     "fb200_ece_bins": (_i, [_P, _i, _i, _P, _P, _P, _i, _P, _P, _P, _P, _P, _P]),
     "fb200_ece_bins_from_rows": (_i, [_P, _P, _P, _P, _i, _P, _i, _P, _P, _P, _P, _P, _P]),
     "fb200_ece_from_bins": (_i, [_P, _P, _P, _i, _i64, _P, _P]),
+    "fb200_ece_pack_bins": (_i, [_P, _P, _P, _i, _P, _i, _P]),
+    "fb200_ece_from_packed_bins": (_i, [_P, _i, _i64, _P, _P, _P]),
     "fb200_quantile_axis0": (_i, [_P, _i, _i64, _P, _i, _P, _P]),
     "fb200_calib_cls_workspace_bytes": (_sz, [_i, _i]),
     "fb200_calib_cls_loss_terms": (_i, [_P, _i, _P, _P, _i, _i, _i, _P, _sz, _P, _P]),

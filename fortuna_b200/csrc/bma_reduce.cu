@@ -1049,11 +1049,13 @@ extern "C" size_t fb200_cls_slot_row_floats(int C) { return C > 0 ? (size_t)(2 *
 
 extern "C" int fb200_bma_reduce_cls_shard(const void* logits, int dtype, const float* log_temp,
                                           const int32_t* targets, int S, int B, int C, int n_ranks, int rank,
-                                          const uint64_t* slot_ptrs, void* stream) {
+                                          const uint64_t* slot_ptrs, float* ensemble_log_prob, void* stream) {
   if (!slot_ptrs) return FB200_E_NULL;
+  if (ensemble_log_prob && !targets) return FB200_E_NULL;
   if (n_ranks <= 0 || B <= 0 || B % n_ranks != 0 || rank < 0 || rank >= n_ranks) return FB200_E_SHAPE;
   ClsArgs a{};
   a.partial_mode = 1;
+  a.out.ensemble_log_prob = ensemble_log_prob;
   a.slot_ptrs = reinterpret_cast<const unsigned long long*>(slot_ptrs);
   a.n_ranks = n_ranks;
   a.tile_rot = rank;  // turned into a tile index once the tile size is known (launch_cls_cfg)
@@ -1070,6 +1072,29 @@ extern "C" int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int r
   const int64_t threads = (int64_t)rows * 32;
   bma_finalize_slots_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       slots, n_src, rows, C, s_total, *out, logf((float)s_total));
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+// predictive.variance / predictive.std of the reference (fortuna/prob_model/predictive/base.py:838-944) combine an
+// aleatoric and an epistemic estimate that may come from DIFFERENT posterior draws: variance = a + e, std = sqrt(variance).
+__global__ void __launch_bounds__(256) variance_combine_kernel(const float* __restrict__ a, const float* __restrict__ e,
+                                                               int64_t n, float* __restrict__ var_out,
+                                                               float* __restrict__ std_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = e ? __fadd_rn(a[i], e[i]) : a[i];
+    if (var_out) var_out[i] = v;
+    if (std_out) std_out[i] = sqrtf(v);
+  }
+}
+
+extern "C" int fb200_variance_combine(const float* aleatoric, const float* epistemic, int64_t n, float* variance_out,
+                                      float* std_out, void* stream) {
+  if (!aleatoric || (!variance_out && !std_out)) return FB200_E_NULL;
+  if (n <= 0) return FB200_E_SHAPE;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  variance_combine_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(aleatoric, epistemic, n, variance_out, std_out);
   FB200_LAUNCH_CHECK();
   return 0;
 }

@@ -1021,6 +1021,38 @@ __global__ void ece_from_bins_kernel(const int32_t* __restrict__ counts, const f
   result[1] = mce;
 }
 
+// The three additive bin counters as ONE float64 vector [counts | correct | conf_sums] (3 n_bins): a B-sharded evaluation
+// all-reduces it in a single collective (int32 counts are exact in float64) and finalises from the packed sums.
+__global__ void ece_pack_bins_kernel(const int32_t* __restrict__ counts, const float* __restrict__ conf_sums,
+                                     const int32_t* __restrict__ correct, int n_bins, double* __restrict__ packed,
+                                     int accumulate) {
+  const int i = threadIdx.x;
+  if (i < n_bins) {
+    const double base0 = accumulate ? packed[i] : 0.0, base1 = accumulate ? packed[n_bins + i] : 0.0,
+                 base2 = accumulate ? packed[2 * n_bins + i] : 0.0;
+    packed[i] = base0 + (double)counts[i];
+    packed[n_bins + i] = base1 + (double)correct[i];
+    packed[2 * n_bins + i] = base2 + (double)conf_sums[i];
+  }
+}
+
+__global__ void ece_from_packed_kernel(const double* __restrict__ packed, int n_bins, float n_total,
+                                       int32_t* __restrict__ counts_out, float* __restrict__ result) {
+  float ece = 0.0f, mce = -CUDART_INF_F;
+  for (int i = 0; i < n_bins; ++i) {
+    const float cnt = (float)packed[i];
+    const bool any = packed[i] > 0.0;
+    const float acc = any ? (float)packed[n_bins + i] / cnt : 0.0f;
+    const float conf = any ? (float)packed[2 * n_bins + i] / cnt : 0.0f;
+    const float w = cnt * fabsf(acc - conf);
+    ece += w;
+    mce = fmaxf(mce, w);
+    if (counts_out) counts_out[i] = (int32_t)packed[i];
+  }
+  result[0] = ece / n_total;
+  result[1] = mce;
+}
+
 __global__ void quantile_sorted_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ q, int nq,
                                        float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1303,6 +1335,24 @@ extern "C" int fb200_ece_from_bins(const int32_t* counts, const float* conf_sums
   if (!counts || !conf_sums || !correct || !result) return FB200_E_NULL;
   if (n_bins <= 0 || n_total <= 0) return FB200_E_SHAPE;
   ece_from_bins_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counts, conf_sums, correct, n_bins, (float)n_total, result);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_ece_pack_bins(const int32_t* counts, const float* conf_sums, const int32_t* correct, int n_bins,
+                                   double* packed, int accumulate, void* stream) {
+  if (!counts || !conf_sums || !correct || !packed) return FB200_E_NULL;
+  if (n_bins <= 0 || n_bins > kMaxBins) return FB200_E_SHAPE;
+  ece_pack_bins_kernel<<<1, kMaxBins, 0, (cudaStream_t)stream>>>(counts, conf_sums, correct, n_bins, packed, accumulate);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int fb200_ece_from_packed_bins(const double* packed, int n_bins, int64_t n_total, int32_t* counts_out,
+                                          float* result, void* stream) {
+  if (!packed || !result) return FB200_E_NULL;
+  if (n_bins <= 0 || n_total <= 0) return FB200_E_SHAPE;
+  ece_from_packed_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(packed, n_bins, (float)n_total, counts_out, result);
   FB200_LAUNCH_CHECK();
   return 0;
 }

@@ -508,7 +508,7 @@ def slot_pointer_table(slot_tensors_or_ptrs, device):
     return torch.from_numpy(np.array(ptrs, dtype=np.uint64).view(np.int64).copy()).to(device)
 
 
-def bma_reduce_cls_shard(logits, slot_ptrs, targets=None, log_temp=None, rank=0):
+def bma_reduce_cls_shard(logits, slot_ptrs, targets=None, log_temp=None, rank=0, ensemble_log_prob=None):
     """Shard mode of the single-pass reduction: export this rank's partial sums row by row into the slot of the
     rank owning the row.  slot_ptrs: int64 device tensor [n_ranks] from slot_pointer_table."""
     S, B, Cn = logits.shape
@@ -524,6 +524,7 @@ def bma_reduce_cls_shard(logits, slot_ptrs, targets=None, log_temp=None, rank=0)
             slot_ptrs.numel(),
             int(rank),
             _ptr(slot_ptrs, torch.int64),
+            _ptr(ensemble_log_prob, torch.float32, True),
             _stream(),
         ),
         "fb200_bma_reduce_cls_shard",
@@ -540,6 +541,17 @@ def bma_finalize_cls_slots(slots, s_total, Cn, want, out=None):
         "fb200_bma_finalize_cls_slots",
     )
     return outs
+
+
+def variance_combine(aleatoric, epistemic=None, want_std=False):
+    """variance = aleatoric + epistemic (or `aleatoric` itself when epistemic is None), optionally its square root."""
+    out = torch.empty_like(aleatoric)
+    check(
+        lib().fb200_variance_combine(_ptr(aleatoric, torch.float32), _ptr(epistemic, torch.float32, True), aleatoric.numel(),
+                                     None if want_std else _ptr(out), _ptr(out) if want_std else None, _stream()),
+        "fb200_variance_combine",
+    )
+    return out
 
 
 def bma_reduce_reg(outputs, want, targets=None, log_temp=None):
@@ -721,6 +733,30 @@ def ece_from_bins(counts, conf_sums, correct, n_total):
         "fb200_ece_from_bins",
     )
     return out
+
+
+def ece_pack_bins(ece, out=None, accumulate=False):
+    """float64 [3 n_bins] = [counts | correct | conf_sums] of an ece_bins result: ONE all-reduce for a sharded evaluation;
+    ``accumulate`` adds to ``out`` (bins of a loader walked batch by batch)."""
+    nb = ece["counts"].numel()
+    if accumulate and out is None:
+        raise ValueError("accumulate needs the running `out`")
+    packed = out if out is not None else torch.empty(3 * nb, dtype=torch.float64, device=ece["counts"].device)
+    check(lib().fb200_ece_pack_bins(_ptr(ece["counts"], torch.int32), _ptr(ece["conf_sums"], torch.float32),
+                                    _ptr(ece["correct"], torch.int32), nb, _ptr(packed, torch.float64), int(bool(accumulate)),
+                                    _stream()),
+          "fb200_ece_pack_bins")
+    return packed
+
+
+def ece_from_packed_bins(packed, n_total, want_counts=False):
+    """(ECE, MCE) float32[2] (and the int32 bin counts) from the all-reduced packed counters."""
+    nb = packed.numel() // 3
+    out = torch.empty(2, dtype=torch.float32, device=packed.device)
+    counts = torch.empty(nb, dtype=torch.int32, device=packed.device) if want_counts else None
+    check(lib().fb200_ece_from_packed_bins(_ptr(packed, torch.float64), nb, int(n_total), _ptr(counts, torch.int32, True),
+                                           _ptr(out), _stream()), "fb200_ece_from_packed_bins")
+    return (out, counts) if want_counts else out
 
 
 def quantile_sorted(x_sorted, q):

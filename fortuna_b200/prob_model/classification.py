@@ -122,6 +122,29 @@ class ProbClassifier:
         self.posterior.load_state(checkpoint_path)
         self.predictive = self._predictive_cls(self.posterior, log_temp=self.posterior.log_temp)
 
+    def attach_posterior_samples(self, samples: torch.Tensor, freeze_fun=None, steps=None, last_layer_dtype=torch.float32,
+                                 logits_dtype=torch.float32) -> None:
+        """Make ``samples`` - float32 [n_samples, N_trainable], rows in the flat parameter layout of
+        ``utils.flat_tree`` over the leaves ``freeze_fun`` keeps trainable - the posterior of this model without running a
+        fit here: chains that ran elsewhere (one per GPU, another job), or the benchmark's random-init weights.  The
+        in-memory sibling of ``load_state`` (which reads the same rows from ``<dir>/<i>`` checkpoints).
+        ``last_layer_dtype`` / ``logits_dtype``: see ``ClassificationPredictive``."""
+        from .posterior.sgmcmc.sgmcmc_posterior_state_repository import SGMCMCPosteriorStateRepository
+
+        self.model.to(self.device)
+        bound = BoundModel(self.model, self.device, freeze_fun=freeze_fun)
+        n, width = samples.shape
+        if width != bound.params.flat.numel():
+            raise ValueError(f"samples have {width} parameters per row, the trainable tree has {bound.params.flat.numel()}")
+        cls = SGHMCPosterior if isinstance(self.posterior_approximator, SGHMCPosteriorApproximator) else CyclicalSGLDPosterior
+        self.posterior = cls(bound, self.prior, self.posterior_approximator, self.rng)
+        repo = SGMCMCPosteriorStateRepository(n, template=bound.params)
+        repo.bank.copy_(samples.to(device=self.device, dtype=torch.float32))
+        repo._filled = [True] * n
+        repo.steps = list(steps) if steps is not None else list(range(n))
+        self.posterior.state = repo
+        self.predictive = self._predictive_cls(self.posterior, last_layer_dtype=last_layer_dtype, logits_dtype=logits_dtype)
+
     def save_state(self, checkpoint_path, keep_top_n_checkpoints: int = 1) -> None:
         if self.posterior is None:
             raise ValueError("No state available.")

@@ -52,8 +52,34 @@ def aps_sets(mean: torch.Tensor, calib) -> Tuple[torch.Tensor, torch.Tensor]:
     return ops.conformal_sets(calib.val_sorted, ops.aps_scores(mean, None), calib.threshold)
 
 
+class PhaseTimer:
+    """CUDA events around the phases of a step, on the current stream (optional: the events cost ~2 us each)."""
+
+    def __init__(self):
+        self.marks = []  # [(name, event)] of the step being recorded
+        self.steps = []  # finished steps
+
+    def mark(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.marks.append((name, ev))
+
+    def end_step(self):
+        self.steps.append(self.marks)
+        self.marks = []
+
+    def summary_ms(self):
+        """Mean milliseconds per phase over the recorded steps (call after a synchronize)."""
+        acc = {}
+        for marks in self.steps:
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                acc.setdefault(n1, []).append(e0.elapsed_time(e1))
+        return {k: sum(v) / len(v) for k, v in acc.items()}
+
+
 class PredictivePipeline:
-    def __init__(self, S, B, C, device, want: Sequence[str], world: int = 1, rank: int = 0, transport: Optional[str] = None):
+    def __init__(self, S, B, C, device, want: Sequence[str], world: int = 1, rank: int = 0, transport: Optional[str] = None,
+                 fused_sets: bool = False):
         self.S, self.B, self.C = S, B, C
         self.device = device
         self.want = tuple(want)
@@ -66,6 +92,9 @@ class PredictivePipeline:
         self.scores = None
         self.thresholds = torch.from_numpy(ece_thresholds(B)).to(device)
         self.transport = "single"
+        self.timer: Optional[PhaseTimer] = None
+        self.fused_sets = bool(fused_sets) and world == 1 and C <= 1024
+        self._sets_ws = None
         if world > 1:
             from .sharded import PeerSlots, SampleShardExchange
 
@@ -75,8 +104,6 @@ class PredictivePipeline:
             if self.transport == "p2p":
                 try:
                     self.peer = PeerSlots(world, rank, self.B_local, rowf, device)
-                    self.recv = self.peer.recv
-                    self.slot_ptrs = ops.slot_pointer_table(self.peer.dest_ptrs, device)
                 except Exception as exc:  # no peer mapping on this system (no NVLink / symmetric memory): one all-to-all
                     import warnings
 
@@ -86,33 +113,58 @@ class PredictivePipeline:
                 self.send = ops.alloc_cls_slots(world, self.B_local, C, device)
                 self.recv = torch.empty_like(self.send)
                 self.slot_ptrs = ops.slot_pointer_table([self.send[o] for o in range(world)], device)
-        # reduce, sort + sets (fused), ece_bins, ece_finalize; sharded: + finalize_slots, ece_from_bins
-        fused_sets = C <= 1024
-        self.launches_per_step = (4 if world == 1 else 6) + (0 if fused_sets else 1)
+        # reduce, sort + sets (fused), ece_bins, ece_finalize; sharded: + finalize_slots, pack_bins, ece_from_packed
+        fused_sort = C <= 1024
+        self.launches_per_step = (4 if world == 1 else 7) + (0 if fused_sort else 1)
+
+    def _mark(self, name):
+        if self.timer is not None:
+            self.timer.mark(name)
 
     # -------------------------------------------------------------------------------- K3 / K4
-    def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor], kernel_events=None):
-        """kernel_events: optional (start, end) CUDA events recorded around the reduction kernel alone."""
+    def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor], kernel_events=None, calib=None):
+        """kernel_events: optional (start, end) CUDA events recorded around the reduction kernel alone.
+        calib: with ``fused_sets``, the conformal calibration whose APS sets the same launch emits."""
+        self._mark("begin")
         if kernel_events:
             kernel_events[0].record()
         if self.world == 1:
-            self.outs = ops.bma_reduce_cls(z, self._kernel_want if targets is not None else self.want, targets=targets,
-                                           out=self.outs or None)
+            want = self._kernel_want if targets is not None else self.want
+            if self.fused_sets and calib is not None:
+                if self._sets_ws is None:
+                    self.mask = torch.empty((self.B, self.C), dtype=torch.uint8, device=self.device)
+                    self.sizes = torch.empty(self.B, dtype=torch.int32, device=self.device)
+                    self._sets_ws = torch.empty(int(ops.lib().fb200_bma_reduce_cls_sets_workspace_bytes(self.B)),
+                                                dtype=torch.uint8, device=self.device)
+                self.outs, self.mask, self.sizes = ops.bma_reduce_cls_sets(
+                    z, want, calib.val_sorted, calib.threshold, targets=targets, out=self.outs or None, mask=self.mask,
+                    sizes=self.sizes, workspace=self._sets_ws)
+            else:
+                self.outs = ops.bma_reduce_cls(z, want, targets=targets, out=self.outs or None)
             if kernel_events:
                 kernel_events[1].record()
+            self._mark("reduce")
             return self.outs
-        ops.bma_reduce_cls_shard(z, self.slot_ptrs, targets=targets, rank=self.rank)
+        if self.transport == "p2p":
+            par = self.peer.step & 1
+            self.peer.step += 1
+            ops.bma_reduce_cls_shard(z, self.peer.slot_table(parity=par), targets=targets, rank=self.rank)
+        else:
+            ops.bma_reduce_cls_shard(z, self.slot_ptrs, targets=targets, rank=self.rank)
         if kernel_events:
             kernel_events[1].record()
+        self._mark("reduce")
         # the one exchange step of the S-sharded path: every rank ends up with all ranks' partials for its B/N rows
         if self.transport == "p2p":
             self.peer.barrier()  # the kernel's epilogue already stored into the owners' buffers over NVLink
+            recv = self.peer.recv_view(parity=par)
         else:
             self.exchange.exchange_slots(self.send, self.recv)
+            recv = self.recv
+        self._mark("exchange")
         want = [w for w in self.want if w != "ensemble_log_prob"]
-        self.outs = ops.bma_finalize_cls_slots(self.recv, self.S * self.world, self.C, want, out=self.outs or None)
-        if self.transport == "p2p":
-            self.peer.barrier()  # nobody overwrites a receive buffer that is still being read
+        self.outs = ops.bma_finalize_cls_slots(recv, self.S * self.world, self.C, want, out=self.outs or None)
+        self._mark("finalize")
         return self.outs
 
     # -------------------------------------------------------------------------------- K5 / K6 / K7
@@ -120,16 +172,22 @@ class PredictivePipeline:
         mean = self.outs["mean"]
         lo, hi = self.rank * self.B_local, (self.rank + 1) * self.B_local
         t_local = targets[lo:hi] if self.world > 1 else targets
-        self.mask, self.sizes = aps_sets(mean, calib)
+        if not (self.fused_sets and self._sets_ws is not None):
+            self.mask, self.sizes = aps_sets(mean, calib)
+        self._mark("sets")
         if self.world == 1 and "confidence" in self.outs:
             # the reduction kernel's epilogue already holds max_c mean, its arg-max and the Brier term of every row
             self.ece = ops.ece_bins_from_rows(self.outs["confidence"], self.outs["mode"], t_local, self.thresholds,
                                               brier_terms=self.outs.get("brier_terms"))
         else:
             self.ece = ops.ece_bins(mean, t_local, self.thresholds)
+        self._mark("ece")
         if self.world > 1:
             self.exchange.allreduce_bins(self.ece)
-            self.ece["result_global"] = ops.ece_from_bins(self.ece["counts"], self.ece["conf_sums"], self.ece["correct"], self.B)
+            self.ece["result_global"], self.ece["counts_global"] = ops.ece_from_packed_bins(self.ece["packed"], self.B, True)
+            self._mark("ece_allreduce")
+        if self.timer is not None:
+            self.timer.end_step()
         return self.mask, self.sizes, self.ece
 
 

@@ -46,6 +46,14 @@ class SampleShardExchange:
         return recv
 
     def allreduce_bins(self, ece: Dict[str, torch.Tensor]):
+        """Sum the additive ECE counters over the ranks.  On the GPU: ONE collective over the packed float64 vector
+        (fb200_ece_pack_bins), which ``ece["packed"]`` then holds; CPU tensors (the gloo tests): one per counter."""
+        if ece["counts"].is_cuda:
+            from ... import ops
+
+            ece["packed"] = ops.ece_pack_bins(ece, out=ece.get("packed"))
+            dist.all_reduce(ece["packed"], op=dist.ReduceOp.SUM, group=self.group)
+            return ece
         for n in ("counts", "correct", "conf_sums"):
             dist.all_reduce(ece[n], op=dist.ReduceOp.SUM, group=self.group)
         return ece
@@ -53,18 +61,50 @@ class SampleShardExchange:
 
 class PeerSlots:
     """Receive buffers mapped into every rank's address space (torch.distributed._symmetric_memory): rank r's
-    reduction kernel stores its partials for rows owned by rank o straight into ``recv_o[r]`` over NVLink."""
+    reduction kernel stores its partials for rows owned by rank o straight into ``recv_o[r]`` over NVLink.
+
+    TWO receive buffers, used alternately: step i stores into buffer i & 1, so ONE barrier per step is enough - it makes
+    step i's peer stores visible before the finalisation reads them, and, because every rank reaches the barrier of step
+    i + 1 only after its own finalisation of step i (stream order), nobody's step i + 2 stores can land in a buffer that
+    is still being read.  (A single buffer needs a second barrier after the finalisation.)
+
+    ``rows`` is the LARGEST number of rows per rank; a step with fewer rows (a loader's last batch) uses the front of the
+    buffer with its own slot stride (``dest_ptrs(rows)`` / ``recv_view(rows)``)."""
 
     def __init__(self, world: int, rank: int, rows: int, row_floats: int, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
 
-        self.world, self.rank = world, rank
+        self.world, self.rank, self.rows, self.row_floats = world, rank, int(rows), int(row_floats)
         group = group if group is not None else dist.group.WORLD
-        self.recv = symm_mem.empty((world, rows, row_floats), dtype=torch.float32, device=device)
-        self.handle = symm_mem.rendezvous(self.recv, group.group_name if hasattr(group, "group_name") else group)
-        slot_bytes = rows * row_floats * 4
-        # where THIS rank writes inside rank o's receive buffer: slot index = this rank
-        self.dest_ptrs = [int(self.handle.buffer_ptrs[o]) + rank * slot_bytes for o in range(world)]
+        self._buf = symm_mem.empty((2, world, self.rows, self.row_floats), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self._buf, group.group_name if hasattr(group, "group_name") else group)
+        self._half_bytes = world * self.rows * self.row_floats * 4
+        self._tables = {}
+        self.step = 0
+        self.recv = self._buf[0]  # first buffer, full size (kept for callers that look at one step)
+
+    def dest_ptrs(self, rows: int = None, parity: int = 0):
+        """Where THIS rank writes inside every owner's receive buffer `parity`: slot index = this rank."""
+        rows = self.rows if rows is None else int(rows)
+        slot_bytes = rows * self.row_floats * 4
+        return [int(self.handle.buffer_ptrs[o]) + parity * self._half_bytes + self.rank * slot_bytes
+                for o in range(self.world)]
+
+    def slot_table(self, rows: int = None, parity: int = 0) -> torch.Tensor:
+        """Device pointer table for fb200_bma_reduce_cls_shard (cached per (rows, parity))."""
+        from ... import ops
+
+        rows = self.rows if rows is None else int(rows)
+        key = (rows, parity)
+        if key not in self._tables:
+            self._tables[key] = ops.slot_pointer_table(self.dest_ptrs(rows, parity), self._buf.device)
+        return self._tables[key]
+
+    def recv_view(self, rows: int = None, parity: int = 0) -> torch.Tensor:
+        """[world, rows, row_floats] view of receive buffer `parity` for a step with `rows` rows per rank."""
+        rows = self.rows if rows is None else int(rows)
+        flat = self._buf[parity].reshape(-1)
+        return flat[: self.world * rows * self.row_floats].view(self.world, rows, self.row_floats)
 
     def barrier(self):
         """All ranks' peer stores issued before this point (on the current stream) are visible after it."""

@@ -304,11 +304,18 @@ size_t fb200_cls_slot_row_floats(int C);
  * `rank` (this rank's index) only staggers the order in which input tiles are visited - rank r starts r/N of the way
  * through - so that at any moment the N ranks store into N different owners instead of all into the same one. */
 int fb200_bma_reduce_cls_shard(const void* logits, int dtype, const float* log_temp, const int32_t* targets, int S,
-                               int B, int C, int n_ranks, int rank, const uint64_t* slot_ptrs, void* stream);
+                               int B, int C, int n_ranks, int rank, const uint64_t* slot_ptrs,
+                               float* ensemble_log_prob /* optional [S,B]: ll of THIS rank's samples */, void* stream);
 /* Finalise `rows` owned rows from the n_src slots received (slots: [n_src][rows][fb200_cls_slot_row_floats(C)],
  * one per source rank, summed in source order; the (max, sumexp) pairs are merged), over s_total samples. */
 int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int rows, int C, int s_total,
                                  const fb200_cls_outputs_t* out, void* stream);
+
+/* Predictive.variance / Predictive.std (fortuna/prob_model/predictive/base.py:838-944): variance = aleatoric + epistemic
+ * (the two estimates may come from different posterior draws, as in the reference), std = sqrt(variance).  epistemic may
+ * be NULL (then the first array IS the variance: std(variances=...)); either output may be NULL. */
+int fb200_variance_combine(const float* aleatoric, const float* epistemic, int64_t n, float* variance_out, float* std_out,
+                           void* stream);
 
 /* Regression BMA reductions over calibrated outputs z[S,B,2d] = [mu, log var]
  * (fortuna/prob_output_layer/regression.py:30-34, 67-74; fortuna/likelihood/regression.py:55-99;
@@ -393,6 +400,14 @@ int fb200_ece_bins_from_rows(const float* confidence, const int32_t* preds, cons
  * fb200_ece_bins returns are additive: all-reduce them across the ranks of a B-sharded evaluation, then call this). */
 int fb200_ece_from_bins(const int32_t* counts, const float* conf_sums, const int32_t* correct, int n_bins,
                         int64_t n_total, float* result, void* stream);
+/* The same in one collective: pack the three counters into packed[3 n_bins] float64 = [counts | correct | conf_sums]
+ * (all-reduce THAT with a sum), then result[2] = {ECE, MCE} from the packed sums (counts_out optional int32[n_bins]).
+ * accumulate != 0 adds to what `packed` holds - the bins of a loader evaluated batch by batch (thresholds from the TOTAL
+ * number of data points, metric/classification.py:76). */
+int fb200_ece_pack_bins(const int32_t* counts, const float* conf_sums, const int32_t* correct, int n_bins, double* packed,
+                        int accumulate, void* stream);
+int fb200_ece_from_packed_bins(const double* packed, int n_bins, int64_t n_total, int32_t* counts_out, float* result,
+                               void* stream);
 /* jnp.quantile(x, q) for sorted ascending x[n], method="linear"
  * (fortuna/conformal/regression/quantile.py:89-90, onedim_uncertainty.py:89-90): out[nq]. */
 int fb200_quantile_sorted(const float* x_sorted, int64_t n, const float* q, int nq, float* out, void* stream);

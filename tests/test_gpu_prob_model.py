@@ -273,7 +273,8 @@ def test_predictive_sample_classification(cuda):
     assert y.shape == (5, 400) and y.dtype == torch.int32
     want = []
     for xb in inputs:
-        stored = pm.predictive._stored_logits(torch.as_tensor(np.asarray(xb), dtype=torch.float32, device=cuda)).cpu().numpy()
+        stored = pm.predictive._logits_fn(None, calibrated=False)(
+            torch.as_tensor(np.asarray(xb), dtype=torch.float32, device=cuda)).cpu().numpy()
         want.append(P.cls_sample_targets(stored, ops.key_to_host(key), 5)[0])
     assert np.array_equal(y.cpu().numpy(), np.concatenate(want, axis=1))
     assert float((y[0].cpu() == torch.as_tensor(test[1])).float().mean()) > 0.9  # a trained model mostly samples the label
@@ -340,3 +341,130 @@ def test_fitted_temperature_travels_with_the_checkpoints(cuda, tmp_path):
     key = pm.rng.get()
     inputs = test_loader.to_inputs_loader()
     assert torch.equal(pm2.predictive.mean(inputs, 8, rng=key), pm.predictive.mean(inputs, 8, rng=key))
+
+
+def _small_fit(last_layer_only, seed=0, n_samples=8):
+    from fortuna_b200.prob_model import FitConfig, FitOptimizer, ProbClassifier, SGHMCPosteriorApproximator
+
+    MLP, train, test, train_loader, test_loader = _setup()
+    torch.manual_seed(seed)
+    pm = ProbClassifier(model=MLP(), posterior_approximator=SGHMCPosteriorApproximator(
+        n_samples=n_samples, n_thinning=5, burnin_length=100, step_schedule=1e-3), seed=seed)
+    freeze = (lambda path, v: "trainable" if "output_subnet" in path else "frozen") if last_layer_only else None
+    pm.train(train_loader, fit_config=FitConfig(optimizer=FitOptimizer(n_epochs=40, freeze_fun=freeze)))
+    return pm, train, test
+
+
+@pytest.mark.parametrize("last_layer_only", [True, False])
+def test_predictive_streams_the_loader_batch_by_batch(cuda, last_layer_only):
+    """prob_model.predictive.* walks the loader like the reference's _loop_fun_through_inputs_loader (base.py:946-1013):
+    the result does not depend on the batch size (ragged last batch included), equals the oracle on the drawn samples'
+    logits, and two DIFFERENT inputs of the same shape give different answers (the round-1 cache keyed on a freed
+    tensor's address could return the first one's logits)."""
+    from fortuna_b200.data import DataLoader, InputsLoader
+    from oracle import predictive as P
+
+    pm, train, test = _small_fit(last_layer_only)
+    key = pm.rng.get()
+    names = ("mean", "entropy", "aleatoric_variance", "epistemic_variance", "log_prob", "ensemble_log_prob", "mode")
+    whole = pm.predictive.statistics(DataLoader.from_array_data(test, batch_size=None), names, 12, rng=key)
+    for bs in (128, 37, 400):
+        part = pm.predictive.statistics(DataLoader.from_array_data(test, batch_size=bs), names, 12, rng=key)
+        for k in names:  # the torch backbone picks its GEMM kernel by batch size: equal to float32 rounding, not bits
+            if k == "mode":
+                assert float((part[k] != whole[k]).float().mean()) < 0.01
+            else:
+                np.testing.assert_allclose(part[k].cpu().numpy(), whole[k].cpu().numpy(), rtol=2e-5, atol=2e-6, err_msg=f"{k} {bs}")
+    z = pm.predictive.sample_calibrated_outputs(InputsLoader.from_array_inputs(test[0], batch_size=90), 12, rng=key).cpu().numpy()
+    np.testing.assert_allclose(whole["mean"].cpu().numpy(), P.cls_mean(z), rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(whole["log_prob"].cpu().numpy(), P.cls_log_prob(z, test[1]), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(whole["ensemble_log_prob"].cpu().numpy(), P.cls_ensemble_log_prob(z, test[1]), rtol=1e-5, atol=2e-6)
+    other = (test[0][::-1] * np.float32(0.5)).copy()
+    m1 = pm.predictive.mean(InputsLoader.from_array_inputs(test[0]), 12, rng=key)
+    m2 = pm.predictive.mean(InputsLoader.from_array_inputs(other), 12, rng=key)
+    m1b = pm.predictive.mean(InputsLoader.from_array_inputs(test[0]), 12, rng=key)
+    assert torch.equal(m1, m1b) and not torch.equal(m1, m2)
+    z2 = pm.predictive.sample_calibrated_outputs(InputsLoader.from_array_inputs(other), 12, rng=key).cpu().numpy()
+    np.testing.assert_allclose(m2.cpu().numpy(), P.cls_mean(z2), rtol=1e-5, atol=1e-8)
+
+
+def test_predictive_variance_and_std_follow_the_reference_key_schedule(cuda):
+    """base.py:838-944: variance = aleatoric_variance(key1) + epistemic_variance(key2) with rng, key1 = split(rng) and
+    rng, key2 = split(rng) - two different sets of posterior draws; std = sqrt(variance); given estimates are used as
+    they are."""
+    from fortuna_b200 import ops
+    from fortuna_b200.data import InputsLoader
+    from oracle import predictive as P
+    from oracle import prng as oprng
+
+    pm, train, test = _small_fit(True, seed=2)
+    inputs = InputsLoader.from_array_inputs(test[0], batch_size=150)
+    rng = pm.rng.get()
+    k = ops.key_to_host(rng)
+    r1, key1 = oprng.split(k)
+    r2, key2 = oprng.split(r1)
+    idx1 = np.array([oprng.choice(q, 8) for q in oprng.split(key1, 9)])
+    idx2 = np.array([oprng.choice(q, 8) for q in oprng.split(key2, 9)])
+    assert not np.array_equal(idx1, idx2)
+    stored = pm.predictive._logits_fn(None)(torch.as_tensor(test[0], device=cuda)).cpu().numpy()  # [8, B, C]
+    want = (P.cls_aleatoric_variance(stored[idx1]) + P.cls_epistemic_variance(stored[idx2])).astype(np.float32)
+    var = pm.predictive.variance(inputs, 9, rng=rng)
+    np.testing.assert_allclose(var.cpu().numpy(), want, rtol=1e-5, atol=4e-7)
+    std = pm.predictive.std(inputs, 9, rng=rng)
+    np.testing.assert_allclose(std.cpu().numpy(), np.sqrt(want), rtol=1e-5, atol=1e-6)
+    # given estimates: no draws at all
+    a = pm.predictive.aleatoric_variance(inputs, 9, rng=rng)
+    e = pm.predictive.epistemic_variance(inputs, 9, rng=rng)
+    assert torch.equal(pm.predictive.variance(inputs, 9, aleatoric_variances=a, epistemic_variances=e), a + e)
+    assert torch.equal(pm.predictive.std(inputs, variances=a + e), torch.sqrt(a + e))
+    # only the aleatoric term given: the epistemic one is drawn with the FIRST split of rng (base.py:889-897)
+    v2 = pm.predictive.variance(inputs, 9, aleatoric_variances=a, rng=rng)
+    want2 = a.cpu().numpy() + P.cls_epistemic_variance(stored[idx1])
+    np.testing.assert_allclose(v2.cpu().numpy(), want2, rtol=1e-5, atol=4e-7)
+
+
+def test_predictive_bf16_last_layer_and_conformal_sets_in_one_pass(cuda):
+    """The bench's route through the public API: bf16 last-layer contraction + bf16 logits (north_star: rtol 2e-2 on the
+    GEMM), statistics and APS conformal sets from ONE pass over the loader; sets equal fb200_aps_conformal_sets on the
+    returned mean bit for bit."""
+    from fortuna_b200 import ops
+    from fortuna_b200.data import DataLoader
+    from fortuna_b200.prob_model.predictive import pipeline
+    from fortuna_b200.prob_model.predictive.classification import ClassificationPredictive
+
+    pm, train, test = _small_fit(True, seed=1)
+    key = pm.rng.get()
+    loader = DataLoader.from_array_data(test, batch_size=128)
+    ref = pm.predictive.statistics(loader, ("mean", "entropy"), 16, rng=key)
+    fast = ClassificationPredictive(pm.posterior, last_layer_dtype=torch.bfloat16, logits_dtype=torch.bfloat16)
+    t = torch.as_tensor(test[1], dtype=torch.int32, device=cuda)
+    val = ops.sort_f32_(ops.aps_scores(ref["mean"], t).clone())
+    calib = pipeline.ConformalCalibration(val, len(test[1]), 0.1)
+    out = fast.statistics(loader, ("mean", "entropy"), 16, rng=key, conformal=calib)
+    np.testing.assert_allclose(out["mean"].cpu().numpy(), ref["mean"].cpu().numpy(), rtol=2e-2, atol=2e-3)
+    m, sz = ops.aps_conformal_sets(out["mean"], calib.val_sorted, calib.threshold)
+    assert torch.equal(out["conformal_mask"], m) and torch.equal(out["conformal_sizes"], sz)
+
+
+def test_predictive_statistics_to_host_with_streamed_ece(cuda):
+    """statistics(..., to_host=True, ece=True): pinned host results equal the device results, and the ECE accumulated
+    batch by batch (thresholds of the WHOLE data set) equals the metric on the full mean."""
+    from fortuna_b200 import ops
+    from fortuna_b200.data import DataLoader
+    from fortuna_b200.prob_model.predictive import pipeline
+    from oracle import scoring as Sc
+
+    pm, train, test = _small_fit(True, seed=4)
+    key = pm.rng.get()
+    loader = DataLoader.from_array_data(test, batch_size=96)
+    names = ("mean", "entropy", "log_prob", "mode")
+    dev_out = pm.predictive.statistics(loader, names, 10, rng=key, ece=True)
+    host_out = pm.predictive.statistics(loader, names, 10, rng=key, ece=True, to_host=True)
+    for k in names + ("ece",):
+        assert not host_out[k].is_cuda and (k == "ece" or host_out[k].is_pinned())
+        assert torch.equal(host_out[k], dev_out[k].cpu()), k
+    mean = dev_out["mean"].cpu().numpy()
+    want = Sc.expected_calibration_error(mean.argmax(-1), mean, test[1])
+    np.testing.assert_allclose(float(dev_out["ece"][0]), want, rtol=1e-5, atol=1e-7)
+    again = pm.predictive.statistics(loader, names, 10, rng=key, ece=True, to_host=host_out)  # buffers reused
+    assert again["mean"].data_ptr() == host_out["mean"].data_ptr()

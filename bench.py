@@ -8,9 +8,10 @@ z[S=64, B=65536, C=1000] (float32, 16.8 GB, larger than L2):
     fb200_aps_conformal_sets  -> adaptive-prediction-set scores for every class of the mean and the rank-count sets
                                  against 50 000 pre-sorted validation scores, one kernel
     fb200_ece_bins_from_rows  -> ECE / MCE / accuracy / Brier of the mean from those per-row quantities
-`value` times that with z resident in HBM; `e2e` times the same work through the public
-`predictive_from_logits_batches` call with pinned HOST batches (H2D of every batch and D2H of every
-result inside the timed region).  `--impl reference` times the CPU oracle (numpy restatement of the
+`value` times that with z resident in HBM; `e2e` times the user's call -
+`ProbClassifier.predictive.statistics(data_loader, ..., conformal=..., ece=True, to_host=True)` - from pinned HOST
+features [B, 2048] through the last-layer GEMM (K2, tcgen05), the reductions, the sets and the ECE back to pinned host
+results (H2D of every batch and D2H of every result inside the timed region).  `--impl reference` times the CPU oracle (numpy restatement of the
 reference's jnp path - JAX itself cannot be installed here) on a bounded sample with all host cores.
 
 Contract: python bench.py --gpus N --steps K --warmup W  (N > 1 under torchrun, one rank per GPU).
@@ -294,6 +295,119 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+class HostBatches:
+    """A loader of pinned HOST batches: (features [Bc, D] bf16, targets [Bc] int32) pairs - what a data loader hands
+    ``predictive.statistics`` (fortuna/data/loader/base.py); iterating yields the same pinned tensors every pass."""
+
+    def __init__(self, xs, ts):
+        self.xs, self.ts = xs, ts
+        self.size = sum(int(x.shape[0]) for x in xs)
+
+    def __iter__(self):
+        return iter(zip(self.xs, self.ts))
+
+    def to_array_targets(self):  # marks this as a DATA loader (targets are read from the batches)
+        import torch
+
+        return torch.cat(self.ts)
+
+
+def build_prob_classifier(dev, S, D, Cn, seed, logits_dtype):
+    """ProbClassifier over a last-layer posterior of S random-init samples: ``dfe_subnet`` = identity (the features ARE the
+    inputs: the backbone is outside the hot path), ``output_subnet`` = Linear(D, C); bf16 contraction on tcgen05."""
+    import torch
+
+    from fortuna_b200.prob_model import ProbClassifier, SGHMCPosteriorApproximator
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dfe_subnet = torch.nn.Identity()
+            self.output_subnet = torch.nn.Linear(D, Cn)
+
+        def forward(self, x):
+            return self.output_subnet(self.dfe_subnet(x).float())
+
+    pm = ProbClassifier(model=Head(), posterior_approximator=SGHMCPosteriorApproximator(n_samples=S), seed=seed, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11 + seed)
+    n_tr = Cn * D + Cn  # flat layout (sorted leaf names): output_subnet/bias [C], output_subnet/weight [C, D]
+    bank = torch.empty((S, n_tr), device=dev)
+    bank[:, :Cn].normal_(generator=gen)
+    bank[:, Cn:].normal_(generator=gen).mul_(D ** -0.5)
+    pm.attach_posterior_samples(bank, freeze_fun=lambda path, v: "trainable" if "output_subnet" in path else "frozen",
+                                last_layer_dtype=torch.bfloat16, logits_dtype=logits_dtype)
+    pm.predictive.log_temp = torch.tensor([0.3], device=dev)
+    return pm
+
+
+def bench_e2e_api(dev, S, B, D, Cn, calib, args, world, rank):
+    """`e2e`: the metric through the public call a user makes -
+    ``ProbClassifier.predictive.statistics(data_loader, names, n_posterior_samples=S, conformal=..., ece=True,
+    to_host=True)`` - with pinned HOST inputs: every step copies the step's features and targets to the device and all
+    results back inside the timed region.  N > 1: ``sharded_io`` - every rank feeds its own B / N rows of each batch and
+    receives the results of those rows; the S draws are sharded over the ranks (strong scaling: S, B fixed)."""
+    import torch
+    import torch.distributed as dist
+
+    logits_dtype = torch.bfloat16 if args.e2e_logits == "bf16" else torch.float32
+    pm = build_prob_classifier(dev, S, D, Cn, 0, logits_dtype)
+    B_local = B // world
+    # rows per batch per rank: the whole job's batch at N = 1; at N > 1 at least 4096 rows per rank (a smaller batch leaves
+    # the GEMM launch-sized), so fewer batches per step as N grows
+    Bc = min(args.e2e_batch if world == 1 else max(4096, args.e2e_batch // world), B_local)
+    n_batches = (B_local + Bc - 1) // Bc
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(21 + rank)
+    xs, ts = [], []
+    for i in range(n_batches):
+        rows = min(Bc, B_local - i * Bc)
+        d = torch.empty((rows, D), device=dev).normal_(generator=gen).to(torch.bfloat16)
+        hx = torch.empty((rows, D), dtype=torch.bfloat16, pin_memory=True)
+        hx.copy_(d)
+        xs.append(hx)
+        ts.append(torch.randint(0, Cn, (rows,), dtype=torch.int32).pin_memory())
+        del d
+    loader = HostBatches(xs, ts)
+    key = pm.rng.get()
+    host = True
+    times = []
+    for it in range(2 + args.e2e_steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        host = pm.predictive.statistics(loader, WANT, n_posterior_samples=S, rng=key, conformal=calib, ece=True,
+                                        to_host=host, distribute=world > 1, sharded_io=world > 1)
+        torch.cuda.synchronize()
+        if it >= 2:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    if world > 1:
+        tt = torch.tensor([sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = float(tt[0])
+    h2d = sum(x.numel() * x.element_size() for x in xs) + sum(t.numel() * 4 for t in ts)
+    d2h = sum(v.numel() * v.element_size() for v in host.values())
+    return {
+        "value": float(S) * B * Cn / sec,
+        "unit": UNIT,
+        "ms_per_step": sec * 1e3,
+        "h2d_bytes_per_step": int(h2d) * world,
+        "d2h_bytes_per_step": int(d2h) * world,
+        "steps": len(times),
+        "api": "fortuna_b200.prob_model.ProbClassifier.predictive.statistics(data_loader, names, n_posterior_samples=S, "
+               "conformal=calib, ece=True, to_host=True" + (", distribute=True, sharded_io=True)" if world > 1 else ")"),
+        "what": f"pinned host features [B={B},{D}] bf16 + targets -> last-layer GEMM over S={S} drawn samples of the resident bank "
+                f"(tcgen05, {args.e2e_logits} logits) -> single-pass reductions -> APS conformal sets + ECE -> pinned host results; "
+                f"{n_batches} batches of {Bc} rows per rank, copies overlapped with compute",
+        "sharding": "single GPU" if world == 1 else
+                    f"strong scaling: S={S} draws sharded x{world} ({S // world} per rank), every rank feeds and receives B/{world} rows; "
+                    "inputs all-gathered over NVLink, partial sums exchanged by peer stores",
+        "gemm_flops_per_step": 2.0 * S * B * D * Cn,
+    }
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
@@ -312,9 +426,23 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    S, B, Cn = args.S, args.B, args.C
-    if B % world:
-        raise SystemExit("B must be divisible by the number of GPUs")
+    strong = args.scaling == "strong" and world > 1
+    S_total, B, Cn = args.S, args.B, args.C
+    if B % world or (strong and S_total % world):
+        raise SystemExit("B (and, for strong scaling, S) must be divisible by the number of GPUs")
+    S = S_total // world if strong else S_total  # samples THIS rank evaluates
+
+    parity = None
+    if world > 1:
+        # the S-sharded path against the single-GPU kernel on the same samples, once, outside the timed region
+        from scripts.check_sharded_predictive import run_check
+
+        parity = run_check(dev, rank, world, args.transport, verbose=False)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "S-sharded parity check failed", "parity": parity}), flush=True)
+            dist.destroy_process_group()
+            raise SystemExit(1)
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -368,8 +496,27 @@ def run_gpu_arm(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms, reduce_ms = float(tt[0]), float(tt[1])
     ms_per_step = total_ms / args.steps
-    elems_per_step = float(S) * B * Cn * world  # every rank evaluates its own S samples (weak scaling in S)
+    elems_per_step = float(S) * B * Cn * world  # weak: every rank its own S samples; strong: S_total = S * world fixed
     value = elems_per_step / (ms_per_step * 1e-3)
+
+    # per-phase breakdown of a step (CUDA events on the launching stream), measured in a second, untimed run of a few steps
+    phases = None
+    if world > 1 or args.phases:
+        runner.timer = pipeline.PhaseTimer()
+        for _ in range(min(10, args.steps)):
+            one_step()
+        torch.cuda.synchronize()
+        ph = runner.timer.summary_ms()
+        runner.timer = None
+        if world > 1:
+            keys = sorted(ph)
+            tt = torch.tensor([ph[k] for k in keys], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ph = {k: float(v) for k, v in zip(keys, tt)}
+        phases = {"ms_max_over_ranks": ph, "sum_ms": sum(ph.values()),
+                  "note": "reduce = reduction kernel incl. its peer stores; exchange = the one symmetric-memory barrier (or the "
+                          "all-to-all); finalize = sum the N source slots + finalise the owned rows; sets = APS sort + conformal "
+                          "sets; ece = binning; ece_allreduce = pack + ONE all-reduce + finalise"}
 
     # roofline of the dominant kernel: algorithmic bytes per launch / measured launch time
     # logits read once + outputs written once: single GPU -> mean + two variance arrays [B,C] and six [B] vectors;
@@ -381,7 +528,7 @@ def run_gpu_arm(args):
     achieved = alg_bytes / (reduce_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
         with open(tpath) as f:
             traffic = json.load(f).get("bma_reduce_cls_kernel")
 
@@ -394,17 +541,17 @@ def run_gpu_arm(args):
         "warmup": args.warmup,
         "ms_per_step": ms_per_step,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
         "config": {
-            "workload": f"c4 predictive z[S={S},B={B},C={Cn}] f32 -> BMA reductions + APS conformal sets + ECE",
-            "S_per_gpu": S, "B": B, "C": Cn, "n_val": N_VAL, "error": ERROR,
+            "workload": f"c4 predictive z[S={S * world if strong else S},B={B},C={Cn}] f32 -> BMA reductions + APS conformal sets + ECE",
+            "S_per_gpu": S, "S_total": S * world, "B": B, "C": Cn, "n_val": N_VAL, "error": ERROR,
             "parallelism": "single GPU" if world == 1 else (
                 f"S-sharded x{world}: partial sums exchanged by " + ("ONE NCCL all-to-all" if runner.transport == "nccl" else
-                "peer stores from the reduction kernel over NVLink (symmetric memory) + barrier")),
-            "l2": "inputs (16.8 GB) larger than L2; no flush needed",
+                "peer stores from the reduction kernel over NVLink (symmetric memory, double-buffered) + ONE barrier")),
+            "l2": "inputs larger than L2; no flush needed" if 4.0 * S * B * Cn > 2.5e8 else "inputs re-read from HBM each step",
         },
         "roofline": {
             "bound": "hbm", "kernel": "bma_reduce_cls_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -414,24 +561,28 @@ def run_gpu_arm(args):
         "gpu_launches": runner.launches_per_step * args.steps,
         "clocks": clocks,
     }
+    if parity is not None:
+        line["parity"] = parity
+    if phases is not None:
+        line["phases"] = phases
+    if world > 1:
+        # the exchange: every rank ships the slot rows of the inputs it does not own and receives as many
+        slot_bytes = 4.0 * B * (2 * Cn + 4)
+        link = slot_bytes * (world - 1) / world
+        ex_ms = (phases["ms_max_over_ranks"].get("exchange", 0.0) + reduce_ms) if phases else None
+        line["nvlink"] = {"bytes_out_per_rank_per_step": link, "bytes_in_per_rank_per_step": link,
+                          "note": "peer stores are issued by the reduction kernel's row epilogue and overlap it; the lower bound of "
+                                  "reduce + exchange is max(HBM time of the logits, link bytes / 770 GB/s)",
+                          "link_bound_ms_at_770GBs": link / 770e9 * 1e3,
+                          "reduce_plus_exchange_ms": ex_ms,
+                          "achieved_GBs_per_direction": (link / (ex_ms * 1e-3) / 1e9) if ex_ms else None}
+    del z, runner
+    torch.cuda.empty_cache()
 
     if not args.no_e2e:
-        # every rank streams its own [S,B,C] host logits through the public call (inputs sharded over B like the
-        # reference's pmap prediction mode: no collective); whole-job value = N * S*B*C / max-over-ranks time
-        e2e = pipeline.bench_e2e(S, B, Cn, dev, WANT, calib, args, UNIT)
-        if world > 1:
-            tt = torch.tensor([e2e["ms_per_step"]], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e["ms_per_step"] = float(tt[0])
-            e2e["value"] = float(S) * B * Cn * world / (e2e["ms_per_step"] * 1e-3)
-            e2e["h2d_bytes_per_step"] *= world
-            e2e["d2h_bytes_per_step"] *= world
-            e2e["sharding"] = f"inputs sharded over {world} ranks (B per rank = {B}), no collective"
+        e2e = bench_e2e_api(dev, S_total, B, args.D, Cn, calib, args, world, rank)
         e2e["host_threads_bound_to_gpu_numa_node"] = numa_cores
         line["e2e"] = e2e
-        if world == 1:
-            # the same predictive outputs starting one stage earlier, from HOST features through the last-layer GEMM
-            line["e2e_from_features"] = pipeline.bench_e2e_from_features(S, B, args.D, Cn, dev, WANT, calib, args, UNIT)
     if rank == 0 and world == 1 and not args.no_extras:
         try:
             from fortuna_b200.bench_extras import last_layer_extras, sampler_extras
@@ -487,8 +638,13 @@ def main():
     ap.add_argument("--C", type=int, default=C_FULL)
     ap.add_argument("--D", type=int, default=2048, help="last-layer feature width for e2e_from_features / GEMM extras")
     ap.add_argument("--cpu-rows-per-core", type=int, default=64)
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-batch", type=int, default=4096)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-batch", type=int, default=8192, help="rows per batch of the e2e loader (whole job; / N per rank)")
+    ap.add_argument("--e2e-logits", default="bf16", choices=["bf16", "f32"],
+                    help="dtype of the logits between the last-layer GEMM and the reductions in the e2e path")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every rank evaluates S samples (S_total = N S); strong = S_total = S fixed, S / N per rank")
+    ap.add_argument("--phases", action="store_true", help="add the per-phase CUDA-event breakdown at N = 1 too")
     ap.add_argument("--transport", default="p2p", choices=["nccl", "p2p"],
                     help="N > 1 exchange: one NCCL all-to-all, or peer stores from the reduction kernel over NVLink")
     ap.add_argument("--no-e2e", action="store_true")

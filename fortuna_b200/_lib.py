@@ -138,7 +138,7 @@ SIGNATURES = {
     "fb200_bma_reduce_cls_wide": (_i, [_P, _i, _P, _P, _i, _i, _i, C.POINTER(ClsOutputs), _P, _sz, _P]),
     "fb200_cls_slot_row_floats": (_sz, [_i]),
     "fb200_bma_reduce_cls_shard": (_i, [_P, _i, _P, _P, _i, _i, _i, _i, _i, _P, _P, _P]),
-    "fb200_bma_finalize_cls_slots": (_i, [_P, _i, _i, _i, _i, C.POINTER(ClsOutputs), _P]),
+    "fb200_bma_finalize_cls_slots": (_i, [_P, _i, _i, _i, _i, C.POINTER(ClsOutputs), _P, _P]),
     "fb200_variance_combine": (_i, [_P, _P, _i64, _P, _P, _P]),
     "fb200_bma_reduce_reg": (_i, [_P, _P, _P, _i, _i, _i, C.POINTER(RegOutputs), _P]),
     "fb200_aps_scores": (_i, [_P, _P, _i, _i, _P, _P, _P]),

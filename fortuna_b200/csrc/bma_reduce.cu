@@ -623,9 +623,14 @@ static int launch_cls_wide(const ClsArgs& a, float* lse_ws, cudaStream_t st) {
 // above): sums are taken in source-rank order (deterministic), the (max, sumexp) pairs are merged, then the same
 // finalisation as the single-GPU kernel.  One warp per row.
 // ------------------------------------------------------------------------------------------------
+template <bool V4>
 __global__ void __launch_bounds__(256) bma_finalize_slots_kernel(const float* __restrict__ slots, int n_src, int rows,
                                                                  int C, int s_total, const fb200_cls_outputs_t out,
-                                                                 float log_S) {
+                                                                 const int32_t* __restrict__ targets, float log_S) {
+  // One warp per owned row: the N source rows are streamed with 128-bit loads (V4: C % 4 == 0; a slot row is 2C + 4
+  // floats, so every row and its second half start 16-byte aligned), summed in source-rank order, finalised like the
+  // single-GPU epilogue (div_s: correctly rounded x / S without the IEEE-division slow path).  HBM-bound:
+  // n_src (2C + 4) floats read + the requested outputs written per row.
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -633,32 +638,61 @@ __global__ void __launch_bounds__(256) bma_finalize_slots_kernel(const float* __
   const size_t RS = (size_t)(2 * C + 4);
   const size_t src_stride = (size_t)rows * RS;
   const float* row0 = slots + (size_t)b * RS;
-  const float Sf = (float)s_total;
-  float ent_terms = 0.0f;
+  const DivS dS = make_divs((float)s_total);
+  const int y = targets ? targets[b] : -1;
+  float ent_terms = 0.0f, msq = 0.0f, mean_y = 0.0f;
   float best_v = -CUDART_INF_F;
   int best_c = 0x7FFFFFFF;
-  for (int c = lane; c < C; c += 32) {
-    float sp = 0.0f, sp2 = 0.0f;
+  constexpr int W = V4 ? 4 : 1;
+  for (int c0 = lane * W; c0 < C; c0 += 32 * W) {
+    float sp[W], sp2[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) sp[k] = sp2[k] = 0.0f;
     for (int r = 0; r < n_src; ++r) {
-      sp += row0[(size_t)r * src_stride + c];
-      sp2 += row0[(size_t)r * src_stride + C + c];
+      const float* pr = row0 + (size_t)r * src_stride;
+      if constexpr (V4) {
+        const float4 a = *reinterpret_cast<const float4*>(pr + c0);
+        const float4 q = *reinterpret_cast<const float4*>(pr + C + c0);
+        sp[0] += a.x; sp[1] += a.y; sp[2] += a.z; sp[3] += a.w;
+        sp2[0] += q.x; sp2[1] += q.y; sp2[2] += q.z; sp2[3] += q.w;
+      } else {
+        sp[0] += pr[c0];
+        sp2[0] += pr[C + c0];
+      }
     }
-    const size_t o = (size_t)b * C + c;
-    const float mean = sp / Sf;
-    const float av = (sp - sp2) / Sf;
-    const float ev = fmaxf(0.0f, __fsub_rn(sp2 / Sf, __fmul_rn(mean, mean)));
-    if (mean > 0.0f) ent_terms = fmaf(mean, logf(mean), ent_terms);
-    if (mean > best_v) {
-      best_v = mean;
-      best_c = c;
+    float mean[W], av[W], ev[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      mean[k] = div_s(sp[k], dS);
+      av[k] = div_s(sp[k] - sp2[k], dS);
+      ev[k] = fmaxf(0.0f, __fsub_rn(div_s(sp2[k], dS), __fmul_rn(mean[k], mean[k])));
+      if (mean[k] > 0.0f) ent_terms = fmaf(mean[k], __logf(mean[k]), ent_terms);
+      msq = fmaf(mean[k], mean[k], msq);
+      mean_y = (c0 + k == y) ? mean[k] : mean_y;
+      if (mean[k] > best_v) {
+        best_v = mean[k];
+        best_c = c0 + k;
+      }
     }
-    if (out.mean) out.mean[o] = mean;
-    if (out.aleatoric_variance) out.aleatoric_variance[o] = av;
-    if (out.epistemic_variance) out.epistemic_variance[o] = ev;
-    if (out.variance) out.variance[o] = av + ev;
-    if (out.std) out.std[o] = sqrtf(av + ev);
+    const size_t o = (size_t)b * C + c0;
+    if constexpr (V4) {
+      if (out.mean) st_f4(out.mean + o, mean[0], mean[1], mean[2], mean[3]);
+      if (out.aleatoric_variance) st_f4(out.aleatoric_variance + o, av[0], av[1], av[2], av[3]);
+      if (out.epistemic_variance) st_f4(out.epistemic_variance + o, ev[0], ev[1], ev[2], ev[3]);
+      if (out.variance) st_f4(out.variance + o, av[0] + ev[0], av[1] + ev[1], av[2] + ev[2], av[3] + ev[3]);
+      if (out.std)
+        st_f4(out.std + o, sqrtf(av[0] + ev[0]), sqrtf(av[1] + ev[1]), sqrtf(av[2] + ev[2]), sqrtf(av[3] + ev[3]));
+    } else {
+      if (out.mean) out.mean[o] = mean[0];
+      if (out.aleatoric_variance) out.aleatoric_variance[o] = av[0];
+      if (out.epistemic_variance) out.epistemic_variance[o] = ev[0];
+      if (out.variance) out.variance[o] = av[0] + ev[0];
+      if (out.std) out.std[o] = sqrtf(av[0] + ev[0]);
+    }
   }
   const float ent = -group_sum<32>(ent_terms);
+  msq = group_sum<32>(msq);
+  mean_y = group_sum<32>(mean_y);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
@@ -681,13 +715,14 @@ __global__ void __launch_bounds__(256) bma_finalize_slots_kernel(const float* __
       if (mr > -CUDART_INF_F) ssum += sr * __expf(mr - M);
       else if (sr != sr) ssum = sr;  // NaN propagates like the reference's logsumexp
     }
-    const float alea = -plogp / Sf;
+    const float alea = -plogp / (float)s_total;
     if (out.entropy) out.entropy[b] = ent;
     if (out.aleatoric_entropy) out.aleatoric_entropy[b] = alea;
     if (out.epistemic_entropy) out.epistemic_entropy[b] = ent - alea;
     if (out.mode) out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
     if (out.confidence) out.confidence[b] = best_v;
     if (out.log_prob) out.log_prob[b] = (M + logf(ssum)) - log_S;
+    if (out.brier_terms) out.brier_terms[b] = (y >= 0 && y < C) ? (msq - 2.0f * mean_y) + 1.0f : msq;
   }
 }
 
@@ -1064,14 +1099,22 @@ extern "C" int fb200_bma_reduce_cls_shard(const void* logits, int dtype, const f
 }
 
 extern "C" int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int rows, int C, int s_total,
-                                            const fb200_cls_outputs_t* out, void* stream) {
+                                            const fb200_cls_outputs_t* out, const int32_t* targets, void* stream) {
   if (!slots || !out) return FB200_E_NULL;
   if (out->ensemble_log_prob) return FB200_E_UNSUPPORTED;  // per-sample values live on the rank that holds the sample
-  if (out->brier_terms) return FB200_E_UNSUPPORTED;        // needs the targets: use fb200_ece_bins on the finalised mean
+  if (out->brier_terms && !targets) return FB200_E_NULL;   // the Brier term needs the owned rows' targets
   if (n_src <= 0 || rows <= 0 || C <= 0 || s_total <= 0) return FB200_E_SHAPE;
   const int64_t threads = (int64_t)rows * 32;
-  bma_finalize_slots_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      slots, n_src, rows, C, s_total, *out, logf((float)s_total));
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  const bool v4 = (C % 4 == 0) && fb200_aligned16(slots) && fb200_aligned16(out->mean) &&
+                  fb200_aligned16(out->aleatoric_variance) && fb200_aligned16(out->epistemic_variance) &&
+                  fb200_aligned16(out->variance) && fb200_aligned16(out->std);
+  if (v4)
+    bma_finalize_slots_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(slots, n_src, rows, C, s_total, *out, targets,
+                                                                            logf((float)s_total));
+  else
+    bma_finalize_slots_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(slots, n_src, rows, C, s_total, *out, targets,
+                                                                             logf((float)s_total));
   FB200_LAUNCH_CHECK();
   return 0;
 }

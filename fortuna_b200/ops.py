@@ -531,13 +531,15 @@ def bma_reduce_cls_shard(logits, slot_ptrs, targets=None, log_temp=None, rank=0,
     )
 
 
-def bma_finalize_cls_slots(slots, s_total, Cn, want, out=None):
-    """slots [n_src, rows, row_floats] (received, one per source rank) -> final outputs for the owned rows."""
+def bma_finalize_cls_slots(slots, s_total, Cn, want, out=None, targets=None):
+    """slots [n_src, rows, row_floats] (received, one per source rank) -> final outputs for the owned rows; `targets`
+    (int32 [rows], the owned rows') only for ``brier_terms``."""
     n_src, rows, _ = slots.shape
     outs = out if out is not None else _alloc_cls_outputs(tuple(want), s_total, rows, Cn, slots.device)
     ost = _cls_struct(outs)
     check(
-        lib().fb200_bma_finalize_cls_slots(_ptr(slots, torch.float32), n_src, rows, Cn, int(s_total), C.byref(ost), _stream()),
+        lib().fb200_bma_finalize_cls_slots(_ptr(slots, torch.float32), n_src, rows, Cn, int(s_total), C.byref(ost),
+                                           _ptr(targets, torch.int32, True), _stream()),
         "fb200_bma_finalize_cls_slots",
     )
     return outs

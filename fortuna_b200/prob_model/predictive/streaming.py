@@ -71,7 +71,8 @@ class ShardContext:
 
     def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor], s_total: int, want: Sequence[str],
                log_temp=None, ens_local: Optional[torch.Tensor] = None, out=None) -> Dict[str, torch.Tensor]:
-        """z [S_local, rows, C] (rows % world == 0) -> finalised outputs of THIS rank's rows / world rows."""
+        """z [S_local, rows, C] (rows % world == 0) -> finalised outputs of THIS rank's rows / world rows.
+        `targets`: int32 [rows] of the WHOLE batch (every rank scores its samples on all rows)."""
         _, rows, C = z.shape
         per = rows // self.world
         self._ensure(per, C)
@@ -90,7 +91,8 @@ class ShardContext:
             ops.bma_reduce_cls_shard(z, table, targets=targets, log_temp=log_temp, rank=self.rank,
                                      ensemble_log_prob=ens_local)
             dist.all_to_all_single(recv.reshape(-1), send.reshape(-1))
-        return ops.bma_finalize_cls_slots(recv, s_total, C, want, out=out)
+        t_own = targets[self.rank * per : (self.rank + 1) * per] if targets is not None else None
+        return ops.bma_finalize_cls_slots(recv, s_total, C, want, out=out, targets=t_own)
 
 
 def _alloc_result(names, S, B, C, device):
@@ -196,14 +198,16 @@ def stream_cls_reduce(
     if targets is not None and not isinstance(targets, torch.Tensor):
         targets = np.asarray(targets)
     staging = staging if staging is not None else {}
-    st_x = staging.setdefault("x", _Staging(device))
-    st_t = staging.setdefault("t", _Staging(device))
+    if "x" not in staging:  # streams and staging buffers live as long as the predictive object
+        staging["x"], staging["t"] = _Staging(device), _Staging(device)
+        staging["copy_stream"], staging["out_stream"] = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    st_x, st_t = staging["x"], staging["t"]
     cur = torch.cuda.current_stream(device)
-    copy_s = staging.setdefault("copy_stream", torch.cuda.Stream(device))
+    copy_s = staging["copy_stream"]
     copy_s.wait_stream(cur)
     out_s = None
     if to_host is not False and to_host is not None:
-        out_s = staging.setdefault("out_stream", torch.cuda.Stream(device))
+        out_s = staging["out_stream"]
         out_s.wait_stream(cur)
     host = to_host if isinstance(to_host, dict) else ({} if out_s is not None else None)
     ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -222,7 +226,7 @@ def stream_cls_reduce(
 
         ece_thr = torch.from_numpy(ece_thresholds(int(ece_total))).to(device)
         want_targets = True
-        for n in ("confidence", "mode") + (("brier_terms",) if world == 1 else ()):  # per-row ECE inputs from K3's epilogue
+        for n in ("confidence", "mode") + (("brier_terms",) if world == 1 or sharded_io else ()):  # per-row ECE inputs
             if n not in kernel_names:
                 kernel_names = kernel_names + (n,)
         names = names + tuple(n for n in kernel_names if n not in names)

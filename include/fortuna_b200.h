@@ -309,7 +309,9 @@ int fb200_bma_reduce_cls_shard(const void* logits, int dtype, const float* log_t
 /* Finalise `rows` owned rows from the n_src slots received (slots: [n_src][rows][fb200_cls_slot_row_floats(C)],
  * one per source rank, summed in source order; the (max, sumexp) pairs are merged), over s_total samples. */
 int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int rows, int C, int s_total,
-                                 const fb200_cls_outputs_t* out, void* stream);
+                                 const fb200_cls_outputs_t* out,
+                                 const int32_t* targets /* optional int32[rows]: the owned rows' targets, for brier_terms */,
+                                 void* stream);
 
 /* Predictive.variance / Predictive.std (fortuna/prob_model/predictive/base.py:838-944): variance = aleatoric + epistemic
  * (the two estimates may come from different posterior draws, as in the reference), std = sqrt(variance).  epistemic may

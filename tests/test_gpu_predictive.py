@@ -208,9 +208,10 @@ def test_last_layer_cuda_core_path(cuda, S, B, D, C, dtype, layout):
 
 
 def test_pipeline_from_host_features_matches_oracle(cuda):
-    """The loader-shaped last-layer predictive: host features -> K2 -> K3 -> K5-K7 -> host, vs the oracle chain."""
+    """The loader-shaped last-layer predictive (streaming.stream_cls_reduce, the engine behind prob_model.predictive.*):
+    pinned host features -> K2 -> K3 -> K5-K7 -> pinned host results, vs the oracle chain."""
     from fortuna_b200 import ops
-    from fortuna_b200.prob_model.predictive import pipeline
+    from fortuna_b200.prob_model.predictive import pipeline, streaming
     from oracle import scoring as Sc
 
     r = np.random.default_rng(21)
@@ -225,17 +226,21 @@ def test_pipeline_from_host_features_matches_oracle(cuda):
     idx_np = idx.cpu().numpy()
     z = P.last_layer_logits(x, w[idx_np], bias[idx_np], lt, bf16_inputs=True)  # [S,B,C] oracle logits
     xs = P.round_to_bf16(x)
-    hx = [torch.from_numpy(xs[i : i + 128]).to(torch.bfloat16).pin_memory() for i in range(0, B, 128)]
-    ht = [torch.from_numpy(t[i : i + 128]).pin_memory() for i in range(0, B, 128)]
+    batches = [(torch.from_numpy(xs[i : i + 128]).to(torch.bfloat16).pin_memory(), torch.from_numpy(t[i : i + 128]).pin_memory())
+               for i in range(0, B, 128)]
     wt = ops.transpose_w_bf16(torch.from_numpy(w).to(cuda))
+    bias_d, lt_d = torch.from_numpy(bias).to(cuda), torch.from_numpy(lt).to(cuda)
     val_probs = P.softmax((2 * r.standard_normal((500, C))).astype(np.float32))
     val_t = r.integers(0, C, 500)
     val_sorted = torch.from_numpy(np.sort(Sc.aps_score(val_probs, val_t))).to(cuda)
     calib = pipeline.ConformalCalibration(val_sorted, 500, 0.1)
     want = ("mean", "entropy", "log_prob", "mode")
-    out = pipeline.predictive_from_feature_batches(hx, ht, wt, torch.from_numpy(bias).to(cuda), torch.from_numpy(lt).to(cuda),
-                                                   calib, want, cuda, sample_idx=idx)
-    torch.cuda.synchronize()
+
+    def logits_fn(xd):
+        assert xd.dtype == torch.bfloat16  # pinned bf16 batches are the DMA source as they are
+        return ops.last_layer_logits(xd, wt, bias_d, lt_d, w_layout=ops.W_SCD, sample_idx=idx)
+
+    out = streaming.stream_cls_reduce(batches, logits_fn, want, B, S, cuda, sets=calib, to_host=True, ece_total=B)
     # bf16 GEMM with float32 accumulation in a different order than the oracle's: logits agree to ~1e-3 relative
     np.testing.assert_allclose(out["mean"].numpy(), P.cls_mean(z), rtol=5e-3, atol=1e-5)
     np.testing.assert_allclose(out["entropy"].numpy(), P.cls_entropy(z), rtol=5e-3, atol=1e-4)
@@ -245,7 +250,7 @@ def test_pipeline_from_host_features_matches_oracle(cuda):
     conds, sizes, _ = Sc.conformal_sets(val_sorted.cpu().numpy(), Sc.aps_cumsums(mean), 0.1)
     assert np.array_equal(out["conformal_mask"].numpy().astype(bool), conds)
     assert np.array_equal(out["conformal_sizes"].numpy(), sizes)
-    np.testing.assert_allclose(out["ece_result"].numpy()[0], Sc.expected_calibration_error(mean.argmax(-1), mean, t), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(out["ece"].numpy()[0], Sc.expected_calibration_error(mean.argmax(-1), mean, t), rtol=1e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("n,B,C,T", [(5, 7, 2, 6), (10, 129, 10, 30), (3, 33, 1000, 4), (4, 50, 37, 3), (2, 9, 1, 2), (6, 300, 1024, 2)])

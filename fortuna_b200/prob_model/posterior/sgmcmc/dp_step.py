@@ -25,6 +25,27 @@ def symmetric_empty(n: int, device) -> torch.Tensor:
     return symm_mem.empty(int(n), dtype=torch.float32, device=device)
 
 
+def gather_owned_ranges(vec: torch.Tensor, ranges, group=None) -> torch.Tensor:
+    """In place: everything outside this rank's ``ranges`` [(begin, end), ...] is dropped and one all-reduce (sum) leaves
+    on every rank the concatenation of all ranks' owned pieces (the ranges of the ranks partition the vector)."""
+    keep = torch.zeros_like(vec)
+    for lo, hi in ranges:
+        keep[lo:hi] = vec[lo:hi]
+    dist.all_reduce(keep, op=dist.ReduceOp.SUM, group=group)
+    vec.copy_(keep)
+    return vec
+
+
+def owned_ranges(scheme: str, n: int, world: int, rank: int, lens, offsets):
+    """Element ranges rank `rank` owns: "elems" = the exploration step's contiguous split, "tiles" = the sampling step's."""
+    if scheme == "elems":
+        return [ops.dp_elem_range(n, world, rank)]
+    if scheme != "tiles":
+        raise ValueError(scheme)
+    n_tiles = sum((((int(k) + 1) // 2) + ops._lib.TILE_PAIRS - 1) // ops._lib.TILE_PAIRS for k in lens)
+    return ops.dp_owned_elem_ranges(lens, offsets, ops.dp_tile_range(n_tiles, world, rank))
+
+
 class PeerReplicas:
     """The parameter replica and the gradient buffer of every rank, mapped into this rank's address space."""
 
@@ -55,22 +76,11 @@ class PeerReplicas:
     # SGLD changes, a chain checkpoint is written) the owned pieces are gathered: everything a rank does not own under
     # `scheme` is zeroed and one all-reduce (sum) leaves the complete vector on every rank.
     def owned_ranges(self, scheme: str, lens, offsets):
-        n = self.params.numel()
-        if scheme == "elems":
-            return [ops.dp_elem_range(n, self.world, self.rank)]
-        if scheme != "tiles":
-            raise ValueError(scheme)
-        n_tiles = sum((((int(k) + 1) // 2) + ops._lib.TILE_PAIRS - 1) // ops._lib.TILE_PAIRS for k in lens)
-        return ops.dp_owned_elem_ranges(lens, offsets, ops.dp_tile_range(n_tiles, self.world, self.rank))
+        return owned_ranges(scheme, self.params.numel(), self.world, self.rank, lens, offsets)
 
     def gather_owned(self, vec: torch.Tensor, scheme: str, lens, offsets, group=None) -> torch.Tensor:
         """In place: ``vec`` becomes the concatenation of every rank's owned pieces under ``scheme``."""
-        keep = torch.zeros_like(vec)
-        for lo, hi in self.owned_ranges(scheme, lens, offsets):
-            keep[lo:hi] = vec[lo:hi]
-        dist.all_reduce(keep, op=dist.ReduceOp.SUM, group=group)
-        vec.copy_(keep)
-        return vec
+        return gather_owned_ranges(vec, self.owned_ranges(scheme, lens, offsets), group)
 
     def step(self, momentum, precond_v, leaves, tiles, key_in, key_out, leaf_keys, hp, joint=None, tile_range=None):
         """barrier (all gradients written) -> fused step on the owned tiles -> barrier (all parameters landed)."""
@@ -96,6 +106,8 @@ class DataParallelStep:
     def __init__(self, lens: Sequence[int], offsets: Sequence[int], n: int, device, world: int, rank: int, group=None,
                  rmsprop: bool = False, seed: int = 0, multicast="auto"):
         self.world, self.rank, self.n = world, rank, int(n)
+        self.lens, self.offsets = [int(k) for k in lens], [int(o) for o in offsets]
+        self._v_scheme = None  # which split last advanced the preconditioner moments ("tiles" / "elems")
         self.params = symmetric_empty(self.n, device)
         self.grad = symmetric_empty(self.n, device)
         self.peers = PeerReplicas(self.params, self.grad, world, rank, group, multicast)
@@ -111,9 +123,25 @@ class DataParallelStep:
     def step(self, hp, joint: Optional[tuple] = None) -> None:
         """One sampler step of the whole job.  ``self.grad`` must hold this rank's gradient (written on the current
         stream); afterwards ``self.params`` holds the new parameters on every rank."""
+        self._sync_precond("tiles")
         self.peers.step(self.momentum, self.precond_v, self.leaves, self.tiles, self.key, self._key_next,
                         self._leaf_keys, hp, joint=joint, tile_range=self.tile_range)
         self.key, self._key_next = self._key_next, self.key
 
     def explore_step(self, hp, joint: Optional[tuple] = None) -> None:
+        self._sync_precond("elems")
         self.peers.explore_step(self.precond_v, hp, joint=joint)
+
+    def _sync_precond(self, scheme: str) -> None:
+        """The two phases of cyclical SGLD split the elements differently over the ranks and the RMSprop moments are
+        rank-local: on a phase change gather the pieces advanced under the previous split (see the integrator)."""
+        if self.precond_v is not None and self._v_scheme is not None and self._v_scheme != scheme:
+            self.peers.gather_owned(self.precond_v, self._v_scheme, self.lens, self.offsets)
+        self._v_scheme = scheme
+
+    def gather_state(self) -> None:
+        """Momentum and preconditioner moments whole on every rank (e.g. before a checkpoint)."""
+        self.peers.gather_owned(self.momentum, "tiles", self.lens, self.offsets)
+        if self.precond_v is not None and self._v_scheme is not None:
+            self.peers.gather_owned(self.precond_v, self._v_scheme, self.lens, self.offsets)
+            self._v_scheme = None

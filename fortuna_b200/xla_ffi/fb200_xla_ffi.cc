@@ -1,184 +1,537 @@
-// XLA-FFI shim over the C ABI of include/fortuna_b200.h - the binding north_star names ("thin jax.ffi
-// custom-call bindings").  NOT built by fortuna_b200/build.py: it needs the XLA FFI headers that ship inside
-// jaxlib (jaxlib/include/xla/ffi/api/ffi.h), and jax/jaxlib cannot be installed in the build container or on
-// the GPU box.  Where jaxlib is present:
+// XLA-FFI shim over the C ABI of include/fortuna_b200.h - the binding north_star names ("thin jax.ffi custom-call
+// bindings").  One handler per hot-path entry point the Python mirror (fortuna_b200/ops.py) calls: PRNG, the sampler
+// steps, the sample bank, the last-layer contraction, the single-pass reductions (plain, fused sets, wide, shard,
+// finalise), the scoring kernels and the ECE.  Every handler only unpacks buffers / attributes and forwards to ONE
+// fb200_* call on XLA's stream; no arithmetic lives here.  Conventions:
+//   * an OPTIONAL input (targets, log_temp, bias, sample_idx, ...) is passed as a zero-element buffer;
+//   * an unwanted OUTPUT of the reduction kernels is a zero-element result buffer (XLA still needs a result slot);
+//   * logits may be f32 or bf16 (AnyBuffer); scalars the reference passes as Python numbers are attributes;
+//   * in-place state (params, momentum, preconditioner moments) uses input_output_aliases on the Python side, and a
+//     copy first when XLA could not alias.
 //
-//   g++ -O2 -fPIC -shared -std=c++17 fb200_xla_ffi.cc -I$(python -c "import jaxlib,os;print(os.path.join(os.path.dirname(jaxlib.__file__),'include'))") \
-//       -I../../include -I/usr/local/cuda/include -L../lib -lfortuna_b200 -Wl,-rpath,'$ORIGIN/../lib' -o libfb200_xla_ffi.so
+// NOT built by fortuna_b200/build.py: it needs the XLA FFI headers that ship inside jaxlib
+// (jaxlib/include/xla/ffi/api/ffi.h), and jax / jaxlib cannot be installed in the build container or on the GPU box
+// (SURVEY.md section 0).  What IS checked here: scripts/check_xla_ffi_syntax.sh compiles this file with
+// `g++ -fsyntax-only` against mock/xla/ffi/api/ffi.h, whose Binding::To() static_asserts every handler against its
+// binding - a syntax / signature check, not an integration test.  Where jaxlib is present:
 //
-// and register the handlers from Python with jax_bindings.py (same directory).  Every handler only unpacks
-// buffers/attributes and forwards to ONE fb200_* call on XLA's stream; no arithmetic lives here.
+//   JAXLIB_INC=$(python -c "import jaxlib,os;print(os.path.join(os.path.dirname(jaxlib.__file__),'include'))")
+//   g++ -O2 -fPIC -shared -std=c++17 fb200_xla_ffi.cc -I$JAXLIB_INC -I../../include -I/usr/local/cuda/include
+//       -L../lib -lfortuna_b200 -Wl,-rpath,'$ORIGIN/../lib' -o libfb200_xla_ffi.so
+//
+// and register the handlers from Python with jax_bindings.py (same directory).
 #if __has_include("xla/ffi/api/ffi.h")
 #include <cuda_runtime_api.h>
 
 #include <cstdint>
+#include <string>
 
 #include "fortuna_b200.h"
 #include "xla/ffi/api/ffi.h"
 
 namespace ffi = xla::ffi;
 
-static ffi::Error Check(int rc, const char* what) {
+namespace {
+
+ffi::Error Check(int rc, const char* what) {
   if (rc == 0) return ffi::Error::Success();
   return ffi::Error(rc < 0 ? ffi::ErrorCode::kInvalidArgument : ffi::ErrorCode::kInternal,
                     std::string(what) + ": " + fb200_error_string(rc));
 }
 
-// ---- K1: one SGHMC / SGLD step.  params, momentum, precond_v are donated (input_output_aliases) so the
-// update is in place; key -> new key.  Replaces sghmc_integrator.update_fn + optax.apply_updates.
-static ffi::Error SgmcmcStep(cudaStream_t stream, ffi::Buffer<ffi::F32> params, ffi::Buffer<ffi::F32> grad,
-                             ffi::Buffer<ffi::F32> momentum, ffi::Buffer<ffi::F32> precond_v,
-                             ffi::Buffer<ffi::S64> leaves, ffi::Buffer<ffi::S32> tiles, ffi::Buffer<ffi::U32> key,
-                             ffi::ResultBuffer<ffi::F32> params_out, ffi::ResultBuffer<ffi::F32> momentum_out,
-                             ffi::ResultBuffer<ffi::F32> precond_out, ffi::ResultBuffer<ffi::U32> key_out,
-                             ffi::ResultBuffer<ffi::U32> leaf_keys_ws, float step_size, double momentum_decay,
-                             int32_t rmsprop, double rms_alpha, double rms_eps) {
-  // aliasing makes *_out the same buffers as the inputs; when XLA could not alias, copy first
+template <typename B>
+int Dim(const B& b, int i) {
+  return static_cast<int>(b.dimensions()[i]);
+}
+// optional input / unwanted output: zero elements -> NULL
+template <ffi::DataType dt>
+ffi::NativeType<dt>* Opt(const ffi::Buffer<dt>& b) {
+  return b.element_count() ? b.typed_data() : nullptr;
+}
+template <ffi::DataType dt>
+ffi::NativeType<dt>* Opt(ffi::ResultBuffer<dt>& b) {
+  return b->element_count() ? b->typed_data() : nullptr;
+}
+// f32 / bf16 tensors arrive as AnyBuffer
+int DTypeOf(const ffi::AnyBuffer& b) {
+  if (b.element_type() == ffi::F32) return FB200_F32;
+  if (b.element_type() == ffi::BF16) return FB200_BF16;
+  return -1;
+}
+ffi::Error BadDType(const char* what) {
+  return ffi::Error(ffi::ErrorCode::kInvalidArgument, std::string(what) + ": expected a float32 or bfloat16 tensor");
+}
+void CopyIfNotAliased(const void* src, void* dst, size_t bytes, cudaStream_t s) {
+  if (src != dst && bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
+}
+
+using F32 = ffi::Buffer<ffi::F32>;
+using F64 = ffi::Buffer<ffi::F64>;
+using S32 = ffi::Buffer<ffi::S32>;
+using S64 = ffi::Buffer<ffi::S64>;
+using U32 = ffi::Buffer<ffi::U32>;
+using U64 = ffi::Buffer<ffi::U64>;
+using U8 = ffi::Buffer<ffi::U8>;
+using BF16 = ffi::Buffer<ffi::BF16>;
+using Any = ffi::AnyBuffer;
+using RF32 = ffi::ResultBuffer<ffi::F32>;
+using RF64 = ffi::ResultBuffer<ffi::F64>;
+using RS32 = ffi::ResultBuffer<ffi::S32>;
+using RU32 = ffi::ResultBuffer<ffi::U32>;
+using RU8 = ffi::ResultBuffer<ffi::U8>;
+using RBF16 = ffi::ResultBuffer<ffi::BF16>;
+using RAny = ffi::Result<ffi::AnyBuffer>;
+using Stream = ffi::PlatformStream<cudaStream_t>;
+
+// the reduction kernels' output struct from eleven result slots (zero elements = not wanted) + the three ECE row inputs
+struct ClsOuts {
+  RF32 &mean, &alea_var, &epi_var, &variance, &std_, &entropy, &alea_ent, &epi_ent, &log_prob, &ens_log_prob, &confidence,
+      &brier;
+  RS32& mode;
+  fb200_cls_outputs_t get() {
+    fb200_cls_outputs_t o{};
+    o.mean = Opt(mean);
+    o.aleatoric_variance = Opt(alea_var);
+    o.epistemic_variance = Opt(epi_var);
+    o.variance = Opt(variance);
+    o.std = Opt(std_);
+    o.mode = Opt(mode);
+    o.entropy = Opt(entropy);
+    o.aleatoric_entropy = Opt(alea_ent);
+    o.epistemic_entropy = Opt(epi_ent);
+    o.log_prob = Opt(log_prob);
+    o.ensemble_log_prob = Opt(ens_log_prob);
+    o.confidence = Opt(confidence);
+    o.brier_terms = Opt(brier);
+    return o;
+  }
+};
+#define FB200_CLS_OUT_PARAMS                                                                                          \
+  RF32 mean, RF32 alea_var, RF32 epi_var, RF32 variance, RF32 std_, RS32 mode, RF32 entropy, RF32 alea_ent, RF32 epi_ent, \
+      RF32 log_prob, RF32 ens_log_prob, RF32 confidence, RF32 brier
+#define FB200_CLS_OUT_STRUCT \
+  ClsOuts{mean, alea_var, epi_var, variance, std_, entropy, alea_ent, epi_ent, log_prob, ens_log_prob, confidence, brier, mode}.get()
+#define FB200_CLS_OUT_BINDING                                                                                       \
+  .Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<S32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>() \
+      .Ret<F32>().Ret<F32>()
+
+}  // namespace
+
+// ================================================================================================ PRNG (jax.random)
+// jax.random.split(key, num) - fortuna/utils/random.py:11-14, 38-49
+static ffi::Error Split(cudaStream_t s, U32 key, RU32 out) {
+  return Check(fb200_threefry_split(key.typed_data(), Dim(*out, 0), out->typed_data(), s), "fb200_threefry_split");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_split, Split, ffi::Ffi::Bind().Ctx<Stream>().Arg<U32>().Ret<U32>());
+
+// jax.random.fold_in(key, data) - fortuna/training/trainer.py:676-680
+static ffi::Error FoldIn(cudaStream_t s, U32 key, RU32 out, int64_t data) {
+  return Check(fb200_threefry_fold_in(key.typed_data(), static_cast<uint32_t>(data), out->typed_data(), s),
+               "fb200_threefry_fold_in");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_fold_in, FoldIn, ffi::Ffi::Bind().Ctx<Stream>().Arg<U32>().Ret<U32>().Attr<int64_t>("data"));
+
+static ffi::Error RandomBits(cudaStream_t s, U32 key, RU32 out) {
+  return Check(fb200_random_bits(key.typed_data(), static_cast<int64_t>(out->element_count()), out->typed_data(), s),
+               "fb200_random_bits");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_random_bits, RandomBits, ffi::Ffi::Bind().Ctx<Stream>().Arg<U32>().Ret<U32>());
+
+// jax.random.normal(key, shape, float32) - fortuna/utils/random.py:17-23
+static ffi::Error RandomNormal(cudaStream_t s, U32 key, RF32 out) {
+  return Check(fb200_random_normal(key.typed_data(), static_cast<int64_t>(out->element_count()), out->typed_data(), s),
+               "fb200_random_normal");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_random_normal, RandomNormal, ffi::Ffi::Bind().Ctx<Stream>().Arg<U32>().Ret<F32>());
+
+// idx[s] = choice(split(key, S)[s], n_samples) - predictive/base.py:632 + sgmcmc_posterior.py:48-52
+static ffi::Error SampleIndices(cudaStream_t s, U32 key, RS32 idx, int32_t n_samples) {
+  return Check(fb200_sample_indices(key.typed_data(), Dim(*idx, 0), n_samples, idx->typed_data(), s), "fb200_sample_indices");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_sample_indices, SampleIndices,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<U32>().Ret<S32>().Attr<int32_t>("n_samples"));
+
+// idx[i] = choice(keys[i], n_samples)
+static ffi::Error ChoiceFromKeys(cudaStream_t s, U32 keys, RS32 idx, int32_t n_samples) {
+  return Check(fb200_choice_from_keys(keys.typed_data(), Dim(keys, 0), n_samples, idx->typed_data(), s), "fb200_choice_from_keys");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_choice_from_keys, ChoiceFromKeys,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<U32>().Ret<S32>().Attr<int32_t>("n_samples"));
+
+// ================================================================================================ K1 sampler
+// One SGHMC / SGLD step with TrainState.apply_gradients fused (sghmc_integrator.py:59-92 + optax.apply_updates).
+// params, momentum, precond_v are donated (input_output_aliases {0:0, 2:1, 3:2}); key -> new key.
+static ffi::Error SgmcmcStep(cudaStream_t s, F32 params, F32 grad, F32 momentum, F32 precond_v, S64 leaves, S32 tiles, U32 key,
+                             RF32 params_out, RF32 momentum_out, RF32 precond_out, RU32 key_out, RU32 leaf_keys_ws,
+                             float step_size, double momentum_decay, int32_t zero_momentum, int32_t rmsprop, double rms_alpha,
+                             double rms_eps) {
   const size_t n = grad.element_count();
-  auto same_or_copy = [&](const float* src, float* dst) {
-    if (src != dst) cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, stream);
-  };
-  same_or_copy(params.typed_data(), params_out->typed_data());
-  same_or_copy(momentum.typed_data(), momentum_out->typed_data());
-  if (rmsprop) same_or_copy(precond_v.typed_data(), precond_out->typed_data());
-  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, 0, rmsprop, rms_alpha, rms_eps};
-  const int n_leaves = static_cast<int>(leaves.dimensions()[0]);
-  const int64_t n_tiles = tiles.dimensions()[0];
+  CopyIfNotAliased(params.typed_data(), params_out->typed_data(), n * 4, s);
+  CopyIfNotAliased(momentum.typed_data(), momentum_out->typed_data(), n * 4, s);
+  if (rmsprop) CopyIfNotAliased(precond_v.typed_data(), precond_out->typed_data(), n * 4, s);
+  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps};
   return Check(fb200_sgmcmc_step_f32(params_out->typed_data(), grad.typed_data(), momentum_out->typed_data(),
-                                     rmsprop ? precond_out->typed_data() : nullptr, nullptr, (int64_t)n,
-                                     reinterpret_cast<const fb200_leaf_t*>(leaves.typed_data()), n_leaves,
-                                     reinterpret_cast<const fb200_tile_t*>(tiles.typed_data()), n_tiles,
-                                     key.typed_data(), key_out->typed_data(), leaf_keys_ws->typed_data(), &hp, stream),
+                                     rmsprop ? precond_out->typed_data() : nullptr, nullptr, static_cast<int64_t>(n),
+                                     reinterpret_cast<const fb200_leaf_t*>(leaves.typed_data()), Dim(leaves, 0),
+                                     reinterpret_cast<const fb200_tile_t*>(tiles.typed_data()), tiles.dimensions()[0],
+                                     key.typed_data(), key_out->typed_data(), leaf_keys_ws->typed_data(), &hp, s),
                "fb200_sgmcmc_step_f32");
 }
+#define FB200_HP_ATTRS                                                                                                  \
+  .Attr<float>("step_size").Attr<double>("momentum_decay").Attr<int32_t>("zero_momentum").Attr<int32_t>("rmsprop")      \
+      .Attr<double>("rms_alpha").Attr<double>("rms_eps")
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_sgmcmc_step, SgmcmcStep,
-                              ffi::Ffi::Bind()
-                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::S64>>()
-                                  .Arg<ffi::Buffer<ffi::S32>>()
-                                  .Arg<ffi::Buffer<ffi::U32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::U32>>()
-                                  .Ret<ffi::Buffer<ffi::U32>>()
-                                  .Attr<float>("step_size")
-                                  .Attr<double>("momentum_decay")
-                                  .Attr<int32_t>("rmsprop")
-                                  .Attr<double>("rms_alpha")
-                                  .Attr<double>("rms_eps"));
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<S64>().Arg<S32>()
+                                  .Arg<U32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<U32>().Ret<U32>() FB200_HP_ATTRS);
 
-// ---- K2: last-layer logits for S samples (bf16 operands, K-major weights) -> [S,B,C] float32
-static ffi::Error LastLayer(cudaStream_t stream, ffi::Buffer<ffi::BF16> x, ffi::Buffer<ffi::BF16> wt,
-                            ffi::Buffer<ffi::F32> bias, ffi::Buffer<ffi::F32> log_temp,
-                            ffi::Buffer<ffi::S32> sample_idx, ffi::ResultBuffer<ffi::F32> out) {
-  const int B = (int)x.dimensions()[0], D = (int)x.dimensions()[1];
-  const int n = (int)wt.dimensions()[0], C = (int)wt.dimensions()[1];
-  const int S = (int)sample_idx.dimensions()[0];
-  return Check(fb200_last_layer_logits(x.untyped_data(), wt.untyped_data(), bias.typed_data(), log_temp.typed_data(),
-                                       sample_idx.typed_data(), n, out->untyped_data(), S, B, D, C, FB200_BF16,
-                                       FB200_F32, FB200_W_SCD, /*path=*/0, stream),
+// The same with the log-joint gradient assembled in the kernel (joint/base.py:54-122, prior/gaussian.py:29-32):
+// grad = gradient of the batch log-likelihood SUM; also returns sum(theta^2) of the pre-update parameters.
+static ffi::Error SgmcmcStepJoint(cudaStream_t s, F32 params, F32 grad, F32 momentum, F32 precond_v, S64 leaves, S32 tiles,
+                                  U32 key, RF32 params_out, RF32 momentum_out, RF32 precond_out, RU32 key_out,
+                                  RU32 leaf_keys_ws, RF64 sq_ws, RF64 theta_sq, float step_size, double momentum_decay,
+                                  int32_t zero_momentum, int32_t rmsprop, double rms_alpha, double rms_eps, float lik_scale,
+                                  float prior_prec) {
+  const size_t n = grad.element_count();
+  CopyIfNotAliased(params.typed_data(), params_out->typed_data(), n * 4, s);
+  CopyIfNotAliased(momentum.typed_data(), momentum_out->typed_data(), n * 4, s);
+  if (rmsprop) CopyIfNotAliased(precond_v.typed_data(), precond_out->typed_data(), n * 4, s);
+  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps};
+  fb200_joint_grad_t jg{lik_scale, prior_prec};
+  return Check(fb200_sgmcmc_step_joint_f32(params_out->typed_data(), grad.typed_data(), momentum_out->typed_data(),
+                                           rmsprop ? precond_out->typed_data() : nullptr, static_cast<int64_t>(n),
+                                           reinterpret_cast<const fb200_leaf_t*>(leaves.typed_data()), Dim(leaves, 0),
+                                           reinterpret_cast<const fb200_tile_t*>(tiles.typed_data()), tiles.dimensions()[0],
+                                           key.typed_data(), key_out->typed_data(), leaf_keys_ws->typed_data(), &hp, &jg,
+                                           Opt(sq_ws), Opt(theta_sq), s),
+               "fb200_sgmcmc_step_joint_f32");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_sgmcmc_step_joint, SgmcmcStepJoint,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<S64>().Arg<S32>()
+                                  .Arg<U32>().Ret<F32>().Ret<F32>().Ret<F32>().Ret<U32>().Ret<U32>().Ret<F64>().Ret<F64>()
+                                      FB200_HP_ATTRS.Attr<float>("lik_scale").Attr<float>("prior_prec"));
+
+// Exploration phase of cyclical SGLD (cyclical_sgld_integrator.py:65-84): preconditioned ascent step, no noise.
+static ffi::Error SgdExploreStep(cudaStream_t s, F32 params, F32 grad, F32 precond_v, RF32 params_out, RF32 precond_out,
+                                 float step_size, double momentum_decay, int32_t zero_momentum, int32_t rmsprop,
+                                 double rms_alpha, double rms_eps) {
+  const size_t n = grad.element_count();
+  CopyIfNotAliased(params.typed_data(), params_out->typed_data(), n * 4, s);
+  if (rmsprop) CopyIfNotAliased(precond_v.typed_data(), precond_out->typed_data(), n * 4, s);
+  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps};
+  return Check(fb200_sgd_explore_step_f32(params_out->typed_data(), grad.typed_data(),
+                                          rmsprop ? precond_out->typed_data() : nullptr, nullptr, static_cast<int64_t>(n), &hp, s),
+               "fb200_sgd_explore_step_f32");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_sgd_explore_step, SgdExploreStep,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Ret<F32>().Ret<F32>() FB200_HP_ATTRS);
+
+static ffi::Error SgdExploreStepJoint(cudaStream_t s, F32 params, F32 grad, F32 precond_v, RF32 params_out, RF32 precond_out,
+                                      RF64 sq_ws, RF64 theta_sq, float step_size, double momentum_decay, int32_t zero_momentum,
+                                      int32_t rmsprop, double rms_alpha, double rms_eps, float lik_scale, float prior_prec) {
+  const size_t n = grad.element_count();
+  CopyIfNotAliased(params.typed_data(), params_out->typed_data(), n * 4, s);
+  if (rmsprop) CopyIfNotAliased(precond_v.typed_data(), precond_out->typed_data(), n * 4, s);
+  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps};
+  fb200_joint_grad_t jg{lik_scale, prior_prec};
+  return Check(fb200_sgd_explore_step_joint_f32(params_out->typed_data(), grad.typed_data(),
+                                                rmsprop ? precond_out->typed_data() : nullptr, static_cast<int64_t>(n), &hp, &jg,
+                                                Opt(sq_ws), Opt(theta_sq), s),
+               "fb200_sgd_explore_step_joint_f32");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_sgd_explore_step_joint, SgdExploreStepJoint,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Ret<F32>().Ret<F32>().Ret<F64>()
+                                  .Ret<F64>() FB200_HP_ATTRS.Attr<float>("lik_scale").Attr<float>("prior_prec"));
+
+// sample bank row write (sgmcmc_posterior_state_repository.py:39-54): bank is donated
+static ffi::Error BankPut(cudaStream_t s, F32 bank, F32 src, RF32 bank_out, int32_t row) {
+  CopyIfNotAliased(bank.typed_data(), bank_out->typed_data(), bank.size_bytes(), s);
+  return Check(fb200_bank_put_f32(bank_out->typed_data(), bank.dimensions()[1], row, src.typed_data(), s), "fb200_bank_put_f32");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_bank_put, BankPut,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Ret<F32>().Attr<int32_t>("row"));
+
+// ================================================================================================ K2 last layer
+// calibrated logits of S drawn samples: x [B,D], w [n,C,D] (K-major) or [n,D,C], bias [n,C], log_temp [1], idx [S]
+static ffi::Error LastLayer(cudaStream_t s, Any x, Any w, F32 bias, F32 log_temp, S32 sample_idx, RAny out, int32_t w_layout,
+                            int32_t path) {
+  const int in_dt = DTypeOf(x), out_dt = DTypeOf(*out);
+  if (in_dt < 0 || out_dt < 0 || DTypeOf(w) != in_dt) return BadDType("fb200_xla_last_layer");
+  const int S = Dim(*out, 0), B = Dim(*out, 1), C = Dim(*out, 2), D = Dim(x, 1);
+  return Check(fb200_last_layer_logits(x.untyped_data(), w.untyped_data(), Opt(bias), Opt(log_temp), Opt(sample_idx), Dim(w, 0),
+                                       out->untyped_data(), S, B, D, C, in_dt, out_dt, w_layout, path, s),
                "fb200_last_layer_logits");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_last_layer, LastLayer,
-                              ffi::Ffi::Bind()
-                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
-                                  .Arg<ffi::Buffer<ffi::BF16>>()
-                                  .Arg<ffi::Buffer<ffi::BF16>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::S32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>());
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Arg<Any>().Arg<F32>().Arg<F32>().Arg<S32>().Ret<Any>()
+                                  .Attr<int32_t>("w_layout").Attr<int32_t>("path"));
 
-// ---- K3/K4: all classification reductions of one [S,B,C] logits tensor in one pass
-static ffi::Error BmaReduceCls(cudaStream_t stream, ffi::Buffer<ffi::F32> logits, ffi::Buffer<ffi::S32> targets,
-                               ffi::ResultBuffer<ffi::F32> mean, ffi::ResultBuffer<ffi::F32> alea_var,
-                               ffi::ResultBuffer<ffi::F32> epi_var, ffi::ResultBuffer<ffi::F32> entropy,
-                               ffi::ResultBuffer<ffi::F32> alea_ent, ffi::ResultBuffer<ffi::F32> epi_ent,
-                               ffi::ResultBuffer<ffi::F32> log_prob, ffi::ResultBuffer<ffi::S32> mode) {
-  const int S = (int)logits.dimensions()[0], B = (int)logits.dimensions()[1], C = (int)logits.dimensions()[2];
-  fb200_cls_outputs_t o{};
-  o.mean = mean->typed_data();
-  o.aleatoric_variance = alea_var->typed_data();
-  o.epistemic_variance = epi_var->typed_data();
-  o.entropy = entropy->typed_data();
-  o.aleatoric_entropy = alea_ent->typed_data();
-  o.epistemic_entropy = epi_ent->typed_data();
-  o.log_prob = log_prob->typed_data();
-  o.mode = mode->typed_data();
-  return Check(fb200_bma_reduce_cls(logits.untyped_data(), FB200_F32, nullptr, targets.typed_data(), S, B, C, &o, stream),
-               "fb200_bma_reduce_cls");
+// the same with the softmax / log-softmax epilogue and / or the row logsumexp (prob_output_layer/classification.py:25-69)
+static ffi::Error LastLayerEx(cudaStream_t s, Any x, Any w, F32 bias, F32 log_temp, S32 sample_idx, RAny out, RF32 lse, RU8 ws,
+                              int32_t w_layout, int32_t epilogue) {
+  const int in_dt = DTypeOf(x), out_dt = DTypeOf(*out);
+  if (in_dt < 0 || out_dt < 0 || DTypeOf(w) != in_dt) return BadDType("fb200_xla_last_layer_ex");
+  const int S = Dim(*out, 0), B = Dim(*out, 1), C = Dim(*out, 2), D = Dim(x, 1);
+  return Check(fb200_last_layer_logits_ex(x.untyped_data(), w.untyped_data(), Opt(bias), Opt(log_temp), Opt(sample_idx),
+                                          Dim(w, 0), out->untyped_data(), S, B, D, C, in_dt, out_dt, w_layout, epilogue,
+                                          Opt(lse), Opt(ws), ws->size_bytes(), s),
+               "fb200_last_layer_logits_ex");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_last_layer_ex, LastLayerEx,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Arg<Any>().Arg<F32>().Arg<F32>().Arg<S32>().Ret<Any>()
+                                  .Ret<F32>().Ret<U8>().Attr<int32_t>("w_layout").Attr<int32_t>("epilogue"));
+
+// log_prob / ensemble_log_prob from logits + their row logsumexp (predictive/base.py:104-128, 179-203)
+static ffi::Error LogProbFromLse(cudaStream_t s, Any logits, F32 lse, S32 targets, RF32 ens, RF32 log_prob) {
+  const int dt = DTypeOf(logits);
+  if (dt < 0) return BadDType("fb200_xla_log_prob_from_lse");
+  return Check(fb200_log_prob_from_lse(logits.untyped_data(), dt, lse.typed_data(), targets.typed_data(), Dim(logits, 0),
+                                       Dim(logits, 1), Dim(logits, 2), Opt(ens), log_prob->typed_data(), s),
+               "fb200_log_prob_from_lse");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_log_prob_from_lse, LogProbFromLse,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Arg<F32>().Arg<S32>().Ret<F32>().Ret<F32>());
+
+// W [S,D,C] (flax nn.Dense layout) -> K-major bf16 [S,C,D] for the tcgen05 path, once per sample bank
+static ffi::Error TransposeW(cudaStream_t s, Any w, RBF16 wt) {
+  const int dt = DTypeOf(w);
+  if (dt < 0) return BadDType("fb200_xla_transpose_w");
+  return Check(fb200_transpose_w_bf16(w.untyped_data(), dt, wt->untyped_data(), Dim(w, 0), Dim(w, 1), Dim(w, 2), s),
+               "fb200_transpose_w_bf16");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_transpose_w, TransposeW, ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Ret<BF16>());
+
+// in-place row softmax / log_softmax / temperature scaling (+ row logsumexp); z is donated
+static ffi::Error SoftmaxRows(cudaStream_t s, Any z, F32 log_temp, RAny z_out, RF32 lse, int32_t epilogue) {
+  const int dt = DTypeOf(z);
+  if (dt < 0) return BadDType("fb200_xla_softmax_rows");
+  CopyIfNotAliased(z.untyped_data(), z_out->untyped_data(), z.size_bytes(), s);
+  const int nd = static_cast<int>(z.dimensions().size());
+  const int C = Dim(z, nd - 1);
+  return Check(fb200_softmax_rows(z_out->untyped_data(), dt, static_cast<int64_t>(z.element_count() / (C ? C : 1)), C, epilogue,
+                                  Opt(log_temp), Opt(lse), s),
+               "fb200_softmax_rows");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_softmax_rows, SoftmaxRows,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Arg<F32>().Ret<Any>().Ret<F32>().Attr<int32_t>("epilogue"));
+
+// ================================================================================================ K3 / K4 reductions
+// every classification statistic of one [S,B,C] logits tensor in one pass (predictive/base.py:624-836,
+// predictive/classification.py:71-432); C > 1024 takes the two-pass kernel with `ws` = S*B floats
+static ffi::Error BmaReduceCls(cudaStream_t s, Any logits, F32 log_temp, S32 targets, FB200_CLS_OUT_PARAMS, RU8 ws) {
+  const int dt = DTypeOf(logits);
+  if (dt < 0) return BadDType("fb200_xla_bma_reduce_cls");
+  const int S = Dim(logits, 0), B = Dim(logits, 1), C = Dim(logits, 2);
+  const fb200_cls_outputs_t o = FB200_CLS_OUT_STRUCT;
+  if (C > 1024)
+    return Check(fb200_bma_reduce_cls_wide(logits.untyped_data(), dt, Opt(log_temp), Opt(targets), S, B, C, &o, Opt(ws),
+                                           ws->size_bytes(), s),
+                 "fb200_bma_reduce_cls_wide");
+  return Check(fb200_bma_reduce_cls(logits.untyped_data(), dt, Opt(log_temp), Opt(targets), S, B, C, &o, s), "fb200_bma_reduce_cls");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_bma_reduce_cls, BmaReduceCls,
-                              ffi::Ffi::Bind()
-                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::S32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::S32>>());
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Arg<F32>().Arg<S32>() FB200_CLS_OUT_BINDING.Ret<U8>());
 
-// ---- K5: APS scores (targets rank-0 buffer of size B, or size 0 for "every class")
-static ffi::Error ApsScores(cudaStream_t stream, ffi::Buffer<ffi::F32> probs, ffi::Buffer<ffi::S32> targets,
-                            ffi::ResultBuffer<ffi::F32> scores) {
-  const int B = (int)probs.dimensions()[0], C = (int)probs.dimensions()[1];
-  const int32_t* t = targets.element_count() ? targets.typed_data() : nullptr;
-  return Check(fb200_aps_scores(probs.typed_data(), t, B, C, scores->typed_data(), nullptr, stream), "fb200_aps_scores");
+// the reductions + the APS conformal sets of the mean row (adaptive_prediction.py:11-22, conformal/classification/base.py:45-82)
+static ffi::Error BmaReduceClsSets(cudaStream_t s, Any logits, F32 log_temp, S32 targets, F32 val_sorted, FB200_CLS_OUT_PARAMS,
+                                   RU8 mask, RS32 sizes, RU8 ws, float threshold) {
+  const int dt = DTypeOf(logits);
+  if (dt < 0) return BadDType("fb200_xla_bma_reduce_cls_sets");
+  const fb200_cls_outputs_t o = FB200_CLS_OUT_STRUCT;
+  return Check(fb200_bma_reduce_cls_sets(logits.untyped_data(), dt, Opt(log_temp), Opt(targets), Dim(logits, 0), Dim(logits, 1),
+                                         Dim(logits, 2), &o, val_sorted.typed_data(), Dim(val_sorted, 0), threshold,
+                                         mask->typed_data(), Opt(sizes), Opt(ws), ws->size_bytes(), s),
+               "fb200_bma_reduce_cls_sets");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_bma_reduce_cls_sets, BmaReduceClsSets,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Arg<F32>().Arg<S32>().Arg<F32>() FB200_CLS_OUT_BINDING
+                                  .Ret<U8>().Ret<S32>().Ret<U8>().Attr<float>("threshold"));
+
+// S-sharded mode: this rank's partial sums, row by row, into the owners' slots (peer or local memory)
+static ffi::Error BmaReduceClsShard(cudaStream_t s, Any logits, F32 log_temp, S32 targets, U64 slot_ptrs, RF32 ens_log_prob,
+                                    int32_t rank) {
+  const int dt = DTypeOf(logits);
+  if (dt < 0) return BadDType("fb200_xla_bma_reduce_cls_shard");
+  return Check(fb200_bma_reduce_cls_shard(logits.untyped_data(), dt, Opt(log_temp), Opt(targets), Dim(logits, 0), Dim(logits, 1),
+                                          Dim(logits, 2), Dim(slot_ptrs, 0), rank, slot_ptrs.typed_data(), Opt(ens_log_prob), s),
+               "fb200_bma_reduce_cls_shard");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_bma_reduce_cls_shard, BmaReduceClsShard,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Arg<F32>().Arg<S32>().Arg<U64>().Ret<F32>()
+                                  .Attr<int32_t>("rank"));
+
+// ... and the owners' finalisation of the received slots [n_src, rows, 2C + 4]
+static ffi::Error BmaFinalizeSlots(cudaStream_t s, F32 slots, S32 targets, FB200_CLS_OUT_PARAMS, int32_t n_classes,
+                                   int32_t s_total) {
+  const fb200_cls_outputs_t o = FB200_CLS_OUT_STRUCT;
+  return Check(fb200_bma_finalize_cls_slots(slots.typed_data(), Dim(slots, 0), Dim(slots, 1), n_classes, s_total, &o,
+                                            Opt(targets), s),
+               "fb200_bma_finalize_cls_slots");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_bma_finalize_cls_slots, BmaFinalizeSlots,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<S32>() FB200_CLS_OUT_BINDING
+                                  .Attr<int32_t>("n_classes").Attr<int32_t>("s_total"));
+
+// Predictive.variance / .std: aleatoric + epistemic estimates that may come from different draws (predictive/base.py:838-944)
+static ffi::Error VarianceCombine(cudaStream_t s, F32 aleatoric, F32 epistemic, RF32 variance, RF32 std_) {
+  return Check(fb200_variance_combine(aleatoric.typed_data(), Opt(epistemic), static_cast<int64_t>(aleatoric.element_count()),
+                                      Opt(variance), Opt(std_), s),
+               "fb200_variance_combine");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_variance_combine, VarianceCombine,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Ret<F32>().Ret<F32>());
+
+// regression maps over [S,B,2d] = [mu | log var] (prob_output_layer/regression.py:30-74)
+static ffi::Error BmaReduceReg(cudaStream_t s, F32 outputs, F32 log_temp, F32 targets, RF32 mean, RF32 alea_var, RF32 epi_var,
+                               RF32 variance, RF32 std_, RF32 log_prob, RF32 ens_log_prob) {
+  fb200_reg_outputs_t o{Opt(mean), Opt(alea_var), Opt(epi_var), Opt(variance), Opt(std_), Opt(log_prob), Opt(ens_log_prob)};
+  return Check(fb200_bma_reduce_reg(outputs.typed_data(), Opt(log_temp), Opt(targets), Dim(outputs, 0), Dim(outputs, 1),
+                                    Dim(outputs, 2) / 2, &o, s),
+               "fb200_bma_reduce_reg");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_bma_reduce_reg, BmaReduceReg,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Ret<F32>().Ret<F32>().Ret<F32>()
+                                  .Ret<F32>().Ret<F32>().Ret<F32>().Ret<F32>());
+
+// ================================================================================================ K5 - K9 scoring
+// adaptive_prediction.py:11-22 (targets given: [B]) / conformal/classification/base.py:72-82 (all classes: [B,C])
+static ffi::Error ApsScores(cudaStream_t s, F32 probs, S32 targets, RF32 scores, RS32 perm) {
+  return Check(fb200_aps_scores(probs.typed_data(), Opt(targets), Dim(probs, 0), Dim(probs, 1), scores->typed_data(), Opt(perm), s),
+               "fb200_aps_scores");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_aps_scores, ApsScores,
-                              ffi::Ffi::Bind()
-                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::S32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>());
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<S32>().Ret<F32>().Ret<S32>());
 
-// ---- K6: rank-count conformal sets against sorted validation scores
-static ffi::Error ConformalSets(cudaStream_t stream, ffi::Buffer<ffi::F32> val_sorted, ffi::Buffer<ffi::F32> test,
-                                ffi::ResultBuffer<ffi::U8> mask, ffi::ResultBuffer<ffi::S32> sizes, float threshold) {
-  const int B = (int)test.dimensions()[0], C = (int)test.dimensions()[1];
-  return Check(fb200_conformal_sets(val_sorted.typed_data(), (int)val_sorted.element_count(), test.typed_data(), B, C,
-                                    threshold, mask->typed_data(), sizes->typed_data(), stream),
+// simple_prediction.py:10-18
+static ffi::Error SimpleScores(cudaStream_t s, F32 probs, S32 targets, RF32 scores) {
+  return Check(fb200_simple_scores(probs.typed_data(), Opt(targets), Dim(probs, 0), Dim(probs, 1), scores->typed_data(), s),
+               "fb200_simple_scores");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_simple_scores, SimpleScores, ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<S32>().Ret<F32>());
+
+// conformal/classification/base.py:45-64: mask[b,c] = count(val > score) < threshold, sizes = row sums
+static ffi::Error ConformalSets(cudaStream_t s, F32 val_sorted, F32 scores, RU8 mask, RS32 sizes, float threshold) {
+  return Check(fb200_conformal_sets(val_sorted.typed_data(), Dim(val_sorted, 0), scores.typed_data(), Dim(scores, 0),
+                                    Dim(scores, 1), threshold, mask->typed_data(), Opt(sizes), s),
                "fb200_conformal_sets");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_conformal_sets, ConformalSets,
-                              ffi::Ffi::Bind()
-                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::U8>>()
-                                  .Ret<ffi::Buffer<ffi::S32>>()
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Ret<U8>().Ret<S32>().Attr<float>("threshold"));
+
+// APS scores of every class + the sets, one kernel (scores optional)
+static ffi::Error ApsConformalSets(cudaStream_t s, F32 probs, F32 val_sorted, RF32 scores, RU8 mask, RS32 sizes, float threshold) {
+  return Check(fb200_aps_conformal_sets(probs.typed_data(), Dim(probs, 0), Dim(probs, 1), val_sorted.typed_data(),
+                                        Dim(val_sorted, 0), threshold, Opt(scores), mask->typed_data(), Opt(sizes), s),
+               "fb200_aps_conformal_sets");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_aps_conformal_sets, ApsConformalSets,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Ret<F32>().Ret<U8>().Ret<S32>()
                                   .Attr<float>("threshold"));
 
-// ---- K7: ECE / MCE binning
-static ffi::Error EceBins(cudaStream_t stream, ffi::Buffer<ffi::F32> probs, ffi::Buffer<ffi::S32> targets,
-                          ffi::Buffer<ffi::F32> thresholds, ffi::ResultBuffer<ffi::S32> counts,
-                          ffi::ResultBuffer<ffi::F32> conf_sums, ffi::ResultBuffer<ffi::S32> correct,
-                          ffi::ResultBuffer<ffi::F32> result) {
-  const int B = (int)probs.dimensions()[0], C = (int)probs.dimensions()[1];
-  return Check(fb200_ece_bins(probs.typed_data(), B, C, nullptr, targets.typed_data(), thresholds.typed_data(),
-                              (int)thresholds.element_count(), nullptr, counts->typed_data(),
-                              conf_sums->typed_data(), correct->typed_data(), result->typed_data(), stream),
+// predictive/classification.py:465-483
+static ffi::Error CredibleSets(cudaStream_t s, F32 mean, RS32 labels, RS32 sizes, float threshold) {
+  return Check(fb200_credible_sets(mean.typed_data(), Dim(mean, 0), Dim(mean, 1), threshold, labels->typed_data(),
+                                   sizes->typed_data(), s),
+               "fb200_credible_sets");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_credible_sets, CredibleSets,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Ret<S32>().Ret<S32>().Attr<float>("threshold"));
+
+// ascending sort of a float32 vector (validation scores, quantiles); x is donated
+static ffi::Error SortF32(cudaStream_t s, F32 x, RF32 x_out, RU8 ws) {
+  CopyIfNotAliased(x.typed_data(), x_out->typed_data(), x.size_bytes(), s);
+  return Check(fb200_sort_f32(x_out->typed_data(), static_cast<int64_t>(x.element_count()), ws->typed_data(), ws->size_bytes(), s),
+               "fb200_sort_f32");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_sort_f32, SortF32, ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Ret<F32>().Ret<U8>());
+
+// jnp.quantile (conformal/regression/quantile.py:89-90)
+static ffi::Error QuantileSorted(cudaStream_t s, F32 x_sorted, F32 q, RF32 out) {
+  return Check(fb200_quantile_sorted(x_sorted.typed_data(), static_cast<int64_t>(x_sorted.element_count()), q.typed_data(),
+                                     Dim(q, 0), out->typed_data(), s),
+               "fb200_quantile_sorted");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_quantile_sorted, QuantileSorted, ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Ret<F32>());
+
+static ffi::Error QuantileAxis0(cudaStream_t s, F32 x, F32 q, RF32 out) {
+  const int T = Dim(x, 0);
+  return Check(fb200_quantile_axis0(x.typed_data(), T, static_cast<int64_t>(x.element_count() / (T ? T : 1)), q.typed_data(),
+                                    Dim(q, 0), out->typed_data(), s),
+               "fb200_quantile_axis0");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_quantile_axis0, QuantileAxis0, ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Ret<F32>());
+
+// metric/classification.py:43-220: bins, ECE, MCE, accuracy, Brier.  result = [ece, mce, accuracy, brier | confs | accs]
+static ffi::Error EceBins(cudaStream_t s, F32 probs, S32 preds, S32 targets, F32 thresholds, RS32 bin_idx, RS32 counts,
+                          RF32 conf_sums, RS32 correct, RF32 result) {
+  const int nd = static_cast<int>(probs.dimensions().size());
+  return Check(fb200_ece_bins(probs.typed_data(), Dim(probs, 0), nd > 1 ? Dim(probs, 1) : 1, Opt(preds), Opt(targets),
+                              thresholds.typed_data(), Dim(thresholds, 0), Opt(bin_idx), counts->typed_data(),
+                              conf_sums->typed_data(), correct->typed_data(), result->typed_data(), s),
                "fb200_ece_bins");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_ece_bins, EceBins,
-                              ffi::Ffi::Bind()
-                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::S32>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::S32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::S32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>());
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<S32>().Arg<S32>().Arg<F32>().Ret<S32>().Ret<S32>()
+                                  .Ret<F32>().Ret<S32>().Ret<F32>());
+
+// the same from the per-row quantities the reduction kernel emits (confidence, mode, brier_terms)
+static ffi::Error EceBinsFromRows(cudaStream_t s, F32 confidence, S32 preds, F32 brier, S32 targets, F32 thresholds, RS32 bin_idx,
+                                  RS32 counts, RF32 conf_sums, RS32 correct, RF32 result) {
+  return Check(fb200_ece_bins_from_rows(confidence.typed_data(), preds.typed_data(), Opt(brier), Opt(targets), Dim(confidence, 0),
+                                        thresholds.typed_data(), Dim(thresholds, 0), Opt(bin_idx), counts->typed_data(),
+                                        conf_sums->typed_data(), correct->typed_data(), result->typed_data(), s),
+               "fb200_ece_bins_from_rows");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_ece_bins_from_rows, EceBinsFromRows,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<S32>().Arg<F32>().Arg<S32>().Arg<F32>().Ret<S32>()
+                                  .Ret<S32>().Ret<F32>().Ret<S32>().Ret<F32>());
+
+// sharded evaluation: pack the additive counters (-> one psum), finalise from the packed sums
+static ffi::Error EcePackBins(cudaStream_t s, S32 counts, F32 conf_sums, S32 correct, F64 packed_in, RF64 packed,
+                              int32_t accumulate) {
+  if (accumulate) CopyIfNotAliased(packed_in.typed_data(), packed->typed_data(), packed_in.size_bytes(), s);
+  return Check(fb200_ece_pack_bins(counts.typed_data(), conf_sums.typed_data(), correct.typed_data(), Dim(counts, 0),
+                                   packed->typed_data(), accumulate, s),
+               "fb200_ece_pack_bins");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_ece_pack_bins, EcePackBins,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<S32>().Arg<F32>().Arg<S32>().Arg<F64>().Ret<F64>()
+                                  .Attr<int32_t>("accumulate"));
+
+static ffi::Error EceFromPackedBins(cudaStream_t s, F64 packed, RS32 counts, RF32 result, int64_t n_total) {
+  return Check(fb200_ece_from_packed_bins(packed.typed_data(), Dim(packed, 0) / 3, n_total, Opt(counts), result->typed_data(), s),
+               "fb200_ece_from_packed_bins");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_ece_from_packed_bins, EceFromPackedBins,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F64>().Ret<S32>().Ret<F32>().Attr<int64_t>("n_total"));
+
+// Predictive.sample for classification (predictive/base.py:318-440, prob_output_layer/classification.py:33-51)
+static ffi::Error ClsSampleTargets(cudaStream_t s, F32 logits, F32 log_temp, U32 key, RS32 y, RS32 idx) {
+  return Check(fb200_cls_sample_targets(logits.typed_data(), Opt(log_temp), key.typed_data(), Dim(*y, 0), Dim(logits, 0),
+                                        Dim(logits, 1), Dim(logits, 2), y->typed_data(), Opt(idx), s),
+               "fb200_cls_sample_targets");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_cls_sample_targets, ClsSampleTargets,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<U32>().Ret<S32>().Ret<S32>());
+
+// SG-MCMC diagnostics over the sample bank (sgmcmc_diagnostic.py:16-140)
+static ffi::Error KsdImq(cudaStream_t s, F32 samples, F32 grads, RU8 ws, RF32 out, float c, float beta) {
+  return Check(fb200_ksd_imq(samples.typed_data(), grads.typed_data(), Dim(samples, 0), samples.dimensions()[1],
+                             samples.dimensions()[1], c, beta, ws->typed_data(), ws->size_bytes(), out->typed_data(), s),
+               "fb200_ksd_imq");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_ksd_imq, KsdImq,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Ret<U8>().Ret<F32>().Attr<float>("c")
+                                  .Attr<float>("beta"));
+
+static ffi::Error Ess(cudaStream_t s, F32 samples, RF32 out, int32_t use_threshold, float threshold) {
+  return Check(fb200_ess(samples.typed_data(), Dim(samples, 0), samples.dimensions()[1], samples.dimensions()[1], use_threshold,
+                         threshold, out->typed_data(), s),
+               "fb200_ess");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_ess, Ess,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Ret<F32>().Attr<int32_t>("use_threshold")
+                                  .Attr<float>("threshold"));
+
 #else
-#error "XLA FFI headers not found: this shim only builds where jaxlib is installed (see the header comment)"
+#error "xla/ffi/api/ffi.h not found: add jaxlib's include directory (or, for the syntax check only, fortuna_b200/xla_ffi/mock)"
 #endif

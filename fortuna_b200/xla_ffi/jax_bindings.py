@@ -1,5 +1,6 @@
 """Reference-side binding: registers the XLA-FFI handlers of fb200_xla_ffi.cc with JAX and exposes the
-drop-ins a Fortuna maintainer would import.  Requires jax/jaxlib (absent from the build container and the
+drop-ins a Fortuna maintainer would import (one worked example, the SGHMC integrator; the other handlers are bound the
+same way - INTEGRATION.md lists all of them with the reference call each replaces).  Requires jax/jaxlib (absent from the build container and the
 GPU box, so this module is NOT imported by the package, the tests or the benchmark - the ctypes driver in
 fortuna_b200/ops.py is what runs here).  Tolerates both spellings of the FFI module: ``jax.extend.ffi`` at the
 pinned jax 0.4.30, ``jax.ffi`` from 0.4.38.
@@ -23,8 +24,45 @@ def _ffi():
         return ffi
 
 
-_TARGETS = ("fb200_xla_sgmcmc_step", "fb200_xla_last_layer", "fb200_xla_bma_reduce_cls", "fb200_xla_aps_scores",
-            "fb200_xla_conformal_sets", "fb200_xla_ece_bins")
+_TARGETS = (
+    "fb200_xla_split",
+    "fb200_xla_fold_in",
+    "fb200_xla_random_bits",
+    "fb200_xla_random_normal",
+    "fb200_xla_sample_indices",
+    "fb200_xla_choice_from_keys",
+    "fb200_xla_sgmcmc_step",
+    "fb200_xla_sgmcmc_step_joint",
+    "fb200_xla_sgd_explore_step",
+    "fb200_xla_sgd_explore_step_joint",
+    "fb200_xla_bank_put",
+    "fb200_xla_last_layer",
+    "fb200_xla_last_layer_ex",
+    "fb200_xla_log_prob_from_lse",
+    "fb200_xla_transpose_w",
+    "fb200_xla_softmax_rows",
+    "fb200_xla_bma_reduce_cls",
+    "fb200_xla_bma_reduce_cls_sets",
+    "fb200_xla_bma_reduce_cls_shard",
+    "fb200_xla_bma_finalize_cls_slots",
+    "fb200_xla_variance_combine",
+    "fb200_xla_bma_reduce_reg",
+    "fb200_xla_aps_scores",
+    "fb200_xla_simple_scores",
+    "fb200_xla_conformal_sets",
+    "fb200_xla_aps_conformal_sets",
+    "fb200_xla_credible_sets",
+    "fb200_xla_sort_f32",
+    "fb200_xla_quantile_sorted",
+    "fb200_xla_quantile_axis0",
+    "fb200_xla_ece_bins",
+    "fb200_xla_ece_bins_from_rows",
+    "fb200_xla_ece_pack_bins",
+    "fb200_xla_ece_from_packed_bins",
+    "fb200_xla_cls_sample_targets",
+    "fb200_xla_ksd_imq",
+    "fb200_xla_ess",
+)
 _registered = False
 
 
@@ -74,7 +112,9 @@ def sghmc_integrator(momentum_decay, momentum_resample_steps, rng_key, step_sche
         new_p, new_m, new_v, new_key, _ = ffi.ffi_call(
             "fb200_xla_sgmcmc_step", out_types, pflat, gflat, state["momentum"], state["v"], jnp.asarray(leaves),
             jnp.asarray(tiles), state["rng_key"], step_size=np.float32(step_schedule(state["count"])),
-            momentum_decay=float(momentum_decay), rmsprop=np.int32(rms), rms_alpha=float(running_average_factor),
+            momentum_decay=float(momentum_decay), zero_momentum=np.int32(
+                momentum_resample_steps is not None and int(state["count"]) % momentum_resample_steps == 0),
+            rmsprop=np.int32(rms), rms_alpha=float(running_average_factor),
             rms_eps=float(eps), input_output_aliases={0: 0, 2: 1, 3: 2})
         new_state = dict(count=state["count"] + 1, rng_key=new_key, momentum=new_m, v=new_v)
         return unravel(new_p - pflat), new_state

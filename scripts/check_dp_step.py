@@ -142,6 +142,57 @@ def parity(dev, rank, world, multicast):
     return bad
 
 
+def phase_switch(dev, rank, world):
+    """Cyclical SGLD with the RMSprop preconditioner, data-parallel: sampling steps (tile split) and exploration steps
+    (element split) interleaved - sampling x2, exploration x2, sampling x2, exploration x1 - against the single-GPU chain
+    on the averaged gradients.  The preconditioner moments are rank-local, so every phase change has to hand them over
+    (round-1 bug: the new owner saw moments that had missed the other phase's updates - zero in the first cycle)."""
+    lens = [4096 * 3, 7, 1025, 64 * 1024 + 3, 2048, 1, 333]
+    offs, n = _tree(lens)
+    dp = DataParallelStep(lens, offs, n, dev, world, rank, rmsprop=True, seed=5, multicast=False)
+    g = torch.Generator(device=dev)
+    g.manual_seed(13)
+    p0 = torch.empty(n, device=dev).normal_(0, 1, generator=g)
+    dp.params.copy_(p0)
+    ref_p, ref_m, ref_v = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    key, key2 = ops.PRNGKey(5, dev), torch.empty(2, dtype=ops.KEY_DTYPE, device=dev)
+    lk = torch.empty((len(lens), 2), dtype=ops.KEY_DTYPE, device=dev)
+    hp = ops.make_hparams(1e-3, 0.0, rmsprop=True)
+    bad = 0
+    for it, phase in enumerate("ssEEssE"):
+        grads = []
+        for r in range(world):
+            gr = torch.Generator(device=dev)
+            gr.manual_seed(7000 + 10 * it + r)
+            grads.append(torch.empty(n, device=dev).normal_(0, 1, generator=gr))
+        dp.grad.copy_(grads[rank])
+        acc = grads[0].clone()
+        for r in range(1, world):
+            acc += grads[r]
+        acc *= 1.0 / world
+        if phase == "s":
+            dp.step(hp)
+            ops.sgmcmc_step(ref_p, acc, ref_m, ref_v, None, dp.leaves, dp.tiles, key, key2, lk, hp)
+            key, key2 = key2, key
+        else:
+            dp.explore_step(hp)
+            ops.sgd_explore_step(ref_p, acc, ref_v, None, hp)
+        torch.cuda.synchronize()
+        # 1 / (eps + sqrt(v)) is ill-conditioned in the last ulp of a near-zero gradient: allow a handful of elements
+        off = ((dp.params - ref_p).abs() > 2e-6 + 2e-5 * ref_p.abs()).sum().item()
+        if off > n // 2000:
+            bad += 1
+            print(f"rank {rank}: phase-switch step {it} ({phase}): {off} elements differ, max abs "
+                  f"{(dp.params - ref_p).abs().max().item()}")
+        ref_p.copy_(dp.params)
+    dp.gather_state()
+    torch.cuda.synchronize()
+    if not torch.allclose(dp.precond_v, ref_v, rtol=1e-5, atol=1e-9):
+        bad += 1
+        print(f"rank {rank}: gathered preconditioner moments differ from the single-GPU chain's")
+    return bad
+
+
 def bench(dev, rank, world, multicast, steps=20):
     lens = [23440896, 393216, 1536] + [2359296 // 4 * 4] * 36 + [589824] * 1 + [768] * 100  # ~109.5 M, BERT-base-like
     offs, n = _tree(lens)
@@ -201,6 +252,11 @@ def main():
             print(f"dp_step parity (multicast={multicast}):", "OK" if tot.item() == 0 else f"{tot.item()} MISMATCHES")
         if "--bench" in sys.argv and tot.item() == 0:
             bench(dev, rank, world, multicast)
+    tot = torch.tensor([phase_switch(dev, rank, world)], device=dev)
+    dist.all_reduce(tot)
+    fails += int(tot.item())
+    if rank == 0:
+        print("dp_step RMSprop phase switch (cyclical SGLD):", "OK" if tot.item() == 0 else f"{tot.item()} MISMATCHES")
     dist.destroy_process_group()
     sys.exit(1 if fails else 0)
 

@@ -78,3 +78,22 @@ def test_missing_library_fails_loudly(built, monkeypatch):
     monkeypatch.setattr(built, "LIB_PATH", "/nonexistent/libfortuna_b200.so")
     with pytest.raises(built.FortunaB200LibraryError):
         built.lib()
+
+
+def test_xla_ffi_shim_passes_the_syntax_check():
+    """fortuna_b200/xla_ffi/fb200_xla_ffi.cc compiles (g++ -fsyntax-only) against the mock XLA FFI header, whose
+    Binding::To() static_asserts every handler against its binding, and against the real C-ABI header; the Python-side
+    target list names exactly the handlers the shim defines.  A syntax / signature check - jaxlib is not installable."""
+    import subprocess
+
+    r = subprocess.run(["bash", os.path.join(ROOT, "scripts", "check_xla_ffi_syntax.sh")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    src = open(os.path.join(ROOT, "fortuna_b200", "xla_ffi", "fb200_xla_ffi.cc")).read()
+    handlers = re.findall(r"^XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),", src, flags=re.M)
+    assert len(handlers) >= 30 and len(set(handlers)) == len(handlers)
+    py = open(os.path.join(ROOT, "fortuna_b200", "xla_ffi", "jax_bindings.py")).read()
+    targets = re.findall(r'"(fb200_xla_\w+)"', py.split("_TARGETS = (")[1].split(")")[0])
+    assert targets == handlers
+    # every fb200_* entry point a handler forwards to is declared in the header
+    called = set(re.findall(r"\b(fb200_[a-z0-9_]+)\s*\(", src)) - {"fb200_error_string"}
+    assert called <= set(_declared()), called - set(_declared())

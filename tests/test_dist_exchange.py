@@ -186,3 +186,86 @@ def test_fit_processor_defaults_and_single_process_binding():
     assert FitConfig().processor.devices == -1 and FitConfig().processor.disable_jit is False
     assert FitConfig(processor=FitProcessor(devices=0)).processor.devices == 0
     assert not dist.is_initialized()
+
+
+# ------------------------------------------------------------------------------------------------
+# Rank-local sampler state of the data-parallel step: who owns what under the two splits, and the gather that makes the
+# state whole (phase change of cyclical SGLD with RMSprop, chain checkpoints)
+# ------------------------------------------------------------------------------------------------
+def _tile_owner_mask(lens, offsets, t0, t1, n):
+    """Brute force: elements the kernel touches for tiles [t0, t1) - pair i of a leaf is elements i and i + ceil(len/2)."""
+    tiles = [(li, ps) for li, l in enumerate(lens) for ps in range(0, (l + 1) // 2, 1024)]
+    m = np.zeros(n, bool)
+    for li, ps in tiles[t0:t1]:
+        h = (lens[li] + 1) // 2
+        e = min(ps + 1024, h)
+        m[offsets[li] + ps : offsets[li] + e] = True
+        m[offsets[li] + h + ps : offsets[li] + min(h + e, lens[li])] = True
+    return m
+
+
+def test_dp_owned_elem_ranges_match_the_tile_walk():
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc.dp_step import owned_ranges
+
+    rng = np.random.default_rng(3)
+    for lens in ([5000, 7, 2049], [1, 1, 3], [30522 * 8, 768, 2, 3072 * 5 + 1], list(rng.integers(1, 9000, 17))):
+        offsets, off = [], 0
+        for l in lens:
+            offsets.append(off)
+            off += (int(l) + 3) // 4 * 4
+        n_tiles = sum(((int(l) + 1) // 2 + 1023) // 1024 for l in lens)
+        for world in (1, 2, 3, 8):
+            seen = np.zeros(off, np.int32)
+            for rank in range(world):
+                t0, t1 = ops.dp_tile_range(n_tiles, world, rank)
+                m = np.zeros(off, bool)
+                rs = owned_ranges("tiles", off, world, rank, lens, offsets)
+                assert all(a < b for a, b in rs) and all(rs[i][1] < rs[i + 1][0] for i in range(len(rs) - 1))  # merged, sorted
+                for a, b in rs:
+                    m[a:b] = True
+                assert np.array_equal(m, _tile_owner_mask(lens, offsets, t0, t1, off)), (lens[:4], world, rank)
+                seen += m
+                (e0, e1), = owned_ranges("elems", off, world, rank, lens, offsets)
+                assert e0 % 4 == 0 and 0 <= e0 <= e1 <= off
+            real = np.zeros(off, bool)
+            for l, o in zip(lens, offsets):
+                real[o : o + int(l)] = True
+            assert np.array_equal(seen == 1, real) and not (seen > 1).any()  # every parameter has exactly one owner
+
+
+def _gather_worker(rank, port, out_dir):
+    import torch.distributed as dist
+
+    from fortuna_b200.prob_model.posterior.sgmcmc.dp_step import gather_owned_ranges, owned_ranges
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    lens, offsets = [5000, 7, 2049], [0, 5000, 5008]
+    n = 5008 + 2052
+    truth = np.arange(n, dtype=np.float32) + 1
+    for scheme in ("tiles", "elems"):
+        rs = owned_ranges(scheme, n, WORLD, rank, lens, offsets)
+        v = np.full(n, -7.0, np.float32)  # stale values everywhere ...
+        for a, b in rs:
+            v[a:b] = truth[a:b]           # ... except on the owned pieces
+        t = torch.from_numpy(v)
+        gather_owned_ranges(t, rs)
+        np.save(os.path.join(out_dir, f"g_{scheme}_{rank}.npy"), t.numpy())
+    dist.destroy_process_group()
+
+
+def test_gather_owned_state_world2_gloo(tmp_path):
+    """After the gather every rank holds every owner's values (alignment padding, owned by nobody, becomes zero)."""
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    n = 5008 + 2052
+    truth = np.arange(n, dtype=np.float32) + 1
+    real = np.zeros(n, bool)
+    for l, o in zip([5000, 7, 2049], [0, 5000, 5008]):
+        real[o : o + l] = True
+    for rk in range(WORLD):
+        got = np.load(tmp_path / f"g_tiles_{rk}.npy")
+        assert np.array_equal(got[real], truth[real]) and not got[~real].any()
+        got = np.load(tmp_path / f"g_elems_{rk}.npy")
+        assert np.array_equal(got, truth)  # the element split covers the padding too

@@ -43,6 +43,8 @@ class SgmcmcHParams(C.Structure):
         ("rmsprop", C.c_int32),
         ("rms_alpha", C.c_double),
         ("rms_eps", C.c_double),
+        ("grad_mult", C.c_void_p),
+        ("grad_dtype", C.c_int32),
     ]
 
 
@@ -114,6 +116,8 @@ SIGNATURES = {
         _i,
         [_P, _P, _P, _P, _P, _i64, _P, _i, _P, _i64, _P, _P, _P, C.POINTER(SgmcmcHParams), _P],
     ),
+    "fb200_grad_clip_workspace_doubles": (_i64, [_i64]),
+    "fb200_grad_clip_mult": (_i, [_P, _i, _P, C.POINTER(JointGrad), _i64, _f, _P, _P, _P]),
     "fb200_sgd_explore_step_f32": (_i, [_P, _P, _P, _P, _i64, C.POINTER(SgmcmcHParams), _P]),
     "fb200_sgmcmc_step_dp_f32": (_i, [_P, _P, _i64, _P, _i, _P, _i64, _i64, _P, _P, _P, C.POINTER(SgmcmcHParams),
                                  C.POINTER(JointGrad), C.POINTER(DpPeers), _P]),

@@ -11,6 +11,8 @@
 // 28 B/param (RMSprop).  The noise never touches HBM: each thread evaluates the threefry2x32 block
 // of counter pair (i, i + h) of its leaf, whose two outputs are jax's normal() draws for elements i
 // and i + h of that leaf (h = ceil(len/2)), so a thread updates two 16-byte vectors, one in each half.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fb200 {
@@ -38,6 +40,8 @@ __global__ void __launch_bounds__(128) sgmcmc_keys_kernel(const uint32_t* __rest
   }
 }
 
+constexpr int64_t kFoldKeysMaxTiles = 1024;  // ~2 M parameters: below this the step is launch-bound, not bandwidth-bound
+
 struct StepCoef {
   float sqrt_eps;     // sqrt(float32(step_size))
   float beta;         // float32(momentum_decay)
@@ -47,7 +51,19 @@ struct StepCoef {
   float rms_eps;      // float32(eps)
   float step_size;    // float32 epsilon_t (exploration phase)
   int zero_momentum;
+  const float* grad_mult;  // device float[1] or null: clip_grandients_by_norm's multiplier (utils/training.py:14-20)
+  int grad_bf16;           // `grad` holds bfloat16 (single-GPU kernels only)
 };
+
+// four consecutive bf16 gradients (8-byte aligned) -> float4
+__device__ __forceinline__ float4 ld_bf16x4(const float* grad_as_bf16, int64_t e) {
+  const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(grad_as_bf16) + e);
+  return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
+                     __uint_as_float(w.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ float ld_bf16(const float* grad_as_bf16, int64_t e) {
+  return __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(grad_as_bf16)[e] << 16);
+}
 
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
@@ -155,19 +171,48 @@ template <bool RMS, bool JOINT, int NP>  // NP = 0: single GPU; 2 / 4 / 8: data-
 __global__ void __launch_bounds__(256)
     sgmcmc_step_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ mom,
                        float* __restrict__ pv, float* __restrict__ upd, const fb200_leaf_t* __restrict__ leaves,
-                       const uint2* __restrict__ leaf_keys, const fb200_tile_t* __restrict__ tiles,
+                       const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_out,
+                       uint32_t* __restrict__ leaf_keys, uint32_t n_leaves, const fb200_tile_t* __restrict__ tiles,
                        const StepCoef c, const JointCoef jc, const DpPeers dp) {
   constexpr bool DP = NP > 0;
   constexpr bool MC = NP == 1;
   const fb200_tile_t tile = tiles[blockIdx.x];
   const fb200_leaf_t leaf = leaves[tile.leaf];
-  const uint2 key = leaf_keys[tile.leaf];
+  // Key schedule.  Large trees: a tiny kernel of its own has already written leaf_keys (key_in == null here).  Small
+  // trees are launch-bound and that second launch was a third of the step, so there the schedule is derived right here,
+  // once per WARP and without a barrier: (key, new_key) = split(key_in) - blocks (0,2) and (1,3) of random_bits(key_in, 4),
+  // one per lane - then this leaf's key = elements 2l, 2l+1 of random_bits(key, 2 n_leaves), again one per lane,
+  // broadcast by shuffles (two dependent threefry blocks on two lanes: ~0.4 us per CTA, which matters at 53 K tiles and
+  // not at 30).
+  uint2 key;
+  if (key_in == nullptr) {
+    key = reinterpret_cast<const uint2*>(leaf_keys)[tile.leaf];
+  } else {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t kw = 0u;
+    if (lane < 2u) {
+      const uint32_t k0 = key_in[0], k1 = key_in[1];
+      uint32_t x0 = lane, x1 = lane + 2u;
+      threefry2x32(k0, k1, x0, x1);                          // lane 0: (a0, a1); lane 1: (b0, b1)
+      const uint32_t o0 = __shfl_xor_sync(0x3u, x0, 1), o1 = __shfl_xor_sync(0x3u, x1, 1);
+      const uint32_t a0 = lane ? o0 : x0, b0 = lane ? x0 : o0;  // key = (a0, b0) drives the noise
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        key_out[0] = x1;                                     // new_key = (a1, b1) is stored
+        key_out[1] = o1;
+      }
+      kw = random_bits_elem(a0, b0, 2u * n_leaves, 2u * (uint32_t)tile.leaf + lane);
+      if (tile.pair_start == 0 && threadIdx.x < 2) leaf_keys[2 * tile.leaf + lane] = kw;  // split(key, L), inspectable
+    }
+    key.x = __shfl_sync(0xffffffffu, kw, 0);
+    key.y = __shfl_sync(0xffffffffu, kw, 1);
+  }
   const uint32_t n = (uint32_t)leaf.len;
   const uint32_t h = (n >> 1) + (n & 1u);
   const uint32_t i0 = tile.pair_start + threadIdx.x * 4u;
   float sq = 0.0f;  // JOINT: this thread's sum of theta^2
-  if (!JOINT && i0 >= h) return;
-  if (i0 < h) {
+  const bool active = i0 < h;
+  if (!JOINT && !active) return;
+  if (active) {
   const int64_t e0 = leaf.offset + i0;      // first-half elements e0 .. e0+3
   const int64_t e1 = leaf.offset + h + i0;  // second-half elements e1 .. e1+3
 
@@ -191,6 +236,9 @@ __global__ void __launch_bounds__(256)
     } else if constexpr (DP) {
       g0 = dp_grad4<NP>(dp, e0);
       g1 = dp_grad4<NP>(dp, e1);
+    } else if (c.grad_bf16) {
+      g0 = ld_bf16x4(grad, e0);
+      g1 = ld_bf16x4(grad, e1);
     } else {
       g0 = *reinterpret_cast<const float4*>(grad + e0);
       g1 = *reinterpret_cast<const float4*>(grad + e1);
@@ -214,6 +262,11 @@ __global__ void __launch_bounds__(256)
       g1.z = fmaf(jc.lik_scale, g1.z, jc.prior_coef * p1.z); g1.w = fmaf(jc.lik_scale, g1.w, jc.prior_coef * p1.w);
       sq = ((p0.x * p0.x + p0.y * p0.y) + (p0.z * p0.z + p0.w * p0.w)) +
            ((p1.x * p1.x + p1.y * p1.y) + (p1.z * p1.z + p1.w * p1.w));
+    }
+    if (c.grad_mult) {  // clip_grandients_by_norm: g <- mult * g (the multiplier comes from fb200_grad_clip_mult)
+      const float gm = __ldg(c.grad_mult);
+      g0.x = __fmul_rn(gm, g0.x); g0.y = __fmul_rn(gm, g0.y); g0.z = __fmul_rn(gm, g0.z); g0.w = __fmul_rn(gm, g0.w);
+      g1.x = __fmul_rn(gm, g1.x); g1.y = __fmul_rn(gm, g1.y); g1.z = __fmul_rn(gm, g1.z); g1.w = __fmul_rn(gm, g1.w);
     }
     float4 u0, u1;
     u0.x = sghmc_elem<RMS>(g0.x, m0.x, v0.x, r0[0], c);
@@ -267,12 +320,13 @@ __global__ void __launch_bounds__(256)
         float g;
         if constexpr (MC) g = mc_ld_reduce1(dp.mc_grad + e) * dp.inv_n;
         else if constexpr (DP) g = dp_grad1(dp, e);
-        else g = grad[e];
+        else g = c.grad_bf16 ? ld_bf16(grad, e) : grad[e];
         if (JOINT) {
           const float p = params[e];
           g = fmaf(jc.lik_scale, g, jc.prior_coef * p);
           sq += p * p;
         }
+        if (c.grad_mult) g = __fmul_rn(__ldg(c.grad_mult), g);
         const float u = sghmc_elem<RMS>(g, m, v, half ? r1[k] : r0[k], c);
         mom[e] = m;
         if (RMS) pv[e] = v;
@@ -286,7 +340,7 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  }  // i0 < h
+  }  // active
   if (JOINT && jc.sq_part) {
     __shared__ float wsum[8];
     sq = group_sum<32>(sq);
@@ -362,6 +416,11 @@ __global__ void __launch_bounds__(256)
           sq += pp[k] * pp[k];
         }
       }
+      if (c.grad_mult) {
+        const float gm = __ldg(c.grad_mult);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gg[k] = __fmul_rn(gm, gg[k]);
+      }
       float uu[4];
       float vv[4] = {0.f, 0.f, 0.f, 0.f};
       if (RMS) {
@@ -404,6 +463,7 @@ __global__ void __launch_bounds__(256)
           g = fmaf(jc.lik_scale, g, __fmul_rn(jc.prior_coef, p));
           sq += p * p;
         }
+        if (c.grad_mult) g = __fmul_rn(__ldg(c.grad_mult), g);
         float u = __fmul_rn(c.step_size, g);
         if (RMS) {
           const float v = __fadd_rn(__fmul_rn(pv[j], c.alpha), __fmul_rn(__fmul_rn(g, g), c.one_m_alpha));
@@ -438,6 +498,54 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// clip_grandients_by_norm (fortuna/utils/training.py:14-20): the global norm of the gradient the step is about to use,
+// as float64 partials per CTA (summed in order by sum_partials_kernel: deterministic), then
+// mult = min(1, max_norm / (1e-7 + sqrt(sum))) in float32.  The step kernels scale by *mult as they load the gradient.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grad_sq_partials_kernel(const float* __restrict__ grad, int grad_bf16,
+                                                               const float* __restrict__ params, const JointCoef jc,
+                                                               int joint, int64_t n, double* __restrict__ part) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  double acc = 0.0;
+  for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < n; e += stride) {
+    float g[4] = {0.f, 0.f, 0.f, 0.f}, p[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e + 3 < n) {
+      const float4 gv = grad_bf16 ? ld_bf16x4(grad, e) : *reinterpret_cast<const float4*>(grad + e);
+      g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+      if (joint) {
+        const float4 pv = *reinterpret_cast<const float4*>(params + e);
+        p[0] = pv.x; p[1] = pv.y; p[2] = pv.z; p[3] = pv.w;
+      }
+    } else {
+      for (int k = 0; k < 4 && e + k < n; ++k) {
+        g[k] = grad_bf16 ? ld_bf16(grad, e + k) : grad[e + k];
+        if (joint) p[k] = params[e + k];
+      }
+    }
+    float s4 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gj = joint ? fmaf(jc.lik_scale, g[k], jc.prior_coef * p[k]) : g[k];  // as the step kernel forms it
+      s4 = fmaf(gj, gj, s4);
+    }
+    acc += (double)s4;
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+
+__global__ void grad_clip_finish_kernel(const double* __restrict__ sum_sq, float max_norm, float* __restrict__ mult) {
+  const float norm = sqrtf((float)sum_sq[0]);
+  mult[0] = fminf(1.0f, max_norm / (1e-7f + norm));
+}
+
 __global__ void __launch_bounds__(256) bank_put_kernel(float* __restrict__ dst, const float* __restrict__ src,
                                                        int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -463,6 +571,8 @@ static StepCoef make_coef(const fb200_sgmcmc_hparams_t* hp) {
   c.one_m_alpha = (float)(1.0 - hp->rms_alpha);
   c.rms_eps = (float)hp->rms_eps;
   c.zero_momentum = hp->zero_momentum;
+  c.grad_mult = hp->grad_mult;
+  c.grad_bf16 = hp->grad_dtype == FB200_BF16;
   return c;
 }
 
@@ -512,14 +622,13 @@ static int sgmcmc_step_impl(float* params, const float* grad, float* momentum, f
   if (n <= 0 || n_leaves <= 0 || n_tiles <= 0 || n_tiles > 0x7FFFFFFFll || n_leaves >= (1 << 30))
     return FB200_E_SHAPE;
   if (key_in == key_out) return FB200_E_SHAPE;
+  if (hp->grad_dtype != FB200_F32 && hp->grad_dtype != FB200_BF16) return FB200_E_UNSUPPORTED;
+  if (hp->grad_dtype == FB200_BF16 && dpp) return FB200_E_UNSUPPORTED;  // peer gradients are float32
   if (!fb200_aligned16(grad) || !fb200_aligned16(momentum) || (params && !fb200_aligned16(params)) ||
       (updates_out && !fb200_aligned16(updates_out)) || (hp->rmsprop && !fb200_aligned16(precond_v)))
     return FB200_E_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const StepCoef c = make_coef(hp);
-  sgmcmc_keys_kernel<<<(n_leaves + 127) / 128, 128, 0, st>>>(key_in, key_out, leaf_keys_ws, (uint32_t)n_leaves);
-  FB200_LAUNCH_CHECK();
-  const uint2* lk = reinterpret_cast<const uint2*>(leaf_keys_ws);
   JointCoef jc{1.0f, 0.0f, nullptr};
   if (joint) {
     jc.lik_scale = joint->lik_scale;
@@ -528,41 +637,36 @@ static int sgmcmc_step_impl(float* params, const float* grad, float* momentum, f
   }
   const unsigned g = (unsigned)n_tiles;
   const DpPeers nodp{};
-  if (dpp) {
-#define FB200_DP_LAUNCH(NPV)                                                                                          \
-  do {                                                                                                                \
-    if (joint) {                                                                                                      \
-      if (hp->rmsprop)                                                                                                \
-        sgmcmc_step_kernel<true, true, NPV><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, nullptr, leaves, lk, \
-                                                               tiles, c, jc, *dpp);                                   \
-      else                                                                                                            \
-        sgmcmc_step_kernel<false, true, NPV><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, nullptr, leaves, lk,  \
-                                                                tiles, c, jc, *dpp);                                  \
-    } else {                                                                                                          \
-      if (hp->rmsprop)                                                                                                \
-        sgmcmc_step_kernel<true, false, NPV><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, nullptr, leaves,    \
-                                                                lk, tiles, c, jc, *dpp);                              \
-      else                                                                                                            \
-        sgmcmc_step_kernel<false, false, NPV><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, nullptr, leaves, lk, \
-                                                                 tiles, c, jc, *dpp);                                 \
-    }                                                                                                                 \
-  } while (0)
-    if (dpp->mc_grad) FB200_DP_LAUNCH(1);
-    else if (dpp->n <= 2) FB200_DP_LAUNCH(2);
-    else if (dpp->n <= 4) FB200_DP_LAUNCH(4);
-    else FB200_DP_LAUNCH(8);
-#undef FB200_DP_LAUNCH
-  } else if (joint) {
-    if (hp->rmsprop)
-      sgmcmc_step_kernel<true, true, 0><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc, nodp);
-    else
-      sgmcmc_step_kernel<false, true, 0><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc, nodp);
-  } else {
-    if (hp->rmsprop)
-      sgmcmc_step_kernel<true, false, 0><<<g, 256, 0, st>>>(params, grad, momentum, precond_v, updates_out, leaves, lk, tiles, c, jc, nodp);
-    else
-      sgmcmc_step_kernel<false, false, 0><<<g, 256, 0, st>>>(params, grad, momentum, nullptr, updates_out, leaves, lk, tiles, c, jc, nodp);
+  const DpPeers& dpa = dpp ? *dpp : nodp;
+  // key schedule: folded into the step kernel for launch-bound (small) trees, a kernel of its own otherwise
+  const bool fold_keys = n_tiles <= kFoldKeysMaxTiles;
+  if (!fold_keys) {
+    sgmcmc_keys_kernel<<<(n_leaves + 127) / 128, 128, 0, st>>>(key_in, key_out, leaf_keys_ws, (uint32_t)n_leaves);
+    FB200_LAUNCH_CHECK();
+    key_in = nullptr;
   }
+  float* pv = hp->rmsprop ? precond_v : nullptr;
+  float* up = dpp ? nullptr : updates_out;
+#define FB200_STEP_LAUNCH(RMS_, JOINT_, NP_)                                                                          \
+  sgmcmc_step_kernel<RMS_, JOINT_, NP_><<<g, 256, 0, st>>>(params, grad, momentum, pv, up, leaves, key_in, key_out,    \
+                                                           leaf_keys_ws, (uint32_t)n_leaves, tiles, c, jc, dpa)
+#define FB200_STEP_MODES(NP_)                         \
+  do {                                                \
+    if (joint) {                                      \
+      if (hp->rmsprop) FB200_STEP_LAUNCH(true, true, NP_);   \
+      else FB200_STEP_LAUNCH(false, true, NP_);       \
+    } else {                                          \
+      if (hp->rmsprop) FB200_STEP_LAUNCH(true, false, NP_);  \
+      else FB200_STEP_LAUNCH(false, false, NP_);      \
+    }                                                 \
+  } while (0)
+  if (!dpp) FB200_STEP_MODES(0);
+  else if (dpp->mc_grad) FB200_STEP_MODES(1);
+  else if (dpp->n <= 2) FB200_STEP_MODES(2);
+  else if (dpp->n <= 4) FB200_STEP_MODES(4);
+  else FB200_STEP_MODES(8);
+#undef FB200_STEP_MODES
+#undef FB200_STEP_LAUNCH
   FB200_LAUNCH_CHECK();
   if (joint && sq_out) {
     sum_partials_kernel<<<1, 1024, 0, st>>>(sq_ws, n_tiles, sq_out);
@@ -633,6 +737,40 @@ extern "C" int fb200_sgmcmc_step_dp_f32(float* momentum, float* precond_v, int64
                           nullptr, nullptr, stream, &dp);
 }
 
+extern "C" int64_t fb200_grad_clip_workspace_doubles(int64_t n) {
+  if (n <= 0) return 0;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  return blocks + 1;  // per-CTA partials + their sum
+}
+
+extern "C" int fb200_grad_clip_mult(const void* grad, int grad_dtype, const float* params, const fb200_joint_grad_t* joint,
+                                    int64_t n, float max_grad_norm, double* workspace, float* mult_out, void* stream) {
+  if (!grad || !workspace || !mult_out) return FB200_E_NULL;
+  if (joint && !params) return FB200_E_NULL;
+  if (n <= 0 || !(max_grad_norm > 0.0f)) return FB200_E_SHAPE;
+  if (grad_dtype != FB200_F32 && grad_dtype != FB200_BF16) return FB200_E_UNSUPPORTED;
+  if ((grad_dtype == FB200_F32 && !fb200_aligned16(grad)) || (reinterpret_cast<uintptr_t>(grad) & 7u) ||
+      (joint && !fb200_aligned16(params)))
+    return FB200_E_ALIGN;
+  const int64_t blocks = fb200_grad_clip_workspace_doubles(n) - 1;
+  JointCoef jc{1.0f, 0.0f, nullptr};
+  if (joint) {
+    jc.lik_scale = joint->lik_scale;
+    jc.prior_coef = -joint->prior_prec;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  grad_sq_partials_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(grad), grad_dtype == FB200_BF16,
+                                                            params, jc, joint != nullptr, n, workspace);
+  FB200_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, 1024, 0, st>>>(workspace, blocks, workspace + blocks);
+  FB200_LAUNCH_CHECK();
+  grad_clip_finish_kernel<<<1, 1, 0, st>>>(workspace + blocks, max_grad_norm, mult_out);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
 static int explore_blocks(int64_t n) {
   int64_t blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
@@ -669,6 +807,7 @@ static int sgd_explore_impl(float* params, const float* grad, float* precond_v, 
   if (begin < 0 || end > n || begin > end) return FB200_E_SHAPE;
   if (begin == end) return 0;
   if (begin & 3) return FB200_E_SHAPE;
+  if (hp->grad_dtype != FB200_F32) return FB200_E_UNSUPPORTED;  // the exploration step takes float32 gradients
   if (!fb200_aligned16(grad) || (params && !fb200_aligned16(params)) ||
       (updates_out && !fb200_aligned16(updates_out)) || (hp->rmsprop && !fb200_aligned16(precond_v)))
     return FB200_E_ALIGN;

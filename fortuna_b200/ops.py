@@ -114,8 +114,35 @@ def build_leaf_tables(lens, offsets, device):
     return torch.from_numpy(leaves_np).to(device), torch.from_numpy(tiles_np).to(device)
 
 
-def make_hparams(step_size, momentum_decay=0.0, rmsprop=False, rms_alpha=0.99, rms_eps=1e-7, zero_momentum=False):
+def grad_clip_mult(grad, max_grad_norm, params=None, joint=None, ws_cache=None):
+    """float32 [1] device tensor: min(1, max_grad_norm / (1e-7 + ||g||)) - clip_grandients_by_norm's multiplier
+    (fortuna/utils/training.py:14-20) for the gradient the step is about to use.  ``joint = (lik_scale, prior_prec)``: g is
+    the log-joint gradient the fused mode forms from ``grad`` and ``params``.  Pass the result as
+    ``make_hparams(..., grad_mult=...)``: the step kernel scales the gradient as it loads it."""
+    n = grad.numel()
+    nws = int(lib().fb200_grad_clip_workspace_doubles(n))
+    ws = ws_cache.get("clip_ws") if ws_cache is not None else None
+    if ws is None or ws.numel() < nws or ws.device != grad.device:
+        ws = torch.empty(nws, dtype=torch.float64, device=grad.device)
+        if ws_cache is not None:
+            ws_cache["clip_ws"] = ws
+    mult = torch.empty(1, dtype=torch.float32, device=grad.device)
+    jg = _joint_struct(joint)
+    check(
+        lib().fb200_grad_clip_mult(_ptr(grad, (torch.float32, torch.bfloat16)), _DT[grad.dtype], _ptr(params, torch.float32, True),
+                                   C.byref(jg) if jg is not None else None, n, float(np.float32(max_grad_norm)),
+                                   _ptr(ws, torch.float64), _ptr(mult), _stream()),
+        "fb200_grad_clip_mult",
+    )
+    return mult
+
+
+def make_hparams(step_size, momentum_decay=0.0, rmsprop=False, rms_alpha=0.99, rms_eps=1e-7, zero_momentum=False,
+                 grad_mult=None, grad_dtype=torch.float32):
+    """``grad_mult``: optional device float32[1] (see ``grad_clip_mult``); the caller keeps it alive across the step."""
     hp = _lib.SgmcmcHParams()
+    hp.grad_mult = grad_mult.data_ptr() if grad_mult is not None else None
+    hp.grad_dtype = _DT[grad_dtype]
     hp.step_size = float(np.float32(step_size))
     hp.momentum_decay = float(momentum_decay)
     hp.zero_momentum = int(bool(zero_momentum))
@@ -152,7 +179,7 @@ def sgmcmc_step(params, grad, momentum, precond_v, updates_out, leaves, tiles, k
         jg, wsp, outp = _joint_args(joint, tiles.shape[0], grad.device, ws_cache)
         check(
             lib().fb200_sgmcmc_step_joint_f32(
-                _ptr(params, torch.float32), _ptr(grad, torch.float32), _ptr(momentum, torch.float32),
+                _ptr(params, torch.float32), _ptr(grad, (torch.float32, torch.bfloat16)), _ptr(momentum, torch.float32),
                 _ptr(precond_v, torch.float32, True), n, _ptr(leaves, torch.int64), leaves.shape[0],
                 _ptr(tiles, torch.int32), tiles.shape[0], _ptr(key_in, KEY_DTYPE), _ptr(key_out, KEY_DTYPE),
                 _ptr(leaf_keys_ws, KEY_DTYPE), C.byref(hp), C.byref(jg), wsp, outp, _stream(),
@@ -163,7 +190,7 @@ def sgmcmc_step(params, grad, momentum, precond_v, updates_out, leaves, tiles, k
     check(
         lib().fb200_sgmcmc_step_f32(
             _ptr(params, torch.float32, True),
-            _ptr(grad, torch.float32),
+            _ptr(grad, (torch.float32, torch.bfloat16)),
             _ptr(momentum, torch.float32),
             _ptr(precond_v, torch.float32, True),
             _ptr(updates_out, torch.float32, True),

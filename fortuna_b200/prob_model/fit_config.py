@@ -38,10 +38,26 @@ class FitProcessor:
         self.disable_jit = disable_jit
 
 
+class FitHyperparameters:
+    """fortuna/prob_model/fit_config/hyperparameters.py:4-21.  As in the reference, the SG-MCMC fits do NOT read it
+    (only the MAP / ADVI trainers pass ``max_grad_norm`` on: posterior/map/map_posterior.py:109; sghmc_posterior.py:97-111
+    does not) - so setting it changes nothing for SGHMC / cyclical SGLD, there or here.  The clipping itself
+    (fortuna/training/trainer.py:158-169, utils/training.py:14-20) is available on the sampler step:
+    ``sghmc_integrator(...).apply(..., max_grad_norm=...)`` / ``run_sgmcmc(..., max_grad_norm=...)`` - one extra read of
+    the gradient for the norm, the scaling rides inside the sampler kernel.  Gradient accumulation is not built."""
+
+    def __init__(self, max_grad_norm: Optional[float] = None, gradient_accumulation_steps: Optional[int] = None):
+        if gradient_accumulation_steps is not None and gradient_accumulation_steps > 1:
+            raise NotImplementedError("gradient accumulation is outside the hot path")
+        self.max_grad_norm = max_grad_norm
+        self.gradient_accumulation_steps = gradient_accumulation_steps
+
+
 class FitConfig:
     def __init__(self, optimizer: FitOptimizer = None, checkpointer: FitCheckpointer = None, monitor: FitMonitor = None,
-                 processor: FitProcessor = None, **_ignored):
+                 processor: FitProcessor = None, hyperparameters: FitHyperparameters = None, **_ignored):
         self.optimizer = optimizer or FitOptimizer()
         self.checkpointer = checkpointer or FitCheckpointer()
         self.monitor = monitor or FitMonitor()
         self.processor = processor or FitProcessor()
+        self.hyperparameters = hyperparameters or FitHyperparameters()

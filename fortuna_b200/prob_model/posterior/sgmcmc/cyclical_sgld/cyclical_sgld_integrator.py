@@ -14,7 +14,7 @@ import numpy as np
 
 from ..... import ops
 from .....utils.flat_tree import FlatTree, as_flat_tree
-from ..sghmc.sghmc_integrator import GradientTransformation, OptaxSGHMCState, sghmc_integrator
+from ..sghmc.sghmc_integrator import GradientTransformation, OptaxSGHMCState, clip_multiplier, sghmc_integrator
 from ..sgmcmc_preconditioner import Preconditioner, precond_buffer
 from ..sgmcmc_step_schedule import cyclical_cosine_schedule_with_const_burnin
 
@@ -56,12 +56,12 @@ def cyclical_sgld_integrator(
 
     ws = {}
 
-    def _explore(gradient, state, params, joint=None, dp=None):
+    def _explore(gradient, state, params, joint=None, dp=None, max_grad_norm=None):
         inner = state.sgld_state
         grad = as_flat_tree(gradient, like=inner.momentum)
         hp = ops.make_hparams(
             step_schedule(inner.count), 0.0, preconditioner.is_rmsprop, preconditioner.running_average_factor,
-            preconditioner.eps,
+            preconditioner.eps, grad_mult=clip_multiplier(grad, params, joint, max_grad_norm, dp, ws),
         )
         v = precond_buffer(inner.preconditioner_state)
         updates = grad.empty_like() if params is None else None
@@ -82,11 +82,11 @@ def cyclical_sgld_integrator(
         new_inner = inner._replace(count=inner.count + 1)
         return updates, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=new_inner)
 
-    def update_fn(gradient, state, *_):
+    def update_fn(gradient, state, *_, max_grad_norm=None):
         if is_sampling_phase(state.sgld_state.count, cycle_length, exploration_ratio):
-            updates, inner = sgld.update(gradient, state.sgld_state)
+            updates, inner = sgld.update(gradient, state.sgld_state, max_grad_norm=max_grad_norm)
             return updates, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner)
-        return _explore(gradient, state, None)
+        return _explore(gradient, state, None, max_grad_norm=max_grad_norm)
 
     def _sync_precond(state, dp, scheme):
         """Data-parallel RMSprop: the two phases split the elements differently over the ranks and the moment estimates
@@ -99,13 +99,13 @@ def cyclical_sgld_integrator(
             dp.gather_owned(v.flat, last, v.lens, v.offsets)
         ws["v_scheme"] = scheme if dp is not None else None
 
-    def apply_fn(params: FlatTree, gradient, state, joint=None, dp=None):
+    def apply_fn(params: FlatTree, gradient, state, joint=None, dp=None, max_grad_norm=None):
         sampling = is_sampling_phase(state.sgld_state.count, cycle_length, exploration_ratio)
         _sync_precond(state, dp, "tiles" if sampling else "elems")
         if sampling:
-            _, inner = sgld.apply(params, gradient, state.sgld_state, joint=joint, dp=dp)
+            _, inner = sgld.apply(params, gradient, state.sgld_state, joint=joint, dp=dp, max_grad_norm=max_grad_norm)
             return params, OptaxCyclicalSGLDState(sgd_state=state.sgd_state, sgld_state=inner)
-        _, new_state = _explore(gradient, state, params, joint=joint, dp=dp)
+        _, new_state = _explore(gradient, state, params, joint=joint, dp=dp, max_grad_norm=max_grad_norm)
         return params, new_state
 
     def dp_gather(state, dp):

@@ -42,7 +42,7 @@ def batched_log_joint_prob(bound: BoundModel, prior, inputs: torch.Tensor, targe
 
 def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader, n_epochs: int, val_data_loader=None,
                log_likelihood_sum=categorical_log_likelihood_sum, save_chain=None,
-               save_every_n_steps=None, fuse_prior: bool = True) -> Dict[str, np.ndarray]:
+               save_every_n_steps=None, fuse_prior: bool = True, max_grad_norm=None) -> Dict[str, np.ndarray]:
     """``save_chain(state)`` writes the chain checkpoint (``<save_checkpoint_dir>/c``): every ``save_every_n_steps``
     steps (fortuna/training/trainer.py:236-247) and once when training ends (:146-150)."""
     state = TrainState.create(params=bound.params, tx=tx)
@@ -83,19 +83,19 @@ def run_sgmcmc(bound: BoundModel, prior, tx, callbacks: List, train_data_loader,
                 # the log prior of the pre-update parameters, for the logged value only (the step kernel forms its gradient)
                 with torch.no_grad():
                     lp = sum(prior.log_joint_prob(p) for p in bound.trainable.values())
-                state = state.apply_gradients(grads=bound.grads, joint=(scale, prec, None), dp=dp)
+                state = state.apply_gradients(grads=bound.grads, joint=(scale, prec, None), dp=dp, max_grad_norm=max_grad_norm)
                 lj = (lp.double() + scale * ll.detach().double()).float()
             elif fuse:
                 ll = log_likelihood_sum(bound.model(x), y)
                 ll.backward()                                # d sum-log-lik / d theta lands in bound.grads (flat)
                 scale = n_data / x.shape[0]
                 sq = torch.empty(1, dtype=torch.float64, device=dev)
-                state = state.apply_gradients(grads=bound.grads, joint=(scale, prec, sq))
+                state = state.apply_gradients(grads=bound.grads, joint=(scale, prec, sq), max_grad_norm=max_grad_norm)
                 lj = (lp_const - 0.5 * prec * sq[0] + scale * ll.detach().double()).float()
             else:
                 lj = batched_log_joint_prob(bound, prior, x, y, n_data, log_likelihood_sum)
                 lj.backward()                                    # d log-joint / d theta lands in bound.grads (flat)
-                state = state.apply_gradients(grads=bound.grads)  # fused sampler step, params updated in place
+                state = state.apply_gradients(grads=bound.grads, max_grad_norm=max_grad_norm)  # fused sampler step, in place
             for cb in callbacks:
                 state = cb.training_step_end(state)
             if save_chain is not None and save_every_n_steps and state.step % save_every_n_steps == 0:

@@ -20,13 +20,15 @@ class TrainState(NamedTuple):
         params = as_flat_tree(params)
         return cls(step=0, params=params, tx=tx, opt_state=tx.init(params), mutable=mutable)
 
-    def apply_gradients(self, grads, joint=None, dp=None, **kwargs):
+    def apply_gradients(self, grads, joint=None, dp=None, max_grad_norm=None, **kwargs):
         """flax TrainState.apply_gradients: tx.update + optax.apply_updates + step += 1, in one launch.
-        ``joint`` (see sghmc_integrator.apply) additionally fuses the log-joint gradient assembly into that launch."""
+        ``joint`` (see sghmc_integrator.apply) additionally fuses the log-joint gradient assembly into that launch;
+        ``max_grad_norm`` the trainer's gradient clipping (fortuna/training/trainer.py:158-169)."""
+        extra = {"max_grad_norm": max_grad_norm} if max_grad_norm else {}
         if dp is not None:
-            params, opt_state = self.tx.apply(self.params, grads, self.opt_state, joint=joint, dp=dp)
+            params, opt_state = self.tx.apply(self.params, grads, self.opt_state, joint=joint, dp=dp, **extra)
         elif joint is not None:
-            params, opt_state = self.tx.apply(self.params, grads, self.opt_state, joint=joint)
+            params, opt_state = self.tx.apply(self.params, grads, self.opt_state, joint=joint, **extra)
         else:
-            params, opt_state = self.tx.apply(self.params, grads, self.opt_state)
+            params, opt_state = self.tx.apply(self.params, grads, self.opt_state, **extra)
         return self._replace(step=self.step + 1, params=params, opt_state=opt_state, **kwargs)

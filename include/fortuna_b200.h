@@ -87,6 +87,11 @@ int fb200_sgmcmc_build_tiles_host(const fb200_leaf_t* leaves_host, int n_leaves,
                                   int64_t n_tiles);
 
 typedef struct {
+  float lik_scale;
+  float prior_prec;
+} fb200_joint_grad_t;
+
+typedef struct {
   float step_size;        /* epsilon_t = step_schedule(count), evaluated by the caller in float32       */
   double momentum_decay;  /* beta as the python float Fortuna holds; 0 for SGLD.  The library forms      */
                           /* float32(beta) and sqrt(float32(2*(1-beta))) exactly as jax weak-typing does */
@@ -94,6 +99,11 @@ typedef struct {
   int32_t rmsprop;        /* 0 identity preconditioner, 1 RMSprop                                        */
   double rms_alpha;       /* running_average_factor (python float); float32(alpha), float32(1-alpha)     */
   double rms_eps;         /* eps (python float)                                                          */
+  /* gradient-side options; zero-initialised = off, so older callers are unaffected */
+  const float* grad_mult; /* optional DEVICE float[1]: the gradient is scaled by it inside the step - the multiplier of
+                             clip_grandients_by_norm (fortuna/utils/training.py:14-20), see fb200_grad_clip_mult      */
+  int32_t grad_dtype;     /* dtype of `grad`: FB200_F32 (0) or FB200_BF16 (1: 18 instead of 20 B/param; single-GPU
+                             fb200_sgmcmc_step_f32 / _joint_f32 only)                                                */
 } fb200_sgmcmc_hparams_t;
 
 /* One sampling step (SGHMC, or the SGLD phase of cyclical SGLD with momentum_decay = 0):
@@ -110,6 +120,16 @@ int fb200_sgmcmc_step_f32(float* params, const float* grad, float* momentum, flo
                           uint32_t* key_out, uint32_t* leaf_keys_ws, const fb200_sgmcmc_hparams_t* hp,
                           void* stream);
 
+/* Gradient clipping by global norm (fortuna/utils/training.py:14-20, call site fortuna/training/trainer.py:168-169):
+ *   mult = min(1, max_grad_norm / (1e-7 + sqrt(sum g^2)))   (float32; the sum of squares in float64, deterministic)
+ * written to mult_out (device float[1]); hand that pointer to the step through hp->grad_mult and the scaling rides inside
+ * the step kernel - the clipped gradient is never written.  joint (optional): g is the log-joint gradient the fused
+ * mode forms, lik_scale * grad - prior_prec * params (then `params` is required), else g = grad.  One extra read of the
+ * gradient (4 B/param; 8 with the prior).  workspace: fb200_grad_clip_workspace_doubles(n) doubles. */
+int64_t fb200_grad_clip_workspace_doubles(int64_t n);
+int fb200_grad_clip_mult(const void* grad, int grad_dtype, const float* params, const fb200_joint_grad_t* joint, int64_t n,
+                         float max_grad_norm, double* workspace, float* mult_out, void* stream);
+
 /* Exploration step of cyclical SGLD (cyclical_sgld_integrator.py:65-84): preconditioner update and
  * u = (eps_t g) / (eps + sqrt(v')); params += u; no noise; key and momentum untouched. */
 int fb200_sgd_explore_step_f32(float* params, const float* grad, float* precond_v, float* updates_out,
@@ -124,10 +144,6 @@ int fb200_sgd_explore_step_f32(float* params, const float* grad, float* precond_
  * sum(theta^2) of the PRE-update parameters - the log-prior value -0.5 (prec * sum + n (log 2 pi + log_var)) of the
  * logged loss; sq_workspace: double[n_tiles] (step) / double[fb200_sgd_explore_joint_workspace_doubles(n)] (explore),
  * required iff theta_sq_out is given.  params is required (in-place apply mode only). */
-typedef struct {
-  float lik_scale;
-  float prior_prec;
-} fb200_joint_grad_t;
 int fb200_sgmcmc_step_joint_f32(float* params, const float* grad_loglik, float* momentum, float* precond_v, int64_t n,
                                 const fb200_leaf_t* leaves, int n_leaves, const fb200_tile_t* tiles, int64_t n_tiles,
                                 const uint32_t* key_in, uint32_t* key_out, uint32_t* leaf_keys_ws,

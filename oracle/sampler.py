@@ -219,6 +219,26 @@ def sghmc_update_selected(grad_sel, mom_sel, v_sel, rng_key, count, n_leaves, mo
     return updates, momentum, v, new_key
 
 
+def clip_gradients_by_norm(grad, max_grad_norm):
+    """fortuna/utils/training.py:14-20 (``clip_grandients_by_norm``): norm = sqrt(tree_reduce(x + sum(y**2))) over the
+    leaves in flatten order, mult = minimum(1, max_grad_norm / (1e-7 + norm)), grad <- mult * grad, all float32.
+    (XLA's and numpy's float32 ``sum`` associate differently - pairwise blocks either way - so the norm agrees to
+    rounding, not bits; the GPU kernel sums in float64.)"""
+    acc = F32(0)
+    for _, leaf in tree_flatten(grad):
+        acc = F32(acc + np.sum(leaf.astype(F32) ** 2, dtype=F32))
+    norm = np.sqrt(acc, dtype=F32)
+    mult = np.minimum(F32(1), F32(max_grad_norm) / (F32(1e-7) + norm)).astype(F32)
+    return tree_map(lambda z: (mult * z).astype(F32), grad), mult
+
+
+def round_to_bf16(x):
+    """float32 -> nearest bfloat16 (ties to even) -> float32: what a bf16 gradient buffer holds."""
+    u = np.ascontiguousarray(x, dtype=F32).view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(F32)
+
+
 def apply_updates(params, updates):
     """optax.apply_updates as used by flax TrainState.apply_gradients: p + u."""
     return tree_map(lambda p, u: (p + u).astype(p.dtype), params, updates)

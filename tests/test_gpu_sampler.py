@@ -19,9 +19,10 @@ def _grad_tree(params, seed):
     return osamp.tree_map(lambda p: (0.3 * r.standard_normal(p.shape) + p).astype(np.float32), params)
 
 
-def _assert_tree_close(got, want, what):
+def _assert_tree_close(got, want, what, floor=0.0):
+    """floor: absolute floor for trees whose steps are much larger than some (cancelling) leaf values."""
     for (path, g), (_, w) in zip(osamp.tree_flatten(got), osamp.tree_flatten(want)):
-        atol = 1e-6 * max(1e-30, float(np.max(np.abs(w))))
+        atol = max(floor, 1e-6 * max(1e-30, float(np.max(np.abs(w)))))
         np.testing.assert_allclose(g, w, rtol=1e-5, atol=atol, err_msg=f"{what} {'/'.join(path)}")
 
 
@@ -242,3 +243,76 @@ def test_bert_base_tree_steps_match_oracle(cuda, precond):
             if precond == "rmsprop":
                 np.testing.assert_allclose(leaf(state.preconditioner_state.grad_moment_estimates, i), o_v[i], rtol=1e-5,
                                            err_msg=f"v {name} step {step}")
+
+
+@pytest.mark.parametrize("precond", ["identity", "rmsprop"])
+@pytest.mark.parametrize("joint", [False, True])
+def test_gradient_clipping_fused_into_the_step(cuda, precond, joint):
+    """clip_grandients_by_norm (fortuna/utils/training.py:14-20) as a norm pre-pass whose multiplier the
+    step kernel applies while loading the gradient - vs the oracle: clip the (log-joint) gradient, then the plain step.
+    Both regimes: a threshold above the norm (multiplier exactly 1) and one far below it."""
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+    from fortuna_b200.prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    params_np = trees.ragged_tree(4, scale=0.3)
+    lik_scale, prec = np.float32(7.5), np.float32(0.6)
+    for max_norm in (1e6, 0.05):
+        o_pre = osamp.Preconditioner(precond)
+        o_state = osamp.sghmc_init(params_np, oprng.PRNGKey(2), o_pre)
+        o_params = params_np
+        pre = pc.rmsprop_preconditioner() if precond == "rmsprop" else pc.identity_preconditioner()
+        tx = sghmc_integrator(0.02, None, ops.PRNGKey(2, cuda), sched.constant_schedule(1e-3), pre)
+        params = FlatTree.from_tree(params_np, device=cuda)
+        state = tx.init(params)
+        for step in range(3):
+            g_np = _grad_tree(o_params, 40 + step)
+            g_used = osamp.tree_map(lambda g, p: (lik_scale * g + (-prec) * p).astype(np.float32), g_np, o_params) if joint else g_np
+            g_clip, mult = osamp.clip_gradients_by_norm(g_used, max_norm)
+            assert (mult == 1) == (max_norm > 1)
+            upd, o_state = osamp.sghmc_update(g_clip, o_state, 0.02, osamp.constant_schedule(1e-3), o_pre)
+            o_params = osamp.apply_updates(o_params, upd)
+            params, state = tx.apply(params, FlatTree.from_tree(g_np, device=cuda), state,
+                                     joint=(float(lik_scale), float(prec), None) if joint else None, max_grad_norm=max_norm)
+            # parameters of scale 0.3 take steps of scale 0.05: a 1-element leaf that lands near zero keeps the absolute
+            # rounding of the larger operands (one ulp of 0.5 = 6e-8)
+            _assert_tree_close(params.to_numpy_tree(), o_params, f"params step {step} max_norm {max_norm}", floor=2e-7)
+            _assert_tree_close(state.momentum.to_numpy_tree(), o_state.momentum, f"momentum step {step}", floor=2e-7)
+
+
+def test_bf16_gradient_input(cuda):
+    """the step reads a bfloat16 gradient vector (18 instead of 20 B/param) - identical to the float32 step
+    on the same values (bf16 -> f32 is exact), for the vector path and the ragged leaves, with clipping on top."""
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+    from fortuna_b200.prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    params_np = trees.ragged_tree(6)
+    g_np = osamp.tree_map(osamp.round_to_bf16, _grad_tree(params_np, 77))
+    outs = []
+    for as_bf16 in (False, True):
+        tx = sghmc_integrator(0.05, None, ops.PRNGKey(8, cuda), sched.constant_schedule(2e-3), pc.rmsprop_preconditioner())
+        params = FlatTree.from_tree(params_np, device=cuda)
+        state = tx.init(params)
+        g = FlatTree.from_tree(g_np, device=cuda)
+        if as_bf16:
+            g = FlatTree(g.flat.to(torch.bfloat16), g.paths, g.shapes, g.offsets)
+            assert torch.equal(g.flat.float(), FlatTree.from_tree(g_np, device=cuda).flat)
+        for _ in range(2):
+            params, state = tx.apply(params, g, state, max_grad_norm=0.5)
+        outs.append((params.flat.clone(), state.momentum.flat.clone(), ops.key_to_host(state.rng_key)))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    # and against the oracle, one step, no clipping
+    o_pre = osamp.Preconditioner("rmsprop")
+    o_state = osamp.sghmc_init(params_np, oprng.PRNGKey(8), o_pre)
+    upd, o_state = osamp.sghmc_update(g_np, o_state, 0.05, osamp.constant_schedule(2e-3), o_pre)
+    tx = sghmc_integrator(0.05, None, ops.PRNGKey(8, cuda), sched.constant_schedule(2e-3), pc.rmsprop_preconditioner())
+    params = FlatTree.from_tree(params_np, device=cuda)
+    state = tx.init(params)
+    g = FlatTree.from_tree(g_np, device=cuda)
+    params, state = tx.apply(params, FlatTree(g.flat.to(torch.bfloat16), g.paths, g.shapes, g.offsets), state)
+    _assert_tree_close(params.to_numpy_tree(), osamp.apply_updates(params_np, upd), "params (bf16 gradient)")

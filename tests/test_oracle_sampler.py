@@ -126,3 +126,17 @@ def test_selected_leaves_step_equals_full_step():
                 assert np.array_equal(upd_s[i], uflat[i][1]) and np.array_equal(mom_s[i], m2[i][1])
                 if kind == "rmsprop":
                     assert np.array_equal(v_s[i], sampler.tree_flatten(st.precond)[i][1])
+
+
+def test_clip_by_norm_restatement():
+    """clip_gradients_by_norm (fortuna/utils/training.py:14-20): identity below the threshold, norm == max above it."""
+    r = np.random.default_rng(1)
+    g = {"a": r.standard_normal((7, 5)).astype(np.float32), "b": {"c": r.standard_normal(11).astype(np.float32)}}
+    norm = float(np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for _, v in sampler.tree_flatten(g))))
+    out, mult = sampler.clip_gradients_by_norm(g, 10 * norm)
+    assert mult == np.float32(1) and all(np.array_equal(a, b) for (_, a), (_, b) in zip(sampler.tree_flatten(out), sampler.tree_flatten(g)))
+    out, mult = sampler.clip_gradients_by_norm(g, 0.25 * norm)
+    new_norm = float(np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for _, v in sampler.tree_flatten(out))))
+    np.testing.assert_allclose(new_norm, 0.25 * norm, rtol=1e-5)
+    x = np.array([1.0, 1.00390625, 1.01171875, -3.3895314e38, 1e-40], np.float32)
+    np.testing.assert_array_equal(sampler.round_to_bf16(x)[:3], np.array([1.0, 1.0, 1.015625], np.float32))

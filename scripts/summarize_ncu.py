@@ -62,7 +62,7 @@ def summarize_rep(name, rep, tag):
                 return float(v.replace(",", "")) * scale
             rd = to_bytes(*d["dram__bytes_read.sum"])
             wr = to_bytes(*d["dram__bytes_write.sum"])
-            traffic[kname.split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()] = rd + wr
+            traffic[kname.replace("void ", "").split("(")[0].split("<")[0].split("::")[-1].strip()] = rd + wr
             lines.append(f"dram traffic per launch (read+write): {rd + wr:.4e} bytes")
         except Exception:
             pass

@@ -135,9 +135,6 @@ SIGNATURES = {
     "fb200_log_prob_from_lse": (_i, [_P, _i, _P, _P, _i, _i, _i, _P, _P, _P]),
     "fb200_transpose_w_bf16": (_i, [_P, _i, _P, _i, _i, _i, _P]),
     "fb200_bma_reduce_cls": (_i, [_P, _i, _P, _P, _i, _i, _i, C.POINTER(ClsOutputs), _P]),
-    "fb200_bma_reduce_cls_sets_workspace_bytes": (_sz, [_i]),
-    "fb200_bma_reduce_cls_sets": (_i, [_P, _i, _P, _P, _i, _i, _i, C.POINTER(ClsOutputs), _P, _i, _f, _P, _P, _P, _sz, _P]),
-    "fb200_debug_force_tiled": (_i, [_i]),
     "fb200_bma_reduce_cls_wide_workspace_bytes": (_sz, [_i, _i]),
     "fb200_bma_reduce_cls_wide": (_i, [_P, _i, _P, _P, _i, _i, _i, C.POINTER(ClsOutputs), _P, _sz, _P]),
     "fb200_cls_slot_row_floats": (_sz, [_i]),

@@ -14,8 +14,6 @@
 // producer warp with cp.async.bulk (TMA engine) into an mbarrier-signalled shared-memory ring.  Eight
 // consumer warps each own whole rows (G lanes per row), so the per-row max / sum-exp are warp-shuffle
 // reductions and the per-(b,c) sums over s live in registers until the tile's single store.
-#include <stdlib.h>
-
 #include "bma_reduce.cuh"
 
 namespace fb200 {
@@ -889,12 +887,6 @@ static int launch_cls_cfg(ClsArgs a, cudaStream_t st) {
 template <typename T, int G, int NV, int VEC, bool TAILONLY>
 static int launch_cls(const ClsArgs& a, cudaStream_t st) {
   if constexpr (NV * VEC >= 20) {
-    static const int cfg = [] {
-      const char* e = getenv("FB200_K3_CFG");  // experiment knob: 1 = 16 warps x 1 sample, 2 = 8 x 2
-      return e ? atoi(e) : 0;
-    }();
-    if (cfg == 1) return launch_cls_cfg<T, G, NV, VEC, TAILONLY, 16, 1>(a, st);
-    if (cfg == 2) return launch_cls_cfg<T, G, NV, VEC, TAILONLY, 8, 2>(a, st);
     return launch_cls_cfg<T, G, NV, VEC, TAILONLY, 12, 2>(a, st);
   } else {
     return launch_cls_cfg<T, G, NV, VEC, TAILONLY, 16, 2>(a, st);
@@ -943,25 +935,6 @@ static int dispatch_cls(const ClsArgs& a, cudaStream_t st) {
 
 using namespace fb200;
 
-// Wide rows (128 < C <= 1024) have two kernels: the tiled one (default: a CTA-wide ring fed by a producer warp; 2.55 ms at
-// c4, HBM-bound) and the warp-autonomous one of bma_reduce_rows.cu (2.66 ms; it exists for the fused conformal-set
-// epilogue, fb200_bma_reduce_cls_sets(..., fuse = 1)).  FB200_K3_ROWS=1 in the environment, or
-// fb200_debug_force_tiled(0), selects the warp-autonomous kernel for plain reductions too - for A/B measurements and for
-// the tests that hold the two designs bit-identical.
-static int g_force_tiled = -1;
-static bool k3_force_tiled() {
-  if (g_force_tiled < 0) {
-    const char* e = getenv("FB200_K3_ROWS");
-    g_force_tiled = (e && e[0] == '1') ? 0 : 1;
-  }
-  return g_force_tiled == 1;
-}
-extern "C" int fb200_debug_force_tiled(int on) {
-  const int prev = k3_force_tiled() ? 1 : 0;
-  if (on >= 0) g_force_tiled = on ? 1 : 0;
-  return prev;
-}
-
 static int reduce_cls_common(ClsArgs& a, const void* logits, int dtype, const float* log_temp,
                              const int32_t* targets, int S, int B, int C, void* stream) {
   if (!logits) return FB200_E_NULL;
@@ -985,8 +958,6 @@ static int reduce_cls_common(ClsArgs& a, const void* logits, int dtype, const fl
     if (dtype == FB200_F32) return launch_cls_narrow<float>(a, (cudaStream_t)stream);
     return launch_cls_narrow<__nv_bfloat16>(a, (cudaStream_t)stream);
   }
-  // wide rows: the warp-autonomous kernel
-  if (!k3_force_tiled() && cls_rows_supported(a, dtype)) return launch_cls_rows(a, dtype, (cudaStream_t)stream);
   if (dtype == FB200_F32) return dispatch_cls<float>(a, (cudaStream_t)stream);
   return dispatch_cls<__nv_bfloat16>(a, (cudaStream_t)stream);
 }
@@ -998,60 +969,6 @@ extern "C" int fb200_bma_reduce_cls(const void* logits, int dtype, const float* 
   a.out = *out;
   if ((a.out.log_prob || a.out.ensemble_log_prob || a.out.brier_terms) && !targets) return FB200_E_NULL;
   return reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
-}
-
-namespace fb200 {
-int aps_sets_for_rows(const float* probs, int B, int C, const float* val_sorted, int q_index, int all_true, int all_false,
-                      uint8_t* mask, int32_t* sizes, const int32_t* row_list, const int32_t* row_count, int max_ctas,
-                      cudaStream_t st);
-long long conformal_rank_bound_host(float threshold, int n_val);
-}  // namespace fb200
-
-extern "C" size_t fb200_bma_reduce_cls_sets_workspace_bytes(int B) { return B > 0 ? ((size_t)B + 4) * sizeof(int32_t) : 0; }
-
-extern "C" int fb200_bma_reduce_cls_sets(const void* logits, int dtype, const float* log_temp, const int32_t* targets,
-                                         int S, int B, int C, const fb200_cls_outputs_t* out,
-                                         const float* val_scores_sorted, int n_val, float threshold, uint8_t* mask,
-                                         int32_t* sizes, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!out || !val_scores_sorted || !mask || !out->mean) return FB200_E_NULL;
-  if (n_val <= 0) return FB200_E_SHAPE;
-  ClsArgs a{};
-  a.out = *out;
-  if ((a.out.log_prob || a.out.ensemble_log_prob || a.out.brier_terms) && !targets) return FB200_E_NULL;
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long K = conformal_rank_bound_host(threshold, n_val);
-  const int all_true = K >= n_val, all_false = K < 0;
-  const int q_index = (all_true || all_false) ? 0 : (int)(n_val - 1 - K);
-  a.logits = logits;
-  a.C = C;
-  a.cs_mask = mask;
-  const bool fused = logits && C > 0 && (dtype == FB200_F32 || dtype == FB200_BF16) && !k3_force_tiled() &&
-                     cls_rows_supported(a, dtype);
-  if (!fused) {
-    // rows the in-register epilogue does not cover (narrow or ragged heads): reduction, then the scoring kernel
-    a.cs_mask = nullptr;
-    const int rc = reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
-    if (rc != 0) return rc;
-    return fb200_aps_conformal_sets(out->mean, B, C, val_scores_sorted, n_val, threshold, nullptr, mask, sizes, stream);
-  }
-  if (!workspace) return FB200_E_NULL;
-  if (workspace_bytes < fb200_bma_reduce_cls_sets_workspace_bytes(B)) return FB200_E_WORKSPACE;
-  int32_t* ws = reinterpret_cast<int32_t*>(workspace);
-  cudaError_t e = cudaMemsetAsync(ws, 0, 4 * sizeof(int32_t), st);
-  if (e != cudaSuccess) return (int)e;
-  a.cs_sizes = sizes;
-  a.cs_val_sorted = val_scores_sorted;
-  a.cs_q_index = q_index;
-  a.cs_all_true = all_true;
-  a.cs_all_false = all_false;
-  a.fb_count = ws;
-  a.fb_rows = ws + 4;
-  const int rc = reduce_cls_common(a, logits, dtype, log_temp, targets, S, B, C, stream);
-  if (rc != 0) return rc;
-  if (all_true || all_false) return 0;
-  // general path for the listed rows (usually none or a handful: a few CTAs find the list empty and exit)
-  return aps_sets_for_rows(out->mean, B, C, val_scores_sorted, q_index, all_true, all_false, mask, sizes, ws + 4, ws,
-                           2 * sm_count(), st);
 }
 
 extern "C" size_t fb200_bma_reduce_cls_wide_workspace_bytes(int S, int B) {

@@ -1,6 +1,5 @@
-// Shared pieces of the BMA reduction kernels (bma_reduce.cu: tiled / narrow / wide / finalise; bma_reduce_rows.cu: the
-// warp-autonomous kernel with the fused conformal-set epilogue): launch arguments, row loads, the packed per-logit
-// arithmetic (process_rows).
+// Shared pieces of the BMA reduction kernels (bma_reduce.cu: tiled / narrow / wide / finalise): launch arguments, row
+// loads, the packed per-logit arithmetic (process_rows), the compact row-constant division.
 #pragma once
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -43,18 +42,6 @@ struct ClsArgs {
   uint32_t stage_bytes;        // multiple of 128
   int bulk_ok;                 // base pointer and sample stride are 16-byte aligned
   float log_S;                 // float32 log(S)
-  // warp-autonomous kernel (bma_reduce_cls_rows_kernel)
-  uint32_t row_bytes, row_stride_bytes;  // one row of logits; its slot in the warp's ring (multiple of 16)
-  int row_rot;                           // shard mode: rows are visited starting here
-  int stagger_ns;                        // warp w starts w * stagger_ns late (fused sets: de-phases the row epilogues)
-  // fused APS conformal sets (conformal/classification/adaptive_prediction.py:11-22 + base.py:45-64) on the mean row
-  uint8_t* cs_mask;            // [B,C] or null
-  int32_t* cs_sizes;           // [B] or null
-  const float* cs_val_sorted;  // sorted validation scores
-  int cs_q_index;              // n_val - 1 - K: in the set  <=>  !(score < val_sorted[cs_q_index])
-  int cs_all_true, cs_all_false;
-  int32_t* fb_count;           // [1] rows that need the general (rank lookup) path ...
-  int32_t* fb_rows;            // [B] ... and which
 };
 
 template <typename T, int VEC>
@@ -246,9 +233,5 @@ static inline int sm_count() {
   }
   return cached[dev];
 }
-
-// bma_reduce_rows.cu: 0 = launched, FB200_E_UNSUPPORTED = shape not covered (caller uses the tiled kernel)
-bool cls_rows_supported(const ClsArgs& a, int dtype);
-int launch_cls_rows(const ClsArgs& a, int dtype, cudaStream_t st);
 
 }  // namespace fb200

@@ -1,7 +1,6 @@
-// Warp-level row sort building blocks shared by the scoring kernels (scoring.cu) and the fused conformal-set
-// epilogue of the reduction kernel (bma_reduce.cu): order-preserving float <-> uint maps, the key-only 32-bit
-// bitonic network over 32*NR register-resident keys, and the inclusive prefix sum in jnp.cumsum's association
-// order (jax.lax.associative_scan).  See scoring.cu for the derivations.
+// Warp-level row sort building blocks of the scoring kernels (scoring.cu): order-preserving float <-> uint maps, the
+// key-only 32-bit bitonic network over 32*NR register-resident keys, and the inclusive prefix sum in jnp.cumsum's
+// association order (jax.lax.associative_scan).  See scoring.cu for the derivations.
 #pragma once
 #include <stdint.h>
 

@@ -34,11 +34,6 @@ struct RowSortArgs {
   const float* cs_val_sorted;
   int cs_q_index;          // n_val - 1 - K
   int cs_all_true, cs_all_false;
-  // optional row list (key-only kernel, all-class mode): process rows row_list[0 .. *row_count) instead of 0 .. B-1 -
-  // the rows the fused epilogue of the reduction kernel (bma_reduce_rows.cu) left to the general path
-  const int32_t* row_list;
-  const int32_t* row_count;
-  int max_ctas;  // 0 = default grid
 };
 
 __global__ void __launch_bounds__(256) row_sort_cumsum_kernel(const RowSortArgs a) {
@@ -358,12 +353,9 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
   int* scnt = reinterpret_cast<int*>(skey);  // tie pass only; the sorted keys are dead by then
   const bool vec16 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.probs) & 15) == 0);
   const int nwarps = gridDim.x * kSortWarps;
-  const int n_rows = (MODE == 0 && a.row_count) ? min(*a.row_count, a.B) : a.B;
-  auto row_at = [&](int i) { return (MODE == 0 && a.row_list) ? a.row_list[i] : i; };
-  int bi = blockIdx.x * kSortWarps + warp_in_cta;
-  if (bi < n_rows) row_prefetch<NR>(srow, a.probs + (size_t)row_at(bi) * C, C, lane, vec16);
-  for (; bi < n_rows; bi += nwarps) {
-    const int b = row_at(bi);
+  int b = blockIdx.x * kSortWarps + warp_in_cta;
+  if (b < a.B) row_prefetch<NR>(srow, a.probs + (size_t)b * C, C, lane, vec16);
+  for (; b < a.B; b += nwarps) {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     uint32_t own[NR], key[NR];
@@ -389,7 +381,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
         tpos = cnt;
       }
       __syncwarp();
-      if (bi + nwarps < n_rows) row_prefetch<NR>(srow, a.probs + (size_t)row_at(bi + nwarps) * C, C, lane, vec16);
+      if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
     }
     warp_bitonic_sort32<NR>(key, lane);
     float x[NR];
@@ -450,7 +442,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
           }
           if (lane == 0 && a.cs_sizes) a.cs_sizes[b] = n_true;
           __syncwarp();
-          if (bi + nwarps < n_rows) row_prefetch<NR>(srow, a.probs + (size_t)row_at(bi + nwarps) * C, C, lane, vec16);
+          if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
           done = true;
         }
       }
@@ -470,7 +462,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
         asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(ad), "f"(x[r]), "n"(PAD * 4) : "memory");
       }
       __syncwarp();
-      if (bi + nwarps < n_rows) row_prefetch<NR>(srow, a.probs + (size_t)row_at(bi + nwarps) * C, C, lane, vec16);
+      if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
       // lower bound, kept as the shared-space BYTE address of the slot so that a probe is one LDS with an
       // immediate offset, one compare and one predicated add
       uint32_t ap[NR];
@@ -539,7 +531,6 @@ static int launch_row_sort32_warp(const RowSortArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)kSortWarps * words * sizeof(uint32_t);
   int grid = (a.B + kSortWarps - 1) / kSortWarps;
   if (grid > 148 * 16) grid = 148 * 16;
-  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
   if (mode == 0) {
     auto kern = row_sort32_warp_kernel<NR, 0>;
     if (smem > 48 * 1024) {
@@ -1234,31 +1225,6 @@ extern "C" int fb200_aps_conformal_sets(const float* probs, int B, int C, const 
   a.cs_q_index = (a.cs_all_true || a.cs_all_false) ? 0 : (int)(n_val - 1 - K);
   return launch_row_sort(a, (cudaStream_t)stream);
 }
-
-// The fused reduction epilogue's general path: APS sets of the listed rows of `probs` (bma_reduce.cu calls this on the
-// rows its in-register threshold test could not decide: equal probabilities or a non-monotone boundary).
-namespace fb200 {
-int aps_sets_for_rows(const float* probs, int B, int C, const float* val_sorted, int q_index, int all_true, int all_false,
-                      uint8_t* mask, int32_t* sizes, const int32_t* row_list, const int32_t* row_count, int max_ctas,
-                      cudaStream_t st) {
-  RowSortArgs a{};
-  a.probs = probs;
-  a.B = B;
-  a.C = C;
-  a.set_threshold = INFINITY;
-  a.cs_mask = mask;
-  a.cs_sizes = sizes;
-  a.cs_val_sorted = val_sorted;
-  a.cs_q_index = q_index;
-  a.cs_all_true = all_true;
-  a.cs_all_false = all_false;
-  a.row_list = row_list;
-  a.row_count = row_count;
-  a.max_ctas = max_ctas;
-  return launch_row_sort(a, st);
-}
-long long conformal_rank_bound_host(float threshold, int n_val) { return conformal_rank_bound(threshold, n_val); }
-}  // namespace fb200
 
 extern "C" int fb200_conformal_sets(const float* val_scores_sorted, int n_val, const float* test_scores, int B,
                                     int C, float threshold, uint8_t* mask, int32_t* sizes, void* stream) {

@@ -488,37 +488,6 @@ def bma_reduce_cls(logits, want, targets=None, log_temp=None, out=None):
     return outs
 
 
-def bma_reduce_cls_sets(logits, want, val_sorted, threshold, targets=None, log_temp=None, out=None, mask=None, sizes=None,
-                        workspace=None):
-    """The single-pass reductions plus the APS conformal sets of the mean row in one call (fb200_bma_reduce_cls_sets):
-    returns (outs, mask uint8 [B,C], sizes int32 [B]).  `want` must contain "mean"."""
-    S, B, Cn = logits.shape
-    if Cn > 1024:
-        outs = bma_reduce_cls(logits, want, targets=targets, log_temp=log_temp, out=out)
-        m, sz = conformal_sets(val_sorted, aps_scores(outs["mean"], None), threshold)
-        return outs, m, sz
-    outs = out if out is not None else _alloc_cls_outputs(tuple(want), S, B, Cn, logits.device)
-    if "mean" not in outs:
-        raise ValueError("the fused conformal sets are those of the mean: request it")
-    st = _cls_struct(outs)
-    if mask is None:
-        mask = torch.empty((B, Cn), dtype=torch.uint8, device=logits.device)
-    if sizes is None:
-        sizes = torch.empty(B, dtype=torch.int32, device=logits.device)
-    nbytes = int(lib().fb200_bma_reduce_cls_sets_workspace_bytes(B))
-    if workspace is None or workspace.numel() < nbytes:
-        workspace = torch.empty(nbytes, dtype=torch.uint8, device=logits.device)
-    check(
-        lib().fb200_bma_reduce_cls_sets(
-            _ptr(logits, (torch.float32, torch.bfloat16)), _DT[logits.dtype], _ptr(log_temp, torch.float32, True),
-            _ptr(targets, torch.int32, True), S, B, Cn, C.byref(st), _ptr(val_sorted, torch.float32), val_sorted.numel(),
-            float(np.float32(threshold)), _ptr(mask, torch.uint8), _ptr(sizes, torch.int32), _ptr(workspace), nbytes, _stream(),
-        ),
-        "fb200_bma_reduce_cls_sets",
-    )
-    return outs, mask, sizes
-
-
 def cls_slot_row_floats(Cn):
     """Floats per row of a shard slot: [sum p (C) | sum p^2 (C) | sum plogp, ll_max, ll_sumexp, 0]."""
     return int(lib().fb200_cls_slot_row_floats(int(Cn)))

@@ -72,8 +72,7 @@ class PhaseTimer:
 
 
 class PredictivePipeline:
-    def __init__(self, S, B, C, device, want: Sequence[str], world: int = 1, rank: int = 0, transport: Optional[str] = None,
-                 fused_sets: bool = False):
+    def __init__(self, S, B, C, device, want: Sequence[str], world: int = 1, rank: int = 0, transport: Optional[str] = None):
         self.S, self.B, self.C = S, B, C
         self.device = device
         self.want = tuple(want)
@@ -88,8 +87,6 @@ class PredictivePipeline:
         self.thresholds = torch.from_numpy(ece_thresholds(B)).to(device)
         self.transport = "single"
         self.timer: Optional[PhaseTimer] = None
-        self.fused_sets = bool(fused_sets) and world == 1 and C <= 1024
-        self._sets_ws = None
         if world > 1:
             from .sharded import PeerSlots, SampleShardExchange
 
@@ -117,25 +114,14 @@ class PredictivePipeline:
             self.timer.mark(name)
 
     # -------------------------------------------------------------------------------- K3 / K4
-    def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor], kernel_events=None, calib=None):
-        """kernel_events: optional (start, end) CUDA events recorded around the reduction kernel alone.
-        calib: with ``fused_sets``, the conformal calibration whose APS sets the same launch emits."""
+    def reduce(self, z: torch.Tensor, targets: Optional[torch.Tensor], kernel_events=None):
+        """kernel_events: optional (start, end) CUDA events recorded around the reduction kernel alone."""
         self._mark("begin")
         if kernel_events:
             kernel_events[0].record()
         if self.world == 1:
             want = self._kernel_want if targets is not None else self.want
-            if self.fused_sets and calib is not None:
-                if self._sets_ws is None:
-                    self.mask = torch.empty((self.B, self.C), dtype=torch.uint8, device=self.device)
-                    self.sizes = torch.empty(self.B, dtype=torch.int32, device=self.device)
-                    self._sets_ws = torch.empty(int(ops.lib().fb200_bma_reduce_cls_sets_workspace_bytes(self.B)),
-                                                dtype=torch.uint8, device=self.device)
-                self.outs, self.mask, self.sizes = ops.bma_reduce_cls_sets(
-                    z, want, calib.val_sorted, calib.threshold, targets=targets, out=self.outs or None, mask=self.mask,
-                    sizes=self.sizes, workspace=self._sets_ws)
-            else:
-                self.outs = ops.bma_reduce_cls(z, want, targets=targets, out=self.outs or None)
+            self.outs = ops.bma_reduce_cls(z, want, targets=targets, out=self.outs or None)
             if kernel_events:
                 kernel_events[1].record()
             self._mark("reduce")
@@ -169,8 +155,7 @@ class PredictivePipeline:
         mean = self.outs["mean"]
         lo, hi = self.rank * self.B_local, (self.rank + 1) * self.B_local
         t_local = targets[lo:hi] if self.world > 1 else targets
-        if not (self.fused_sets and self._sets_ws is not None):
-            self.mask, self.sizes = aps_sets(mean, calib)
+        self.mask, self.sizes = aps_sets(mean, calib)
         self._mark("sets")
         if "confidence" in self.outs:
             # the reduction kernel's epilogue already holds max_c mean, its arg-max and the Brier term of every row

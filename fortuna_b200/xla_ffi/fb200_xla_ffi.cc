@@ -1,7 +1,6 @@
 // XLA-FFI shim over the C ABI of include/fortuna_b200.h - the binding north_star names ("thin jax.ffi custom-call
 // bindings").  One handler per hot-path entry point the Python mirror (fortuna_b200/ops.py) calls: PRNG, the sampler
-// steps, the sample bank, the last-layer contraction, the single-pass reductions (plain, fused sets, wide, shard,
-// finalise), the scoring kernels and the ECE.  Every handler only unpacks buffers / attributes and forwards to ONE
+// steps, the sample bank, the last-layer contraction, the single-pass reductions (plain, wide, shard, finalise), the scoring kernels and the ECE.  Every handler only unpacks buffers / attributes and forwards to ONE
 // fb200_* call on XLA's stream; no arithmetic lives here.  Conventions:
 //   * an OPTIONAL input (targets, log_temp, bias, sample_idx, ...) is passed as a zero-element buffer;
 //   * an unwanted OUTPUT of the reduction kernels is a zero-element result buffer (XLA still needs a result slot);
@@ -169,7 +168,7 @@ static ffi::Error SgmcmcStep(cudaStream_t s, F32 params, F32 grad, F32 momentum,
   CopyIfNotAliased(params.typed_data(), params_out->typed_data(), n * 4, s);
   CopyIfNotAliased(momentum.typed_data(), momentum_out->typed_data(), n * 4, s);
   if (rmsprop) CopyIfNotAliased(precond_v.typed_data(), precond_out->typed_data(), n * 4, s);
-  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps};
+  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps, nullptr, FB200_F32};
   return Check(fb200_sgmcmc_step_f32(params_out->typed_data(), grad.typed_data(), momentum_out->typed_data(),
                                      rmsprop ? precond_out->typed_data() : nullptr, nullptr, static_cast<int64_t>(n),
                                      reinterpret_cast<const fb200_leaf_t*>(leaves.typed_data()), Dim(leaves, 0),
@@ -195,7 +194,7 @@ static ffi::Error SgmcmcStepJoint(cudaStream_t s, F32 params, F32 grad, F32 mome
   CopyIfNotAliased(params.typed_data(), params_out->typed_data(), n * 4, s);
   CopyIfNotAliased(momentum.typed_data(), momentum_out->typed_data(), n * 4, s);
   if (rmsprop) CopyIfNotAliased(precond_v.typed_data(), precond_out->typed_data(), n * 4, s);
-  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps};
+  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps, nullptr, FB200_F32};
   fb200_joint_grad_t jg{lik_scale, prior_prec};
   return Check(fb200_sgmcmc_step_joint_f32(params_out->typed_data(), grad.typed_data(), momentum_out->typed_data(),
                                            rmsprop ? precond_out->typed_data() : nullptr, static_cast<int64_t>(n),
@@ -217,7 +216,7 @@ static ffi::Error SgdExploreStep(cudaStream_t s, F32 params, F32 grad, F32 preco
   const size_t n = grad.element_count();
   CopyIfNotAliased(params.typed_data(), params_out->typed_data(), n * 4, s);
   if (rmsprop) CopyIfNotAliased(precond_v.typed_data(), precond_out->typed_data(), n * 4, s);
-  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps};
+  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps, nullptr, FB200_F32};
   return Check(fb200_sgd_explore_step_f32(params_out->typed_data(), grad.typed_data(),
                                           rmsprop ? precond_out->typed_data() : nullptr, nullptr, static_cast<int64_t>(n), &hp, s),
                "fb200_sgd_explore_step_f32");
@@ -231,7 +230,7 @@ static ffi::Error SgdExploreStepJoint(cudaStream_t s, F32 params, F32 grad, F32 
   const size_t n = grad.element_count();
   CopyIfNotAliased(params.typed_data(), params_out->typed_data(), n * 4, s);
   if (rmsprop) CopyIfNotAliased(precond_v.typed_data(), precond_out->typed_data(), n * 4, s);
-  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps};
+  fb200_sgmcmc_hparams_t hp{step_size, momentum_decay, zero_momentum, rmsprop, rms_alpha, rms_eps, nullptr, FB200_F32};
   fb200_joint_grad_t jg{lik_scale, prior_prec};
   return Check(fb200_sgd_explore_step_joint_f32(params_out->typed_data(), grad.typed_data(),
                                                 rmsprop ? precond_out->typed_data() : nullptr, static_cast<int64_t>(n), &hp, &jg,
@@ -330,21 +329,6 @@ static ffi::Error BmaReduceCls(cudaStream_t s, Any logits, F32 log_temp, S32 tar
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_bma_reduce_cls, BmaReduceCls,
                               ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Arg<F32>().Arg<S32>() FB200_CLS_OUT_BINDING.Ret<U8>());
-
-// the reductions + the APS conformal sets of the mean row (adaptive_prediction.py:11-22, conformal/classification/base.py:45-82)
-static ffi::Error BmaReduceClsSets(cudaStream_t s, Any logits, F32 log_temp, S32 targets, F32 val_sorted, FB200_CLS_OUT_PARAMS,
-                                   RU8 mask, RS32 sizes, RU8 ws, float threshold) {
-  const int dt = DTypeOf(logits);
-  if (dt < 0) return BadDType("fb200_xla_bma_reduce_cls_sets");
-  const fb200_cls_outputs_t o = FB200_CLS_OUT_STRUCT;
-  return Check(fb200_bma_reduce_cls_sets(logits.untyped_data(), dt, Opt(log_temp), Opt(targets), Dim(logits, 0), Dim(logits, 1),
-                                         Dim(logits, 2), &o, val_sorted.typed_data(), Dim(val_sorted, 0), threshold,
-                                         mask->typed_data(), Opt(sizes), Opt(ws), ws->size_bytes(), s),
-               "fb200_bma_reduce_cls_sets");
-}
-XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_bma_reduce_cls_sets, BmaReduceClsSets,
-                              ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Arg<F32>().Arg<S32>().Arg<F32>() FB200_CLS_OUT_BINDING
-                                  .Ret<U8>().Ret<S32>().Ret<U8>().Attr<float>("threshold"));
 
 // S-sharded mode: this rank's partial sums, row by row, into the owners' slots (peer or local memory)
 static ffi::Error BmaReduceClsShard(cudaStream_t s, Any logits, F32 log_temp, S32 targets, U64 slot_ptrs, RF32 ens_log_prob,

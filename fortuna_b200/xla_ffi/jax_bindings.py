@@ -42,7 +42,6 @@ _TARGETS = (
     "fb200_xla_transpose_w",
     "fb200_xla_softmax_rows",
     "fb200_xla_bma_reduce_cls",
-    "fb200_xla_bma_reduce_cls_sets",
     "fb200_xla_bma_reduce_cls_shard",
     "fb200_xla_bma_finalize_cls_slots",
     "fb200_xla_variance_combine",

@@ -277,27 +277,6 @@ typedef struct {
 int fb200_bma_reduce_cls(const void* logits, int dtype, const float* log_temp, const int32_t* targets, int S,
                          int B, int C, const fb200_cls_outputs_t* out, void* stream);
 
-/* The reductions AND the adaptive-prediction-set conformal sets of the mean row in ONE pass
- * (fortuna/conformal/classification/adaptive_prediction.py:11-22 scores of every class of the mean,
- * fortuna/conformal/classification/base.py:45-64, 72-82 rank-count sets against the sorted validation scores):
- * what fb200_bma_reduce_cls followed by fb200_aps_conformal_sets(out->mean, ...) returns, bit for bit.  By default that
- * is exactly what runs (two launches: 2.55 + 0.46 ms at c4); with the warp-autonomous kernel selected
- * (fb200_debug_force_tiled(0)) and 128 < C <= 1024, C % 4 == 0, the warp that reduced a row sorts its mean in registers
- * and the [B,C] mean is not read back (one launch, 3.5 ms at c4: the sort's instruction footprint does not overlap with
- * the streaming loop as hoped - kept selectable).  out->mean is required; mask uint8 [B,C] (4-byte aligned), sizes int32 [B] (optional);
- * threshold = float32((1 - error) * (n_val + 1)); workspace: fb200_bma_reduce_cls_sets_workspace_bytes(B) bytes. */
-size_t fb200_bma_reduce_cls_sets_workspace_bytes(int B);
-int fb200_bma_reduce_cls_sets(const void* logits, int dtype, const float* log_temp, const int32_t* targets, int S, int B,
-                              int C, const fb200_cls_outputs_t* out, const float* val_scores_sorted, int n_val,
-                              float threshold, uint8_t* mask, int32_t* sizes, void* workspace, size_t workspace_bytes,
-                              void* stream);
-
-/* Testing / measurement knob.  Rows of 128 < C <= 1024 classes (C % 4 == 0) have two reduction kernels: the tiled one
- * (default) and the warp-autonomous one, which also carries the fused conformal-set epilogue of
- * fb200_bma_reduce_cls_sets.  on = 0 selects the warp-autonomous kernel (also: FB200_K3_ROWS=1 in the environment),
- * on = 1 the tiled one, on < 0 only queries.  Returns the previous setting.  Results are bit-identical either way. */
-int fb200_debug_force_tiled(int on);
-
 /* The same outputs for heads of ANY width (the single-pass kernel above keeps a row in one warp's registers: C <= 1024).
  * Two passes over [S,B,C] - row logsumexp into `workspace` (fb200_bma_reduce_cls_wide_workspace_bytes = S*B floats),
  * then one CTA per input - i.e. twice the HBM traffic. */

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""A/B timing of the K3 reduction designs at c4 (z[64,65536,1000]): tiled kernel vs warp-autonomous kernel, float32 and
-bf16 logits, with and without the fused APS conformal sets.  CUDA events, inputs larger than L2."""
+"""K3 (single-pass reductions) and K5+K6 (APS conformal sets) alone at c4 (z[64,65536,1000]), float32 and bf16 logits.
+CUDA events, inputs larger than L2."""
 import argparse
 import json
 import os
@@ -9,7 +9,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fortuna_b200 import _lib, ops  # noqa: E402
+from fortuna_b200 import ops  # noqa: E402
 
 WANT = ("mean", "aleatoric_variance", "epistemic_variance", "entropy", "aleatoric_entropy", "epistemic_entropy", "log_prob",
         "mode", "confidence", "brier_terms")
@@ -40,7 +40,6 @@ def main():
     S, B, Cn = args.S, args.B, args.C
     gen = torch.Generator(device=dev)
     gen.manual_seed(1)
-    lib = _lib.lib()
     peak = 6541.5
     try:
         peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -61,26 +60,14 @@ def main():
         esz = z.element_size()
         alg = esz * S * B * Cn + 4.0 * 3 * B * Cn + 4.0 * B * 8
         outs = ops._alloc_cls_outputs(WANT, S, B, Cn, dev)
-        mask = torch.empty((B, Cn), dtype=torch.uint8, device=dev)
-        sizes = torch.empty(B, dtype=torch.int32, device=dev)
-        ws = torch.empty(int(lib.fb200_bma_reduce_cls_sets_workspace_bytes(B)), dtype=torch.uint8, device=dev)
         res = {"dtype": dt, "S": S, "B": B, "C": Cn, "algorithmic_GB": alg / 1e9}
-        for name, tiled in (("tiled", 1), ("rows", 0)):
-            lib.fb200_debug_force_tiled(tiled)
-            ms = timeit(lambda: ops.bma_reduce_cls(z, WANT, targets=t, out=outs), args.steps)
-            res[name + "_ms"] = ms
-            res[name + "_hbm_frac"] = alg / (ms * 1e-3) / 1e9 / peak
-        lib.fb200_debug_force_tiled(0)  # warp-autonomous kernel: fused epilogue
-        ms = timeit(lambda: ops.bma_reduce_cls_sets(z, WANT, val_sorted, thr, targets=t, out=outs, mask=mask, sizes=sizes,
-                                                    workspace=ws), args.steps)
-        res["rows_fused_sets_ms"] = ms
-        res["fallback_rows"] = int(ws[:4].view(torch.int32)[0])
-        lib.fb200_debug_force_tiled(1)
+        ms = timeit(lambda: ops.bma_reduce_cls(z, WANT, targets=t, out=outs), args.steps)
+        res["reduce_ms"] = ms
+        res["reduce_hbm_frac"] = alg / (ms * 1e-3) / 1e9 / peak
         ms2 = timeit(lambda: ops.aps_conformal_sets(outs["mean"], val_sorted, thr), args.steps)
-        res["separate_sets_kernel_ms"] = ms2
+        res["sets_kernel_ms"] = ms2
         m2, s2 = ops.aps_conformal_sets(outs["mean"], val_sorted, thr)
-        res["fused_equals_separate"] = bool(torch.equal(m2, mask) and torch.equal(s2, sizes))
-        res["mean_set_size"] = float(sizes.float().mean())
+        res["mean_set_size"] = float(s2.float().mean())
         print(json.dumps(res), flush=True)
         del z
 

@@ -326,118 +326,3 @@ def test_calibrate_temperature_recovers_the_generating_temperature(cuda):
         optimizer=CalibOptimizer(method=Adam(5e-2), n_epochs=60)), z_val=z[:, :1000].contiguous(), targets_val=y[:1000])
     assert status["loss"].shape == (60,) and status["val_loss"].shape == (60,)
     assert status["loss"][-1] < status["loss"][0] and abs(float(log_temp[0]) - np.log(3.0)) < 0.12
-
-
-# ------------------------------------------------------------------------------------------------ warp-autonomous kernel
-ROWS_SHAPES = [(8, 512, 1000), (5, 517, 1000), (3, 41, 1024), (9, 130, 512), (2, 19, 260), (7, 77, 132), (4, 1, 640),
-               (1, 50, 1000), (13, 30, 904)]
-
-
-@pytest.mark.parametrize("S,B,C", ROWS_SHAPES)
-@pytest.mark.parametrize("dtype", ["f32", "bf16"])
-def test_rows_kernel_equals_tiled_kernel_bit_for_bit(cuda, S, B, C, dtype):
-    """128 < C <= 1024, C % 4 == 0 has two kernels, the tiled one (default) and the warp-autonomous one
-    (bma_reduce_rows.cu); fb200_debug_force_tiled selects between them on the same input.  Same per-logit arithmetic in the same sample order: identical bits, with and
-    without a temperature, and against the oracle."""
-    from fortuna_b200 import _lib, ops
-
-    if dtype == "bf16" and C % 8:
-        pytest.skip("bf16 rows of C % 8 != 0 are not 16-byte granular: tiled kernel only")
-    z = _logits(S, B, C, seed=S * 7 + C)
-    t = np.random.default_rng(2).integers(0, C, B).astype(np.int32)
-    zt = torch.from_numpy(z).to(cuda)
-    if dtype == "bf16":
-        zt = zt.to(torch.bfloat16)
-        z = zt.float().cpu().numpy()
-    tt = torch.from_numpy(t).to(cuda)
-    lt = torch.tensor([0.2], device=cuda)
-    want = ALL + ("confidence", "brier_terms")
-    lib = _lib.lib()
-    try:
-        assert lib.fb200_debug_force_tiled(0) == 1  # the tiled kernel is the default
-        new = ops.bma_reduce_cls(zt, want, targets=tt)
-        new_t = ops.bma_reduce_cls(zt, ("mean", "entropy", "log_prob"), targets=tt, log_temp=lt)
-        lib.fb200_debug_force_tiled(1)
-        old = ops.bma_reduce_cls(zt, want, targets=tt)
-        old_t = ops.bma_reduce_cls(zt, ("mean", "entropy", "log_prob"), targets=tt, log_temp=lt)
-    finally:
-        lib.fb200_debug_force_tiled(1)
-    for k in want:
-        assert torch.equal(new[k], old[k]), k
-    for k in old_t:
-        assert torch.equal(new_t[k], old_t[k]), k
-    _check(new, z, t, S)
-
-
-@pytest.mark.parametrize("S,B,C", [(8, 512, 1000), (3, 41, 1024), (9, 130, 512), (2, 19, 260), (6, 64, 128), (4, 100, 33),
-                                   (5, 200, 904), (3, 25, 1001)])
-@pytest.mark.parametrize("error", [0.05, 0.5, 0.999])
-def test_fused_sets_equal_reduce_then_aps_sets(cuda, S, B, C, error):
-    """fb200_bma_reduce_cls_sets = fb200_bma_reduce_cls + fb200_aps_conformal_sets on the mean, bit for bit (masks, sizes
-    and every reduction output), and the masks equal the oracle's literal rank-count sets (base.py:45-64)."""
-    from fortuna_b200 import ops
-    from oracle import scoring as Sc
-
-    r = np.random.default_rng(C + S)
-    z = _logits(S, B, C, seed=S + 3 * C, scale=3.0)
-    t = r.integers(0, C, B).astype(np.int32)
-    n_val = 333
-    pv = P.softmax((3.0 * r.standard_normal((n_val, C))).astype(np.float32))
-    val = np.sort(Sc.aps_score(pv, r.integers(0, C, n_val)))
-    thr = Sc.conformal_threshold(n_val, error)
-    zt, tt, vt = torch.from_numpy(z).to(cuda), torch.from_numpy(t).to(cuda), torch.from_numpy(val).to(cuda)
-    want = ("mean", "aleatoric_variance", "epistemic_variance", "entropy", "log_prob", "mode", "confidence", "brier_terms")
-    from fortuna_b200 import _lib
-
-    lib = _lib.lib()
-    ref = ops.bma_reduce_cls(zt, want, targets=tt)
-    for select_tiled in (1, 0):  # default route (two launches) and the fused epilogue of the warp-autonomous kernel
-        try:
-            lib.fb200_debug_force_tiled(select_tiled)
-            outs, mask, sizes = ops.bma_reduce_cls_sets(zt, want, vt, thr, targets=tt)
-        finally:
-            lib.fb200_debug_force_tiled(1)
-        for k in want:
-            assert torch.equal(outs[k], ref[k]), k
-        if select_tiled:
-            mask_t, sizes_t = mask, sizes
-        else:
-            assert torch.equal(mask, mask_t) and torch.equal(sizes, sizes_t)
-    if C <= 1024:
-        m2, s2 = ops.aps_conformal_sets(ref["mean"], vt, thr)
-        assert torch.equal(mask, m2) and torch.equal(sizes, s2)
-    mean = ref["mean"].cpu().numpy()
-    conds, sz, _ = Sc.conformal_sets(val, Sc.aps_cumsums(mean), error)
-    assert np.array_equal(mask.cpu().numpy().astype(bool), conds)
-    assert np.array_equal(sizes.cpu().numpy(), sz)
-
-
-def test_fused_sets_general_path_rows(cuda, request):
-    """Rows the in-register threshold test cannot decide - equal probabilities (uniform rows, duplicated logits) - go
-    through the fallback list to the rank-lookup kernel; all-true / all-false thresholds never sort.  Same bits."""
-    from fortuna_b200 import ops
-    from oracle import scoring as Sc
-
-    S, B, C = 4, 300, 1000
-    r = np.random.default_rng(5)
-    z = _logits(S, B, C, seed=11, scale=3.0)
-    z[:, ::3, :] = 0.0                      # every third row: all classes tie
-    z[:, 1::7, 500:] = z[:, 1::7, :500]     # pairs of equal logits in other rows
-    t = r.integers(0, C, B).astype(np.int32)
-    pv = P.softmax((3.0 * r.standard_normal((200, C))).astype(np.float32))
-    val = np.sort(Sc.aps_score(pv, r.integers(0, C, 200)))
-    zt, tt, vt = torch.from_numpy(z).to(cuda), torch.from_numpy(t).to(cuda), torch.from_numpy(val).to(cuda)
-    from fortuna_b200 import _lib
-
-    _lib.lib().fb200_debug_force_tiled(0)  # the fused epilogue lives in the warp-autonomous kernel
-    request.addfinalizer(lambda: _lib.lib().fb200_debug_force_tiled(1))
-    for error in (0.1, 0.7):
-        thr = Sc.conformal_threshold(len(val), error)
-        outs, mask, sizes = ops.bma_reduce_cls_sets(zt, ("mean",), vt, thr, targets=tt)
-        m2, s2 = ops.aps_conformal_sets(outs["mean"], vt, thr)
-        assert torch.equal(mask, m2) and torch.equal(sizes, s2)
-        conds, sz, _ = Sc.conformal_sets(val, Sc.aps_cumsums(outs["mean"].cpu().numpy()), error)
-        assert np.array_equal(mask.cpu().numpy().astype(bool), conds) and np.array_equal(sizes.cpu().numpy(), sz)
-    for thr, full in ((np.float32(1e9), True), (np.float32(0.0), False)):
-        _, mask, sizes = ops.bma_reduce_cls_sets(zt, ("mean",), vt, thr)
-        assert bool((mask == (1 if full else 0)).all()) and bool((sizes == (C if full else 0)).all())

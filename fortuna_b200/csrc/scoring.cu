@@ -399,21 +399,14 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
       if (lane == 0 && a.scores) a.scores[b] = ys;
     }
     if (MODE == 0) {
-      // equal neighbours among the real (rank < C) keys?
-      bool tie = false;
-#pragma unroll
-      for (int r = 0; r + 1 < NR; ++r) tie |= (key[r] == key[r + 1]) && (lane * NR + r + 1 < C);
-      {
-        const uint32_t nxt = __shfl_down_sync(0xffffffffu, key[0], 1);
-        tie |= (lane < 31) && (key[NR - 1] == nxt) && ((lane + 1) * NR < C);
-      }
-      const bool any_tie = __any_sync(0xffffffffu, tie);
       // Sets without scores: no class needs its exact rank.  score(rank) >= q is a threshold function of the rank
       // whenever the prefix sums are monotone around q (checked on the actual values: the tree order can break
-      // monotonicity by an ulp), so with distinct keys  rank(c) >= r1  <=>  prob(c) <= prob at rank r1  - one compare
-      // per class instead of the ten-probe rank lookup.  Rows with ties or a non-monotone boundary take the general path.
+      // monotonicity by an ulp); the set is then the ranks >= first, and  rank(c) >= first  <=>  prob(c) <= prob at rank
+      // `first`  as long as the key just BEFORE the boundary differs from the boundary key (equal probabilities anywhere
+      // else leave the sorted values, their prefix sums and this test untouched) - one compare per class instead of the
+      // ten-probe rank lookup.  Rows with a tie across the boundary or a non-monotone boundary take the general path.
       bool done = false;
-      if (a.cs_mask && !a.scores && !any_tie && !a.cs_all_true && !a.cs_all_false) {
+      if (a.cs_mask && !a.scores && !a.cs_all_true && !a.cs_all_false) {
         const float q = __ldg(a.cs_val_sorted + a.cs_q_index);
         int n_true = 0, first = 0x7FFFFFFF;
 #pragma unroll
@@ -429,16 +422,40 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
           first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
         }
         const bool none = first == 0x7FFFFFFF;
-        if (none ? (n_true == 0) : (n_true == C - first)) {  // warp-uniform
-          float pb = 0.0f;  // probability at the boundary rank
+        // boundary key and the key before it (previous register slot, or the previous lane's last slot)
+        const uint32_t prev_last = __shfl_up_sync(0xffffffffu, key[NR - 1], 1);
+        uint32_t kb = 0u, kp = 0u;
 #pragma unroll
-          for (int r = 0; r < NR; ++r) pb = (lane * NR + r == first) ? f32_unordered(~key[r]) : pb;
-          pb = __shfl_sync(0xffffffffu, pb, none ? 0 : first / NR);
+        for (int r = 0; r < NR; ++r) {
+          const bool hit = lane * NR + r == first;
+          kb = hit ? key[r] : kb;
+          kp = hit ? (r > 0 ? key[r > 0 ? r - 1 : 0] : prev_last) : kp;
+        }
+        const int src = none ? 0 : first / NR;
+        kb = __shfl_sync(0xffffffffu, kb, src);
+        kp = __shfl_sync(0xffffffffu, kp, src);
+        const bool boundary_tie = !none && first > 0 && kp == kb;
+        if ((none ? (n_true == 0) : (n_true == C - first)) && !boundary_tie) {  // warp-uniform
+          const float pb = f32_unordered(~kb);  // probability at the boundary rank
           uint8_t* mrow = a.cs_mask + (size_t)b * C;
+          if (vec16 && (reinterpret_cast<uintptr_t>(mrow) & 3u) == 0) {
+            // four classes per lane and store: class c = (lane + 32 j) * 4 + k
 #pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            const int c = r * 32 + lane;
-            if (c < C) mrow[c] = (!none && (srow[c] + 0.0f) <= pb) ? 1 : 0;
+            for (int j = 0; j < (NR + 3) / 4; ++j) {
+              const int c0 = (lane + 32 * j) * 4;
+              if (c0 < C) {
+                const float4 v = *reinterpret_cast<const float4*>(srow + c0);
+                const uint32_t w = ((!none && v.x <= pb) ? 1u : 0u) | ((!none && v.y <= pb) ? 0x100u : 0u) |
+                                   ((!none && v.z <= pb) ? 0x10000u : 0u) | ((!none && v.w <= pb) ? 0x1000000u : 0u);
+                *reinterpret_cast<uint32_t*>(mrow + c0) = w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              const int c = r * 32 + lane;
+              if (c < C) mrow[c] = (!none && srow[c] <= pb) ? 1 : 0;  // -0 == +0: no canonicalisation needed to compare
+            }
           }
           if (lane == 0 && a.cs_sizes) a.cs_sizes[b] = n_true;
           __syncwarp();
@@ -447,6 +464,15 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
         }
       }
       if (!done) {
+      // equal neighbours among the real (rank < C) keys?  (only such rows run the exact tie pass of the rank lookup)
+      bool tie = false;
+#pragma unroll
+      for (int r = 0; r + 1 < NR; ++r) tie |= (key[r] == key[r + 1]) && (lane * NR + r + 1 < C);
+      {
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, key[0], 1);
+        tie |= (lane < 31) && (key[NR - 1] == nxt) && ((lane + 1) * NR < C);
+      }
+      const bool any_tie = __any_sync(0xffffffffu, tie);
       // the row's own keys again, class order, then the staging buffer is free for the next row
 #pragma unroll
       for (int r = 0; r < NR; ++r) {

@@ -304,6 +304,56 @@ __global__ void __launch_bounds__(256) ess_kernel(const EssArgs a) {
   }
 }
 
+// Short chains (S <= SMAX = 32 / 64 stored samples - every BASELINE config): ONE THREAD PER PARAMETER, the whole chain
+// in its registers.  A warp's load of sample t is 32 consecutive floats (one 128-byte line), all S loads of a thread are
+// in flight together, the lagged products are S^2/2 register FMAs (entries past S are zero, so the unrolled triangle
+// needs no bounds), and the lag walk follows in the same thread: no shared memory, no barrier, no per-slab latency chain
+// (the slab kernel below reached 19 % of the HBM peak at c5: load -> centre -> lags -> walk, one after the other).
+template <int SMAX>
+__global__ void __launch_bounds__(256) ess_short_kernel(const EssArgs a) {
+  const int S = a.S;
+  const float fS = (float)S;
+  const float inv_S = 1.0f / fS;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += (int64_t)gridDim.x * blockDim.x) {
+    float x[SMAX];
+#pragma unroll
+    for (int t = 0; t < SMAX; ++t) x[t] = t < S ? __ldg(a.x + (int64_t)t * a.stride + n) : 0.0f;
+    float sum = 0.0f;
+#pragma unroll
+    for (int t = 0; t < SMAX; ++t) sum += x[t];
+    const float mean = sum / fS;  // sgmcmc_diagnostic.py:107-108
+#pragma unroll
+    for (int t = 0; t < SMAX; ++t) x[t] = t < S ? x[t] - mean : 0.0f;
+    float inv_cov0 = 0.0f, acc_w = 0.0f;
+    bool open = true;
+#pragma unroll
+    for (int k = 0; k < SMAX; ++k) {
+      float prod = 0.0f;
+#pragma unroll
+      for (int t = 0; t + k < SMAX; ++t) prod = fmaf(x[t], x[t + k], prod);  // sum_t x[t] x[t+k]
+      if (k < S) {
+        const float cov = prod * (1.0f / (fS - (float)k));  // unbiased normalisation (:120-128), reciprocal like the slab kernel
+        if (k == 0) inv_cov0 = 1.0f / cov;
+        const float rho = cov * inv_cov0;
+        if (a.use_threshold && rho < a.threshold) open = false;  // cumulative mask: this lag and every later one drop out
+        const float w = ((fS - (float)k) * inv_S) * rho;
+        if (open) acc_w += w;
+        else if (rho != rho) acc_w += rho;  // NaN auto-correlations propagate like `weighted * mask` does
+      }
+    }
+    a.ess[n] = fS / (-1.0f + 2.0f * acc_w);
+  }
+}
+
+template <int SMAX>
+static int launch_ess_short(const EssArgs& a, cudaStream_t st) {
+  int64_t blocks = (a.N + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ess_short_kernel<SMAX><<<(unsigned)blocks, 256, 0, st>>>(a);
+  FB200_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int COLS>
 static int launch_ess(const EssArgs& a, cudaStream_t st) {
   const int groups = 256 / COLS;
@@ -406,6 +456,8 @@ extern "C" int fb200_ess(const float* samples, int S, int64_t N, int64_t row_str
   a.threshold = threshold;
   a.ess = ess;
   cudaStream_t st = (cudaStream_t)stream;
+  if (S <= 32) return launch_ess_short<32>(a, st);  // the chain of a parameter fits one thread's registers
+  if (S <= 64) return launch_ess_short<64>(a, st);
   const size_t per_col = ((size_t)(2 * S + ESS_R + 32)) * sizeof(float);
   const size_t budget = 200 * 1024 - (size_t)S * sizeof(float);
   if (per_col * 128 <= 110 * 1024 && N >= 128) return launch_ess<128>(a, st);  // short chains: wide slabs

@@ -211,11 +211,22 @@ class SGMCMCPosterior(WithRNG):
                              overwrite=True)
 
     def last_layer(self) -> LastLayerSamples:
+        """The stored output layers as ``LastLayerSamples`` (kernel [n, D, C], bias [n, C]).  Two leaf conventions exist in
+        a bank: a flax module's ``<last_layer_path>/kernel`` [D, C] (checkpoints written by Fortuna) and a torch
+        ``nn.Linear``'s ``output_subnet/weight`` [C, D] (a fit run here) - the latter is transposed into the former."""
         if self._last_layer is None:
-            kernel = self.state.leaf_matrix(self.last_layer_path + ("kernel",))
-            try:
-                bias = self.state.leaf_matrix(self.last_layer_path + ("bias",))
-            except ValueError:
-                bias = None
+            paths = [tuple(p) for p in self.state._template.paths]
+            if self.last_layer_path + ("kernel",) in paths:
+                kernel = self.state.leaf_matrix(self.last_layer_path + ("kernel",))
+                bias = self.state.leaf_matrix(self.last_layer_path + ("bias",)) if self.last_layer_path + ("bias",) in paths else None
+            else:
+                from .torch_model import PREFIX
+
+                w = PREFIX + ("output_subnet", "weight")
+                if w not in paths:
+                    raise ValueError(f"the sample bank holds neither {self.last_layer_path + ('kernel',)} nor {w}")
+                kernel = self.state.leaf_matrix(w).transpose(1, 2).contiguous()  # [n, C, D] -> [n, D, C]
+                b = PREFIX + ("output_subnet", "bias")
+                bias = self.state.leaf_matrix(b) if b in paths else None
             self._last_layer = LastLayerSamples(kernel, bias, self.log_temp)
         return self._last_layer

@@ -31,13 +31,47 @@ class RegressionPredictive:
         x = loader.to_array_inputs() if hasattr(loader, "to_array_inputs") else loader
         return torch.as_tensor(np.asarray(x), dtype=torch.float32, device=self.posterior.bound.device)
 
+    @staticmethod
+    def _batches(loader, with_targets: bool = False):
+        """(inputs, targets or None) batches: a loader is walked batch by batch like the reference's
+        ``_loop_fun_through_inputs_loader`` / ``_loop_fun_through_data_loader`` (predictive/base.py:946-1013), targets
+        staying with their inputs; a bare array is one batch."""
+        if hasattr(loader, "__iter__") and not isinstance(loader, (np.ndarray, torch.Tensor)):
+            for b in loader:
+                if isinstance(b, tuple):
+                    yield (b[0], b[1] if with_targets else None)
+                else:
+                    yield (b, None)
+        else:
+            yield (loader, None)
+
     def _reduce(self, loader, names, n_posterior_samples, rng, targets=None):
+        """One pass over the loader: per batch one forward pass per STORED sample, the gather of the drawn ones and the
+        reduction kernels; batches are concatenated along the input axis (the per-sample axis of ``ensemble_log_prob``
+        stays first).  ``distribute`` is accepted by the public methods and ignored: regression outputs are a few floats
+        per input, every rank evaluates everything (replicas)."""
         if rng is None:
             rng = self.posterior.rng.get()
-        idx = self.posterior.sample_indices(rng, n_posterior_samples)
-        z = self._stored_outputs(self._x(loader)).index_select(0, idx.long()).contiguous()
-        t = None if targets is None else torch.as_tensor(np.asarray(targets), dtype=torch.float32, device=z.device).reshape(z.shape[1], -1)
-        return ops.bma_reduce_reg(z, names, targets=t, log_temp=self.log_temp)
+        idx = self.posterior.sample_indices(rng, n_posterior_samples).long()
+        dev = self.posterior.bound.device
+        parts = {n: [] for n in names}
+        with_t = targets is not None
+        array_targets = None
+        if with_t and not (hasattr(loader, "__iter__") and not isinstance(loader, (np.ndarray, torch.Tensor))):
+            array_targets = np.asarray(targets)
+        b0 = 0
+        for xb, tb in self._batches(loader, with_targets=with_t):
+            x = torch.as_tensor(np.asarray(xb), dtype=torch.float32, device=dev)
+            z = self._stored_outputs(x).index_select(0, idx).contiguous()
+            t = None
+            if with_t:
+                tsrc = tb if tb is not None else array_targets[b0 : b0 + x.shape[0]]
+                t = torch.as_tensor(np.asarray(tsrc), dtype=torch.float32, device=dev).reshape(z.shape[1], -1)
+            out = ops.bma_reduce_reg(z, names, targets=t, log_temp=self.log_temp)
+            for n in names:
+                parts[n].append(out[n])
+            b0 += x.shape[0]
+        return {n: (v[0] if len(v) == 1 else torch.cat(v, dim=1 if n == "ensemble_log_prob" else 0)) for n, v in parts.items()}
 
     def mean(self, inputs_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
         return self._reduce(inputs_loader, ("mean",), n_posterior_samples, rng)["mean"]
@@ -58,11 +92,18 @@ class RegressionPredictive:
         return self._reduce(inputs_loader, ("std",), n_posterior_samples, rng)["std"]
 
     def log_prob(self, data_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
-        return self._reduce(data_loader, ("log_prob",), n_posterior_samples, rng, data_loader.to_array_targets())["log_prob"]
+        return self._reduce(data_loader, ("log_prob",), n_posterior_samples, rng, self._targets(data_loader))["log_prob"]
 
     def ensemble_log_prob(self, data_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
         return self._reduce(data_loader, ("ensemble_log_prob",), n_posterior_samples, rng,
-                            data_loader.to_array_targets())["ensemble_log_prob"]
+                            self._targets(data_loader))["ensemble_log_prob"]
+
+    @staticmethod
+    def _targets(data_loader):
+        """Marker / array for ``_reduce``: a loader's targets are read from its (inputs, targets) batches."""
+        if hasattr(data_loader, "__iter__") and not isinstance(data_loader, (np.ndarray, torch.Tensor)):
+            return True
+        return np.asarray(data_loader.to_array_targets())
 
     def _mc_entropy(self, name, inputs_loader, n_posterior_samples, n_target_samples, rng):
         """regression.py:51-267: ``key1, *keys = split(rng, 1 + S)``; the S posterior draws use key1, the target samples of
@@ -71,8 +112,13 @@ class RegressionPredictive:
             rng = self.posterior.rng.get()
         ks = ops.split(rng, 1 + n_posterior_samples)
         idx = self.posterior.sample_indices(ks[0].contiguous(), n_posterior_samples)
-        z = self._stored_outputs(self._x(inputs_loader))
-        return ops.reg_mc_entropies(z, idx, ks[1:].contiguous(), n_target_samples, (name,), log_temp=self.log_temp)[name]
+        tkeys = ks[1:].contiguous()
+        dev = self.posterior.bound.device
+        parts = []
+        for xb, _ in self._batches(inputs_loader):  # the same keys for every batch, like the reference's batched loop
+            z = self._stored_outputs(torch.as_tensor(np.asarray(xb), dtype=torch.float32, device=dev))
+            parts.append(ops.reg_mc_entropies(z, idx, tkeys, n_target_samples, (name,), log_temp=self.log_temp)[name])
+        return parts[0] if len(parts) == 1 else torch.cat(parts)
 
     def aleatoric_entropy(self, inputs_loader, n_posterior_samples: int = 30, n_target_samples: int = 30, rng=None,
                           distribute: bool = True):
@@ -94,8 +140,7 @@ class RegressionPredictive:
         if rng is None:
             rng = self.posterior.rng.get()
         parts = []
-        batches = inputs_loader if hasattr(inputs_loader, "__iter__") else [inputs_loader]
-        for xb in batches:
+        for xb, _ in self._batches(inputs_loader):
             zb = self._stored_outputs(self._x(xb))
             parts.append(ops.reg_sample_targets(zb, rng, n_target_samples, log_temp=self.log_temp))
         return torch.cat(parts, dim=1)

@@ -1,5 +1,9 @@
-"""Checkpoints in the reference's on-disk format, so that posterior samples written by Fortuna load into the device
-sample bank and samples written here load in Fortuna.
+"""Checkpoints in the reference's on-disk format: the wire format and the
+state-dict shape are Fortuna's, so its sample files load into the device sample bank (and the last-layer predictive) as
+they are.  What a file's ``params`` tree looks like follows the MODEL definition, though: Fortuna's flax modules store
+``.../kernel`` [D, C], a torch ``nn.Linear`` fitted here stores ``.../weight`` [C, D] - the bytes round-trip either way
+(``SGMCMCPosterior.last_layer`` accepts both), but loading one framework's files into the other's backbone needs a
+name / transpose map that is not provided.
 
 The reference saves every state through ``flax.training.checkpoints.save_checkpoint`` / ``restore_checkpoint``
 (fortuna/training/mixin.py:32-85): one file ``<dir>/<prefix><step>`` holding

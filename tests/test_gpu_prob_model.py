@@ -468,3 +468,20 @@ def test_predictive_statistics_to_host_with_streamed_ece(cuda):
     np.testing.assert_allclose(float(dev_out["ece"][0]), want, rtol=1e-5, atol=1e-7)
     again = pm.predictive.statistics(loader, names, 10, rng=key, ece=True, to_host=host_out)  # buffers reused
     assert again["mean"].data_ptr() == host_out["mean"].data_ptr()
+
+
+def test_last_layer_samples_from_a_torch_fit(cuda):
+    """SGMCMCPosterior.last_layer() on a bank filled by a fit here (torch nn.Linear: weight [C, D]) gives the flax-layout
+    kernel [n, D, C] the contraction kernels take - the same logits as the predictive's own route."""
+    from fortuna_b200 import ops
+
+    pm, train, test = _small_fit(True, seed=5, n_samples=6)
+    ll = pm.posterior.last_layer()
+    w = pm.posterior.state.leaf_matrix(("model", "params", "output_subnet", "weight"))
+    assert ll.kernel.shape == (6, w.shape[2], w.shape[1]) and torch.equal(ll.kernel, w.transpose(1, 2))
+    x = torch.as_tensor(test[0], device=cuda)
+    with torch.no_grad():
+        feats = pm.posterior.bound.model.dfe_subnet(x).contiguous()
+    z = ops.last_layer_logits(feats, ll.kernel, ll.bias, path=1)  # W_SDC layout
+    ref = pm.predictive._logits_fn(None, calibrated=False)(x)
+    np.testing.assert_allclose(z.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5)

@@ -61,6 +61,13 @@ def test_prob_regressor_sine(cuda):
     assert float((mean.cpu() - torch.from_numpy(yt)).abs().mean()) < 0.15
     lp = pr.predictive.log_prob(test, 20, rng=key)
     assert lp.shape == (64,) and bool(torch.isfinite(lp).all())
+    # batch by batch == all at once (to float32 rounding: the torch backbone picks its GEMM by batch size)
+    whole = DataLoader.from_array_data((xt, yt), batch_size=None)
+    np.testing.assert_allclose(lp.cpu().numpy(), pr.predictive.log_prob(whole, 20, rng=key).cpu().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(mean.cpu().numpy(), pr.predictive.mean(whole.to_inputs_loader(), 20, rng=key).cpu().numpy(),
+                               rtol=2e-5, atol=2e-6)
+    elp = pr.predictive.ensemble_log_prob(test, 20, rng=key)
+    assert elp.shape == (20, 64)
     # sample / quantile / credible interval: reference semantics (per-batch noise with the same key) vs the oracle
     smp = pr.predictive.sample(inputs, n_target_samples=30, rng=key)
     assert smp.shape == (30, 64, 1)
@@ -77,7 +84,10 @@ def test_prob_regressor_sine(cuda):
     with pytest.raises(ValueError):
         pr.predictive.credible_interval(inputs, interval_type="both")
     # Monte-Carlo entropies (regression.py:51-267) through the user API, against the oracle on the stored outputs
-    want_e = P.reg_mc_entropies(stored, ops.key_to_host(key), 12, 9)
+    # like the reference's batched loop (predictive/base.py:946-1013) every BATCH of the loader is evaluated with the same
+    # keys - the target-sample noise has the batch's shape - so the oracle runs per batch of 32 too
+    parts = [P.reg_mc_entropies(stored[:, i : i + 32], ops.key_to_host(key), 12, 9) for i in (0, 32)]
+    want_e = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
     for name in ("entropy", "aleatoric_entropy", "epistemic_entropy"):
         got = getattr(pr.predictive, name)(inputs, n_posterior_samples=12, n_target_samples=9, rng=key)
         assert got.shape == (64,)

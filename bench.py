@@ -450,13 +450,14 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     strong = args.scaling == "strong" and world > 1
+    bshard = args.scaling == "strong-b" and world > 1  # inputs sharded, samples replicated: no exchange at all
     S_total, B, Cn = args.S, args.B, args.C
     if B % world or (strong and S_total % world):
         raise SystemExit("B (and, for strong scaling, S) must be divisible by the number of GPUs")
     S = S_total // world if strong else S_total  # samples THIS rank evaluates
 
     parity = None
-    if world > 1:
+    if world > 1 and not bshard:
         # the S-sharded path against the single-GPU kernel on the same samples, once, outside the timed region
         from scripts.check_sharded_predictive import run_check
 
@@ -470,11 +471,14 @@ def run_gpu_arm(args):
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     # synthetic calibrated logits 4*N(0,1): softmax neither flat nor one-hot; generated in slabs
-    z = torch.empty((S, B, Cn), dtype=torch.float32, device=dev)
+    B_rows = B // world if bshard else B  # rows of the logits THIS rank holds
+    z = torch.empty((S, B_rows, Cn), dtype=torch.float32, device=dev)
     for s in range(S):
         z[s].normal_(0.0, 4.0, generator=gen)
     gen.manual_seed(99)  # targets / validation scores identical on every rank
     targets = torch.randint(0, Cn, (B,), device=dev, generator=gen, dtype=torch.int32)
+    if bshard:
+        targets = targets[rank * B_rows : (rank + 1) * B_rows].contiguous()
     val_logits = torch.empty((N_VAL, Cn), dtype=torch.float32, device=dev).normal_(0.0, 4.0, generator=gen)
     val_targets = torch.randint(0, Cn, (N_VAL,), device=dev, generator=gen, dtype=torch.int32)
     val_mean = ops.bma_reduce_cls(val_logits.unsqueeze(0).contiguous(), ("mean",))["mean"]
@@ -482,12 +486,24 @@ def run_gpu_arm(args):
     del val_logits, val_mean
     calib = pipeline.ConformalCalibration(val_sorted, N_VAL, ERROR)
 
-    runner = pipeline.PredictivePipeline(S, B, Cn, dev, WANT, world=world, rank=rank, transport=args.transport)
+    if bshard:
+        # every rank runs the single-GPU pipeline on ITS B / N rows with all S samples (a last-layer sample bank is a few
+        # hundred MB: replicate it); the only traffic between the ranks is the packed ECE bin counters
+        from fortuna_b200.prob_model.predictive.sharded import SampleShardExchange
+
+        runner = pipeline.PredictivePipeline(S, B_rows, Cn, dev, WANT)
+        runner.thresholds = torch.from_numpy(pipeline.ece_thresholds(B)).to(dev)  # bins of the WHOLE data set
+        bins = SampleShardExchange(world, rank)
+    else:
+        runner = pipeline.PredictivePipeline(S, B, Cn, dev, WANT, world=world, rank=rank, transport=args.transport)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (args.steps + 1))]
 
     def one_step(i=None):
         runner.reduce(z, targets, kernel_events=(ev[2 * i], ev[2 * i + 1]) if i is not None else None)
         runner.score(targets, calib)
+        if bshard:
+            bins.allreduce_bins(runner.ece)
+            runner.ece["result_global"] = ops.ece_from_packed_bins(runner.ece["packed"], B)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -519,7 +535,8 @@ def run_gpu_arm(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms, reduce_ms = float(tt[0]), float(tt[1])
     ms_per_step = total_ms / args.steps
-    elems_per_step = float(S) * B * Cn * world  # weak: every rank its own S samples; strong: S_total = S * world fixed
+    # weak: every rank its own S samples; strong: S_total = S * world fixed; strong-b: S samples x B / N rows per rank
+    elems_per_step = float(S) * B * Cn * (1 if bshard else world)
     value = elems_per_step / (ms_per_step * 1e-3)
 
     # per-phase breakdown of a step (CUDA events on the launching stream), measured in a second, untimed run of a few steps
@@ -546,7 +563,10 @@ def run_gpu_arm(args):
     # shard mode -> one slot row of 2C+4 floats per input (sum p, sum p^2, three scalars)
     # with the peer-store exchange only the rows this rank owns (1/N of them) land in its own HBM - the rest leaves over
     # NVLink - and it RECEIVES (N-1)/N of a slot buffer from its peers: HBM bytes per rank = logits + one slot buffer
-    alg_bytes = 4.0 * S * B * Cn + (4.0 * 3 * B * Cn + 4.0 * B * 8 if world == 1 else 4.0 * B * (2 * Cn + 4))
+    if world == 1 or bshard:
+        alg_bytes = 4.0 * S * B_rows * Cn + 4.0 * 3 * B_rows * Cn + 4.0 * B_rows * 8
+    else:
+        alg_bytes = 4.0 * S * B * Cn + 4.0 * B * (2 * Cn + 4)
     peak, peak_src = _peaks()
     achieved = alg_bytes / (reduce_ms * 1e-3) / 1e9
     traffic = None
@@ -564,14 +584,16 @@ def run_gpu_arm(args):
         "warmup": args.warmup,
         "ms_per_step": ms_per_step,
         "higher_is_better": True,
-        "scaling": "strong" if strong else "weak",
+        "scaling": "strong" if (strong or bshard) else "weak",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
         "config": {
             "workload": f"c4 predictive z[S={S * world if strong else S},B={B},C={Cn}] f32 -> BMA reductions + APS conformal sets + ECE",
-            "S_per_gpu": S, "S_total": S * world, "B": B, "C": Cn, "n_val": N_VAL, "error": ERROR,
-            "parallelism": "single GPU" if world == 1 else (
+            "S_per_gpu": S, "S_total": S if bshard else S * world, "B": B, "B_per_gpu": B_rows, "C": Cn, "n_val": N_VAL,
+            "error": ERROR,
+            "parallelism": "single GPU" if world == 1 else (f"B-sharded x{world}: every rank holds all S samples and B/{world} inputs; no "
+                                                            "exchange (one packed all-reduce of the ECE bin counters)") if bshard else (
                 f"S-sharded x{world}: partial sums exchanged by " + ("ONE NCCL all-to-all" if runner.transport == "nccl" else
                 "peer stores from the reduction kernel over NVLink (symmetric memory, double-buffered) + ONE barrier")),
             "l2": "inputs larger than L2; no flush needed" if 4.0 * S * B * Cn > 2.5e8 else "inputs re-read from HBM each step",
@@ -588,7 +610,7 @@ def run_gpu_arm(args):
         line["parity"] = parity
     if phases is not None:
         line["phases"] = phases
-    if world > 1:
+    if world > 1 and not bshard:
         # the exchange: every rank ships the slot rows of the inputs it does not own and receives as many
         slot_bytes = 4.0 * B * (2 * Cn + 4)
         link = slot_bytes * (world - 1) / world
@@ -667,8 +689,10 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=8192, help="rows per batch of the e2e loader (whole job; / N per rank)")
     ap.add_argument("--e2e-logits", default="bf16", choices=["bf16", "f32"],
                     help="dtype of the logits between the last-layer GEMM and the reductions in the e2e path")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = every rank evaluates S samples (S_total = N S); strong = S_total = S fixed, S / N per rank")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong", "strong-b"],
+                    help="N > 1: weak = every rank evaluates S samples (S_total = N S); strong = S_total = S fixed, S / N per rank "
+                         "(S-sharded, exchange of partial sums); strong-b = S and B fixed, B / N inputs per rank with the samples "
+                         "replicated (no exchange)")
     ap.add_argument("--phases", action="store_true", help="add the per-phase CUDA-event breakdown at N = 1 too")
     ap.add_argument("--transport", default="p2p", choices=["nccl", "p2p"],
                     help="N > 1 exchange: one NCCL all-to-all, or peer stores from the reduction kernel over NVLink")

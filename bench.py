@@ -211,8 +211,13 @@ def cpu_reference_throughput(rows_per_core, steps, warmup, cores=None):
     cores = cores or len(os.sched_getaffinity(0)) or os.cpu_count() or 1
     r = np.random.default_rng(0)
     shards = []
-    # the GPU arm's validation set: N_VAL scores of 4 N(0,1) logits (built once, outside the timed steps)
-    val = np.sort(Sc.aps_score(P.softmax((4 * r.standard_normal((N_VAL, C_FULL))).astype(np.float32)), r.integers(0, C_FULL, N_VAL)))
+    # validation scores as in the GPU arm: APS scores of BMA mean rows against random targets (built once, outside the timed
+    # steps; 4 samples per row instead of 64 to keep the set-up short - argsort + searchsorted cost the same whatever the values)
+    vmean = np.zeros((N_VAL, C_FULL), dtype=np.float32)
+    for _ in range(4):
+        vmean += P.softmax((4 * r.standard_normal((N_VAL, C_FULL))).astype(np.float32))
+    val = np.sort(Sc.aps_score(vmean / np.float32(4), r.integers(0, C_FULL, N_VAL)))
+    del vmean
     thr = Sc.conformal_threshold(len(val), ERROR)
     for _ in range(cores):
         z = (4 * r.standard_normal((S_FULL, rows_per_core, C_FULL))).astype(np.float32)
@@ -479,9 +484,14 @@ def run_gpu_arm(args):
     targets = torch.randint(0, Cn, (B,), device=dev, generator=gen, dtype=torch.int32)
     if bshard:
         targets = targets[rank * B_rows : (rank + 1) * B_rows].contiguous()
-    val_logits = torch.empty((N_VAL, Cn), dtype=torch.float32, device=dev).normal_(0.0, 4.0, generator=gen)
+    # validation probabilities = BMA means over S_FULL samples, like the test rows (the reference feeds both
+    # predictive.mean(val) and predictive.mean(test) to conformal_set); round 1 / early round 2 used single-sample
+    # validation rows, whose quantile sits ~670 ranks deep in the flatter test rows (--val-samples 1 reproduces that)
+    val_logits = torch.empty((args.val_samples, N_VAL, Cn), dtype=torch.float32, device=dev)
+    for s in range(args.val_samples):
+        val_logits[s].normal_(0.0, 4.0, generator=gen)
     val_targets = torch.randint(0, Cn, (N_VAL,), device=dev, generator=gen, dtype=torch.int32)
-    val_mean = ops.bma_reduce_cls(val_logits.unsqueeze(0).contiguous(), ("mean",))["mean"]
+    val_mean = ops.bma_reduce_cls(val_logits, ("mean",))["mean"]
     val_sorted = ops.sort_f32_(ops.aps_scores(val_mean, val_targets))
     del val_logits, val_mean
     calib = pipeline.ConformalCalibration(val_sorted, N_VAL, ERROR)
@@ -591,7 +601,7 @@ def run_gpu_arm(args):
         "config": {
             "workload": f"c4 predictive z[S={S * world if strong else S},B={B},C={Cn}] f32 -> BMA reductions + APS conformal sets + ECE",
             "S_per_gpu": S, "S_total": S if bshard else S * world, "B": B, "B_per_gpu": B_rows, "C": Cn, "n_val": N_VAL,
-            "error": ERROR,
+            "val_samples": args.val_samples, "error": ERROR,
             "parallelism": "single GPU" if world == 1 else (f"B-sharded x{world}: every rank holds all S samples and B/{world} inputs; no "
                                                             "exchange (one packed all-reduce of the ECE bin counters)") if bshard else (
                 f"S-sharded x{world}: partial sums exchanged by " + ("ONE NCCL all-to-all" if runner.transport == "nccl" else
@@ -693,6 +703,8 @@ def main():
                     help="N > 1: weak = every rank evaluates S samples (S_total = N S); strong = S_total = S fixed, S / N per rank "
                          "(S-sharded, exchange of partial sums); strong-b = S and B fixed, B / N inputs per rank with the samples "
                          "replicated (no exchange)")
+    ap.add_argument("--val-samples", type=int, default=S_FULL,
+                    help="posterior samples behind the validation rows of the conformal calibration (default: as many as the test rows)")
     ap.add_argument("--phases", action="store_true", help="add the per-phase CUDA-event breakdown at N = 1 too")
     ap.add_argument("--transport", default="p2p", choices=["nccl", "p2p"],
                     help="N > 1 exchange: one NCCL all-to-all, or peer stores from the reduction kernel over NVLink")

@@ -34,6 +34,8 @@ struct RowSortArgs {
   const float* cs_val_sorted;
   int cs_q_index;          // n_val - 1 - K
   int cs_all_true, cs_all_false;
+  int only_flagged;        // all-class key-only kernel: visit only the rows whose cs_sizes entry is -1 (left by the
+                           // select kernel below for the rows it could not decide)
 };
 
 __global__ void __launch_bounds__(256) row_sort_cumsum_kernel(const RowSortArgs a) {
@@ -353,9 +355,16 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
   int* scnt = reinterpret_cast<int*>(skey);  // tie pass only; the sorted keys are dead by then
   const bool vec16 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.probs) & 15) == 0);
   const int nwarps = gridDim.x * kSortWarps;
-  int b = blockIdx.x * kSortWarps + warp_in_cta;
+  // the warp's next row at or after b: every row, or (second pass of the select kernel) only the flagged ones
+  auto row_from = [&](int r) {
+    if (MODE == 0 && a.only_flagged)
+      while (r < a.B && a.cs_sizes[r] != -1) r += nwarps;
+    return r;
+  };
+  int b = row_from(blockIdx.x * kSortWarps + warp_in_cta);
   if (b < a.B) row_prefetch<NR>(srow, a.probs + (size_t)b * C, C, lane, vec16);
-  for (; b < a.B; b += nwarps) {
+  for (int nb; b < a.B; b = nb) {
+    nb = row_from(b + nwarps);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     uint32_t own[NR], key[NR];
@@ -381,7 +390,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
         tpos = cnt;
       }
       __syncwarp();
-      if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
+      if (nb < a.B) row_prefetch<NR>(srow, a.probs + (size_t)nb * C, C, lane, vec16);
     }
     warp_bitonic_sort32<NR>(key, lane);
     float x[NR];
@@ -459,7 +468,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
           }
           if (lane == 0 && a.cs_sizes) a.cs_sizes[b] = n_true;
           __syncwarp();
-          if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
+          if (nb < a.B) row_prefetch<NR>(srow, a.probs + (size_t)nb * C, C, lane, vec16);
           done = true;
         }
       }
@@ -488,7 +497,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
         asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(ad), "f"(x[r]), "n"(PAD * 4) : "memory");
       }
       __syncwarp();
-      if (b + nwarps < a.B) row_prefetch<NR>(srow, a.probs + (size_t)(b + nwarps) * C, C, lane, vec16);
+      if (nb < a.B) row_prefetch<NR>(srow, a.probs + (size_t)nb * C, C, lane, vec16);
       // lower bound, kept as the shared-space BYTE address of the slot so that a probe is one LDS with an
       // immediate offset, one compare and one predicated add
       uint32_t ap[NR];
@@ -569,6 +578,237 @@ static int launch_row_sort32_warp(const RowSortArgs& a, cudaStream_t st) {
   }
   FB200_LAUNCH_CHECK();
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5+K6 "select": APS conformal sets without the scores and without sorting the row.
+// The set of a row is {classes whose score >= q} = the ranks >= first, first = the smallest rank whose prefix sum
+// reaches q (base.py:51-53 counts the validation scores ABOVE a test score, so the set is the low-probability tail).
+// Only the exact prefix sums of the ranks up to `first` decide it, and in jax.lax.associative_scan's order the prefix
+// at rank i depends on the values at ranks <= i alone.  So: pick a probability threshold t, take A = {p >= t} - the
+// top-|A| of the row as a set, whatever the ties - and if A holds at most kSelMax values whose mass reaches q, sort
+// just A (1..8 keys per lane instead of 32), take its prefix sums in the same tree order and find the boundary there.
+// What A cannot show is checked instead of assumed:
+//   * ranks inside A: every prefix is compared with q (the tree order may break monotonicity by an ulp);
+//   * ranks beyond A: prefix[i] >= exact[i] (1 - g) >= exact[|A|-1] (1 - g) >= prefix[|A|-1] (1 - g) / (1 + g) for
+//     non-negative values, g = 20 * 2^-24 (no value of a 1024-long scan goes through more than 20 additions), so
+//     prefix[|A|-1] * (1 - 4e-6) >= q proves them all in;  rows with a negative value or -0 never get here;
+//   * a tie across the boundary rank needs the stable order of the classes: not decided here.
+// Rows this kernel cannot decide get size -1 and are done by row_sort32_warp_kernel<NR, 0> (only_flagged) right after.
+// The threshold is t = max * 2^x; x is the warp's running estimate (found by bisection on its first row; afterwards
+// loosened by 0.7 when the mass falls short, tightened by 1.2 after every accepted row - a warp only sees a few dozen
+// rows, so it has to adapt quickly), so a typical row costs 1.2-1.5 counting passes and sorts 64-128 values.
+// Rows are double-buffered in shared memory (cp.async): the next row's HBM latency hides behind the current one.
+// A warp that fails kSelGiveUp rows in a row flags its next kSelSkip rows unread, so data whose boundaries lie deep
+// (flat rows against a high quantile) costs the full sort plus about a tenth of a counting pass per row.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelWarps = 4;
+constexpr int kSelMax = 256;  // most values a row may need sorted (8 per lane)
+constexpr int kSelGiveUp = 3;  // undecided rows in a row after which a warp stops reading rows ...
+constexpr int kSelSkip = 12;   // ... for this many of its rows
+
+template <int NRS>
+__device__ __forceinline__ bool aps_select_decide(const uint32_t* scratch, int cnt, int lane, float q, float& pb,
+                                                  int& first_out) {
+  uint32_t key[NRS];
+#pragma unroll
+  for (int r = 0; r < NRS; ++r) {
+    const int i = r * 32 + lane;
+    key[r] = i < cnt ? ~scratch[i] : 0xFFFFFFFFu;  // descending values = ascending complemented bits; padding last
+  }
+  warp_bitonic_sort32<NRS>(key, lane);
+  float x[NRS];
+#pragma unroll
+  for (int r = 0; r < NRS; ++r) x[r] = (lane * NRS + r < cnt) ? __uint_as_float(~key[r]) : 0.0f;
+  warp_row_tree_prefix<NRS>(x, lane);
+  int n_true = 0, first = 0x7FFFFFFF;
+  float xl = 0.0f;
+#pragma unroll
+  for (int r = NRS - 1; r >= 0; --r) {
+    const int rank = lane * NRS + r;
+    const bool t = (rank < cnt) && !(x[r] < q);
+    n_true += t ? 1 : 0;
+    first = t ? rank : first;
+    xl = (rank == cnt - 1) ? x[r] : xl;
+  }
+  n_true = __reduce_add_sync(0xffffffffu, n_true);
+  first = __reduce_min_sync(0xffffffffu, first);
+  xl = __shfl_sync(0xffffffffu, xl, (cnt - 1) / NRS);
+  if (first == 0x7FFFFFFF) return false;
+  const uint32_t prev_last = __shfl_up_sync(0xffffffffu, key[NRS - 1], 1);
+  uint32_t kb = 0u, kp = 0u;
+#pragma unroll
+  for (int r = 0; r < NRS; ++r) {
+    const bool hit = lane * NRS + r == first;
+    kb = hit ? key[r] : kb;
+    kp = hit ? (r > 0 ? key[r > 0 ? r - 1 : 0] : prev_last) : kp;
+  }
+  kb = __shfl_sync(0xffffffffu, kb, first / NRS);
+  kp = __shfl_sync(0xffffffffu, kp, first / NRS);
+  pb = __uint_as_float(~kb);
+  first_out = first;
+  return n_true == cnt - first && !(first > 0 && kp == kb) && (xl * 0.999996f >= q);
+}
+
+template <int NR>  // 32 * NR >= C, C % 4 == 0, rows 16-byte aligned, mask rows 4-byte aligned
+__global__ void __launch_bounds__(kSelWarps * 32, 5) aps_sets_select_kernel(const RowSortArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int N = 32 * NR;
+  constexpr int kWarpWords = 2 * N + kSelMax;
+  const int warp_in_cta = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int C = a.C;
+  float* rows = reinterpret_cast<float*>(smem_raw) + (size_t)warp_in_cta * kWarpWords;
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(rows + 2 * N);
+  const int nwarps = gridDim.x * kSelWarps;
+  const float q = __ldg(a.cs_val_sorted + a.cs_q_index);
+  const float qm = q * 1.00002f;  // the counting pass sums in another order than the scan: aim a little above q
+  float xs = 0.0f;      // log2 of the threshold / row maximum ratio the warp tries first on its next row
+  bool primed = false;  // ... once a row has told it where to look
+  int buf = 0, fails = 0;
+  // the rows are copied as C floats; the padding classes [C, 32 NR) of both buffers read as zero from here on
+  for (int i = C + lane; i < N; i += 32) rows[i] = 0.0f, rows[N + i] = 0.0f;
+  __syncwarp();
+  int b = blockIdx.x * kSelWarps + warp_in_cta;
+  if (b < a.B) row_prefetch<NR>(rows, a.probs + (size_t)b * C, C, lane, true);
+  for (int nb; b < a.B; b = nb, buf ^= 1) {
+    const float* srow = rows + buf * N;
+    nb = b + nwarps;
+    if (fails >= kSelGiveUp) {
+      // the data is not of the kind this kernel decides (boundary ranks deeper than kSelMax): leave the next
+      // kSelSkip rows to the full sort unread, then probe again (one more miss and the next burst is skipped)
+      const int r = nb + lane * nwarps;
+      if (lane < kSelSkip && r < a.B) a.cs_sizes[r] = -1;
+      nb += kSelSkip * nwarps;
+      fails = kSelGiveUp - 1;
+    }
+    if (nb < a.B) {
+      row_prefetch<NR>(rows + (buf ^ 1) * N, a.probs + (size_t)nb * C, C, lane, true);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncwarp();
+    // the row, four consecutive classes per lane and slot: class (lane + 32 j) * 4 + k in v[4 j + k]
+    float v[NR];
+    uint32_t orb = 0u, mxb = 0u;
+#pragma unroll
+    for (int j = 0; j < NR / 4; ++j) {
+      const float4 f = *reinterpret_cast<const float4*>(srow + (lane + 32 * j) * 4);
+      v[4 * j] = f.x, v[4 * j + 1] = f.y, v[4 * j + 2] = f.z, v[4 * j + 3] = f.w;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t u = __float_as_uint(v[4 * j + k]);
+        orb |= u;
+        mxb = max(mxb, u);
+      }
+    }
+    __syncwarp();  // all lanes hold their part of the row: this buffer may be refilled by the NEXT iteration's prefetch
+    orb = __reduce_or_sync(0xffffffffu, orb);
+    mxb = __reduce_max_sync(0xffffffffu, mxb);
+    // non-negative finite rows only (bit patterns then order like the values; -0, negatives, inf, NaN: general path)
+    bool decided = false;
+    float pb = 0.0f;
+    int first = 0;
+    if (!(orb & 0x80000000u) && mxb < 0x7F800000u && mxb != 0u) {
+      const float mx = __uint_as_float(mxb);
+      // threshold search in log2(t / mx).  First row of the warp: bisection over [-20, -1] from -6; afterwards one
+      // step of -log2(0.7) when the mass falls short, +2 when more than kSelMax values pass, bisection once bracketed.
+      float lo = primed ? -CUDART_INF_F : -20.0f, hi = primed ? CUDART_INF_F : -1.0f;
+      float x = primed ? xs : -6.0f, t = 0.0f;
+      const int max_tries = primed ? 5 : 7;
+      int mycnt = 0, cnt = 0;
+      bool accept = false, hopeless = false;
+#pragma unroll 1
+      for (int tr = 0; tr < max_tries && !accept && !hopeless; ++tr) {
+        t = mx * exp2f(x);
+        float mass = 0.0f, cntf = 0.0f;  // three FP-pipe instructions per value: FSET.BF, FFMA, FADD
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const float in = v[r] >= t ? 1.0f : 0.0f;
+          mass = fmaf(in, v[r], mass);
+          cntf += in;
+        }
+        mycnt = (int)cntf;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mass += __shfl_xor_sync(0xffffffffu, mass, o);
+        cnt = __reduce_add_sync(0xffffffffu, mycnt);
+        if (!(mass >= qm)) {  // A too small (or q is NaN): lower the threshold ...
+          hopeless = cnt >= kSelMax;  // ... unless that could only add values: boundary deeper than kSelMax ranks
+          hi = x;
+          x = lo > -CUDART_INF_F ? 0.5f * (lo + hi) : x - 0.515f;
+        } else if (cnt > kSelMax) {  // enough mass but too many values: raise it
+          lo = x;
+          x = hi < CUDART_INF_F ? 0.5f * (lo + hi) : x + 2.0f;
+        } else {
+          accept = true;
+        }
+      }
+      if (!hopeless) {  // (a hopeless row says nothing about where the decidable ones have their boundary)
+        xs = fminf(fmaxf(accept ? x + 0.263f : x, -30.0f), -1.0f);  // accepted: try 1.2 x tighter on the next row
+        primed = true;
+      }
+      if (accept) {
+        // compact A into the scratch buffer (any order: it is sorted next)
+        int pos = mycnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, pos, o);
+          if (lane >= o) pos += up;
+        }
+        uint32_t wa = (uint32_t)__cvta_generic_to_shared(scratch) + (uint32_t)(pos - mycnt) * 4u;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {  // compare, predicated store, predicated address bump
+          asm volatile(
+              "{ .reg .pred p; setp.ge.f32 p, %1, %2; @p st.shared.f32 [%0], %1; @p add.u32 %0, %0, 4; }"
+              : "+r"(wa)
+              : "f"(v[r]), "f"(t)
+              : "memory");
+        }
+        __syncwarp();
+        if (cnt <= 32) decided = aps_select_decide<1>(scratch, cnt, lane, q, pb, first);
+        else if (cnt <= 64) decided = aps_select_decide<2>(scratch, cnt, lane, q, pb, first);
+        else if (cnt <= 128) decided = aps_select_decide<4>(scratch, cnt, lane, q, pb, first);
+        else decided = aps_select_decide<8>(scratch, cnt, lane, q, pb, first);
+        __syncwarp();  // scratch is free again
+      }
+    }
+    if (decided) {
+      uint8_t* mrow = a.cs_mask + (size_t)b * C;
+#pragma unroll
+      for (int j = 0; j < NR / 4; ++j) {
+        const int c0 = (lane + 32 * j) * 4;
+        if (c0 < C) {
+          // FSET.BF per class (1.0f = 0x3F800000 or 0), the four top bytes gathered by three PRMTs, one AND
+          const uint32_t m0 = __float_as_uint(v[4 * j] <= pb ? 1.0f : 0.0f);
+          const uint32_t m1 = __float_as_uint(v[4 * j + 1] <= pb ? 1.0f : 0.0f);
+          const uint32_t m2 = __float_as_uint(v[4 * j + 2] <= pb ? 1.0f : 0.0f);
+          const uint32_t m3 = __float_as_uint(v[4 * j + 3] <= pb ? 1.0f : 0.0f);
+          const uint32_t w = __byte_perm(__byte_perm(m0, m1, 0x0073), __byte_perm(m2, m3, 0x0073), 0x5410);
+          *reinterpret_cast<uint32_t*>(mrow + c0) = w & 0x01010101u;
+        }
+      }
+      if (lane == 0) a.cs_sizes[b] = C - first;
+      fails = 0;
+    } else {
+      if (lane == 0) a.cs_sizes[b] = -1;
+      ++fails;
+    }
+  }
+}
+
+template <int NR>
+static int launch_aps_sets_select(RowSortArgs a, cudaStream_t st) {
+  const size_t smem = (size_t)kSelWarps * (2 * 32 * NR + kSelMax) * sizeof(uint32_t);
+  auto kern = aps_sets_select_kernel<NR>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int grid = (a.B + kSelWarps - 1) / kSelWarps;
+  if (grid > 148 * 5) grid = 148 * 5;
+  kern<<<grid, kSelWarps * 32, smem, st>>>(a);
+  FB200_LAUNCH_CHECK();
+  a.only_flagged = 1;  // whatever it left undecided: full sort + rank lookup
+  return launch_row_sort32_warp<NR>(a, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -677,6 +917,12 @@ static int launch_cls_sample(const ClsSampleArgs& a, cudaStream_t st) {
 }
 
 static int launch_row_sort(RowSortArgs a, cudaStream_t st) {
+  if (!a.perm && !a.set_size && !a.targets && !a.scores && a.cs_mask && a.cs_sizes && !a.cs_all_true && !a.cs_all_false &&
+      a.C > 256 && a.C <= 1024 && a.C % 4 == 0 && fb200_aligned16(a.probs) &&
+      (reinterpret_cast<uintptr_t>(a.cs_mask) & 3u) == 0) {
+    // sets without scores on wide rows: threshold selection instead of the full sort (rows it cannot decide: below)
+    return a.C <= 512 ? launch_aps_sets_select<16>(a, st) : launch_aps_sets_select<32>(a, st);
+  }
   if (!a.perm && !a.set_size && a.C <= 1024) {
     if (a.C <= 32) return launch_row_sort32_warp<1>(a, st);
     if (a.C <= 64) return launch_row_sort32_warp<2>(a, st);

@@ -106,8 +106,9 @@ class PredictivePipeline:
                 self.recv = torch.empty_like(self.send)
                 self.slot_ptrs = ops.slot_pointer_table([self.send[o] for o in range(world)], device)
         # reduce, sort + sets (fused), ece_bins, ece_finalize; sharded: + finalize_slots, pack_bins, ece_from_packed
-        fused_sort = C <= 1024
-        self.launches_per_step = (4 if world == 1 else 7) + (0 if fused_sort else 1)
+        # the sets are one launch for C <= 256 (sort + sets fused), two for wide rows (select kernel + the full sort over the
+        # rows it left undecided, or - C > 1024 - scores then sets)
+        self.launches_per_step = (4 if world == 1 else 7) + (0 if C <= 256 or (C <= 1024 and C % 4) else 1)
 
     def _mark(self, name):
         if self.timer is not None:

@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--C", type=int, default=1000)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--dtypes", default="f32,bf16")
+    ap.add_argument("--val-samples", type=int, default=1,
+                    help="posterior samples behind the validation probabilities (1: peaked rows, so the quantile sits deep "
+                         "in the flatter S-sample test rows; S: the validation rows are BMA means like the test rows)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     S, B, Cn = args.S, args.B, args.C
@@ -47,9 +50,9 @@ def main():
         pass
     t = torch.randint(0, Cn, (B,), device=dev, generator=gen, dtype=torch.int32)
     n_val = 50000
-    vl = torch.empty((n_val, Cn), device=dev).normal_(0.0, 4.0, generator=gen)
+    vl = torch.empty((args.val_samples, n_val, Cn), device=dev).normal_(0.0, 4.0, generator=gen)
     vt = torch.randint(0, Cn, (n_val,), device=dev, generator=gen, dtype=torch.int32)
-    vm = ops.bma_reduce_cls(vl.unsqueeze(0).contiguous(), ("mean",))["mean"]
+    vm = ops.bma_reduce_cls(vl, ("mean",))["mean"]
     val_sorted = ops.sort_f32_(ops.aps_scores(vm, vt))
     thr = float((1 - 0.05) * (n_val + 1))
     del vl, vm
@@ -68,6 +71,9 @@ def main():
         res["sets_kernel_ms"] = ms2
         m2, s2 = ops.aps_conformal_sets(outs["mean"], val_sorted, thr)
         res["mean_set_size"] = float(s2.float().mean())
+        res["val_samples"] = args.val_samples
+        m3, s3, _ = ops.aps_conformal_sets(outs["mean"], val_sorted, thr, want_scores=True)  # sorts every row
+        res["sets_equal_full_sort"] = bool(torch.equal(m2, m3) and torch.equal(s2, s3))
         print(json.dumps(res), flush=True)
         del z
 

@@ -271,3 +271,76 @@ def test_ece_from_reduction_rows_equals_ece_on_the_mean(cuda, S, B, C):
     assert torch.equal(a["bin_idx"], b["bin_idx"]) and torch.equal(a["counts"], b["counts"]) and torch.equal(a["correct"], b["correct"])
     assert torch.equal(a["conf_sums"], b["conf_sums"])  # fixed-point sums of the same confidences: identical
     np.testing.assert_allclose(b["result"].cpu().numpy(), a["result"].cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def _select_rows(C, seed):
+    """Rows that exercise every exit of the select kernel: peaked / very peaked / flat softmax rows, tie-heavy rows,
+    exact zeros, uniform, one-hot, -0.0 and a slightly negative value."""
+    r = np.random.default_rng(seed)
+    blocks = [
+        P.softmax((4 * r.standard_normal((1500, C))).astype(np.float32)),
+        P.softmax((8 * r.standard_normal((300, C))).astype(np.float32)),
+        P.softmax((1 * r.standard_normal((300, C))).astype(np.float32)),   # boundary deeper than the selection holds
+        P.softmax((2 * r.standard_normal((300, C))).astype(np.float32)),
+        P.softmax(np.round(4 * r.standard_normal((300, C))).astype(np.float32)),  # ties, some across the boundary
+        P.softmax(np.round(2 * r.standard_normal((200, C))).astype(np.float32)),
+    ]
+    z = P.softmax((4 * r.standard_normal((60, C))).astype(np.float32))
+    z[r.random(z.shape) < 0.6] = 0.0
+    blocks.append(z)
+    blocks.append(np.full((3, C), 1.0 / C, dtype=np.float32))
+    oh = np.zeros((3, C), dtype=np.float32)
+    oh[np.arange(3), r.integers(0, C, 3)] = 1.0
+    blocks.append(oh)
+    nz = P.softmax((4 * r.standard_normal((4, C))).astype(np.float32))
+    nz[:2, ::5] = np.float32(-0.0)
+    nz[2:, 7] = np.float32(-1e-9)
+    blocks.append(nz)
+    p = np.concatenate(blocks).astype(np.float32)
+    return p[r.permutation(len(p))]
+
+
+@pytest.mark.parametrize("C", [1000, 1024, 512, 260])
+@pytest.mark.parametrize("error", [0.02, 0.05, 0.3, 0.7])
+def test_aps_sets_select_kernel(cuda, C, error):
+    """Sets without scores on wide rows run the select kernel (threshold selection + a sort of the selected values only,
+    undecided rows re-done by the full sort): same mask and sizes as the oracle and as the path that sorts every row."""
+    from fortuna_b200 import ops
+
+    n_val = 5000
+    vp = _probs(n_val, C, seed=12)
+    vt = np.random.default_rng(13).integers(0, C, n_val).astype(np.int32)
+    tp = _select_rows(C, seed=C + int(error * 100))
+    val_scores, test_scores = Sc.get_scores(vp, vt, tp, "aps")
+    conds, sizes, _ = Sc.conformal_sets(val_scores, test_scores, error)
+    vs = ops.sort_f32_(torch.from_numpy(val_scores.copy()).to(cuda))
+    thr = Sc.conformal_threshold(n_val, error)
+    tpt = torch.from_numpy(tp).to(cuda)
+    mask, sz = ops.aps_conformal_sets(tpt, vs, thr)
+    assert np.array_equal(sz.cpu().numpy(), sizes)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), conds)
+    m1, s1, _ = ops.aps_conformal_sets(tpt, vs, thr, want_scores=True)
+    assert torch.equal(m1, mask) and torch.equal(s1, sz)
+
+
+@pytest.mark.parametrize("C", [1000, 512])
+def test_aps_sets_select_kernel_quantile_equal_to_a_prefix_sum(cuda, C):
+    """The validation scores ARE prefix sums of the test rows, so the quantile equals a test score exactly: the
+    boundary rank is decided by equality, and the select kernel's margin test has to send near-misses to the full sort."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(C)
+    tp = P.softmax((4 * r.standard_normal((2000, C))).astype(np.float32))
+    n_val = 400
+    vp = tp[:n_val]
+    cums = Sc.aps_cumsums(vp)
+    order = Sc.descending_perm(vp)
+    vt = order[np.arange(n_val), r.integers(5, 80, n_val)].astype(np.int32)  # class at a random shallow rank
+    for error in (0.1, 0.5, 0.9):
+        val_scores, test_scores = Sc.get_scores(vp, vt, tp, "aps")
+        assert np.array_equal(val_scores, cums[np.arange(n_val), vt])
+        conds, sizes, _ = Sc.conformal_sets(val_scores, test_scores, error)
+        vs = ops.sort_f32_(torch.from_numpy(val_scores.copy()).to(cuda))
+        mask, sz = ops.aps_conformal_sets(torch.from_numpy(tp).to(cuda), vs, Sc.conformal_threshold(n_val, error))
+        assert np.array_equal(sz.cpu().numpy(), sizes)
+        assert np.array_equal(mask.cpu().numpy().astype(bool), conds)

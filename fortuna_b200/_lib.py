@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfortuna_b200.so")
+# FB200_LIB: another build of the same library (A/B comparisons of a kernel variant, scripts/ab_lib.sh)
+LIB_PATH = os.environ.get("FB200_LIB") or os.path.join(_HERE, "lib", "libfortuna_b200.so")
 
 F32, BF16 = 0, 1
 W_SDC, W_SCD = 0, 1

@@ -18,6 +18,9 @@ namespace fb200 {
 
 // ------------------------------------------------------------------------------------------------
 // threefry2x32, 20 rounds, jax/_src/prng.py layout.  rotl is one SHF.L.W; xors are LOP3.
+// (Round 2 tried taking the rotation from the 64-bit product x1 * 2^r - one IMAD.WIDE on the FMA pipe, the OR of its two
+// words folded into the XOR's LOP3 - to relieve the half-rate ALU pipe K1 is co-limited by: 0.381 ms instead of 0.355 ms
+// per c5 step on the same box, scripts/ab_lib.sh + scripts/bench_sampler.py.  The plain form stays.)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
 

@@ -168,6 +168,10 @@ SIGNATURES = {
     "fb200_reg_output_sample_targets": (_i, [_P, _P, _P, _i, _i, _i, _P, _P]),
     "fb200_output_calib_focal_loss_terms": (_i, [_P, _i, _P, _P, _i, _i, _f, _P, _sz, _P, _P]),
     "fb200_output_calib_scaled_mse_terms": (_i, [_P, _P, _P, _i, _i, _P, _sz, _P, _P]),
+    "fb200_focal_loss_grad": (_i, [_P, _P, _i, _i, _f, _P, _P, _P, _P]),
+    "fb200_scaled_mse_loss_grad": (_i, [_P, _P, _i, _i, _P, _P, _P, _P]),
+    "fb200_dot_f32": (_i, [_P, _P, _i64, _P, _P]),
+    "fb200_adam_step_f32": (_i, [_P, _P, _P, _P, _i64, _f, _f, _f, _f, _f, _f, _P]),
     "fb200_reg_mc_entropies": (_i, [_P, _P, _P, _P, _i, _i, _i, _i, _i, _P, _P, _P, _P]),
     "fb200_conformal_bayes_workspace_bytes": (_sz, [_i, _i, _i]),
     "fb200_conformal_bayes_sets": (_i, [_P, _P, _i, _i, _i, _i, _f, _P, _sz, _P, _P, _P, _P, _P]),

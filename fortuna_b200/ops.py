@@ -856,6 +856,59 @@ def output_calib_scaled_mse_terms(outputs, targets, log_temp=None):
     return out
 
 
+def focal_loss_grad(logits, targets, gamma=2.0, want_grad=True):
+    """logits float32 [n,C], targets int32 [n] -> (loss float64 [1] = mean focal loss, grad float32 [n,C] = d loss / d logits
+    or None, loss_rows float32 [n]) - the loss head of CalibClassifier.calibrate (fb200_focal_loss_grad)."""
+    n, Cn = logits.shape
+    grad = torch.empty_like(logits) if want_grad else None
+    rows = torch.empty(n, dtype=torch.float32, device=logits.device)
+    loss = torch.empty(1, dtype=torch.float64, device=logits.device)
+    check(
+        lib().fb200_focal_loss_grad(_ptr(logits, torch.float32), _ptr(targets, torch.int32), n, Cn, float(gamma),
+                                    _ptr(grad, torch.float32, True), _ptr(rows), _ptr(loss), _stream()),
+        "fb200_focal_loss_grad",
+    )
+    return loss, grad, rows
+
+
+def scaled_mse_loss_grad(outputs, targets, want_grad=True):
+    """outputs float32 [n,2d] = [mu | log var], targets float32 [n,d] -> (loss float64 [1] = mean over n of the summed
+    variance-scaled squared errors, grad float32 [n,2d] or None, loss_terms float32 [n,d]) (fb200_scaled_mse_loss_grad)."""
+    n, two_d = outputs.shape
+    d = two_d // 2
+    grad = torch.empty_like(outputs) if want_grad else None
+    terms = torch.empty((n, d), dtype=torch.float32, device=outputs.device)
+    loss = torch.empty(1, dtype=torch.float64, device=outputs.device)
+    check(
+        lib().fb200_scaled_mse_loss_grad(_ptr(outputs, torch.float32), _ptr(targets, torch.float32), n, d,
+                                         _ptr(grad, torch.float32, True), _ptr(terms), _ptr(loss), _stream()),
+        "fb200_scaled_mse_loss_grad",
+    )
+    return loss, grad, terms
+
+
+def dot_f32(a, b):
+    """float64 [1] = sum a * b over two float32 tensors of equal size, fixed summation order (fb200_dot_f32)."""
+    out = torch.empty(1, dtype=torch.float64, device=a.device)
+    check(lib().fb200_dot_f32(_ptr(a, torch.float32), _ptr(b, torch.float32), a.numel(), _ptr(out), _stream()), "fb200_dot_f32")
+    return out
+
+
+def adam_step_(params, grads, mu, nu, count, lr=1e-2, b1=0.9, b2=0.999, eps=1e-8):
+    """optax.adam step number ``count`` (1-based) over flat float32 vectors, in place (fb200_adam_step_f32)."""
+    import numpy as np
+
+    f = np.float32
+    c1, c2 = f(1) - f(b1) ** f(count), f(1) - f(b2) ** f(count)
+    check(
+        lib().fb200_adam_step_f32(_ptr(params, torch.float32), _ptr(grads, torch.float32), _ptr(mu, torch.float32),
+                                  _ptr(nu, torch.float32), params.numel(), float(lr), float(b1), float(b2), float(eps),
+                                  float(c1), float(c2), _stream()),
+        "fb200_adam_step_f32",
+    )
+    return params
+
+
 def maxcov_counts(probs, targets, taus, side, threshold):
     """probs float32 [n], targets int32 [n], taus float32 [n_taus] sorted (ascending for side 0, descending for side 1)
     -> (counts, labels) int32 [n_taus]: per candidate tau the number of selected points and the sum of their counted

@@ -7,7 +7,7 @@ import numpy as np
 
 from ..utils.random import RandomNumberGenerator
 from .config.base import Config
-from .output_calib_model_calibrator import OutputCalibModelCalibrator, resolve_loss
+from .output_calib_model_calibrator import OutputCalibModelCalibrator, resolve_loss_or_user
 from .output_calib_state_repository import OutputCalibStateRepository, restore_state
 from .state import OutputCalibState
 
@@ -48,7 +48,9 @@ class OutputCalibModel:
         config = config or Config()
         if (val_targets is not None and val_outputs is None) or (val_targets is None and val_outputs is not None):
             raise ValueError("For validation, both `val_outputs` and `val_targets` must be passed as arguments.")
-        loss_kind = resolve_loss(loss_fn, self._regression)
+        loss_kind = resolve_loss_or_user(loss_fn, self._regression)
+        if loss_kind[0] == "user":
+            loss_kind = ("user", loss_kind[1], self._regression)
         identity = self.output_calibrator is None
         calibrator = OutputCalibModelCalibrator(
             calib_outputs=calib_outputs, calib_targets=calib_targets, val_outputs=val_outputs, val_targets=val_targets,

@@ -60,8 +60,49 @@ def resolve_loss(loss_fn: Callable, regression: bool):
         "loss-and-derivative kernel.")
 
 
+def resolve_loss_or_user(loss_fn: Callable, regression: bool):
+    """As ``resolve_loss``; any other callable ``loss_fn(calibrated_outputs, targets) -> scalar`` over torch tensors is
+    accepted as ("user", loss_fn): user code is differentiated by autograd in the calibrated outputs, and the chain rule
+    through the temperature is one ordered dot product on the device (``loss_and_grad``)."""
+    try:
+        return resolve_loss(loss_fn, regression)
+    except NotImplementedError:
+        if not callable(loss_fn) or isinstance(loss_fn, functools.partial) and loss_fn.func in (focal_loss_fn, scaled_mse_fn):
+            raise
+        return ("user", loss_fn)
+
+
+def _user_loss_and_grad(fn, outputs: torch.Tensor, targets: torch.Tensor, log_temp, identity: bool, regression: bool):
+    """Classification: z' = z exp(-log_temp), dloss/dlog_temp = -sum dloss/dz' . z' (output_calibrator/classification.py:
+    7-17).  Regression: log var' = log var + log_temp, dloss/dlog_temp = sum dloss/dlog var' (regression.py:7-19)."""
+    zc = outputs.clone()
+    if not identity:
+        lt = torch.as_tensor(np.array(log_temp, dtype=np.float32).reshape(1), device=outputs.device)
+        if regression:
+            d = outputs.shape[1] // 2
+            zc[:, d:] += lt  # the calibrated log variance is a one-scalar shift
+        else:
+            ops.softmax_rows_(zc, ops.EPI_LOGITS, log_temp=lt)
+    leaf = zc.requires_grad_(True)
+    with torch.enable_grad():
+        loss = fn(leaf, targets)
+        loss.backward()
+    g = leaf.grad.contiguous()
+    if identity:
+        return np.float32(loss.item()), np.float32(0.0)
+    if regression:
+        d = outputs.shape[1] // 2
+        glv = g[:, d:].contiguous()
+        dlt = ops.dot_f32(glv, torch.ones_like(glv)).item()
+    else:
+        dlt = -ops.dot_f32(g, zc.detach().contiguous()).item()
+    return np.float32(loss.item()), np.float32(dlt)
+
+
 def loss_and_grad(kind, outputs: torch.Tensor, targets: torch.Tensor, log_temp: np.ndarray, identity: bool = False):
     """(loss, dloss/dlog_temp) at log_temp, float32 scalars; the mean over the calibration inputs."""
+    if kind[0] == "user":
+        return _user_loss_and_grad(kind[1], outputs, targets, log_temp, identity, kind[2])
     lt = None if identity else torch.as_tensor(np.array(log_temp, dtype=np.float32).reshape(1), device=outputs.device)
     n = outputs.shape[0]
     if kind[0] == "focal":

@@ -445,6 +445,31 @@ int fb200_output_calib_focal_loss_terms(const void* logits, int dtype, const int
 int fb200_output_calib_scaled_mse_terms(const float* outputs, const float* targets, const float* log_temp, int B, int d,
                                         void* workspace, size_t workspace_bytes, double* out, void* stream);
 
+/* Loss heads of the calibration models (CalibClassifier / CalibRegressor .calibrate, fortuna/calib_model/base.py:62-154
+ * -> CalibModelCalibrator.training_loss_step, fortuna/calib_model/calib_model_calibrator.py:29-77 -> Loss.__call__,
+ * fortuna/calib_model/loss.py:26-128, which the reference differentiates through the model by autodiff) for their DEFAULT
+ * loss functions: one pass over the model outputs returns the per-input loss terms and the gradient in the outputs,
+ * scaled by 1/n (the losses are means), for the backbone's backward pass:
+ *   focal (fortuna/loss/classification/focal_loss.py:10-36): p = softmax(logits_i)[y_i]; loss_rows[i] = -(1-p)^gamma log p;
+ *     grad[i,c] = (1/n) (gamma (1-p)^(gamma-1) log p - (1-p)^gamma / p) p (delta(c, y_i) - softmax(logits_i)[c])
+ *   scaled MSE (fortuna/loss/regression/scaled_mse.py:6-26): outputs_i = [mu | log var];
+ *     loss_terms[i,j] = exp(-lv) (y - mu)^2 + lv;  grad = (1/n) [-2 exp(-lv)(y - mu) | 1 - exp(-lv)(y - mu)^2]
+ * grad / loss_rows may be NULL; loss_mean (double[1], optional, needs the loss terms) = their sum / n in a fixed order. */
+int fb200_focal_loss_grad(const float* logits, const int32_t* targets, int n, int C, float gamma, float* grad,
+                          float* loss_rows, double* loss_mean, void* stream);
+int fb200_scaled_mse_loss_grad(const float* outputs, const float* targets, int n, int d, float* grad, float* loss_terms,
+                               double* loss_mean, void* stream);
+/* optax.adam(lr, b1, b2, eps) - the default `Optimizer.method` of the calibration configs
+ * (fortuna/calib_model/config/optimizer.py:20, applied by TrainState.apply_gradients at fortuna/training/trainer.py:170) -
+ * over a flat float32 parameter vector, in place: mu = (1-b1) g + b1 mu; nu = (1-b2) g^2 + b2 nu;
+ * params += -lr (mu / c1) / (sqrt(nu / c2) + eps), c1 = 1 - b1^t, c2 = 1 - b2^t (float32, from the caller). */
+int fb200_adam_step_f32(float* params, const float* grads, float* mu, float* nu, int64_t n, float lr, float b1, float b2,
+                        float eps, float c1, float c2, void* stream);
+/* out[0] = sum_i a[i] b[i] in double, fixed order: the chain rule of a USER-SUPPLIED output-calibration loss through the
+ * temperature, d loss / d log_temp = -sum dloss/dz' . z' with z' the calibrated outputs
+ * (fortuna/output_calib_model/loss.py:26-79, output_calibrator/classification.py:7-17). */
+int fb200_dot_f32(const float* a, const float* b, int64_t n, double* out, void* stream);
+
 /* Maximum-coverage fixed-precision calibration of a binary classifier
  * (MaxCoverageFixedPrecisionBinaryClassificationCalibrator, fortuna/conformal/classification/
  * maxcovfixprec_binary_classfication.py:33-124).  For a SORTED grid of candidate taus (ascending for side 0, descending

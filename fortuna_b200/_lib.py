@@ -172,6 +172,11 @@ SIGNATURES = {
     "fb200_scaled_mse_loss_grad": (_i, [_P, _P, _i, _i, _P, _P, _P, _P]),
     "fb200_dot_f32": (_i, [_P, _P, _i64, _P, _P]),
     "fb200_adam_step_f32": (_i, [_P, _P, _P, _P, _i64, _f, _f, _f, _f, _f, _f, _P]),
+    "fb200_multivalid_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "fb200_multivalid_stats": (_i, [_P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _i, _P, _sz, _P, _P]),
+    "fb200_multivalid_patch": (_i, [_P, _P, _i, _i, _i, _i, _i, _i, _f, _i, _i, _f, _f, _i, _P, _P]),
+    "fb200_multivalid_loss": (_i, [_P, _P, _i, _i, _i, _i, _f, _P, _P, _P]),
+    "fb200_batchmvp_delta_counts": (_i, [_P, _P, _P, _i, _i, _i, _i, _f, _i, _P, _i, _P, _P]),
     "fb200_reg_mc_entropies": (_i, [_P, _P, _P, _P, _i, _i, _i, _i, _i, _P, _P, _P, _P]),
     "fb200_conformal_bayes_workspace_bytes": (_sz, [_i, _i, _i]),
     "fb200_conformal_bayes_sets": (_i, [_P, _P, _i, _i, _i, _i, _f, _P, _sz, _P, _P, _P, _P, _P]),

@@ -11,3 +11,13 @@ from .classification.simple_prediction import (  # noqa: F401
     SimplePredictionConformalClassifier,
 )
 from .regression.quantile import OneDimensionalUncertaintyConformalRegressor, QuantileConformalRegressor  # noqa: F401
+from .multivalid.iterative.classification.binary_multicalibrator import BinaryClassificationMulticalibrator  # noqa: F401
+from .multivalid.iterative.classification.top_label_multicalibrator import TopLabelMulticalibrator  # noqa: F401
+from .multivalid.iterative.multicalibrator import Multicalibrator  # noqa: F401
+from .multivalid.iterative.regression.batch_mvp import BatchMVPConformalClassifier  # noqa: F401
+from .multivalid.one_shot.classification.binary_multicalibrator import (  # noqa: F401
+    OneShotBinaryClassificationMulticalibrator,
+)
+from .multivalid.one_shot.classification.top_label_multicalibrator import OneShotTopLabelMulticalibrator  # noqa: F401
+from .multivalid.one_shot.multicalibrator import OneShotMulticalibrator  # noqa: F401
+from .regression.batch_mvp import BatchMVPConformalRegressor  # noqa: F401

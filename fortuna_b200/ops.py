@@ -909,6 +909,75 @@ def adam_step_(params, grads, mu, nu, count, lr=1e-2, b1=0.9, b2=0.999, eps=1e-8
     return params
 
 
+# ------------------------------------------------------------------------------------------- multivalid scorers
+def multivalid_stats(values, scores, groups, buckets, top_label=False, mode=0, taus=(0, 1, 2)):
+    """values float32 [n, Dv], scores float32 [n, D], groups uint8 [n, G] or None, buckets float32 [n_buckets] ->
+    float64 [3, G, n_buckets, D, 3]: per (bucket type, group, bucket, dimension) the member count, the sum of the
+    statistic (mode 0: the score; mode 1: [score <= value]) and the sum of the values over the members
+    (fb200_multivalid_stats)."""
+    n, Dv = values.shape
+    D = scores.shape[1]
+    G = 1 if groups is None else groups.shape[1]
+    nb = buckets.numel()
+    nbytes = int(lib().fb200_multivalid_workspace_bytes(n, G, nb, D))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=values.device)
+    out = torch.empty((3, G, nb, D, 3), dtype=torch.float64, device=values.device)
+    mask = sum(1 << int(t) for t in taus)
+    check(
+        lib().fb200_multivalid_stats(_ptr(values, torch.float32), _ptr(scores, torch.float32), _ptr(groups, torch.uint8, True),
+                                     _ptr(buckets, torch.float32), n, D, Dv, G, nb, int(bool(top_label)), int(mode), mask,
+                                     _ptr(ws), nbytes, _ptr(out), _stream()),
+        "fb200_multivalid_stats",
+    )
+    return out
+
+
+def multivalid_patch_(values, groups, g, c, tau, v, n_buckets, eta, patch, top_label=False, multiplicative=False):
+    """In place: the (tau, g, v, c) members of values [n, Dv] move by the patch and are clipped to [0, 1]; returns the
+    member count as an int32 [1] tensor (fb200_multivalid_patch)."""
+    n, Dv = values.shape
+    G = 1 if groups is None else groups.shape[1]
+    cnt = torch.empty(1, dtype=torch.int32, device=values.device)
+    check(
+        lib().fb200_multivalid_patch(_ptr(values, torch.float32), _ptr(groups, torch.uint8, True), n, Dv, G, int(g), int(c),
+                                     int(tau), float(v), int(n_buckets), int(bool(top_label)), float(eta), float(patch),
+                                     int(bool(multiplicative)), _ptr(cnt), _stream()),
+        "fb200_multivalid_patch",
+    )
+    return cnt
+
+
+def multivalid_loss(values, scores, mode=0, coverage=0.0):
+    """float64 [1]: sum over all elements of (values - scores)^2 (mode 0) or of the pinball terms at ``coverage`` (mode 1);
+    values float32 [n, Dv], scores float32 [n, D], Dv = 1 (scores[:, 0] is used) or D (fb200_multivalid_loss)."""
+    n, Dv = values.shape
+    D = scores.shape[1]
+    terms = torch.empty(n * Dv, dtype=torch.float32, device=values.device)
+    out = torch.empty(1, dtype=torch.float64, device=values.device)
+    check(
+        lib().fb200_multivalid_loss(_ptr(values, torch.float32), _ptr(scores, torch.float32), n, D, Dv, int(mode),
+                                    float(coverage), _ptr(terms), _ptr(out), _stream()),
+        "fb200_multivalid_loss",
+    )
+    return out
+
+
+def batchmvp_delta_counts(values, scores, groups, g, tau, v, n_buckets, deltas):
+    """int64 [m + 1]: per delta the members of (tau, g, v) with score <= value + delta; last entry the member count
+    (fb200_batchmvp_delta_counts).  values / scores float32 [n]."""
+    n = values.numel()
+    G = 1 if groups is None else groups.shape[1]
+    m = deltas.numel()
+    counts = torch.empty(m + 1, dtype=torch.int64, device=values.device)
+    check(
+        lib().fb200_batchmvp_delta_counts(_ptr(values, torch.float32), _ptr(scores, torch.float32),
+                                          _ptr(groups, torch.uint8, True), n, G, int(g), int(tau), float(v), int(n_buckets),
+                                          _ptr(deltas, torch.float32), m, _ptr(counts), _stream()),
+        "fb200_batchmvp_delta_counts",
+    )
+    return counts
+
+
 def maxcov_counts(probs, targets, taus, side, threshold):
     """probs float32 [n], targets int32 [n], taus float32 [n_taus] sorted (ascending for side 0, descending for side 1)
     -> (counts, labels) int32 [n_taus]: per candidate tau the number of selected points and the sum of their counted

@@ -470,6 +470,37 @@ int fb200_adam_step_f32(float* params, const float* grads, float* mu, float* nu,
  * (fortuna/output_calib_model/loss.py:26-79, output_calibrator/classification.py:7-17). */
 int fb200_dot_f32(const float* a, const float* b, int64_t n, double* out, void* stream);
 
+/* Multivalid scorers: BatchMVP and the multicalibrators (fortuna/conformal/multivalid/iterative/base.py:34-333,
+ * multicalibrator.py:14-151, batch_mvp.py:17-288, classification/top_label_multicalibrator.py:19-133).
+ * fb200_multivalid_stats - the per-round statistics the reference computes as a vmap over (bucket type tau, group g, bucket
+ * v_j, score dimension c) of _calibration_error: for b = cond_tau(x, v_j) * groups[:, g] (* [argmax_k values[:, k] == c]
+ * when top_label), cond_0: |x - v| < h, cond_1: x + h >= v, cond_2: x - h <= v, h = float32(0.5 / n_buckets)
+ * (iterative/base.py:346-364), x = values[:, 0] (Dv = 1) or values[:, c] (Dv = D):
+ *   out[((tau * G + g) * n_buckets + j) * D + c][0..2] = ( |b|,  sum stat b,  sum x b )   (double; tau = 0..2)
+ *   mode 0: stat = scores[:, c] (mean(scores b), multicalibrator.py:81-100); mode 1: stat = [scores <= x]
+ *   (mean(conds), batch_mvp.py:166-192).  tau_mask: bit tau = compute that bucket type (others stay zero).
+ * values float32 [n, Dv]; scores float32 [n, D]; groups uint8 [n, G] or NULL (one all-true group, G = 1); buckets float32
+ * [n_buckets] = linspace(0, 1, n_buckets).  Deterministic (integer counts, float sums added in a fixed order).
+ * fb200_multivalid_patch - iterative/base.py:381-397 on the members of ONE (tau, g, v, c), in place:
+ *   values[b(, c)] = clip(values + eta patch, 0, 1)  |  clip(values (1 - eta (1 - patch)), 0, 1);  n_members = |b| (int32[1],
+ *   optional).
+ * fb200_multivalid_loss - mode 0: sum (values - scores)^2 over all n * Dv elements (mixins/multicalibrator.py:10-15; the
+ *   caller divides where the reference takes a mean); mode 1: sum of the pinball terms at `coverage` (mixins/batchmvp.py:
+ *   12-27).  terms: float32 [n * Dv] scratch.  out: double[1].
+ * fb200_batchmvp_delta_counts - the patch search of BatchMVP (batch_mvp.py:194-230): counts[k] = #{i in b : scores_i <=
+ *   values_i + deltas[k]}, counts[m] = |b| (uint64 [m + 1]). */
+size_t fb200_multivalid_workspace_bytes(int n, int G, int n_buckets, int D);
+int fb200_multivalid_stats(const float* values, const float* scores, const uint8_t* groups, const float* buckets, int n, int D,
+                           int Dv, int G, int n_buckets, int top_label, int mode, int tau_mask, void* workspace,
+                           size_t workspace_bytes, double* out, void* stream);
+int fb200_multivalid_patch(float* values, const uint8_t* groups, int n, int Dv, int G, int g, int c, int tau, float v,
+                           int n_buckets, int top_label, float eta, float patch, int multiplicative, int32_t* n_members,
+                           void* stream);
+int fb200_multivalid_loss(const float* values, const float* scores, int n, int D, int Dv, int mode, float coverage,
+                          float* terms, double* out, void* stream);
+int fb200_batchmvp_delta_counts(const float* values, const float* scores, const uint8_t* groups, int n, int G, int g, int tau,
+                                float v, int n_buckets, const float* deltas, int m, uint64_t* counts, void* stream);
+
 /* Maximum-coverage fixed-precision calibration of a binary classifier
  * (MaxCoverageFixedPrecisionBinaryClassificationCalibrator, fortuna/conformal/classification/
  * maxcovfixprec_binary_classfication.py:33-124).  For a SORTED grid of candidate taus (ascending for side 0, descending

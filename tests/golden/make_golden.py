@@ -203,6 +203,37 @@ def oracle_vectors():
     tp, tn, vp, vn = MC.calibrate(yb, pb, 0.8, 0.8, n_taus=40)
     out["mc_taus"], out["mc_values_pos"], out["mc_values_neg"] = np.array([tp, tn], np.float32), vp, vn
     out["mc_patched"] = MC.apply_patches(pb, tp, tn)
+    # --- calibration models (loss heads, Adam) and multivalid scorers
+    from oracle import calib_model as CM
+    from oracle import multivalid as MV
+
+    zc = (2 * r.standard_normal((40, 6))).astype(np.float32)
+    yc = r.integers(0, 6, 40).astype(np.int32)
+    out["cm_logits"], out["cm_targets"] = zc, yc
+    out["cm_focal_g2"] = np.array(CM.focal_loss(zc, yc, 2.0), np.float32)
+    out["cm_focal_grad_g2"] = CM.focal_loss_grad(zc, yc, 2.0).astype(np.float32)
+    ad = CM.Adam(1e-2)
+    pa, ga = zc.ravel().copy(), CM.focal_loss_grad(zc, yc, 2.0).astype(np.float32).ravel()
+    st = ad.init(pa)
+    for _ in range(3):
+        pa, st = ad.step(pa, ga, st)
+    out["cm_adam3"] = pa
+    sm0 = r.random(300).astype(np.float32)
+    xm = np.clip(sm0 + 0.2, 0, 1).astype(np.float32)  # values biased upwards against the scores: something to patch
+    sm = np.clip(sm0 + 0.1 * r.standard_normal(300), 0, 1).astype(np.float32)
+    gm = r.random((300, 2)) < 0.5
+    out["mv_values"], out["mv_scores"], out["mv_groups"] = xm, sm, gm
+    out["mv_perm_seed2_n300"] = MV.permutation(2, 300).astype(np.int32)
+    it = MV.Iterative("multicalibrator", seed=2)
+    stt = it.calibrate(sm, gm, values=xm, n_rounds=4, n_buckets=8, eta=0.5)
+    out["mv_mc_losses"] = np.array(stt["losses"], np.float32)
+    out["mv_mc_patches"] = np.array(it.patches, np.float64)
+    out["mv_mc_applied"] = it.apply_patches(gm, xm)
+    bm = MV.Iterative("batchmvp", seed=2)
+    stb = bm.calibrate(sm, gm, n_rounds=4, n_buckets=8, eta=0.5, coverage=0.9, bucket_types=(">=", "<="))
+    out["mv_bm_losses"] = np.array(stb["losses"], np.float32)
+    out["mv_bm_patches"] = np.array(bm.patches, np.float64)
+    out["mv_oneshot_patches"] = MV.one_shot_patches(sm, np.round(xm, 1), n_buckets=11)
     return out
 
 

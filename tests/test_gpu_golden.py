@@ -239,3 +239,36 @@ def test_output_calib_and_maxcov_vectors(cuda):
     assert cal.patches["tau_pos"] == VEC["mc_taus"][0] and cal.patches["tau_neg"] == VEC["mc_taus"][1]
     assert np.array_equal(cal._values[0], VEC["mc_values_pos"]) and np.array_equal(cal._values[1], VEC["mc_values_neg"])
     assert np.array_equal(patched.cpu().numpy(), VEC["mc_patched"])
+
+
+def test_calib_model_and_multivalid_against_frozen_vectors(cuda):
+    """The loss head, the fused Adam and the multivalid classes on the frozen inputs of oracle_vectors.npz."""
+    from fortuna_b200 import ops
+    from fortuna_b200.conformal import BatchMVPConformalRegressor, Multicalibrator, OneShotMulticalibrator
+    from fortuna_b200.conformal.multivalid.iterative.base import jax_permutation
+
+    z = torch.from_numpy(VEC["cm_logits"]).to(cuda)
+    y = torch.from_numpy(VEC["cm_targets"]).to(cuda)
+    loss, grad, _ = ops.focal_loss_grad(z, y, 2.0)
+    np.testing.assert_allclose(loss.item(), float(VEC["cm_focal_g2"]), rtol=1e-5)
+    np.testing.assert_allclose(grad.cpu().numpy(), VEC["cm_focal_grad_g2"], rtol=2e-4, atol=1e-8)
+    p = z.reshape(-1).clone()
+    g = torch.from_numpy(VEC["cm_focal_grad_g2"].ravel().copy()).to(cuda)
+    mu, nu = torch.zeros_like(p), torch.zeros_like(p)
+    for step in (1, 2, 3):
+        ops.adam_step_(p, g, mu, nu, step, 1e-2)
+    assert np.array_equal(p.cpu().numpy(), VEC["cm_adam3"])
+    assert np.array_equal(jax_permutation(2, 300, cuda), VEC["mv_perm_seed2_n300"])
+    x, s, gr = VEC["mv_values"], VEC["mv_scores"], VEC["mv_groups"]
+    mc = Multicalibrator(seed=2)
+    st = mc.calibrate(scores=s, groups=gr, values=x, n_rounds=4, n_buckets=8, eta=0.5)
+    np.testing.assert_allclose(st["losses"], VEC["mv_mc_losses"], rtol=2e-5)
+    np.testing.assert_allclose(np.array(mc.patches, np.float64), VEC["mv_mc_patches"], rtol=2e-4, atol=1e-7)
+    np.testing.assert_allclose(mc.apply_patches(gr, x).cpu().numpy(), VEC["mv_mc_applied"], rtol=1e-5, atol=1e-6)
+    bm = BatchMVPConformalRegressor(seed=2)
+    sb = bm.calibrate(scores=s, groups=gr, n_rounds=4, n_buckets=8, eta=0.5, coverage=0.9)
+    np.testing.assert_allclose(sb["losses"], VEC["mv_bm_losses"], rtol=2e-5)
+    np.testing.assert_allclose(np.array(bm.patches, np.float64), VEC["mv_bm_patches"], rtol=1e-6, atol=1e-7)
+    os_ = OneShotMulticalibrator()
+    os_.calibrate(scores=s, values=np.round(x, 1).astype(np.float32), n_buckets=11)
+    np.testing.assert_allclose(os_.patches, VEC["mv_oneshot_patches"], rtol=1e-5, atol=1e-7)

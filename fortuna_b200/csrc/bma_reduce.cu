@@ -621,7 +621,7 @@ static int launch_cls_wide(const ClsArgs& a, float* lse_ws, cudaStream_t st) {
 // above): sums are taken in source-rank order (deterministic), the (max, sumexp) pairs are merged, then the same
 // finalisation as the single-GPU kernel.  One warp per row.
 // ------------------------------------------------------------------------------------------------
-template <bool V4>
+template <bool V4, int NSRC>  // NSRC > 0: the source count at compile time (the loads of all sources are in flight at once)
 __global__ void __launch_bounds__(256) bma_finalize_slots_kernel(const float* __restrict__ slots, int n_src, int rows,
                                                                  int C, int s_total, const fb200_cls_outputs_t out,
                                                                  const int32_t* __restrict__ targets, float log_S) {
@@ -646,16 +646,31 @@ __global__ void __launch_bounds__(256) bma_finalize_slots_kernel(const float* __
     float sp[W], sp2[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) sp[k] = sp2[k] = 0.0f;
-    for (int r = 0; r < n_src; ++r) {
-      const float* pr = row0 + (size_t)r * src_stride;
-      if constexpr (V4) {
-        const float4 a = *reinterpret_cast<const float4*>(pr + c0);
-        const float4 q = *reinterpret_cast<const float4*>(pr + C + c0);
-        sp[0] += a.x; sp[1] += a.y; sp[2] += a.z; sp[3] += a.w;
-        sp2[0] += q.x; sp2[1] += q.y; sp2[2] += q.z; sp2[3] += q.w;
-      } else {
-        sp[0] += pr[c0];
-        sp2[0] += pr[C + c0];
+    if constexpr (V4 && NSRC > 0) {
+      float4 a[NSRC], q[NSRC];
+#pragma unroll
+      for (int r = 0; r < NSRC; ++r) {
+        const float* pr = row0 + (size_t)r * src_stride;
+        a[r] = *reinterpret_cast<const float4*>(pr + c0);
+        q[r] = *reinterpret_cast<const float4*>(pr + C + c0);
+      }
+#pragma unroll
+      for (int r = 0; r < NSRC; ++r) {  // same source-rank order as the rolled loop
+        sp[0] += a[r].x; sp[1] += a[r].y; sp[2] += a[r].z; sp[3] += a[r].w;
+        sp2[0] += q[r].x; sp2[1] += q[r].y; sp2[2] += q[r].z; sp2[3] += q[r].w;
+      }
+    } else {
+      for (int r = 0; r < n_src; ++r) {
+        const float* pr = row0 + (size_t)r * src_stride;
+        if constexpr (V4) {
+          const float4 a = *reinterpret_cast<const float4*>(pr + c0);
+          const float4 q = *reinterpret_cast<const float4*>(pr + C + c0);
+          sp[0] += a.x; sp[1] += a.y; sp[2] += a.z; sp[3] += a.w;
+          sp2[0] += q.x; sp2[1] += q.y; sp2[2] += q.z; sp2[3] += q.w;
+        } else {
+          sp[0] += pr[c0];
+          sp2[0] += pr[C + c0];
+        }
       }
     }
     float mean[W], av[W], ev[W];
@@ -1026,12 +1041,18 @@ extern "C" int fb200_bma_finalize_cls_slots(const float* slots, int n_src, int r
   const bool v4 = (C % 4 == 0) && fb200_aligned16(slots) && fb200_aligned16(out->mean) &&
                   fb200_aligned16(out->aleatoric_variance) && fb200_aligned16(out->epistemic_variance) &&
                   fb200_aligned16(out->variance) && fb200_aligned16(out->std);
-  if (v4)
-    bma_finalize_slots_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(slots, n_src, rows, C, s_total, *out, targets,
-                                                                            logf((float)s_total));
+  const float log_S = logf((float)s_total);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (v4 && n_src == 8)
+    bma_finalize_slots_kernel<true, 8><<<grid, 256, 0, st>>>(slots, n_src, rows, C, s_total, *out, targets, log_S);
+  else if (v4 && n_src == 4)
+    bma_finalize_slots_kernel<true, 4><<<grid, 256, 0, st>>>(slots, n_src, rows, C, s_total, *out, targets, log_S);
+  else if (v4 && n_src == 2)
+    bma_finalize_slots_kernel<true, 2><<<grid, 256, 0, st>>>(slots, n_src, rows, C, s_total, *out, targets, log_S);
+  else if (v4)
+    bma_finalize_slots_kernel<true, 0><<<grid, 256, 0, st>>>(slots, n_src, rows, C, s_total, *out, targets, log_S);
   else
-    bma_finalize_slots_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(slots, n_src, rows, C, s_total, *out, targets,
-                                                                             logf((float)s_total));
+    bma_finalize_slots_kernel<false, 0><<<grid, 256, 0, st>>>(slots, n_src, rows, C, s_total, *out, targets, log_S);
   FB200_LAUNCH_CHECK();
   return 0;
 }

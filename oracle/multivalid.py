@@ -18,15 +18,19 @@ from .scoring import linspace_f32
 F32 = np.float32
 
 
-def permutation(seed: int, n: int) -> np.ndarray:
-    """jax.random.choice(PRNGKey(seed), n, shape=(n,), replace=False) -> jax/_src/random.py _shuffle."""
-    key = prng.PRNGKey(seed)
+def permutation_from_key(key, n: int) -> np.ndarray:
+    """jax.random.choice(key, n, shape=(n,), replace=False) -> jax/_src/random.py _shuffle."""
+    key = np.asarray(key, dtype=np.uint32)
     rounds = int(np.ceil(3 * np.log(max(1, n)) / np.log(np.iinfo(np.uint32).max)))
     x = np.arange(n)
     for _ in range(rounds):
         key, sub = prng.split(key, 2)
         x = x[np.argsort(prng.random_bits(sub, n), kind="stable")]
     return x
+
+
+def permutation(seed: int, n: int) -> np.ndarray:
+    return permutation_from_key(prng.PRNGKey(seed), n)
 
 
 def get_b(groups, values, v, g, c, tau, n_buckets, top_label=False):

@@ -11,7 +11,8 @@ What a run through this stand-in pins, and what it does not:
   reference's .py files.
 * not pinned: the numerics of jax PRIMITIVES.  jnp.sum / mean use numpy's pairwise order instead of XLA's; exp / log /
   cos are libm's; jnp.cumsum is bound to the XLA-order scan restated in oracle/scoring.py (flagged there as a
-  restatement); jax.random is bound to the threefry restatement in oracle/prng.py, which IS pinned by the Random123
+  restatement); jnp.linspace and jnp.quantile are restated below from jax's library source (their formulas, not
+  numpy's: numpy's linspace differs from jax's in the last bit of interior points); jax.random is bound to the threefry restatement in oracle/prng.py, which IS pinned by the Random123
   and jax known answers in tests/golden/kat.json.  jax.nn.softmax / one_hot and jax.scipy.special.logsumexp are
   restated from jax's library source (jax/_src/nn/functions.py, jax/_src/ops/special.py).
 
@@ -434,6 +435,10 @@ class _Lax(types.ModuleType):
     def stop_gradient(x):
         return x
 
+    @staticmethod
+    def select(pred, on_true, on_false):
+        return _j(np.where(np.asarray(pred), np.asarray(on_true), np.asarray(on_false)))
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # module construction
@@ -459,6 +464,8 @@ def _make_jnp():
 
     m.array = array
     m.shape, m.ndim, m.size = np.shape, np.ndim, np.size
+    m.copy = lambda x: _j(np.array(x))
+    m.unravel_index = lambda i, shape: tuple(_j(v) for v in np.unravel_index(int(i), shape))
     m.asarray = lambda x, dtype=None: array(x, dtype)
 
     def cumsum(x, axis=None, dtype=None):
@@ -497,6 +504,18 @@ def _make_jnp():
         return _j(am[lo] * lw.reshape(sh) + am[hi] * hw.reshape(sh))
 
     m.quantile = quantile
+
+    def linspace(start, stop, num=50, endpoint=True, dtype=None):
+        # jnp.linspace is a LIBRARY function (jax/_src/numpy/lax_numpy.py), not numpy's formula: in the computation dtype
+        # (float32), step = iota(div) / div, out = start * (1 - step) + stop * step, and the endpoint is appended as is.
+        assert endpoint and num > 1
+        f = np.float32
+        start, stop, div = f(start), f(stop), num - 1
+        step = (np.arange(div, dtype=f) / f(div)).astype(f)
+        out = (start * (f(1) - step) + stop * step).astype(f)
+        return _j(np.concatenate([out, np.array([stop], dtype=f)]))
+
+    m.linspace = linspace
     m.pi, m.inf, m.nan, m.e, m.newaxis = np.pi, np.inf, np.nan, np.e, None
     m.ndarray = JArray
     for t in ("float32", "float64", "int32", "int64", "uint32", "uint8", "int8", "bool_", "complex64", "float16"):
@@ -529,8 +548,15 @@ def _make_random():
         return _j(P.uniform(np.asarray(key), n, minval, maxval).reshape(tuple(shape)))
 
     def choice(key, a, shape=(), replace=True, p=None, axis=0):
+        if p is None and not replace and tuple(shape) == (int(a),):
+            # choice(key, n, (n,), replace=False) == permutation(key, n) (jax/_src/random.py): the sort-based shuffle
+            # restated in oracle/multivalid.py (a jax LIBRARY algorithm, flagged there as a restatement)
+            from oracle import multivalid as _mv
+
+            return _j(_mv.permutation_from_key(np.asarray(key), int(a)))
         if p is not None or tuple(shape) != ():
-            raise NotImplementedError("stand-in: only the scalar, uniform random.choice(key, n) of SGMCMCPosterior.sample")
+            raise NotImplementedError("stand-in: the scalar uniform random.choice(key, n) of SGMCMCPosterior.sample and the "
+                                      "full permutation of the multivalid split only")
         return _j(np.int32(P.choice(np.asarray(key), int(a))))
 
     m.normal, m.uniform, m.choice = normal, uniform, choice
@@ -698,6 +724,22 @@ REAL_MODULES = (
     "fortuna.prob_model.predictive.base",
     "fortuna.prob_model.predictive.classification",
     "fortuna.prob_model.predictive.regression",
+    "fortuna.conformal.multivalid.base",
+    "fortuna.conformal.multivalid.iterative.base",
+    "fortuna.conformal.multivalid.iterative.batch_mvp",
+    "fortuna.conformal.multivalid.iterative.multicalibrator",
+    "fortuna.conformal.multivalid.iterative.regression.batch_mvp",
+    "fortuna.conformal.multivalid.iterative.classification.binary_multicalibrator",
+    "fortuna.conformal.multivalid.iterative.classification.top_label_multicalibrator",
+    "fortuna.conformal.multivalid.mixins.batchmvp",
+    "fortuna.conformal.multivalid.mixins.multicalibrator",
+    "fortuna.conformal.multivalid.mixins.classification.binary_multicalibrator",
+    "fortuna.conformal.multivalid.mixins.classification.top_label_multicalibrator",
+    "fortuna.conformal.multivalid.one_shot.base",
+    "fortuna.conformal.multivalid.one_shot.multicalibrator",
+    "fortuna.conformal.multivalid.one_shot.classification.binary_multicalibrator",
+    "fortuna.conformal.multivalid.one_shot.classification.top_label_multicalibrator",
+    "fortuna.conformal.classification.maxcovfixprec_binary_classfication",
 )
 
 

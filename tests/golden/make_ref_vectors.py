@@ -355,12 +355,112 @@ def gen_diagnostics():
     put("diag/ess", np.concatenate([A(ess[k]).ravel() for k in sorted(ess)]))
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# 6. multivalid scorers (conformal/multivalid/): iterative (Multicalibrator, BatchMVP, top-label, binary) and one-shot
+# --------------------------------------------------------------------------------------------------------------------
+def _mv_data(n, seed=0):
+    r = np.random.default_rng(seed)
+    x = r.random(n).astype(np.float32)
+    scores = np.clip(0.7 * x + 0.3 * r.random(n), 0, 1).astype(np.float32)
+    groups = np.stack([x < 0.5, r.random(n) < 0.3], axis=1)
+    return x, scores, groups
+
+
+def _put_run(pre, status, patches):
+    put(pre + "losses", np.array([float(A(v)) for v in status["losses"]], np.float32))
+    put(pre + "n_rounds", np.int32(status["n_rounds"]))
+    put(pre + "converged", np.int32(bool(status["converged"])))
+    # patches: (tau, g, v, c, patch) per round
+    put(pre + "patches", np.array([[float(A(t)) for t in p] for p in patches], np.float64).reshape(len(patches), 5))
+    print(f"  {pre} rounds kept: {len(patches)}")
+
+
+def gen_multivalid():
+    logging_off()
+    mc = imp("fortuna.conformal.multivalid.iterative.multicalibrator")
+    bm = imp("fortuna.conformal.multivalid.iterative.regression.batch_mvp")
+    tlm = imp("fortuna.conformal.multivalid.iterative.classification.top_label_multicalibrator")
+    bcm = imp("fortuna.conformal.multivalid.iterative.classification.binary_multicalibrator")
+    osm = imp("fortuna.conformal.multivalid.one_shot.multicalibrator")
+    osb = imp("fortuna.conformal.multivalid.one_shot.classification.binary_multicalibrator")
+    ost = imp("fortuna.conformal.multivalid.one_shot.classification.top_label_multicalibrator")
+
+    x, scores, groups = _mv_data(500)
+    tx, ts, tg = _mv_data(120, seed=5)
+    v0 = np.clip(x + 0.2, 0, 1).astype(np.float32)
+    for k, v in dict(x=x, scores=scores, groups=groups, tx=tx, ts=ts, tg=tg, v0=v0).items():
+        put("mv/data/" + k, v)
+    for tag, kw in {"add": dict(bucket_types=("<=", ">="), patch_type="additive"),
+                    "mul": dict(bucket_types=("=", ">=", "<="), patch_type="multiplicative")}.items():
+        m = mc.Multicalibrator(seed=1)
+        tv, status = m.calibrate(scores=J._j(scores), groups=J._j(groups), values=J._j(v0), test_groups=J._j(tg),
+                                 test_values=J._j(tx), n_rounds=6, n_buckets=8, eta=0.5, **kw)
+        _put_run(f"mv/multicalibrator_{tag}/", status, m.patches)
+        put(f"mv/multicalibrator_{tag}/test_values", tv)
+        put(f"mv/multicalibrator_{tag}/calibration_error", m.calibration_error(J._j(ts), J._j(tg), tv))
+    b = bm.BatchMVPConformalClassifier(seed=2)
+    status = b.calibrate(scores=J._j(scores), groups=J._j(groups), n_rounds=5, n_buckets=10, eta=0.5, coverage=0.9)
+    _put_run("mv/batchmvp/", status, b.patches)
+    th = b.apply_patches(J._j(tg))
+    put("mv/batchmvp/test_thresholds", th)
+    put("mv/batchmvp/calibration_error", b.calibration_error(J._j(ts), J._j(tg), th))
+
+    r = np.random.default_rng(4)
+    n, C = 700, 4
+    logits = r.standard_normal((n, C)).astype(np.float32)
+    probs = (np.exp(logits) / np.exp(logits).sum(1, keepdims=True)).astype(np.float32)
+    targets = np.array([r.choice(C, p=q / q.sum()) for q in probs.astype(np.float64)], dtype=np.int32)
+    probs = (np.exp(3 * logits) / np.exp(3 * logits).sum(1, keepdims=True)).astype(np.float32)  # over-confident model
+    cg = r.random((n, 2)) < 0.5
+    for k, v in dict(probs=probs, targets=targets, groups=cg).items():
+        put("mv/cls/" + k, v)
+    t = tlm.TopLabelMulticalibrator(n_classes=C, seed=0)
+    status = t.calibrate(targets=J._j(targets), groups=J._j(cg), probs=J._j(probs), n_rounds=4, n_buckets=5, eta=1.0)
+    _put_run("mv/top_label/", status, t.patches)
+    put("mv/top_label/applied", t.apply_patches(J._j(cg), J._j(probs)))
+    y = (r.random(n) < probs[:, 0] ** 2).astype(np.int32)  # the model over-predicts the positive class
+    put("mv/cls/binary_targets", y)
+    bc = bcm.BinaryClassificationMulticalibrator(seed=0)
+    status = bc.calibrate(targets=J._j(y), groups=J._j(cg), probs=J._j(probs[:, 0].copy()), n_rounds=4, n_buckets=6, eta=0.5)
+    _put_run("mv/binary/", status, bc.patches)
+
+    # one-shot: repeated values, several data points per unique value
+    xr = np.round(x, 2).astype(np.float32)
+    txr = np.round(tx, 2).astype(np.float32)
+    put("mv/one_shot/values", xr)
+    put("mv/one_shot/test_values", txr)
+    o = osm.OneShotMulticalibrator()
+    tv = o.calibrate(scores=J._j(scores), values=J._j(xr), test_values=J._j(txr), n_buckets=10)
+    put("mv/one_shot/patches", o.patches)
+    put("mv/one_shot/applied", tv)
+    yb = (np.random.default_rng(1).random(len(xr)) < xr).astype(np.int32)
+    put("mv/one_shot/binary_targets", yb)
+    ob = osb.OneShotBinaryClassificationMulticalibrator()
+    ob.calibrate(targets=J._j(yb), probs=J._j(xr), n_buckets=10)
+    put("mv/one_shot/binary_patches", ob.patches)
+    pr = np.round(np.random.default_rng(2).dirichlet(np.ones(3), 300), 2).astype(np.float32)
+    tt = np.random.default_rng(3).integers(0, 3, 300).astype(np.int32)
+    put("mv/one_shot/tl_probs", pr)
+    put("mv/one_shot/tl_targets", tt)
+    ot = ost.OneShotTopLabelMulticalibrator(n_classes=3)
+    out = ot.calibrate(targets=J._j(tt), probs=J._j(pr), test_probs=J._j(pr), n_buckets=10)
+    put("mv/one_shot/tl_patches", ot.patches)
+    put("mv/one_shot/tl_applied", out)
+
+
+def logging_off():
+    import logging
+
+    logging.disable(logging.WARNING)
+
+
 def main():
     gen_cls_predictive()
     gen_reg_predictive()
     gen_samplers()
     gen_scoring()
     gen_diagnostics()
+    gen_multivalid()
     path = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **OUT)
     print(f"wrote {path}: {len(OUT)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")

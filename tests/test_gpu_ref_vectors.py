@@ -42,8 +42,15 @@ def make_classifier(cuda, c):
             return self.output_subnet(self.dfe_subnet(x).float())
 
     pm = ProbClassifier(model=Head(), posterior_approximator=SGHMCPosteriorApproximator(n_samples=n), seed=0, device=cuda)
-    # flat layout (sorted leaf names): output_subnet/bias [C], output_subnet/weight [C, D] = kernel^T
-    bank = np.concatenate([c["b"], c["W"].transpose(0, 2, 1).reshape(n, -1)], axis=1).astype(np.float32)
+    # flat layout (sorted leaf names, leaves aligned as utils.flat_tree does): output_subnet/bias [C], then
+    # output_subnet/weight [C, D] = kernel^T
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    tmpl = FlatTree.from_shapes({"model": {"params": {"output_subnet": {"bias": (Cn,), "weight": (Cn, D)}}}}, device="cpu")
+    ob, ow = tmpl.offsets
+    bank = np.zeros((n, tmpl.flat.numel()), np.float32)
+    bank[:, ob : ob + Cn] = c["b"]
+    bank[:, ow : ow + Cn * D] = c["W"].transpose(0, 2, 1).reshape(n, -1)
     pm.attach_posterior_samples(torch.from_numpy(bank).to(cuda),
                                 freeze_fun=lambda path, v: "trainable" if "output_subnet" in path else "frozen")
     if not np.isnan(c["log_temp"]):
@@ -145,8 +152,12 @@ def _run(cuda, tx, tree_name, pre, inner_of, rms):
             continue
         flat = np.concatenate([v.cpu().numpy().ravel() for v in params.leaf_views()])
         mom = np.concatenate([v.cpu().numpy().ravel() for v in inner.momentum.leaf_views()])
-        np.testing.assert_allclose(flat, REF[pre + f"step{step}/params"], rtol=1e-5, atol=1e-7)
-        np.testing.assert_allclose(mom, REF[pre + f"step{step}/momentum"], rtol=1e-5, atol=1e-7)
+        # after k steps a parameter is p0 + a sum of k updates: rtol 1e-5 of the value, plus an absolute floor of 1e-6 of
+        # the array's scale for the elements where those terms cancel (with RMSprop the updates are O(0.1) against
+        # parameters of O(0.01); measured: 4 of 24 018 elements off by 1.5e-7 after six steps)
+        want_p, want_m = REF[pre + f"step{step}/params"], REF[pre + f"step{step}/momentum"]
+        np.testing.assert_allclose(flat, want_p, rtol=1e-5, atol=1e-6 * float(np.abs(want_p).max()))
+        np.testing.assert_allclose(mom, want_m, rtol=1e-5, atol=1e-6 * float(np.abs(want_m).max()))
         if rms:
             v = np.concatenate([x.cpu().numpy().ravel() for x in inner.preconditioner_state.grad_moment_estimates.leaf_views()])
             np.testing.assert_allclose(v, REF[pre + f"step{step}/v"], rtol=1e-5, atol=1e-12)
@@ -195,10 +206,13 @@ def test_step_schedules_and_clip(cuda):
         got = np.array([fn(int(c)) for c in REF["schedule/counts"]], dtype=np.float32)
         np.testing.assert_allclose(got, REF[f"schedule/{name}"], rtol=3e-7, err_msg=name)
     params = FlatTree.from_tree(trees.ragged_tree(0), device=cuda)
-    g = params.flat * 0.5 + 0.01
+    g = params.zeros_like()  # alignment gaps between the leaves stay zero: they must not enter the norm
+    for pv, gv in zip(params.leaf_views(), g.leaf_views()):
+        gv.copy_(pv * 0.5 + 0.01)
     for i in range(2):
-        mult = ops.grad_clip_mult(g, float(REF[f"clip/{i}/max_norm"]))
-        np.testing.assert_allclose((mult * g).cpu().numpy(), REF[f"clip/{i}/grad"], rtol=1e-6)
+        mult = ops.grad_clip_mult(g.flat, float(REF[f"clip/{i}/max_norm"]))
+        got = np.concatenate([(mult * v).cpu().numpy().ravel() for v in g.leaf_views()])
+        np.testing.assert_allclose(got, REF[f"clip/{i}/grad"], rtol=1e-6)
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
@@ -246,3 +260,74 @@ def test_diagnostics(cuda):
     np.testing.assert_allclose(ops.ksd_imq(x, g, c=2.0, beta=-0.75).cpu().numpy()[0], REF["diag/ksd_c2_b075"], rtol=2e-5)
     ok = Dg.ess_threshold_margin(REF["diag/samples"]) > 1e-4
     np.testing.assert_allclose(ops.ess(x).cpu().numpy()[ok], REF["diag/ess"][ok], rtol=2e-4)
+
+
+# ------------------------------------------------------------------------------------------------ multivalid scorers
+def _same_mv_run(pre, status, patches):
+    want = REF[pre + "patches"]
+    assert status["n_rounds"] == int(REF[pre + "n_rounds"]) and bool(status["converged"]) == bool(REF[pre + "converged"])
+    np.testing.assert_allclose(np.array([float(v) for v in status["losses"]], np.float32), REF[pre + "losses"], rtol=2e-5)
+    assert len(patches) == len(want)
+    for got, w in zip(patches, want):
+        assert (int(got[0]), int(got[1]), int(got[3])) == (int(w[0]), int(w[1]), int(w[3])), (got, w)
+        assert abs(float(got[2]) - w[2]) < 1e-7
+        np.testing.assert_allclose(float(got[4]), w[4], rtol=2e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag,kw", [("add", dict(bucket_types=("<=", ">="), patch_type="additive")),
+                                    ("mul", dict(bucket_types=("=", ">=", "<="), patch_type="multiplicative"))])
+def test_multicalibrator(cuda, tag, kw):
+    from fortuna_b200.conformal import Multicalibrator
+
+    d = case("mv/data/")
+    pre = f"mv/multicalibrator_{tag}/"
+    mc = Multicalibrator(seed=1)
+    tv, status = mc.calibrate(scores=d["scores"], groups=d["groups"], values=d["v0"], test_groups=d["tg"],
+                              test_values=d["tx"], n_rounds=6, n_buckets=8, eta=0.5, **kw)
+    _same_mv_run(pre, status, mc.patches)
+    np.testing.assert_allclose(tv.cpu().numpy(), REF[pre + "test_values"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(mc.calibration_error(d["ts"], d["tg"], tv).cpu().numpy(), REF[pre + "calibration_error"],
+                               rtol=1e-4, atol=1e-7)
+
+
+def test_batchmvp(cuda):
+    from fortuna_b200.conformal import BatchMVPConformalRegressor
+
+    d = case("mv/data/")
+    bm = BatchMVPConformalRegressor(seed=2)
+    status = bm.calibrate(scores=d["scores"], groups=d["groups"], n_rounds=5, n_buckets=10, eta=0.5, coverage=0.9)
+    _same_mv_run("mv/batchmvp/", status, bm.patches)
+    th = bm.apply_patches(d["tg"])
+    np.testing.assert_allclose(th.cpu().numpy(), REF["mv/batchmvp/test_thresholds"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(bm.calibration_error(d["ts"], d["tg"], th).cpu().numpy(), REF["mv/batchmvp/calibration_error"],
+                               rtol=1e-4, atol=1e-7)
+
+
+def test_top_label_binary_and_one_shot_multicalibrators(cuda):
+    from fortuna_b200.conformal import (BinaryClassificationMulticalibrator, OneShotBinaryClassificationMulticalibrator,
+                                        OneShotMulticalibrator, OneShotTopLabelMulticalibrator, TopLabelMulticalibrator)
+
+    d = case("mv/cls/")
+    C = d["probs"].shape[1]
+    tl = TopLabelMulticalibrator(n_classes=C, seed=0)
+    status = tl.calibrate(targets=d["targets"], groups=d["groups"], probs=d["probs"], n_rounds=4, n_buckets=5, eta=1.0)
+    _same_mv_run("mv/top_label/", status, tl.patches)
+    np.testing.assert_allclose(tl.apply_patches(d["groups"], d["probs"]).cpu().numpy(), REF["mv/top_label/applied"],
+                               rtol=1e-5, atol=1e-6)
+    bc = BinaryClassificationMulticalibrator(seed=0)
+    sb = bc.calibrate(targets=d["binary_targets"], groups=d["groups"], probs=d["probs"][:, 0].copy(), n_rounds=4,
+                      n_buckets=6, eta=0.5)
+    _same_mv_run("mv/binary/", sb, bc.patches)
+
+    dd, o = case("mv/data/"), case("mv/one_shot/")
+    os_ = OneShotMulticalibrator()
+    tv = os_.calibrate(scores=dd["scores"], values=o["values"], test_values=o["test_values"], n_buckets=10)
+    np.testing.assert_allclose(os_.patches, o["patches"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(tv.cpu().numpy(), o["applied"], rtol=1e-5, atol=1e-7)
+    ob = OneShotBinaryClassificationMulticalibrator()
+    ob.calibrate(targets=o["binary_targets"], probs=o["values"], n_buckets=10)
+    np.testing.assert_allclose(ob.patches, o["binary_patches"], rtol=1e-5, atol=1e-7)
+    ot = OneShotTopLabelMulticalibrator(n_classes=3)
+    out = ot.calibrate(targets=o["tl_targets"], probs=o["tl_probs"], test_probs=o["tl_probs"], n_buckets=10)
+    np.testing.assert_allclose(ot.patches, o["tl_patches"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(out.cpu().numpy(), o["tl_applied"], rtol=1e-5, atol=1e-7)

@@ -228,3 +228,69 @@ def test_diagnostics():
     ok = margin > 1e-4
     assert ok.mean() > 0.8
     np.testing.assert_allclose(ess[ok], ref[ok], rtol=2e-4)
+
+
+# ------------------------------------------------------------------------------------------------ multivalid scorers
+from oracle import multivalid as M  # noqa: E402
+
+
+def _same_mv_run(pre, status, patches):
+    """Round for round: the chosen (tau, g, v, c) exactly, patches and validation losses to float32 rounding."""
+    want = REF[pre + "patches"]
+    assert status["n_rounds"] == int(REF[pre + "n_rounds"]) and bool(status["converged"]) == bool(REF[pre + "converged"])
+    np.testing.assert_allclose(np.array(status["losses"], np.float32), REF[pre + "losses"], rtol=2e-6)
+    assert len(patches) == len(want)
+    for got, w in zip(patches, want):
+        assert (got[0], got[1], got[3]) == (int(w[0]), int(w[1]), int(w[3])) and np.float32(got[2]) == np.float32(w[2])
+        np.testing.assert_allclose(got[4], w[4], rtol=2e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag,kw", [("add", dict(bucket_types=("<=", ">="), patch_type="additive")),
+                                    ("mul", dict(bucket_types=("=", ">=", "<="), patch_type="multiplicative"))])
+def test_multicalibrator(tag, kw):
+    d = case("mv/data/")
+    pre = f"mv/multicalibrator_{tag}/"
+    o = M.Iterative("multicalibrator", seed=1)
+    st = o.calibrate(d["scores"], d["groups"], values=d["v0"], n_rounds=6, n_buckets=8, eta=0.5, **kw)
+    _same_mv_run(pre, st, o.patches)
+    tv = o.apply_patches(d["tg"], d["tx"])
+    np.testing.assert_allclose(tv, REF[pre + "test_values"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(o.calibration_error(d["ts"], d["tg"], tv), REF[pre + "calibration_error"], rtol=2e-5, atol=1e-8)
+
+
+def test_batchmvp():
+    d = case("mv/data/")
+    o = M.Iterative("batchmvp", seed=2)
+    st = o.calibrate(d["scores"], d["groups"], n_rounds=5, n_buckets=10, eta=0.5, coverage=0.9, bucket_types=(">=", "<="))
+    _same_mv_run("mv/batchmvp/", st, o.patches)
+    th = o.apply_patches(d["tg"])
+    np.testing.assert_allclose(th, REF["mv/batchmvp/test_thresholds"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(o.calibration_error(d["ts"], d["tg"], th), REF["mv/batchmvp/calibration_error"], rtol=2e-5,
+                               atol=1e-8)
+
+
+def test_top_label_and_binary_multicalibrators():
+    d = case("mv/cls/")
+    C = d["probs"].shape[1]
+    o = M.Iterative("top_label", seed=0, n_classes=C)
+    onehot = (d["targets"][:, None] == np.arange(C)[None]).astype(np.float32)
+    st = o.calibrate(onehot, d["groups"], values=d["probs"], n_rounds=4, n_buckets=5, eta=1.0)
+    _same_mv_run("mv/top_label/", st, o.patches)
+    np.testing.assert_allclose(o.apply_patches(d["groups"], d["probs"]), REF["mv/top_label/applied"], rtol=1e-6, atol=1e-7)
+    ob = M.Iterative("multicalibrator", seed=0)
+    sb = ob.calibrate(d["binary_targets"].astype(np.float32), d["groups"], values=d["probs"][:, 0].copy(), n_rounds=4,
+                      n_buckets=6, eta=0.5)
+    _same_mv_run("mv/binary/", sb, ob.patches)
+
+
+def test_one_shot_multicalibrators():
+    d, o = case("mv/data/"), case("mv/one_shot/")
+    p = M.one_shot_patches(d["scores"], o["values"], n_buckets=10)
+    np.testing.assert_allclose(p, o["patches"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(M.one_shot_apply(p, o["test_values"], 10), o["applied"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(M.one_shot_patches(o["binary_targets"].astype(np.float32), o["values"], n_buckets=10),
+                               o["binary_patches"], rtol=1e-6, atol=1e-8)
+    onehot = (o["tl_targets"][:, None] == np.arange(3)[None]).astype(np.float32)
+    wp = M.one_shot_patches(onehot, o["tl_probs"], n_buckets=10, top_label=True)
+    np.testing.assert_allclose(wp, o["tl_patches"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(M.one_shot_apply(wp, o["tl_probs"], 10, top_label=True), o["tl_applied"], rtol=1e-6, atol=1e-8)

@@ -516,6 +516,16 @@ def _make_jnp():
         return _j(np.concatenate([out, np.array([stop], dtype=f)]))
 
     m.linspace = linspace
+
+    def clip(a, a_min=None, a_max=None, **kw):
+        a = _wrap_in(a) if not _is_weak(a) else _j(np.asarray(a))
+        if a_min is not None:
+            a = np.maximum(a, a_min)
+        if a_max is not None:
+            a = np.minimum(a, a_max)
+        return _j(a)
+
+    m.clip = clip
     m.pi, m.inf, m.nan, m.e, m.newaxis = np.pi, np.inf, np.nan, np.e, None
     m.ndarray = JArray
     for t in ("float32", "float64", "int32", "int64", "uint32", "uint8", "int8", "bool_", "complex64", "float16"):

@@ -448,6 +448,31 @@ def gen_multivalid():
     put("mv/one_shot/tl_applied", out)
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# 7. MaxCoverageFixedPrecision binary calibrator (conformal/classification/maxcovfixprec_binary_classfication.py)
+# --------------------------------------------------------------------------------------------------------------------
+def gen_maxcov():
+    logging_off()
+    mod = imp("fortuna.conformal.classification.maxcovfixprec_binary_classfication")
+    r = np.random.default_rng(6)
+    n = 800
+    q = r.random(n).astype(np.float32)
+    y = (r.random(n) < q ** 1.3).astype(np.int32)
+    pt = r.random(200).astype(np.float32)
+    for k, v in dict(probs=q, targets=y, test_probs=pt).items():
+        put("maxcov/" + k, v)
+    for i, (tp, tn, margin) in enumerate(((0.8, 0.75, 0.0), (0.9, 0.9, 0.02))):
+        cal = mod.MaxCoverageFixedPrecisionBinaryClassificationCalibrator()
+        out = cal.calibrate(targets=J._j(y), probs=J._j(q), true_positive_precision_threshold=tp,
+                            true_negative_precision_threshold=tn, test_probs=J._j(pt), n_taus=60, margin=margin)
+        put(f"maxcov/{i}/thresholds", np.array([tp, tn, margin], np.float64))
+        put(f"maxcov/{i}/tau_pos", cal.patches["tau_pos"])
+        put(f"maxcov/{i}/tau_neg", cal.patches["tau_neg"])
+        put(f"maxcov/{i}/applied", out)
+        put(f"maxcov/{i}/tp_precision", cal.true_positive_precision(out, J._j(y[:200]), tp))
+        put(f"maxcov/{i}/tn_precision", cal.true_negative_precision(out, J._j(y[:200]), tn))
+
+
 def logging_off():
     import logging
 
@@ -461,6 +486,7 @@ def main():
     gen_scoring()
     gen_diagnostics()
     gen_multivalid()
+    gen_maxcov()
     path = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **OUT)
     print(f"wrote {path}: {len(OUT)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")

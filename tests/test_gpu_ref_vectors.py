@@ -331,3 +331,16 @@ def test_top_label_binary_and_one_shot_multicalibrators(cuda):
     out = ot.calibrate(targets=o["tl_targets"], probs=o["tl_probs"], test_probs=o["tl_probs"], n_buckets=10)
     np.testing.assert_allclose(ot.patches, o["tl_patches"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(out.cpu().numpy(), o["tl_applied"], rtol=1e-5, atol=1e-7)
+
+
+def test_maxcov_fixed_precision_calibrator(cuda):
+    from fortuna_b200.conformal import MaxCoverageFixedPrecisionBinaryClassificationCalibrator as Cal
+
+    d = case("maxcov/")
+    for i in range(2):
+        tp, tn, margin = (float(v) for v in d[f"{i}/thresholds"])
+        cal = Cal()
+        out = cal.calibrate(targets=d["targets"], probs=d["probs"], true_positive_precision_threshold=tp,
+                            true_negative_precision_threshold=tn, test_probs=d["test_probs"], n_taus=60, margin=margin)
+        assert np.float32(cal.patches["tau_pos"]) == d[f"{i}/tau_pos"] and np.float32(cal.patches["tau_neg"]) == d[f"{i}/tau_neg"]
+        assert np.array_equal(out.cpu().numpy(), d[f"{i}/applied"])

@@ -294,3 +294,17 @@ def test_one_shot_multicalibrators():
     wp = M.one_shot_patches(onehot, o["tl_probs"], n_buckets=10, top_label=True)
     np.testing.assert_allclose(wp, o["tl_patches"], rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(M.one_shot_apply(wp, o["tl_probs"], 10, top_label=True), o["tl_applied"], rtol=1e-6, atol=1e-8)
+
+
+def test_maxcov_fixed_precision_calibrator():
+    from oracle import maxcov as Mc
+
+    d = case("maxcov/")
+    for i in range(2):
+        tp, tn, margin = d[f"{i}/thresholds"]
+        tau_pos, tau_neg, _, _ = Mc.calibrate(d["targets"], d["probs"], tp, tn, n_taus=60, margin=margin)
+        assert np.float32(tau_pos) == d[f"{i}/tau_pos"] and np.float32(tau_neg) == d[f"{i}/tau_neg"]
+        out = Mc.apply_patches(d["test_probs"], tau_pos, tau_neg)
+        assert np.array_equal(out, d[f"{i}/applied"])
+        np.testing.assert_allclose(Mc.true_positive_precision(out, d["targets"][:200], tp), d[f"{i}/tp_precision"], rtol=1e-6)
+        np.testing.assert_allclose(Mc.true_negative_precision(out, d["targets"][:200], tn), d[f"{i}/tn_precision"], rtol=1e-6)

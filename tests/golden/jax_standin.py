@@ -750,6 +750,8 @@ REAL_MODULES = (
     "fortuna.conformal.multivalid.one_shot.classification.binary_multicalibrator",
     "fortuna.conformal.multivalid.one_shot.classification.top_label_multicalibrator",
     "fortuna.conformal.classification.maxcovfixprec_binary_classfication",
+    "fortuna.loss.classification.focal_loss",
+    "fortuna.loss.regression.scaled_mse",
 )
 
 

@@ -473,6 +473,26 @@ def gen_maxcov():
         put(f"maxcov/{i}/tn_precision", cal.true_negative_precision(out, J._j(y[:200]), tn))
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# 8. calibration losses (loss/classification/focal_loss.py, loss/regression/scaled_mse.py)
+# --------------------------------------------------------------------------------------------------------------------
+def gen_losses():
+    fl = imp("fortuna.loss.classification.focal_loss").focal_loss_fn
+    sm = imp("fortuna.loss.regression.scaled_mse").scaled_mse_fn
+    r = np.random.default_rng(8)
+    z = (3 * r.standard_normal((300, 7))).astype(np.float32)
+    t = r.integers(0, 7, 300).astype(np.int32)
+    put("loss/logits", z)
+    put("loss/targets", t)
+    for g in (2.0, 0.5):
+        put(f"loss/focal_gamma{g}", fl(J._j(z), J._j(t), gamma=g))
+    o = r.standard_normal((200, 6)).astype(np.float32)
+    y = r.standard_normal((200, 3)).astype(np.float32)
+    put("loss/outputs", o)
+    put("loss/y", y)
+    put("loss/scaled_mse", sm(J._j(o), J._j(y)))
+
+
 def logging_off():
     import logging
 
@@ -487,6 +507,7 @@ def main():
     gen_diagnostics()
     gen_multivalid()
     gen_maxcov()
+    gen_losses()
     path = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **OUT)
     print(f"wrote {path}: {len(OUT)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")

@@ -344,3 +344,15 @@ def test_maxcov_fixed_precision_calibrator(cuda):
                             true_negative_precision_threshold=tn, test_probs=d["test_probs"], n_taus=60, margin=margin)
         assert np.float32(cal.patches["tau_pos"]) == d[f"{i}/tau_pos"] and np.float32(cal.patches["tau_neg"]) == d[f"{i}/tau_neg"]
         assert np.array_equal(out.cpu().numpy(), d[f"{i}/applied"])
+
+
+def test_calibration_losses(cuda):
+    from fortuna_b200 import ops
+
+    d = case("loss/")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    for g in (2.0, 0.5):
+        loss, _, _ = ops.focal_loss_grad(t(d["logits"]), t(d["targets"]), gamma=g, want_grad=False)
+        np.testing.assert_allclose(float(loss[0]), d[f"focal_gamma{g}"], rtol=1e-5)
+    loss, _, _ = ops.scaled_mse_loss_grad(t(d["outputs"]), t(d["y"]), want_grad=False)
+    np.testing.assert_allclose(float(loss[0]), d["scaled_mse"], rtol=1e-5)

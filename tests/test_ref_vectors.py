@@ -308,3 +308,12 @@ def test_maxcov_fixed_precision_calibrator():
         assert np.array_equal(out, d[f"{i}/applied"])
         np.testing.assert_allclose(Mc.true_positive_precision(out, d["targets"][:200], tp), d[f"{i}/tp_precision"], rtol=1e-6)
         np.testing.assert_allclose(Mc.true_negative_precision(out, d["targets"][:200], tn), d[f"{i}/tn_precision"], rtol=1e-6)
+
+
+def test_calibration_losses():
+    from oracle import calib_model as Cm
+
+    d = case("loss/")
+    for g in (2.0, 0.5):
+        np.testing.assert_allclose(Cm.focal_loss(d["logits"], d["targets"], gamma=g), d[f"focal_gamma{g}"], rtol=2e-6)
+    np.testing.assert_allclose(Cm.scaled_mse(d["outputs"], d["y"]), d["scaled_mse"], rtol=2e-6)

@@ -217,6 +217,14 @@ struct EssArgs {
   float* ess;
 };
 
+// Short-chain kernel: per-lag / per-row constants live in the kernel parameters (constant bank, warp-uniform operands):
+// live[t] = 1 for t < S else 0 (centres real rows only, one FFMA per element), inv_len[k] = 1 / (S - k), wgt[k] = (S - k) / S.
+struct EssShortArgs {
+  EssArgs a;
+  float inv_S_rn;  // RN(1 / S) for the correctly rounded mean (Markstein)
+  float live[64], inv_len[64], wgt[64];
+};
+
 template <int COLS>
 __global__ void __launch_bounds__(256) ess_kernel(const EssArgs a) {
   extern __shared__ __align__(16) float ess_smem[];
@@ -309,47 +317,136 @@ __global__ void __launch_bounds__(256) ess_kernel(const EssArgs a) {
 // in flight together, the lagged products are S^2/2 register FMAs (entries past S are zero, so the unrolled triangle
 // needs no bounds), and the lag walk follows in the same thread: no shared memory, no barrier, no per-slab latency chain
 // (the slab kernel below reached 19 % of the HBM peak at c5: load -> centre -> lags -> walk, one after the other).
-template <int SMAX>
-__global__ void __launch_bounds__(256) ess_short_kernel(const EssArgs a) {
+// With a cut-off (the default filter_threshold = 0) the lags stop as soon as all 32 chains of the warp are masked.
+// Prefetch ring: a thread's S loads for its NEXT parameters are issued as 4-byte cp.async (LDGSTS) into a private column
+// of a DEPTH-stage shared-memory buffer before it computes the current one, so the loads of DEPTH - 1 iterations are in
+// flight under the lag arithmetic (registers alone gave 2 blocks per SM that alternate between waiting for 30 loads and
+// computing: 44 % of the HBM peak).  Every thread reads back only what it copied itself: cp.async.wait_group is all the
+// synchronisation there is.  4-byte copies: rows of a [S, N] matrix are only 4-byte aligned to each other in general.
+template <int SMAX, int DEPTH>
+__global__ void __launch_bounds__(256) ess_short_kernel(const __grid_constant__ EssShortArgs args) {
+  static_assert(SMAX % 2 == 0 && SMAX <= 64, "pairs");
+  constexpr int HP = SMAX / 2;
+  extern __shared__ __align__(16) float ess_ring[];  // [DEPTH][SMAX][256]
+  const EssArgs& a = args.a;
   const int S = a.S;
   const float fS = (float)S;
-  const float inv_S = 1.0f / fS;
-  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += (int64_t)gridDim.x * blockDim.x) {
-    float x[SMAX];
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // rows S .. SMAX-1 of this thread's ring columns are never copied into: zero them once, the loads below need no guard
+  for (int d = 0; d < DEPTH; ++d)
+    for (int t = S; t < SMAX; ++t) ess_ring[((size_t)d * SMAX + t) * 256 + threadIdx.x] = 0.0f;
+  auto prefetch = [&](int64_t n, int stage) {
+    if (n < a.N) {
+      float* dst = ess_ring + ((size_t)stage * SMAX) * 256 + threadIdx.x;
+      const float* src = a.x + n;
+#pragma unroll 6
+      for (int t = 0; t < S; ++t, src += a.stride, dst += 256) cp_async4_zfill(dst, src, true);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per iteration, empty past the end
+  };
 #pragma unroll
-    for (int t = 0; t < SMAX; ++t) x[t] = t < S ? __ldg(a.x + (int64_t)t * a.stride + n) : 0.0f;
+  for (int d = 0; d < DEPTH - 1; ++d) prefetch(n0 + d * step, d);
+  int stage = 0;
+  for (int64_t n = n0; n < a.N; n += step) {
+    const unsigned lanes = __activemask();
+    prefetch(n + (DEPTH - 1) * step, (stage + DEPTH - 1) % DEPTH);
+    asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+    const float* src = ess_ring + ((size_t)stage * SMAX) * 256 + threadIdx.x;
+    stage = (stage + 1) % DEPTH;
+    float x[SMAX + 2];
+#pragma unroll
+    for (int t = 0; t < SMAX; ++t) x[t] = src[t * 256];
+    x[SMAX] = x[SMAX + 1] = 0.0f;
     float sum = 0.0f;
 #pragma unroll
     for (int t = 0; t < SMAX; ++t) sum += x[t];
-    const float mean = sum / fS;  // sgmcmc_diagnostic.py:107-108
+    // mean = sum / S (sgmcmc_diagnostic.py:107-108), correctly rounded without the division's slow path: q = sum * r,
+    // q' = q + (sum - S q) r with r = RN(1 / S) (Markstein)
+    const float q = sum * args.inv_S_rn;
+    const float mean = fmaf(fmaf(-fS, q, sum), args.inv_S_rn, q);
 #pragma unroll
-    for (int t = 0; t < SMAX; ++t) x[t] = t < S ? x[t] - mean : 0.0f;
+    for (int t = 0; t < SMAX; ++t) x[t] = fmaf(-mean, args.live[t], x[t]);  // real rows centred, padding stays zero
+    // The lagged products as packed float32x2 FMAs (FFMA2: one issue slot for two products) on the chain held as aligned
+    // pairs xe[i] = (x[2i], x[2i+1]); entries past the end are zero.
+    //   even lag 2m:  E_m = sum_i xe[i] * xe[i+m]                 ->  prod = E_m.lo + E_m.hi
+    //   odd lags:     O_m = sum_i xe[i] * swap(xe[i+m])           (the operand swizzle of FFMA2, no register moves)
+    //                 O_m.lo = sum_i x[2i] x[2(i+m)+1]   = the even-t half of lag 2m+1
+    //                 O_m.hi = sum_i x[2i+1] x[2(i+m)]   = the odd-t  half of lag 2m-1
+    //                 ->  prod(2m+1) = O_m.lo + O_{m+1}.hi
+    // (a shifted copy of the chain for the odd lags cost two MOVs per FFMA2: the compiler rebuilt the pairs every time.)
+    // Even and odd t accumulate separately and meet at the end; the reference's FFT route has no defined order either.
+    float2 xe[HP];
+#pragma unroll
+    for (int i = 0; i < HP; ++i) xe[i] = make_float2(x[2 * i], x[2 * i + 1]);
+    auto lag_pairs = [&](int m, bool swapped) {  // two accumulator pairs per chain: independent FFMA2s in flight
+      float2 pa = make_float2(0.0f, 0.0f), pb = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int i = 0; i + m < HP; i += 2) {
+        const float2 b0 = xe[i + m];
+        pa = __ffma2_rn(xe[i], swapped ? make_float2(b0.y, b0.x) : b0, pa);
+        if (i + 1 + m < HP) {
+          const float2 b1 = xe[i + 1 + m];
+          pb = __ffma2_rn(xe[i + 1], swapped ? make_float2(b1.y, b1.x) : b1, pb);
+        }
+      }
+      return make_float2(pa.x + pb.x, pa.y + pb.y);
+    };
     float inv_cov0 = 0.0f, acc_w = 0.0f;
     bool open = true;
+    float2 odd_prev = lag_pairs(0, true);  // O_0
+    // Two lags per round (2m and 2m+1); the warp votes on the cut-off once per round.
 #pragma unroll
-    for (int k = 0; k < SMAX; ++k) {
-      float prod = 0.0f;
+    for (int k0 = 0; k0 < SMAX; k0 += 2) {
+      if (k0 >= S) break;
+      const int m = k0 / 2;
+      const float2 ev = lag_pairs(m, false);
+      const float2 odd_next = m + 1 < HP ? lag_pairs(m + 1, true) : make_float2(0.0f, 0.0f);
+      float prod[2];
+      prod[0] = ev.x + ev.y;
+      prod[1] = odd_prev.x + odd_next.y;
+      odd_prev = odd_next;
 #pragma unroll
-      for (int t = 0; t + k < SMAX; ++t) prod = fmaf(x[t], x[t + k], prod);  // sum_t x[t] x[t+k]
-      if (k < S) {
-        const float cov = prod * (1.0f / (fS - (float)k));  // unbiased normalisation (:120-128), reciprocal like the slab kernel
-        if (k == 0) inv_cov0 = 1.0f / cov;
-        const float rho = cov * inv_cov0;
-        if (a.use_threshold && rho < a.threshold) open = false;  // cumulative mask: this lag and every later one drop out
-        const float w = ((fS - (float)k) * inv_S) * rho;
-        if (open) acc_w += w;
-        else if (rho != rho) acc_w += rho;  // NaN auto-correlations propagate like `weighted * mask` does
+      for (int q = 0; q < 2; ++q) {
+        const int k = k0 + q;
+        if (k < S) {
+          const float cov = prod[q] * args.inv_len[k];  // unbiased normalisation (:120-128)
+          if (k == 0) inv_cov0 = 1.0f / cov;
+          const float rho = cov * inv_cov0;
+          if (a.use_threshold && rho < a.threshold) open = false;  // cumulative mask: this lag and every later one drop out
+          const float w = args.wgt[k] * rho;
+          if (open) acc_w += w;
+          else if (rho != rho) acc_w += rho;  // NaN auto-correlations propagate like `weighted * mask` does
+        }
       }
+      // Once every chain of the warp is past its cut-off the later lags cannot change any result: a closed chain only
+      // takes NaN terms, and |sum_t x[t] x[t+k]| <= sum_t x[t]^2 (Cauchy-Schwarz), so a lag can only be NaN / inf if lag
+      // 0 already was - and then acc_w has been NaN since k = 0.
+      if (a.use_threshold && !__any_sync(lanes, open)) break;
     }
     a.ess[n] = fS / (-1.0f + 2.0f * acc_w);
   }
 }
 
-template <int SMAX>
+template <int SMAX, int DEPTH>
 static int launch_ess_short(const EssArgs& a, cudaStream_t st) {
+  constexpr size_t smem = (size_t)DEPTH * SMAX * 256 * sizeof(float);
+  constexpr int per_sm = (int)((220 * 1024) / smem) < 2 ? 1 : 2;  // resident blocks per SM the ring leaves room for
+  auto kern = ess_short_kernel<SMAX, DEPTH>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  EssShortArgs args;
+  args.a = a;
+  const float fS = (float)a.S;
+  args.inv_S_rn = 1.0f / fS;
+  for (int t = 0; t < 64; ++t) {
+    args.live[t] = t < a.S ? 1.0f : 0.0f;
+    args.inv_len[t] = t < a.S ? 1.0f / (fS - (float)t) : 0.0f;
+    args.wgt[t] = t < a.S ? (fS - (float)t) * (1.0f / fS) : 0.0f;
+  }
   int64_t blocks = (a.N + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  ess_short_kernel<SMAX><<<(unsigned)blocks, 256, 0, st>>>(a);
+  if (blocks > 148 * per_sm) blocks = 148 * per_sm;  // persistent: every block walks its parameters through the ring
+  kern<<<(unsigned)blocks, 256, smem, st>>>(args);
   FB200_LAUNCH_CHECK();
   return 0;
 }
@@ -456,8 +553,8 @@ extern "C" int fb200_ess(const float* samples, int S, int64_t N, int64_t row_str
   a.threshold = threshold;
   a.ess = ess;
   cudaStream_t st = (cudaStream_t)stream;
-  if (S <= 32) return launch_ess_short<32>(a, st);  // the chain of a parameter fits one thread's registers
-  if (S <= 64) return launch_ess_short<64>(a, st);
+  if (S <= 32) return launch_ess_short<32, 3>(a, st);  // the chain of a parameter fits one thread's registers
+  if (S <= 64) return launch_ess_short<64, 2>(a, st);
   const size_t per_col = ((size_t)(2 * S + ESS_R + 32)) * sizeof(float);
   const size_t budget = 200 * 1024 - (size_t)S * sizeof(float);
   if (per_col * 128 <= 110 * 1024 && N >= 128) return launch_ess<128>(a, st);  // short chains: wide slabs

@@ -51,6 +51,16 @@ def main():
             "ess_fma_tflops": 2 * (S * (S + 1) / 2) * N / ess_ms / 1e9,
             "ess_hbm_gbs": (4 * S * N + 4 * N) / ess_ms / 1e6,
         }
+        if S * N >= 1_000_000_000:
+            # the same size as a correlated chain (AR(1), phi = 0.9): the cut-off comes tens of lags later than for white
+            # noise, so the warp-level early exit of the short-chain kernel saves little there
+            x[0].normal_(generator=g)
+            for t in range(1, S):
+                torch.randn(N, device=dev, generator=g, out=gr[0])
+                x[t] = 0.9 * x[t - 1] + 0.436 * gr[0]
+            row["ess_ms_ar1_phi0.9"] = timed(lambda: ops.ess(x, 0.0))
+            row["ess_hbm_gbs_ar1_phi0.9"] = (4 * S * N + 4 * N) / row["ess_ms_ar1_phi0.9"] / 1e6
+            row["ess_ms_no_cutoff"] = timed(lambda: ops.ess(x, None))
         if a.cpu and S * N <= 5_000_000:
             from oracle import diagnostic as D
 

@@ -147,6 +147,136 @@ __global__ void __launch_bounds__(KSD_THREADS) ksd_pair_sums_kernel(const KsdArg
     }
 }
 
+// Chains of <= 32 samples (every BASELINE config's default: 10 - 30 stored samples) are ONE diagonal tile: the square
+// kernel above computes all 32 x 32 pairs of it although only i <= j are needed (2.2 x the work at S = 30) with 2 x 2
+// pairs per thread (8 shared loads per 20 FMA-pipe instructions).  Here the tile is cut into 8 x 8 blocks of 4 x 4 pairs
+// and only the 36 blocks bi <= bj exist: a thread owns one block (four 128-bit shared loads per 80 FMA-pipe instructions
+// per column), 36 threads cover one column, and the CTA's 7 groups of 36 threads take every seventh column of a stage.
+constexpr int KSD_TRI_GROUPS = 7;    // 7 x 36 = 252 computing threads in a 256-thread CTA: 8 warps, so that two CTAs per SM put
+constexpr int KSD_TRI_THREADS = 256; // 4 warps on every scheduler and each thread may hold 128 registers (9 warps: 96)
+constexpr int KSD_TRI_KC = 16 * KSD_TRI_GROUPS;       // columns per stage (16 per thread between two CTA barriers)
+constexpr int KSD_TRI_ROW = 36;                       // floats per staged column: 32 samples + 4 (16-byte rows, bank shift)
+
+__global__ void __launch_bounds__(KSD_TRI_THREADS, 2) ksd_tri32_kernel(const KsdArgs a) {
+  constexpr int ARR = KSD_TRI_KC * KSD_TRI_ROW;
+  extern __shared__ __align__(16) float ksd_smem[];  // [2 buffers][x | g][KSD_TRI_KC][KSD_TRI_ROW]
+  const int split = blockIdx.y;
+  const int64_t n0 = (int64_t)split * a.cols_per_split;
+  const int64_t n1 = min(a.N, n0 + a.cols_per_split);
+  const int tid = threadIdx.x;
+  const bool computes = tid < 36 * KSD_TRI_GROUPS;  // the last 4 threads only help with the copies
+  const int grp = computes ? tid / 36 : 0;
+  int b = tid % 36, bi = 0;  // block index -> (bi, bj), bi <= bj
+  while (b >= 8 - bi) {
+    b -= 8 - bi;
+    ++bi;
+  }
+  const int bj = bi + b;
+  float dd[4][4], gg[4][4], gid[4][4], gjd[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dd[i][j] = gg[i][j] = gid[i][j] = gjd[i][j] = 0.0f;
+
+  // staging: warp w copies samples w, w + 8, w + 16, w + 24; a lane takes columns lane, lane + 32, ... of the stage (one
+  // 128-byte line per warp instruction, no index division)
+  const int lane = tid & 31, warp = tid >> 5;
+  auto stage = [&](int buf, int64_t nb) {
+    float* base = ksd_smem + (size_t)buf * 2 * ARR;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int s = warp + 8 * q;
+      const bool oks = s < a.S;
+      const float* rx = a.x + (int64_t)(oks ? s : 0) * a.stride;
+      const float* rg = a.g + (int64_t)(oks ? s : 0) * a.stride;
+#pragma unroll
+      for (int c = lane; c < KSD_TRI_KC; c += 32) {
+        const int64_t col = nb + c;
+        const bool ok = oks && col < n1;
+        float* d = base + (size_t)c * KSD_TRI_ROW + s;
+        cp_async4_zfill(d, rx + (ok ? col : 0), ok);
+        cp_async4_zfill(d + ARR, rg + (ok ? col : 0), ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  if (n0 < n1) stage(0, n0);
+  for (int64_t nb = n0; nb < n1; nb += KSD_TRI_KC, buf ^= 1) {
+    if (nb + KSD_TRI_KC < n1) {
+      stage(buf ^ 1, nb + KSD_TRI_KC);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* sx = ksd_smem + (size_t)buf * 2 * ARR;
+    const float* sg = sx + ARR;
+    // operands of the next column are loaded before the current one is consumed: with 4 - 5 warps per scheduler the
+    // 128-bit shared loads at the top of each column were the largest stall (ncu: 16 % of all samples)
+    const float* px = sx + grp * KSD_TRI_ROW;
+    const float* pg = sg + grp * KSD_TRI_ROW;
+    float4 a4 = *reinterpret_cast<const float4*>(px + 4 * bi), b4 = *reinterpret_cast<const float4*>(pg + 4 * bi);
+    float4 c4 = *reinterpret_cast<const float4*>(px + 4 * bj), d4 = *reinterpret_cast<const float4*>(pg + 4 * bj);
+#pragma unroll 1
+    for (int c = computes ? grp : KSD_TRI_KC; c < KSD_TRI_KC; c += KSD_TRI_GROUPS) {
+      const float xi[4] = {a4.x, a4.y, a4.z, a4.w}, gi[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float xj[4] = {c4.x, c4.y, c4.z, c4.w}, gj[4] = {d4.x, d4.y, d4.z, d4.w};
+      if (c + KSD_TRI_GROUPS < KSD_TRI_KC) {
+        px += KSD_TRI_GROUPS * KSD_TRI_ROW;
+        pg += KSD_TRI_GROUPS * KSD_TRI_ROW;
+        a4 = *reinterpret_cast<const float4*>(px + 4 * bi);
+        b4 = *reinterpret_cast<const float4*>(pg + 4 * bi);
+        c4 = *reinterpret_cast<const float4*>(px + 4 * bj);
+        d4 = *reinterpret_cast<const float4*>(pg + 4 * bj);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float d = xi[i] - xj[j];
+          dd[i][j] = fmaf(d, d, dd[i][j]);
+          gg[i][j] = fmaf(gi[i], gj[j], gg[i][j]);
+          gid[i][j] = fmaf(gi[i], d, gid[i][j]);
+          gjd[i][j] = fmaf(gj[j], d, gjd[i][j]);
+        }
+    }
+    __syncthreads();  // everyone is done with `buf` before the next iteration's copies overwrite it
+  }
+  // the groups hold partial sums over disjoint columns of the same pairs: add them in group order through shared
+  // memory (deterministic)
+  __syncthreads();
+  float4* red = reinterpret_cast<float4*>(ksd_smem);  // [groups][36 blocks][16 pairs]
+  if (computes) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        red[((size_t)grp * 36 + (tid % 36)) * 16 + i * 4 + j] = make_float4(dd[i][j], gg[i][j], gid[i][j], gjd[i][j]);
+  }
+  __syncthreads();
+  float4* out = reinterpret_cast<float4*>(a.partial) + (int64_t)split * a.S * a.S;
+  for (int e = tid; e < 36 * 16; e += KSD_TRI_THREADS) {
+    const int blk = e / 16, ij = e % 16;
+    float4 acc = red[(size_t)blk * 16 + ij];
+    for (int g2 = 1; g2 < KSD_TRI_GROUPS; ++g2) {
+      const float4 v = red[((size_t)g2 * 36 + blk) * 16 + ij];
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    int bb = blk, ri = 0;
+    while (bb >= 8 - ri) {
+      bb -= 8 - ri;
+      ++ri;
+    }
+    const int si = 4 * ri + ij / 4, sj = 4 * (ri + bb) + ij % 4;
+    if (si < a.S && sj < a.S) out[(int64_t)si * a.S + sj] = acc;
+  }
+}
+
 // k0 of one pair from its four sums, the reference's expression term by term (sgmcmc_diagnostic.py:52-61).
 __device__ __forceinline__ double ksd_k0(double dd, double gg, double gid, double gjd, double c2, double beta,
                                          double dim) {
@@ -431,7 +561,7 @@ __global__ void __launch_bounds__(256) ess_short_kernel(const __grid_constant__ 
 template <int SMAX, int DEPTH>
 static int launch_ess_short(const EssArgs& a, cudaStream_t st) {
   constexpr size_t smem = (size_t)DEPTH * SMAX * 256 * sizeof(float);
-  constexpr int per_sm = (int)((220 * 1024) / smem) < 2 ? 1 : 2;  // resident blocks per SM the ring leaves room for
+  constexpr int per_sm = (int)((220 * 1024) / smem) > 3 ? 3 : (int)((220 * 1024) / smem);  // resident blocks per SM the ring leaves room for
   auto kern = ess_short_kernel<SMAX, DEPTH>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -530,10 +660,22 @@ extern "C" int fb200_ksd_imq(const float* samples, const float* grads, int S, in
     kern<<<grid, KSD_THREADS, smem, st>>>(a);
     return 0;
   };
-  const int lrc = a.tile == 32 ? launch(ksd_pair_sums_kernel<32>, 32) : launch(ksd_pair_sums_kernel<64>, 64);
-  if (lrc != 0) return lrc;
+  int mirror_granule = a.tile;  // pairs (i, j) with i / granule > j / granule are read at the mirrored entry
+  if (S <= 32) {
+    // one diagonal tile: the triangle kernel (4 x 4 blocks bi <= bj only)
+    // two stages of [x | g][112][36] floats = 64 512 B, re-used by the final reduction over the 7 groups (also 64 512 B)
+    static_assert(2 * 2 * KSD_TRI_KC * KSD_TRI_ROW * sizeof(float) >= KSD_TRI_GROUPS * 36 * 16 * sizeof(float4), "red fits");
+    const size_t smem = (size_t)2 * 2 * KSD_TRI_KC * KSD_TRI_ROW * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(ksd_tri32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    ksd_tri32_kernel<<<dim3(1, (unsigned)a.n_splits), KSD_TRI_THREADS, smem, st>>>(a);
+    mirror_granule = 4;
+  } else {
+    const int lrc = launch(ksd_pair_sums_kernel<64>, 64);
+    if (lrc != 0) return lrc;
+  }
   FB200_LAUNCH_CHECK();
-  ksd_row_kernel<<<(unsigned)S, 256, 0, st>>>(a.partial, S, N, a.n_splits, a.tile, c, beta, row_sums);
+  ksd_row_kernel<<<(unsigned)S, 256, 0, st>>>(a.partial, S, N, a.n_splits, mirror_granule, c, beta, row_sums);
   FB200_LAUNCH_CHECK();
   ksd_total_kernel<<<1, 32, 0, st>>>(row_sums, S, out);
   FB200_LAUNCH_CHECK();
@@ -553,7 +695,7 @@ extern "C" int fb200_ess(const float* samples, int S, int64_t N, int64_t row_str
   a.threshold = threshold;
   a.ess = ess;
   cudaStream_t st = (cudaStream_t)stream;
-  if (S <= 32) return launch_ess_short<32, 3>(a, st);  // the chain of a parameter fits one thread's registers
+  if (S <= 32) return launch_ess_short<32, 2>(a, st);  // the chain of a parameter fits one thread's registers
   if (S <= 64) return launch_ess_short<64, 2>(a, st);
   const size_t per_col = ((size_t)(2 * S + ESS_R + 32)) * sizeof(float);
   const size_t budget = 200 * 1024 - (size_t)S * sizeof(float);

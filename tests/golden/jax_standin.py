@@ -451,7 +451,7 @@ def _make_jnp():
         "conj ceil floor unique nan_to_num split swapaxes expand_dims squeeze prod all any cumprod matmul einsum "
         "isnan var std tile repeat reshape ravel broadcast_to searchsorted outer diff sign power logical_and logical_or "
         "logical_not allclose array_equal moveaxis take median quantile percentile count_nonzero eye diag tril triu "
-        "log1p expm1 tanh atleast_1d atleast_2d hstack vstack flip isfinite argwhere nonzero round floor_divide mod "
+        "log1p expm1 tanh atleast_1d atleast_2d hstack vstack dstack vsplit hsplit flip isfinite argwhere nonzero round floor_divide mod "
         "equal not_equal less greater less_equal greater_equal add subtract multiply divide negative"
     ).split():
         setattr(m, name, _np_fn(getattr(np, name)))

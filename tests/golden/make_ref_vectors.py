@@ -43,6 +43,58 @@ OUT = {}
 A = np.asarray
 
 
+# Loader doubles (fortuna/data/loader/base.py and utils.py:169-174 restated: iteration over batches, sizes, the
+# "concatenate" test grid of conformal_set, ConcatenatedLoader's chained iteration).  They are put into the stub module
+# BEFORE the reference's predictive modules are imported, so those modules bind these names.
+class InputsLoaderDouble:
+    def __init__(self, batches):
+        self.batches = list(batches)
+
+    def __iter__(self):
+        return iter(self.batches)
+
+    @property
+    def size(self):
+        return sum(int(b.shape[0]) for b in self.batches)
+
+
+class DataLoaderDouble:
+    def __init__(self, batches, num_unique_labels=None):
+        self.batches, self.num_unique_labels = batches, num_unique_labels
+
+    def __iter__(self):
+        return iter(self.batches() if callable(self.batches) else self.batches)
+
+    @property
+    def size(self):
+        return sum(int(b[0].shape[0]) for b in self)
+
+    @classmethod
+    def from_inputs_loaders(cls, inputs_loaders, targets, how="interpose"):
+        assert how == "concatenate"
+
+        def inner():
+            for loader, target in zip(inputs_loaders, targets):
+                for inputs in loader:
+                    yield inputs, J._j(target * np.ones(inputs.shape[0], dtype="int32"))
+
+        return cls(inner)
+
+
+class ConcatenatedLoaderDouble:
+    def __init__(self, loaders):
+        self._loaders = loaders
+
+    def __iter__(self):
+        for loader in self._loaders:
+            yield from loader
+
+
+_loader_mod = imp("fortuna.data.loader")
+_loader_mod.DataLoader, _loader_mod.InputsLoader = DataLoaderDouble, InputsLoaderDouble
+_loader_mod.ConcatenatedLoader = ConcatenatedLoaderDouble
+
+
 def put(name, value):
     v = A(value)
     assert v.dtype != object, name
@@ -493,6 +545,33 @@ def gen_losses():
     put("loss/scaled_mse", sm(J._j(o), J._j(y)))
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# 9. conformal Bayes sets (prob_model/predictive/classification.py:485-626)
+# --------------------------------------------------------------------------------------------------------------------
+def gen_conformal_bayes():
+    n, D, C, n_train, n_test, S, seed = 9, 12, 5, 60, 25, 8, 21
+    r = np.random.default_rng(seed)
+    W = (2 * r.standard_normal((n, D, C)) / np.sqrt(D)).astype(np.float32)
+    b = (0.5 * r.standard_normal((n, C))).astype(np.float32)
+    xtr = r.standard_normal((n_train, D)).astype(np.float32)
+    ytr = r.integers(0, C, n_train).astype(np.int32)
+    xte = r.standard_normal((n_test, D)).astype(np.float32)
+    key = OP.PRNGKey(300 + seed)
+    pred = make_predictive("cls", W, b, None)
+    train = DataLoaderDouble([(J._j(xtr[:32]), J._j(ytr[:32])), (J._j(xtr[32:]), J._j(ytr[32:]))], num_unique_labels=C)
+    test = InputsLoaderDouble([J._j(xte[:16]), J._j(xte[16:])])
+    for k, v in dict(W=W, b=b, x_train=xtr, y_train=ytr, x_test=xte, key=key, S=np.int32(S)).items():
+        put("cb/" + k, v)
+    for e in (0.05, 0.3):
+        sets, ess = pred.conformal_set(train, test, n_posterior_samples=S, error=e, rng=J._j(key), distribute=False,
+                                       return_ess=True)
+        mask = np.zeros((n_test, C), np.uint8)
+        for i, s_ in enumerate(sets):
+            mask[i, s_] = 1
+        put(f"cb/region_{e}", mask)
+    put("cb/ess", np.asarray(ess).reshape(n_test, C))
+
+
 def logging_off():
     import logging
 
@@ -508,6 +587,7 @@ def main():
     gen_multivalid()
     gen_maxcov()
     gen_losses()
+    gen_conformal_bayes()
     path = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **OUT)
     print(f"wrote {path}: {len(OUT)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")

@@ -356,3 +356,20 @@ def test_calibration_losses(cuda):
         np.testing.assert_allclose(float(loss[0]), d[f"focal_gamma{g}"], rtol=1e-5)
     loss, _, _ = ops.scaled_mse_loss_grad(t(d["outputs"]), t(d["y"]), want_grad=False)
     np.testing.assert_allclose(float(loss[0]), d["scaled_mse"], rtol=1e-5)
+
+
+def test_conformal_bayes_sets(cuda):
+    from fortuna_b200.data import DataLoader, InputsLoader
+
+    c = case("cb/")
+    pm = make_classifier(cuda, dict(W=c["W"], b=c["b"], log_temp=np.float32(np.nan)))
+    train = DataLoader.from_array_data((c["x_train"], c["y_train"]), batch_size=32)
+    test = InputsLoader.from_array_inputs(c["x_test"], batch_size=16)
+    key = dev_key(c["key"], cuda)
+    for e in (0.05, 0.3):
+        sets, ess = pm.predictive.conformal_set(train, test, n_posterior_samples=int(c["S"]), error=e, rng=key, return_ess=True)
+        mask = np.zeros(c[f"region_{e}"].shape, bool)
+        for i, s in enumerate(sets):
+            mask[i, s] = True
+        assert (mask != c[f"region_{e}"].astype(bool)).sum() <= 1
+    np.testing.assert_allclose(ess.cpu().numpy().reshape(c["ess"].shape), c["ess"], rtol=1e-4)

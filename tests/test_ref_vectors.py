@@ -317,3 +317,18 @@ def test_calibration_losses():
     for g in (2.0, 0.5):
         np.testing.assert_allclose(Cm.focal_loss(d["logits"], d["targets"], gamma=g), d[f"focal_gamma{g}"], rtol=2e-6)
     np.testing.assert_allclose(Cm.scaled_mse(d["outputs"], d["y"]), d["scaled_mse"], rtol=2e-6)
+
+
+def test_conformal_bayes_sets():
+    """predictive/classification.py:485-626 through the reference's own code (the test grid, the shared draws, the
+    importance weights, the rank count).  The rank is a count of float32 comparisons between dot products over the S
+    draws: entries the reference decides by less than 1e-6 relative could flip with the summation order."""
+    c = case("cb/")
+    n = c["W"].shape[0]
+    idx = drawn(c["key"], c["S"], n)
+    ell = P.cls_ensemble_log_prob(P.last_layer_logits(c["x_train"], c["W"][idx], c["b"][idx]), c["y_train"])
+    lsm = P.log_softmax_rows(P.last_layer_logits(c["x_test"], c["W"][idx], c["b"][idx]))
+    for e in (0.05, 0.3):
+        region = Sc.conformal_bayes_region(ell, lsm, e)
+        assert (region != c[f"region_{e}"].astype(bool)).sum() <= 1
+    np.testing.assert_allclose(Sc.conformal_bayes_ess(lsm), c["ess"], rtol=1e-5)

@@ -551,10 +551,14 @@ def gen_losses():
 def gen_conformal_bayes():
     n, D, C, n_train, n_test, S, seed = 9, 12, 5, 60, 25, 8, 21
     r = np.random.default_rng(seed)
-    W = (2 * r.standard_normal((n, D, C)) / np.sqrt(D)).astype(np.float32)
-    b = (0.5 * r.standard_normal((n, C))).astype(np.float32)
+    # stored samples scattered around one confident model, training labels from that model: the sets are selective
+    W0 = (5 * r.standard_normal((D, C)) / np.sqrt(D)).astype(np.float32)
+    W = (W0[None] + 0.6 * r.standard_normal((n, D, C)) / np.sqrt(D)).astype(np.float32)
+    b = (0.3 * r.standard_normal((n, C))).astype(np.float32)
     xtr = r.standard_normal((n_train, D)).astype(np.float32)
-    ytr = r.integers(0, C, n_train).astype(np.int32)
+    ytr = (xtr @ W0).argmax(1).astype(np.int32)
+    flip = r.random(n_train) < 0.15
+    ytr[flip] = r.integers(0, C, int(flip.sum()))
     xte = r.standard_normal((n_test, D)).astype(np.float32)
     key = OP.PRNGKey(300 + seed)
     pred = make_predictive("cls", W, b, None)
@@ -562,7 +566,7 @@ def gen_conformal_bayes():
     test = InputsLoaderDouble([J._j(xte[:16]), J._j(xte[16:])])
     for k, v in dict(W=W, b=b, x_train=xtr, y_train=ytr, x_test=xte, key=key, S=np.int32(S)).items():
         put("cb/" + k, v)
-    for e in (0.05, 0.3):
+    for e in (0.1, 0.4):
         sets, ess = pred.conformal_set(train, test, n_posterior_samples=S, error=e, rng=J._j(key), distribute=False,
                                        return_ess=True)
         mask = np.zeros((n_test, C), np.uint8)

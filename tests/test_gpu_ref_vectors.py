@@ -366,7 +366,7 @@ def test_conformal_bayes_sets(cuda):
     train = DataLoader.from_array_data((c["x_train"], c["y_train"]), batch_size=32)
     test = InputsLoader.from_array_inputs(c["x_test"], batch_size=16)
     key = dev_key(c["key"], cuda)
-    for e in (0.05, 0.3):
+    for e in (0.1, 0.4):
         sets, ess = pm.predictive.conformal_set(train, test, n_posterior_samples=int(c["S"]), error=e, rng=key, return_ess=True)
         mask = np.zeros(c[f"region_{e}"].shape, bool)
         for i, s in enumerate(sets):

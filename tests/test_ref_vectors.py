@@ -328,7 +328,7 @@ def test_conformal_bayes_sets():
     idx = drawn(c["key"], c["S"], n)
     ell = P.cls_ensemble_log_prob(P.last_layer_logits(c["x_train"], c["W"][idx], c["b"][idx]), c["y_train"])
     lsm = P.log_softmax_rows(P.last_layer_logits(c["x_test"], c["W"][idx], c["b"][idx]))
-    for e in (0.05, 0.3):
+    for e in (0.1, 0.4):
         region = Sc.conformal_bayes_region(ell, lsm, e)
         assert (region != c[f"region_{e}"].astype(bool)).sum() <= 1
     np.testing.assert_allclose(Sc.conformal_bayes_ess(lsm), c["ess"], rtol=1e-5)

@@ -576,6 +576,41 @@ def gen_conformal_bayes():
     put("cb/ess", np.asarray(ess).reshape(n_test, C))
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# 10. conformal regression (conformal/regression/quantile.py, onedim_uncertainty.py, base.py)
+# --------------------------------------------------------------------------------------------------------------------
+def gen_conformal_regression():
+    qm = imp("fortuna.conformal.regression.quantile")
+    om = imp("fortuna.conformal.regression.onedim_uncertainty")
+    r = np.random.default_rng(13)
+    nv, nt = 137, 21
+    vy = r.standard_normal((nv, 1)).astype(np.float32)
+    vlo = (vy[:, 0] - 1.0 + 0.7 * r.standard_normal(nv)).astype(np.float32)
+    vhi = (vlo + 2.0 + 0.3 * r.random(nv)).astype(np.float32)
+    tlo = r.standard_normal(nt).astype(np.float32)
+    thi = (tlo + 2.0).astype(np.float32)
+    for k, v in dict(val_targets=vy, val_lower=vlo, val_upper=vhi, test_lower=tlo, test_upper=thi).items():
+        put("creg/" + k, v)
+    c = qm.QuantileConformalRegressor()
+    put("creg/q_scores", c.score(J._j(vlo), J._j(vhi), J._j(vy)))
+    for e in (0.05, 0.2):
+        put(f"creg/q_quantile_{e}", c.quantile(J._j(vlo), J._j(vhi), J._j(vy), e))
+        ci = c.conformal_interval(J._j(vlo), J._j(vhi), J._j(tlo), J._j(thi), J._j(vy), e)
+        put(f"creg/q_interval_{e}", ci)
+        put(f"creg/q_is_in_{e}", c.is_in(J._j(np.zeros(nt, np.float32)), ci))
+    vp = r.standard_normal((nv, 1)).astype(np.float32)
+    vu = (0.2 + r.random((nv, 1))).astype(np.float32)
+    tp = r.standard_normal((nt, 1)).astype(np.float32)
+    tu = (0.2 + r.random((nt, 1))).astype(np.float32)
+    for k, v in dict(val_preds=vp, val_unc=vu, test_preds=tp, test_unc=tu).items():
+        put("creg/" + k, v)
+    o = om.OneDimensionalUncertaintyConformalRegressor()
+    put("creg/o_scores", o.score(J._j(vp), J._j(vu), J._j(vy)))
+    for e in (0.05, 0.2):
+        put(f"creg/o_quantile_{e}", o.quantile(J._j(vp), J._j(vu), J._j(vy), e))
+        put(f"creg/o_interval_{e}", o.conformal_interval(J._j(vp), J._j(vu), J._j(tp), J._j(tu), J._j(vy), e))
+
+
 def logging_off():
     import logging
 
@@ -592,6 +627,7 @@ def main():
     gen_maxcov()
     gen_losses()
     gen_conformal_bayes()
+    gen_conformal_regression()
     path = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **OUT)
     print(f"wrote {path}: {len(OUT)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")

@@ -373,3 +373,22 @@ def test_conformal_bayes_sets(cuda):
             mask[i, s] = True
         assert (mask != c[f"region_{e}"].astype(bool)).sum() <= 1
     np.testing.assert_allclose(ess.cpu().numpy().reshape(c["ess"].shape), c["ess"], rtol=1e-4)
+
+
+def test_conformal_regressors(cuda):
+    from fortuna_b200.conformal.regression.quantile import (OneDimensionalUncertaintyConformalRegressor,
+                                                            QuantileConformalRegressor)
+
+    c = case("creg/")
+    q = QuantileConformalRegressor()
+    assert np.array_equal(q.score(c["val_lower"], c["val_upper"], c["val_targets"]), c["q_scores"])
+    o = OneDimensionalUncertaintyConformalRegressor()
+    assert np.array_equal(o.score(c["val_preds"], c["val_unc"], c["val_targets"]), c["o_scores"])
+    for e in (0.05, 0.2):
+        assert np.float32(float(q.quantile(c["val_lower"], c["val_upper"], c["val_targets"], e))) == c[f"q_quantile_{e}"]
+        ci = q.conformal_interval(c["val_lower"], c["val_upper"], c["test_lower"], c["test_upper"], c["val_targets"], e)
+        assert np.array_equal(ci, c[f"q_interval_{e}"])
+        assert np.array_equal(q.is_in(np.zeros(len(ci), np.float32), ci), c[f"q_is_in_{e}"].astype(bool))
+        assert np.float32(float(o.quantile(c["val_preds"], c["val_unc"], c["val_targets"], e))) == c[f"o_quantile_{e}"]
+        ci = o.conformal_interval(c["val_preds"], c["val_unc"], c["test_preds"], c["test_unc"], c["val_targets"], e)
+        assert np.array_equal(ci, c[f"o_interval_{e}"])

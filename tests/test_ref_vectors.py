@@ -332,3 +332,16 @@ def test_conformal_bayes_sets():
         region = Sc.conformal_bayes_region(ell, lsm, e)
         assert (region != c[f"region_{e}"].astype(bool)).sum() <= 1
     np.testing.assert_allclose(Sc.conformal_bayes_ess(lsm), c["ess"], rtol=1e-5)
+
+
+def test_conformal_regression_quantiles():
+    """quantile.py / onedim_uncertainty.py: scores and the conformal quantile level + linear interpolation."""
+    c = case("creg/")
+    y = c["val_targets"][:, 0]
+    qs = np.maximum(c["val_lower"] - y, y - c["val_upper"]).astype(np.float32)
+    assert np.array_equal(qs, c["q_scores"])
+    os_ = (np.abs(c["val_targets"] - c["val_preds"]) / c["val_unc"])[:, 0].astype(np.float32)
+    assert np.array_equal(os_, c["o_scores"])
+    for e in (0.05, 0.2):
+        assert np.float32(Sc.conformal_quantile(qs, e)) == c[f"q_quantile_{e}"]
+        assert np.float32(Sc.conformal_quantile(os_, e)) == c[f"o_quantile_{e}"]

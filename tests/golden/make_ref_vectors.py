@@ -611,6 +611,29 @@ def gen_conformal_regression():
         put(f"creg/o_interval_{e}", o.conformal_interval(J._j(vp), J._j(vu), J._j(tp), J._j(tu), J._j(vy), e))
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# 11. calibration loss with ensemble outputs (predictive/base.py:205-316, likelihood/base.py:124-262)
+# --------------------------------------------------------------------------------------------------------------------
+def gen_calibration_loss():
+    r = np.random.default_rng(31)
+    S, B, C, d = 5, 40, 6, 2
+    z = (2 * r.standard_normal((S, B, C))).astype(np.float32)
+    t = r.integers(0, C, B).astype(np.int32)
+    zr = r.standard_normal((S, B, 2 * d)).astype(np.float32)
+    y = r.standard_normal((B, d)).astype(np.float32)
+    for k, v in dict(logits=z, targets=t, outputs=zr, y=y, n_data=np.int32(3 * B)).items():
+        put("calib/" + k, v)
+    W = np.zeros((1, 3, C), np.float32)
+    for kind, ens, tg, ncol in (("cls", z, t, C), ("reg", zr, y, 2 * d)):
+        pred = make_predictive(kind, np.zeros((1, 3, ncol), np.float32), np.zeros((1, ncol), np.float32), 0.0)
+        for lt in (0.0, 0.4, -0.3):
+            cal = {"output_calibrator": {"log_temp": J._j(np.array([lt], np.float32))}}
+            v = pred._batched_negative_log_joint_prob((J._j(np.zeros((B, 3), np.float32)), J._j(tg)), 3 * B,
+                                                      return_aux=[], ensemble_outputs=J._j(ens), calib_params=cal,
+                                                      calib_mutable=None)
+            put(f"calib/{kind}_loss_{lt}", v)
+
+
 def logging_off():
     import logging
 
@@ -628,6 +651,7 @@ def main():
     gen_losses()
     gen_conformal_bayes()
     gen_conformal_regression()
+    gen_calibration_loss()
     path = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **OUT)
     print(f"wrote {path}: {len(OUT)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")

@@ -392,3 +392,16 @@ def test_conformal_regressors(cuda):
         assert np.float32(float(o.quantile(c["val_preds"], c["val_unc"], c["val_targets"], e))) == c[f"o_quantile_{e}"]
         ci = o.conformal_interval(c["val_preds"], c["val_unc"], c["test_preds"], c["test_unc"], c["val_targets"], e)
         assert np.array_equal(ci, c[f"o_interval_{e}"])
+
+
+def test_calibration_loss_with_ensemble_outputs(cuda):
+    from fortuna_b200.prob_model.calibration import loss_and_grad
+
+    c = case("calib/")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    n_data = int(c["n_data"])
+    for lt in (0.0, 0.4, -0.3):
+        loss, _ = loss_and_grad(t(c["logits"]), t(c["targets"]), np.float32(lt), n_data=n_data)
+        np.testing.assert_allclose(loss, c[f"cls_loss_{lt}"], rtol=1e-5)
+        loss, _ = loss_and_grad(t(c["outputs"]), t(c["y"]), np.float32(lt), n_data=n_data, regression=True)
+        np.testing.assert_allclose(loss, c[f"reg_loss_{lt}"], rtol=1e-5)

@@ -345,3 +345,18 @@ def test_conformal_regression_quantiles():
     for e in (0.05, 0.2):
         assert np.float32(Sc.conformal_quantile(qs, e)) == c[f"q_quantile_{e}"]
         assert np.float32(Sc.conformal_quantile(os_, e)) == c[f"o_quantile_{e}"]
+
+
+def test_calibration_loss_with_ensemble_outputs():
+    """predictive/base.py:205-316 + likelihood/base.py:124-262: -(logsumexp_s((n_data / B) L_s) - log S) under the
+    temperature scalers (the oracle evaluates in float64, the reference source in float32: rtol 1e-5)."""
+    from oracle import calibration as Cal
+
+    c = case("calib/")
+    n_data = int(c["n_data"])
+    for lt in (0.0, 0.4, -0.3):
+        np.testing.assert_allclose(Cal.calib_loss(c["logits"], c["targets"], lt, n_data), c[f"cls_loss_{lt}"], rtol=1e-5)
+        L, _ = Cal.calib_terms_reg(c["outputs"], c["y"], lt)
+        a = (n_data / c["y"].shape[0]) * L
+        want = -(a.max() + np.log(np.exp(a - a.max()).sum()) - np.log(len(a)))
+        np.testing.assert_allclose(want, c[f"reg_loss_{lt}"], rtol=1e-5)

@@ -564,9 +564,19 @@ def _make_random():
             from oracle import multivalid as _mv
 
             return _j(_mv.permutation_from_key(np.asarray(key), int(a)))
+        if p is not None and replace:
+            # choice with probabilities and replacement (jax/_src/random.py): p_cuml = cumsum(p);
+            # r = p_cuml[-1] * (1 - uniform(key, shape)); searchsorted(p_cuml, r) - a jax LIBRARY algorithm, restated
+            from oracle.scoring import cumsum_f32
+
+            n_draw = int(np.prod(shape)) if len(tuple(shape)) else 1
+            p_cuml = cumsum_f32(np.asarray(p, dtype=np.float32))
+            u = P.uniform(np.asarray(key), n_draw).astype(np.float32)
+            r = (p_cuml[-1] * (np.float32(1) - u)).astype(np.float32)
+            return _j(np.searchsorted(p_cuml, r, side="left").astype(np.int32).reshape(tuple(shape)))
         if p is not None or tuple(shape) != ():
-            raise NotImplementedError("stand-in: the scalar uniform random.choice(key, n) of SGMCMCPosterior.sample and the "
-                                      "full permutation of the multivalid split only")
+            raise NotImplementedError("stand-in: the scalar uniform random.choice(key, n) of SGMCMCPosterior.sample, the "
+                                      "full permutation of the multivalid split and choice(p=) with replacement only")
         return _j(np.int32(P.choice(np.asarray(key), int(a))))
 
     m.normal, m.uniform, m.choice = normal, uniform, choice

@@ -204,6 +204,11 @@ def gen_cls_predictive():
         put(pre + "ensemble_log_prob", pred.ensemble_log_prob(dloader, **kw))
         put(pre + "calibrated_outputs", pred.sample_calibrated_outputs(loader, n_output_samples=S, rng=J._j(key),
                                                                        distribute=False))
+        # target samples: Predictive.sample cannot take an explicit rng (base.py:355, see the regression case below)
+        RNG = imp("fortuna.utils.random").RandomNumberGenerator
+        put(pre + "sample_key", RNG(seed).get())
+        pred.rng = RNG(seed)
+        put(pre + "sample", pred.sample([J._j(x)], n_target_samples=6, distribute=False))
         cs = pred.credible_set(loader, n_posterior_samples=S, error=0.1, rng=J._j(key), distribute=False)
         sizes_cs = np.array([len(s) for s in cs], np.int32)
         padded = np.full((B, C), -1, np.int32)

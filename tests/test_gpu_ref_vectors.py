@@ -83,6 +83,10 @@ def test_classification_predictive_api(cuda, tag):
         np.testing.assert_allclose(got(getattr(p, name)(inputs, S, rng=key)), c[name], rtol=1e-5, atol=4e-6, err_msg=name)
     np.testing.assert_allclose(got(p.log_prob(data, S, rng=key)), c["log_prob"], rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(got(p.ensemble_log_prob(data, S, rng=key)), c["ensemble_log_prob"], rtol=1e-5, atol=2e-6)
+    # target samples: integer class draws; a draw whose uniform lands within float32 rounding of a cumulative probability
+    # may fall on the neighbouring class
+    ys = got(p.sample(InputsLoader.from_array_inputs(c["x"]), 6, rng=dev_key(c["sample_key"], cuda)))
+    assert ys.shape == c["sample"].shape and (ys != c["sample"]).mean() <= 0.01
     sets = p.credible_set(inputs, S, error=0.1, rng=key)
     # a set boundary is a threshold test on a float32 prefix sum: rows whose boundary the reference decides by less
     # than the mean's tolerance are skipped (none in these fixtures would be a surprise; the count is asserted)

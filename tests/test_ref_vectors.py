@@ -69,6 +69,11 @@ def test_classification_predictive(tag):
         np.testing.assert_allclose(fn(z), c[name], rtol=2e-6, atol=5e-7, err_msg=name)
     # the literal O(C^2) form of the reference's loop agrees with the closed form the kernels use
     np.testing.assert_allclose(P.cls_entropy_faithful(z, "entropy"), c["entropy"], rtol=2e-6, atol=5e-7)
+    # target samples (Predictive.sample -> ClassificationProbOutputLayer.sample): one key per target sample, split into
+    # the posterior draw and the per-row keys of jax.random.choice(p=)
+    stored = P.last_layer_logits(c["x"], c["W"], c["b"])
+    y, _ = P.cls_sample_targets(stored, c["sample_key"], 6, log_temp=lt)
+    assert np.array_equal(y, c["sample"])
     sets = P.cls_credible_set(P.cls_mean(z), 0.1)
     assert np.array_equal(np.array([len(s) for s in sets]), c["credible_set_sizes"])
     for i, s in enumerate(sets):

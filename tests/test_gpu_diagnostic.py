@@ -120,3 +120,54 @@ def test_ess_of_the_sample_bank(cuda):
     ok = D.ess_threshold_margin(trees, 0.0) > 1e-4
     np.testing.assert_allclose(flat[ok], want[ok], rtol=2e-4)
     assert got["a"]["kernel"].shape == (3, 5)
+
+
+@pytest.mark.parametrize("S", [1, 2, 3, 31, 32, 33, 63, 64])
+@pytest.mark.parametrize("N", [1, 255, 300_001])
+def test_ess_short_chain_kernel_edges(cuda, S, N):
+    """The register-resident kernel (S <= 64: prefetch ring, packed lag products, warp-level early exit) at the ends of its
+    ranges: chains that fill / do not fill the 32- and 64-sample instantiations, one parameter, a ragged last warp, more
+    parameters than one pass of the persistent grid, rows strided inside a wider matrix, with and without the cut-off."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(S * 7 + N % 1000)
+    ar = np.zeros((S, N), np.float32)
+    e = r.standard_normal((S, N)).astype(np.float32)
+    rho = r.uniform(0.0, 0.9, N).astype(np.float32)
+    for t in range(1, S):
+        ar[t] = rho * ar[t - 1] + e[t]
+    x = (1.0 + ar).astype(np.float32)
+    wide = torch.zeros((S, N + 5), device=cuda)
+    wide[:, 2 : N + 2] = torch.from_numpy(x).to(cuda)
+    for thr in (0.0, None):
+        got = ops.ess(wide[:, 2 : N + 2], thr).cpu().numpy()
+        assert got.shape == (N,)
+        if S < 3:
+            continue  # S = 1: 0 / 0; S = 2: the two lags cancel exactly - NaN / inf / rounding noise in the reference too
+        if thr is None:
+            continue  # every lag kept: the denominator is rounding noise (see test_oracle_diagnostic), shapes only
+        want = D.effective_sample_size_direct(x, thr)
+        ok = D.ess_threshold_margin(x, thr) > 1e-4
+        np.testing.assert_allclose(got[ok], want[ok], rtol=3e-4)
+    if S == 1:
+        assert np.isnan(ops.ess(wide[:, 2 : N + 2], 0.0).cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("S", [2, 5, 17, 31, 32])
+@pytest.mark.parametrize("N", [1, 111, 113, 100_003])
+def test_ksd_triangle_kernel_edges(cuda, S, N):
+    """Chains of <= 32 samples take the triangle kernel (4 x 4 pair blocks bi <= bj): block edges inside and at the end of
+    the tile, fewer columns than one 112-column stage, a ragged last stage, several splits, strided rows."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(S * 13 + N % 1000)
+    centre = r.standard_normal(N).astype(np.float32)
+    x = (centre + 0.05 * r.standard_normal((S, N))).astype(np.float32)
+    g = (-(x - centre) / 0.05**2 * 0.01 + 0.1 * r.standard_normal((S, N))).astype(np.float32)
+    wx = torch.zeros((S, N + 3), device=cuda)
+    wg = torch.zeros((S, N + 3), device=cuda)
+    wx[:, 1 : N + 1] = torch.from_numpy(x).to(cuda)
+    wg[:, 1 : N + 1] = torch.from_numpy(g).to(cuda)
+    got = float(ops.ksd_imq(wx[:, 1 : N + 1], wg[:, 1 : N + 1]).item())
+    want, total, slack = _ksd_tol(x, g, 1.0, -0.5)
+    assert abs(got**2 * S * S - total) <= slack + 1e-5 * abs(total)

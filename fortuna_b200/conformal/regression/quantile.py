@@ -3,8 +3,6 @@ onedim_uncertainty.py, base.py).  The conformal quantile ``jnp.quantile(scores, 
 interpolation over the validation scores - runs on the device (fb200_sort_f32 + fb200_quantile_sorted); ``score`` and
 ``conformal_interval`` are one elementwise expression each over validation-set-sized vectors, evaluated in float32 on the
 host in the reference's operation order (small-n host algebra, not a kernel)."""
-from typing import Optional
-
 import numpy as np
 import torch
 

@@ -25,7 +25,6 @@ from __future__ import annotations
 
 import importlib.abc
 import importlib.machinery
-import importlib.util
 import os
 import sys
 import types
@@ -258,10 +257,6 @@ class TreeDef:
 
     def __repr__(self):
         return f"TreeDef({self.skeleton!r})"
-
-
-def _is_leaf_obj(x):
-    return not isinstance(x, (dict, list, tuple)) and x is not None
 
 
 def _flatten(tree, leaves, is_leaf=None):
@@ -805,7 +800,3 @@ def load_reference():
     if _FINDER not in sys.meta_path:
         sys.meta_path.insert(0, _FINDER)
     return importlib.import_module
-
-
-def to_np(x):
-    return np.asarray(x)

@@ -16,7 +16,9 @@ possible doubles, all defined below:
 /root/reference does not travel to the GPU box, so the vectors are committed; tests/test_ref_vectors.py checks the
 oracle against them on CPU and tests/test_gpu_ref_vectors.py the CUDA path.
 
-Run from the repo root:  python tests/golden/make_ref_vectors.py
+Run from the repo root:  python tests/golden/make_ref_vectors.py [--out other.npz]
+(tests/test_ref_vectors.py::test_committed_vectors_are_what_the_reference_source_produces re-runs it wherever
+/root/reference is present and compares every array with the committed file.)
 """
 import os
 import sys
@@ -657,7 +659,7 @@ def main():
     gen_conformal_bayes()
     gen_conformal_regression()
     gen_calibration_loss()
-    path = os.path.join(HERE, "ref_vectors.npz")
+    path = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **OUT)
     print(f"wrote {path}: {len(OUT)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")
 

@@ -36,11 +36,6 @@ def log_temp_of(c):
     return None if np.isnan(c["log_temp"]) else np.float32(c["log_temp"])
 
 
-def ulps(a, b):
-    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
-    return np.max(np.abs(a.astype(np.float64) - b) / np.maximum(np.spacing(np.abs(b)), np.float32(1e-45)))
-
-
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
 def test_classification_predictive(tag):
     c = case(f"cls_{tag}/")
@@ -365,3 +360,21 @@ def test_calibration_loss_with_ensemble_outputs():
         a = (n_data / c["y"].shape[0]) * L
         want = -(a.max() + np.log(np.exp(a - a.max()).sum()) - np.log(len(a)))
         np.testing.assert_allclose(want, c[f"reg_loss_{lt}"], rtol=1e-5)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/fortuna"), reason="the reference tree only exists in the build container")
+def test_committed_vectors_are_what_the_reference_source_produces(tmp_path):
+    """Provenance of ref_vectors.npz: re-run the generator (which imports and executes the reference's files from
+    /root/reference) and compare every array with the committed fixture, bit for bit."""
+    import subprocess
+    import sys
+
+    out = tmp_path / "regen.npz"
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_ref_vectors.py"), "--out", str(out)], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    new = np.load(out)
+    assert sorted(new.files) == sorted(REF.files)
+    for k in REF.files:
+        assert new[k].dtype == REF[k].dtype and np.array_equal(new[k], REF[k], equal_nan=True), k

@@ -132,6 +132,137 @@ __global__ void __launch_bounds__(256) last_layer_simt_kernel(const TI* __restri
   }
 }
 
+// float32, K-major weights (w[s][c][d]: what a torch nn.Linear holds and what the predictive passes), D % 4 == 0, 16-byte
+// aligned operands - the c2 / c3 shapes (LeNet 84 x 10, ResNet-18 512 x 10).  Same 128 x 64 x 16 tiling over the flattened
+// column n = s * C + c and the same k-ascending FMA order per output as the kernel above (bit-identical results), but:
+// both operands stay K-major in shared memory ([row][k], 20-float rows) and arrive by 16-byte cp.async into a double
+// buffer (one barrier per k-step, copies of step k + 1 under the arithmetic of step k); fragments are read as float4
+// along k (12 LDS.128 per 128 FMAs; a thread's four columns are 16 apart, which makes the weight reads conflict-free);
+// the finished tile goes through shared memory so that each sample's [rows, classes] block - contiguous in the output -
+// is written with coalesced stores instead of 4-byte stores C floats apart.  Measured at c3 (S=256, B=10 000, D=512,
+// C=10): 1.00 -> 0.68 ms = 38 TFLOP/s, which is this part's float32 CUDA-core rate (a 3-register FFMA issues every
+// other cycle per scheduler: 148 x 64 lanes x 2 x 1.96 GHz = 37 TFLOP/s; the same loop on packed FFMA2 - even / odd k in
+// the two halves - measured 0.68 ms too and was not kept: it is the pipe, not the issue slots).
+constexpr int kKM_ROW = kBK + 4;  // floats per staged row: 16-byte aligned, 20 * r mod 32 distinct for 8 consecutive r
+
+__device__ __forceinline__ void cp_async16_zfill(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256, 2) last_layer_simt_kmajor_kernel(const float* __restrict__ x,
+                                                                        const float* __restrict__ w,
+                                                                        const float* __restrict__ bias,
+                                                                        const float* __restrict__ log_temp,
+                                                                        const int32_t* __restrict__ sample_idx,
+                                                                        TO* __restrict__ out, int S, int B, int D, int C) {
+  constexpr int A_STAGE = kBM * kKM_ROW, B_STAGE = kBN * kKM_ROW;
+  constexpr int C_ROW = kBN + 1;
+  constexpr int SMEM_FLOATS = (2 * (A_STAGE + B_STAGE) > kBM * C_ROW) ? 2 * (A_STAGE + B_STAGE) : kBM * C_ROW;
+  __shared__ __align__(16) float smem[SMEM_FLOATS];
+  float* As = smem;                // [2][kBM][kKM_ROW]
+  float* Bs = smem + 2 * A_STAGE;  // [2][kBN][kKM_ROW]
+  const int N = S * C;
+  const int n0 = blockIdx.x * kBN;
+  const int b0 = blockIdx.y * kBM;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // thread tile: rows ty*8 .. +8, columns tx + 16 j
+
+  // copy roles: A - two 16-byte chunks per thread (row = id / 4, k chunk = id % 4); B - one chunk (column tid / 4)
+  const int kc = tid & 3;
+  const int a_row0 = tid >> 2, a_row1 = a_row0 + 64;
+  const bool a_ok0 = b0 + a_row0 < B, a_ok1 = b0 + a_row1 < B;
+  const float* a_src0 = x + (size_t)(a_ok0 ? b0 + a_row0 : 0) * D + kc * 4;
+  const float* a_src1 = x + (size_t)(a_ok1 ? b0 + a_row1 : 0) * D + kc * 4;
+  const int b_col = tid >> 2;
+  const bool b_ok = n0 + b_col < N;
+  const float* b_src;
+  {
+    const int n = b_ok ? n0 + b_col : 0;
+    const int sn = n / C, cn = n - sn * C;
+    const int sw = sample_idx ? sample_idx[sn] : sn;
+    b_src = w + ((size_t)sw * C + cn) * (size_t)D + kc * 4;
+  }
+  auto stage = [&](int buf, int k0) {
+    const bool kin = k0 + kc * 4 < D;  // D % 4 == 0: a chunk is inside or outside as a whole
+    cp_async16_zfill(As + buf * A_STAGE + a_row0 * kKM_ROW + kc * 4, a_src0 + (kin ? k0 : 0), a_ok0 && kin);
+    cp_async16_zfill(As + buf * A_STAGE + a_row1 * kKM_ROW + kc * 4, a_src1 + (kin ? k0 : 0), a_ok1 && kin);
+    cp_async16_zfill(Bs + buf * B_STAGE + b_col * kKM_ROW + kc * 4, b_src + (kin ? k0 : 0), b_ok && kin);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  stage(0, 0);
+  int buf = 0;
+  for (int k0 = 0; k0 < D; k0 += kBK, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // step k0 has landed for everyone, and everyone is done reading the other buffer
+    if (k0 + kBK < D) stage(buf ^ 1, k0 + kBK);
+    const float* Ab = As + buf * A_STAGE + (ty * 8) * kKM_ROW;
+    const float* Bb = Bs + buf * B_STAGE + tx * kKM_ROW;
+#pragma unroll
+    for (int kq = 0; kq < kBK / 4; ++kq) {
+      float4 a4[8], b4[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a4[i] = *reinterpret_cast<const float4*>(Ab + i * kKM_ROW + kq * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b4[j] = *reinterpret_cast<const float4*>(Bb + (16 * j) * kKM_ROW + kq * 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(a4[i].x, b4[j].x, acc[i][j]);
+          acc[i][j] = fmaf(a4[i].y, b4[j].y, acc[i][j]);
+          acc[i][j] = fmaf(a4[i].z, b4[j].z, acc[i][j]);
+          acc[i][j] = fmaf(a4[i].w, b4[j].w, acc[i][j]);
+        }
+    }
+  }
+  __syncthreads();  // the operand buffers become the output tile
+
+  const float scale = log_temp ? expf(-log_temp[0]) : 1.0f;
+  float* Cs = smem;  // [kBM][C_ROW]
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int nl = tx + 16 * j, n = n0 + nl;
+    float bj = 0.0f;
+    if (bias && n < N) {
+      const int sn = n / C, cn = n - sn * C;
+      bj = bias[(size_t)(sample_idx ? sample_idx[sn] : sn) * C + cn];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = acc[i][j] + bj;
+      if (log_temp) v *= scale;
+      Cs[(ty * 8 + i) * C_ROW + nl] = v;
+    }
+  }
+  __syncthreads();
+  // per sample of the tile: out[s][b0 .. b0 + rows)[c_lo .. c_hi) - one contiguous block when the sample's classes are all
+  // inside the tile, rows of (c_hi - c_lo) floats C apart at the tile's edges
+  const int rows = min(kBM, B - b0);
+  const int n_end = min(n0 + kBN, N);
+  for (int ns = n0; ns < n_end;) {
+    const int sn = ns / C, c_lo = ns - sn * C;
+    const int c_hi = min(C, c_lo + (n_end - ns));
+    const int wseg = c_hi - c_lo;
+    TO* obase = out + ((size_t)sn * B + b0) * C + c_lo;
+    const float* cbase = Cs + (ns - n0);
+    for (int e = tid; e < rows * wseg; e += 256) {
+      const int r = e / wseg, c = e - r * wseg;
+      store_out(obase + (size_t)r * C + c, cbase[r * C_ROW + c]);
+    }
+    ns += wseg;
+  }
+}
+
 // wt[s][c][d] (bf16) = w[s][d][c]
 template <typename TI>
 __global__ void __launch_bounds__(256) transpose_w_kernel(const TI* __restrict__ w, __nv_bfloat16* __restrict__ wt,
@@ -161,6 +292,17 @@ static int launch_simt(const void* x, const void* w, const float* bias, const fl
   if (N > 0x7FFFFFFFll) return FB200_E_UNSUPPORTED;
   dim3 grid((unsigned)((N + kBN - 1) / kBN), (B + kBM - 1) / kBM, 1);
   if (grid.y > 65535) return FB200_E_UNSUPPORTED;
+  if constexpr (sizeof(TI) == 4) {
+    // float32 operands, K-major weights, whole 16-byte chunks along k: the double-buffered kernel
+    // (from D = 128 up: at LeNet's D = 84 - six k-steps - the tile epilogue weighs as much as the copies save, 89 vs 84 us)
+    if (w_layout == FB200_W_SCD && D % 4 == 0 && D >= 128 && fb200_aligned16(x) && fb200_aligned16(w)) {
+      last_layer_simt_kmajor_kernel<TO><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x),
+                                                                reinterpret_cast<const float*>(w), bias, log_temp,
+                                                                sample_idx, reinterpret_cast<TO*>(out), S, B, D, C);
+      FB200_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   if (w_layout == FB200_W_SDC)
     last_layer_simt_kernel<TI, TO, FB200_W_SDC><<<grid, 256, 0, st>>>(
         reinterpret_cast<const TI*>(x), reinterpret_cast<const TI*>(w), bias, log_temp, sample_idx,

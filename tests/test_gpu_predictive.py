@@ -326,3 +326,34 @@ def test_calibrate_temperature_recovers_the_generating_temperature(cuda):
         optimizer=CalibOptimizer(method=Adam(5e-2), n_epochs=60)), z_val=z[:, :1000].contiguous(), targets_val=y[:1000])
     assert status["loss"].shape == (60,) and status["val_loss"].shape == (60,)
     assert status["loss"][-1] < status["loss"][0] and abs(float(log_temp[0]) - np.log(3.0)) < 0.12
+
+
+@pytest.mark.parametrize("S,B,D,C", [(100, 1000, 84, 10), (32, 513, 512, 10), (7, 130, 128, 3), (3, 127, 132, 17), (5, 129, 256, 64),
+                                     (64, 300, 768, 2), (1, 1, 128, 1)])
+@pytest.mark.parametrize("gather", [False, True])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_last_layer_kmajor_f32_kernel(cuda, S, B, D, C, gather, out_bf16):
+    """float32 operands with K-major weights, D % 4 == 0 and D >= 128 take the double-buffered kernel (the c3 shape among them):
+    same FMA order per output as the generic kernel - bit-identical to it (reached through the [S, D, C] layout) - and
+    within rtol 1e-5 of the oracle; tiles that cut samples, ragged rows, one-class and one-row edges, gathered samples."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(S * 1000 + D)
+    n = S + 3 if gather else S
+    x = r.standard_normal((B, D)).astype(np.float32)
+    w = (r.standard_normal((n, D, C)) / np.sqrt(D)).astype(np.float32)
+    bias = r.standard_normal((n, C)).astype(np.float32)
+    lt = np.array([-0.2], dtype=np.float32)
+    idx = r.integers(0, n, S).astype(np.int32) if gather else None
+    xt, w_sdc = torch.from_numpy(x).to(cuda), torch.from_numpy(w).to(cuda)
+    w_scd = w_sdc.transpose(1, 2).contiguous()
+    bt, ltt = torch.from_numpy(bias).to(cuda), torch.from_numpy(lt).to(cuda)
+    it = torch.from_numpy(idx).to(cuda) if gather else None
+    od = torch.bfloat16 if out_bf16 else torch.float32
+    new = ops.last_layer_logits(xt, w_scd, bt, ltt, out_dtype=od, w_layout=ops.W_SCD, sample_idx=it, path=1)
+    old = ops.last_layer_logits(xt, w_sdc, bt, ltt, out_dtype=od, w_layout=ops.W_SDC, sample_idx=it, path=1)
+    assert new.shape == (S, B, C) and torch.equal(new, old)
+    sel = idx if gather else np.arange(S)
+    want = P.last_layer_logits(x, w[sel], bias[sel], lt)
+    tol = dict(rtol=1e-2, atol=1e-2) if out_bf16 else dict(rtol=1e-5, atol=1e-5 * np.sqrt(D))
+    np.testing.assert_allclose(new.float().cpu().numpy(), want, **tol)

@@ -183,6 +183,7 @@ def gen_cls_predictive():
         "a": (8, 20, 11, 50, 9, None, 1),
         "b": (6, 16, 3, 40, 30, 0.3, 2),     # S > n: draws repeat, as in the reference
         "c": (12, 32, 100, 24, 7, -0.2, 3),
+        "d": (8, 16, 1000, 36, 16, 0.1, 4),  # the headline width: C = 1000 (tiled single-pass reduction, select kernel)
     }.items():
         r = np.random.default_rng(seed)
         W = (3 * r.standard_normal((n, D, C)) / np.sqrt(D)).astype(np.float32)
@@ -204,8 +205,9 @@ def gen_cls_predictive():
             put(pre + m, getattr(pred, m)(loader, **kw))
         put(pre + "log_prob", pred.log_prob(dloader, **kw))
         put(pre + "ensemble_log_prob", pred.ensemble_log_prob(dloader, **kw))
-        put(pre + "calibrated_outputs", pred.sample_calibrated_outputs(loader, n_output_samples=S, rng=J._j(key),
-                                                                       distribute=False))
+        if C < 1000:  # [S, B, C]: left out of the wide case to keep the fixture small
+            put(pre + "calibrated_outputs", pred.sample_calibrated_outputs(loader, n_output_samples=S, rng=J._j(key),
+                                                                           distribute=False))
         # target samples: Predictive.sample cannot take an explicit rng (base.py:355, see the regression case below)
         RNG = imp("fortuna.utils.random").RandomNumberGenerator
         put(pre + "sample_key", RNG(seed).get())

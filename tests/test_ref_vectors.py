@@ -36,13 +36,14 @@ def log_temp_of(c):
     return None if np.isnan(c["log_temp"]) else np.float32(c["log_temp"])
 
 
-@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
 def test_classification_predictive(tag):
     c = case(f"cls_{tag}/")
     n, lt = c["W"].shape[0], log_temp_of(c)
     idx = drawn(c["key"], c["S"], n)
     z = P.last_layer_logits(c["x"], c["W"][idx], c["b"][idx], log_temp=lt)
-    assert np.array_equal(z, c["calibrated_outputs"])
+    if "calibrated_outputs" in c:
+        assert np.array_equal(z, c["calibrated_outputs"])
     # one evaluation order: exact
     assert np.array_equal(P.cls_mean(z), c["mean"])
     assert np.array_equal(P.cls_mode(z), c["mode"])

@@ -16,6 +16,7 @@
 // reductions and the per-(b,c) sums over s live in registers until the tile's single store.
 #include "bma_reduce.cuh"
 
+
 namespace fb200 {
 
 template <typename T, int G, int NV, int VEC, bool TAILONLY, int NW, int RI>
@@ -222,8 +223,8 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
           const float spq = spv - sp2v;  // sum_s p(1-p)
           av[k] = div_s(spq, dS);
           const float m2 = div_s(sp2v, dS);
-          ev[k] = fmaxf(0.0f, __fsub_rn(m2, __fmul_rn(mean[k], mean[k])));
-          if (mean[k] > 0.0f) ent_terms = fmaf(mean[k], __logf(mean[k]), ent_terms);
+          ev[k] = clamp0_keep_nan(__fsub_rn(m2, __fmul_rn(mean[k], mean[k])));
+          if (!(mean[k] <= 0.0f)) ent_terms = fmaf(mean[k], __logf(mean[k]), ent_terms);
           if (mean[k] > best_v) {
             best_v = mean[k];
             best_c = c0 + k;
@@ -322,8 +323,8 @@ __global__ void __launch_bounds__(32 * kNarrowStreams) bma_reduce_cls_narrow_ker
           float tmp[1];
           RowLoad<T, 1>::load(rp + c, tmp);
           z[c] = tmp[0];
+          m = fmaxf(m, z[c]);  // the row's own entries only: padding must not lend an all -inf row a finite maximum
         }
-        m = fmaxf(m, z[c]);
       }
       const float ms = (fabsf(m) <= 3.4028234e38f) ? m : 0.0f;
       const float csh = ms * k2;
@@ -338,7 +339,8 @@ __global__ void __launch_bounds__(32 * kNarrowStreams) bma_reduce_cls_narrow_ker
         sum += ev;
         set = fmaf(ev, u, set);
       }
-      const float inv = rcp_approx_ftz(sum);
+      // softmax of a row whose maximum is not finite is NaN in every class (jax.nn.softmax; see process_rows)
+      const float inv = (fabsf(m) <= 3.4028234e38f) ? rcp_approx_ftz(sum) : CUDART_NAN_F;
       const float inv2 = inv * inv;
       const float l2s = lg2_approx(sum);
       spl = fmaf(inv, set, spl);
@@ -402,10 +404,10 @@ __global__ void __launch_bounds__(32 * kNarrowStreams) bma_reduce_cls_narrow_ker
     if (c < C) {
       const float mean = sp[c] / Sf;
       const float av = (sp[c] - sp2[c]) / Sf;
-      const float ev = fmaxf(0.0f, __fsub_rn(sp2[c] / Sf, __fmul_rn(mean, mean)));
+      const float ev = clamp0_keep_nan(__fsub_rn(sp2[c] / Sf, __fmul_rn(mean, mean)));
       msq = fmaf(mean, mean, msq);
       if (c == y) mean_y = mean;
-      if (mean > 0.0f) ent_terms = fmaf(mean, logf(mean), ent_terms);
+      if (!(mean <= 0.0f)) ent_terms = fmaf(mean, logf(mean), ent_terms);
       if (mean > best_v) {
         best_v = mean;
         best_c = c;
@@ -508,10 +510,10 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const
     }
     const float mean = sp / Sf;
     const float av = (sp - sp2) / Sf;
-    const float ev = fmaxf(0.0f, __fsub_rn(sp2 / Sf, __fmul_rn(mean, mean)));
+    const float ev = clamp0_keep_nan(__fsub_rn(sp2 / Sf, __fmul_rn(mean, mean)));
     msq = fmaf(mean, mean, msq);
     if (c == y) mean_y = mean;
-    if (mean > 0.0f) ent_terms = fmaf(mean, logf(mean), ent_terms);
+    if (!(mean <= 0.0f)) ent_terms = fmaf(mean, logf(mean), ent_terms);
     if (mean > best_v) {
       best_v = mean;
       best_c = c;
@@ -678,8 +680,8 @@ __global__ void __launch_bounds__(256) bma_finalize_slots_kernel(const float* __
     for (int k = 0; k < W; ++k) {
       mean[k] = div_s(sp[k], dS);
       av[k] = div_s(sp[k] - sp2[k], dS);
-      ev[k] = fmaxf(0.0f, __fsub_rn(div_s(sp2[k], dS), __fmul_rn(mean[k], mean[k])));
-      if (mean[k] > 0.0f) ent_terms = fmaf(mean[k], __logf(mean[k]), ent_terms);
+      ev[k] = clamp0_keep_nan(__fsub_rn(div_s(sp2[k], dS), __fmul_rn(mean[k], mean[k])));
+      if (!(mean[k] <= 0.0f)) ent_terms = fmaf(mean[k], __logf(mean[k]), ent_terms);
       msq = fmaf(mean[k], mean[k], msq);
       mean_y = (c0 + k == y) ? mean[k] : mean_y;
       if (mean[k] > best_v) {
@@ -762,7 +764,7 @@ __global__ void __launch_bounds__(256) bma_reduce_reg_moments_kernel(const float
   const float Sf = (float)S;
   const float mean = smu / Sf;
   const float av = sv / Sf;
-  const float ev = fmaxf(0.0f, __fsub_rn(smu2 / Sf, __fmul_rn(mean, mean)));
+  const float ev = clamp0_keep_nan(__fsub_rn(smu2 / Sf, __fmul_rn(mean, mean)));
   if (out.mean) out.mean[i] = mean;
   if (out.aleatoric_variance) out.aleatoric_variance[i] = av;
   if (out.epistemic_variance) out.epistemic_variance[i] = ev;

@@ -121,8 +121,16 @@ __device__ __forceinline__ void process_rows(const T* const (&rowp)[RI], int g, 
     for (int j = 0; j < NV; ++j) {
       const int c0 = (g + G * j) * VEC;
       float t[VEC];
+      // the maximum is taken over the row's own entries only: a padding value must not become the shift of a row whose
+      // logits are all -inf (the reference's softmax of such a row is NaN, not 0)
       if ((TAILONLY && j < NV - 1) || c0 < C) {  // TAILONLY: every lane's chunk but the last is inside the row
         RowLoad<T, VEC>::load(rowp[ri] + c0, t);
+        if constexpr (VEC == 4) {
+          pm = fmaxf(fmaxf(pm, t[0]), t[1]);
+          pm = fmaxf(fmaxf(pm, t[2]), t[3]);
+        } else {
+          pm = fmaxf(pm, t[0]);
+        }
       } else {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) t[k] = -1.0e30f;
@@ -130,11 +138,8 @@ __device__ __forceinline__ void process_rows(const T* const (&rowp)[RI], int g, 
       if constexpr (VEC == 4) {
         z[ri][j][0] = make_float2(t[0], t[1]);
         z[ri][j][1] = make_float2(t[2], t[3]);
-        pm = fmaxf(fmaxf(pm, t[0]), t[1]);
-        pm = fmaxf(fmaxf(pm, t[2]), t[3]);
       } else {
         z[ri][j][0] = make_float2(t[0], -1.0e30f);
-        pm = fmaxf(pm, t[0]);
       }
     }
     m[ri] = pm;
@@ -185,7 +190,10 @@ __device__ __forceinline__ void process_rows(const T* const (&rowp)[RI], int g, 
   // pass C: p = e / sum, accumulate in sample order: sum p += e * inv, sum p^2 += (e*e) * inv^2 (two FFMA2 + one FMUL2 per pair)
 #pragma unroll
   for (int ri = 0; ri < RI; ++ri) {
-    const float inv = rcp_approx_ftz(sum[ri]);
+    // jax.nn.softmax subtracts the row maximum as it is: a row whose maximum is +inf or -inf (an infinite logit, or every
+    // logit -inf) is NaN in every class there - unlike logsumexp, which replaces a non-finite maximum by 0 (the shift
+    // used above, and what log_prob keeps).  The normaliser carries the NaN into sum p, sum p^2 and the entropy terms.
+    const float inv = (fabsf(m[ri]) <= 3.4028234e38f) ? rcp_approx_ftz(sum[ri]) : CUDART_NAN_F;
     const float inv2 = inv * inv;
     const float2 inv_2 = make_float2(inv, inv), inv2_2 = make_float2(inv2, inv2);
     l2sum[ri] = lg2_approx(sum[ri]);
@@ -215,6 +223,11 @@ __device__ __forceinline__ float div_s(float x, const DivS d) {
   const float q = x * d.r;
   return fmaf(fmaf(-d.S, q, x), d.r, q);
 }
+
+// max(0, v) that keeps a NaN (jnp.maximum propagates it; fmaxf(0, NaN) is 0): the epistemic variance of an input whose
+// mean is NaN is NaN in the reference.  The entropy terms likewise skip mean == 0 (an underflowed probability: 0 in the
+// reference's log-domain expression too) but not a NaN mean: `!(mean <= 0)`.
+__device__ __forceinline__ float clamp0_keep_nan(float v) { return v < 0.0f ? 0.0f : v; }
 
 // element k (0..VEC-1) of chunk j of a pair-packed accumulator
 template <int NV, int NP>

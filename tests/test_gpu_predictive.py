@@ -357,3 +357,38 @@ def test_last_layer_kmajor_f32_kernel(cuda, S, B, D, C, gather, out_bf16):
     want = P.last_layer_logits(x, w[sel], bias[sel], lt)
     tol = dict(rtol=1e-2, atol=1e-2) if out_bf16 else dict(rtol=1e-5, atol=1e-5 * np.sqrt(D))
     np.testing.assert_allclose(new.float().cpu().numpy(), want, **tol)
+
+
+@pytest.mark.parametrize("C", [10, 130, 1000, 1024])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_reduction_special_values_follow_the_reference(cuda, C, dtype):
+    """Rows that hold +inf, -inf or NaN, rows far below zero, rows whose lanes differ by hundreds of units, constant rows
+    and a sample whose logits are ALL -inf: NaN / inf patterns and values as the reference's float32 expressions give
+    them (oracle).  The bf16 instantiation shifts every lane's exponentials by the lane's own maximum and rescales
+    afterwards; the float32 one keeps the row shift - both must land on the same answers.  (Padding lanes - C not a
+    multiple of the lane tiling - must not lend an all -inf row a finite maximum: the reference's softmax of it is NaN.)"""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(C)
+    S, B = 6, 96
+    z = P.round_to_bf16((4 * r.standard_normal((S, B, C))).astype(np.float32))
+    z[0, 1, :] = -300.0                      # far below zero: exp underflows without a shift
+    z[1, 2, :] = 0.0                         # constant row
+    z[2, 3, : C // 2] = 250.0                # entries that differ by hundreds of units
+    z[2, 3, C // 2 :] = -250.0
+    z[3, 4, C // 3] = np.inf                 # +inf: jax.nn.softmax subtracts the maximum as it is - the whole row is NaN
+    z[4, 5, C // 4] = -np.inf                # -inf: p = 0, p ln p = NaN in the aleatoric entropy
+    z[5, 6, C - 1] = np.nan                  # NaN poisons its row
+    z[0, 7, :] = -np.inf                     # a sample of -inf only: softmax = NaN
+    names = ("mean", "aleatoric_variance", "epistemic_variance", "entropy", "aleatoric_entropy", "epistemic_entropy")
+    zt = torch.from_numpy(z).to(cuda)
+    got = ops.bma_reduce_cls(zt.to(torch.bfloat16) if dtype == "bf16" else zt, names)
+    with np.errstate(all="ignore"):
+        want = {"mean": P.cls_mean(z), "aleatoric_variance": P.cls_aleatoric_variance(z),
+                "epistemic_variance": P.cls_epistemic_variance(z), "entropy": P.cls_entropy(z),
+                "aleatoric_entropy": P.cls_aleatoric_entropy(z), "epistemic_entropy": P.cls_epistemic_entropy(z)}
+    for n in names:
+        x, y = got[n].float().cpu().numpy(), np.asarray(want[n], np.float32)
+        assert np.array_equal(np.isnan(x), np.isnan(y)), n
+        ok = np.isfinite(y)
+        np.testing.assert_allclose(x[ok], y[ok], rtol=2e-5, atol=4e-6, err_msg=n)

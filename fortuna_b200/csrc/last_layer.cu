@@ -330,13 +330,19 @@ __global__ void __launch_bounds__(256) row_lse_kernel(TO* __restrict__ z, int64_
     float m = -INFINITY;
     for (int c = lane; c < C; c += 32) m = fmaxf(m, (float)row[c] * scale);
     m = group_max<32>(m);
+    // jsp.special.logsumexp replaces a non-finite maximum by 0 (lse, and the log-softmax z - lse the reference's
+    // per-class log_prob is); jax.nn.softmax subtracts the maximum as it is: a row holding +inf, or only -inf, is NaN
+    // in every class there
+    const bool m_finite = fabsf(m) <= 3.4028234e38f;
+    const float ms = m_finite ? m : 0.0f;
     float s = 0.0f;
-    for (int c = lane; c < C; c += 32) s += __expf((float)row[c] * scale - m);
+    for (int c = lane; c < C; c += 32) s += __expf((float)row[c] * scale - ms);
     s = group_sum<32>(s);
-    const float lse = m + __logf(s);
+    const float lse = ms + __logf(s);
     if (lane == 0 && lse_out) lse_out[r] = lse;
     if (epi == 1) {
-      for (int c = lane; c < C; c += 32) row[c] = (TO)__expf((float)row[c] * scale - lse);
+      for (int c = lane; c < C; c += 32)
+        row[c] = (TO)(m_finite ? __expf((float)row[c] * scale - lse) : CUDART_NAN_F);
     } else if (epi == 2) {
       for (int c = lane; c < C; c += 32) row[c] = (TO)((float)row[c] * scale - lse);
     } else if (log_temp) {

@@ -392,3 +392,28 @@ def test_reduction_special_values_follow_the_reference(cuda, C, dtype):
         assert np.array_equal(np.isnan(x), np.isnan(y)), n
         ok = np.isfinite(y)
         np.testing.assert_allclose(x[ok], y[ok], rtol=2e-5, atol=4e-6, err_msg=n)
+
+
+@pytest.mark.parametrize("C", [10, 130, 1000])
+def test_row_softmax_special_values_follow_the_reference(cuda, C):
+    """fb200_softmax_rows on rows holding +inf / -inf / NaN / only -inf: the softmax epilogue follows jax.nn.softmax
+    (x - max as it is: such rows are NaN), the log-softmax epilogue and the row logsumexp follow jsp.special.logsumexp
+    (a non-finite maximum is replaced by 0: z - lse is -inf for the finite classes of a row with a +inf logit)."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(C)
+    z = (4 * r.standard_normal((64, C))).astype(np.float32)
+    z[1, :] = -300.0
+    z[3, C // 3] = np.inf
+    z[4, C // 4] = -np.inf
+    z[5, C - 1] = np.nan
+    z[6, :] = -np.inf
+    with np.errstate(all="ignore"):
+        want_sm, want_lsm, want_lse = P.softmax(z), P.log_softmax_rows(z[None])[0], P.logsumexp(z)
+    for epi, want in ((ops.EPI_SOFTMAX, want_sm), (ops.EPI_LOG_SOFTMAX, want_lsm)):
+        got, lse = ops.softmax_rows_(torch.from_numpy(z.copy()).to(cuda)[None].contiguous(), epi, want_lse=True)
+        got, lse = got[0].cpu().numpy(), lse.reshape(-1).cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
+        ok = np.isfinite(want)
+        np.testing.assert_allclose(got[ok], want[ok], rtol=2e-5, atol=1e-6)
+        assert np.array_equal(np.isnan(lse), np.isnan(want_lse)) and np.array_equal(np.isinf(lse), np.isinf(want_lse))

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(WarpCfg<NW>::kThreads, 1) bma_reduce_cls_kerne
       if (a.out.epistemic_entropy) a.out.epistemic_entropy[b] = ent - alea;
       if (a.out.mode) a.out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
       if (a.out.log_prob) a.out.log_prob[b] = (lmax + logf(lsum)) - a.log_S;
-      if (a.out.confidence) a.out.confidence[b] = best_v;
+      if (a.out.confidence) a.out.confidence[b] = best_c == 0x7FFFFFFF ? CUDART_NAN_F : best_v;  // a NaN row: max = NaN
       if (want_brier) a.out.brier_terms[b] = y_ok ? (msq - 2.0f * mean_y) + 1.0f : msq;
     }
   }
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(32 * kNarrowStreams) bma_reduce_cls_narrow_ker
   if (a.out.epistemic_entropy) a.out.epistemic_entropy[b] = ent - alea;
   if (a.out.mode) a.out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
   if (a.out.log_prob) a.out.log_prob[b] = (lmax + logf(lsum)) - a.log_S;
-  if (a.out.confidence) a.out.confidence[b] = best_v;
+  if (a.out.confidence) a.out.confidence[b] = best_c == 0x7FFFFFFF ? CUDART_NAN_F : best_v;  // a NaN row: max = NaN
   if (a.out.brier_terms) a.out.brier_terms[b] = y_ok ? (msq - 2.0f * mean_y) + 1.0f : msq;
 }
 
@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(256) bma_finalize_slots_kernel(const float* __
     if (out.aleatoric_entropy) out.aleatoric_entropy[b] = alea;
     if (out.epistemic_entropy) out.epistemic_entropy[b] = ent - alea;
     if (out.mode) out.mode[b] = best_c == 0x7FFFFFFF ? 0 : best_c;
-    if (out.confidence) out.confidence[b] = best_v;
+    if (out.confidence) out.confidence[b] = best_c == 0x7FFFFFFF ? CUDART_NAN_F : best_v;  // a NaN row: max = NaN
     if (out.log_prob) out.log_prob[b] = (M + logf(ssum)) - log_S;
     if (out.brier_terms) out.brier_terms[b] = (y >= 0 && y < C) ? (msq - 2.0f * mean_y) + 1.0f : msq;
   }

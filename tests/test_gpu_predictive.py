@@ -392,6 +392,13 @@ def test_reduction_special_values_follow_the_reference(cuda, C, dtype):
         assert np.array_equal(np.isnan(x), np.isnan(y)), n
         ok = np.isfinite(y)
         np.testing.assert_allclose(x[ok], y[ok], rtol=2e-5, atol=4e-6, err_msg=n)
+    # arg-max and max of the mean (jnp.argmax / jnp.max: a NaN row gives class 0 and NaN)
+    extra = ops.bma_reduce_cls(zt.to(torch.bfloat16) if dtype == "bf16" else zt, ("mean", "mode", "confidence"))
+    with np.errstate(all="ignore"):
+        nan_rows = np.isnan(want["mean"]).any(axis=1)
+    mode, conf = extra["mode"].cpu().numpy(), extra["confidence"].cpu().numpy()
+    assert (mode[nan_rows] == 0).all() and np.isnan(conf[nan_rows]).all() and np.isfinite(conf[~nan_rows]).all()
+    assert np.array_equal(mode[~nan_rows], extra["mean"].cpu().numpy()[~nan_rows].argmax(1))
 
 
 @pytest.mark.parametrize("C", [10, 130, 1000])

@@ -375,7 +375,7 @@ def gen_scoring():
             vs, ts = cl.get_scores(jvp, jvt, jtp)
             put(pre + kind + "_val_scores", vs)
             put(pre + kind + "_test_scores", ts)
-            for e in (0.05, 0.2):
+            for e in (0.05, 0.2) + ((0.0, 1.0, 0.999999) if tag == "a" else ()):  # the extremes: every class / none
                 sets = cl.conformal_set(jvp, jvt, jtp, error=e)
                 mask = np.zeros((nt, C), np.uint8)
                 for i, s in enumerate(sets):

@@ -234,7 +234,7 @@ def test_scores_sets_and_calibration_metrics(cuda, tag):
     assert np.array_equal(got(ops.simple_scores(vp, vt)), c["simple_val_scores"])
     assert np.array_equal(got(ops.simple_scores(tp, None)), c["simple_test_scores"])
     n_val = c["val_probs"].shape[0]
-    for e in (0.05, 0.2):
+    for e in (0.05, 0.2) + ((0.0, 1.0, 0.999999) if tag == "a" else ()):
         thr = Sc.conformal_threshold(n_val, e)
         val = ops.sort_f32_(ops.aps_scores(vp, vt))
         mask, sizes = ops.conformal_sets(val, ops.aps_scores(tp, None), thr)

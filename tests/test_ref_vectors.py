@@ -196,7 +196,7 @@ def test_scores_sets_and_calibration_metrics(tag):
     assert np.array_equal(Sc.aps_cumsums(tp), c["aps_test_scores"])
     assert np.array_equal(Sc.simple_score(vp, vt), c["simple_val_scores"])
     assert np.array_equal(Sc.simple_scores_all(tp), c["simple_test_scores"])
-    for e in (0.05, 0.2):
+    for e in (0.05, 0.2) + ((0.0, 1.0, 0.999999) if tag == "a" else ()):
         conds, sizes, _ = Sc.conformal_sets(Sc.aps_score(vp, vt), Sc.aps_cumsums(tp), e)
         assert np.array_equal(conds, c[f"aps_sets_{e}"].astype(bool))
         conds, sizes, _ = Sc.conformal_sets(Sc.simple_score(vp, vt), Sc.simple_scores_all(tp), e)

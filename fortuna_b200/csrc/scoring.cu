@@ -1137,12 +1137,14 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
       float best = -CUDART_INF_F;
       int best_c = 0x7FFFFFFF;
       float sq = 0.0f;
+      bool has_nan = false;  // probs.max(-1) of a row holding a NaN is NaN: the row falls into no bin (classification.py:75-83)
       if ((C & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
         for (int c = lane * 4; c < C; c += 128) {
           const float4 v = *reinterpret_cast<const float4*>(row + c);
           const float pv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            has_nan |= pv[k] != pv[k];
             if (pv[k] > best) {
               best = pv[k];
               best_c = c + k;
@@ -1154,6 +1156,7 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
       } else {
         for (int c = lane; c < C; c += 32) {
           const float p = row[c];
+          has_nan |= p != p;
           if (p > best) {
             best = p;
             best_c = c;
@@ -1172,6 +1175,7 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
           best_c = oc;
         }
       }
+      if (__any_sync(0xffffffffu, has_nan)) best = CUDART_NAN_F;
       if (lane == 0) {
         const int pred = preds ? preds[b] : (best_c == 0x7FFFFFFF ? 0 : best_c);
         int bin = -1;
@@ -1189,7 +1193,7 @@ __global__ void __launch_bounds__(256) ece_bins_kernel(const float* __restrict__
           if (ok) atomicAdd(&s_correct[bin], 1);
         }
         if (ok) atomicAdd(&s_ncorrect, 1);
-        if (targets) atomicAdd(&s_brier, (unsigned long long)((double)sq * 274877906944.0));  // 2^38
+        if (targets && sq == sq) atomicAdd(&s_brier, (unsigned long long)((double)sq * 274877906944.0));  // 2^38 (a NaN has no fixed-point image)
       }
     }
   }

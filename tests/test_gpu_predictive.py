@@ -424,3 +424,32 @@ def test_row_softmax_special_values_follow_the_reference(cuda, C):
         ok = np.isfinite(want)
         np.testing.assert_allclose(got[ok], want[ok], rtol=2e-5, atol=1e-6)
         assert np.array_equal(np.isnan(lse), np.isnan(want_lse)) and np.array_equal(np.isinf(lse), np.isinf(want_lse))
+
+
+@pytest.mark.parametrize("C", [10, 1000])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_log_prob_special_values_follow_the_reference(cuda, C, dtype):
+    """log_prob / ensemble_log_prob keep jsp.special.logsumexp's convention (a non-finite maximum is replaced by 0): a +inf
+    logit makes the other classes' log-likelihood -inf and its own NaN, a -inf target logit -inf, an all -inf sample NaN."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(C)
+    S, B = 6, 96
+    z = P.round_to_bf16((4 * r.standard_normal((S, B, C))).astype(np.float32))
+    t = r.integers(0, C, B).astype(np.int32)
+    z[0, 1, :] = -300.0
+    z[3, 4, C // 3], t[4] = np.inf, C // 3            # the target is the +inf class
+    z[3, 8, C // 3], t[8] = np.inf, (C // 3 + 1) % C  # the target is another class
+    z[4, 5, C // 4], t[5] = -np.inf, C // 4
+    z[4, 9, C // 4], t[9] = -np.inf, (C // 4 + 1) % C
+    z[5, 6, C - 1] = np.nan
+    z[0, 7, :] = -np.inf
+    with np.errstate(all="ignore"):
+        want = {"log_prob": P.cls_log_prob(z, t), "ensemble_log_prob": P.cls_ensemble_log_prob(z, t)}
+    zt = torch.from_numpy(z).to(cuda)
+    got = ops.bma_reduce_cls(zt.to(torch.bfloat16) if dtype == "bf16" else zt, tuple(want), targets=torch.from_numpy(t).to(cuda))
+    for n, w in want.items():
+        g, w = got[n].cpu().numpy(), np.asarray(w, np.float32)
+        assert np.array_equal(np.isnan(g), np.isnan(w)) and np.array_equal(np.isinf(g), np.isinf(w)), n
+        ok = np.isfinite(w)
+        np.testing.assert_allclose(g[ok], w[ok], rtol=1e-5, atol=4e-6, err_msg=n)

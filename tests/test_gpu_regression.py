@@ -150,3 +150,32 @@ def test_regression_temperature_calibration_recovers_variance_scale(cuda):
     status, log_temp = calibrate_temperature(z, y.astype(np.float32), 1000, CalibConfig(
         optimizer=CalibOptimizer(Adam(5e-2), n_epochs=40)), regression=True)
     assert status["loss"][-1] < status["loss"][0] and abs(float(log_temp[0]) - 1.2) < 0.1
+
+
+def test_regression_reductions_special_values(cuda):
+    """inf / NaN means, +-inf and very large log-variances: NaN and inf land where the reference's float32 expressions
+    put them (elementwise maps + max(0, .) that keeps a NaN)."""
+    from fortuna_b200 import ops
+    from oracle import predictive as P
+
+    r = np.random.default_rng(0)
+    S, B, d = 5, 40, 3
+    z = r.standard_normal((S, B, 2 * d)).astype(np.float32)
+    y = r.standard_normal((B, d)).astype(np.float32)
+    z[0, 1, 0] = np.inf
+    z[1, 2, d] = np.inf
+    z[2, 3, d] = -np.inf
+    z[3, 4, 1] = np.nan
+    z[4, 5, d + 1] = 200.0
+    z[0, 6, d + 2] = -200.0
+    z[1, 7, :d] = 1e30
+    with np.errstate(all="ignore"):
+        want = {"mean": P.reg_mean(z), "aleatoric_variance": P.reg_aleatoric_variance(z),
+                "epistemic_variance": P.reg_epistemic_variance(z), "log_prob": P.reg_log_prob(z, y),
+                "ensemble_log_prob": P.reg_ensemble_log_prob(z, y)}
+    got = ops.bma_reduce_reg(torch.from_numpy(z).to(cuda), tuple(want), targets=torch.from_numpy(y).to(cuda))
+    for n, w in want.items():
+        g, w = got[n].cpu().numpy(), np.asarray(w, np.float32)
+        assert np.array_equal(np.isnan(g), np.isnan(w)) and np.array_equal(np.isinf(g), np.isinf(w)), n
+        ok = np.isfinite(w)
+        np.testing.assert_allclose(g[ok], w[ok], rtol=1e-5, atol=1e-6, err_msg=n)

@@ -344,3 +344,33 @@ def test_aps_sets_select_kernel_quantile_equal_to_a_prefix_sum(cuda, C):
         mask, sz = ops.aps_conformal_sets(torch.from_numpy(tp).to(cuda), vs, Sc.conformal_threshold(n_val, error))
         assert np.array_equal(sz.cpu().numpy(), sizes)
         assert np.array_equal(mask.cpu().numpy().astype(bool), conds)
+
+
+def test_ece_bins_rows_with_nan_fall_into_no_bin(cuda):
+    """metric/classification.py:75-83: probs.max(-1) of a row holding a NaN is NaN, and NaN <= threshold is False for
+    every bin - the row is not counted (the oracle's bin index -1).  Also rows sitting exactly on a threshold."""
+    from fortuna_b200 import ops
+    from oracle import predictive as P
+    from oracle import scoring as Sc
+
+    r = np.random.default_rng(1)
+    B, C = 500, 10
+    p = P.softmax((3 * r.standard_normal((B, C))).astype(np.float32))
+    t = r.integers(0, C, B).astype(np.int32)
+    thr = Sc.ece_thresholds(B)
+    p[3] = np.nan
+    p[5, 4] = np.nan
+    p[7] = 0.1
+    p[9] = 0.0
+    p[9, 2] = 1.0
+    p[11] = 0.0
+    p[11, 0], p[11, 1] = thr[4], 1 - thr[4]  # a confidence exactly on a threshold
+    preds = np.where(np.isnan(p).any(1), 0, np.nan_to_num(p).argmax(1)).astype(np.int32)
+    with np.errstate(all="ignore"):
+        counts, confs, accs, idx = Sc.compute_counts_confs_accs(preds, p, t)
+    e = ops.ece_bins(torch.from_numpy(p).to(cuda), torch.from_numpy(t).to(cuda), torch.from_numpy(thr).to(cuda),
+                     preds=torch.from_numpy(preds).to(cuda), want_bin_idx=True)
+    assert np.array_equal(e["counts"].cpu().numpy(), counts) and int(counts.sum()) == B - 2
+    assert np.array_equal(e["bin_idx"].cpu().numpy(), idx) and idx[3] == -1 and idx[5] == -1
+    np.testing.assert_allclose(e["confs"].cpu().numpy(), confs, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(e["accs"].cpu().numpy(), accs, rtol=1e-6)

@@ -977,12 +977,21 @@ __global__ void __launch_bounds__(256) sort_load_kernel(const float* __restrict_
                                                         uint32_t* __restrict__ w) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride)
-    w[i] = i < n ? f32_ordered(x[i] + 0.0f) : 0xFFFFFFFFu;
+  {
+    // NaNs of either sign sort last (lax.sort), in front of the padding only: their key is set explicitly
+    uint32_t key = 0xFFFFFFFFu;
+    if (i < n) {
+      const float v = x[i];
+      key = (v != v) ? 0xFFFFFFFEu : f32_ordered(v + 0.0f);
+    }
+    w[i] = key;
+  }
 }
 __global__ void __launch_bounds__(256) sort_store_kernel(const uint32_t* __restrict__ w, int64_t n,
                                                          float* __restrict__ x) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = f32_unordered(w[i]);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    x[i] = w[i] >= 0xFFFFFFFEu ? CUDART_NAN_F : f32_unordered(w[i]);
 }
 __global__ void __launch_bounds__(256) bitonic_global_step_kernel(uint32_t* __restrict__ w, int64_t n2, int64_t k,
                                                                   int64_t j) {

@@ -374,3 +374,25 @@ def test_ece_bins_rows_with_nan_fall_into_no_bin(cuda):
     assert np.array_equal(e["bin_idx"].cpu().numpy(), idx) and idx[3] == -1 and idx[5] == -1
     np.testing.assert_allclose(e["confs"].cpu().numpy(), confs, rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(e["accs"].cpu().numpy(), accs, rtol=1e-6)
+
+
+def test_sort_and_quantile_with_nan_scores(cuda):
+    """lax.sort puts NaNs (of either sign) last and treats -0 as 0; jnp.quantile of scores holding a NaN is NaN
+    (conformal/regression/quantile.py:89-90 on scores computed from NaN predictions)."""
+    from fortuna_b200 import ops
+    from fortuna_b200.conformal.regression.quantile import conformal_quantile
+    from oracle import scoring as Sc
+
+    s = np.array([0.5, np.nan, 0.25, -1.0, np.inf, -np.inf, 0.0, -0.0, -np.nan], np.float32)
+    x = ops.sort_f32_(torch.from_numpy(s.copy()).to(cuda)).cpu().numpy()
+    assert np.array_equal(x[:7], np.array([-np.inf, -1.0, 0.0, 0.0, 0.25, 0.5, np.inf], np.float32))
+    assert np.isnan(x[7:]).all() and not np.signbit(x[2:4]).any()
+    r = np.random.default_rng(2)
+    for n in (3, 101, 5000):
+        sc = r.random(n).astype(np.float32)
+        want_clean = Sc.conformal_quantile(sc, 0.1)
+        assert float(conformal_quantile(sc, 0.1)) == float(want_clean)
+        sc[n // 2] = np.nan
+        assert np.isnan(float(conformal_quantile(sc, 0.1)))
+        got = ops.sort_f32_(torch.from_numpy(sc.copy()).to(cuda)).cpu().numpy()
+        assert np.array_equal(got[:-1], np.sort(sc)[:-1]) and np.isnan(got[-1])

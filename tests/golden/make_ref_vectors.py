@@ -643,6 +643,54 @@ def gen_calibration_loss():
             put(f"calib/{kind}_loss_{lt}", v)
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# 12. output calibration models: S = 1 predictive maps over given outputs (output_calib_model/predictive/*.py over
+#     prob_output_layer/*.py)
+# --------------------------------------------------------------------------------------------------------------------
+def gen_output_calib_predictive():
+    cm = imp("fortuna.output_calib_model.predictive.classification")
+    rm = imp("fortuna.output_calib_model.predictive.regression")
+    polc = imp("fortuna.prob_output_layer.classification").ClassificationProbOutputLayer()
+    polr = imp("fortuna.prob_output_layer.regression").RegressionProbOutputLayer()
+    RNG = imp("fortuna.utils.random").RandomNumberGenerator
+
+    class StateRepo:
+        def __init__(self, lt):
+            self.s = NS()
+            self.s.params = {"output_calibrator": {"log_temp": J._j(np.array([lt], np.float32))}}
+            self.s.mutable = {"output_calibrator": None}
+
+        def get(self):
+            return self.s
+
+    r = np.random.default_rng(41)
+    z = (2 * r.standard_normal((60, 7))).astype(np.float32)
+    t = r.integers(0, 7, 60).astype(np.int32)
+    o = r.standard_normal((50, 4)).astype(np.float32)
+    y = r.standard_normal((50, 2)).astype(np.float32)
+    key = OP.PRNGKey(77)
+    for k, v in dict(logits=z, targets=t, outputs=o, y=y, key=key, log_temp=np.float32(0.35)).items():
+        put("ocal/" + k, v)
+    pc = cm.ClassificationPredictive(output_calib_manager=ClsTemperature(), prob_output_layer=polc)
+    pc.state = StateRepo(0.35)
+    for cal in (False, True):
+        pre = f"ocal/cls_{int(cal)}/"
+        for m in ("mean", "mode", "variance", "std", "entropy"):
+            put(pre + m, getattr(pc, m)(J._j(z), calibrated=cal))
+        put(pre + "log_prob", pc.log_prob(J._j(z), J._j(t), calibrated=cal))
+        put(pre + "sample", pc.sample(9, J._j(z), rng=J._j(key), calibrated=cal))
+    pr = rm.RegressionPredictive(output_calib_manager=RegTemperature(), prob_output_layer=polr)
+    pr.state = StateRepo(0.35)
+    for cal in (False, True):
+        pre = f"ocal/reg_{int(cal)}/"
+        for m in ("mean", "mode", "variance", "std"):
+            put(pre + m, getattr(pr, m)(J._j(o), calibrated=cal))
+        put(pre + "log_prob", pr.log_prob(J._j(o), J._j(y), calibrated=cal))
+        put(pre + "sample", pr.sample(6, J._j(o), rng=J._j(key), calibrated=cal))
+        put(pre + "entropy", pr.entropy(J._j(o), calibrated=cal, n_target_samples=6, rng=J._j(key)))
+        put(pre + "quantile", pr.quantile([0.1, 0.9], J._j(o), n_samples=6, rng=J._j(key), calibrated=cal))
+
+
 def logging_off():
     import logging
 
@@ -661,6 +709,7 @@ def main():
     gen_conformal_bayes()
     gen_conformal_regression()
     gen_calibration_loss()
+    gen_output_calib_predictive()
     path = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **OUT)
     print(f"wrote {path}: {len(OUT)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")

@@ -410,3 +410,47 @@ def test_calibration_loss_with_ensemble_outputs(cuda):
         np.testing.assert_allclose(loss, c[f"cls_loss_{lt}"], rtol=1e-5)
         loss, _ = loss_and_grad(t(c["outputs"]), t(c["y"]), np.float32(lt), n_data=n_data, regression=True)
         np.testing.assert_allclose(loss, c[f"reg_loss_{lt}"], rtol=1e-5)
+
+
+def test_output_calibration_predictive_maps(cuda):
+    """OutputCalibClassifier / OutputCalibRegressor predictives on given outputs against the reference source's
+    (output_calib_model/predictive/* over prob_output_layer/*), uncalibrated and with a temperature put into the state."""
+    from fortuna_b200.output_calib_model import OutputCalibClassifier, OutputCalibRegressor
+    from fortuna_b200.output_calib_model.output_calib_state_repository import OutputCalibStateRepository
+    from fortuna_b200.output_calib_model.state import OutputCalibState
+
+    c = case("ocal/")
+    key = dev_key(c["key"], cuda)
+
+    def with_temperature(model):
+        repo = OutputCalibStateRepository()
+        repo.put(OutputCalibState.init({"output_calibrator": {"params": {"log_temp": np.array([c["log_temp"]], np.float32)}}}))
+        model.predictive.state = repo
+        return model
+
+    mc, mr = with_temperature(OutputCalibClassifier()), with_temperature(OutputCalibRegressor())
+    got = lambda t: t.cpu().numpy()
+    for cal in (0, 1):
+        p, pre = mc.predictive, f"cls_{cal}/"
+        np.testing.assert_allclose(got(p.mean(c["logits"], calibrated=bool(cal))), c[pre + "mean"], rtol=2e-5, atol=1e-8)
+        assert np.array_equal(got(p.mode(c["logits"], calibrated=bool(cal))), c[pre + "mode"])
+        np.testing.assert_allclose(got(p.variance(c["logits"], calibrated=bool(cal))), c[pre + "variance"], rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(got(p.std(c["logits"], calibrated=bool(cal))), c[pre + "std"], rtol=2e-5, atol=2e-4)
+        np.testing.assert_allclose(got(p.entropy(c["logits"], calibrated=bool(cal))), c[pre + "entropy"], rtol=1e-5, atol=4e-6)
+        np.testing.assert_allclose(got(p.log_prob(c["logits"], c["targets"], calibrated=bool(cal))), c[pre + "log_prob"],
+                                   rtol=1e-5, atol=2e-6)
+        smp = got(p.sample(9, c["logits"], rng=key, calibrated=bool(cal)))
+        assert smp.shape == c[pre + "sample"].shape and (smp != c[pre + "sample"]).mean() <= 0.01
+        p, pre = mr.predictive, f"reg_{cal}/"
+        np.testing.assert_allclose(got(p.mean(c["outputs"], calibrated=bool(cal))), c[pre + "mean"], rtol=1e-6)
+        np.testing.assert_allclose(got(p.mode(c["outputs"], calibrated=bool(cal))), c[pre + "mode"], rtol=1e-6)
+        np.testing.assert_allclose(got(p.variance(c["outputs"], calibrated=bool(cal))), c[pre + "variance"], rtol=2e-5)
+        np.testing.assert_allclose(got(p.std(c["outputs"], calibrated=bool(cal))), c[pre + "std"], rtol=2e-5)
+        np.testing.assert_allclose(got(p.log_prob(c["outputs"], c["y"], calibrated=bool(cal))), c[pre + "log_prob"], rtol=2e-5,
+                                   atol=2e-6)
+        np.testing.assert_allclose(got(p.sample(6, c["outputs"], rng=key, calibrated=bool(cal))), c[pre + "sample"], rtol=1e-5,
+                                   atol=2e-6)
+        np.testing.assert_allclose(got(p.entropy(c["outputs"], n_target_samples=6, rng=key, calibrated=bool(cal))),
+                                   c[pre + "entropy"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(got(p.quantile([0.1, 0.9], c["outputs"], n_samples=6, rng=key, calibrated=bool(cal))),
+                                   c[pre + "quantile"], rtol=1e-5, atol=2e-6)

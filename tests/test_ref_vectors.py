@@ -379,3 +379,32 @@ def test_committed_vectors_are_what_the_reference_source_produces(tmp_path):
     assert sorted(new.files) == sorted(REF.files)
     for k in REF.files:
         assert new[k].dtype == REF[k].dtype and np.array_equal(new[k], REF[k], equal_nan=True), k
+
+
+def test_output_calibration_predictive_maps():
+    """output_calib_model/predictive/* over prob_output_layer/*: the S = 1 maps on given outputs, uncalibrated and under
+    the temperature scalers, including the per-row target draws of ClassificationProbOutputLayer.sample."""
+    from oracle import output_calib as Oc
+
+    c = case("ocal/")
+    lt = np.float32(c["log_temp"])
+    for cal in (0, 1):
+        ltc = lt if cal else None
+        z = c["logits"] if not cal else (c["logits"] * np.exp(-lt, dtype=np.float32)).astype(np.float32)
+        p = P.softmax(z)
+        assert np.array_equal(p, c[f"cls_{cal}/mean"]) and np.array_equal(p.argmax(-1), c[f"cls_{cal}/mode"])
+        assert np.array_equal((p * (1 - p)).astype(np.float32), c[f"cls_{cal}/variance"])
+        assert np.array_equal(np.sqrt(p * (1 - p), dtype=np.float32), c[f"cls_{cal}/std"])
+        np.testing.assert_allclose(P.cls_entropy(z[None]), c[f"cls_{cal}/entropy"], rtol=2e-6, atol=5e-7)
+        assert np.array_equal(P.cls_ensemble_log_prob(z[None], c["targets"])[0], c[f"cls_{cal}/log_prob"])
+        assert np.array_equal(Oc.cls_output_sample(c["logits"], c["key"], 9, ltc), c[f"cls_{cal}/sample"])
+        o = c["outputs"] if not cal else P.reg_calibrate(c["outputs"][None], lt)[0]
+        mu, lv = P.reg_split(o)
+        assert np.array_equal(mu, c[f"reg_{cal}/mean"]) and np.array_equal(mu, c[f"reg_{cal}/mode"])
+        assert np.array_equal(np.exp(lv, dtype=np.float32), c[f"reg_{cal}/variance"])
+        np.testing.assert_allclose(np.sqrt(np.exp(lv, dtype=np.float32)), c[f"reg_{cal}/std"], rtol=2e-7)
+        np.testing.assert_allclose(P.reg_ensemble_log_prob(o[None], c["y"])[0], c[f"reg_{cal}/log_prob"], rtol=2e-6, atol=1e-6)
+        smp = Oc.reg_output_sample(c["outputs"], c["key"], 6, ltc)
+        assert np.array_equal(smp, c[f"reg_{cal}/sample"])
+        np.testing.assert_allclose(Oc.reg_output_entropy(c["outputs"], c["key"], 6, ltc), c[f"reg_{cal}/entropy"], rtol=5e-6, atol=2e-6)
+        np.testing.assert_allclose(P.quantile_axis0(smp, [0.1, 0.9]), c[f"reg_{cal}/quantile"], rtol=1e-6, atol=1e-7)

@@ -25,14 +25,17 @@ Parity status (also in DESIGN.md section 4):
               sgmcmc_posterior.py, sghmc_integrator.py, cyclical_sgld_integrator.py,
               sgmcmc_preconditioner.py, sgmcmc_step_schedule.py, sgmcmc_diagnostic.py,
               utils/random.py, utils/training.py, conformal/classification/*,
-              conformal/multivalid/*, metric/classification.py) and runs them over a
+              conformal/regression/*, conformal/multivalid/*, metric/classification.py,
+              loss/*, output_calib_model/predictive/*) and runs them over a
               numpy stand-in for jax (tests/golden/jax_standin.py: float32
               promotions derived by rule, jax.random bound to the KAT-pinned
               threefry).  tests/test_ref_vectors.py: sampler trajectories
               (parameters, momentum, second moments, key chain), predictive
               mean / mode / variances / std / log-probs, stored-sample draws,
               APS and simple scores, conformal and credible sets, ECE bins,
-              MaxCov patches are BIT-EQUAL to the reference source's results;
+              MaxCov patches, conformal-regression quantiles and intervals, the
+              output-calibration predictive maps and target draws are BIT-EQUAL
+              to the reference source's results;
               entropies, Brier / ECE values, KSD / ESS, multivalid runs agree to a
               few float32 ulps (a jnp.sum over many terms has no single order).
               This pins everything written in the reference's .py files: control

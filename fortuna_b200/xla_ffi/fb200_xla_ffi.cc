@@ -516,6 +516,140 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_ess, Ess,
                               ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Ret<F32>().Attr<int32_t>("use_threshold")
                                   .Attr<float>("threshold"));
 
+// ================================================================================================ the rows of SURVEY 8(f)
+// clip_grandients_by_norm's multiplier (utils/training.py:14-20): min(1, max_norm / (1e-7 + ||g||)); ws: float64 scratch
+static ffi::Error GradClipMult(cudaStream_t s, Any grad, RF64 ws, RF32 mult, float max_grad_norm) {
+  const int dt = DTypeOf(grad);
+  if (dt < 0) return BadDType("grad");
+  return Check(fb200_grad_clip_mult(grad.untyped_data(), dt, nullptr, nullptr, static_cast<int64_t>(grad.element_count()),
+                                    max_grad_norm, ws->typed_data(), mult->typed_data(), s),
+               "fb200_grad_clip_mult");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_grad_clip_mult, GradClipMult,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Ret<F64>().Ret<F32>().Attr<float>("max_grad_norm"));
+
+// Predictive.sample for regression (predictive/base.py:407-441, prob_output_layer/regression.py:38-52)
+static ffi::Error RegSampleTargets(cudaStream_t s, F32 outputs, F32 log_temp, U32 key, RF32 y, RS32 idx) {
+  return Check(fb200_reg_sample_targets(outputs.typed_data(), Opt(log_temp), key.typed_data(), Dim(*y, 0), Dim(outputs, 0),
+                                        Dim(outputs, 1), Dim(outputs, 2) / 2, y->typed_data(), Opt(idx), s),
+               "fb200_reg_sample_targets");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_reg_sample_targets, RegSampleTargets,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<U32>().Ret<F32>().Ret<S32>());
+
+// RegressionPredictive.entropy / aleatoric_entropy / epistemic_entropy (predictive/regression.py:51-267)
+static ffi::Error RegMcEntropies(cudaStream_t s, F32 outputs, F32 log_temp, S32 sample_idx, U32 target_keys, RF32 ent,
+                                 RF32 alea, RF32 epi, int32_t n_target_samples) {
+  return Check(fb200_reg_mc_entropies(outputs.typed_data(), Opt(log_temp), sample_idx.typed_data(), target_keys.typed_data(),
+                                      Dim(outputs, 0), Dim(sample_idx, 0), n_target_samples, Dim(outputs, 1),
+                                      Dim(outputs, 2) / 2, Opt(ent), Opt(alea), Opt(epi), s),
+               "fb200_reg_mc_entropies");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_reg_mc_entropies, RegMcEntropies,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<S32>().Arg<U32>().Ret<F32>().Ret<F32>()
+                                  .Ret<F32>().Attr<int32_t>("n_target_samples"));
+
+// output_calib_model Predictive.sample (output_calib_model/predictive/base.py:69-105) for both output layers
+static ffi::Error ClsOutputSampleTargets(cudaStream_t s, F32 logits, F32 log_temp, U32 key, RS32 y) {
+  return Check(fb200_cls_output_sample_targets(logits.typed_data(), Opt(log_temp), key.typed_data(), Dim(*y, 0),
+                                               Dim(logits, 0), Dim(logits, 1), y->typed_data(), s),
+               "fb200_cls_output_sample_targets");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_cls_output_sample_targets, ClsOutputSampleTargets,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<U32>().Ret<S32>());
+static ffi::Error RegOutputSampleTargets(cudaStream_t s, F32 outputs, F32 log_temp, U32 key, RF32 y) {
+  return Check(fb200_reg_output_sample_targets(outputs.typed_data(), Opt(log_temp), key.typed_data(), Dim(*y, 0),
+                                               Dim(outputs, 0), Dim(outputs, 1) / 2, y->typed_data(), s),
+               "fb200_reg_output_sample_targets");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_reg_output_sample_targets, RegOutputSampleTargets,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<U32>().Ret<F32>());
+
+// ClassificationPredictive.conformal_set by importance sampling (predictive/classification.py:485-626)
+static ffi::Error ConformalBayesSets(cudaStream_t s, F32 ell_train, F32 lsm_test, RU8 ws, RU8 region, RS32 sizes,
+                                     RS32 rank_counts, RF32 ess, float threshold) {
+  return Check(fb200_conformal_bayes_sets(ell_train.typed_data(), lsm_test.typed_data(), Dim(ell_train, 0), Dim(ell_train, 1),
+                                          Dim(lsm_test, 1), Dim(lsm_test, 2), threshold, ws->typed_data(), ws->size_bytes(),
+                                          region->typed_data(), Opt(sizes), Opt(rank_counts), Opt(ess), s),
+               "fb200_conformal_bayes_sets");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_conformal_bayes_sets, ConformalBayesSets,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Ret<U8>().Ret<U8>().Ret<S32>().Ret<S32>()
+                                  .Ret<F32>().Attr<float>("threshold"));
+
+// calibration loss with ensemble outputs (predictive/base.py:205-287): per-sample log-likelihood sums and derivatives
+static ffi::Error CalibClsLossTerms(cudaStream_t s, Any logits, S32 targets, F32 log_temp, RU8 ws, RF64 out) {
+  const int dt = DTypeOf(logits);
+  if (dt < 0) return BadDType("logits");
+  return Check(fb200_calib_cls_loss_terms(logits.untyped_data(), dt, targets.typed_data(), Opt(log_temp), Dim(logits, 0),
+                                          Dim(logits, 1), Dim(logits, 2), ws->typed_data(), ws->size_bytes(),
+                                          out->typed_data(), s),
+               "fb200_calib_cls_loss_terms");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_calib_cls_loss_terms, CalibClsLossTerms,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<Any>().Arg<S32>().Arg<F32>().Ret<U8>().Ret<F64>());
+static ffi::Error CalibRegLossTerms(cudaStream_t s, F32 outputs, F32 targets, F32 log_temp, RU8 ws, RF64 out) {
+  return Check(fb200_calib_reg_loss_terms(outputs.typed_data(), targets.typed_data(), Opt(log_temp), Dim(outputs, 0),
+                                          Dim(outputs, 1), Dim(outputs, 2) / 2, ws->typed_data(), ws->size_bytes(),
+                                          out->typed_data(), s),
+               "fb200_calib_reg_loss_terms");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_calib_reg_loss_terms, CalibRegLossTerms,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Ret<U8>().Ret<F64>());
+
+// calibration-model loss heads (loss/classification/focal_loss.py, loss/regression/scaled_mse.py) with their gradients,
+// and optax.adam over a flat parameter vector (calib_model/config/optimizer.py:20)
+static ffi::Error FocalLossGrad(cudaStream_t s, F32 logits, S32 targets, RF32 grad, RF32 loss_rows, RF64 loss_mean,
+                                float gamma) {
+  return Check(fb200_focal_loss_grad(logits.typed_data(), targets.typed_data(), Dim(logits, 0), Dim(logits, 1), gamma,
+                                     Opt(grad), loss_rows->typed_data(), loss_mean->typed_data(), s),
+               "fb200_focal_loss_grad");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_focal_loss_grad, FocalLossGrad,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<S32>().Ret<F32>().Ret<F32>().Ret<F64>()
+                                  .Attr<float>("gamma"));
+static ffi::Error ScaledMseLossGrad(cudaStream_t s, F32 outputs, F32 targets, RF32 grad, RF32 loss_terms, RF64 loss_mean) {
+  return Check(fb200_scaled_mse_loss_grad(outputs.typed_data(), targets.typed_data(), Dim(outputs, 0), Dim(outputs, 1) / 2,
+                                          Opt(grad), loss_terms->typed_data(), loss_mean->typed_data(), s),
+               "fb200_scaled_mse_loss_grad");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_scaled_mse_loss_grad, ScaledMseLossGrad,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Ret<F32>().Ret<F32>().Ret<F64>());
+// params / mu / nu are donated operands aliased to the results (input_output_aliases on the jax side)
+static ffi::Error AdamStep(cudaStream_t s, F32 params, F32 grads, F32 mu, F32 nu, RF32 params_out, RF32 mu_out, RF32 nu_out,
+                           float lr, float b1, float b2, float eps, float c1, float c2) {
+  const size_t bytes = params.size_bytes();
+  CopyIfNotAliased(params.typed_data(), params_out->typed_data(), bytes, s);
+  CopyIfNotAliased(mu.typed_data(), mu_out->typed_data(), bytes, s);
+  CopyIfNotAliased(nu.typed_data(), nu_out->typed_data(), bytes, s);
+  return Check(fb200_adam_step_f32(params_out->typed_data(), grads.typed_data(), mu_out->typed_data(), nu_out->typed_data(),
+                                   static_cast<int64_t>(params.element_count()), lr, b1, b2, eps, c1, c2, s),
+               "fb200_adam_step_f32");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_adam_step, AdamStep,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Ret<F32>().Ret<F32>()
+                                  .Ret<F32>().Attr<float>("lr").Attr<float>("b1").Attr<float>("b2").Attr<float>("eps")
+                                  .Attr<float>("c1").Attr<float>("c2"));
+
+// MaxCoverageFixedPrecisionBinaryClassificationCalibrator (conformal/classification/maxcovfixprec_binary_classfication.py)
+static ffi::Error MaxcovCounts(cudaStream_t s, F32 probs, S32 targets, F32 taus, RU8 ws, RS32 counts, RS32 labels,
+                               int32_t side, float threshold) {
+  return Check(fb200_maxcov_counts(probs.typed_data(), targets.typed_data(), static_cast<int64_t>(probs.element_count()),
+                                   taus.typed_data(), Dim(taus, 0), side, threshold, ws->typed_data(), ws->size_bytes(),
+                                   counts->typed_data(), labels->typed_data(), s),
+               "fb200_maxcov_counts");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_maxcov_counts, MaxcovCounts,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Arg<S32>().Arg<F32>().Ret<U8>().Ret<S32>().Ret<S32>()
+                                  .Attr<int32_t>("side").Attr<float>("threshold"));
+static ffi::Error MaxcovApplyPatches(cudaStream_t s, F32 probs, RF32 out, float tau_pos, float tau_neg) {
+  return Check(fb200_maxcov_apply_patches(probs.typed_data(), static_cast<int64_t>(probs.element_count()), tau_pos, tau_neg,
+                                          out->typed_data(), s),
+               "fb200_maxcov_apply_patches");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fb200_xla_maxcov_apply_patches, MaxcovApplyPatches,
+                              ffi::Ffi::Bind().Ctx<Stream>().Arg<F32>().Ret<F32>().Attr<float>("tau_pos").Attr<float>("tau_neg"));
+
 #else
 #error "xla/ffi/api/ffi.h not found: add jaxlib's include directory (or, for the syntax check only, fortuna_b200/xla_ffi/mock)"
 #endif

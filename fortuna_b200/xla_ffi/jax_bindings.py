@@ -61,6 +61,19 @@ _TARGETS = (
     "fb200_xla_cls_sample_targets",
     "fb200_xla_ksd_imq",
     "fb200_xla_ess",
+    "fb200_xla_grad_clip_mult",
+    "fb200_xla_reg_sample_targets",
+    "fb200_xla_reg_mc_entropies",
+    "fb200_xla_cls_output_sample_targets",
+    "fb200_xla_reg_output_sample_targets",
+    "fb200_xla_conformal_bayes_sets",
+    "fb200_xla_calib_cls_loss_terms",
+    "fb200_xla_calib_reg_loss_terms",
+    "fb200_xla_focal_loss_grad",
+    "fb200_xla_scaled_mse_loss_grad",
+    "fb200_xla_adam_step",
+    "fb200_xla_maxcov_counts",
+    "fb200_xla_maxcov_apply_patches",
 )
 _registered = False
 

@@ -85,11 +85,32 @@ class RegressionPredictive:
     def epistemic_variance(self, inputs_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
         return self._reduce(inputs_loader, ("epistemic_variance",), n_posterior_samples, rng)["epistemic_variance"]
 
-    def variance(self, inputs_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
-        return self._reduce(inputs_loader, ("variance",), n_posterior_samples, rng)["variance"]
+    def variance(self, inputs_loader, n_posterior_samples: int = 30, aleatoric_variances=None, epistemic_variances=None,
+                 rng=None, distribute: bool = True):
+        """predictive/base.py:838-898 (inherited by RegressionPredictive): ``variance = aleatoric + epistemic`` where each
+        term, unless given, is estimated from ITS OWN draws - ``rng, key = split(rng)`` before the aleatoric term and again
+        before the epistemic one."""
+        if rng is None:
+            rng = self.posterior.rng.get()
+        if aleatoric_variances is None:
+            ks = ops.split(rng, 2)
+            rng, key = ks[0].contiguous(), ks[1].contiguous()
+            aleatoric_variances = self.aleatoric_variance(inputs_loader, n_posterior_samples, rng=key)
+        if epistemic_variances is None:
+            ks = ops.split(rng, 2)
+            rng, key = ks[0].contiguous(), ks[1].contiguous()
+            epistemic_variances = self.epistemic_variance(inputs_loader, n_posterior_samples, rng=key)
+        dev = self.posterior.bound.device
+        a = torch.as_tensor(aleatoric_variances, dtype=torch.float32, device=dev).contiguous()
+        e = torch.as_tensor(epistemic_variances, dtype=torch.float32, device=dev).contiguous()
+        return ops.variance_combine(a, e)
 
-    def std(self, inputs_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
-        return self._reduce(inputs_loader, ("std",), n_posterior_samples, rng)["std"]
+    def std(self, inputs_loader, n_posterior_samples: int = 30, variances=None, rng=None, distribute: bool = True):
+        """predictive/base.py:900-944: ``sqrt(variance)``, the variance estimated as above unless given."""
+        if variances is None:
+            variances = self.variance(inputs_loader, n_posterior_samples, rng=rng)
+        v = torch.as_tensor(variances, dtype=torch.float32, device=self.posterior.bound.device).contiguous()
+        return ops.variance_combine(v, None, want_std=True)
 
     def log_prob(self, data_loader, n_posterior_samples: int = 30, rng=None, distribute: bool = True):
         return self._reduce(data_loader, ("log_prob",), n_posterior_samples, rng, self._targets(data_loader))["log_prob"]

@@ -98,6 +98,27 @@ class ProbRegressor:
             self.posterior.save_state(self.posterior.state.checkpoint_dir)
         return status
 
+    def attach_posterior_samples(self, samples: torch.Tensor, freeze_fun=None, steps=None) -> None:
+        """Make ``samples`` - float32 [n_samples, N_trainable], rows in the flat parameter layout of ``utils.flat_tree`` over
+        the leaves ``freeze_fun`` keeps trainable - the posterior of this model without running a fit here (chains that ran
+        elsewhere).  The in-memory sibling of ``load_state``; same contract as ``ProbClassifier.attach_posterior_samples``."""
+        from .posterior.sgmcmc.sgmcmc_posterior_state_repository import SGMCMCPosteriorStateRepository
+
+        self.model.to(self.device)
+        bound = BoundModel(self.model, self.device, freeze_fun=freeze_fun)
+        n, width = samples.shape
+        if width != bound.params.flat.numel():
+            raise ValueError(f"samples have {width} parameters per row, the trainable tree has {bound.params.flat.numel()}")
+        cls = SGHMCPosterior if isinstance(self.posterior_approximator, SGHMCPosteriorApproximator) else CyclicalSGLDPosterior
+        self.posterior = cls(bound, self.prior, self.posterior_approximator, self.rng)
+        self.posterior.log_likelihood_sum = gaussian_log_likelihood_sum
+        repo = SGMCMCPosteriorStateRepository(n, template=bound.params)
+        repo.bank.copy_(samples.to(device=self.device, dtype=torch.float32))
+        repo._filled = [True] * n
+        repo.steps = list(steps) if steps is not None else list(range(n))
+        self.posterior.state = repo
+        self.predictive = self._predictive_cls(self.posterior)
+
     # ------------------------------------------------------------------ state on disk (fortuna/prob_model/base.py:236-261)
     def load_state(self, checkpoint_path) -> None:
         """Load posterior samples from a checkpoint directory in the reference's layout (``<dir>/c`` chain state,

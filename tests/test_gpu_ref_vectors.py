@@ -454,3 +454,45 @@ def test_output_calibration_predictive_maps(cuda):
                                    c[pre + "entropy"], rtol=2e-5, atol=2e-5)
         np.testing.assert_allclose(got(p.quantile([0.1, 0.9], c["outputs"], n_samples=6, rng=key, calibrated=bool(cal))),
                                    c[pre + "quantile"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_regression_predictive_api(cuda, tag):
+    """The regression predictive through ``ProbRegressor.predictive.*`` with the fixture's stored samples attached (the
+    whole network is the Dense layer of the fixture), key and loader batches - against the reference source's outputs."""
+    from fortuna_b200.data import DataLoader, InputsLoader
+    from fortuna_b200.prob_model import ProbRegressor, SGHMCPosteriorApproximator
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    c = case(f"reg_{tag}/")
+    n, D, two_d = c["W"].shape
+    S, T, bs = int(c["S"]), int(c["T"]), int(c["sizes"][0])
+    pm = ProbRegressor(model=torch.nn.Linear(D, two_d), posterior_approximator=SGHMCPosteriorApproximator(n_samples=n),
+                       output_calibrator=None, seed=0, device=cuda)
+    tmpl = FlatTree.from_shapes({"model": {"params": {"bias": (two_d,), "weight": (two_d, D)}}}, device="cpu")
+    ob, ow = tmpl.offsets
+    bank = np.zeros((n, tmpl.flat.numel()), np.float32)
+    bank[:, ob : ob + two_d] = c["b"]
+    bank[:, ow : ow + two_d * D] = c["W"].transpose(0, 2, 1).reshape(n, -1)
+    pm.attach_posterior_samples(torch.from_numpy(bank).to(cuda))
+    if not np.isnan(c["log_temp"]):
+        pm.predictive.log_temp = torch.tensor([float(c["log_temp"])], device=cuda)
+    inputs = InputsLoader.from_array_inputs(c["x"], batch_size=bs)
+    data = DataLoader.from_array_data((c["x"], c["y"]), batch_size=bs)
+    one = InputsLoader.from_array_inputs(c["x"])
+    key = dev_key(c["key"], cuda)
+    p, got = pm.predictive, (lambda t: t.cpu().numpy())
+    np.testing.assert_allclose(got(p.mean(inputs, S, rng=key)), c["mean"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got(p.mode(inputs, S, rng=key)), c["mode"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got(p.aleatoric_variance(inputs, S, rng=key)), c["aleatoric_variance"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(got(p.epistemic_variance(inputs, S, rng=key)), c["epistemic_variance"], rtol=1e-5,
+                               atol=4e-7 * float(np.abs(c["mean"]).max()) ** 2 + 1e-7)
+    np.testing.assert_allclose(got(p.log_prob(data, S, rng=key)), c["log_prob"], rtol=1e-5, atol=4e-6)
+    np.testing.assert_allclose(got(p.ensemble_log_prob(data, S, rng=key)), c["ensemble_log_prob"], rtol=1e-5, atol=4e-6)
+    np.testing.assert_allclose(got(p.variance(inputs, S, rng=key)), c["variance"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got(p.std(inputs, S, rng=key)), c["std"], rtol=1e-5, atol=1e-6)
+    skey = dev_key(c["sample_key"], cuda)
+    np.testing.assert_allclose(got(p.sample(one, T, rng=skey)), c["sample"], rtol=1e-5, atol=4e-6)
+    np.testing.assert_allclose(got(p.quantile([0.05, 0.5, 0.95], one, T, rng=skey)), c["quantile"], rtol=1e-5, atol=4e-6)
+    for name in ("entropy", "aleatoric_entropy", "epistemic_entropy"):
+        np.testing.assert_allclose(got(getattr(p, name)(one, S, T, rng=key)), c[name], rtol=2e-5, atol=8e-6, err_msg=name)

@@ -381,6 +381,15 @@ def gen_scoring():
                 for i, s in enumerate(sets):
                     mask[i, s] = 1
                 put(pre + f"{kind}_sets_{e}", mask)
+        if tag == "a":  # CV+ variants: two folds (conformal/classification/base.py:92-132)
+            h = nv // 2
+            for kind, cl in (("aps", aps.CVPlusAdaptivePredictionConformalClassifier()),
+                             ("simple", simple.CVPlusSimplePredictionConformalClassifier())):
+                sets = cl.conformal_set([jvp[:h], jvp[h:]], [jvt[:h], jvt[h:]], [jtp[: nt // 2], jtp[nt // 2 :]], error=0.1)
+                mask = np.zeros((nt, C), np.uint8)
+                for i, s_ in enumerate(sets):
+                    mask[i, s_] = 1
+                put(pre + f"cvplus_{kind}_sets_0.1", mask)
         preds = vp.argmax(-1).astype(np.int32)
         jpreds = J._j(preds)
         counts, confs, accs = met.compute_counts_confs_accs(jpreds, jvp, jvt)

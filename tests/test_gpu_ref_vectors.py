@@ -496,3 +496,42 @@ def test_regression_predictive_api(cuda, tag):
     np.testing.assert_allclose(got(p.quantile([0.05, 0.5, 0.95], one, T, rng=skey)), c["quantile"], rtol=1e-5, atol=4e-6)
     for name in ("entropy", "aleatoric_entropy", "epistemic_entropy"):
         np.testing.assert_allclose(got(getattr(p, name)(one, S, T, rng=key)), c[name], rtol=2e-5, atol=8e-6, err_msg=name)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_conformal_classifier_and_metric_apis(cuda, tag):
+    """The mirror classes / functions a user of the reference calls - ``AdaptivePredictionConformalClassifier`` /
+    ``SimplePredictionConformalClassifier`` (and their CV+ variants) ``.conformal_set``, ``fortuna.metric.classification.*`` -
+    against the reference source's results on the same arrays."""
+    from fortuna_b200.conformal import (AdaptivePredictionConformalClassifier, CVPlusAdaptivePredictionConformalClassifier,
+                                        CVPlusSimplePredictionConformalClassifier, SimplePredictionConformalClassifier)
+    from fortuna_b200.metric import classification as M
+
+    c = case(f"score_{tag}/")
+    vp, tp, vt = c["val_probs"], c["test_probs"], c["val_targets"]
+    nt, C = tp.shape
+
+    def as_mask(sets):
+        m = np.zeros((nt, C), bool)
+        for i, s_ in enumerate(sets):
+            m[i, list(s_)] = True
+        return m
+
+    for kind, cls in (("aps", AdaptivePredictionConformalClassifier), ("simple", SimplePredictionConformalClassifier)):
+        for e in (0.05, 0.2):
+            assert np.array_equal(as_mask(cls().conformal_set(vp, vt, tp, error=e)), c[f"{kind}_sets_{e}"].astype(bool)), (kind, e)
+    if tag == "a":
+        h, nv = vp.shape[0] // 2, vp.shape[0]
+        for kind, cls in (("aps", CVPlusAdaptivePredictionConformalClassifier), ("simple", CVPlusSimplePredictionConformalClassifier)):
+            sets = cls().conformal_set([vp[:h], vp[h:]], [vt[:h], vt[h:]], [tp[: nt // 2], tp[nt // 2 :]], error=0.1)
+            assert np.array_equal(as_mask(sets), c[f"cvplus_{kind}_sets_0.1"].astype(bool)), kind
+    preds = vp.argmax(-1).astype(np.int32)
+    f = lambda t: np.asarray(t.cpu().numpy() if hasattr(t, "cpu") else t)
+    counts, confs, accs = M.compute_counts_confs_accs(preds, vp, vt)
+    assert np.array_equal(f(counts).astype(np.int64), c["ece_counts"].astype(np.int64))
+    np.testing.assert_allclose(f(confs), c["ece_confs"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(f(accs), c["ece_accs"], rtol=1e-6)
+    np.testing.assert_allclose(float(f(M.expected_calibration_error(preds, vp, vt))), c["ece"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(float(f(M.maximum_calibration_error(preds, vp, vt))), c["mce"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(float(f(M.accuracy(preds, vt))), c["accuracy"], rtol=1e-6)
+    np.testing.assert_allclose(float(f(M.brier_score(vp, vt))), c["brier"], rtol=1e-5)

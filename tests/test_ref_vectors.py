@@ -204,6 +204,13 @@ def test_scores_sets_and_calibration_metrics(tag):
         # the literal [n_val, n_test, C] broadcast and the rank-count form give the same sets
         assert np.array_equal(Sc.conformal_conds_literal(Sc.aps_score(vp, vt), Sc.aps_cumsums(tp), e),
                               c[f"aps_sets_{e}"].astype(bool))
+    if tag == "a":  # CV+: scores of the folds concatenated (conformal/classification/base.py:111-132)
+        h, nt = vp.shape[0] // 2, tp.shape[0]
+        for kind, sfn, afn in (("aps", Sc.aps_score, Sc.aps_cumsums), ("simple", Sc.simple_score, Sc.simple_scores_all)):
+            val = np.concatenate([sfn(vp[:h], vt[:h]), sfn(vp[h:], vt[h:])])
+            test = np.concatenate([afn(tp[: nt // 2]), afn(tp[nt // 2 :])], axis=0)
+            conds, _, _ = Sc.conformal_sets(val, test, 0.1)
+            assert np.array_equal(conds, c[f"cvplus_{kind}_sets_0.1"].astype(bool)), kind
     preds = vp.argmax(-1).astype(np.int32)
     counts, confs, accs, _ = Sc.compute_counts_confs_accs(preds, vp, vt)
     assert np.array_equal(counts, c["ece_counts"])

@@ -755,6 +755,9 @@ REAL_MODULES = (
     "fortuna.conformal.multivalid.one_shot.classification.binary_multicalibrator",
     "fortuna.conformal.multivalid.one_shot.classification.top_label_multicalibrator",
     "fortuna.conformal.classification.maxcovfixprec_binary_classfication",
+    "fortuna.prob_model.posterior.sgmcmc.sgmcmc_sampling_callback",
+    "fortuna.prob_model.posterior.sgmcmc.sghmc.sghmc_callback",
+    "fortuna.prob_model.posterior.sgmcmc.cyclical_sgld.cyclical_sgld_callback",
     "fortuna.output_calib_model.predictive.base",
     "fortuna.output_calib_model.predictive.classification",
     "fortuna.output_calib_model.predictive.regression",

@@ -700,6 +700,55 @@ def gen_output_calib_predictive():
         put(pre + "quantile", pr.quantile([0.1, 0.9], J._j(o), n_samples=6, rng=J._j(key), calibrated=cal))
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# 13. which training steps store a posterior sample (sghmc_callback.py, cyclical_sgld_callback.py,
+#     sgmcmc_sampling_callback.py)
+# --------------------------------------------------------------------------------------------------------------------
+def gen_sampling_callbacks():
+    sg = imp("fortuna.prob_model.posterior.sgmcmc.sghmc.sghmc_callback")
+    cy = imp("fortuna.prob_model.posterior.sgmcmc.cyclical_sgld.cyclical_sgld_callback")
+
+    class Trainer:
+        def _sync_state(self, state):
+            return state
+
+    class Repo:
+        def __init__(self):
+            self.puts = []
+
+        def put(self, state, i, keep):
+            self.puts.append((i, state))
+
+    def run(cb, repo, n_steps):
+        for step in range(1, n_steps + 1):
+            cb.training_step_end(step)  # the "state" is the 1-based step number
+        return np.array(repo.puts, np.int32).reshape(-1, 2)
+
+    cases = {
+        "sghmc_0": dict(n_epochs=4, n_training_steps=25, n_samples=7, n_thinning=5, burnin_length=40),
+        "sghmc_1": dict(n_epochs=3, n_training_steps=10, n_samples=30, n_thinning=1, burnin_length=0),
+        "csgld_0": dict(n_epochs=5, n_training_steps=20, n_samples=9, n_thinning=2, cycle_length=20, exploration_ratio=0.25),
+        "csgld_1": dict(n_epochs=2, n_training_steps=30, n_samples=6, n_thinning=3, cycle_length=15, exploration_ratio=0.6),
+    }
+    for tag, kw in cases.items():
+        repo = Repo()
+        cls = sg.SGHMCSamplingCallback if tag.startswith("sghmc") else cy.CyclicalSGLDSamplingCallback
+        cb = cls(trainer=Trainer(), state_repository=repo, keep_top_n_checkpoints=1, **kw)
+        put(f"callback/{tag}/stored", run(cb, repo, kw["n_epochs"] * kw["n_training_steps"]))
+        put(f"callback/{tag}/config", np.array([float(v) for v in kw.values()], np.float64))
+    # too few collectable samples: the constructor refuses
+    for tag, cls, kw in (("sghmc", sg.SGHMCSamplingCallback, dict(n_epochs=1, n_training_steps=10, n_samples=5, n_thinning=3,
+                                                                  burnin_length=4)),
+                         ("csgld", cy.CyclicalSGLDSamplingCallback, dict(n_epochs=1, n_training_steps=12, n_samples=4,
+                                                                         n_thinning=2, cycle_length=6, exploration_ratio=0.5))):
+        try:
+            cls(trainer=Trainer(), state_repository=Repo(), keep_top_n_checkpoints=1, **kw)
+            refused = 0
+        except ValueError:
+            refused = 1
+        put(f"callback/{tag}_refuses", np.int32(refused))
+
+
 def logging_off():
     import logging
 
@@ -719,6 +768,7 @@ def main():
     gen_conformal_regression()
     gen_calibration_loss()
     gen_output_calib_predictive()
+    gen_sampling_callbacks()
     path = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **OUT)
     print(f"wrote {path}: {len(OUT)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")

@@ -415,3 +415,49 @@ def test_output_calibration_predictive_maps():
         assert np.array_equal(smp, c[f"reg_{cal}/sample"])
         np.testing.assert_allclose(Oc.reg_output_entropy(c["outputs"], c["key"], 6, ltc), c[f"reg_{cal}/entropy"], rtol=5e-6, atol=2e-6)
         np.testing.assert_allclose(P.quantile_axis0(smp, [0.1, 0.9]), c[f"reg_{cal}/quantile"], rtol=1e-6, atol=1e-7)
+
+
+def test_sampling_callbacks_store_the_reference_steps():
+    """sghmc_callback.py / cyclical_sgld_callback.py / sgmcmc_sampling_callback.py: which 1-based training steps store
+    posterior sample i - the oracle's rules and the product's callback classes (host logic) against the reference's."""
+    from fortuna_b200.prob_model.posterior.sgmcmc.cyclical_sgld.cyclical_sgld_callback import CyclicalSGLDSamplingCallback
+    from fortuna_b200.prob_model.posterior.sgmcmc.sghmc.sghmc_callback import SGHMCSamplingCallback
+
+    class Repo:
+        def __init__(self):
+            self.puts = []
+
+        def put(self, state, i, keep):
+            self.puts.append((i, state))
+
+    names = {"sghmc": ("n_epochs", "n_training_steps", "n_samples", "n_thinning", "burnin_length"),
+             "csgld": ("n_epochs", "n_training_steps", "n_samples", "n_thinning", "cycle_length", "exploration_ratio")}
+    for tag in ("sghmc_0", "sghmc_1", "csgld_0", "csgld_1"):
+        kind = tag.split("_")[0]
+        kw = dict(zip(names[kind], REF[f"callback/{tag}/config"].tolist()))
+        kw = {k: (v if k == "exploration_ratio" else int(v)) for k, v in kw.items()}
+        want = REF[f"callback/{tag}/stored"]
+        n_steps = kw["n_epochs"] * kw["n_training_steps"]
+        # oracle
+        stored, count = [], 0
+        for step in range(1, n_steps + 1):
+            rule_kw = {k: v for k, v in kw.items() if k not in ("n_epochs", "n_training_steps")}
+            hit = S.sghmc_do_sample(step, count, **rule_kw) if kind == "sghmc" else S.cyclical_sgld_do_sample(step, count, **rule_kw)
+            if hit:
+                stored.append((count, step))
+                count += 1
+        assert np.array_equal(np.array(stored, np.int32).reshape(-1, 2), want), tag
+        # product callback classes
+        repo = Repo()
+        cls = SGHMCSamplingCallback if kind == "sghmc" else CyclicalSGLDSamplingCallback
+        cb = cls(trainer=None, state_repository=repo, keep_top_n_checkpoints=1, **kw)
+        for step in range(1, n_steps + 1):
+            cb.training_step_end(step)
+        assert np.array_equal(np.array(repo.puts, np.int32).reshape(-1, 2), want), tag
+    assert int(REF["callback/sghmc_refuses"]) == 1 and int(REF["callback/csgld_refuses"]) == 1
+    with pytest.raises(ValueError):
+        SGHMCSamplingCallback(n_epochs=1, n_training_steps=10, n_samples=5, n_thinning=3, burnin_length=4, trainer=None,
+                              state_repository=Repo(), keep_top_n_checkpoints=1)
+    with pytest.raises(ValueError):
+        CyclicalSGLDSamplingCallback(n_epochs=1, n_training_steps=12, n_samples=4, n_thinning=2, cycle_length=6,
+                                     exploration_ratio=0.5, trainer=None, state_repository=Repo(), keep_top_n_checkpoints=1)

@@ -6,10 +6,14 @@
 
 namespace fb200 {
 
-// Monotone float32 -> uint32 map (total order; -0 is canonicalised to +0 by the caller).
+// Monotone float32 -> uint32 map (total order; -0 is canonicalised to +0 by the caller).  Every NaN, whatever its
+// sign or payload, maps to the top value: lax.sort puts NaNs last, so a descending argsort has them first.  The
+// NaN case is explicit because ptxas rewrites the sign-bit arithmetic below as FADD -|x|, -0 - exact for numbers,
+// but a NaN leaves an FADD as 0x7FFFFFFF and would land between the negative and the positive values.
 __device__ __forceinline__ uint32_t f32_ordered(float f) {
   const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  const uint32_t o = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return (f != f) ? 0xFFFFFFFFu : o;
 }
 __device__ __forceinline__ float f32_unordered(uint32_t o) {
   const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;

@@ -444,7 +444,10 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
         kb = __shfl_sync(0xffffffffu, kb, src);
         kp = __shfl_sync(0xffffffffu, kp, src);
         const bool boundary_tie = !none && first > 0 && kp == kb;
-        if ((none ? (n_true == 0) : (n_true == C - first)) && !boundary_tie) {  // warp-uniform
+        // key 0 is a NaN probability: it ranks first, every score of the row is NaN and "<= pb" decides nothing -
+        // the general path below puts every class in (no validation score is above a NaN)
+        const bool nan_row = !none && kb == 0u;
+        if ((none ? (n_true == 0) : (n_true == C - first)) && !boundary_tie && !nan_row) {  // warp-uniform
           const float pb = f32_unordered(~kb);  // probability at the boundary rank
           uint8_t* mrow = a.cs_mask + (size_t)b * C;
           if (vec16 && (reinterpret_cast<uintptr_t>(mrow) & 3u) == 0) {

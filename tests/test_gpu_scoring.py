@@ -396,3 +396,74 @@ def test_sort_and_quantile_with_nan_scores(cuda):
         assert np.isnan(float(conformal_quantile(sc, 0.1)))
         got = ops.sort_f32_(torch.from_numpy(sc.copy()).to(cuda)).cpu().numpy()
         assert np.array_equal(got[:-1], np.sort(sc)[:-1]) and np.isnan(got[-1])
+
+
+@pytest.mark.parametrize("C", [10, 33, 130, 1000, 1024, 3000])
+def test_rows_with_some_nan_classes_sort_them_first(cuda, C):
+    """lax.sort puts NaNs last, so the descending order of adaptive_prediction.py:13,20 and
+    classification.py:471-483 starts with the NaN classes (larger class first) and every prefix sum after them is
+    NaN: the credible set is the single highest NaN class, all APS scores of the row are NaN.  Positive and
+    negative NaNs alike."""
+    from fortuna_b200 import ops
+
+    r = np.random.default_rng(C)
+    p = P.softmax((3 * r.standard_normal((12, C))).astype(np.float32))
+    neg_nan = np.array([0xFFC00000], dtype=np.uint32).view(np.float32)[0]
+    p[4, 3] = np.nan
+    p[5, 2] = np.nan
+    p[5, 7] = neg_nan
+    p[6, C - 1] = neg_nan
+    p[7, :] = np.nan
+    p[8, 0] = np.nan
+    p[8, C // 2] = np.inf
+    t = r.integers(0, C, p.shape[0]).astype(np.int32)
+    pt = torch.from_numpy(p).to(cuda)
+    with np.errstate(all="ignore"):
+        want_sets = P.cls_credible_set(p, 0.1)
+        want_perm = Sc.descending_perm(p)
+        want_all = Sc.aps_cumsums(p)
+        want_tgt = Sc.aps_score(p, t)
+    labels, size = ops.credible_sets(pt, 0.1)
+    lab, sz = labels.cpu().numpy(), size.cpu().numpy()
+    for i in range(p.shape[0]):
+        assert lab[i, : sz[i]].tolist() == want_sets[i], i
+    assert want_sets[4] == [3] and want_sets[5] == [7] and want_sets[6] == [C - 1]
+    allc, perm = ops.aps_scores(pt, None, want_perm=True)
+    assert np.array_equal(perm.cpu().numpy(), want_perm)
+    assert np.array_equal(allc.cpu().numpy(), want_all, equal_nan=True)
+    assert np.array_equal(ops.aps_scores(pt, None).cpu().numpy(), want_all, equal_nan=True)
+    assert np.array_equal(ops.aps_scores(pt, torch.from_numpy(t).to(cuda)).cpu().numpy(), want_tgt, equal_nan=True)
+
+
+@pytest.mark.parametrize("C", [10, 130, 1000, 1024])
+@pytest.mark.parametrize("error", [0.05, 0.3])
+def test_conformal_sets_of_rows_with_nan_scores_hold_every_class(cuda, C, error):
+    """base.py:51-53 counts the validation scores ABOVE a test score; no number is above a NaN, so the count is 0 and
+    every class of a row whose APS scores are NaN is in the set.  Three routes: scores then sets, the fused sort
+    kernel, the select kernel (which hands such rows to the sort)."""
+    from fortuna_b200 import ops
+
+    n_val = 300
+    vp = _probs(n_val, C, seed=2)
+    vt = np.random.default_rng(3).integers(0, C, n_val).astype(np.int32)
+    tp = _probs(40, C, seed=4)
+    tp[3, 1] = np.nan
+    tp[17, C - 1] = np.array([0xFFC00000], dtype=np.uint32).view(np.float32)[0]
+    tp[18, :] = np.nan
+    tp[30, 0] = np.inf
+    with np.errstate(all="ignore"):
+        val_scores, test_scores = Sc.get_scores(vp, vt, tp, "aps")
+        conds = Sc.conformal_conds_literal(val_scores, test_scores, error)
+    assert conds[3].all() and conds[17].all() and conds[18].all()
+    sizes = conds.sum(1).astype(np.int32)
+    vs = ops.sort_f32_(torch.from_numpy(val_scores.copy()).to(cuda))
+    thr = Sc.conformal_threshold(n_val, error)
+    tpt = torch.from_numpy(tp).to(cuda)
+    m1, s1 = ops.conformal_sets(vs, ops.aps_scores(tpt, None), thr)
+    m2, s2 = ops.aps_conformal_sets(tpt, vs, thr)
+    m3, s3, sc = ops.aps_conformal_sets(tpt, vs, thr, want_scores=True)
+    assert np.array_equal(sc.cpu().numpy(), test_scores, equal_nan=True)
+    for route, (m, s) in enumerate(((m1, s1), (m2, s2), (m3, s3))):
+        bad = np.argwhere(m.cpu().numpy().astype(bool) != conds)
+        assert bad.size == 0, (route, bad[:8].tolist())
+        assert np.array_equal(s.cpu().numpy(), sizes), route

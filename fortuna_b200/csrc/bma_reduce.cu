@@ -489,7 +489,10 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const
   const int S = a.S, B = a.B, C = a.C;
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  for (int s = tid; s < S && s < 1024; s += blockDim.x) s_lse[s] = lse[(size_t)s * B + b];
+  // jax.nn.softmax subtracts the row maximum as it is: a row holding +inf is NaN in EVERY class.  Only such a row
+  // has lse = +inf (the log-probabilities keep logsumexp's convention and read the workspace as it is).
+  auto softmax_lse = [](float v) { return v == CUDART_INF_F ? CUDART_NAN_F : v; };
+  for (int s = tid; s < S && s < 1024; s += blockDim.x) s_lse[s] = softmax_lse(lse[(size_t)s * B + b]);
   __syncthreads();
   const T* base = reinterpret_cast<const T*>(a.logits) + (size_t)b * C;
   const size_t sstride = (size_t)B * C;
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const
     for (int s = 0; s < S; ++s) {
       float t[1];
       RowLoad<T, 1>::load(base + (size_t)s * sstride + c, t);
-      const float l = t[0] * scale - (s < 1024 ? s_lse[s] : lse[(size_t)s * B + b]);  // log p
+      const float l = t[0] * scale - (s < 1024 ? s_lse[s] : softmax_lse(lse[(size_t)s * B + b]));  // log p
       const float p = __expf(l);
       sp += p;
       sp2 = fmaf(p, p, sp2);
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(256) wide_reduce_kernel(const ClsArgs a, const
     if (a.out.aleatoric_entropy) a.out.aleatoric_entropy[b] = alea;
     if (a.out.epistemic_entropy) a.out.epistemic_entropy[b] = ent - alea;
     if (a.out.mode) a.out.mode[b] = bc == 0x7FFFFFFF ? 0 : bc;
-    if (a.out.confidence) a.out.confidence[b] = bv;
+    if (a.out.confidence) a.out.confidence[b] = bc == 0x7FFFFFFF ? CUDART_NAN_F : bv;  // jnp.max of a NaN row
     if (a.out.brier_terms) a.out.brier_terms[b] = (y >= 0 && y < C) ? (sq - 2.0f * my) + 1.0f : sq;
   }
 }

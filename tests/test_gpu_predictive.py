@@ -359,7 +359,7 @@ def test_last_layer_kmajor_f32_kernel(cuda, S, B, D, C, gather, out_bf16):
     np.testing.assert_allclose(new.float().cpu().numpy(), want, **tol)
 
 
-@pytest.mark.parametrize("C", [10, 130, 1000, 1024])
+@pytest.mark.parametrize("C", [10, 130, 1000, 1024, 1500, 4096])
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 def test_reduction_special_values_follow_the_reference(cuda, C, dtype):
     """Rows that hold +inf, -inf or NaN, rows far below zero, rows whose lanes differ by hundreds of units, constant rows

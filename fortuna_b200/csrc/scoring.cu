@@ -33,10 +33,30 @@ struct RowSortArgs {
   int32_t* cs_sizes;       // optional [B]
   const float* cs_val_sorted;
   int cs_q_index;          // n_val - 1 - K
+  int cs_n_val;
   int cs_all_true, cs_all_false;
   int only_flagged;        // all-class key-only kernel: visit only the rows whose cs_sizes entry is -1 (left by the
                            // select kernel below for the rows it could not decide)
 };
+
+// The validation score the rank count compares against: count(val > t) <= K  <=>  !(t < val_sorted[n' - 1 - K]), n' the
+// number of validation scores that are numbers - a NaN is above nothing (base.py:51-53) and fb200_sort_f32 leaves the
+// NaNs at the end like lax.sort.  Without NaNs (the last element says so; its load is independent of the boundary's)
+// this is val_sorted[q_index].  K >= n' puts every class in: -inf does that through the same comparison.
+__device__ __forceinline__ float conformal_boundary_score(const float* __restrict__ v, int n, int q_index) {
+  const float last = __ldg(v + n - 1);
+  const float q = __ldg(v + q_index);
+  if (last == last) return q;
+  int lo = 0, hi = n - 1;  // first NaN
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const float x = __ldg(v + mid);
+    if (x != x) hi = mid;
+    else lo = mid + 1;
+  }
+  const int idx = q_index - (n - lo);
+  return idx < 0 ? -CUDART_INF_F : __ldg(v + idx);
+}
 
 __global__ void __launch_bounds__(256) row_sort_cumsum_kernel(const RowSortArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -416,7 +436,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
       // ten-probe rank lookup.  Rows with a tie across the boundary or a non-monotone boundary take the general path.
       bool done = false;
       if (a.cs_mask && !a.scores && !a.cs_all_true && !a.cs_all_false) {
-        const float q = __ldg(a.cs_val_sorted + a.cs_q_index);
+        const float q = conformal_boundary_score(a.cs_val_sorted, a.cs_n_val, a.cs_q_index);
         int n_true = 0, first = 0x7FFFFFFF;
 #pragma unroll
         for (int r = NR - 1; r >= 0; --r) {
@@ -527,7 +547,9 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
       if (a.cs_mask) {
         // conformal sets straight from the scores (conformal/classification/base.py:45-64, see conformal_sets_kernel):
         // the [B,C] score matrix need not be written and read back
-        const float q = (a.cs_all_true || a.cs_all_false) ? 0.0f : __ldg(a.cs_val_sorted + a.cs_q_index);
+        const float q = (a.cs_all_true || a.cs_all_false)
+                            ? 0.0f
+                            : conformal_boundary_score(a.cs_val_sorted, a.cs_n_val, a.cs_q_index);
         float* orow = a.scores ? a.scores + (size_t)b * C : nullptr;
         uint8_t* mrow = a.cs_mask + (size_t)b * C;
         int cnt = 0;
@@ -664,7 +686,7 @@ __global__ void __launch_bounds__(kSelWarps * 32, 5) aps_sets_select_kernel(cons
   float* rows = reinterpret_cast<float*>(smem_raw) + (size_t)warp_in_cta * kWarpWords;
   uint32_t* scratch = reinterpret_cast<uint32_t*>(rows + 2 * N);
   const int nwarps = gridDim.x * kSelWarps;
-  const float q = __ldg(a.cs_val_sorted + a.cs_q_index);
+  const float q = conformal_boundary_score(a.cs_val_sorted, a.cs_n_val, a.cs_q_index);
   const float qm = q * 1.00002f;  // the counting pass sums in another order than the scan: aim a little above q
   float xs = 0.0f;      // log2 of the threshold / row maximum ratio the warp tries first on its next row
   bool primed = false;  // ... once a row has told it where to look
@@ -1050,7 +1072,7 @@ __global__ void __launch_bounds__(256) conformal_sets_kernel(const float* __rest
   const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
   const bool all_true = K >= n_val;
   const bool all_false = K < 0;
-  const float q = (all_true || all_false) ? 0.0f : val_sorted[n_val - 1 - K];
+  const float q = (all_true || all_false) ? 0.0f : conformal_boundary_score(val_sorted, n_val, n_val - 1 - K);
   for (int b = warp; b < B; b += nwarps) {
     const float* row = test + (size_t)b * C;
     uint8_t* mrow = mask + (size_t)b * C;
@@ -1508,6 +1530,7 @@ extern "C" int fb200_aps_conformal_sets(const float* probs, int B, int C, const 
   a.cs_mask = mask;
   a.cs_sizes = sizes;
   a.cs_val_sorted = val_scores_sorted;
+  a.cs_n_val = n_val;
   a.cs_all_true = K >= n_val;
   a.cs_all_false = K < 0;
   a.cs_q_index = (a.cs_all_true || a.cs_all_false) ? 0 : (int)(n_val - 1 - K);

@@ -109,10 +109,12 @@ def conformal_conds_literal(val_scores, test_scores, error):
 
 def conformal_conds(val_scores, test_scores, error):
     """Same booleans via sort + searchsorted: count(val > t) = n - upper_bound(sorted, t)."""
-    v = np.sort(_f32(val_scores))
+    v = np.sort(_f32(val_scores))  # NaNs last
     t = _f32(test_scores)
+    n = len(v)
+    v = v[: n - int(np.isnan(v).sum())]  # a NaN validation score is above nothing; it still counts in the threshold
     counts = (len(v) - np.searchsorted(v, t, side="right")).astype(np.int32)
-    return counts.astype(F32) < conformal_threshold(len(v), error)
+    return counts.astype(F32) < conformal_threshold(n, error)
 
 
 def conformal_sets(val_scores, test_scores, error):

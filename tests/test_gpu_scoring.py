@@ -437,10 +437,13 @@ def test_rows_with_some_nan_classes_sort_them_first(cuda, C):
 
 @pytest.mark.parametrize("C", [10, 130, 1000, 1024])
 @pytest.mark.parametrize("error", [0.05, 0.3])
-def test_conformal_sets_of_rows_with_nan_scores_hold_every_class(cuda, C, error):
+@pytest.mark.parametrize("n_nan_val", [0, 7, 120, 300])
+def test_conformal_sets_of_rows_with_nan_scores_hold_every_class(cuda, C, error, n_nan_val):
     """base.py:51-53 counts the validation scores ABOVE a test score; no number is above a NaN, so the count is 0 and
     every class of a row whose APS scores are NaN is in the set.  Three routes: scores then sets, the fused sort
-    kernel, the select kernel (which hands such rows to the sort)."""
+    kernel, the select kernel (which hands such rows to the sort).  NaN VALIDATION scores are above nothing either, yet
+    count in the threshold (1 - error) (n + 1): with n_nan_val of them the boundary moves down the sorted vector, and
+    past its start every class is in."""
     from fortuna_b200 import ops
 
     n_val = 300
@@ -453,8 +456,11 @@ def test_conformal_sets_of_rows_with_nan_scores_hold_every_class(cuda, C, error)
     tp[30, 0] = np.inf
     with np.errstate(all="ignore"):
         val_scores, test_scores = Sc.get_scores(vp, vt, tp, "aps")
+        val_scores[np.random.default_rng(5).permutation(n_val)[:n_nan_val]] = np.nan
         conds = Sc.conformal_conds_literal(val_scores, test_scores, error)
+        assert np.array_equal(conds, Sc.conformal_conds(val_scores, test_scores, error))
     assert conds[3].all() and conds[17].all() and conds[18].all()
+    assert n_nan_val < 120 or conds.all()
     sizes = conds.sum(1).astype(np.int32)
     vs = ops.sort_f32_(torch.from_numpy(val_scores.copy()).to(cuda))
     thr = Sc.conformal_threshold(n_val, error)

@@ -473,3 +473,36 @@ def test_conformal_sets_of_rows_with_nan_scores_hold_every_class(cuda, C, error,
         bad = np.argwhere(m.cpu().numpy().astype(bool) != conds)
         assert bad.size == 0, (route, bad[:8].tolist())
         assert np.array_equal(s.cpu().numpy(), sizes), route
+
+
+@pytest.mark.parametrize("error", [0.05, 0.3])
+def test_conformal_bayes_special_values(cuda, error):
+    """Weights of exactly zero (log-probability -inf) in some or in all posterior samples (0 / 0 = NaN: nothing compares
+    <= a NaN, rank 1), a NaN weight, training points impossible under one or under every sample, a NaN training
+    log-probability: counts, region and the NaN pattern of the ESS as predictive/classification.py:557-617 gives them."""
+    from fortuna_b200 import ops
+
+    S, n_train, n_test, C = 30, 500, 12, 5
+    ell, lsm = _cb_inputs(S, n_train, n_test, C, seed=1)
+    lsm[:7, 1, 2] = -np.inf
+    lsm[:, 2, 3] = -np.inf
+    lsm[4, 3, 1] = np.nan
+    ell[5, 17] = -np.inf
+    ell[:, 18] = -np.inf
+    ell[6, 19] = np.nan
+    out = ops.conformal_bayes_sets(torch.from_numpy(ell).to(cuda), torch.from_numpy(lsm).to(cuda), error,
+                                   want_counts=True, want_ess=True)
+    with np.errstate(all="ignore"):
+        cnt, p_train, p_test = Sc.conformal_bayes_counts(ell, lsm, dtype=np.float64)
+        ess = Sc.conformal_bayes_ess(lsm, dtype=np.float64)
+        amb = (np.abs(p_train - p_test[..., None]) <= 4e-6 * p_test[..., None]).sum(axis=2)
+    got = out["rank_counts"].cpu().numpy()
+    assert np.all(np.abs(got - cnt) <= amb)
+    assert got[2, 3] == 0 and got[3, 1] == 0 and cnt[2, 3] == 0 and cnt[3, 1] == 0
+    assert got[0, 0] == cnt[0, 0] == n_train - 1  # the NaN training point is never counted
+    region = out["region"].cpu().numpy().astype(bool)
+    assert np.array_equal(region, (got + 1).astype(np.float32) > np.float32(error * (n_train + 1)))
+    e = out["ess"].cpu().numpy()
+    assert np.array_equal(np.isnan(e), np.isnan(ess)) and np.isnan(e[2, 3]) and np.isnan(e[3, 1])
+    ok = ~np.isnan(ess)
+    np.testing.assert_allclose(e[ok], ess[ok], rtol=2e-5)

@@ -21,7 +21,8 @@ constexpr int MAXCOV_MAX_TAUS = 4096;
 __device__ __forceinline__ bool maxcov_pred(float p, float tau, int side, float thr) {
   if (side == 0) {
     const float ind = p > 0.5f ? 1.0f : 0.0f;
-    const float c = fminf(__fmul_rn(__fadd_rn(1.0f, __fmul_rn(__fadd_rn(tau, -1.0f), ind)), p), 1.0f);
+    const float u = __fmul_rn(__fadd_rn(1.0f, __fmul_rn(__fadd_rn(tau, -1.0f), ind)), p);
+    const float c = (u != u) ? u : fminf(u, 1.0f);  // jnp.minimum keeps a NaN: a NaN probability predicts nothing
     return c >= thr;
   }
   const float ind = p < 0.5f ? 1.0f : 0.0f;

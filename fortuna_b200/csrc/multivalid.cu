@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) mv_patch_kernel(float* __restrict__ value
     if (in) {
       const float y = multiplicative ? __fmul_rn(x, __fsub_rn(1.0f, __fmul_rn(eta, __fsub_rn(1.0f, patch))))
                                      : __fadd_rn(x, __fmul_rn(eta, patch));
-      vrow[col] = fminf(fmaxf(y, 0.0f), 1.0f);
+      vrow[col] = (y != y) ? y : fminf(fmaxf(y, 0.0f), 1.0f);  // jnp.clip keeps a NaN
       ++mine;
     }
   }

@@ -543,7 +543,8 @@ __global__ void __launch_bounds__(256) grad_sq_partials_kernel(const float* __re
 
 __global__ void grad_clip_finish_kernel(const double* __restrict__ sum_sq, float max_norm, float* __restrict__ mult) {
   const float norm = sqrtf((float)sum_sq[0]);
-  mult[0] = fminf(1.0f, max_norm / (1e-7f + norm));
+  const float r = max_norm / (1e-7f + norm);
+  mult[0] = (r != r) ? r : fminf(1.0f, r);  // jnp.minimum keeps a NaN (a NaN gradient makes the whole step NaN)
 }
 
 __global__ void __launch_bounds__(256) bank_put_kernel(float* __restrict__ dst, const float* __restrict__ src,

@@ -77,3 +77,26 @@ def test_reference_case_and_errors(cuda):
         with pytest.raises(ValueError):
             cal.calibrate(targets=y, probs=np.zeros(30, np.float32), true_positive_precision_threshold=bad[0],
                           true_negative_precision_threshold=bad[1])
+
+
+def test_counts_with_nan_probabilities(cuda):
+    """A NaN probability satisfies neither p > 0.5 nor the precision comparison (jnp.minimum keeps the NaN, NaN >= t is
+    False): it is in no count on either side."""
+    from fortuna_b200 import ops
+
+    p, y = _data(5000, 11)
+    p[::7] = np.nan
+    taus_pos, taus_neg = M.tau_grids(0.8, 0.7, 33)
+    pd, yd = torch.from_numpy(p).to(cuda), torch.from_numpy(y).to(cuda)
+    for side, taus, t in ((0, taus_pos, 0.8), (1, taus_neg, 1 - 0.7)):
+        c, l = ops.maxcov_counts(pd, yd, torch.from_numpy(taus).to(cuda), side, t)
+        ind = (p > 0.5) if side == 0 else (p < 0.5)
+        want_c, want_l = [], []
+        for tau in taus:
+            calib = ((np.float32(1) + (tau - np.float32(1)) * ind.astype(np.float32)) * p).astype(np.float32)
+            with np.errstate(invalid="ignore"):
+                b = (np.minimum(calib, np.float32(1)) >= np.float32(t)) if side == 0 else (calib <= np.float32(t))
+            want_c.append(int(b.sum()))
+            want_l.append(int((y * b).sum() if side == 0 else ((1 - y) * b).sum()))
+        assert c.cpu().tolist() == want_c and l.cpu().tolist() == want_l
+        assert max(want_c) <= int((~np.isnan(p)).sum())

@@ -282,6 +282,30 @@ def test_gradient_clipping_fused_into_the_step(cuda, precond, joint):
             _assert_tree_close(state.momentum.to_numpy_tree(), o_state.momentum, f"momentum step {step}", floor=2e-7)
 
 
+def test_a_nan_gradient_makes_the_clipped_step_nan_everywhere(cuda):
+    """utils/training.py:18: jnp.minimum(1, max_norm / (1e-7 + norm)) keeps a NaN norm, so ONE NaN gradient entry turns
+    every gradient - and with it every parameter and momentum - into NaN (fminf would have answered 1 and confined the
+    NaN to its own entry)."""
+    from fortuna_b200 import ops
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_preconditioner as pc
+    from fortuna_b200.prob_model.posterior.sgmcmc import sgmcmc_step_schedule as sched
+    from fortuna_b200.prob_model.posterior.sgmcmc.sghmc.sghmc_integrator import sghmc_integrator
+    from fortuna_b200.utils.flat_tree import FlatTree
+
+    params_np = trees.ragged_tree(4, scale=0.3)
+    g_np = _grad_tree(params_np, 40)
+    first = osamp.tree_flatten(g_np)[0][1]
+    first.reshape(-1)[0] = np.nan
+    g_clip, mult = osamp.clip_gradients_by_norm(g_np, 0.05)
+    assert np.isnan(mult) and all(np.isnan(leaf).all() for _, leaf in osamp.tree_flatten(g_clip))
+    tx = sghmc_integrator(0.02, None, ops.PRNGKey(2, cuda), sched.constant_schedule(1e-3), pc.identity_preconditioner())
+    params = FlatTree.from_tree(params_np, device=cuda)
+    state = tx.init(params)
+    params, state = tx.apply(params, FlatTree.from_tree(g_np, device=cuda), state, max_grad_norm=0.05)
+    assert all(np.isnan(leaf).all() for _, leaf in osamp.tree_flatten(params.to_numpy_tree()))
+    assert all(np.isnan(leaf).all() for _, leaf in osamp.tree_flatten(state.momentum.to_numpy_tree()))
+
+
 def test_bf16_gradient_input(cuda):
     """the step reads a bfloat16 gradient vector (18 instead of 20 B/param) - identical to the float32 step
     on the same values (bf16 -> f32 is exact), for the vector path and the ragged leaves, with clipping on top."""

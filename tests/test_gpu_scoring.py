@@ -506,3 +506,25 @@ def test_conformal_bayes_special_values(cuda, error):
     assert np.array_equal(np.isnan(e), np.isnan(ess)) and np.isnan(e[2, 3]) and np.isnan(e[3, 1])
     ok = ~np.isnan(ess)
     np.testing.assert_allclose(e[ok], ess[ok], rtol=2e-5)
+
+
+@pytest.mark.parametrize("n_data", [100, 1000, 5000])
+def test_ece_bin_edges(cuda, n_data):
+    """Confidences exactly ON the bin thresholds, one ulp either side of them, 0, 1, just above 1 (a rounded sum) and
+    below 0: the bin is the one metric/classification.py's comparisons pick (oracle: bit-exact indices and counts)."""
+    from fortuna_b200 import ops
+
+    thr = Sc.ece_thresholds(n_data)
+    edge = np.concatenate([thr, np.nextafter(thr, np.float32(2)), np.nextafter(thr, np.float32(-2)),
+                           np.array([0.0, 1.0, 1.0000001, 1.5, -0.1, -0.0], dtype=np.float32)]).astype(np.float32)
+    r = np.random.default_rng(n_data)
+    p = np.concatenate([edge, r.random(n_data - edge.size).astype(np.float32)]) if n_data > edge.size else edge[:n_data]
+    p = p[r.permutation(p.size)]
+    preds = r.integers(0, 2, p.size).astype(np.int32)
+    t = r.integers(0, 2, p.size).astype(np.int32)
+    thr = Sc.ece_thresholds(p.size)
+    o = ops.ece_bins(torch.from_numpy(p).to(cuda), torch.from_numpy(t).to(cuda), torch.from_numpy(thr).to(cuda),
+                     preds=torch.from_numpy(preds).to(cuda), want_bin_idx=True)
+    counts, confs, accs, idx = Sc.compute_counts_confs_accs(preds, p, t)
+    assert np.array_equal(o["bin_idx"].cpu().numpy(), idx)
+    assert np.array_equal(o["counts"].cpu().numpy(), counts)

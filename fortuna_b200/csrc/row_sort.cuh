@@ -15,6 +15,12 @@ __device__ __forceinline__ uint32_t f32_ordered(float f) {
   const uint32_t o = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
   return (f != f) ? 0xFFFFFFFFu : o;
 }
+// jnp indexing with a traced index (probs[target], inv_perm[target]): a negative index counts from the end, then the
+// gather clamps to the array (jax "sharp bits": jnp.arange(10)[11] == 9).  No label reads outside its row.
+__device__ __forceinline__ int jax_gather_index(int y, int n) {
+  y = y < 0 ? y + n : y;
+  return min(max(y, 0), n - 1);
+}
 __device__ __forceinline__ float f32_unordered(uint32_t o) {
   const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
   return __uint_as_float(u);

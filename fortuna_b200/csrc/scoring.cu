@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) row_sort_cumsum_kernel(const RowSortArgs 
     for (int i = threadIdx.x; i < C; i += blockDim.x) cum[i] = tree[i];
     __syncthreads();
     if (threadIdx.x == 0) {
-      const int y = a.targets ? a.targets[b] : -1;
+      const int y = a.targets ? jax_gather_index(a.targets[b], C) : -1;
       float ys = CUDART_NAN_F;
       int first = -1;
       for (int r = 0; r < C; ++r) {
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kSortWarps * 32) row_sort_warp_kernel(const Ro
     }
     warp_row_tree_prefix<NR>(x, lane);
     if (MODE == 1) {
-      const int y = a.targets ? a.targets[b] : -1;
+      const int y = a.targets ? jax_gather_index(a.targets[b], C) : -1;
       float ys = CUDART_NAN_F;
       bool mine = false;
 #pragma unroll
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(kSortWarps * 32, 2) row_sort32_warp_kernel(con
     int tpos = -1;
     if (MODE == 1) {
       // rank of the target class, counted on the unsorted row
-      const int y = a.targets ? a.targets[b] : -1;
+      const int y = a.targets ? jax_gather_index(a.targets[b], C) : -1;
       if ((unsigned)y < (unsigned)C) {
         const uint32_t ky = ~f32_ordered(srow[y] + 0.0f);
         int cnt = 0;
@@ -987,7 +987,7 @@ __global__ void __launch_bounds__(256) simple_scores_kernel(const float* __restr
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     if (targets) {
-      const int y = targets[i];
+      const int y = jax_gather_index(targets[i], C);
       scores[i] = 1.0f - probs[i * C + y];
     } else {
       scores[i] = 1.0f - probs[i];

@@ -69,17 +69,24 @@ def aps_cumsums(probs):
     return out
 
 
+def gather_index(targets, n):
+    """jnp indexing with a traced index: negative indices count from the end, then the gather clamps to the array
+    (jax "sharp bits": ``jnp.arange(10)[11] == 9``)."""
+    t = np.asarray(targets).astype(np.int64)
+    return np.clip(np.where(t < 0, t + n, t), 0, n - 1)
+
+
 def aps_score(probs, targets):
     """adaptive_prediction.score_fn: cumsum(probs[perm])[inv_perm[target]]."""
     allc = aps_cumsums(probs)
-    t = np.asarray(targets).astype(np.int64)
+    t = gather_index(targets, allc.shape[1])
     return allc[np.arange(allc.shape[0]), t]
 
 
 def simple_score(probs, targets):
     """simple_prediction.score_fn: 1 - probs[target]."""
     probs = _f32(probs)
-    t = np.asarray(targets).astype(np.int64)
+    t = gather_index(targets, probs.shape[1])
     return (F32(1) - probs[np.arange(probs.shape[0]), t]).astype(F32)
 
 

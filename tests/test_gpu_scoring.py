@@ -528,3 +528,18 @@ def test_ece_bin_edges(cuda, n_data):
     counts, confs, accs, idx = Sc.compute_counts_confs_accs(preds, p, t)
     assert np.array_equal(o["bin_idx"].cpu().numpy(), idx)
     assert np.array_equal(o["counts"].cpu().numpy(), counts)
+
+
+@pytest.mark.parametrize("C", [10, 130, 1000, 3000])
+def test_scores_of_labels_outside_the_row_follow_jax_indexing(cuda, C):
+    """probs[target] / inv_perm[target] with a traced index: a negative label counts from the end and the gather clamps
+    to the row (jnp.arange(10)[11] == 9) - the kernels used to answer NaN (APS) or read outside the row (simple)."""
+    from fortuna_b200 import ops
+
+    p = _probs(64, C, seed=C)
+    t = np.random.default_rng(1).integers(0, C, 64).astype(np.int32)
+    t[:8] = [-1, -C, -C - 5, C, C + 7, 2**31 - 1, -(2**31), C - 1]
+    pt, tt = torch.from_numpy(p).to(cuda), torch.from_numpy(t).to(cuda)
+    assert np.array_equal(ops.aps_scores(pt, tt).cpu().numpy(), Sc.aps_score(p, t))
+    assert np.array_equal(ops.simple_scores(pt, tt).cpu().numpy(), Sc.simple_score(p, t))
+    assert Sc.gather_index(t, C)[:8].tolist() == [C - 1, 0, 0, C - 1, C - 1, C - 1, 0, C - 1]
